@@ -1,0 +1,588 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes front-end of oracle/_build/liblle_oracle.so.
+
+Exposes the oracle behind the same Python surface as the reference's ``lle`` module
+(``World``, ``WorldState``, ``Action``, ``EventType``, ``WorldEvent``, ``LLE``; reference:
+python/lle/world/__init__.pyi, src/bindings/world/pyworld.rs:144-626) so that the reference's
+known-answer tests can be transcribed 1:1 (tests/kat_*.py), plus ``OracleVec``: N lock-stepped
+environments whose output arrays have the layout of the device buffers of ``lle_b200``.
+
+Nothing under ``lle_b200/`` may import this module.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liblle_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile (g++ only, seconds)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "lle_oracle.hpp", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.lleo_last_error.restype = C.c_char_p
+        for name in ("lleo_world_new", "lleo_env_new", "lleo_vec_new"):
+            getattr(L, name).restype = C.c_void_p
+        L.lleo_vec_rollout.restype = C.c_double
+        L.lleo_vec_step_count.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+# ------------------------------------------------------------------ value types
+class Action(enum.IntEnum):
+    """src/action.rs:9-15."""
+
+    NORTH = 0
+    SOUTH = 1
+    EAST = 2
+    WEST = 3
+    STAY = 4
+
+    @property
+    def delta(self):
+        return {0: (-1, 0), 1: (1, 0), 2: (0, 1), 3: (0, -1), 4: (0, 0)}[int(self)]
+
+
+class EventType(enum.IntEnum):
+    """src/bindings/world/pyevent.rs:9-17."""
+
+    AGENT_EXIT = 0
+    GEM_COLLECTED = 1
+    AGENT_DIED = 2
+
+
+@dataclass(frozen=True)
+class WorldEvent:
+    event_type: EventType
+    agent_id: int
+
+
+class WorldState:
+    """src/bindings/world/pyworld_state.rs:53-132."""
+
+    def __init__(self, agents_positions, gems_collected, agents_alive=None):
+        self.agents_positions = [tuple(int(x) for x in p) for p in agents_positions]
+        self.gems_collected = [bool(g) for g in gems_collected]
+        self.agents_alive = [True] * len(self.agents_positions) if agents_alive is None else [bool(a) for a in agents_alive]
+
+    def as_array(self) -> np.ndarray:
+        out = []
+        for i, j in self.agents_positions:
+            out += [float(i), float(j)]
+        out += [1.0 if g else 0.0 for g in self.gems_collected]
+        out += [1.0 if a else 0.0 for a in self.agents_alive]
+        return np.array(out, dtype=np.float32)
+
+    @staticmethod
+    def from_array(array, n_agents: int, n_gems: int) -> "WorldState":
+        array = list(array)
+        if len(array) != n_agents * 3 + n_gems:
+            raise ValueError(f"The array must have a length of {n_agents * 3 + n_gems}.")
+        pos = [(int(array[2 * i]), int(array[2 * i + 1])) for i in range(n_agents)]
+        gems = [array[2 * n_agents + i] == 1.0 for i in range(n_gems)]
+        alive = [array[2 * n_agents + n_gems + i] == 1.0 for i in range(n_agents)]
+        return WorldState(pos, gems, alive)
+
+    def _key(self):
+        return (tuple(self.agents_positions), tuple(self.gems_collected), tuple(self.agents_alive))
+
+    def __eq__(self, other):
+        return isinstance(other, WorldState) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return f"WorldState({self.agents_positions}, {self.gems_collected}, {self.agents_alive})"
+
+
+# ------------------------------------------------------------------ exceptions (src/bindings/pyexceptions.rs:43-183)
+class InvalidWorldStateError(ValueError):
+    pass
+
+
+class InvalidActionError(ValueError):
+    pass
+
+
+class ParsingError(ValueError):
+    pass
+
+
+class InvalidLevelError(ValueError):
+    pass
+
+
+_PARSE_KINDS = range(1, 100)
+_RT = dict(InvalidAction=101, InvalidNumberOfGems=102, InvalidNumberOfAgents=103, InvalidAgentPosition=104,
+           OutOfWorldPosition=105, InvalidNumberOfActions=106, InvalidWorldState=107, TileNotWalkable=108, Panic=109)
+
+
+class RustPanic(RuntimeError):
+    """A code path on which the reference engine would panic."""
+
+
+def _raise(status: int):
+    msg = lib().lleo_last_error().decode()
+    if status in _PARSE_KINDS:
+        raise ParsingError(msg)
+    if status == _RT["InvalidAction"]:
+        raise InvalidActionError(msg)
+    if status in (_RT["InvalidNumberOfGems"], _RT["InvalidNumberOfAgents"], _RT["InvalidAgentPosition"],
+                  _RT["InvalidWorldState"]):
+        raise InvalidWorldStateError(msg)
+    if status == _RT["OutOfWorldPosition"] or status == 201:
+        raise IndexError(msg)
+    if status in (_RT["InvalidNumberOfActions"], 202):
+        raise ValueError(msg)
+    if status == _RT["Panic"]:
+        raise RustPanic(msg)
+    raise RuntimeError(f"oracle error {status}: {msg}")
+
+
+def _check(status: int):
+    if status != 0:
+        _raise(status)
+
+
+# ------------------------------------------------------------------ levels
+def level_text(n: int) -> str:
+    """The six built-in maps, committed as fixtures under tests/golden/levels/ (copied verbatim from
+    the reference's resources/levels/lvl1..6 by tests/golden/make_fixtures.py)."""
+    if not 1 <= n <= 6:
+        raise InvalidLevelError(f"InvalidLevel {{ asked: {n}, min: 1, max: 6 }}")
+    path = os.path.join(os.path.dirname(_HERE), "tests", "golden", "levels", f"lvl{n}")
+    with open(path) as f:
+        return f.read()
+
+
+# ------------------------------------------------------------------ World
+@dataclass(frozen=True)
+class Agent:
+    num: int
+    is_dead: bool
+    has_arrived: bool
+
+    @property
+    def is_alive(self):
+        return not self.is_dead
+
+
+@dataclass(frozen=True)
+class Gem:
+    pos: tuple
+    is_collected: bool
+
+
+class Direction(enum.IntEnum):
+    NORTH = 0
+    EAST = 1
+    SOUTH = 2
+    WEST = 3
+
+
+@dataclass(frozen=True)
+class Laser:
+    pos: tuple
+    laser_id: int
+    agent_id: int
+    direction: Direction
+    is_on: bool
+    is_enabled: bool
+
+    @property
+    def is_off(self):
+        return not self.is_on
+
+
+class LaserSource:
+    def __init__(self, world: "World", idx: int, rec):
+        self._world, self._idx = world, idx
+        self.pos = (int(rec[0]), int(rec[1]))
+        self.agent_id = int(rec[2])
+        self.direction = Direction(int(rec[3]))
+        self.is_enabled = bool(rec[4])
+        self.laser_id = int(rec[5])
+        self.beam_len = int(rec[6])
+
+    def disable(self):
+        lib().lleo_world_source_set_enabled(self._world._h, self._idx, 0)
+        self.is_enabled = False
+
+    def enable(self):
+        lib().lleo_world_source_set_enabled(self._world._h, self._idx, 1)
+        self.is_enabled = True
+
+    def set_colour(self, colour: int):
+        # src/bindings/tiles/pylaser_source.rs:107-142 (validation of the python setter)
+        if colour < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        w = self._world
+        if colour >= w.n_agents:
+            raise ValueError("Agent ID is greater than the number of agents")
+        lib().lleo_world_source_set_agent_id(w._h, self._idx, colour)
+        cells = {l.pos for l in w.lasers if l.laser_id == self.laser_id}
+        for start_agent, starts in enumerate(w.random_start_pos):
+            if start_agent != colour and cells & set(starts):
+                raise ValueError(f"Laser source cannot be changed to agent ID {colour}")
+        self.agent_id = colour
+
+
+class World:
+    """Single oracle world behind the reference's ``lle.World`` surface."""
+
+    def __init__(self, map_str: str):
+        st = C.c_int(0)
+        self._h = C.c_void_p(lib().lleo_world_new(map_str.encode(), C.byref(st)))
+        _check(st.value)
+        self.map_str = map_str
+        d = (C.c_int * 8)()
+        lib().lleo_world_dims(self._h, d)
+        self.height, self.width, self.n_agents, self.n_gems, self.n_sources = d[0], d[1], d[2], d[3], d[4]
+        self._random_starts = [[p] for p in self._positions(4)]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib().lleo_world_free(h)
+            self._h = None
+
+    @staticmethod
+    def level(n: int) -> "World":
+        return World(level_text(n))
+
+    @staticmethod
+    def from_file(name: str) -> "World":
+        low = name.lower()
+        for prefix in ("lvl", "level"):
+            if low.startswith(prefix) and low[len(prefix):].isdigit():
+                return World.level(int(low[len(prefix):]))
+        with open(name) as f:
+            return World(f.read())
+
+    def _positions(self, kind: int):
+        buf = (C.c_int * (2 * self.height * self.width + 2 * 64))()
+        n = lib().lleo_world_positions(self._h, kind, buf, len(buf) // 2)
+        return [(buf[2 * k], buf[2 * k + 1]) for k in range(n)]
+
+    # --- core API
+    def reset(self):
+        _check(lib().lleo_world_reset(self._h))
+
+    def step(self, actions) -> list[WorldEvent]:
+        if isinstance(actions, Action):
+            actions = [actions]
+        elif not isinstance(actions, (list, tuple)) or not all(isinstance(a, Action) for a in actions):
+            raise TypeError("Action must be of type Action or list[Action]")
+        acts = (C.c_uint8 * max(1, len(actions)))(*[int(a) for a in actions])
+        ev = (C.c_int * (4 * self.n_agents * (self.n_agents + 2)))()
+        ps = (C.c_int * (2 * self.n_agents * (self.n_agents + 2)))()
+        n = C.c_int(0)
+        _check(lib().lleo_world_step(self._h, acts, len(actions), ev, ps, C.byref(n)))
+        self.last_event_passes = [ps[k] for k in range(n.value)]
+        return [WorldEvent(EventType(ev[2 * k]), ev[2 * k + 1]) for k in range(n.value)]
+
+    def available_actions(self) -> list[list[Action]]:
+        mask = (C.c_uint8 * (5 * self.n_agents))()
+        order = (C.c_int8 * (5 * self.n_agents))()
+        lib().lleo_world_available(self._h, mask, order)
+        return [[Action(order[a * 5 + k]) for k in range(5) if order[a * 5 + k] >= 0] for a in range(self.n_agents)]
+
+    def available_mask(self) -> np.ndarray:
+        mask = (C.c_uint8 * (5 * self.n_agents))()
+        lib().lleo_world_available(self._h, mask, None)
+        return np.frombuffer(mask, dtype=np.uint8).reshape(self.n_agents, 5).astype(bool)
+
+    def get_state(self) -> WorldState:
+        pos = (C.c_int * (2 * self.n_agents))()
+        gems = (C.c_uint8 * max(1, self.n_gems))()
+        alive = (C.c_uint8 * self.n_agents)()
+        lib().lleo_world_get_state(self._h, pos, gems, alive)
+        return WorldState([(pos[2 * a], pos[2 * a + 1]) for a in range(self.n_agents)],
+                          [bool(gems[g]) for g in range(self.n_gems)], [bool(alive[a]) for a in range(self.n_agents)])
+
+    def set_state(self, state: WorldState) -> list[WorldEvent]:
+        na, ng = len(state.agents_positions), len(state.gems_collected)
+        pos = (C.c_long * max(1, 2 * na))(*[int(x) for p in state.agents_positions for x in p])
+        gems = (C.c_uint8 * max(1, ng))(*[int(g) for g in state.gems_collected])
+        alive = (C.c_uint8 * max(1, na))(*[int(a) for a in state.agents_alive])
+        ev = (C.c_int * (4 * max(1, self.n_agents)))()
+        n = C.c_int(0)
+        _check(lib().lleo_world_set_state(self._h, pos, na, gems, ng, alive, ev, C.byref(n)))
+        return [WorldEvent(EventType(ev[2 * k]), ev[2 * k + 1]) for k in range(n.value)]
+
+    # --- getters
+    @property
+    def agents_positions(self):
+        return self._positions(6)
+
+    @property
+    def agents(self):
+        dead = (C.c_uint8 * self.n_agents)()
+        arr = (C.c_uint8 * self.n_agents)()
+        lib().lleo_world_agents(self._h, dead, arr)
+        return [Agent(a, bool(dead[a]), bool(arr[a])) for a in range(self.n_agents)]
+
+    @property
+    def gems(self):
+        flags = (C.c_uint8 * max(1, self.n_gems))()
+        lib().lleo_world_gem_flags(self._h, flags)
+        return [Gem(p, bool(flags[g])) for g, p in enumerate(self._positions(3))]
+
+    @property
+    def gems_collected(self) -> int:
+        return lib().lleo_world_n_gems_collected(self._h)
+
+    @property
+    def lasers(self):
+        cap = 2 * self.height * self.width + 8
+        buf = (C.c_int * (7 * cap))()
+        n = lib().lleo_world_lasers(self._h, buf, cap)
+        return [Laser((buf[7 * k], buf[7 * k + 1]), buf[7 * k + 2], buf[7 * k + 3], Direction(buf[7 * k + 4]),
+                      bool(buf[7 * k + 5]), bool(buf[7 * k + 6])) for k in range(n)]
+
+    @property
+    def laser_sources(self):
+        buf = (C.c_int * (7 * max(1, self.n_sources)))()
+        n = lib().lleo_world_sources(self._h, buf, self.n_sources)
+        return [LaserSource(self, k, buf[7 * k:7 * k + 7]) for k in range(n)]
+
+    def source_at(self, pos):
+        for s in self.laser_sources:
+            if s.pos == tuple(pos):
+                return s
+        raise ValueError(f"No laser source at {pos}")
+
+    wall_pos = property(lambda self: self._positions(0))
+    void_pos = property(lambda self: self._positions(1))
+    exit_pos = property(lambda self: self._positions(2))
+    start_pos = property(lambda self: self._positions(4))
+    laser_pos = property(lambda self: self._positions(5))
+
+    @property
+    def random_start_pos(self):
+        return self._random_starts
+
+    @property
+    def n_laser_colours(self):
+        return len({s.agent_id for s in self.laser_sources})
+
+    # --- white-box helpers for parity checks
+    def beam_bits(self, idx: int) -> list[bool]:
+        n = self.laser_sources[idx].beam_len
+        buf = (C.c_uint8 * max(1, n))()
+        lib().lleo_world_beam_bits(self._h, idx, buf)
+        return [bool(buf[k]) for k in range(n)]
+
+    def occupied(self) -> np.ndarray:
+        buf = (C.c_uint8 * (self.height * self.width))()
+        lib().lleo_world_occupied(self._h, buf)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.height, self.width).astype(bool)
+
+    def observe_layered(self) -> np.ndarray:
+        """(A, C, H, W) float32, python/lle/observations.py:254-266."""
+        c = 2 * self.n_agents + 4
+        out = np.zeros((c, self.height, self.width), dtype=np.float32)
+        _check(lib().lleo_world_observe_layered(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return np.tile(out, (self.n_agents, 1, 1, 1))
+
+    def state_array(self) -> np.ndarray:
+        out = np.zeros(3 * self.n_agents + self.n_gems, dtype=np.float32)
+        lib().lleo_world_state_array(self._h, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
+
+# ------------------------------------------------------------------ LLE (python/lle/env/env.py)
+@dataclass
+class Step:
+    obs: np.ndarray
+    available_actions: np.ndarray
+    state: np.ndarray
+    reward: np.ndarray
+    done: bool
+    events: list
+
+
+class LLE:
+    def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True):
+        st = C.c_int(0)
+        self._h = C.c_void_p(lib().lleo_env_new(map_str.encode(), int(multi_objective), int(walkable_lasers), C.byref(st)))
+        _check(st.value)
+        d = (C.c_int * 6)()
+        lib().lleo_env_dims(self._h, d)
+        self.height, self.width, self.n_agents, self.n_gems, self.n_channels, self.reward_dim = list(d)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib().lleo_env_free(h)
+            self._h = None
+
+    @staticmethod
+    def level(n: int, **kw) -> "LLE":
+        return LLE(level_text(n), **kw)
+
+    @property
+    def done(self) -> bool:
+        return bool(lib().lleo_env_done(self._h))
+
+    @property
+    def n_arrived(self) -> int:
+        return lib().lleo_env_n_arrived(self._h)
+
+    def observe(self) -> np.ndarray:
+        out = np.zeros((self.n_channels, self.height, self.width), dtype=np.float32)
+        _check(lib().lleo_env_observe(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return np.tile(out, (self.n_agents, 1, 1, 1))
+
+    def get_state(self) -> np.ndarray:
+        out = np.zeros(3 * self.n_agents + self.n_gems, dtype=np.float32)
+        lib().lleo_env_state(self._h, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
+    def available_actions(self) -> np.ndarray:
+        out = np.zeros((self.n_agents, 5), dtype=np.uint8)
+        lib().lleo_env_available(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.astype(bool)
+
+    def reset(self):
+        _check(lib().lleo_env_reset(self._h))
+        return self.observe(), self.get_state()
+
+    def step(self, actions: Sequence[int]) -> Step:
+        acts = (C.c_uint8 * len(actions))(*[int(a) for a in actions])
+        reward = np.zeros(self.reward_dim, dtype=np.float32)
+        done = C.c_uint8(0)
+        ev = (C.c_int * (4 * self.n_agents * (self.n_agents + 2)))()
+        n = C.c_int(0)
+        _check(lib().lleo_env_step(self._h, acts, len(actions), reward.ctypes.data_as(C.POINTER(C.c_float)),
+                                   C.byref(done), ev, C.byref(n)))
+        events = [WorldEvent(EventType(ev[2 * k]), ev[2 * k + 1]) for k in range(n.value)]
+        return Step(self.observe(), self.available_actions(), self.get_state(), reward, bool(done.value), events)
+
+    def set_state(self, state: WorldState):
+        na, ng = len(state.agents_positions), len(state.gems_collected)
+        pos = (C.c_long * max(1, 2 * na))(*[int(x) for p in state.agents_positions for x in p])
+        gems = (C.c_uint8 * max(1, ng))(*[int(g) for g in state.gems_collected])
+        alive = (C.c_uint8 * max(1, na))(*[int(a) for a in state.agents_alive])
+        _check(lib().lleo_env_set_state(self._h, pos, na, gems, ng, alive))
+
+
+# ------------------------------------------------------------------ OracleVec
+class OracleVec:
+    """N oracle environments stepped in lockstep; arrays are views on the C++ buffers."""
+
+    def __init__(self, maps: Sequence[str], map_of_env: Sequence[int] | None, n_envs: int, *, multi_objective=False,
+                 walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0):
+        texts = (C.c_char_p * len(maps))(*[m.encode() for m in maps])
+        moe = None if map_of_env is None else (C.c_int * n_envs)(*[int(m) for m in map_of_env])
+        st = C.c_int(0)
+        self._h = C.c_void_p(lib().lleo_vec_new(texts, len(maps), moe, n_envs, int(multi_objective), int(walkable_lasers),
+                                                int(auto_reset), C.c_uint64(seed), C.c_uint64(env_id_base), C.byref(st)))
+        _check(st.value)
+        d = (C.c_long * 9)()
+        lib().lleo_vec_dims(self._h, d)
+        self.N, self.A, self.G, self.C, self.H, self.W, self.R, self.S, self.NB = list(d)
+        ptrs = (C.c_void_p * 14)()
+        lib().lleo_vec_buffers(self._h, ptrs)
+
+        def view(k, ctype, dtype, shape):
+            n = int(np.prod(shape))
+            if n == 0:
+                return np.zeros(shape, dtype=dtype)
+            arr = np.ctypeslib.as_array(C.cast(ptrs[k], C.POINTER(ctype)), shape=(n,))
+            return arr.view(dtype).reshape(shape)
+
+        N, A = self.N, self.A
+        self.obs = view(0, C.c_float, np.float32, (N, self.C, self.H, self.W))
+        self.state = view(1, C.c_float, np.float32, (N, self.S))
+        self.avail = view(2, C.c_uint8, np.uint8, (N, A, 5))
+        self.reward = view(3, C.c_float, np.float32, (N, self.R))
+        self.done = view(4, C.c_uint8, np.uint8, (N,))
+        self.events = view(5, C.c_uint8, np.uint8, (N, A))
+        self.actions = view(6, C.c_int8, np.int8, (N, A))
+        self.err = view(7, C.c_uint8, np.uint8, (N,))
+        self.pos = view(8, C.c_int16, np.int16, (N, A, 2))
+        self.alive = view(9, C.c_uint8, np.uint8, (N, A))
+        self.arrived = view(10, C.c_uint8, np.uint8, (N, A))
+        self.slot = view(11, C.c_uint8, np.uint8, (N, A))
+        self.beam_on = view(12, C.c_uint64, np.uint64, (N, max(self.NB, 1)))
+        self.collected = view(13, C.c_uint64, np.uint64, (N,))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib().lleo_vec_free(h)
+            self._h = None
+
+    @property
+    def t(self) -> int:
+        return lib().lleo_vec_step_count(self._h)
+
+    @t.setter
+    def t(self, value: int):
+        lib().lleo_vec_set_step_count(self._h, C.c_uint64(value))
+
+    def reset(self):
+        _check(lib().lleo_vec_reset(self._h))
+
+    def step(self, actions: np.ndarray | None = None, n_threads: int = 0):
+        ptr = None
+        if actions is not None:
+            actions = np.ascontiguousarray(actions, dtype=np.int8)
+            assert actions.shape == (self.N, self.A)
+            ptr = actions.ctypes.data_as(C.POINTER(C.c_int8))
+        _check(lib().lleo_vec_step(self._h, ptr, n_threads))
+
+    def rollout(self, steps: int, n_threads: int = 0) -> tuple[float, int]:
+        used = C.c_int(0)
+        secs = lib().lleo_vec_rollout(self._h, steps, n_threads, C.byref(used))
+        return float(secs), used.value
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().lleo_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def sample_action(seed: int, env_id: int, step: int, agent: int, mask5: int) -> int:
+    return lib().lleo_sample_action(C.c_uint64(seed), C.c_uint32(env_id), C.c_uint64(step), C.c_uint32(agent), C.c_uint32(mask5))
+
+
+def decode_events(byte_row: Sequence[int]) -> list[WorldEvent]:
+    """Ordered event list from the (pass, agent) byte encoding shared with include/lle_b200.h."""
+    out = []
+    code_to_type = {1: EventType.AGENT_EXIT, 2: EventType.GEM_COLLECTED, 3: EventType.AGENT_DIED}
+    for a, b in enumerate(byte_row):
+        if int(b) & 3:
+            out.append((1, a, WorldEvent(code_to_type[int(b) & 3], a)))
+    for a, b in enumerate(byte_row):
+        if int(b) >> 2:
+            out.append((int(b) >> 2, a, WorldEvent(EventType.AGENT_DIED, a)))
+    out.sort(key=lambda x: (x[0], x[1]))
+    return [e for _, _, e in out]

@@ -1,0 +1,375 @@
+"""Known-answer tests of the layered observation, the state vector, rewards and done flags,
+transcribed from the reference:
+
+  [O]  python/tests/test_observations.py
+  [E]  python/tests/test_env.py
+  [C]  python/tests/test_core.py
+  [S]  python/tests/test_reward_strategy.py
+
+Run against the oracle (CPU) and, with ``-m gpu``, against the CUDA path (``api.LLE`` is then the
+N=1 view of the batched environment).
+"""
+import numpy as np
+import pytest
+
+
+def channels(n_agents):
+    """python/lle/observations.py:205-211."""
+    a0, laser0 = 0, n_agents
+    wall = laser0 + n_agents
+    return dict(A0=a0, LASER_0=laser0, WALL=wall, VOID=wall + 1, GEM=wall + 2, EXIT=wall + 3, C=wall + 4)
+
+
+# ----------------------------------------------------------------------------- layered observation
+def test_observe_layered_deactivated_laser(api):  # [O]
+    world = api.World(
+        """
+@ @ L0S @  @
+@ .  .  .  @
+@ X  .  S0 @
+@ X  .  S1 @
+@ @  @  @  @
+"""
+    )
+    ch = channels(2)
+    world.reset()
+    layers = world.observe_layered()
+    assert layers.shape == (2, ch["C"], 5, 5) and layers.dtype == np.float32
+    l0, l1 = ch["LASER_0"], ch["LASER_0"] + 1
+    assert np.all(layers[:, l0, 0, 2] == -1)
+    assert np.all(layers[:, l0, 1:4, 2] == 1)
+    assert np.all(layers[:, l1] == 0)
+    world.step([api.Action.WEST, api.Action.STAY])
+    layers = world.observe_layered()
+    assert np.all(layers[:, l0, 0, 2] == -1)
+    assert np.all(layers[:, l0, 1, 2] == 1)
+    assert np.all(layers[:, l0, 2:4, 2] == 0)
+    assert np.all(layers[:, l1] == 0)
+    # agent layers (observations.py:264-265)
+    assert layers[0, ch["A0"], 2, 2] == 1 and layers[0, ch["A0"]].sum() == 1
+    assert layers[0, ch["A0"] + 1, 3, 3] == 1 and layers[0, ch["A0"] + 1].sum() == 1
+
+
+def test_observe_layered_gems_walls(api):  # [O]
+    world = api.World(
+        """
+@ @ L0S @  @
+@ .  .  .  @
+@ X  G  S0 @
+@ .  .  .  @
+@ @  @  @  @
+"""
+    )
+    ch = channels(1)
+    world.reset()
+    layers = world.observe_layered()
+    for i, j in world.wall_pos:
+        assert np.all(layers[:, ch["WALL"], i, j] == 1)
+    assert layers[0, ch["WALL"]].sum() == len(world.wall_pos)
+    for gem in world.gems:
+        assert np.all(layers[:, ch["GEM"], gem.pos[0], gem.pos[1]] == 1)
+    for i, j in world.exit_pos:
+        assert np.all(layers[:, ch["EXIT"], i, j] == 1)
+    for laser in world.lasers:
+        if laser.is_on:
+            assert np.all(layers[:, ch["LASER_0"] + laser.agent_id, laser.pos[0], laser.pos[1]] == 1)
+    for source in world.laser_sources:
+        assert np.all(layers[:, ch["LASER_0"] + source.agent_id, source.pos[0], source.pos[1]] == -1)
+    assert np.all(layers[:, ch["VOID"]] == 0)
+
+
+def test_observe_layered_void(api):  # [O]
+    world = api.World(
+        """
+    V . . S0
+    . . . .
+    V V G X"""
+    )
+    ch = channels(1)
+    world.reset()
+    layers = world.observe_layered()
+    expected = np.zeros((3, 4), dtype=np.float32)
+    for i, j in [(0, 0), (2, 0), (2, 1)]:
+        expected[i, j] = 1.0
+    assert np.array_equal(layers[0, ch["VOID"]], expected)
+
+
+def test_observe_gem_layer_follows_collection(api):  # observations.py:260-263
+    world = api.World("S0 G X")
+    ch = channels(1)
+    world.reset()
+    assert world.observe_layered()[0, ch["GEM"], 0, 1] == 1
+    world.step([api.Action.EAST])
+    assert world.observe_layered()[0, ch["GEM"]].sum() == 0
+
+
+def test_layered_laser_colour_above_n_agents(api):  # [O] test_layered_observation_laser_source_agent_id_above_n_agents
+    world = api.World("S0 L1E X")
+    ch = channels(1)
+    data = world.observe_layered()
+    laser_1_layer = data[0, ch["LASER_0"] + 1]  # aliases the WALL channel
+    assert laser_1_layer[0, 1] == -1
+    assert laser_1_layer[0, 2] == 1
+
+
+def test_layered_laser_colour_out_of_channels(api):  # numpy IndexError in observations.py:235
+    world = api.World("S0 L9E X")
+    with pytest.raises(IndexError):
+        world.observe_layered()
+
+
+def test_all_shapes(api):  # [O] test_all_shapes (layered / flattened / state)
+    for level in range(1, 7):
+        world = api.World.level(level)
+        obs = world.observe_layered()
+        a = world.n_agents
+        assert obs.shape == (a, 2 * a + 4, 12, 13)
+        assert obs.reshape(a, -1).shape == (a, (2 * a + 4) * 12 * 13)  # FlattenedLayered (observations.py:291-293)
+        assert world.state_array().shape == (3 * a + world.n_gems,)
+        for k in range(1, a):
+            assert np.array_equal(obs[0], obs[k])  # np.tile (observations.py:266)
+
+
+def test_level6_initial_observation(api):  # Appendix D of SURVEY.md + resources/levels/lvl6
+    world = api.World.level(6)
+    world.reset()
+    ch = channels(4)
+    obs = world.observe_layered()[0]
+    for a in range(4):
+        assert obs[ch["A0"] + a, 0, 4 + a] == 1 and obs[ch["A0"] + a].sum() == 1
+    # L2S at (0,1): beam of 2 cells stopped by the wall at (3,1)
+    assert obs[ch["LASER_0"] + 2, 0, 1] == -1 and obs[ch["LASER_0"] + 2, 1:3, 1].tolist() == [1, 1]
+    assert obs[ch["LASER_0"] + 2].sum() == 1
+    # L0E at (4,0): 6 cells up to the wall at (4,7)
+    assert obs[ch["LASER_0"], 4, 0] == -1 and obs[ch["LASER_0"], 4, 1:7].tolist() == [1] * 6
+    # L1W at (6,12): 12 cells
+    assert obs[ch["LASER_0"] + 1, 6, 12] == -1 and obs[ch["LASER_0"] + 1, 6, 0:12].tolist() == [1] * 12
+    assert obs[ch["GEM"]].sum() == 4 and obs[ch["EXIT"]].sum() == 4 and obs[ch["VOID"]].sum() == 0
+    assert obs[ch["WALL"]].sum() == len(world.wall_pos) == 18  # 15 walls + 3 sources (parser_v1.rs:22-25)
+
+
+def test_observation_gem_collected_state(api):  # [O] test_observation_gem_collected
+    world = api.World("S0 X . .\n.  . . .\nG  . . .")
+    world.reset()
+    world.step([api.Action.SOUTH])
+    assert world.state_array()[2] == 0.0
+    world.step([api.Action.SOUTH])
+    assert world.state_array()[2] == 1.0
+    world.step([api.Action.NORTH])
+    assert world.state_array()[2] == 1.0
+    assert world.state_array().tolist() == [1.0, 0.0, 1.0, 1.0]
+
+
+# ----------------------------------------------------------------------------- rewards / done (LLE)
+def test_void_reward(api):  # [E]
+    env = api.LLE("S0 V X")
+    env.reset()
+    step = env.step([api.Action.EAST])
+    assert step.reward.tolist() == [-1.0]
+    assert step.done
+
+
+def test_collect_reward(api):  # [E]
+    env = api.LLE("S0 X . .\n.  . . .\nG  . . .")
+    env.reset()
+    env.step([api.Action.SOUTH])
+    assert env.step([api.Action.SOUTH]).reward.tolist() == [1.0]
+
+
+def test_time_reward(api):  # [E]
+    env = api.LLE(". .  . X\n. S0 . .\n. .  . .")
+    env.reset()
+    for action in api.Action:
+        assert env.step([action]).reward.tolist() == [0.0]
+
+
+def test_finish_reward(api):  # [E]
+    env = api.LLE(
+        """@ @ @  @ @ @
+@ . .  . . @
+@ . S0 . . @
+@ . .  X . @
+@ @ @  @ @ @"""
+    )
+    env.reset()
+    env.step([api.Action.EAST])
+    step = env.step([api.Action.SOUTH])
+    assert step.reward.tolist() == [2.0] and step.done
+
+
+def test_arrive_reward_only_once(api):  # [E] 7-step trace
+    A = api.Action
+    env = api.LLE("S0 . G\nS1 X X")
+    trace = [
+        ([A.EAST, A.STAY], 0),
+        ([A.STAY, A.EAST], 1),
+        ([A.STAY, A.STAY], 0),
+        ([A.STAY, A.STAY], 0),
+        ([A.EAST, A.STAY], 1),
+        ([A.STAY, A.STAY], 0),
+        ([A.SOUTH, A.STAY], 2),
+    ]
+    env.reset()
+    for k, (action, reward) in enumerate(trace):
+        step = env.step(action)
+        assert step.reward.tolist() == [float(reward)]
+        assert step.done == (k == len(trace) - 1)
+
+
+def test_reward_after_reset(api):  # [E]
+    A = api.Action
+    env = api.LLE("S0 X . .\n.  . . .\nG  . . .")
+    for _ in range(10):
+        env.reset()
+        env.step([A.SOUTH])
+        assert env.step([A.SOUTH]).reward.tolist() == [1.0]
+        assert not env.done
+        assert env.step([A.NORTH]).reward.tolist() == [0.0]
+        assert env.step([A.NORTH]).reward.tolist() == [0.0]
+        step = env.step([A.EAST])
+        assert env.done and step.reward.tolist() == [2.0]
+
+
+def test_reward_after_set_state(api):  # [E]
+    env = api.LLE("S0 . G\nS1 X X")
+    env.reset()
+    env.set_state(api.WorldState([(0, 1), (1, 1)], [False]))
+    assert env.step([api.Action.EAST, api.Action.STAY]).reward.tolist() == [1.0]
+
+
+def test_reward_set_state_all_arrived(api):  # [E]
+    env = api.LLE("S0 . G\nS1 X X")
+    env.reset()
+    env.set_state(api.WorldState([(0, 2), (1, 1)], [True]))
+    assert env.step([api.Action.SOUTH, api.Action.STAY]).reward.tolist() == [2.0]
+
+
+def test_reward(api):  # [E]
+    A = api.Action
+    env = api.LLE("S0 G .\n.  . X")
+    env.reset()
+    assert env.step([A.EAST]).reward.tolist() == [1.0]
+    assert env.step([A.EAST]).reward.tolist() == [0.0]
+    assert env.step([A.SOUTH]).reward.tolist() == [2.0]
+
+
+def test_reward_death(api):  # [E]
+    env = api.LLE("S0 L0S X\nS1  .  X")
+    env.reset()
+    step = env.step([api.Action.STAY, api.Action.EAST])
+    assert step.reward.tolist() == [-1.0]
+    assert step.done
+
+
+def test_reward_collect_and_death(api):  # [E]
+    env = api.LLE("S0 L0S X\nS1  G  X")
+    env.reset()
+    step = env.step([api.Action.STAY, api.Action.EAST])
+    assert step.reward.item() == -1.0
+    assert step.done
+
+
+def test_step_in_done_env_raises(api):  # env.py:166-167
+    env = api.LLE("S0 V X")
+    env.reset()
+    env.step([api.Action.EAST])
+    with pytest.raises(ValueError):
+        env.step([api.Action.STAY])
+
+
+def test_multi_objective_rewards(api):  # [E]
+    A = api.Action
+    env = api.LLE("S0 G .\n.  . X", multi_objective=True)
+    env.reset()
+    assert env.step([A.EAST]).reward.tolist() == [1.0, 0.0, 0.0, 0.0]
+    assert env.step([A.EAST]).reward.tolist() == [0.0, 0.0, 0.0, 0.0]
+    step = env.step([A.SOUTH])
+    assert step.done
+    assert step.reward.tolist() == [0.0, 1.0, 0.0, 1.0]
+
+
+def test_multi_objective_death(api):  # [E]
+    env = api.LLE("S0 L0S X\nS1  G  X", multi_objective=True)
+    env.reset()
+    assert env.step([api.Action.STAY, api.Action.EAST]).reward.tolist() == [0.0, 0.0, -1.0, 0.0]
+
+
+def test_env_available_actions(api):  # [C] test_available_actions
+    A = api.Action
+    env = api.LLE(
+        """
+@ @ L0S @  @
+@ .  .  .  @
+@ X  .  S0 @
+@ X  .  S1 @
+@ @  @  @  @
+"""
+    )
+    obs, state = env.reset()
+    av = env.available_actions()
+    assert av.shape == (2, 5) and av.dtype == bool
+    assert av[0].tolist() == [True, False, False, True, True]  # N, S, E, W, STAY
+    assert av[1].tolist() == [False, False, False, True, True]
+
+
+WALK = """
+@ @ L{c}S @  @
+@ .  .  .  @
+@ X  {m0} {r0} @
+@ X  .  {r1} @
+@ @  @  @  @
+"""
+
+
+def test_walkable_lasers(api):  # python/tests/test_walkable_lasers.py (all five cases) ; env.py:153-163
+    W = api.Action.WEST
+    # enabled (default): agents may walk into any laser
+    env = api.LLE(WALK.format(c=0, m0=".", r0="S0", r1="S1"))
+    env.reset()
+    av = env.available_actions()
+    assert av[0, W] and av[1, W]
+    # disabled, laser active: the other colour may not enter
+    env = api.LLE(WALK.format(c=0, m0=".", r0="S0", r1="S1"), walkable_lasers=False)
+    env.reset()
+    av = env.available_actions()
+    assert av[0, W] and not av[1, W]
+    # disabled, beam blocked by its owner standing in it
+    env = api.LLE(WALK.format(c=0, m0="S0", r0=".", r1="S1"), walkable_lasers=False)
+    env.reset()
+    assert env.available_actions()[1, W]
+    # switched colours
+    env = api.LLE(WALK.format(c=1, m0=".", r0="S0", r1="S1"), walkable_lasers=False)
+    env.reset()
+    av = env.available_actions()
+    assert not av[0, W] and av[1, W]
+    env = api.LLE(WALK.format(c=1, m0="S1", r0=".", r1="S0"), walkable_lasers=False)
+    env.reset()
+    assert env.available_actions()[0, W]
+
+
+def test_force_end_state_env(api):  # [C] test_force_end_state
+    env = api.LLE("S0 . G\nX  . .")
+    env.reset()
+    env.set_state(api.WorldState([(1, 0)], [True]))
+    assert env.done
+
+
+def test_move_end_game(api):  # [C] test_move_end_game
+    A = api.Action
+    env = api.LLE(
+        """
+    S0 X .
+    .  . .
+    .  . ."""
+    )
+    env.reset()
+    env.step([A.SOUTH])
+    assert not env.done
+    env.step([A.SOUTH])
+    assert not env.done
+    env.step([A.EAST])
+    assert not env.done
+    env.step([A.NORTH])
+    assert not env.done
+    step = env.step([A.NORTH])
+    assert step.done and env.done

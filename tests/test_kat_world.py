@@ -1,0 +1,855 @@
+"""Known-answer tests of the `World` engine, transcribed from the reference's own suites:
+
+  [R]  src/unit_tests/test_world.rs
+  [I]  tests/world_integration_tests.rs
+  [P]  python/tests/test_world.py
+
+Each test names its source.  They run against the oracle (CPU) and, with ``-m gpu``, against the
+CUDA path through the N=1 ``World`` facade — same assertions, bit-exact expectations.
+"""
+import pytest
+
+
+def laser_at(world, pos):
+    """[R] get_laser (test_world.rs:15-22): first listed laser at `pos` (the outermost one)."""
+    for laser in world.lasers:
+        if tuple(laser.pos) == tuple(pos):
+            return laser
+    raise AssertionError(f"No laser at {pos}")
+
+
+# ----------------------------------------------------------------------------- parsing / layout
+def test_tile_type(api):  # [R] test_tile_type :25
+    world = api.World(
+        """
+    S0 . G
+    L0E X @
+    """
+    )
+    world.reset()
+    assert world.start_pos[0] == (0, 0)
+    assert (0, 2) in [g.pos for g in world.gems]
+    source = world.source_at((1, 0))
+    assert source.agent_id == 0
+    assert laser_at(world, (1, 1)).agent_id == 0
+    assert world.exit_pos.count((1, 1)) == 1
+    assert len(world.wall_pos) == 2
+    assert (1, 2) in world.wall_pos and (1, 0) in world.wall_pos
+
+
+def test_duplicate_start_pos(api):  # [R] :64
+    with pytest.raises(api.ParsingError, match="DuplicateStartTile"):
+        api.World("S0 S0 X X")
+
+
+def test_start_pos_order(api):  # [R] :78
+    world = api.World("S1 S0 X X")
+    assert world.start_pos == [(0, 1), (0, 0)]
+    world.reset()
+    assert world.agents_positions == [(0, 1), (0, 0)]
+
+
+def test_start_pos_order_lvl6(api):  # [R] :89
+    world = api.World.from_file("lvl6")
+    world.reset()
+    for agent, pos in enumerate(world.start_pos):
+        assert pos == (0, agent + 4)
+        assert world.agents_positions[agent] == (0, agent + 4)
+
+
+def test_laser_blocked_by_wall(api):  # [R] :100
+    w = api.World(
+        """
+        . L0S .
+        .  .  .
+        X  @  S0
+        .  .  ."""
+    )
+    w.reset()
+    for pos in w.laser_pos:
+        assert pos != (2, 1) and pos != (3, 1)
+
+
+def test_empty_world(api):  # [R] :188, [I] parse_empty_world :95
+    with pytest.raises(api.ParsingError, match="EmptyWorld"):
+        api.World("")
+
+
+def test_parse_inconsistent_row_lengths(api):  # [R] :358
+    with pytest.raises(api.ParsingError, match="InconsistentDimensions"):
+        api.World(
+            """X S0 .
+         . ."""
+        )
+
+
+def test_parse_inconsistent_start_exit_tiles(api):  # [R] :381
+    with pytest.raises(api.ParsingError, match="NotEnoughExitTiles"):
+        api.World("S1 S0 X")
+
+
+def test_parse_no_agents(api):  # [R] :395 ; [P] test_parse_wrong_worlds
+    with pytest.raises(api.ParsingError, match="NoAgents"):
+        api.World(". . G")
+    with pytest.raises(api.ParsingError):
+        api.World("X G")
+    with pytest.raises(api.ParsingError):
+        api.World(
+            """
+            @ @  @ @
+            @ S0 . @
+            @ .  . @
+            @ @  @ @"""
+        )
+
+
+def test_invalid_tile(api):  # parser_v1.rs:163-169
+    with pytest.raises(api.ParsingError, match="InvalidTile"):
+        api.World("S0 Q X")
+
+
+def test_standard_levels(api):  # [R] :439 / :449 ; [P] test_get_standard_level
+    expected = {1: (1, 1), 2: (2, 1), 3: (2, 1), 4: (2, 1), 5: (4, 5), 6: (4, 4)}
+    for level in range(1, 7):
+        for w in (api.World.level(level), api.World.from_file(f"lvl{level}"), api.World.from_file(f"level{level}")):
+            assert (w.height, w.width) == (12, 13)
+            assert (w.n_agents, w.n_gems) == expected[level]
+
+
+def test_laser_on_start_pos_error(api):  # [P] test_laser_on_start_pos_error ; test_parser_v1.rs:61-77
+    with pytest.raises(api.ParsingError, match="AgentWithoutStart"):
+        api.World(
+            """
+    S0  S1 X . X
+    L1N .  . . .
+    """
+        )
+
+
+def test_laser_sources_in_wall_pos(api):  # [P]
+    world = api.World(
+        """
+        S0 . . X
+       L0E . . X
+        S1 . . X
+       L1E . . X
+"""
+    )
+    for source in world.laser_sources:
+        assert source.pos in world.wall_pos
+
+
+def test_laser_num_higher_than_n_agents(api):  # [P]
+    world = api.World("S0 L1E X")
+    assert world.source_at((0, 1)).agent_id == 1
+
+
+def test_n_laser_colours(api):  # [P] test_n_laser_colours*
+    assert api.World("S0 L0E X\nS1 L1E X").n_laser_colours == 2
+    assert api.World("S0 L0E X\n . L2E X").n_laser_colours == 2
+    assert api.World("S0 L0E X\n . L0E X").n_laser_colours == 1
+
+
+def test_many_agents(api):  # [P]
+    rows = [" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)]
+    world = api.World("\n".join(rows))
+    assert world.n_agents == 14
+    assert len(world.laser_sources) == 14
+
+
+def test_source_laser_id_is_source_index(api):  # [R] check_source_laser_id_is_the_same_as_source_index :682
+    w = api.World(
+        """
+S0  S1  S2  S3  S4  S5  S6  S7  S8  S9  S10
+L0S L1S L2S L3S L4S L5S L6S L7S L8S L9S L10S
+ .  .   .   .   .   .   .   .   .   .   .
+ X  X   X   X   X   X   X   X   X   X   X
+"""
+    )
+    for i, source in enumerate(w.laser_sources):
+        assert source.laser_id == i
+
+
+def test_beam_cells(api):  # [R] test_beam_single_source :662, test_beam_long :698, test_beam_south_direction :721
+    w = api.World("L0E . L0S\nS0  X  @")
+    w.reset()
+    assert sorted(l.pos for l in w.lasers if l.laser_id == w.source_at((0, 0)).laser_id) == [(0, 1)]
+    assert [l for l in w.lasers if l.laser_id == w.source_at((0, 2)).laser_id] == []
+
+    w = api.World("L0E .  .  .  .  @\nS0  .  .  .  X  @")
+    assert sorted(l.pos for l in w.lasers) == [(0, 1), (0, 2), (0, 3), (0, 4)]
+
+    w = api.World("@  L0S @\n.  .   .\n.  .   .\nS0 X   @")
+    assert sorted(l.pos for l in w.lasers) == [(1, 1), (2, 1), (3, 1)]
+
+
+def test_beam_two_sources(api):  # [R] :757
+    w = api.World(
+        """
+        @ L0E .  .  .
+        .  .  .  .  .
+        @ L1E .  @  @
+        S0 .  .  X  .
+        S1 .  .  X  ."""
+    )
+    by_id = {}
+    for l in w.lasers:
+        by_id.setdefault(l.laser_id, []).append(l.pos)
+    assert len(by_id[w.source_at((0, 1)).laser_id]) == 3
+    assert len(by_id[w.source_at((2, 1)).laser_id]) == 1
+
+
+def test_laser_on_exit(api):  # [I] :482
+    w = api.World(
+        """
+    .   L0S S1
+    S0   .   .
+    L1E  X   X"""
+    )
+    w.reset()
+    lasers = w.lasers
+    assert len(lasers) == 4
+    for laser_id in range(2):
+        assert len([l for l in lasers if l.laser_id == laser_id]) == 2
+
+
+def test_laser_id(api):  # [I] test_laser_id :410, test_laser_sources_have_different_laser_ids :459
+    w = api.World(
+        """
+        S0 .   G  X
+        .  .  L0W .
+        .  S1  .  X
+        .  .  L0W  ."""
+    )
+    w.reset()
+    ids = {s.pos[0]: s.laser_id for s in w.laser_sources}
+    for l in w.lasers:
+        assert l.laser_id == ids[l.pos[0]]
+    w = api.World("L0E . L0E . X S0")
+    assert len({s.laser_id for s in w.laser_sources}) == 2
+
+
+# ----------------------------------------------------------------------------- stepping
+def test_laser_blocked_on_reset(api):  # [R] :118
+    w = api.World(
+        """
+        @ @ L0S @  @
+        @ .  .  .  @
+        @ X  S0 .  @
+        @ .  .  .  @
+        @ @  @  @  @"""
+    )
+    w.reset()
+    assert all(a.is_alive for a in w.agents)
+    assert laser_at(w, (1, 2)).is_on
+    assert laser_at(w, (2, 2)).is_off
+    assert laser_at(w, (3, 2)).is_off
+
+
+FACING = """
+         @ @ L0S @  @
+         @ X  .  S0 @
+         @ .  .  .  @
+         @ X  .  S1 @
+         @ @ L1N  @ @"""
+
+
+def test_facing_lasers(api):  # [R] :138
+    w = api.World(FACING)
+    w.reset()
+    w.step([api.Action.WEST, api.Action.WEST])
+    assert all(a.is_alive for a in w.agents)
+    assert all(l.is_off for l in w.lasers)
+
+
+def test_facing_lasers_agent_dies(api):  # [R] :172
+    w = api.World(FACING)
+    w.reset()
+    w.step([api.Action.WEST, api.Action.STAY])
+    assert w.agents[0].is_dead
+
+
+def test_event_exit_when_staying(api):  # [R] :158
+    w = api.World("S0 X .\nS1 . X")
+    w.reset()
+    assert len(w.step([api.Action.EAST, api.Action.STAY])) == 1
+    assert len(w.step([api.Action.STAY, api.Action.STAY])) == 0
+
+
+def test_complex_laser_blocking(api):  # [R] :256
+    w = api.World(
+        """
+    G L0E X . X
+    G G . . L1W
+    @ S0 . . @
+    . @ . . .
+    S1 G . . G"""
+    )
+    w.reset()
+    assert laser_at(w, (0, 3)).is_on
+    w.set_state(api.WorldState([(0, 2), (0, 3)], [False] * 5))
+    assert laser_at(w, (0, 3)).is_off
+    assert all(a.is_alive for a in w.agents)
+    w.step([api.Action.STAY, api.Action.EAST])
+    assert all(a.is_alive for a in w.agents)
+    assert laser_at(w, (0, 3)).is_off
+
+
+def test_die_in_void(api):  # [R] :324
+    w = api.World("S0 V X")
+    w.reset()
+    w.step([api.Action.EAST])
+    assert w.agents[0].is_dead
+
+
+def test_num_gems_collected_and_arrived(api):  # [R] test_num_gems_collected :332, test_num_agents_arrived :345
+    world = api.World("S0 G X")
+    world.reset()
+    assert world.gems_collected == 0
+    world.step([api.Action.EAST])
+    assert world.gems_collected == 1 and not world.agents[0].has_arrived
+    world.step([api.Action.STAY])
+    assert world.gems_collected == 1 and not world.agents[0].has_arrived
+    world.step([api.Action.EAST])
+    assert world.gems_collected == 1 and world.agents[0].has_arrived
+
+
+def test_vertex_conflict_rust(api):  # [R] :406
+    w = api.World("S0 X .\n.  . .\nS1 X .")
+    w.reset()
+    w.step([api.Action.SOUTH, api.Action.NORTH])
+    assert w.agents_positions == [(0, 0), (2, 0)]
+
+
+def test_reset_event_lists(api):  # [R] test_reset :422
+    w = api.World("S0 G X")
+    for _ in range(10):
+        w.reset()
+        assert w.agents_positions[0] == (0, 0)
+        assert w.step([api.Action.EAST]) == [api.WorldEvent(api.EventType.GEM_COLLECTED, 0)]
+        assert w.step([api.Action.EAST]) == [api.WorldEvent(api.EventType.AGENT_EXIT, 0)]
+
+
+def test_beam_agent_on_beam_tile(api):  # [R] :738
+    w = api.World(
+        """
+        L0E .  .  .
+        .   S0 .  X
+        .   .  .  . """
+    )
+    w.reset()
+    w.step([api.Action.NORTH])
+    assert w.agents_positions[0] == (0, 1)
+    assert sorted(l.pos for l in w.lasers) == [(0, 1), (0, 2), (0, 3)]
+    assert all(l.is_off for l in w.lasers)
+
+
+def test_available_actions_rust(api):  # [I] :4
+    w = api.World("S0 . G\nL0E X .")
+    w.reset()
+    assert sorted(w.available_actions()[0]) == sorted([api.Action.STAY, api.Action.EAST])
+
+
+AVAIL_MAP = """
+    .  S1 .
+    .  S0 G
+    L0E X X
+    """
+
+
+def test_available_actions_exit_trace(api):  # [I] test_available_actions_two_agents :20, test_available_actions_exit :44
+    A = api.Action
+    w = api.World(AVAIL_MAP)
+    w.reset()
+
+    def check(e0, e1):
+        av = w.available_actions()
+        assert sorted(av[0]) == sorted(e0) and sorted(av[1]) == sorted(e1)
+
+    check([A.STAY, A.EAST, A.WEST, A.SOUTH], [A.STAY, A.EAST, A.WEST])
+    w.step([A.SOUTH, A.EAST])
+    check([A.STAY], [A.STAY, A.WEST, A.SOUTH])
+    w.step([A.STAY, A.SOUTH])
+    check([A.STAY], [A.STAY, A.WEST, A.SOUTH, A.NORTH])
+    w.step([A.STAY, A.SOUTH])
+    check([A.STAY], [A.STAY])
+
+
+def test_available_actions_order(api):  # world.rs:349-351 : Stay first, then N, E, S, W
+    A = api.Action
+    w = api.World(". . .\n. S0 .\n. . X")
+    w.reset()
+    assert w.available_actions()[0] == [A.STAY, A.NORTH, A.EAST, A.SOUTH, A.WEST]
+
+
+def test_take_action_not_available(api):  # [I] :106, :125, :144, :163
+    A = api.Action
+    for text, actions in [
+        ("S0 X", [A.NORTH]),
+        ("S0 X\nS1 X", [A.SOUTH, A.NORTH]),
+        ("L0E X\nS0 .", [A.NORTH]),
+        ("L0E X\nS0 .", [A.WEST]),
+    ]:
+        w = api.World(text)
+        w.reset()
+        before = w.get_state()
+        with pytest.raises(api.InvalidActionError):
+            w.step(actions)
+        assert w.get_state() == before  # world.rs:444-453: no mutation on error
+
+
+def test_wrong_number_of_actions(api):  # world.rs:436-441 -> ValueError (pyexceptions.rs)
+    w = api.World("S0 X\nS1 X")
+    w.reset()
+    with pytest.raises(ValueError):
+        w.step([api.Action.STAY])
+
+
+def test_dead_agent_does_not_block_the_laser(api):  # [I] :279 — two-pass death cascade
+    A, E = api.Action, api.EventType
+    w = api.World(
+        """
+        S0 .   G  X
+        .  .  L2W X
+        .  S1  .  X
+        . L1N  .  S2"""
+    )
+    w.reset()
+    events = w.step([A.EAST, A.NORTH, A.STAY])
+    # pass 1: agent 1 dies in L2W; pass 2: the released L1N beam kills agent 0 (world.rs:468-472)
+    assert events == [api.WorldEvent(E.AGENT_DIED, 1), api.WorldEvent(E.AGENT_DIED, 0)]
+    for l in w.lasers:
+        if l.pos == (0, 1):
+            assert l.is_on
+    # the cell between the dead blocker and the next leaver keeps a stale off bit
+    l1n = {l.pos: l.is_on for l in w.lasers if l.laser_id == 1}
+    assert l1n == {(2, 1): True, (1, 1): False, (0, 1): True}
+
+
+def test_world_state_equal(api):  # [I] :312
+    w = api.World("S0 . G\n.  . X")
+    w.reset()
+    s1 = w.get_state()
+    assert s1 == w.get_state()
+    w.step([api.Action.STAY])
+    assert s1 == w.get_state()
+    w.step([api.Action.EAST])
+    assert s1 != w.get_state()
+
+
+def test_blocked_laser_on_spawn(api):  # [I] :559
+    w = api.World(
+        """
+    . L1S .  X .  .
+    . S1  .  . .  .
+    . S0  .  @ . L0W
+    .  .  .  . .  .
+    @  . L2N . .  X
+    .  .  .  @ .  . """
+    )
+    actions = [api.Action.EAST, api.Action.EAST]
+    w.reset()
+    w.step(actions)
+    w.reset()
+    w.step(actions)
+
+
+def test_reset_in_blocked_laser(api):  # [P]
+    A = api.Action
+    w = api.World(
+        """
+    . .  .  @ .  .  .  . .  .  . . .
+    . .  .  . @  X  .  . .  @  . . .
+    . .  .  . . L1S .  X .  .  @ . @
+    . .  .  . .  .  .  . .  .  . . .
+    . S3  . . . S1  .  . .  .  . @ .
+    . .  .  @ . S0  .  @ . L0W . . .
+    @ .  .  @ .  .  .  . .  .  . . .
+    . .  .  . .  .  .  . .  .  . X .
+    . .  .  . @  . L2N . .  .  . . .
+    . .  S2 . .  .  .  . .  .  . . X
+    . .  .  @ .  .  @  . .  @  . . .
+    . .  .  . .  .  .  @ .  .  . . ."""
+    )
+    w.reset()
+    actions = [A.EAST, A.EAST, A.NORTH, A.SOUTH]
+    ev1 = w.step(actions)
+    w.reset()
+    assert w.step(actions) == ev1
+
+
+def test_world_step_one_action(api):  # [P]
+    world = api.World("S0 X . .\n.  . . .\n.  . . .")
+    world.reset()
+    assert world.step(api.Action.SOUTH) == []
+    assert world.agents_positions == [(1, 0)]
+
+
+def test_world_step_type_errors(api):  # [P] test_world_step_something_else_than_action, ..._invalid_sequence_action
+    world = api.World("S0 X . .\n.  . . .\n.  . . .")
+    world.reset()
+    with pytest.raises(TypeError):
+        world.step(23)
+    world.step((api.Action.SOUTH,))
+    assert world.agents_positions == [(1, 0)]
+    with pytest.raises(TypeError, match="Action must be of type Action or list\\[Action\\]"):
+        world.step((23,))
+
+
+def test_walk_into_wall(api):  # [P]
+    world = api.World(
+        """@ @ @  @ @ @
+@ . .  . . @
+@ . S0 . . @
+@ . .  X . @
+@ @ @  @ @ @"""
+    )
+    world.reset()
+    world.step([api.Action.SOUTH])
+    with pytest.raises(api.InvalidActionError):
+        world.step([api.Action.SOUTH])
+
+
+def test_gem_collected_and_agent_died(api):  # [P] — quirk 5: a gem under a lethal beam is not collected
+    world = api.World("S0  G  X\nS1 L1N X")
+    world.reset()
+    events = world.step([api.Action.EAST, api.Action.STAY])
+    assert len(events) == 1
+    assert events[0].event_type == api.EventType.AGENT_DIED
+    assert world.gems_collected == 0
+
+
+def test_world_gem_collected_and_agent_has_arrived(api):  # [P]
+    A = api.Action
+    world = api.World("S0 X . .\n.  . . .\nG  . . .")
+    world.reset()
+    world.reset()
+    world.step([A.SOUTH])
+    world.step([A.SOUTH])
+    assert world.gems_collected == 1
+    world.step([A.NORTH])
+    world.step([A.NORTH])
+    world.step([A.EAST])
+    assert world.agents[0].has_arrived
+
+
+def test_vertex_conflict_python(api):  # [P]
+    world = api.World(
+        """
+        .  X  .  .
+        S0 .  S1  .
+        .  X  .  ."""
+    )
+    world.reset()
+    state = world.get_state()
+    world.step([api.Action.EAST, api.Action.WEST])
+    assert state == world.get_state()
+
+
+def test_swapping_conflict(api):  # [P]
+    A = api.Action
+    world = api.World("S0 X  .  .\n.  .  S1  .\n.  X  .  .")
+    world.reset()
+    world.step([A.SOUTH, A.WEST])
+    with pytest.raises(api.InvalidActionError):
+        world.step([A.EAST, A.WEST])
+
+
+def test_walk_into_laser_source(api):  # [P]
+    A = api.Action
+    world = api.World(
+        """
+        @ L0S @
+        .  .  .
+        X  .  S0
+        .  .  ."""
+    )
+    world.reset()
+    world.step([A.WEST])
+    world.step([A.NORTH])
+    with pytest.raises(ValueError):
+        world.step([A.NORTH])
+
+
+def test_walk_outside_map(api):  # [P]
+    A = api.Action
+    world = api.World(
+        """@ @ L0S @  @
+@ .  .  .  @
+@ X  .  S0 @
+@ .  .  .  @
+@ @  .  @  @
+"""
+    )
+    world.reset()
+    world.step([A.SOUTH])
+    world.step([A.WEST])
+    world.step([A.SOUTH])
+    with pytest.raises(ValueError):
+        world.step([A.SOUTH])
+
+
+def test_world_done(api):  # [P] — a dead agent may only STAY
+    A = api.Action
+    world = api.World(
+        """
+G  G  . .  S1
+X  .  . @  .
+@  .  G .  .
+G  .  . G  X
+@ L0N . S0 ."""
+    )
+    world.reset()
+    for _ in range(3):
+        world.step([A.STAY, A.WEST])
+    assert world.agents[1].is_dead
+    with pytest.raises(ValueError):
+        world.step([A.STAY, A.WEST])
+
+
+def test_laser_tile_state(api):  # [P]
+    world = api.World("L0E S0 . X")
+    world.reset()
+    assert len(world.lasers) == 3
+    assert all(l.is_off for l in world.lasers)
+    world.step([api.Action.EAST])
+    for laser in world.lasers:
+        assert laser.is_on == (laser.pos == (0, 1))
+
+
+def test_no_reset(api):  # [P] World::new resets itself (world.rs:82)
+    w = api.World("S0 . X")
+    w.step(api.Action.EAST)
+    assert w.agents_positions == [(0, 1)]
+
+
+def test_available_actions_python(api):  # [P] test_available_actions
+    A = api.Action
+    world = api.World(
+        """
+@ @ L0S @  @
+@ .  .  .  @
+@ X  .  S0 @
+@ X  .  S1 @
+@ @  @  @  @
+"""
+    )
+    world.reset()
+    av = world.available_actions()
+    assert sorted(av[0]) == sorted([A.NORTH, A.WEST, A.STAY])
+    assert sorted(av[1]) == sorted([A.WEST, A.STAY])
+
+
+# ----------------------------------------------------------------------------- get_state / set_state
+SMALL = """
+        S0 . G
+        X  . .
+    """
+
+
+def test_force_state_invalid_sizes(api):  # [R] :199, :228
+    w = api.World(SMALL)
+    w.reset()
+    with pytest.raises(api.InvalidWorldStateError, match="InvalidNumberOfAgents"):
+        w.set_state(api.WorldState([(1, 2), (0, 0)], [True]))
+    with pytest.raises(api.InvalidWorldStateError, match="InvalidNumberOfGems"):
+        w.set_state(api.WorldState([(1, 2)], [True, False]))
+
+
+def test_set_state_available_actions(api):  # [R] :303
+    A = api.Action
+    w = api.World(
+        """
+        .  . . @ . . . @ . X
+        .  @ . @ . @ . @ . @
+        S0 @ . . . @ . . . @
+    """
+    )
+    w.reset()
+    w.set_state(api.WorldState([(0, 0)], []))
+    assert sorted(w.available_actions()[0]) == sorted([A.SOUTH, A.STAY, A.EAST])
+
+
+def test_force_state(api):  # [R] test_force_state :456, test_force_end_state :473
+    w = api.World(SMALL)
+    w.reset()
+    w.set_state(api.WorldState([(1, 2)], [True]))
+    assert w.agents_positions[0] == (1, 2)
+    assert w.gems[0].is_collected
+    w.set_state(api.WorldState([(1, 0)], [True]))
+    assert w.agents_positions[0] == (1, 0)
+    assert w.gems[0].is_collected
+
+
+def test_force_state_agent_dies(api):  # [R] :490 ; [I] :230
+    w = api.World(
+        """
+        S0 S1 G
+        X  X L0W
+    """
+    )
+    w.reset()
+    w.set_state(api.WorldState([(1, 0), (1, 1)], [False], [True, False]))
+    assert w.agents[0].has_arrived
+    assert not w.agents[1].has_arrived
+    assert w.agents[1].is_dead
+
+
+def test_wrong_world_state(api):  # [R] :527 ; [P] test_set_invalid_state_dead
+    w = api.World(
+        """
+        S0 L0S X
+        S1  .  X
+    """
+    )
+    w.reset()
+    with pytest.raises(api.InvalidWorldStateError, match="InvalidWorldState"):
+        w.set_state(api.WorldState([(0, 0), (1, 1)], []))
+    w = api.World("S0 L0S X\nS1  .  X")
+    with pytest.raises(api.InvalidWorldStateError):
+        w.set_state(api.WorldState([(0, 0), (0, 1)], [], [True, True]))
+
+
+def test_force_state_agents_have_exited(api):  # [I] :182
+    w = api.World(SMALL)
+    w.reset()
+    events = w.set_state(api.WorldState([(1, 0)], [True]))
+    assert all(a.has_arrived for a in w.agents)
+    assert events == [api.WorldEvent(api.EventType.AGENT_EXIT, 0)]
+
+
+def test_force_wrong_state_check_laser_not_blocked(api):  # [I] :209
+    w = api.World(
+        """
+        S1  S0 X
+        L0E  G  X
+    """
+    )
+    w.reset()
+    with pytest.raises(api.InvalidWorldStateError, match="InvalidAgentPosition"):
+        w.set_state(api.WorldState([(1, 1), (1, 0)], [True]))
+    assert all(l.is_on for l in w.lasers)
+    assert all(not g.is_collected for g in w.gems)
+
+
+def test_set_invalid_state_restores_positions(api):  # [I] test_set_invalid_state :254
+    w = api.World(
+        """
+        S0 S1 X
+        @  @  X
+    """
+    )
+    w.reset()
+    with pytest.raises(api.InvalidWorldStateError, match="InvalidAgentPosition"):
+        w.set_state(api.WorldState([(1, 0), (1, 1)], []))
+    assert w.agents_positions == [(0, 0), (0, 1)]
+
+
+def test_world_state_dead_agents(api):  # [I] :538
+    w = api.World(
+        """
+    S0 . G
+    V  . X
+    """
+    )
+    w.reset()
+    assert w.get_state().agents_alive[0]
+    w.step([api.Action.SOUTH])
+    state = w.get_state()
+    assert not state.agents_alive[0]
+    w.reset()
+    w.set_state(state)
+    assert not w.agents[0].is_alive
+
+
+def test_get_state(api):  # [P]
+    world = api.World("S0 G X")
+    world.reset()
+    state = world.get_state()
+    assert state.agents_positions == [(0, 0)] and state.gems_collected == [False]
+    world.step([api.Action.EAST])
+    state = world.get_state()
+    assert state.agents_positions == [(0, 1)] and state.gems_collected == [True]
+
+
+def test_set_state(api):  # [P]
+    world = api.World("S0 G X")
+    world.reset()
+    world.step([api.Action.EAST])
+    events = world.set_state(api.WorldState([(0, 0)], [False]))
+    assert world.agents_positions == [(0, 0)]
+    assert world.gems_collected == 0
+    assert len(events) == 0
+    events = world.set_state(api.WorldState([(0, 2)], [True]))
+    assert world.agents_positions == [(0, 2)]
+    assert world.gems_collected == 1
+    assert len(events) == 1
+    assert events[0].agent_id == 0
+    assert events[0].event_type == api.EventType.AGENT_EXIT
+
+
+def test_set_invalid_state(api):  # [P]
+    world = api.World(
+        """
+        S1  S0 X
+        L0E  G  X"""
+    )
+    world.reset()
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_state(api.WorldState([(0, 0), (0, 1)], [True, True]))
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_state(api.WorldState([(0, 0)], [True]))
+    with pytest.raises(IndexError):
+        world.set_state(api.WorldState([(10, 1), (1, 0)], [True]))
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_state(api.WorldState([(1, 1), (1, 0)], [True]))
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_state(api.WorldState([(0, 0), (0, 0)], [True]))
+
+
+def test_set_state_agent_dead(api):  # [P]
+    world = api.World("S0 G X")
+    world.reset()
+    world.set_state(api.WorldState([(0, 0)], [False], [False]))
+    assert not world.agents[0].is_alive
+
+
+def test_world_state_hash_eq(api):  # [P] test_world_state_hash_eq, _dead, _neq
+    world = api.World("S0 G X")
+    world.reset()
+    s1, s2 = world.get_state(), world.get_state()
+    assert hash(s1) == hash(s2) and s1 == s2
+    a = api.WorldState([(0, 0)], [False], [True])
+    b = api.WorldState([(0, 0)], [False], [False])
+    assert a != b and hash(a) != hash(b)
+    assert api.WorldState([(0, 0)], [False]) != api.WorldState([(0, 1)], [False])
+
+
+def test_world_state_constructor(api):  # [P]
+    assert all(api.WorldState([(0, 0)], [False]).agents_alive)
+    assert api.WorldState([(0, 0), (1, 1)], [True], [False, True]).agents_alive == [False, True]
+
+
+def test_state_from_to_array(api):  # [P] — exact vectors (pyworld_state.rs:79-132)
+    s = api.WorldState([(0, 0)], [False])
+    assert list(s.as_array()) == [0.0, 0.0, 0.0, 1.0]
+    assert api.WorldState.from_array([0.0, 0.0, 0.0, 1.0], 1, 1) == s
+    s = api.WorldState([(25, 17), (10, 30)], [True, False], agents_alive=[True, False])
+    expected = [25.0, 17.0, 10.0, 30.0, 1.0, 0.0, 1.0, 0.0]
+    assert list(s.as_array()) == expected
+    assert s.as_array().dtype.name == "float32"
+    assert api.WorldState.from_array(expected, 2, 2) == s
+    with pytest.raises(ValueError):
+        api.WorldState.from_array(expected, 2, 1)
+
+
+def test_world_n_agents(api):  # [P]
+    assert api.World("S0 S1 X X").n_agents == 2
+    assert api.World.level(6).n_agents == 4
+
+
+def test_world_tiles(api):  # [P]
+    w = api.World("S0 . X")
+    assert w.start_pos == [(0, 0)]
+    assert w.random_start_pos == [[(0, 0)]]
+    assert w.exit_pos == [(0, 2)]
