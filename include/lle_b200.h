@@ -1,0 +1,198 @@
+/* lle_b200 — C ABI of the B200-native batched `World` step.
+ *
+ * This is the drop-in boundary for the hot path of yamoling/lle: the functions below are what the
+ * reference's FFI would bind to replace its single-world engine calls by a batched device path.
+ * Each entry point cites the reference interface it stands in for (paths relative to the reference
+ * repository).  Plain pointers and sizes only; no C++/torch types.  A `lle_vec` is externally
+ * synchronised (one caller at a time, one stream), like the reference's `Arc<Mutex<World>>`
+ * (src/bindings/world/pyworld.rs:69-82).
+ *
+ * All functions return a status: 0 on success, otherwise one of the LLE_* codes; the message is
+ * available from lle_last_error() (thread-local).
+ */
+#ifndef LLE_B200_H
+#define LLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LLE_API __attribute__((visibility("default")))
+#else
+#define LLE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes.  1..99 mirror ParseError (src/core/parsing/errors.rs:5-70), 101..110 mirror
+ * RuntimeWorldError (src/core/errors.rs:6-45) as mapped to Python exceptions in
+ * src/bindings/pyexceptions.rs:43-183. */
+enum {
+    LLE_OK = 0,
+    LLE_PARSE_EMPTY_WORLD = 1,
+    LLE_PARSE_NO_AGENTS = 2,
+    LLE_PARSE_INVALID_TILE = 3,
+    LLE_PARSE_INVALID_FILE_NAME = 4,
+    LLE_PARSE_INVALID_LEVEL = 5,
+    LLE_PARSE_NOT_ENOUGH_EXITS = 6,
+    LLE_PARSE_NOT_ENOUGH_STARTS = 7,
+    LLE_PARSE_DUPLICATE_START = 8,
+    LLE_PARSE_INCONSISTENT_DIMENSIONS = 9,
+    LLE_PARSE_INVALID_LASER_SOURCE_AGENT_ID = 10,
+    LLE_PARSE_INVALID_AGENT_ID = 11,
+    LLE_PARSE_INVALID_DIRECTION = 12,
+    LLE_PARSE_AGENT_WITHOUT_START = 13,
+    LLE_PARSE_UNSUPPORTED = 20,
+    LLE_LIMIT_EXCEEDED = 21,
+    LLE_RT_INVALID_ACTION = 101,
+    LLE_RT_INVALID_NUMBER_OF_GEMS = 102,
+    LLE_RT_INVALID_NUMBER_OF_AGENTS = 103,
+    LLE_RT_INVALID_AGENT_POSITION = 104,
+    LLE_RT_OUT_OF_WORLD_POSITION = 105,
+    LLE_RT_INVALID_NUMBER_OF_ACTIONS = 106,
+    LLE_RT_INVALID_WORLD_STATE = 107,
+    LLE_RT_DONE = 110,
+    LLE_INDEX_ERROR = 201,
+    LLE_INVALID_ARGUMENT = 202,
+    LLE_CUDA_ERROR = 300,
+    LLE_NO_DEVICE = 301
+};
+
+/* ---- per-env error byte written to lle_vec_buffers.err by step / set_state */
+enum {
+    LLE_ENV_OK = 0,
+    LLE_ENV_INVALID_ACTION = 1,     /* world.rs:444-453 : the env is left untouched              */
+    LLE_ENV_DONE = 2,               /* env.py:166-167   : stepping a done env without auto-reset  */
+    LLE_ENV_STATE_DUPLICATE = 3,    /* world.rs:529-534                                           */
+    LLE_ENV_STATE_OUT_OF_WORLD = 4, /* world.rs:536-540                                           */
+    LLE_ENV_STATE_NOT_WALKABLE = 5, /* world.rs:556-568 : previous state restored                 */
+    LLE_ENV_STATE_MISMATCH = 6      /* world.rs:588-594 : env left modified, as in the reference  */
+};
+
+typedef struct lle_map lle_map; /* a compiled, immutable map (host object)         */
+typedef struct lle_vec lle_vec; /* N independent worlds resident on one CUDA device */
+
+LLE_API const char* lle_last_error(void);
+/* Library / build identification, e.g. "lle_b200 0.1 sm_100a". */
+LLE_API const char* lle_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Maps.  Replaces `World::try_from(&str)` / `parse` (src/core/world.rs:629-643,
+ * src/core/parsing/mod.rs:14-21, parser_v1.rs:132-175, world_config.rs:107-250) and
+ * `World::get_level` (world.rs:599-608).
+ * ---------------------------------------------------------------------------------------------- */
+LLE_API int lle_map_parse(const char* text, size_t len, lle_map** out);
+LLE_API int lle_map_level(int level, lle_map** out); /* 1..6, embedded like src/core/levels.rs:1-8 */
+LLE_API void lle_map_free(lle_map* map);
+
+typedef struct {
+    int32_t height, width, n_agents, n_gems, n_sources, n_channels; /* n_channels = 2*n_agents + 4 */
+    int32_t n_exits, n_walls, n_voids, n_laser_cells, n_lasers;     /* n_lasers = len(World::lasers()) */
+    int32_t obs_invalid;  /* a laser colour indexes past the last channel: the reference's Layered raises IndexError */
+    int32_t max_beam_len;
+    uint64_t gem_toplevel; /* bit g: gem g is not under a beam (World::n_gems_collected counts only those, world.rs:265-275) */
+} lle_map_info;
+LLE_API int lle_map_get_info(const lle_map* map, lle_map_info* out);
+
+/* Position lists as (i, j) pairs: World::{walls, void_positions, exits_positions, gems_positions,
+ * starts} (world.rs:125-127, 236-238, 289-303) and the laser cells. Returns the count via *n. */
+enum { LLE_POS_WALLS = 0, LLE_POS_VOIDS = 1, LLE_POS_EXITS = 2, LLE_POS_GEMS = 3, LLE_POS_STARTS = 4, LLE_POS_LASER_CELLS = 5 };
+LLE_API int lle_map_positions(const lle_map* map, int kind, int32_t* out_ij, int32_t cap, int32_t* n);
+/* World::sources() (world.rs:141-149): 7 ints per source: i, j, agent_id, direction(0 N,1 E,2 S,3 W), enabled, laser_id, beam_len */
+LLE_API int lle_map_sources(const lle_map* map, int32_t* out, int32_t cap, int32_t* n);
+/* World::lasers() (world.rs:159-172): 7 ints per laser tile: i, j, laser_id, agent_id, direction, beam index, offset in beam */
+LLE_API int lle_map_lasers(const lle_map* map, int32_t* out, int32_t cap, int32_t* n);
+/* The map text the map was compiled from (World::world_string for unmodified maps). */
+LLE_API const char* lle_map_text(const lle_map* map);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched worlds.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t device;          /* CUDA ordinal                                                           */
+    int32_t reward_dim;      /* 1 = SingleObjective, 4 = MultiObjective (reward_strategy.py:53, :88)  */
+    int32_t walkable_lasers; /* LLE(walkable_lasers=...), env.py:84, :146-163                          */
+    int32_t auto_reset;      /* reset a done env inside the step that finished it (not in the reference) */
+    int32_t lle_semantics;   /* 1: LLE.step rules (done envs refuse to step, env.py:166-167); 0: raw World */
+    int32_t write_obs;       /* 0 skips the layered observation (state/avail/reward still written)     */
+    uint64_t seed;           /* Philox key for device-sampled actions                                  */
+    uint64_t env_id_base;    /* global id of env 0 (sharding over GPUs keeps streams independent of the GPU count) */
+} lle_vec_options;
+LLE_API void lle_vec_default_options(lle_vec_options* opts);
+
+/* All maps must share (height, width, n_agents, n_gems).  map_of_env may be NULL (every env uses maps[0]). */
+LLE_API int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* map_of_env, int64_t n_envs,
+                   const lle_vec_options* opts, lle_vec** out);
+LLE_API int lle_vec_destroy(lle_vec* vec);
+
+/* Device pointers of the per-step outputs (valid until lle_vec_destroy).  Layouts, C-contiguous:
+ *   obs      f32 [N, obs_stride]   first C*H*W floats of a row = LayeredPadded.observe()[0] (observations.py:254-266);
+ *                                  obs_stride = C*H*W rounded up to 4 floats; the agent dimension of the
+ *                                  reference's (A,C,H,W) result is a stride-0 repeat of this block (np.tile).
+ *   state    f32 [N, 3A+G]         PyWorldState::as_array (pyworld_state.rs:79-101)
+ *   avail    u8  [N, A, 5]         LLE.available_actions (env.py:146-163), indexed by Action value
+ *   reward   f32 [N, reward_dim]   reward_strategy.py:58-75 / :90-109
+ *   done     u8  [N]               LLE.compute_done (env.py:253-254) of the transition just taken
+ *   events   u8  [N, A]            bits 0-1: event of the first move_agents pass (0 none, 1 AgentExit,
+ *                                  2 GemCollected, 3 AgentDied); bits 2-7: pass >= 2 in which the agent died
+ *                                  (world.rs:468-472).  Ordered list = sort by (pass, agent).
+ *   actions  i8  [N, A]            the joint action applied (sampled or supplied)
+ *   err      u8  [N]               LLE_ENV_* */
+typedef struct {
+    int64_t n_envs;
+    int32_t n_agents, n_gems, n_channels, height, width, reward_dim, state_dim, n_beams_max;
+    int64_t obs_stride; /* floats */
+    float* obs;
+    float* state;
+    uint8_t* avail;
+    float* reward;
+    uint8_t* done;
+    uint8_t* events;
+    int8_t* actions;
+    uint8_t* err;
+} lle_vec_buffers;
+LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
+
+/* World::reset / LLE.reset (world.rs:411-432, env.py:191-203) for every env, or for the envs whose byte in
+ * `mask_dev` (device, u8[N]) is non-zero.  Rewrites obs/state/avail; clears reward/done/events/err of those envs. */
+LLE_API int lle_vec_reset(lle_vec* vec, const uint8_t* mask_dev, void* cuda_stream);
+
+/* World::step + LLE.step (world.rs:435-475, env.py:165-189) for every env in one kernel launch.
+ * actions_dev: device i8[N, A] of Action values, or NULL to sample uniformly among the available
+ * actions with Philox4x32-10 (key = seed, counter = (env_id_base+env, step, agent/4)). */
+LLE_API int lle_vec_step(lle_vec* vec, const int8_t* actions_dev, void* cuda_stream);
+
+/* Same step, host-facing: copies `actions_host` (i8[N,A], pinned for async behaviour; NULL = device sampling)
+ * to the device, steps, and copies reward (f32[N,reward_dim]) and done (u8[N]) back, then synchronises the
+ * stream.  The observation stays resident in HBM (zero-copy DLPack hand-off to the policy). */
+LLE_API int lle_vec_step_host(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* cuda_stream);
+
+/* World::set_state / LLE.set_state (world.rs:515-597, env.py:208-216) for every env.
+ *   pos_dev i32[N,A,2], gems_dev u8[N,G], alive_dev u8[N,A] (device).  Per-env failures are reported in err. */
+LLE_API int lle_vec_set_state(lle_vec* vec, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* cuda_stream);
+
+/* Raw engine state (the part of the reference's world that WorldState does not carry), unpacked on the
+ * device into caller-provided device arrays; any pointer may be NULL.
+ *   pos i16[N,A,2]; alive/arrived/slot u8[N,A] (Agent.dead/arrived, tile slot, agent.rs:6-10, tile.rs:86-99);
+ *   beam_on u64[N,n_beams_max] (bit k = LaserBeam.beam[k], laser.rs:16); collected u64[N]; counters u8[N,3] = n_arrived, n_deads, done */
+LLE_API int lle_vec_export_raw(lle_vec* vec, int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
+                       uint64_t* collected, uint8_t* counters, void* cuda_stream);
+
+/* Step counter used as the Philox counter word (incremented by every lle_vec_step). */
+LLE_API int lle_vec_get_step_count(lle_vec* vec, uint64_t* out);
+LLE_API int lle_vec_set_step_count(lle_vec* vec, uint64_t value);
+
+/* Number of kernels this library launched since the vec was created (bench.py's `gpu_launches`). */
+LLE_API int lle_vec_launch_count(lle_vec* vec, uint64_t* out);
+
+/* Average device time (ms, CUDA events on the launching stream) of the step kernels launched between
+ * lle_vec_timing_begin and lle_vec_timing_end; *launches receives how many were timed. */
+LLE_API int lle_vec_timing_begin(lle_vec* vec, void* cuda_stream);
+LLE_API int lle_vec_timing_end(lle_vec* vec, void* cuda_stream, float* total_ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLE_B200_H */

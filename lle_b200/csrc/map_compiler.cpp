@@ -1,0 +1,266 @@
+#include "map_compiler.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cstring>
+#include <sstream>
+
+namespace lle {
+namespace {
+
+struct Token {
+    char kind;  // '.', 'G', '@', 'X', 'V', 'S', 'L'
+    int id;     // agent id for S / L
+    int dir;    // 0 N, 1 E, 2 S, 3 W for L
+};
+
+// Rust's `str::parse::<usize>()`: ASCII digits with an optional leading '+'
+bool parse_usize(const std::string& s, int& out) {
+    size_t k = (!s.empty() && s[0] == '+') ? 1 : 0;
+    if (k >= s.size()) return false;
+    long v = 0;
+    for (; k < s.size(); ++k) {
+        if (s[k] < '0' || s[k] > '9') return false;
+        v = v * 10 + (s[k] - '0');
+        if (v > 1000000) return false;
+    }
+    out = (int)v;
+    return true;
+}
+
+const int DI[4] = {-1, 0, 1, 0};  // N E S W (direction.rs:20-27)
+const int DJ[4] = {0, 1, 0, -1};
+
+size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+}  // namespace
+
+CompiledMap compile_map(const std::string& text) {
+    CompiledMap cm;
+    cm.text = text;
+
+    // ---- grammar (parser_v1.rs:132-175): lines, trimmed, blank lines skipped, whitespace-separated tokens
+    std::vector<std::vector<Token>> rows;
+    {
+        std::istringstream lines(text);
+        std::string line;
+        int width = -1;
+        std::vector<Cell> first_start;
+        while (std::getline(lines, line)) {
+            std::istringstream toks(line);
+            std::string t;
+            std::vector<Token> row;
+            while (toks >> t) {
+                Token tok{(char)std::toupper((unsigned char)t[0]), -1, -1};
+                switch (tok.kind) {
+                    case '.': case 'G': case '@': case 'X': case 'V': break;
+                    case 'S': {
+                        if (!parse_usize(t.substr(1), tok.id))
+                            throw MapError(LLE_PARSE_INVALID_AGENT_ID, "InvalidAgentId { given_agent_id: \"" + t.substr(1) + "\" }");
+                        // a second start for the same agent is an error at the token (parser_v1.rs:27-44)
+                        if ((int)first_start.size() <= tok.id) first_start.resize(tok.id + 1, Cell{-1, -1});
+                        Cell here{(int)rows.size(), (int)row.size()};
+                        if (first_start[tok.id].i >= 0)
+                            throw MapError(LLE_PARSE_DUPLICATE_START,
+                                           "DuplicateStartTile { agent_id: " + std::to_string(tok.id) + ", start1: (" +
+                                               std::to_string(first_start[tok.id].i) + ", " + std::to_string(first_start[tok.id].j) +
+                                               "), start2: (" + std::to_string(here.i) + ", " + std::to_string(here.j) + ") }");
+                        first_start[tok.id] = here;
+                        break;
+                    }
+                    case 'L': {
+                        switch (std::tolower((unsigned char)t.back())) {
+                            case 'n': tok.dir = 0; break;
+                            case 'e': tok.dir = 1; break;
+                            case 's': tok.dir = 2; break;
+                            case 'w': tok.dir = 3; break;
+                            default:  // the reference unwraps the direction and panics (laser_config.rs:20)
+                                throw MapError(LLE_PARSE_INVALID_DIRECTION, "InvalidDirection { given: \"" + t + "\" }");
+                        }
+                        std::string id = t.size() >= 2 ? t.substr(1, t.size() - 2) : std::string();
+                        if (!parse_usize(id, tok.id))
+                            throw MapError(LLE_PARSE_INVALID_AGENT_ID, "InvalidAgentId { given_agent_id: \"" + id + "\" }");
+                        break;
+                    }
+                    default:
+                        throw MapError(LLE_PARSE_INVALID_TILE, "InvalidTile { tile_str: \"" + t + "\", line: " +
+                                                                  std::to_string(rows.size()) + ", col: " + std::to_string(row.size()) + " }");
+                }
+                row.push_back(tok);
+            }
+            if (row.empty()) continue;
+            if (width < 0) width = (int)row.size();
+            if ((int)row.size() != width)
+                throw MapError(LLE_PARSE_INCONSISTENT_DIMENSIONS,
+                               "InconsistentDimensions { expected_n_cols: " + std::to_string(width) + ", actual_n_cols: " +
+                                   std::to_string(row.size()) + ", row: " + std::to_string(rows.size()) + " }");
+            rows.push_back(std::move(row));
+        }
+    }
+    if (rows.empty()) throw MapError(LLE_PARSE_EMPTY_WORLD, "EmptyWorld");
+    const int H = (int)rows.size(), W = (int)rows[0].size();
+
+    // ---- row-major collection (parser_v1.rs:147-161)
+    std::vector<std::vector<Cell>> starts;  // candidate starts per agent (<= 1 in v1)
+    for (int i = 0; i < H; ++i) {
+        for (int j = 0; j < W; ++j) {
+            const Token& t = rows[i][j];
+            Cell c{i, j};
+            switch (t.kind) {
+                case 'G': cm.gems.push_back(c); break;
+                case '@': cm.walls.push_back(c); break;
+                case 'X': cm.exits.push_back(c); break;
+                case 'V': cm.voids.push_back(c); break;
+                case 'S':
+                    if ((int)starts.size() <= t.id) starts.resize(t.id + 1);
+                    starts[t.id].push_back(c);
+                    break;
+                case 'L':
+                    cm.sources.push_back(SourceInfo{c, t.id, t.dir, (int)cm.sources.size(), 0, true});
+                    cm.walls.push_back(c);  // a source is also a wall (parser_v1.rs:22-25)
+                    break;
+                default: break;
+            }
+        }
+    }
+    // ---- pre_validate (world_config.rs:124-148)
+    const int A = (int)starts.size();
+    if (A == 0) throw MapError(LLE_PARSE_NO_AGENTS, "NoAgents");
+    if ((int)cm.exits.size() < A)
+        throw MapError(LLE_PARSE_NOT_ENOUGH_EXITS, "NotEnoughExitTiles { n_starts: " + std::to_string(A) +
+                                                       ", n_exits: " + std::to_string(cm.exits.size()) + " }");
+
+    // ---- base tile plane (world_config.rs:176-199)
+    std::vector<uint16_t> tiles((size_t)H * W, LLE_T_FLOOR);
+    for (size_t g = 0; g < cm.gems.size(); ++g) tiles[cm.gems[g].i * W + cm.gems[g].j] = (uint16_t)(LLE_T_GEM | (g << 8));
+    for (auto& c : cm.exits) tiles[c.i * W + c.j] = LLE_T_EXIT;
+    for (auto& c : cm.voids) tiles[c.i * W + c.j] = LLE_T_VOID;
+    for (auto& c : cm.walls) tiles[c.i * W + c.j] = LLE_T_WALL;
+
+    // ---- beams and start pruning (world_config.rs:203-250), sources in laser_id order
+    std::vector<std::vector<std::pair<int, int>>> cell_beams((size_t)H * W);  // (beam, offset), inner first
+    for (auto& s : cm.sources) {
+        int i = s.pos.i + DI[s.direction], j = s.pos.j + DJ[s.direction];
+        std::vector<Cell> cells;
+        while (i >= 0 && j >= 0 && i < H && j < W && (tiles[i * W + j] & 7u) != LLE_T_WALL) {
+            cells.push_back(Cell{i, j});
+            i += DI[s.direction];
+            j += DJ[s.direction];
+        }
+        s.len = (int)cells.size();
+        bool shielded = false;  // `is_blocked`: from the owner's single start on, the beam is cut at reset
+        for (int k = 0; k < s.len; ++k) {
+            const Cell c = cells[k];
+            if (s.colour < A && starts[s.colour].size() == 1 && starts[s.colour][0] == c) shielded = true;
+            if (!shielded)
+                for (int a = 0; a < A; ++a)
+                    if (a != s.colour) starts[a].erase(std::remove(starts[a].begin(), starts[a].end(), c), starts[a].end());
+            cell_beams[c.i * W + c.j].push_back({s.laser_id, k});
+        }
+    }
+    // ---- post_validate (world_config.rs:150-170)
+    for (int a = 0; a < A; ++a)
+        if (starts[a].empty())
+            throw MapError(LLE_PARSE_AGENT_WITHOUT_START, "AgentWithoutStart { agent_id: " + std::to_string(a) + " }");
+    for (int a = 0; a < A; ++a) {
+        if (starts[a].size() != 1) throw MapError(LLE_PARSE_UNSUPPORTED, "random start positions are not supported");
+        cm.starts.push_back(starts[a][0]);
+    }
+
+    // ---- device-format limits
+    const int G = (int)cm.gems.size(), NB = (int)cm.sources.size();
+    if (A > LLE_MAX_AGENTS || G > LLE_MAX_GEMS || NB > LLE_MAX_BEAMS || H > 256 || W > 256)
+        throw MapError(LLE_LIMIT_EXCEEDED, "map exceeds the device format (agents<=32, gems<=64, sources<=64, H,W<=256)");
+    for (auto& s : cm.sources) {
+        if (s.len > LLE_MAX_BEAM_LEN) throw MapError(LLE_LIMIT_EXCEEDED, "beam longer than 64 cells");
+        if (s.colour > 254) throw MapError(LLE_LIMIT_EXCEEDED, "laser colour above 254");
+        cm.max_beam_len = std::max(cm.max_beam_len, s.len);
+    }
+    cm.H = H; cm.W = W; cm.A = A; cm.G = G; cm.NB = NB;
+    const int C = 2 * A + 4;  // observations.py:205-211
+    cm.C = C;
+    const int LASER_0 = A, WALL = 2 * A, VOID = WALL + 1, GEM = WALL + 2, EXIT = WALL + 3, HW = H * W;
+
+    // ---- lasers listing: the outermost laser of a cell and the one directly under it (world.rs:159-172)
+    std::vector<uint64_t> vis(NB, 0);
+    for (int c = 0; c < HW; ++c) {
+        auto& lst = cell_beams[c];
+        if (lst.empty()) continue;
+        cm.laser_cells.push_back(Cell{c / W, c % W});
+        for (int n = 0; n < 2 && n < (int)lst.size(); ++n) {
+            auto [b, k] = lst[lst.size() - 1 - n];  // later source wraps earlier ones (world_config.rs:233-245)
+            vis[b] |= 1ull << k;
+            cm.lasers.push_back(LaserTileInfo{Cell{c / W, c % W}, b, cm.sources[b].colour, cm.sources[b].direction, b, k});
+        }
+    }
+
+    // ---- layered static plane (observations.py:216-237): wall, void, exit, then sources = -1
+    std::vector<float> stat((size_t)C * HW, 0.0f);
+    bool obs_invalid = false;
+    for (auto& c : cm.walls) stat[(size_t)WALL * HW + c.i * W + c.j] = 1.0f;
+    for (auto& c : cm.voids) stat[(size_t)VOID * HW + c.i * W + c.j] = 1.0f;
+    for (auto& c : cm.exits) stat[(size_t)EXIT * HW + c.i * W + c.j] = 1.0f;
+    for (auto& s : cm.sources) {
+        int ch = LASER_0 + s.colour;
+        if (ch >= C) { obs_invalid = true; continue; }  // numpy IndexError in the reference
+        stat[(size_t)ch * HW + s.pos.i * W + s.pos.j] = -1.0f;
+    }
+    // ---- dynamic cells (observations.py:256-263)
+    std::vector<LlePatch> patch;
+    for (auto& l : cm.lasers) {
+        int ch = LASER_0 + l.colour;
+        if (ch >= C) { obs_invalid = true; continue; }
+        uint32_t idx = (uint32_t)(ch * HW + l.pos.i * W + l.pos.j);
+        patch.push_back(LlePatch{idx, (uint8_t)l.beam, (uint8_t)l.offset, (int8_t)stat[idx], 0});
+    }
+    for (int g = 0; g < G; ++g) {
+        uint32_t idx = (uint32_t)(GEM * HW + cm.gems[g].i * W + cm.gems[g].j);
+        patch.push_back(LlePatch{idx, 0xFF, (uint8_t)g, (int8_t)stat[idx], 0});
+    }
+    std::stable_sort(patch.begin(), patch.end(), [](const LlePatch& x, const LlePatch& y) { return x.idx < y.idx; });
+
+    // ---- blob
+    LleMapHeader h;
+    std::memset(&h, 0, sizeof h);
+    h.H = H; h.W = W; h.A = A; h.G = G; h.NB = NB; h.C = C;
+    h.n_patch = (int)patch.size();
+    h.obs_floats = C * HW;
+    h.obs_invalid = obs_invalid;
+    size_t off = align16(sizeof(LleMapHeader));
+    h.tiles_off = (uint32_t)off;   off = align16(off + tiles.size() * sizeof(uint16_t));
+    h.beams_off = (uint32_t)off;   off = align16(off + (size_t)std::max(NB, 1) * sizeof(LleBeam));
+    h.patch_off = (uint32_t)off;   off = align16(off + std::max<size_t>(patch.size(), 1) * sizeof(LlePatch));
+    h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
+    h.blob_bytes = (uint32_t)off;
+    h.gem_toplevel = 0;
+    for (int g = 0; g < G; ++g) {
+        h.gem_pos[g] = (uint16_t)((cm.gems[g].i << 8) | cm.gems[g].j);
+        if (cell_beams[cm.gems[g].i * W + cm.gems[g].j].empty()) h.gem_toplevel |= 1ull << g;
+    }
+    for (int a = 0; a < A; ++a) h.start[a] = (uint16_t)((cm.starts[a].i << 8) | cm.starts[a].j);
+
+    cm.blob.assign(off, 0);
+    std::memcpy(cm.blob.data(), &h, sizeof h);
+    std::memcpy(cm.blob.data() + h.tiles_off, tiles.data(), tiles.size() * sizeof(uint16_t));
+    for (int b = 0; b < NB; ++b) {
+        const auto& s = cm.sources[b];
+        LleBeam bm;
+        std::memset(&bm, 0, sizeof bm);
+        bm.vis = vis[b];
+        bm.first_i = (uint16_t)(s.pos.i + DI[s.direction]);
+        bm.first_j = (uint16_t)(s.pos.j + DJ[s.direction]);
+        bm.di = (int8_t)DI[s.direction];
+        bm.dj = (int8_t)DJ[s.direction];
+        bm.len = (uint8_t)s.len;
+        bm.colour = (uint8_t)s.colour;
+        bm.enabled = 1;
+        bm.src_i = (uint8_t)s.pos.i;
+        bm.src_j = (uint8_t)s.pos.j;
+        std::memcpy(cm.blob.data() + h.beams_off + b * sizeof(LleBeam), &bm, sizeof bm);
+    }
+    if (!patch.empty()) std::memcpy(cm.blob.data() + h.patch_off, patch.data(), patch.size() * sizeof(LlePatch));
+    std::memcpy(cm.blob.data() + h.static_off, stat.data(), stat.size() * sizeof(float));
+    return cm;
+}
+
+}  // namespace lle

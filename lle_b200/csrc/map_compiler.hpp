@@ -1,0 +1,59 @@
+// Host map compiler: v1 map text -> immutable device tables (static_map.h).
+//
+// It restates, table-first, what the reference does when it builds a `World` from a string:
+//   grammar                    src/core/parsing/parser_v1.rs:132-175, laser_config.rs:19-35
+//   validation                 src/core/parsing/world_config.rs:124-170
+//   tile plane                 src/core/parsing/world_config.rs:176-199 (Floor, then gems, exits, voids, walls)
+//   beams + start pruning      src/core/parsing/world_config.rs:203-250
+//   layered static planes      python/lle/observations.py:216-237
+//   lasers listing (outer two) src/core/world.rs:159-172
+// Instead of wrapping tiles in nested `Laser` objects it records, per source, the beam's first cell,
+// direction and length, and per map a "patch table" of the observation cells that depend on state.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lle_b200.h"
+#include "static_map.h"
+
+namespace lle {
+
+// status codes: the LLE_* enum of include/lle_b200.h
+
+struct MapError : std::runtime_error {
+    int status;
+    MapError(int s, const std::string& msg) : std::runtime_error(msg), status(s) {}
+};
+
+struct Cell {
+    int i, j;
+    bool operator==(const Cell& o) const { return i == o.i && j == o.j; }
+};
+
+struct SourceInfo {
+    Cell pos;
+    int colour, direction /* 0 N, 1 E, 2 S, 3 W */, laser_id, len;
+    bool enabled;
+};
+
+struct LaserTileInfo {  // one entry of World::lasers() (outer two per cell), in row-major cell order
+    Cell pos;
+    int laser_id, colour, direction, beam, offset;
+};
+
+struct CompiledMap {
+    std::string text;
+    int H = 0, W = 0, A = 0, G = 0, NB = 0, C = 0;
+    std::vector<Cell> walls, voids, exits, gems, starts, laser_cells;
+    std::vector<SourceInfo> sources;
+    std::vector<LaserTileInfo> lasers;
+    int max_beam_len = 0;
+    std::vector<uint8_t> blob;  // LleMapHeader + tables, ready for HBM
+    const LleMapHeader& header() const { return *reinterpret_cast<const LleMapHeader*>(blob.data()); }
+};
+
+CompiledMap compile_map(const std::string& text);
+
+}  // namespace lle

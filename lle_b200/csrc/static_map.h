@@ -1,0 +1,89 @@
+// Static (per-map) tables and the dynamic per-env record shared by the host map compiler and the
+// sm_100a kernels.  Everything here is plain-old-data so it can be memcpy'd to HBM verbatim.
+//
+// Reference concepts (paths relative to the reference repository):
+//   base tile plane   <- WorldConfig::make_grid            src/core/parsing/world_config.rs:176-199
+//   beams             <- WorldConfig::laser_setup          src/core/parsing/world_config.rs:203-250
+//   LaserBeam state   <- `beam: RefCell<Vec<bool>>`        src/core/tiles/laser.rs:15-21   (here: one u64 mask)
+//   layered channels  <- LayeredPadded.__init__/_setup     python/lle/observations.py:199-237
+#pragma once
+#include <stdint.h>
+
+#define LLE_MAX_AGENTS 32  // alive/arrived/slot are u32 masks
+#define LLE_MAX_BEAMS 64   // per map
+#define LLE_MAX_GEMS 64    // one u64 collected mask
+#define LLE_MAX_BEAM_LEN 64
+
+// base tile kinds (low 3 bits of a tile word; gem index in bits 8..15)
+enum : uint16_t { LLE_T_FLOOR = 0, LLE_T_WALL = 1, LLE_T_GEM = 2, LLE_T_EXIT = 3, LLE_T_VOID = 4 };
+
+// One laser source and its beam.  Cell k of the beam is (first_i + k*di, first_j + k*dj), k < len.
+struct LleBeam {
+    uint64_t vis;      // bit k set <=> this beam's laser tile at cell k is listed by World::lasers()
+                       //   (only the two outermost lasers of a nested cell are, world.rs:159-172)
+    uint16_t first_i, first_j;
+    int8_t di, dj;
+    uint8_t len;       // 0..64 (0: the source faces a wall or the border)
+    uint8_t colour;    // agent id that blocks the beam; may be >= n_agents (world_config.rs:137-145)
+    uint8_t enabled;   // LaserBeam::is_enabled
+    uint8_t src_i, src_j;
+    uint8_t pad[5];
+};
+static_assert(sizeof(LleBeam) == 24, "LleBeam layout");
+
+// One dynamic cell of the layered observation other than the agents' own cells: a laser tile
+// (1.0 while its beam bit is on) or a gem (1.0 until collected).  `idx` is the float index inside
+// one env's (C,H,W) block; `stat` is what the static plane holds there (restored when the bit is off).
+struct LlePatch {
+    uint32_t idx;
+    uint8_t src;   // beam index, or 0xFF for a gem
+    uint8_t bit;   // offset k in the beam, or gem index
+    int8_t stat;   // -1, 0, 1
+    uint8_t pad;
+};
+static_assert(sizeof(LlePatch) == 8, "LlePatch layout");
+
+// Per-map header; all *_off are byte offsets from the start of the map blob (16-byte aligned).
+struct LleMapHeader {
+    int32_t H, W, A, G, NB, C;
+    int32_t n_patch;
+    int32_t obs_floats;       // C*H*W
+    uint32_t tiles_off;       // uint16_t[H*W]
+    uint32_t beams_off;       // LleBeam[NB]
+    uint32_t patch_off;       // LlePatch[n_patch]
+    uint32_t static_off;      // float[C*H*W]
+    uint32_t blob_bytes;
+    uint32_t obs_invalid;     // some LASER_0+colour >= C: the reference raises IndexError (observations.py:235)
+    uint64_t gem_toplevel;    // bit g set <=> gem g is NOT wrapped by a laser (world.rs:265-275, :550-554)
+    uint16_t start[LLE_MAX_AGENTS];   // packed position (i<<8 | j)
+    uint16_t gem_pos[LLE_MAX_GEMS];   // packed position, gems_positions order (parser_v1.rs:149)
+};
+
+// ---- dynamic per-env record: `n_words` 32-bit words, stored word-major (words[w*N + env]) so that a
+// warp reading word w of 32 consecutive envs issues one 128-byte transaction.
+//   [0, w_flags)                packed positions, two u16 per word
+//   [w_flags, w_gems)           A <= 8: alive | arrived<<8 | slot<<16 | misc<<24 ; else alive, arrived, slot, misc
+//                               misc = n_arrived(4 or 8 bits) | n_deads(sat.) | done   (see step_core.cuh)
+//   [w_gems, w_on)              collected mask (0, 1 or 2 words)
+//   [w_on, n_words)             beam on-masks, 1 word per beam when every beam is <= 32 cells, else 2
+struct LleStateLayout {
+    int32_t n_words, w_flags, w_gems, w_on;
+    int32_t gem_words, on_words;  // per-gem-mask words (0/1/2), words per beam (1/2)
+    int32_t wide_flags;           // A > 8
+    int32_t pad;
+};
+
+#ifdef __cplusplus
+static inline LleStateLayout lle_state_layout(int A, int G, int NB, int max_beam_len) {
+    LleStateLayout L;
+    L.wide_flags = A > 8;
+    L.w_flags = (A + 1) / 2;
+    L.w_gems = L.w_flags + (L.wide_flags ? 4 : 1);
+    L.gem_words = G == 0 ? 0 : (G <= 32 ? 1 : 2);
+    L.w_on = L.w_gems + L.gem_words;
+    L.on_words = max_beam_len <= 32 ? 1 : 2;
+    L.n_words = L.w_on + NB * L.on_words;
+    L.pad = 0;
+    return L;
+}
+#endif

@@ -1,0 +1,486 @@
+// lle_b200 — host side of the C ABI (include/lle_b200.h): map handles, device buffers, launch
+// configuration and the kernel launches.  The kernel itself lives in vec_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lle_b200.h"
+#include "levels_embedded.inc"
+#include "map_compiler.hpp"
+#include "vec_kernels.cuh"
+
+namespace lle {
+
+// Unpacks the per-env records for white-box comparisons (tests) and `get_state`-style host queries.
+__global__ void lle_export_raw_kernel(const uint32_t* words, LleStateLayout L, int64_t N, int64_t N_pad, int A, int NBmax,
+                                      int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
+                                      uint64_t* collected, uint8_t* counters) {
+    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= N) return;
+    auto ld = [&](int w) { return words[(int64_t)w * N_pad + env]; };
+    uint32_t al, ar, sl, na, nd, dn;
+    if (!L.wide_flags) {
+        uint32_t f = ld(L.w_flags);
+        al = f & 0xFF; ar = (f >> 8) & 0xFF; sl = (f >> 16) & 0xFF; na = (f >> 24) & 0xF; nd = (f >> 28) & 7; dn = f >> 31;
+    } else {
+        al = ld(L.w_flags); ar = ld(L.w_flags + 1); sl = ld(L.w_flags + 2);
+        uint32_t m = ld(L.w_flags + 3);
+        na = m & 0xFF; nd = (m >> 8) & 0xFF; dn = (m >> 16) & 1;
+    }
+    for (int a = 0; a < A; ++a) {
+        uint32_t w = ld(a >> 1);
+        uint32_t pp = (a & 1) ? (w >> 16) : (w & 0xFFFF);
+        if (pos) { pos[(env * A + a) * 2] = (int16_t)(pp >> 8); pos[(env * A + a) * 2 + 1] = (int16_t)(pp & 0xFF); }
+        if (alive) alive[env * A + a] = (al >> a) & 1;
+        if (arrived) arrived[env * A + a] = (ar >> a) & 1;
+        if (slot) slot[env * A + a] = (sl >> a) & 1;
+    }
+    if (collected) {
+        uint64_t c = 0;
+        if (L.gem_words >= 1) c = ld(L.w_gems);
+        if (L.gem_words == 2) c |= (uint64_t)ld(L.w_gems + 1) << 32;
+        collected[env] = c;
+    }
+    if (beam_on) {
+        for (int b = 0; b < NBmax; ++b) {
+            uint64_t v = ld(L.w_on + b * L.on_words);
+            if (L.on_words == 2) v |= (uint64_t)ld(L.w_on + b * 2 + 1) << 32;
+            beam_on[env * NBmax + b] = v;
+        }
+    }
+    if (counters) { counters[env * 3] = (uint8_t)na; counters[env * 3 + 1] = (uint8_t)nd; counters[env * 3 + 2] = (uint8_t)dn; }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+thread_local std::string g_error;
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+
+#define LLE_CUDA(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? LLE_NO_DEVICE : LLE_CUDA_ERROR, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+    } while (0)
+
+#define LLE_DECL_BUCKET(A, NB)                                                                  \
+    cudaError_t launch_bucket_##A##_##NB(const KParams& p, int grid, size_t smem, cudaStream_t s); \
+    cudaError_t occupancy_bucket_##A##_##NB(size_t smem, int* blocks);
+LLE_DECL_BUCKET(4, 4)
+LLE_DECL_BUCKET(8, 8)
+LLE_DECL_BUCKET(8, 16)
+LLE_DECL_BUCKET(16, 16)
+
+}  // namespace lle
+
+using namespace lle;
+
+struct lle_map {
+    CompiledMap cm;
+};
+
+struct lle_vec {
+    lle_vec_options opts;
+    int device = 0;
+    int64_t N = 0, N_pad = 0;
+    int A = 0, G = 0, NBmax = 0, C = 0, H = 0, W = 0, S = 0, R = 1, max_beam_len = 0;
+    int bucket = 0;  // index into kBuckets
+    LleStateLayout L;
+    // device memory
+    std::vector<uint8_t*> d_blobs;
+    const uint8_t** d_blob_table = nullptr;
+    int32_t* d_map_of_env = nullptr;
+    uint32_t* d_words = nullptr;
+    float* d_obs = nullptr;
+    float* d_state = nullptr;
+    uint8_t* d_avail = nullptr;
+    float* d_reward = nullptr;
+    uint8_t* d_done = nullptr;
+    uint8_t* d_events = nullptr;
+    int8_t* d_actions = nullptr;
+    uint8_t* d_err = nullptr;
+    uint32_t* d_sched = nullptr;
+    int8_t* d_actions_stage = nullptr;  // for step_host
+    int64_t obs_stride = 0;
+    // launch configuration
+    int grid = 0, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, desc_words = 0, warp_smem = 0;
+    size_t smem = 0;
+    uint64_t t = 0, launches = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t timing_launches0 = 0;
+};
+
+namespace {
+
+int desc_words_of(int bucket) { return (kBuckets[bucket].amax + 1) / 2 + 2 + 2 * kBuckets[bucket].nbmax; }
+
+cudaError_t launch(lle_vec* v, const KParams& p, cudaStream_t s) {
+    switch (v->bucket) {
+        case 0: return launch_bucket_4_4(p, v->grid, v->smem, s);
+        case 1: return launch_bucket_8_8(p, v->grid, v->smem, s);
+        case 2: return launch_bucket_8_16(p, v->grid, v->smem, s);
+        default: return launch_bucket_16_16(p, v->grid, v->smem, s);
+    }
+}
+cudaError_t occupancy(int bucket, size_t smem, int* blocks) {
+    switch (bucket) {
+        case 0: return occupancy_bucket_4_4(smem, blocks);
+        case 1: return occupancy_bucket_8_8(smem, blocks);
+        case 2: return occupancy_bucket_8_16(smem, blocks);
+        default: return occupancy_bucket_16_16(smem, blocks);
+    }
+}
+
+KParams base_params(lle_vec* v) {
+    KParams p;
+    std::memset(&p, 0, sizeof p);
+    p.blobs = v->d_blob_table;
+    p.map_of_env = v->d_map_of_env;
+    p.words = v->d_words;
+    p.L = v->L;
+    p.N = v->N;
+    p.N_pad = v->N_pad;
+    p.A = v->A; p.G = v->G; p.NBmax = v->NBmax; p.C = v->C; p.H = v->H; p.W = v->W; p.S = v->S; p.R = v->R;
+    p.HW = v->H * v->W;
+    p.obs = v->d_obs; p.obs_stride = v->obs_stride;
+    p.state = v->d_state; p.avail = v->d_avail; p.reward = v->d_reward; p.done = v->d_done;
+    p.events = v->d_events; p.actions = v->d_actions; p.err = v->d_err;
+    p.seed = v->opts.seed; p.env_id_base = v->opts.env_id_base; p.t = v->t;
+    p.auto_reset = v->opts.auto_reset; p.lle_semantics = v->opts.lle_semantics;
+    p.walkable = v->opts.walkable_lasers; p.write_obs = v->opts.write_obs;
+    p.E = v->E; p.n_chunks = v->n_chunks; p.chunk_floats = v->chunk_floats; p.tile_floats = v->tile_floats;
+    p.warp_smem_bytes = v->warp_smem;
+    p.sched = v->d_sched;
+    p.n_units = (uint32_t)(v->N_pad / 32);
+    p.n_warps_total = (uint32_t)(v->grid * kWarps);
+    return p;
+}
+
+template <class T>
+cudaError_t dalloc(T** ptr, size_t count) {
+    cudaError_t e = cudaMalloc((void**)ptr, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*ptr, 0, std::max<size_t>(count, 1) * sizeof(T));
+    return e;
+}
+
+int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
+
+}  // namespace
+
+extern "C" {
+
+const char* lle_last_error(void) { return g_error.c_str(); }
+const char* lle_version(void) { return "lle_b200 0.1 (sm_100a)"; }
+
+int lle_map_parse(const char* text, size_t len, lle_map** out) {
+    if (!text || !out) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    try {
+        auto m = std::make_unique<lle_map>();
+        m->cm = compile_map(std::string(text, len));
+        *out = m.release();
+        return LLE_OK;
+    } catch (const MapError& e) {
+        return fail(e.status, e.what());
+    } catch (const std::exception& e) {
+        return fail(LLE_INVALID_ARGUMENT, e.what());
+    }
+}
+
+int lle_map_level(int level, lle_map** out) {
+    if (level < 1 || level > 6)  // world.rs:599-606
+        return fail(LLE_PARSE_INVALID_LEVEL, "InvalidLevel { asked: " + std::to_string(level) + ", min: 1, max: 6 }");
+    const char* text = kEmbeddedLevels[level - 1];
+    return lle_map_parse(text, std::strlen(text), out);
+}
+
+void lle_map_free(lle_map* map) { delete map; }
+
+int lle_map_get_info(const lle_map* map, lle_map_info* out) {
+    if (!map || !out) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    const CompiledMap& c = map->cm;
+    std::memset(out, 0, sizeof *out);
+    out->height = c.H; out->width = c.W; out->n_agents = c.A; out->n_gems = c.G; out->n_sources = c.NB; out->n_channels = c.C;
+    out->n_exits = (int)c.exits.size(); out->n_walls = (int)c.walls.size(); out->n_voids = (int)c.voids.size();
+    out->n_laser_cells = (int)c.laser_cells.size(); out->n_lasers = (int)c.lasers.size();
+    out->obs_invalid = (int)c.header().obs_invalid;
+    out->max_beam_len = c.max_beam_len;
+    out->gem_toplevel = c.header().gem_toplevel;
+    return LLE_OK;
+}
+
+int lle_map_positions(const lle_map* map, int kind, int32_t* out_ij, int32_t cap, int32_t* n) {
+    if (!map || !n) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    const CompiledMap& c = map->cm;
+    const std::vector<Cell>* v;
+    switch (kind) {
+        case LLE_POS_WALLS: v = &c.walls; break;
+        case LLE_POS_VOIDS: v = &c.voids; break;
+        case LLE_POS_EXITS: v = &c.exits; break;
+        case LLE_POS_GEMS: v = &c.gems; break;
+        case LLE_POS_STARTS: v = &c.starts; break;
+        case LLE_POS_LASER_CELLS: v = &c.laser_cells; break;
+        default: return fail(LLE_INVALID_ARGUMENT, "unknown position kind");
+    }
+    *n = (int32_t)v->size();
+    for (int k = 0; k < (int)v->size() && k < cap && out_ij; ++k) {
+        out_ij[2 * k] = (*v)[k].i;
+        out_ij[2 * k + 1] = (*v)[k].j;
+    }
+    return LLE_OK;
+}
+
+int lle_map_sources(const lle_map* map, int32_t* out, int32_t cap, int32_t* n) {
+    if (!map || !n) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    const auto& s = map->cm.sources;
+    *n = (int32_t)s.size();
+    for (int k = 0; k < (int)s.size() && k < cap && out; ++k) {
+        int32_t* o = out + 7 * k;
+        o[0] = s[k].pos.i; o[1] = s[k].pos.j; o[2] = s[k].colour; o[3] = s[k].direction; o[4] = s[k].enabled; o[5] = s[k].laser_id; o[6] = s[k].len;
+    }
+    return LLE_OK;
+}
+
+int lle_map_lasers(const lle_map* map, int32_t* out, int32_t cap, int32_t* n) {
+    if (!map || !n) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    const auto& l = map->cm.lasers;
+    *n = (int32_t)l.size();
+    for (int k = 0; k < (int)l.size() && k < cap && out; ++k) {
+        int32_t* o = out + 7 * k;
+        o[0] = l[k].pos.i; o[1] = l[k].pos.j; o[2] = l[k].laser_id; o[3] = l[k].colour; o[4] = l[k].direction; o[5] = l[k].beam; o[6] = l[k].offset;
+    }
+    return LLE_OK;
+}
+
+const char* lle_map_text(const lle_map* map) { return map ? map->cm.text.c_str() : ""; }
+
+void lle_vec_default_options(lle_vec_options* o) {
+    std::memset(o, 0, sizeof *o);
+    o->device = 0; o->reward_dim = 1; o->walkable_lasers = 1; o->auto_reset = 1; o->lle_semantics = 1; o->write_obs = 1;
+    o->seed = 0; o->env_id_base = 0;
+}
+
+int lle_vec_destroy(lle_vec* v) {
+    if (!v) return LLE_OK;
+    cudaSetDevice(v->device);
+    for (auto* b : v->d_blobs) cudaFree(b);
+    cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_words); cudaFree(v->d_obs); cudaFree(v->d_state);
+    cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
+    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_actions_stage);
+    if (v->ev0) cudaEventDestroy(v->ev0);
+    if (v->ev1) cudaEventDestroy(v->ev1);
+    delete v;
+    return LLE_OK;
+}
+
+int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* map_of_env, int64_t n_envs,
+                   const lle_vec_options* opts, lle_vec** out) {
+    if (!maps || n_maps < 1 || n_envs < 1 || !opts || !out) return fail(LLE_INVALID_ARGUMENT, "bad argument");
+    if (opts->reward_dim != 1 && opts->reward_dim != 4) return fail(LLE_INVALID_ARGUMENT, "reward_dim must be 1 or 4");
+    auto v = std::unique_ptr<lle_vec, int (*)(lle_vec*)>(new lle_vec(), lle_vec_destroy);
+    v->opts = *opts;
+    v->device = opts->device;
+    const CompiledMap& m0 = maps[0]->cm;
+    v->A = m0.A; v->G = m0.G; v->C = m0.C; v->H = m0.H; v->W = m0.W; v->R = opts->reward_dim;
+    v->S = 3 * m0.A + m0.G;
+    for (int k = 0; k < n_maps; ++k) {
+        const CompiledMap& m = maps[k]->cm;
+        if (m.A != v->A || m.G != v->G || m.H != v->H || m.W != v->W)
+            return fail(LLE_INVALID_ARGUMENT, "all maps of a vec must share (height, width, n_agents, n_gems)");
+        v->NBmax = std::max(v->NBmax, m.NB);
+        v->max_beam_len = std::max(v->max_beam_len, m.max_beam_len);
+    }
+    if (map_of_env)
+        for (int64_t e = 0; e < n_envs; ++e)
+            if (map_of_env[e] < 0 || map_of_env[e] >= n_maps) return fail(LLE_INVALID_ARGUMENT, "map_of_env out of range");
+    v->bucket = -1;
+    for (int b = 0; b < kNumBuckets; ++b)
+        if (v->A <= kBuckets[b].amax && v->NBmax <= kBuckets[b].nbmax) { v->bucket = b; break; }
+    if (v->bucket < 0)
+        return fail(LLE_LIMIT_EXCEEDED, "the device path supports up to 16 agents and 16 laser sources per map");
+    v->N = n_envs;
+    v->N_pad = (n_envs + 31) / 32 * 32;
+    v->L = lle_state_layout(v->A, v->G, v->NBmax, v->max_beam_len);
+    v->obs_stride = ((int64_t)v->C * v->H * v->W + 3) / 4 * 4;
+    v->desc_words = desc_words_of(v->bucket);
+
+    LLE_CUDA(cudaSetDevice(v->device));
+    cudaDeviceProp prop;
+    LLE_CUDA(cudaGetDeviceProperties(&prop, v->device));
+
+    // ---- observation tiling: one bulk store should move ~4-8 KB; tiles are double-buffered per warp
+    const int64_t stride = v->obs_stride;
+    const int64_t kTileTargetFloats = 2048, kTileMaxFloats = 6144;  // 8 KB target, 24 KB cap per buffer
+    if (stride <= kTileMaxFloats) {
+        v->n_chunks = 1;
+        v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
+        v->chunk_floats = (int)stride;
+        v->tile_floats = (int)(v->E * stride);
+    } else {
+        v->E = 1;
+        v->chunk_floats = (int)kTileMaxFloats / 2;  // 12 KB chunks
+        v->n_chunks = (int)((stride + v->chunk_floats - 1) / v->chunk_floats);
+        v->tile_floats = v->chunk_floats;
+    }
+    {
+        size_t bytes = (size_t)2 * v->tile_floats * 4;          // tiles
+        bytes += (size_t)v->desc_words * 32 * 4;                // unit descriptors
+        bytes += (size_t)2 * v->E * v->desc_words * 4;          // applied descriptors
+        bytes += (size_t)(2 * v->E + 2) * 4;                    // tags
+        v->warp_smem = (int)((bytes + 127) / 128 * 128);
+        v->smem = (size_t)v->warp_smem * kWarps;
+    }
+    int blocks_per_sm = 0;
+    LLE_CUDA(occupancy(v->bucket, v->smem, &blocks_per_sm));
+    if (blocks_per_sm < 1) return fail(LLE_CUDA_ERROR, "kernel does not fit on an SM");
+    const int64_t n_units = v->N_pad / 32;
+    v->grid = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * blocks_per_sm, (n_units + kWarps - 1) / kWarps);
+    v->grid = std::max(v->grid, 1);
+
+    // ---- device memory
+    std::vector<const uint8_t*> table;
+    for (int k = 0; k < n_maps; ++k) {
+        const auto& blob = maps[k]->cm.blob;
+        uint8_t* d = nullptr;
+        LLE_CUDA(cudaMalloc((void**)&d, blob.size()));
+        v->d_blobs.push_back(d);
+        LLE_CUDA(cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        table.push_back(d);
+    }
+    LLE_CUDA(cudaMalloc((void**)&v->d_blob_table, table.size() * sizeof(uint8_t*)));
+    LLE_CUDA(cudaMemcpy((void*)v->d_blob_table, table.data(), table.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice));
+    if (map_of_env && n_maps > 1) {
+        std::vector<int32_t> padded((size_t)v->N_pad, 0);
+        std::copy(map_of_env, map_of_env + n_envs, padded.begin());
+        for (int64_t e = n_envs; e < v->N_pad; ++e) padded[(size_t)e] = map_of_env[n_envs - 1];
+        LLE_CUDA(dalloc(&v->d_map_of_env, (size_t)v->N_pad));
+        LLE_CUDA(cudaMemcpy(v->d_map_of_env, padded.data(), padded.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    } else if (map_of_env && n_maps == 1) {
+        v->d_map_of_env = nullptr;
+    }
+    const size_t Np = (size_t)v->N_pad;
+    LLE_CUDA(dalloc(&v->d_words, (size_t)v->L.n_words * Np));
+    if (opts->write_obs) LLE_CUDA(dalloc(&v->d_obs, (size_t)v->obs_stride * Np));
+    LLE_CUDA(dalloc(&v->d_state, (size_t)v->S * Np));
+    LLE_CUDA(dalloc(&v->d_avail, (size_t)v->A * 5 * Np));
+    LLE_CUDA(dalloc(&v->d_reward, (size_t)v->R * Np));
+    LLE_CUDA(dalloc(&v->d_done, Np));
+    LLE_CUDA(dalloc(&v->d_events, (size_t)v->A * Np));
+    LLE_CUDA(dalloc(&v->d_actions, (size_t)v->A * Np));
+    LLE_CUDA(dalloc(&v->d_err, Np));
+    LLE_CUDA(dalloc(&v->d_sched, 2));
+    LLE_CUDA(dalloc(&v->d_actions_stage, (size_t)v->A * Np));
+    LLE_CUDA(cudaEventCreate(&v->ev0));
+    LLE_CUDA(cudaEventCreate(&v->ev1));
+
+    // World::new resets itself (world.rs:82)
+    int rc = lle_vec_reset(v.get(), nullptr, nullptr);
+    if (rc != LLE_OK) return rc;
+    LLE_CUDA(cudaDeviceSynchronize());
+    *out = v.release();
+    return LLE_OK;
+}
+
+int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
+    if (!v || !out) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    std::memset(out, 0, sizeof *out);
+    out->n_envs = v->N;
+    out->n_agents = v->A; out->n_gems = v->G; out->n_channels = v->C; out->height = v->H; out->width = v->W;
+    out->reward_dim = v->R; out->state_dim = v->S; out->n_beams_max = v->NBmax;
+    out->obs_stride = v->obs_stride;
+    out->obs = v->d_obs; out->state = v->d_state; out->avail = v->d_avail; out->reward = v->d_reward; out->done = v->d_done;
+    out->events = v->d_events; out->actions = v->d_actions; out->err = v->d_err;
+    return LLE_OK;
+}
+
+int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    LLE_CUDA(cudaSetDevice(v->device));
+    KParams p = base_params(v);
+    p.mode = MODE_RESET;
+    p.reset_mask = mask_dev;
+    LLE_CUDA(launch(v, p, (cudaStream_t)stream));
+    v->launches++;
+    return LLE_OK;
+}
+
+int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    LLE_CUDA(cudaSetDevice(v->device));
+    KParams p = base_params(v);
+    p.mode = MODE_STEP;
+    p.actions_in = actions_dev;
+    LLE_CUDA(launch(v, p, (cudaStream_t)stream));
+    v->launches++;
+    v->t++;
+    return LLE_OK;
+}
+
+int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    LLE_CUDA(cudaSetDevice(v->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int8_t* dev_actions = nullptr;
+    if (actions_host) {
+        LLE_CUDA(cudaMemcpyAsync(v->d_actions_stage, actions_host, (size_t)v->N * v->A, cudaMemcpyHostToDevice, s));
+        dev_actions = v->d_actions_stage;
+    }
+    int rc = lle_vec_step(v, dev_actions, stream);
+    if (rc != LLE_OK) return rc;
+    if (reward_host) LLE_CUDA(cudaMemcpyAsync(reward_host, v->d_reward, (size_t)v->N * v->R * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (done_host) LLE_CUDA(cudaMemcpyAsync(done_host, v->d_done, (size_t)v->N, cudaMemcpyDeviceToHost, s));
+    LLE_CUDA(cudaStreamSynchronize(s));
+    return LLE_OK;
+}
+
+int lle_vec_set_state(lle_vec* v, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* stream) {
+    if (!v || !pos_dev || !alive_dev || (v->G > 0 && !gems_dev)) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    LLE_CUDA(cudaSetDevice(v->device));
+    KParams p = base_params(v);
+    p.mode = MODE_SET_STATE;
+    p.ss_pos = pos_dev; p.ss_gems = gems_dev; p.ss_alive = alive_dev;
+    LLE_CUDA(launch(v, p, (cudaStream_t)stream));
+    v->launches++;
+    return LLE_OK;
+}
+
+int lle_vec_export_raw(lle_vec* v, int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
+                       uint64_t* collected, uint8_t* counters, void* stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    LLE_CUDA(cudaSetDevice(v->device));
+    int threads = 128;
+    int blocks = (int)((v->N + threads - 1) / threads);
+    lle_export_raw_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(v->d_words, v->L, v->N, v->N_pad, v->A, v->NBmax,
+                                                                      pos, alive, arrived, slot, v->NBmax ? beam_on : nullptr, collected, counters);
+    LLE_CUDA(cudaGetLastError());
+    v->launches++;
+    return LLE_OK;
+}
+
+int lle_vec_get_step_count(lle_vec* v, uint64_t* out) { if (!v || !out) return fail(LLE_INVALID_ARGUMENT, "null"); *out = v->t; return LLE_OK; }
+int lle_vec_set_step_count(lle_vec* v, uint64_t value) { if (!v) return fail(LLE_INVALID_ARGUMENT, "null"); v->t = value; return LLE_OK; }
+int lle_vec_launch_count(lle_vec* v, uint64_t* out) { if (!v || !out) return fail(LLE_INVALID_ARGUMENT, "null"); *out = v->launches; return LLE_OK; }
+
+int lle_vec_timing_begin(lle_vec* v, void* stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    LLE_CUDA(cudaSetDevice(v->device));
+    v->timing_launches0 = v->launches;
+    LLE_CUDA(cudaEventRecord(v->ev0, (cudaStream_t)stream));
+    return LLE_OK;
+}
+int lle_vec_timing_end(lle_vec* v, void* stream, float* total_ms, uint64_t* launches) {
+    if (!v || !total_ms) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    LLE_CUDA(cudaSetDevice(v->device));
+    LLE_CUDA(cudaEventRecord(v->ev1, (cudaStream_t)stream));
+    LLE_CUDA(cudaEventSynchronize(v->ev1));
+    LLE_CUDA(cudaEventElapsedTime(total_ms, v->ev0, v->ev1));
+    if (launches) *launches = v->launches - v->timing_launches0;
+    return LLE_OK;
+}
+
+}  // extern "C"

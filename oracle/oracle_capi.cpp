@@ -491,6 +491,29 @@ int lleo_vec_reset(void* p) {
         }
     });
 }
+// LLE.set_state on one env of the vec (events dropped); returns the oracle status code.
+int lleo_vec_set_state_env(void* p, long e, const long* pos, int n_agents, const uint8_t* gems, int n_gems,
+                           const uint8_t* alive) {
+    Vec& v = *(Vec*)p;
+    return guarded([&] {
+        WorldState s;
+        for (int a = 0; a < n_agents; ++a) {
+            // negative coordinates wrap to huge usize values in the reference's (usize, usize) positions
+            s.agents_positions.push_back(Position{(size_t)pos[2 * a], (size_t)pos[2 * a + 1]});
+            s.agents_alive.push_back(alive[a] != 0);
+        }
+        for (int g = 0; g < n_gems; ++g) s.gems_collected.push_back(gems[g] != 0);
+        v.envs[(size_t)e]->set_state(s);
+    });
+}
+// Re-export every env's outputs (after out-of-band mutations such as lleo_vec_set_state_env).
+void lleo_vec_refresh(void* p) {
+    Vec& v = *(Vec*)p;
+    for (size_t e = 0; e < v.N; ++e) {
+        v.done[e] = v.envs[e]->done;
+        v.export_env(e);
+    }
+}
 uint64_t lleo_vec_step_count(void* p) { return ((Vec*)p)->t; }
 void lleo_vec_set_step_count(void* p, uint64_t t) { ((Vec*)p)->t = t; }
 

@@ -12,9 +12,11 @@ import sys
 
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -46,6 +48,3 @@ def layouts():
         return json.load(f)
 
 
-def level_text(n: int) -> str:
-    with open(os.path.join(GOLDEN, "levels", f"lvl{n}")) as f:
-        return f.read()
