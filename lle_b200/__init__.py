@@ -1,0 +1,22 @@
+"""lle_b200 — B200-native batched implementation of the `World` step of yamoling/lle.
+
+Public surface (mirrors the reference's `lle` package for the accelerated path):
+    World, WorldState, Action, EventType, WorldEvent, LLE        single-world API (N = 1 on the device)
+    VecWorld, VecLLE, Map, level, from_str, from_file            batched API
+The package needs its CUDA extension (lle_b200/_native/liblle_b200.so, sm_100a) and a CUDA device;
+there is no CPU fallback.
+"""
+from .types import (Action, Agent, Direction, EventType, Gem, InvalidActionError, InvalidLevelError, InvalidWorldStateError,
+                    Laser, LaserSource, ParsingError, WorldEvent, WorldState)
+from ._native import LIB_PATH, lib as _load_native
+
+_load_native()  # fail loudly at import time if the extension is not built
+
+from .vec_world import Map, VecWorld  # noqa: E402
+from .world import LLE, Step, World, decode_events  # noqa: E402
+from .env import Builder, VecLLE, from_file, from_str, level  # noqa: E402
+
+__all__ = ["Action", "Agent", "Direction", "EventType", "Gem", "InvalidActionError", "InvalidLevelError",
+           "InvalidWorldStateError", "Laser", "LaserSource", "ParsingError", "WorldEvent", "WorldState", "Map", "VecWorld",
+           "World", "LLE", "Step", "VecLLE", "Builder", "level", "from_str", "from_file", "decode_events", "LIB_PATH"]
+__version__ = "0.1.0"

@@ -1,0 +1,110 @@
+"""ctypes binding of include/lle_b200.h (lle_b200/_native/liblle_b200.so).
+
+There is no CPU fallback: if the CUDA extension is missing or no CUDA device is usable, the product
+raises.  (The oracle under oracle/ is test infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .types import InvalidActionError, InvalidLevelError, InvalidWorldStateError, ParsingError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_native", "liblle_b200.so")
+
+SYMBOLS = [
+    "lle_last_error", "lle_version", "lle_map_parse", "lle_map_level", "lle_map_free", "lle_map_get_info",
+    "lle_map_positions", "lle_map_sources", "lle_map_lasers", "lle_map_text", "lle_vec_default_options", "lle_vec_create",
+    "lle_vec_destroy", "lle_vec_get_buffers", "lle_vec_reset", "lle_vec_step", "lle_vec_step_host", "lle_vec_set_state",
+    "lle_vec_export_raw", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
+    "lle_vec_timing_begin", "lle_vec_timing_end",
+]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("height", "width", "n_agents", "n_gems", "n_sources", "n_channels", "n_exits",
+                                          "n_walls", "n_voids", "n_laser_cells", "n_lasers", "obs_invalid", "max_beam_len")] + [
+        ("gem_toplevel", C.c_uint64)]
+
+
+class VecOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("device", "reward_dim", "walkable_lasers", "auto_reset", "lle_semantics", "write_obs")] + [
+        ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+class VecBuffers(C.Structure):
+    _fields_ = [("n_envs", C.c_int64)] + [(n, C.c_int32) for n in ("n_agents", "n_gems", "n_channels", "height", "width",
+                                                                   "reward_dim", "state_dim", "n_beams_max")] + [
+        ("obs_stride", C.c_int64), ("obs", C.c_void_p), ("state", C.c_void_p), ("avail", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the extension; fail loudly when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"lle_b200: the CUDA extension {LIB_PATH} is missing. Build it with `python -m lle_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name in SYMBOLS:
+        getattr(L, name)  # AttributeError if the library is stale
+    L.lle_last_error.restype = C.c_char_p
+    L.lle_version.restype = C.c_char_p
+    L.lle_map_text.restype = C.c_char_p
+    L.lle_map_text.argtypes = [C.c_void_p]
+    L.lle_map_free.argtypes = [C.c_void_p]
+    L.lle_map_free.restype = None
+    L.lle_vec_default_options.restype = None
+    L.lle_map_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.lle_map_level.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.lle_map_get_info.argtypes = [C.c_void_p, C.POINTER(MapInfo)]
+    L.lle_map_positions.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+    L.lle_map_sources.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+    L.lle_map_lasers.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+    L.lle_vec_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(VecOptions),
+                                 C.POINTER(C.c_void_p)]
+    L.lle_vec_destroy.argtypes = [C.c_void_p]
+    L.lle_vec_get_buffers.argtypes = [C.c_void_p, C.POINTER(VecBuffers)]
+    L.lle_vec_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lle_vec_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lle_vec_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lle_vec_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lle_vec_export_raw.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+    L.lle_vec_get_step_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.lle_vec_set_step_count.argtypes = [C.c_void_p, C.c_uint64]
+    L.lle_vec_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.lle_vec_timing_begin.argtypes = [C.c_void_p, C.c_void_p]
+    L.lle_vec_timing_end.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().lle_last_error().decode()
+
+
+def check(status: int):
+    """Map a status code to the exception the reference raises (src/bindings/pyexceptions.rs:43-183)."""
+    if status == 0:
+        return
+    msg = last_error()
+    if status == 5:
+        raise InvalidLevelError(msg)
+    if 1 <= status < 100:
+        raise ParsingError(msg)
+    if status == 101:
+        raise InvalidActionError(msg)
+    if status in (102, 103, 104, 107):
+        raise InvalidWorldStateError(msg)
+    if status in (105, 201):
+        raise IndexError(msg)
+    if status in (106, 110, 202):
+        raise ValueError(msg)
+    raise RuntimeError(f"lle_b200 error {status}: {msg}")

@@ -77,7 +77,7 @@ struct StepResult {
 // ---- record <-> registers ------------------------------------------------------------------------
 template <int AMAX, int NBMAX, class Load>
 LLE_HD void env_load(Env<AMAX, NBMAX>& e, const LleStateLayout& L, int A, int NB, Load&& ld) {
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int w = 0; w < (AMAX + 1) / 2; ++w) {
         if (w < L.w_flags) {
             uint32_t v = ld(w);
@@ -105,7 +105,7 @@ LLE_HD void env_load(Env<AMAX, NBMAX>& e, const LleStateLayout& L, int A, int NB
     e.collected = 0;
     if (L.gem_words >= 1) e.collected = ld(L.w_gems);
     if (L.gem_words == 2) e.collected |= (uint64_t)ld(L.w_gems + 1) << 32;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         e.on[b] = 0;
         if (b < NB) {
@@ -118,7 +118,7 @@ LLE_HD void env_load(Env<AMAX, NBMAX>& e, const LleStateLayout& L, int A, int NB
 
 template <int AMAX, int NBMAX, class Store>
 LLE_HD void env_store(const Env<AMAX, NBMAX>& e, const LleStateLayout& L, int A, int NB, Store&& st) {
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int w = 0; w < (AMAX + 1) / 2; ++w) {
         if (w < L.w_flags) {
             uint32_t v = e.pos[2 * w];
@@ -137,7 +137,7 @@ LLE_HD void env_store(const Env<AMAX, NBMAX>& e, const LleStateLayout& L, int A,
     }
     if (L.gem_words >= 1) st(L.w_gems, (uint32_t)e.collected);
     if (L.gem_words == 2) st(L.w_gems + 1, (uint32_t)(e.collected >> 32));
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         if (b < NB) {
             st(L.w_on + b * L.on_words, (uint32_t)e.on[b]);
@@ -153,7 +153,7 @@ LLE_HD void env_store(const Env<AMAX, NBMAX>& e, const LleStateLayout& L, int A,
 template <int AMAX, int NBMAX>
 LLE_HD void tile_leave(const MapView& m, Env<AMAX, NBMAX>& e, int a, int NB) {
     int i = e.pos[a] >> 8, j = e.pos[a] & 0xFF;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         if (b < NB) {
             const LleBeam bm = m.beams[b];
@@ -170,7 +170,7 @@ template <int AMAX, int NBMAX>
 LLE_HD void tile_pre_enter(const MapView& m, Env<AMAX, NBMAX>& e, int a, uint16_t p, int NB) {
     if (!((e.alive >> a) & 1u)) return;
     int i = p >> 8, j = p & 0xFF;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         if (b < NB) {
             const LleBeam bm = m.beams[b];
@@ -189,7 +189,7 @@ template <int AMAX, int NBMAX>
 LLE_HD uint32_t tile_enter(const MapView& m, Env<AMAX, NBMAX>& e, int a, uint16_t p, int NB) {
     int i = p >> 8, j = p & 0xFF;
     bool lethal = false;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         if (b < NB) {
             const LleBeam bm = m.beams[b];
@@ -236,7 +236,7 @@ LLE_HD uint32_t tile_enter(const MapView& m, Env<AMAX, NBMAX>& e, int a, uint16_
 // stays fully off; gem.rs:21-24).  Agents are NOT touched.
 template <int AMAX, int NBMAX>
 LLE_HD void tiles_reset(const MapView& m, Env<AMAX, NBMAX>& e, int NB) {
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         if (b < NB) {
             const LleBeam bm = m.beams[b];
@@ -258,12 +258,12 @@ LLE_HD void env_reset(const MapView& m, Env<AMAX, NBMAX>& e) {
     e.n_arrived = 0;
     e.n_deads = 0;
     e.done = 0;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) e.pos[a] = a < A ? m.hdr->start[a] : (uint16_t)0;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a)
         if (a < A) tile_pre_enter(m, e, a, e.pos[a], NB);
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a)
         if (a < A) (void)tile_enter(m, e, a, e.pos[a], NB);  // events are dropped (world.rs:428-430)
 }
@@ -283,7 +283,7 @@ LLE_HD uint32_t env_available(const MapView& m, const Env<AMAX, NBMAX>& e, int a
         if ((m.tiles[ti * W + tj] & 7u) == LLE_T_WALL) continue;  // Wall or LaserSource (tile.rs:63-73)
         uint16_t tp = (uint16_t)((ti << 8) | tj);
         bool occupied = false;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int o = 0; o < AMAX; ++o)
             if (o < A && ((e.slot >> o) & 1u) && e.pos[o] == tp) occupied = true;  // Tile::is_occupied
         if (!occupied) mask |= 1u << act;
@@ -303,7 +303,7 @@ LLE_HD uint32_t env_available_no_walk(const MapView& m, const Env<AMAX, NBMAX>& 
         if (!((mask >> act) & 1u)) continue;
         int ti = i + act_di(act), tj = j + act_dj(act);
         bool blocked = false;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int b = 0; b < NBMAX; ++b) {
             if (b < NB) {
                 const LleBeam bm = m.beams[b];
@@ -324,7 +324,7 @@ template <int AMAX, int NBMAX>
 LLE_HD StepResult env_step(const MapView& m, Env<AMAX, NBMAX>& e, const uint8_t* act, uint8_t* ev) {
     const int A = m.hdr->A, NB = m.hdr->NB;
     uint16_t np[AMAX];
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         np[a] = 0;
         if (a < A) {
@@ -336,13 +336,13 @@ LLE_HD StepResult env_step(const MapView& m, Env<AMAX, NBMAX>& e, const uint8_t*
     // vertex conflicts: every agent whose target is shared goes back to where it stands; repeat.
     for (;;) {
         uint32_t dup = 0;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a)
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
             for (int o = a + 1; o < AMAX; ++o)
                 if (o < A && np[a] == np[o]) dup |= (1u << a) | (1u << o);
         if (!dup) break;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a)
             if (a < A && ((dup >> a) & 1u)) np[a] = e.pos[a];
     }
@@ -351,13 +351,13 @@ LLE_HD StepResult env_step(const MapView& m, Env<AMAX, NBMAX>& e, const uint8_t*
     bool died;
     do {
         died = false;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a)
             if (a < A && ((e.alive >> a) & 1u)) tile_leave(m, e, a, NB);
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a)
             if (a < A) tile_pre_enter(m, e, a, np[a], NB);
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a) {
             if (a < A) {
                 uint32_t code = tile_enter(m, e, a, np[a], NB);
@@ -373,7 +373,7 @@ LLE_HD StepResult env_step(const MapView& m, Env<AMAX, NBMAX>& e, const uint8_t*
             }
         }
         if (pass == 1) {
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
             for (int a = 0; a < AMAX; ++a)
                 if (a < A) e.pos[a] = np[a];
         }
@@ -417,17 +417,17 @@ LLE_HD uint8_t set_state_apply(const MapView& m, Env<AMAX, NBMAX>& e, const int3
     const int A = m.hdr->A, NB = m.hdr->NB, W = m.hdr->W;
     tiles_reset(m, e, NB);
     e.collected = sg & m.hdr->gem_toplevel;  // only top-level Gem tiles can be force-collected (:550-554)
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         if (a < A) {
             if ((m.tiles[si[a] * W + sj[a]] & 7u) == LLE_T_WALL) return ERR_STATE_NOT_WALKABLE;  // :556-568
             tile_pre_enter(m, e, a, (uint16_t)((si[a] << 8) | sj[a]), NB);
         }
     }
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a)
         if (a < A) e.pos[a] = (uint16_t)((si[a] << 8) | sj[a]);  // :571
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         if (a < A) {
             e.alive |= 1u << a;  // agent.reset() (:578)
@@ -454,24 +454,24 @@ template <int AMAX, int NBMAX>
 LLE_HD uint8_t env_set_state(const MapView& m, Env<AMAX, NBMAX>& e, const int32_t* si, const int32_t* sj, uint64_t sg,
                              uint32_t sa, uint8_t* ev, bool lle_level) {
     const int A = m.hdr->A, H = m.hdr->H, W = m.hdr->W;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) ev[a] = 0;
     if (lle_level) {  // reward_strategy.reset() precedes world.set_state (env.py:213)
         e.n_arrived = 0;
         e.n_deads = 0;
     }
     // :529-534 duplicates, then :536-540 bounds (in that order)
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a)
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int o = a + 1; o < AMAX; ++o)
             if (o < A && si[a] == si[o] && sj[a] == sj[o]) return ERR_STATE_DUPLICATE;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a)
         if (a < A && (si[a] < 0 || sj[a] < 0 || si[a] >= H || sj[a] >= W)) return ERR_STATE_OUT_OF_WORLD;
     // current_state = self.get_state() (:541)
     int32_t ci[AMAX], cj[AMAX];
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         ci[a] = e.pos[a] >> 8;
         cj[a] = e.pos[a] & 0xFF;
@@ -484,7 +484,7 @@ LLE_HD uint8_t env_set_state(const MapView& m, Env<AMAX, NBMAX>& e, const int32_
         // self.set_state(&current_state).unwrap() (:563): the previous state is re-derived, events dropped
         uint8_t scratch[AMAX];
         StepResult r2{0, 0, 0, false};
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a) scratch[a] = 0;
         (void)set_state_apply(m, e, ci, cj, cg, ca, scratch, r2);
         return code;
@@ -502,7 +502,7 @@ LLE_HD uint8_t env_set_state(const MapView& m, Env<AMAX, NBMAX>& e, const int32_
 template <int AMAX, int NBMAX, class Put>
 LLE_HD void env_state_vector(const MapView& m, const Env<AMAX, NBMAX>& e, Put&& put) {
     const int A = m.hdr->A, G = m.hdr->G;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         if (a < A) {
             put(2 * a, (float)(e.pos[a] >> 8));

@@ -100,7 +100,7 @@ LLE_HD void desc_write(const Env<AMAX, NBMAX>& e, uint32_t* out, int stride) {
     }
     out[(D::PW + 0) * stride] = (uint32_t)e.collected;
     out[(D::PW + 1) * stride] = (uint32_t)(e.collected >> 32);
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int b = 0; b < NBMAX; ++b) {
         out[(D::PW + 2 + 2 * b) * stride] = (uint32_t)e.on[b];
         out[(D::PW + 3 + 2 * b) * stride] = (uint32_t)(e.on[b] >> 32);
@@ -117,7 +117,7 @@ LLE_HD void unit_logic(const KParams& p, int64_t env, const MapView& mv, Env<AMA
     uint8_t act[AMAX];
     float reward[4] = {0.f, 0.f, 0.f, 0.f};
     uint8_t err = ERR_OK;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         ev[a] = 0;
         act[a] = 4;
@@ -126,16 +126,16 @@ LLE_HD void unit_logic(const KParams& p, int64_t env, const MapView& mv, Env<AMA
 
     if (p.mode == MODE_STEP) {
         uint32_t av[AMAX];
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a) av[a] = a < A ? env_available(mv, e, a) : 16u;
         if (p.actions_in) {
             if (env < p.N) {  // padding worlds (env >= N) just STAY
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
                 for (int a = 0; a < AMAX; ++a)
                     if (a < A) act[a] = (uint8_t)p.actions_in[env * A + a];
             }
         } else {
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
             for (int q = 0; q < (AMAX + 3) / 4; ++q) {
                 if (q * 4 < A) {
                     uint32_t r[4];
@@ -151,7 +151,7 @@ LLE_HD void unit_logic(const KParams& p, int64_t env, const MapView& mv, Env<AMA
             err = ERR_DONE;
         } else {
             bool bad = false;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
             for (int a = 0; a < AMAX; ++a)
                 if (a < A && (act[a] > 4 || !((av[a] >> act[a]) & 1u))) bad = true;
             if (bad) {
@@ -170,7 +170,7 @@ LLE_HD void unit_logic(const KParams& p, int64_t env, const MapView& mv, Env<AMA
         int32_t si[AMAX], sj[AMAX];
         uint32_t sa = 0;
         uint64_t sg = 0;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a) {
             si[a] = sj[a] = 0;
             if (a < A) {
@@ -188,7 +188,7 @@ LLE_HD void unit_logic(const KParams& p, int64_t env, const MapView& mv, Env<AMA
         for (int k = 0; k < p.R; ++k) p.reward[env * p.R + k] = reward[k];
         p.done[env] = (uint8_t)e.done;
         p.err[env] = err;
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
         for (int a = 0; a < AMAX; ++a) {
             if (a < A) {
                 p.events[env * A + a] = ev[a];
@@ -202,7 +202,7 @@ LLE_HD void unit_logic(const KParams& p, int64_t env, const MapView& mv, Env<AMA
 
     env_store(e, p.L, A, NB, [&](int w, uint32_t v) { p.words[(int64_t)w * p.N_pad + env] = v; });
     env_state_vector(mv, e, [&](int k, float v) { p.state[env * p.S + k] = v; });
-#pragma unroll
+#pragma unroll(AMAX <= 8 ? 16 : 1)
     for (int a = 0; a < AMAX; ++a) {
         if (a < A) {
             uint32_t m = env_available(mv, e, a);

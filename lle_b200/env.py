@@ -1,0 +1,124 @@
+"""`VecLLE`: the batched counterpart of `lle.LLE` (python/lle/env/env.py) — what an RL loop uses.
+
+`lle_b200.level(6).n_envs(65536).build()` mirrors the reference's fluent builder
+(python/lle/env/builder.py:30-160) for the options that exist on the accelerated path.
+All per-step results are device tensors (zero-copy views, DLPack-exportable); nothing is copied to the host.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from .vec_world import Map, VecWorld
+
+
+class VecLLE:
+    """N lock-stepped `LLE` environments on one GPU.
+
+    step() semantics: reward / done / events describe the transition just taken; with auto_reset (default)
+    obs / state / available_actions are those of the freshly reset world when done is set.
+    """
+
+    def __init__(self, maps, n_envs: int, *, map_of_env: Sequence[int] | None = None, device=0, multi_objective: bool = False,
+                 walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True):
+        self.world = VecWorld(maps, n_envs, map_of_env=map_of_env, device=device, reward_dim=4 if multi_objective else 1,
+                              walkable_lasers=walkable_lasers, auto_reset=auto_reset, lle_semantics=True, write_obs=write_obs,
+                              seed=seed, env_id_base=env_id_base)
+        for m in self.world.maps:
+            if m.obs_invalid and write_obs:
+                raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
+        w = self.world
+        self.n_envs, self.n_agents, self.n_actions = w.n_envs, w.n_agents, 5
+        self.observation_shape = (w.n_channels, w.height, w.width)
+        self.state_shape = (w.state_dim,)
+        self.reward_dim = w.reward_dim
+
+    # tensors (views on device buffers)
+    obs = property(lambda self: self.world.obs)                      # (N, C, H, W)
+    obs_per_agent = property(lambda self: self.world.obs_per_agent)  # (N, A, C, H, W), stride-0 agent dim
+    state = property(lambda self: self.world.state)                  # (N, 3A+G)
+    available_actions = property(lambda self: self.world.avail)      # (N, A, 5) u8
+    reward = property(lambda self: self.world.reward)                # (N, reward_dim)
+    done = property(lambda self: self.world.done)                    # (N,) u8
+    events = property(lambda self: self.world.events)                # (N, A) u8
+    actions = property(lambda self: self.world.actions)              # (N, A) i8
+    err = property(lambda self: self.world.err)                      # (N,) u8
+
+    def reset(self, mask: torch.Tensor | None = None):
+        self.world.reset(mask)
+        return self.obs, self.state
+
+    def step(self, actions: torch.Tensor | None = None):
+        """actions: int8 (N, A) on the device, or None to sample uniformly among available actions on the GPU."""
+        self.world.step(actions)
+        return self.obs, self.state, self.reward, self.done
+
+    def dlpack(self, name: str):
+        return getattr(self, name).__dlpack__()
+
+
+class Builder:
+    """Subset of python/lle/env/builder.py that exists on the accelerated path."""
+
+    def __init__(self, maps):
+        self._maps = maps
+        self._kw = {}
+        self._n = 1
+
+    def n_envs(self, n: int):
+        self._n = int(n)
+        return self
+
+    def device(self, device):
+        self._kw["device"] = device
+        return self
+
+    def seed(self, seed: int):
+        self._kw["seed"] = int(seed)
+        return self
+
+    def multi_objective(self, enabled: bool = True):
+        self._kw["multi_objective"] = enabled
+        return self
+
+    def walkable_lasers(self, walkable: bool = True):
+        self._kw["walkable_lasers"] = walkable
+        return self
+
+    def auto_reset(self, enabled: bool = True):
+        self._kw["auto_reset"] = enabled
+        return self
+
+    def obs_type(self, obs_type: str):
+        if obs_type not in ("layered", "flattened"):
+            raise NotImplementedError(f"observation type {obs_type!r} is not on the accelerated path (layered / flattened are)")
+        return self
+
+    def state_type(self, state_type: str):
+        if state_type != "state":
+            raise NotImplementedError(f"state type {state_type!r} is not on the accelerated path")
+        return self
+
+    def death_strategy(self, strategy: str):
+        if strategy == "respawn":
+            raise NotImplementedError("Respawn strategy is not implemented yet")  # env.py:106-108
+        if strategy != "end":
+            raise ValueError(f"Unknown death strategy: {strategy}")
+        return self
+
+    def build(self) -> VecLLE:
+        return VecLLE(self._maps, self._n, **self._kw)
+
+
+def level(n: int) -> Builder:
+    return Builder(Map(level=n))
+
+
+def from_str(world_string: str) -> Builder:
+    return Builder(Map(world_string))
+
+
+def from_file(path: str) -> Builder:
+    with open(path) as f:
+        return Builder(Map(f.read()))

@@ -1,0 +1,159 @@
+"""Value types and exceptions of the reference's Python surface (python/lle/world/__init__.pyi,
+src/bindings/world/{pyaction,pyevent,pyworld_state}.rs, src/bindings/pyexceptions.rs)."""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+
+class Action(enum.IntEnum):
+    """src/action.rs:9-15 ; src/bindings/world/pyaction.rs."""
+
+    NORTH = 0
+    SOUTH = 1
+    EAST = 2
+    WEST = 3
+    STAY = 4
+
+    @property
+    def delta(self) -> tuple[int, int]:
+        return _DELTAS[int(self)]
+
+    def opposite(self) -> "Action":
+        return _OPPOSITE[self]
+
+    @staticmethod
+    def variants() -> list["Action"]:
+        return list(Action)
+
+    @staticmethod
+    def cardinality() -> int:
+        return 5
+
+
+_DELTAS = {0: (-1, 0), 1: (1, 0), 2: (0, 1), 3: (0, -1), 4: (0, 0)}
+_OPPOSITE = {Action.NORTH: Action.SOUTH, Action.SOUTH: Action.NORTH, Action.EAST: Action.WEST, Action.WEST: Action.EAST,
+             Action.STAY: Action.STAY}
+
+
+class Direction(enum.IntEnum):
+    """src/core/tiles/direction.rs:9-18 (numbering of include/lle_b200.h)."""
+
+    NORTH = 0
+    EAST = 1
+    SOUTH = 2
+    WEST = 3
+
+
+class EventType(enum.IntEnum):
+    """src/bindings/world/pyevent.rs:9-17."""
+
+    AGENT_EXIT = 0
+    GEM_COLLECTED = 1
+    AGENT_DIED = 2
+
+
+@dataclass(frozen=True)
+class WorldEvent:
+    event_type: EventType
+    agent_id: int
+
+
+class WorldState:
+    """src/bindings/world/pyworld_state.rs:53-132."""
+
+    def __init__(self, agents_positions, gems_collected, agents_alive=None):
+        self.agents_positions = [tuple(int(x) for x in p) for p in agents_positions]
+        self.gems_collected = [bool(g) for g in gems_collected]
+        self.agents_alive = ([True] * len(self.agents_positions) if agents_alive is None else [bool(a) for a in agents_alive])
+
+    def as_array(self) -> np.ndarray:
+        out = [float(x) for p in self.agents_positions for x in p]
+        out += [1.0 if g else 0.0 for g in self.gems_collected]
+        out += [1.0 if a else 0.0 for a in self.agents_alive]
+        return np.array(out, dtype=np.float32)
+
+    @staticmethod
+    def from_array(array, n_agents: int, n_gems: int) -> "WorldState":
+        array = list(array)
+        expected = n_agents * 3 + n_gems
+        if len(array) != expected:
+            raise ValueError(f"The array must have a length of {expected}.")
+        pos = [(int(array[2 * i]), int(array[2 * i + 1])) for i in range(n_agents)]
+        gems = [array[2 * n_agents + i] == 1.0 for i in range(n_gems)]
+        alive = [array[2 * n_agents + n_gems + i] == 1.0 for i in range(n_agents)]
+        return WorldState(pos, gems, alive)
+
+    def _key(self):
+        return (tuple(self.agents_positions), tuple(self.gems_collected), tuple(self.agents_alive))
+
+    def __eq__(self, other):
+        return isinstance(other, WorldState) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return f"WorldState(agents_positions={self.agents_positions}, gems_collected={self.gems_collected}, agents_alive={self.agents_alive})"
+
+
+@dataclass(frozen=True)
+class Agent:
+    num: int
+    is_dead: bool
+    has_arrived: bool
+
+    @property
+    def is_alive(self) -> bool:
+        return not self.is_dead
+
+
+@dataclass(frozen=True)
+class Gem:
+    pos: tuple
+    is_collected: bool
+
+
+@dataclass(frozen=True)
+class Laser:
+    """Snapshot of one laser tile, like PyLaser (src/bindings/tiles/pylaser.rs:44-54)."""
+
+    pos: tuple
+    laser_id: int
+    agent_id: int
+    direction: Direction
+    is_on: bool
+    is_enabled: bool
+
+    @property
+    def is_off(self) -> bool:
+        return not self.is_on
+
+
+@dataclass(frozen=True)
+class LaserSource:
+    pos: tuple
+    agent_id: int
+    direction: Direction
+    is_enabled: bool
+    laser_id: int
+    beam_len: int
+
+
+# ---- exceptions, src/bindings/pyexceptions.rs:43-183
+class InvalidWorldStateError(ValueError):
+    pass
+
+
+class InvalidActionError(ValueError):
+    pass
+
+
+class ParsingError(ValueError):
+    pass
+
+
+class InvalidLevelError(ValueError):
+    pass

@@ -1,0 +1,244 @@
+"""`VecWorld`: N independent worlds resident on one B200, stepped by one fused kernel launch.
+
+Host-side mirror of the reference's `World` for a batch (src/bindings/world/pyworld.rs:144-626): the
+same operations (`reset`, `step`, `available_actions`, `get_state`, `set_state`), but every result is a
+zero-copy torch view of a device buffer owned by the C-ABI object (include/lle_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import MapInfo, VecBuffers, VecOptions, check, lib
+from .types import Direction, InvalidLevelError, LaserSource
+
+
+class Map:
+    """A compiled map (lle_map).  Replaces `World::try_from(&str)` up to, but excluding, the dynamic state."""
+
+    def __init__(self, text: str | None = None, *, level: int | None = None):
+        h = C.c_void_p()
+        if level is not None:
+            if not isinstance(level, int) or not 1 <= level <= 6:
+                raise InvalidLevelError(f"InvalidLevel {{ asked: {level}, min: 1, max: 6 }}")
+            check(lib().lle_map_level(level, C.byref(h)))
+        else:
+            raw = text.encode()
+            check(lib().lle_map_parse(raw, len(raw), C.byref(h)))
+        self._h = h
+        info = MapInfo()
+        check(lib().lle_map_get_info(self._h, C.byref(info)))
+        self.info = info
+        self.height, self.width = info.height, info.width
+        self.n_agents, self.n_gems, self.n_sources, self.n_channels = info.n_agents, info.n_gems, info.n_sources, info.n_channels
+        self.obs_invalid = bool(info.obs_invalid)
+        self.gem_toplevel = int(info.gem_toplevel)
+        self.text = lib().lle_map_text(self._h).decode()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib().lle_map_free(h)
+            self._h = None
+
+    def positions(self, kind: int) -> list[tuple[int, int]]:
+        n = C.c_int32(0)
+        check(lib().lle_map_positions(self._h, kind, None, 0, C.byref(n)))
+        buf = (C.c_int32 * max(1, 2 * n.value))()
+        check(lib().lle_map_positions(self._h, kind, buf, n.value, C.byref(n)))
+        return [(buf[2 * k], buf[2 * k + 1]) for k in range(n.value)]
+
+    walls = property(lambda self: self.positions(0))
+    voids = property(lambda self: self.positions(1))
+    exits = property(lambda self: self.positions(2))
+    gems = property(lambda self: self.positions(3))
+    starts = property(lambda self: self.positions(4))
+    laser_cells = property(lambda self: self.positions(5))
+
+    def sources(self) -> list[LaserSource]:
+        n = C.c_int32(0)
+        check(lib().lle_map_sources(self._h, None, 0, C.byref(n)))
+        buf = (C.c_int32 * max(1, 7 * n.value))()
+        check(lib().lle_map_sources(self._h, buf, n.value, C.byref(n)))
+        return [LaserSource((buf[7 * k], buf[7 * k + 1]), buf[7 * k + 2], Direction(buf[7 * k + 3]), bool(buf[7 * k + 4]),
+                            buf[7 * k + 5], buf[7 * k + 6]) for k in range(n.value)]
+
+    def laser_tiles(self) -> list[tuple[tuple[int, int], int, int, Direction, int, int]]:
+        """(pos, laser_id, agent_id, direction, beam, offset) of every tile listed by World::lasers()."""
+        n = C.c_int32(0)
+        check(lib().lle_map_lasers(self._h, None, 0, C.byref(n)))
+        buf = (C.c_int32 * max(1, 7 * n.value))()
+        check(lib().lle_map_lasers(self._h, buf, n.value, C.byref(n)))
+        return [((buf[7 * k], buf[7 * k + 1]), buf[7 * k + 2], buf[7 * k + 3], Direction(buf[7 * k + 4]), buf[7 * k + 5],
+                 buf[7 * k + 6]) for k in range(n.value)]
+
+
+class _DevArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, shape: tuple[int, ...], typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class VecWorld:
+    """N worlds on one CUDA device.
+
+    Parameters mirror `lle_vec_options`.  `maps` is a list of `Map` / map strings / level numbers; all maps
+    must share (height, width, n_agents, n_gems).  `map_of_env[e]` selects the map of env e.
+    """
+
+    def __init__(self, maps: Sequence[Map | str | int] | Map | str | int, n_envs: int, *, map_of_env: Sequence[int] | None = None,
+                 device: int | str | torch.device = 0, reward_dim: int = 1, walkable_lasers: bool = True, auto_reset: bool = True,
+                 lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("lle_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if isinstance(maps, (Map, str, int)):
+            maps = [maps]
+        self.maps = [m if isinstance(m, Map) else (Map(level=m) if isinstance(m, int) else Map(m)) for m in maps]
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        opts = VecOptions()
+        lib().lle_vec_default_options(C.byref(opts))
+        opts.device = self.device.index or 0
+        opts.reward_dim, opts.walkable_lasers, opts.auto_reset = int(reward_dim), int(walkable_lasers), int(auto_reset)
+        opts.lle_semantics, opts.write_obs = int(lle_semantics), int(write_obs)
+        opts.seed, opts.env_id_base = int(seed), int(env_id_base)
+        handles = (C.c_void_p * len(self.maps))(*[m._h for m in self.maps])
+        moe = None
+        if map_of_env is not None:
+            arr = np.ascontiguousarray(map_of_env, dtype=np.int32)
+            if arr.shape != (n_envs,):
+                raise ValueError("map_of_env must have n_envs entries")
+            moe = arr.ctypes.data_as(C.POINTER(C.c_int32))
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()  # make sure torch's primary context exists
+            h = C.c_void_p()
+            check(lib().lle_vec_create(handles, len(self.maps), moe, int(n_envs), C.byref(opts), C.byref(h)))
+        self._h = h
+        b = VecBuffers()
+        check(lib().lle_vec_get_buffers(self._h, C.byref(b)))
+        self.n_envs, self.n_agents, self.n_gems, self.n_channels = int(b.n_envs), b.n_agents, b.n_gems, b.n_channels
+        self.height, self.width, self.reward_dim, self.state_dim, self.n_beams_max = b.height, b.width, b.reward_dim, b.state_dim, b.n_beams_max
+        self.obs_stride = int(b.obs_stride)
+        N, A = self.n_envs, self.n_agents
+        dev = self.device
+
+        def wrap(ptr, shape, typestr):
+            return torch.as_tensor(_DevArray(ptr, shape, typestr, self), device=dev)
+
+        #: layered observation, one (C,H,W) block per env (observations.py:254-266)
+        self.obs = None
+        if write_obs:
+            rows = wrap(b.obs, (N, self.obs_stride), "<f4")
+            chw = self.n_channels * self.height * self.width
+            self.obs = rows[:, :chw].unflatten(1, (self.n_channels, self.height, self.width))
+        self.state = wrap(b.state, (N, self.state_dim), "<f4")
+        self.avail = wrap(b.avail, (N, A, 5), "|u1")
+        self.reward = wrap(b.reward, (N, self.reward_dim), "<f4")
+        self.done = wrap(b.done, (N,), "|u1")
+        self.events = wrap(b.events, (N, A), "|u1")
+        self.actions = wrap(b.actions, (N, A), "|i1")
+        self.err = wrap(b.err, (N,), "|u1")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib().lle_vec_destroy(h)
+            self._h = None
+
+    # ---- views
+    @property
+    def obs_per_agent(self) -> torch.Tensor:
+        """(N, A, C, H, W) view whose agent dimension has stride 0 — the values of the reference's np.tile."""
+        return self.obs.unsqueeze(1).expand(-1, self.n_agents, -1, -1, -1)
+
+    @property
+    def obs_flattened(self) -> torch.Tensor:
+        """FlattenedLayered (observations.py:291-293)."""
+        return self.obs.flatten(1)
+
+    # ---- operations
+    def reset(self, mask: torch.Tensor | None = None):
+        ptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            ptr = mask.data_ptr()
+        check(lib().lle_vec_reset(self._h, ptr, _stream_ptr(self.device)))
+
+    def step(self, actions: torch.Tensor | None = None):
+        """One lockstep step.  `actions`: int8 (N, A) device tensor, or None for on-device Philox sampling."""
+        ptr = None
+        if actions is not None:
+            if actions.shape != (self.n_envs, self.n_agents):
+                raise ValueError(f"InvalidNumberOfActions: expected shape {(self.n_envs, self.n_agents)}, got {tuple(actions.shape)}")
+            actions = actions.to(device=self.device, dtype=torch.int8).contiguous()
+            ptr = actions.data_ptr()
+        check(lib().lle_vec_step(self._h, ptr, _stream_ptr(self.device)))
+
+    def step_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor):
+        """Host-facing step: H2D actions, step, D2H reward/done, stream sync (lle_vec_step_host)."""
+        ptr = None
+        if actions is not None:
+            t = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(actions)
+            assert t.dtype == torch.int8 and t.is_contiguous() and not t.is_cuda
+            ptr = t.data_ptr()
+        check(lib().lle_vec_step_host(self._h, ptr, reward_out.data_ptr(), done_out.data_ptr(), _stream_ptr(self.device)))
+
+    def set_state(self, positions: torch.Tensor, gems_collected: torch.Tensor, agents_alive: torch.Tensor):
+        pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
+        gems = gems_collected.to(device=self.device, dtype=torch.uint8).contiguous()
+        alive = agents_alive.to(device=self.device, dtype=torch.uint8).contiguous()
+        if pos.shape != (self.n_envs, self.n_agents, 2) or alive.shape != (self.n_envs, self.n_agents):
+            raise ValueError("InvalidNumberOfAgents")
+        if gems.shape != (self.n_envs, self.n_gems):
+            raise ValueError("InvalidNumberOfGems")
+        check(lib().lle_vec_set_state(self._h, pos.data_ptr(), gems.data_ptr() if self.n_gems else None, alive.data_ptr(),
+                                      _stream_ptr(self.device)))
+
+    def export_raw(self) -> dict[str, torch.Tensor]:
+        N, A, NB = self.n_envs, self.n_agents, max(self.n_beams_max, 1)
+        d = self.device
+        out = dict(pos=torch.zeros((N, A, 2), dtype=torch.int16, device=d), alive=torch.zeros((N, A), dtype=torch.uint8, device=d),
+                   arrived=torch.zeros((N, A), dtype=torch.uint8, device=d), slot=torch.zeros((N, A), dtype=torch.uint8, device=d),
+                   beam_on=torch.zeros((N, NB), dtype=torch.int64, device=d), collected=torch.zeros((N,), dtype=torch.int64, device=d),
+                   counters=torch.zeros((N, 3), dtype=torch.uint8, device=d))
+        check(lib().lle_vec_export_raw(self._h, out["pos"].data_ptr(), out["alive"].data_ptr(), out["arrived"].data_ptr(),
+                                       out["slot"].data_ptr(), out["beam_on"].data_ptr() if self.n_beams_max else None,
+                                       out["collected"].data_ptr(), out["counters"].data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    @property
+    def step_count(self) -> int:
+        v = C.c_uint64(0)
+        check(lib().lle_vec_get_step_count(self._h, C.byref(v)))
+        return v.value
+
+    @step_count.setter
+    def step_count(self, value: int):
+        check(lib().lle_vec_set_step_count(self._h, int(value)))
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_uint64(0)
+        check(lib().lle_vec_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def timing_begin(self):
+        check(lib().lle_vec_timing_begin(self._h, _stream_ptr(self.device)))
+
+    def timing_end(self) -> tuple[float, int]:
+        ms, n = C.c_float(0), C.c_uint64(0)
+        check(lib().lle_vec_timing_end(self._h, _stream_ptr(self.device), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.device).synchronize()

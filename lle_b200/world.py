@@ -1,0 +1,282 @@
+"""`World` and `LLE`: the reference's single-world API served by the batched device path with N = 1.
+
+Same names, argument meaning and error behaviour as `lle.World` (src/bindings/world/pyworld.rs:144-626,
+python/lle/world/__init__.pyi) and `lle.LLE` (python/lle/env/env.py), so the reference's own tests read
+the same against this backend.  Every call runs the sm_100a kernel; nothing is computed on the CPU except
+marshalling.  For throughput use `VecWorld` / `VecLLE`.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from .types import (Action, Agent, Direction, EventType, Gem, InvalidActionError, InvalidWorldStateError, Laser, LaserSource,
+                    WorldEvent, WorldState)
+from .vec_world import Map, VecWorld
+
+_EVENT_OF_CODE = {1: EventType.AGENT_EXIT, 2: EventType.GEM_COLLECTED, 3: EventType.AGENT_DIED}
+
+
+def decode_events(byte_row: Sequence[int]) -> list[WorldEvent]:
+    """Ordered event list (world.rs:464-472: pass by pass, agents in id order) from the event bytes."""
+    keyed = []
+    for a, b in enumerate(byte_row):
+        b = int(b)
+        if b & 3:
+            keyed.append((1, a, WorldEvent(_EVENT_OF_CODE[b & 3], a)))
+        if b >> 2:
+            keyed.append((b >> 2, a, WorldEvent(EventType.AGENT_DIED, a)))
+    keyed.sort(key=lambda x: (x[0], x[1]))
+    return [e for _, _, e in keyed]
+
+
+def _check_actions(actions, n_agents: int) -> list[Action]:
+    """Argument handling of PyWorld::step / extract_actions (pyworld.rs:123-141, :431-446)."""
+    if isinstance(actions, Action):
+        actions = [actions]
+    elif not isinstance(actions, (list, tuple)) or not all(isinstance(a, Action) for a in actions):
+        raise TypeError("Action must be of type Action or list[Action]")
+    if len(actions) != n_agents:
+        raise ValueError(f"InvalidNumberOfActions {{ given: {len(actions)}, expected: {n_agents} }}")
+    return list(actions)
+
+
+class _Single:
+    """Shared N=1 plumbing of World and LLE."""
+
+    def _init_single(self, map_str: str | None, level: int | None, device, **vec_kw):
+        self._map = Map(map_str, level=level)
+        m = self._map
+        self.height, self.width, self.n_agents, self.n_gems = m.height, m.width, m.n_agents, m.n_gems
+        self._vec = VecWorld(m, 1, device=device, write_obs=not m.obs_invalid, **vec_kw)
+        self._laser_tiles = m.laser_tiles()
+        self._sources = m.sources()
+
+    # ---- state queries (one small D2H each)
+    def _raw(self):
+        raw = self._vec.export_raw()
+        self._vec.synchronize()
+        return {k: v[0].cpu().numpy() for k, v in raw.items()}
+
+    @property
+    def agents_positions(self) -> list[tuple[int, int]]:
+        return [(int(i), int(j)) for i, j in self._raw()["pos"]]
+
+    @property
+    def agents(self) -> list[Agent]:
+        raw = self._raw()
+        return [Agent(a, not bool(raw["alive"][a]), bool(raw["arrived"][a])) for a in range(self.n_agents)]
+
+    @property
+    def gems(self) -> list[Gem]:
+        coll = int(self._raw()["collected"])
+        return [Gem(p, bool((coll >> g) & 1)) for g, p in enumerate(self._map.gems)]
+
+    @property
+    def gems_collected(self) -> int:
+        """World::n_gems_collected (world.rs:265-275): gems wrapped by a beam are not counted."""
+        return bin(int(self._raw()["collected"]) & self._map.gem_toplevel).count("1")
+
+    @property
+    def lasers(self) -> list[Laser]:
+        """World::lasers (world.rs:159-172) with `is_on` read from the device beam masks."""
+        on = self._raw()["beam_on"].view(np.uint64)
+        return [Laser(pos, lid, colour, direction, bool((int(on[beam]) >> off) & 1), True)
+                for pos, lid, colour, direction, beam, off in self._laser_tiles]
+
+    @property
+    def laser_sources(self) -> list[LaserSource]:
+        return list(self._sources)
+
+    def source_at(self, pos) -> LaserSource:
+        for s in self._sources:
+            if s.pos == tuple(pos):
+                return s
+        raise ValueError(f"There is no laser source at {tuple(pos)}")
+
+    wall_pos = property(lambda self: self._map.walls)
+    void_pos = property(lambda self: self._map.voids)
+    exit_pos = property(lambda self: self._map.exits)
+    start_pos = property(lambda self: self._map.starts)
+    laser_pos = property(lambda self: self._map.laser_cells)
+
+    @property
+    def random_start_pos(self):
+        return [[p] for p in self._map.starts]
+
+    @property
+    def n_laser_colours(self) -> int:
+        return len({s.agent_id for s in self._sources})
+
+    @property
+    def world_string(self) -> str:
+        return self._map.text
+
+    def observe_layered(self) -> np.ndarray:
+        """LayeredPadded.observe (observations.py:254-266): (A, C, H, W) float32."""
+        if self._map.obs_invalid:
+            raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
+        self._vec.synchronize()
+        return self._vec.obs_per_agent[0].cpu().numpy()
+
+    def state_array(self) -> np.ndarray:
+        self._vec.synchronize()
+        return self._vec.state[0].cpu().numpy()
+
+    def _world_state(self) -> WorldState:
+        raw = self._raw()
+        coll = int(raw["collected"])
+        return WorldState([(int(i), int(j)) for i, j in raw["pos"]], [bool((coll >> g) & 1) for g in range(self.n_gems)],
+                          [bool(x) for x in raw["alive"]])
+
+    def _force_state(self, state: WorldState) -> list[WorldEvent]:
+        """World::set_state (world.rs:515-597) incl. its error mapping (pyexceptions.rs)."""
+        if len(state.gems_collected) != self.n_gems:
+            raise InvalidWorldStateError(f"InvalidNumberOfGems {{ given: {len(state.gems_collected)}, expected: {self.n_gems} }}")
+        if len(state.agents_positions) != self.n_agents:
+            raise InvalidWorldStateError(f"InvalidNumberOfAgents {{ given: {len(state.agents_positions)}, expected: {self.n_agents} }}")
+        pos = torch.tensor([state.agents_positions], dtype=torch.int64).clamp(-1, 1 << 20).to(torch.int32)
+        gems = torch.tensor([state.gems_collected], dtype=torch.uint8).reshape(1, self.n_gems)
+        alive = torch.tensor([state.agents_alive], dtype=torch.uint8)
+        self._vec.set_state(pos, gems, alive)
+        self._vec.synchronize()
+        err = int(self._vec.err[0])
+        if err == 3:
+            raise InvalidWorldStateError("InvalidWorldState { reason: \"There are two agents at the same position\" }")
+        if err == 4:
+            raise IndexError("OutOfWorldPosition")
+        if err == 5:
+            raise InvalidWorldStateError("InvalidAgentPosition { reason: \"The tile is not walkable\" }")
+        if err == 6:
+            raise InvalidWorldStateError("InvalidWorldState { reason: \"The given state is invalid (e.g. an agent whose alive "
+                                         "status was set to `true` died).\" }")
+        return decode_events(self._vec.events[0].cpu().tolist())
+
+    def _available(self) -> np.ndarray:
+        self._vec.synchronize()
+        return self._vec.avail[0].cpu().numpy().astype(bool)
+
+
+class World(_Single):
+    """`lle.World` backed by the device path (raw engine rules: no done/auto-reset)."""
+
+    def __init__(self, map_str: str, device=0):
+        self._init_single(map_str, None, device, lle_semantics=False, auto_reset=False)
+
+    @staticmethod
+    def level(level: int, device=0) -> "World":
+        w = World.__new__(World)
+        w._init_single(None, level, device, lle_semantics=False, auto_reset=False)
+        return w
+
+    @staticmethod
+    def from_file(filename: str, device=0) -> "World":
+        """World::from_file (world.rs:610-626): "lvlN" / "levelN" name the built-in levels."""
+        low = str(filename).lower()
+        for prefix in ("lvl", "level"):
+            if low.startswith(prefix) and low[len(prefix):].isdigit():
+                return World.level(int(low[len(prefix):]), device)
+        if not os.path.exists(filename):
+            raise FileNotFoundError(filename)
+        with open(filename) as f:
+            return World(f.read(), device)
+
+    def reset(self):
+        self._vec.reset()
+
+    def step(self, actions) -> list[WorldEvent]:
+        acts = _check_actions(actions, self.n_agents)
+        t = torch.tensor([[int(a) for a in acts]], dtype=torch.int8)
+        self._vec.step(t)
+        self._vec.synchronize()
+        if int(self._vec.err[0]) == 1:
+            avail = self._available()
+            for agent, a in enumerate(acts):
+                if not avail[agent, int(a)]:
+                    raise InvalidActionError(f"InvalidAction {{ agent_id: {agent}, available: "
+                                             f"{[Action(k).name for k in (4, 0, 2, 1, 3) if avail[agent, k]]}, taken: {a.name} }}")
+            raise InvalidActionError("InvalidAction")
+        return decode_events(self._vec.events[0].cpu().tolist())
+
+    def available_actions(self) -> list[list[Action]]:
+        """World::available_actions: per agent, Stay then N, E, S, W (world.rs:349-351)."""
+        avail = self._available()
+        order = (Action.STAY, Action.NORTH, Action.EAST, Action.SOUTH, Action.WEST)
+        return [[a for a in order if avail[agent, int(a)]] for agent in range(self.n_agents)]
+
+    def get_state(self) -> WorldState:
+        return self._world_state()
+
+    def set_state(self, state: WorldState) -> list[WorldEvent]:
+        return self._force_state(state)
+
+
+@dataclass
+class Step:
+    """The fields of marlenv's Step that the path produces (env.py:178-189)."""
+
+    obs: np.ndarray
+    available_actions: np.ndarray
+    state: np.ndarray
+    reward: np.ndarray
+    done: bool
+    events: list
+
+
+class LLE(_Single):
+    """`lle.LLE` (python/lle/env/env.py) for one environment, served by the device path."""
+
+    def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
+                 walkable_lasers: bool = True, device=0):
+        self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
+                          reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers)
+        if self._map.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
+            raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
+        self.reward_dim = self._vec.reward_dim
+
+    @staticmethod
+    def level(level: int, **kw) -> "LLE":
+        return LLE(level=level, **kw)
+
+    @property
+    def done(self) -> bool:
+        self._vec.synchronize()
+        return bool(self._vec.done[0])
+
+    @property
+    def n_arrived(self) -> int:
+        return int(self._raw()["counters"][0])
+
+    def observe(self) -> np.ndarray:
+        return self.observe_layered()
+
+    def get_state(self) -> np.ndarray:
+        return self.state_array()
+
+    def available_actions(self) -> np.ndarray:
+        return self._available()
+
+    def reset(self):
+        self._vec.reset()
+        return self.observe(), self.get_state()
+
+    def step(self, actions: Sequence[int]) -> Step:
+        acts = [int(a) for a in actions]
+        if len(acts) != self.n_agents:
+            raise ValueError(f"InvalidNumberOfActions {{ given: {len(acts)}, expected: {self.n_agents} }}")
+        self._vec.step(torch.tensor([acts], dtype=torch.int8))
+        self._vec.synchronize()
+        err = int(self._vec.err[0])
+        if err == 2:
+            raise ValueError("Cannot step in a done environment")
+        if err == 1:
+            raise InvalidActionError("InvalidAction")
+        return Step(self.observe(), self.available_actions(), self.get_state(), self._vec.reward[0].cpu().numpy(),
+                    bool(self._vec.done[0]), decode_events(self._vec.events[0].cpu().tolist()))
+
+    def set_state(self, state: WorldState):
+        self._force_state(state)

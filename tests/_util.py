@@ -6,3 +6,65 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def level_text(n: int) -> str:
     with open(os.path.join(GOLDEN, "levels", f"lvl{n}")) as f:
         return f.read()
+
+
+def synthetic_map(h: int, w: int, n_agents: int, n_sources: int, seed: int = 0, n_gems: int | None = None) -> str:
+    """Seeded synthetic map in the v1 grammar (BASELINE config 5): border-free grid, starts on the first row,
+    exits on the last row, laser sources of mixed colours and directions placed so that every beam is at most
+    63 cells long and never crosses a start tile, a few walls and gems."""
+    import random
+
+    rng = random.Random(seed)
+    grid = [["." for _ in range(w)] for _ in range(h)]
+    start_cols = rng.sample(range(2, w - 2), n_agents)
+    for a, j in enumerate(start_cols):
+        grid[0][j] = f"S{a}"
+    exit_cols = rng.sample(range(2, w - 2), n_agents)
+    for j in exit_cols:
+        grid[h - 1][j] = "X"
+    used_rows, used_cols = {0, h - 1}, set(start_cols) | set(exit_cols)
+    placed = 0
+    attempts = 0
+    while placed < n_sources and attempts < 10000:
+        attempts += 1
+        colour = placed % n_agents
+        if rng.random() < 0.5:  # horizontal beam on a free row
+            i = rng.randrange(2, h - 2)
+            if i in used_rows:
+                continue
+            used_rows.add(i)
+            if rng.random() < 0.5:
+                grid[i][0] = f"L{colour}E"
+            else:
+                grid[i][w - 1] = f"L{colour}W"
+            # a wall somewhere keeps the beam <= 63 cells on 64-wide maps
+            grid[i][rng.randrange(w // 2, w - 1) if grid[i][0].startswith("L") else rng.randrange(1, w // 2)] = "@"
+        else:  # vertical beam on a free column, starting below the start row
+            j = rng.randrange(1, w - 1)
+            if j in used_cols:
+                continue
+            used_cols.add(j)
+            grid[1][j] = f"L{colour}S"
+            grid[rng.randrange(h // 2, h - 1)][j] = "@"
+        placed += 1
+    free = [(i, j) for i in range(1, h - 1) for j in range(w) if grid[i][j] == "."]
+    rng.shuffle(free)
+    n_gems = n_agents if n_gems is None else n_gems
+    for i, j in free[:n_gems]:
+        grid[i][j] = "G"
+    for i, j in free[n_gems : n_gems + (h * w) // 40]:
+        grid[i][j] = "@"
+    return "\n".join(" ".join(f"{t:>4}" for t in row) for row in grid)
+
+
+def rollout_digest(x) -> list[int]:
+    """Order-sensitive 64-bit checksums of one step's outputs (obs, state, avail, reward, done, events, actions)."""
+    import zlib
+
+    import numpy as np
+
+    out = []
+    for name in ("obs", "state", "avail", "reward", "done", "events", "actions"):
+        a = np.ascontiguousarray(np.asarray(getattr(x, name)))
+        out.append(zlib.crc32(a.tobytes()) ^ (zlib.adler32(a.tobytes()) << 32))
+    return out

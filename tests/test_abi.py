@@ -1,0 +1,88 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/lle_b200.h declares, and its host-side map compiler agrees with the oracle on the whole corpus.
+No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from _util import level_text
+from oracle import lle_oracle as lo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _native():
+    from lle_b200 import _native
+    return _native
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lle_b200.h")).read()
+    declared = re.findall(r"LLE_API\s+[\w\s\*]+?\b(lle_\w+)\s*\(", header)
+    assert len(declared) >= 24
+    L = C.CDLL(_native().LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in include/lle_b200.h but not exported"
+    assert sorted(declared) == sorted(_native().SYMBOLS)
+    assert b"sm_100a" in _native().lib().lle_version()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    import lle_b200
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lle_b200.VecWorld(lle_b200.Map(level=1), 4)
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lle_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "lle_oracle" not in text and "oracle/" not in text.replace("oracle/ is test", ""), f
+
+
+def _map_facts_native(text=None, level=None):
+    import lle_b200
+
+    m = lle_b200.Map(text, level=level)
+    return dict(dims=(m.height, m.width, m.n_agents, m.n_gems, m.n_sources), walls=m.walls, voids=m.voids, exits=m.exits,
+                gems=m.gems, starts=m.starts, laser_cells=m.laser_cells,
+                sources=[(s.pos, s.agent_id, int(s.direction), s.laser_id, s.beam_len) for s in m.sources()],
+                lasers=[(pos, lid, colour, int(d)) for pos, lid, colour, d, _, _ in m.laser_tiles()])
+
+
+def _map_facts_oracle(text):
+    w = lo.World(text)
+    return dict(dims=(w.height, w.width, w.n_agents, w.n_gems, w.n_sources), walls=w.wall_pos, voids=w.void_pos, exits=w.exit_pos,
+                gems=[g.pos for g in w.gems], starts=w.start_pos, laser_cells=w.laser_pos,
+                sources=[(s.pos, s.agent_id, int(s.direction), s.laser_id, s.beam_len) for s in w.laser_sources],
+                lasers=[(l.pos, l.laser_id, l.agent_id, int(l.direction)) for l in w.lasers])
+
+
+def test_map_compiler_matches_oracle_on_corpus(layouts):
+    texts = [level_text(n) for n in range(1, 7)] + [t for _, t in sorted(layouts.items())]
+    texts += ["S0 L1E X", ".   L0S S1\nS0   .   .\nL1E  X   X", "L0E . L0E . X S0",
+              "\n".join([" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)])]
+    for text in texts:
+        assert _map_facts_native(text) == _map_facts_oracle(text)
+    for n in range(1, 7):
+        assert _map_facts_native(level=n) == _map_facts_oracle(level_text(n))
+
+
+def test_map_errors():
+    import lle_b200
+
+    for text, name in [("", "EmptyWorld"), ("S0 S0 X X", "DuplicateStartTile"), ("S1 S0 X", "NotEnoughExitTiles"),
+                       (". . G", "NoAgents"), ("X S0 .\n . .", "InconsistentDimensions"), ("S0 Q X", "InvalidTile"),
+                       ("S0  S1 X . X\nL1N .  . . .", "AgentWithoutStart")]:
+        with pytest.raises(lle_b200.ParsingError, match=name):
+            lle_b200.Map(text)
+    with pytest.raises(lle_b200.InvalidLevelError):
+        lle_b200.Map(level=7)

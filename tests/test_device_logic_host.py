@@ -176,3 +176,16 @@ def test_map_compiler_errors_match_oracle():
         assert (st != 0) == (expected is not None), (text, st, msg, expected)
         if expected:
             assert msg.split(" ")[0].split("{")[0].strip() in expected or expected.split(":")[0] in msg, (text, msg, expected)
+
+
+def test_synthetic_64x64_config5():
+    from _util import synthetic_map
+
+    text = synthetic_map(64, 64, 8, 16, seed=5)
+    ora = lo.OracleVec([text], None, 32, seed=6)
+    shim = ShimVec([text], None, 32, seed=6)
+    assert shim.n_chunks > 1
+    for t in range(25):
+        ora.step(None, 2)
+        shim.step(None)
+        assert_same(shim, ora, shim.export_raw(), f"step {t}")

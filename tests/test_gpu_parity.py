@@ -1,0 +1,224 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the oracle
+on the same seeded inputs, bit for bit — outputs (obs, state, avail, reward, done, events, actions, err) and
+the raw engine state (positions, alive/arrived, tile slots, beam masks, gems)."""
+import numpy as np
+import pytest
+import torch
+
+from _parity import assert_same
+from _util import level_text
+from oracle import lle_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+
+class Dev:
+    """Adapter: host copies of a VecWorld's buffers with the oracle's attribute names."""
+
+    def __init__(self, vec):
+        self.vec = vec
+
+    def pull(self):
+        v = self.vec
+        v.synchronize()
+        for name in ("obs", "state", "avail", "reward", "done", "events", "actions", "err"):
+            setattr(self, name, getattr(v, name).cpu().numpy())
+        raw = {k: t.cpu().numpy() for k, t in v.export_raw().items()}
+        raw["beam_on"] = raw["beam_on"].view(np.uint64)
+        raw["collected"] = raw["collected"].view(np.uint64)
+        return raw
+
+
+def make_pair(maps, map_of_env, n_envs, **kw):
+    import lle_b200
+
+    okw = dict(multi_objective=kw.get("reward_dim", 1) == 4, walkable_lasers=kw.get("walkable_lasers", True),
+               auto_reset=kw.get("auto_reset", True), seed=kw.get("seed", 0), env_id_base=kw.get("env_id_base", 0))
+    ora = lo.OracleVec(maps, map_of_env, n_envs, **okw)
+    vec = lle_b200.VecWorld(maps, n_envs, map_of_env=map_of_env, **kw)
+    return ora, Dev(vec)
+
+
+def run_pair(maps, map_of_env, n_envs, steps, check_every=1, **kw):
+    ora, dev = make_pair(maps, map_of_env, n_envs, **kw)
+    assert_same(dev, ora, dev.pull(), "after reset")
+    for t in range(steps):
+        ora.step(None)
+        dev.vec.step(None)
+        if t % check_every == 0 or t == steps - 1:
+            assert_same(dev, ora, dev.pull(), f"step {t}")
+    return ora, dev
+
+
+def test_levels_philox_rollout():
+    for level in range(1, 7):
+        run_pair([level_text(level)], None, 200, 200, seed=level)
+
+
+def test_layout_corpus_philox_rollout(layouts):
+    for k, (name, text) in enumerate(sorted(layouts.items())):
+        run_pair([text], None, 96, 100, seed=100 + k)
+
+
+def test_config1_anchor_level1():
+    """BASELINE config 1: lvl1, N=4096 envs, device Philox actions replayed in the oracle."""
+    run_pair([level_text(1)], None, 4096, 300, check_every=7, seed=1234)
+
+
+def test_config2_level6_full_size():
+    """BASELINE config 2 at full size: lvl6, 65,536 envs, layered observations."""
+    run_pair([level_text(6)], None, 65536, 12, seed=77)
+
+
+def test_ragged_batch_sizes():
+    for n in (1, 31, 33, 100):
+        run_pair([level_text(6)], None, n, 40, seed=n)
+
+
+def test_heterogeneous_maps_in_one_batch():
+    maps = [level_text(2), level_text(3), level_text(4)]
+    moe = [(e * 7 + e // 5) % 3 for e in range(1000)]
+    run_pair(maps, moe, 1000, 150, seed=11, env_id_base=1000)
+
+
+def test_options():
+    run_pair([level_text(6)], None, 256, 150, reward_dim=4, seed=7)
+    run_pair([level_text(5)], None, 256, 150, walkable_lasers=False, seed=8)
+    ora, dev = run_pair([level_text(6)], None, 256, 250, auto_reset=False, seed=5)
+    assert (ora.err == 2).any()
+
+
+def test_supplied_actions_with_invalid_ones():
+    rng = np.random.default_rng(0)
+    ora, dev = make_pair([level_text(5)], None, 512, seed=1)
+    n_bad = 0
+    for t in range(100):
+        actions = rng.integers(0, 5, size=(512, ora.A)).astype(np.int8)
+        if t % 10 == 0:
+            actions[::17, 0] = 7
+        ora.step(actions)
+        dev.vec.step(torch.from_numpy(actions).cuda())
+        assert_same(dev, ora, dev.pull(), f"step {t}")
+        n_bad += int((ora.err == 1).sum())
+    assert n_bad > 100
+
+
+def test_many_agents_and_small_maps():
+    rows = [" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)]
+    run_pair(["\n".join(rows)], None, 64, 60, seed=2)
+    run_pair(["S0 G X"], None, 64, 30, seed=3)          # 1x3 map: 18 floats per env, 32 envs per tile
+    run_pair(["S0 . G\nS1 X X"], None, 70, 50, seed=4)  # 2x3 map
+
+
+def test_large_map_chunked_tiles():
+    """A 64x64 map with 8 agents and 16 sources: one observation (327,680 B) is streamed in chunks."""
+    from _util import synthetic_map
+
+    text = synthetic_map(64, 64, 8, 16, seed=5)
+    run_pair([text], None, 64, 40, check_every=3, seed=6)
+
+
+def test_set_state_fuzz(layouts):
+    import ctypes as C
+
+    rng = np.random.default_rng(42)
+    L = lo.lib()
+    for text in [level_text(6), level_text(5), layouts["eight-agent-interdependent-8"]]:
+        n = 128
+        ora, dev = make_pair([text], None, n, auto_reset=False, seed=9)
+        H, W, A, G = ora.H, ora.W, ora.A, ora.G
+        for rnd in range(4):
+            ora.reset()
+            dev.vec.reset()
+            for _ in range(3 + rnd):
+                ora.step(None)
+                dev.vec.step(None)
+            pos = np.stack([rng.integers(-1, H + 1, size=(n, A)), rng.integers(-1, W + 1, size=(n, A))], axis=-1).astype(np.int32)
+            pos[: n // 2] = np.clip(pos[: n // 2], 0, [H - 1, W - 1])
+            gems = rng.integers(0, 2, size=(n, G)).astype(np.uint8)
+            alive = (rng.random((n, A)) < 0.85).astype(np.uint8)
+            dev.vec.set_state(torch.from_numpy(pos), torch.from_numpy(gems), torch.from_numpy(alive))
+            exp_err = np.zeros(n, np.uint8)
+            for e in range(n):
+                p = (C.c_long * (2 * A))(*[int(x) for x in pos[e].reshape(-1)])
+                g = (C.c_uint8 * max(1, G))(*[int(x) for x in gems[e]])
+                a = (C.c_uint8 * A)(*[int(x) for x in alive[e]])
+                st = L.lleo_vec_set_state_env(ora._h, C.c_long(e), p, A, g, G, a)
+                exp_err[e] = {0: 0, 105: 4, 104: 5}.get(st, 3 if st == 107 and b"same position" in L.lleo_last_error() else 6)
+            L.lleo_vec_refresh(ora._h)
+            raw = dev.pull()
+            assert np.array_equal(dev.err, exp_err)
+            for name in ("pos", "alive", "arrived", "slot", "collected"):
+                assert np.array_equal(raw[name], np.asarray(getattr(ora, name))), name
+            assert np.array_equal(raw["beam_on"][:, : ora.NB], ora.beam_on[:, : ora.NB])
+            for name in ("obs", "state", "done"):
+                assert np.array_equal(getattr(dev, name), np.asarray(getattr(ora, name))), name
+            ok = exp_err != 6  # stale availability cache of the reference after InvalidWorldState
+            assert np.array_equal(dev.avail[ok], ora.avail[ok])
+
+
+def test_determinism_and_shard_independence():
+    """Same seed => same stream; an env's stream depends on its global id only, not on how envs are sharded."""
+    import lle_b200
+
+    text = level_text(6)
+    full = lle_b200.VecWorld(text, 256, seed=3)
+    lo_half = lle_b200.VecWorld(text, 128, seed=3, env_id_base=0)
+    hi_half = lle_b200.VecWorld(text, 128, seed=3, env_id_base=128)
+    for _ in range(60):
+        for v in (full, lo_half, hi_half):
+            v.step(None)
+    full.synchronize()
+    for name in ("obs", "state", "reward", "done", "events", "actions"):
+        a = getattr(full, name).cpu()
+        b = torch.cat([getattr(lo_half, name).cpu(), getattr(hi_half, name).cpu()])
+        assert torch.equal(a, b), name
+
+
+def test_golden_fixture_level6():
+    """Committed fixture (tests/golden/rollout_lvl6.npz, generated by tests/golden/make_rollout_fixture.py)."""
+    import os
+
+    import lle_b200
+    from _util import GOLDEN, rollout_digest
+
+    fx = np.load(os.path.join(GOLDEN, "rollout_lvl6.npz"))
+    vec = lle_b200.VecWorld(level_text(6), int(fx["n_envs"]), seed=int(fx["seed"]))
+    dev = Dev(vec)
+    for t in range(int(fx["steps"])):
+        vec.step(None)
+        dev.pull()
+        assert rollout_digest(dev) == fx["digests"][t].tolist(), f"step {t}"
+    assert np.array_equal(dev.obs, fx["final_obs"])
+    assert np.array_equal(dev.state, fx["final_state"])
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE config 2 size (65,536 x lvl6), 200 steps."""
+    import lle_b200
+
+    vec = lle_b200.VecWorld(level_text(6), 65536, seed=99)
+    m = vec.maps[0]
+    A, C, H, W = vec.n_agents, vec.n_channels, vec.height, vec.width
+    walls = torch.zeros(H, W)
+    for i, j in m.walls:
+        walls[i, j] = 1
+    n_done = 0
+    for t in range(200):
+        vec.step(None)
+        if t % 20 == 19:
+            vec.synchronize()
+            obs = vec.obs
+            assert torch.all((obs == 0) | (obs == 1) | (obs == -1))
+            assert torch.equal(obs[:, :A].sum(dim=(2, 3)), torch.ones(65536, A, device=obs.device))  # one cell per agent plane
+            assert torch.equal(obs[:, 2 * A].cpu(), walls.expand(65536, H, W))                        # static wall plane
+            st = vec.state
+            pos = st[:, : 2 * A].reshape(-1, A, 2).long()
+            onehot = obs[:, :A].flatten(2).argmax(dim=2)
+            assert torch.equal(onehot, pos[..., 0] * W + pos[..., 1])                                 # state <-> obs
+            gem_plane = obs[:, 2 * A + 2].sum(dim=(1, 2))
+            assert torch.equal(gem_plane, (1 - st[:, 2 * A : 2 * A + vec.n_gems]).sum(dim=1))          # gems <-> obs
+            assert torch.all(vec.err == 0)
+            assert torch.all(vec.avail[:, :, 4] == 1)                                                 # STAY always available
+            n_done += int(vec.done.sum())
+    assert n_done > 0
