@@ -1,0 +1,26 @@
+"""Quick device-timed loop of the step kernel (development aid, not the contract bench)."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import lle_b200
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--level", type=int, default=6)
+ap.add_argument("--envs", type=int, default=65536)
+ap.add_argument("--steps", type=int, default=2000)
+ap.add_argument("--no-obs", action="store_true")
+ap.add_argument("--map", type=str, default=None)
+args = ap.parse_args()
+maps = lle_b200.Map(level=args.level)
+vec = lle_b200.VecWorld(maps, args.envs, seed=1, write_obs=not args.no_obs)
+for _ in range(50):
+    vec.step(None)
+vec.synchronize()
+vec.timing_begin()
+for _ in range(args.steps):
+    vec.step(None)
+ms, n = vec.timing_end()
+us = ms * 1e3 / n
+obs_bytes = vec.n_channels * vec.height * vec.width * 4 * args.envs
+print(json.dumps({"level": args.level, "envs": args.envs, "obs": not args.no_obs, "us_per_step": round(us, 2),
+                  "env_steps_per_s": round(args.envs / (us * 1e-6)), "obs_GBps": round(obs_bytes / (us * 1e-6) / 1e9, 1)}))
