@@ -228,6 +228,8 @@ CompiledMap compile_map(const std::string& text) {
     h.obs_invalid = obs_invalid;
     size_t off = align16(sizeof(LleMapHeader));
     h.tiles_off = (uint32_t)off;   off = align16(off + tiles.size() * sizeof(uint16_t));
+    h.cellinfo_off = (uint32_t)off;  off = align16(off + (size_t)HW * sizeof(uint32_t));
+    h.cellbeams_off = (uint32_t)off; off = align16(off + (size_t)HW * sizeof(LleCellBeams));
     h.beams_off = (uint32_t)off;   off = align16(off + (size_t)std::max(NB, 1) * sizeof(LleBeam));
     h.patch_off = (uint32_t)off;   off = align16(off + std::max<size_t>(patch.size(), 1) * sizeof(LlePatch));
     h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
@@ -257,6 +259,35 @@ CompiledMap compile_map(const std::string& text) {
         bm.src_i = (uint8_t)s.pos.i;
         bm.src_j = (uint8_t)s.pos.j;
         std::memcpy(cm.blob.data() + h.beams_off + b * sizeof(LleBeam), &bm, sizeof bm);
+    }
+    // per-cell lookup tables
+    {
+        std::vector<uint32_t> info((size_t)HW, 0);
+        std::vector<LleCellBeams> cb((size_t)HW);
+        const int adi[4] = {-1, 1, 0, 0}, adj[4] = {0, 0, 1, -1};  // Action deltas N, S, E, W (action.rs:18-26)
+        for (int i = 0; i < H; ++i) {
+            for (int j = 0; j < W; ++j) {
+                const int c = i * W + j;
+                uint32_t nbr = 0;
+                for (int act = 0; act < 4; ++act) {
+                    int ti = i + adi[act], tj = j + adj[act];
+                    if (ti >= 0 && tj >= 0 && ti < H && tj < W && (tiles[ti * W + tj] & 7u) != LLE_T_WALL) nbr |= 1u << act;
+                }
+                info[c] = (tiles[c] & 7u) | (nbr << 3) | ((uint32_t)(tiles[c] >> 8) << 8);
+                for (int n = 0; n < 4; ++n) cb[c].e[n] = LLE_NO_BEAM;
+                const auto& lst = cell_beams[c];
+                if (lst.size() > 4) throw MapError(LLE_LIMIT_EXCEEDED, "more than four beams cross one cell");
+                for (size_t n = 0; n < lst.size(); ++n) {
+                    const int b = lst[n].first, k = lst[n].second;
+                    const auto& src = cm.sources[b];
+                    const uint32_t listed = (vis[b] >> k) & 1ull;
+                    cb[c].e[n] = (uint32_t)b | ((uint32_t)k << 6) | ((uint32_t)src.colour << 12) | ((uint32_t)src.len << 20) |
+                                 (1u << 27) | (listed << 28);
+                }
+            }
+        }
+        std::memcpy(cm.blob.data() + h.cellinfo_off, info.data(), info.size() * sizeof(uint32_t));
+        std::memcpy(cm.blob.data() + h.cellbeams_off, cb.data(), cb.size() * sizeof(LleCellBeams));
     }
     if (!patch.empty()) std::memcpy(cm.blob.data() + h.patch_off, patch.data(), patch.size() * sizeof(LlePatch));
     std::memcpy(cm.blob.data() + h.static_off, stat.data(), stat.size() * sizeof(float));

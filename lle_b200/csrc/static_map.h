@@ -43,12 +43,26 @@ struct LlePatch {
 };
 static_assert(sizeof(LlePatch) == 8, "LlePatch layout");
 
+// Per-cell lookup tables used by the step kernel (one load each instead of a scan over all beams):
+//   cellinfo[cell]  : bits 0-2 base tile kind | bits 3-6 walkable-neighbour mask indexed by Action value
+//                     (N, S, E, W: in bounds and neither Wall nor LaserSource, tile.rs:63-73) | bits 8-15 gem index
+//   cellbeams[cell] : the (at most four: one per direction of travel) beams crossing the cell, inner first.
+//                     entry = b (0-5) | k<<6 (6-11) | colour<<12 (12-19) | len<<20 (20-26) | enabled<<27 | listed<<28
+//                     (listed: the laser tile is one of the two reported by World::lasers(), world.rs:159-172);
+//                     0xFFFFFFFF = no entry.
+#define LLE_NO_BEAM 0xFFFFFFFFu
+struct LleCellBeams {
+    uint32_t e[4];
+};
+
 // Per-map header; all *_off are byte offsets from the start of the map blob (16-byte aligned).
 struct LleMapHeader {
     int32_t H, W, A, G, NB, C;
     int32_t n_patch;
     int32_t obs_floats;       // C*H*W
     uint32_t tiles_off;       // uint16_t[H*W]
+    uint32_t cellinfo_off;    // uint32_t[H*W]
+    uint32_t cellbeams_off;   // LleCellBeams[H*W]
     uint32_t beams_off;       // LleBeam[NB]
     uint32_t patch_off;       // LlePatch[n_patch]
     uint32_t static_off;      // float[C*H*W]
@@ -59,18 +73,19 @@ struct LleMapHeader {
     uint16_t gem_pos[LLE_MAX_GEMS];   // packed position, gems_positions order (parser_v1.rs:149)
 };
 
-// ---- dynamic per-env record: `n_words` 32-bit words, stored word-major (words[w*N + env]) so that a
-// warp reading word w of 32 consecutive envs issues one 128-byte transaction.
-//   [0, w_flags)                packed positions, two u16 per word
-//   [w_flags, w_gems)           A <= 8: alive | arrived<<8 | slot<<16 | misc<<24 ; else alive, arrived, slot, misc
-//                               misc = n_arrived(4 or 8 bits) | n_deads(sat.) | done   (see step_core.cuh)
-//   [w_gems, w_on)              collected mask (0, 1 or 2 words)
-//   [w_on, n_words)             beam on-masks, 1 word per beam when every beam is <= 32 cells, else 2
+// ---- dynamic per-env record: `stride` 32-bit words per environment, stored contiguously (array of
+// records): a warp owns one world at a time and moves its record with one coalesced transaction.
+//   [0, w_flags)        packed positions (i<<8 | j), two per word
+//   [w_flags, w_gems)   A <= 8: alive | arrived<<8 | slot<<16 | n_arrived<<24 (4 bits) | n_deads<<28 (3 bits, saturating)
+//                       | done<<31 ; else four words: alive, arrived, slot, n_arrived | n_deads<<8 | done<<16
+//   [w_gems, w_on)      collected mask (0, 1 or 2 words)
+//   [w_on, n_words)     beam on-masks (LaserBeam.beam, laser.rs:16): 1 word per beam when every beam of the
+//                       batch is <= 32 cells, else 2
 struct LleStateLayout {
     int32_t n_words, w_flags, w_gems, w_on;
-    int32_t gem_words, on_words;  // per-gem-mask words (0/1/2), words per beam (1/2)
+    int32_t gem_words, on_words;  // words of the gem mask (0/1/2), words per beam (1/2)
     int32_t wide_flags;           // A > 8
-    int32_t pad;
+    int32_t stride;               // n_words rounded up to 4 words (16 bytes)
 };
 
 #ifdef __cplusplus
@@ -83,7 +98,7 @@ static inline LleStateLayout lle_state_layout(int A, int G, int NB, int max_beam
     L.w_on = L.w_gems + L.gem_words;
     L.on_words = max_beam_len <= 32 ? 1 : 2;
     L.n_words = L.w_on + NB * L.on_words;
-    L.pad = 0;
+    L.stride = (L.n_words + 3) / 4 * 4;
     return L;
 }
 #endif

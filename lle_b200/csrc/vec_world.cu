@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -12,49 +13,9 @@
 #include "../../include/lle_b200.h"
 #include "levels_embedded.inc"
 #include "map_compiler.hpp"
-#include "vec_kernels.cuh"
+#include "world_kernel.cuh"
 
 namespace lle {
-
-// Unpacks the per-env records for white-box comparisons (tests) and `get_state`-style host queries.
-__global__ void lle_export_raw_kernel(const uint32_t* words, LleStateLayout L, int64_t N, int64_t N_pad, int A, int NBmax,
-                                      int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
-                                      uint64_t* collected, uint8_t* counters) {
-    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= N) return;
-    auto ld = [&](int w) { return words[(int64_t)w * N_pad + env]; };
-    uint32_t al, ar, sl, na, nd, dn;
-    if (!L.wide_flags) {
-        uint32_t f = ld(L.w_flags);
-        al = f & 0xFF; ar = (f >> 8) & 0xFF; sl = (f >> 16) & 0xFF; na = (f >> 24) & 0xF; nd = (f >> 28) & 7; dn = f >> 31;
-    } else {
-        al = ld(L.w_flags); ar = ld(L.w_flags + 1); sl = ld(L.w_flags + 2);
-        uint32_t m = ld(L.w_flags + 3);
-        na = m & 0xFF; nd = (m >> 8) & 0xFF; dn = (m >> 16) & 1;
-    }
-    for (int a = 0; a < A; ++a) {
-        uint32_t w = ld(a >> 1);
-        uint32_t pp = (a & 1) ? (w >> 16) : (w & 0xFFFF);
-        if (pos) { pos[(env * A + a) * 2] = (int16_t)(pp >> 8); pos[(env * A + a) * 2 + 1] = (int16_t)(pp & 0xFF); }
-        if (alive) alive[env * A + a] = (al >> a) & 1;
-        if (arrived) arrived[env * A + a] = (ar >> a) & 1;
-        if (slot) slot[env * A + a] = (sl >> a) & 1;
-    }
-    if (collected) {
-        uint64_t c = 0;
-        if (L.gem_words >= 1) c = ld(L.w_gems);
-        if (L.gem_words == 2) c |= (uint64_t)ld(L.w_gems + 1) << 32;
-        collected[env] = c;
-    }
-    if (beam_on) {
-        for (int b = 0; b < NBmax; ++b) {
-            uint64_t v = ld(L.w_on + b * L.on_words);
-            if (L.on_words == 2) v |= (uint64_t)ld(L.w_on + b * 2 + 1) << 32;
-            beam_on[env * NBmax + b] = v;
-        }
-    }
-    if (counters) { counters[env * 3] = (uint8_t)na; counters[env * 3 + 1] = (uint8_t)nd; counters[env * 3 + 2] = (uint8_t)dn; }
-}
 
 // ---------------------------------------------------------------------------------------- host side
 thread_local std::string g_error;
@@ -67,14 +28,6 @@ int fail(int code, const std::string& msg) { g_error = msg; return code; }
             return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? LLE_NO_DEVICE : LLE_CUDA_ERROR, \
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
     } while (0)
-
-#define LLE_DECL_BUCKET(A, NB)                                                                  \
-    cudaError_t launch_bucket_##A##_##NB(const KParams& p, int grid, size_t smem, cudaStream_t s); \
-    cudaError_t occupancy_bucket_##A##_##NB(size_t smem, int* blocks);
-LLE_DECL_BUCKET(4, 4)
-LLE_DECL_BUCKET(8, 8)
-LLE_DECL_BUCKET(8, 16)
-LLE_DECL_BUCKET(16, 16)
 
 }  // namespace lle
 
@@ -89,13 +42,12 @@ struct lle_vec {
     int device = 0;
     int64_t N = 0, N_pad = 0;
     int A = 0, G = 0, NBmax = 0, C = 0, H = 0, W = 0, S = 0, R = 1, max_beam_len = 0;
-    int bucket = 0;  // index into kBuckets
     LleStateLayout L;
     // device memory
     std::vector<uint8_t*> d_blobs;
     const uint8_t** d_blob_table = nullptr;
     int32_t* d_map_of_env = nullptr;
-    uint32_t* d_words = nullptr;
+    uint32_t* d_records = nullptr;
     float* d_obs = nullptr;
     float* d_state = nullptr;
     uint8_t* d_avail = nullptr;
@@ -108,7 +60,7 @@ struct lle_vec {
     int8_t* d_actions_stage = nullptr;  // for step_host
     int64_t obs_stride = 0;
     // launch configuration
-    int grid = 0, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, desc_words = 0, warp_smem = 0;
+    int grid = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
     size_t smem = 0;
     uint64_t t = 0, launches = 0;
     // timing
@@ -118,23 +70,14 @@ struct lle_vec {
 
 namespace {
 
-int desc_words_of(int bucket) { return (kBuckets[bucket].amax + 1) / 2 + 2 + 2 * kBuckets[bucket].nbmax; }
-
 cudaError_t launch(lle_vec* v, const KParams& p, cudaStream_t s) {
-    switch (v->bucket) {
-        case 0: return launch_bucket_4_4(p, v->grid, v->smem, s);
-        case 1: return launch_bucket_8_8(p, v->grid, v->smem, s);
-        case 2: return launch_bucket_8_16(p, v->grid, v->smem, s);
-        default: return launch_bucket_16_16(p, v->grid, v->smem, s);
-    }
+    lle_world_kernel<<<v->grid, kThreads, v->smem, s>>>(p);
+    return cudaGetLastError();
 }
-cudaError_t occupancy(int bucket, size_t smem, int* blocks) {
-    switch (bucket) {
-        case 0: return occupancy_bucket_4_4(smem, blocks);
-        case 1: return occupancy_bucket_8_8(smem, blocks);
-        case 2: return occupancy_bucket_8_16(smem, blocks);
-        default: return occupancy_bucket_16_16(smem, blocks);
-    }
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : fallback;
 }
 
 KParams base_params(lle_vec* v) {
@@ -142,7 +85,7 @@ KParams base_params(lle_vec* v) {
     std::memset(&p, 0, sizeof p);
     p.blobs = v->d_blob_table;
     p.map_of_env = v->d_map_of_env;
-    p.words = v->d_words;
+    p.records = v->d_records;
     p.L = v->L;
     p.N = v->N;
     p.N_pad = v->N_pad;
@@ -154,10 +97,11 @@ KParams base_params(lle_vec* v) {
     p.seed = v->opts.seed; p.env_id_base = v->opts.env_id_base; p.t = v->t;
     p.auto_reset = v->opts.auto_reset; p.lle_semantics = v->opts.lle_semantics;
     p.walkable = v->opts.walkable_lasers; p.write_obs = v->opts.write_obs;
-    p.E = v->E; p.n_chunks = v->n_chunks; p.chunk_floats = v->chunk_floats; p.tile_floats = v->tile_floats;
+    p.Wd = v->Wd; p.group = v->group; p.E = v->E; p.n_chunks = v->n_chunks; p.chunk_floats = v->chunk_floats; p.tile_floats = v->tile_floats;
+    p.n_buf = v->n_buf;
     p.warp_smem_bytes = v->warp_smem;
     p.sched = v->d_sched;
-    p.n_units = (uint32_t)(v->N_pad / 32);
+    p.n_tickets = (uint32_t)(v->N_pad / v->group);
     p.n_warps_total = (uint32_t)(v->grid * kWarps);
     return p;
 }
@@ -269,7 +213,7 @@ int lle_vec_destroy(lle_vec* v) {
     if (!v) return LLE_OK;
     cudaSetDevice(v->device);
     for (auto* b : v->d_blobs) cudaFree(b);
-    cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_words); cudaFree(v->d_obs); cudaFree(v->d_state);
+    cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
     cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_actions_stage);
     if (v->ev0) cudaEventDestroy(v->ev0);
@@ -298,48 +242,57 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (map_of_env)
         for (int64_t e = 0; e < n_envs; ++e)
             if (map_of_env[e] < 0 || map_of_env[e] >= n_maps) return fail(LLE_INVALID_ARGUMENT, "map_of_env out of range");
-    v->bucket = -1;
-    for (int b = 0; b < kNumBuckets; ++b)
-        if (v->A <= kBuckets[b].amax && v->NBmax <= kBuckets[b].nbmax) { v->bucket = b; break; }
-    if (v->bucket < 0)
-        return fail(LLE_LIMIT_EXCEEDED, "the device path supports up to 16 agents and 16 laser sources per map");
     v->N = n_envs;
     v->N_pad = (n_envs + 31) / 32 * 32;
     v->L = lle_state_layout(v->A, v->G, v->NBmax, v->max_beam_len);
     v->obs_stride = ((int64_t)v->C * v->H * v->W + 3) / 4 * 4;
-    v->desc_words = desc_words_of(v->bucket);
 
     LLE_CUDA(cudaSetDevice(v->device));
     cudaDeviceProp prop;
     LLE_CUDA(cudaGetDeviceProperties(&prop, v->device));
 
-    // ---- observation tiling: one bulk store should move ~4-8 KB; tiles are double-buffered per warp
+    // ---- work decomposition and observation tiling.  One bulk store should move a few KB; a warp takes a
+    // ticket for `group` consecutive worlds, computes them, then streams their observation tiles.
+    v->Wd = 1;
+    while (v->Wd < v->A) v->Wd *= 2;
+    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", 1)));
     const int64_t stride = v->obs_stride;
-    const int64_t kTileTargetFloats = 2048, kTileMaxFloats = 6144;  // 8 KB target, 24 KB cap per buffer
+    const int64_t kTileTargetFloats = 2048, kTileMaxFloats = 6144;  // 8 KB target, 24 KB cap per tile buffer
     if (stride <= kTileMaxFloats) {
         v->n_chunks = 1;
         v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
         v->chunk_floats = (int)stride;
         v->tile_floats = (int)(v->E * stride);
+        v->group = std::max(std::max(v->E, 4), 32 / v->Wd);
+        v->n_buf = 1;
     } else {
         v->E = 1;
         v->chunk_floats = (int)kTileMaxFloats / 2;  // 12 KB chunks
         v->n_chunks = (int)((stride + v->chunk_floats - 1) / v->chunk_floats);
         v->tile_floats = v->chunk_floats;
+        v->group = std::max(8, 32 / v->Wd);
+        v->n_buf = 2;
+    }
+    v->n_buf = std::max(1, std::min(2, env_int("LLE_B200_NBUF", v->n_buf)));          // tuning knobs (development)
+    {
+        int g = env_int("LLE_B200_GROUP", v->group);
+        if (g >= v->E && g >= 32 / v->Wd && g <= 32 && (g & (g - 1)) == 0) v->group = g;
     }
     {
-        size_t bytes = (size_t)2 * v->tile_floats * 4;          // tiles
-        bytes += (size_t)v->desc_words * 32 * 4;                // unit descriptors
-        bytes += (size_t)2 * v->E * v->desc_words * 4;          // applied descriptors
-        bytes += (size_t)(2 * v->E + 2) * 4;                    // tags
+        size_t bytes = (size_t)v->n_buf * v->tile_floats * 4;             // tiles
+        bytes += (size_t)v->group * v->L.stride * 4;                      // records of the group
+        bytes += (size_t)v->n_buf * v->E * v->L.stride * 4;               // records applied to the tiles
+        bytes += (size_t)(v->n_buf * v->E + v->n_buf + v->group) * 4;     // tags + map ids
         v->warp_smem = (int)((bytes + 127) / 128 * 128);
         v->smem = (size_t)v->warp_smem * kWarps;
     }
     int blocks_per_sm = 0;
-    LLE_CUDA(occupancy(v->bucket, v->smem, &blocks_per_sm));
+    LLE_CUDA(cudaFuncSetAttribute(lle_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
+    LLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lle_world_kernel, kThreads, v->smem));
     if (blocks_per_sm < 1) return fail(LLE_CUDA_ERROR, "kernel does not fit on an SM");
-    const int64_t n_units = v->N_pad / 32;
-    v->grid = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * blocks_per_sm, (n_units + kWarps - 1) / kWarps);
+    blocks_per_sm = std::min(blocks_per_sm, std::max(1, env_int("LLE_B200_MAX_CTAS_PER_SM", 16)));
+    const int64_t n_tickets = v->N_pad / v->group;
+    v->grid = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * blocks_per_sm, (n_tickets + kWarps - 1) / kWarps);
     v->grid = std::max(v->grid, 1);
 
     // ---- device memory
@@ -364,7 +317,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->d_map_of_env = nullptr;
     }
     const size_t Np = (size_t)v->N_pad;
-    LLE_CUDA(dalloc(&v->d_words, (size_t)v->L.n_words * Np));
+    LLE_CUDA(dalloc(&v->d_records, (size_t)v->L.stride * Np));
     if (opts->write_obs) LLE_CUDA(dalloc(&v->d_obs, (size_t)v->obs_stride * Np));
     LLE_CUDA(dalloc(&v->d_state, (size_t)v->S * Np));
     LLE_CUDA(dalloc(&v->d_avail, (size_t)v->A * 5 * Np));
@@ -455,7 +408,7 @@ int lle_vec_export_raw(lle_vec* v, int16_t* pos, uint8_t* alive, uint8_t* arrive
     LLE_CUDA(cudaSetDevice(v->device));
     int threads = 128;
     int blocks = (int)((v->N + threads - 1) / threads);
-    lle_export_raw_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(v->d_words, v->L, v->N, v->N_pad, v->A, v->NBmax,
+    lle_export_raw_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(v->d_records, v->L, v->N, v->A, v->NBmax,
                                                                       pos, alive, arrived, slot, v->NBmax ? beam_on : nullptr, collected, counters);
     LLE_CUDA(cudaGetLastError());
     v->launches++;

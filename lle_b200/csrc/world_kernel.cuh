@@ -1,0 +1,783 @@
+// lle_b200 — the fused `World` step kernel for NVIDIA B200 (sm_100a).  Device code only.
+//
+// One launch advances N independent worlds by one joint action (or resets them, or forces a state) and
+// writes every per-step output of the reference's `LLE.step`:
+//   world.rs:435-475 (step) . world.rs:343-363 (availability) . reward_strategy.py:58-109 .
+//   env.py:253-254 (done) . pyworld_state.rs:79-101 (state vector) . observations.py:254-266 (layered).
+//
+// Layout of the work — "warp per world, lane per agent":
+//   * A warp takes a ticket for a small group of consecutive worlds and handles them one after the other.
+//   * The world's record (a few 32-bit words, contiguous in HBM) is copied into the warp's shared memory with
+//     one coalesced load.  Lane a owns agent a: its position, its action, its event.  The per-agent flags
+//     (alive / arrived / tile slot) are warp-uniform bitmasks maintained with __ballot_sync; the beam masks
+//     (`LaserBeam.beam`) stay in shared memory and are updated with shared-memory atomics
+//     (leave: OR of a suffix, pre_enter: AND of a prefix), which is order-independent exactly like the
+//     reference's sequential loops.  No thread ever scans a beam cell by cell: a per-cell
+//     table gives the (at most four) beams through the cell and the agent's offset on each.
+//   * The layered observation is not recomputed cell by cell either.  Each warp keeps observation tiles in
+//     shared memory, initialised from the map's static plane; for the next world it un-patches the few cells
+//     that depended on the previous occupant's state, patches the new ones (agents, lit laser cells,
+//     uncollected gems) and hands the tile to the TMA engine with ONE `cp.async.bulk.global.shared::cta`
+//     (SASS: UBLKCP) per tile.  The LSU never touches the 7.5 KB of an observation, and the store drains
+//     while the warp already computes its next world.
+//   * Small outputs (state vector, availability, reward, done, events, actions, err) are written by the warp
+//     with coalesced stores straight from registers / the shared record.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "static_map.h"
+
+namespace lle {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+enum Mode : int { MODE_STEP = 0, MODE_RESET = 1, MODE_SET_STATE = 2 };
+
+// event codes of one agent in one pass (bits 0-1 of the exported event byte)
+enum : uint32_t { EV_NONE = 0, EV_EXIT = 1, EV_GEM = 2, EV_DIED = 3 };
+
+// per-env error codes (LLE_ENV_* of include/lle_b200.h)
+enum : uint32_t {
+    ERR_OK = 0,
+    ERR_INVALID_ACTION = 1,      // RuntimeWorldError::InvalidAction (world.rs:444-453)
+    ERR_DONE = 2,                // "Cannot step in a done environment" (env.py:166-167)
+    ERR_STATE_DUPLICATE = 3,     // world.rs:529-534
+    ERR_STATE_OUT_OF_WORLD = 4,  // world.rs:536-540
+    ERR_STATE_NOT_WALKABLE = 5,  // world.rs:556-568
+    ERR_STATE_MISMATCH = 6,      // world.rs:588-594
+};
+
+struct KParams {
+    const uint8_t* const* blobs;  // device array [n_maps] of map blobs
+    const int32_t* map_of_env;    // device [N_pad] or nullptr
+    uint32_t* records;            // [N_pad][L.stride]
+    LleStateLayout L;
+    int64_t N, N_pad;
+    int32_t A, G, NBmax, C, H, W, S, R, HW;
+    float* obs;
+    int64_t obs_stride;  // floats per env
+    float* state;
+    uint8_t* avail;
+    float* reward;
+    uint8_t* done;
+    uint8_t* events;
+    int8_t* actions;
+    uint8_t* err;
+    const int8_t* actions_in;
+    const uint8_t* reset_mask;
+    const int32_t* ss_pos;
+    const uint8_t* ss_gems;
+    const uint8_t* ss_alive;
+    uint64_t seed, env_id_base, t;
+    int32_t mode, auto_reset, lle_semantics, walkable, write_obs;
+    // work decomposition / observation tiling
+    int32_t Wd;            // lanes per world: the power of two >= n_agents (32/Wd worlds share a warp)
+    int32_t group;         // worlds per ticket (multiple of E and of 32/Wd, divides 32)
+    int32_t E;             // worlds per tile (n_chunks == 1)
+    int32_t n_chunks;      // > 1: one world's block is streamed in chunks (E == 1)
+    int32_t chunk_floats;  // floats per chunk, multiple of 4
+    int32_t tile_floats;   // floats per shared-memory tile buffer
+    int32_t n_buf;         // tile buffers per warp (1 or 2)
+    int32_t warp_smem_bytes;
+    uint32_t* sched;       // [0] next ticket, [1] warps finished
+    uint32_t n_tickets, n_warps_total;
+};
+
+// ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- map view -------------------------------------------------------------------------------------------
+struct MapDev {
+    const uint8_t* blob;
+    const LleMapHeader* hdr;
+    const uint32_t* cellinfo;
+    const LleCellBeams* cellbeams;
+    const LleBeam* beams;
+    const LlePatch* patches;
+    const float* stat;
+    int n_patch, NB, obs_floats;
+    uint64_t gem_toplevel;
+    __device__ __forceinline__ void bind(const uint8_t* b) {
+        blob = b;
+        hdr = reinterpret_cast<const LleMapHeader*>(b);
+        cellinfo = reinterpret_cast<const uint32_t*>(b + hdr->cellinfo_off);
+        cellbeams = reinterpret_cast<const LleCellBeams*>(b + hdr->cellbeams_off);
+        beams = reinterpret_cast<const LleBeam*>(b + hdr->beams_off);
+        patches = reinterpret_cast<const LlePatch*>(b + hdr->patch_off);
+        stat = reinterpret_cast<const float*>(b + hdr->static_off);
+        n_patch = hdr->n_patch;
+        NB = hdr->NB;
+        obs_floats = hdr->obs_floats;
+        gem_toplevel = hdr->gem_toplevel;
+    }
+};
+
+// beam-entry fields (static_map.h: LleCellBeams)
+__device__ __forceinline__ int be_b(uint32_t e) { return e & 63u; }
+__device__ __forceinline__ int be_k(uint32_t e) { return (e >> 6) & 63u; }
+__device__ __forceinline__ int be_colour(uint32_t e) { return (e >> 12) & 255u; }
+__device__ __forceinline__ int be_len(uint32_t e) { return (e >> 20) & 127u; }
+__device__ __forceinline__ bool be_enabled(uint32_t e) { return (e >> 27) & 1u; }
+__device__ __forceinline__ bool be_listed(uint32_t e) { return (e >> 28) & 1u; }
+
+__device__ __forceinline__ uint64_t len_mask(int len) { return len >= 64 ? ~0ull : ((1ull << len) - 1ull); }
+
+// Action deltas on a packed position (i<<8 | j), src/action.rs:18-26 (N=0, S=1, E=2, W=3, STAY=4)
+__device__ __forceinline__ int act_delta(int a) { return a == 0 ? -256 : a == 1 ? 256 : a == 2 ? 1 : a == 3 ? -1 : 0; }
+
+// ---- Philox4x32-10 action stream -------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// k-th set bit of a 5-bit availability mask, k = mulhi(word, popcount)
+__device__ __forceinline__ uint32_t pick_action(uint32_t word, uint32_t mask) {
+    uint32_t k = __umulhi(word, (uint32_t)__popc(mask & 31u));
+    uint32_t m = mask & 31u;
+    for (uint32_t n = 0; n < k; ++n) m &= m - 1;  // drop the k lowest set bits
+    return m ? (uint32_t)(__ffs(m) - 1) : 4u;
+}
+
+// =============================================================================================================
+// Sub-warp groups: a warp processes P = 32/Wd worlds at once, Wd = the power of two >= n_agents.  Lane
+// (sub, gl) = (lane / Wd, lane % Wd) owns agent `gl` of the warp's world number `sub`.  Values that the
+// reference keeps per world (alive / arrived / slot masks, counters) are group-uniform registers holding
+// group-relative bit masks, maintained with group ballots; beam masks and the gem mask stay in the world's
+// shared-memory record and are updated with shared-memory atomics.  Every phase takes a per-lane predicate
+// (`on`: this lane's world takes part) so that worlds in one warp may diverge (errors, resets, extra passes)
+// while the warp stays converged for the shuffles.
+// =============================================================================================================
+struct World {
+    uint32_t* rec;      // this lane's world record in shared memory (layout L)
+    LleStateLayout L;
+    MapDev m;           // this lane's map (group-uniform)
+    int A, W, Wd, gl;   // agents, map width, group width, lane within group
+    uint32_t gbase, wmask, amask;
+    // per lane
+    uint32_t pos;
+    // group-uniform
+    uint32_t alive, arrived, slot, n_arrived, n_deads, done;
+
+    __device__ __forceinline__ uint32_t gballot(bool pred) const { return (__ballot_sync(kFull, pred) >> gbase) & wmask; }
+    __device__ __forceinline__ uint32_t gshfl(uint32_t v, int src) const { return __shfl_sync(kFull, v, src, Wd); }
+    __device__ __forceinline__ uint32_t cell(uint32_t p) const { return (p >> 8) * (uint32_t)W + (p & 0xFFu); }
+    __device__ __forceinline__ uint32_t* on_words(int b) const { return rec + L.w_on + b * L.on_words; }
+    __device__ __forceinline__ bool on_bit(int b, int k) const { return (on_words(b)[k >> 5] >> (k & 31)) & 1u; }
+    __device__ __forceinline__ uint64_t collected() const {
+        uint64_t c = 0;
+        if (L.gem_words >= 1) c = rec[L.w_gems];
+        if (L.gem_words == 2) c |= (uint64_t)rec[L.w_gems + 1] << 32;
+        return c;
+    }
+    // gl == 0 writes; callers synchronise
+    __device__ __forceinline__ void set_collected(uint64_t c) {
+        if (L.gem_words >= 1) rec[L.w_gems] = (uint32_t)c;
+        if (L.gem_words == 2) rec[L.w_gems + 1] = (uint32_t)(c >> 32);
+    }
+
+    // ---- record <-> registers
+    __device__ __forceinline__ void unpack() {
+        pos = 0;
+        if (gl < A) {
+            const uint32_t w = rec[gl >> 1];
+            pos = (gl & 1) ? (w >> 16) : (w & 0xFFFFu);
+        }
+        if (!L.wide_flags) {
+            const uint32_t f = rec[L.w_flags];
+            alive = f & 0xFFu; arrived = (f >> 8) & 0xFFu; slot = (f >> 16) & 0xFFu;
+            n_arrived = (f >> 24) & 0xFu; n_deads = (f >> 28) & 0x7u; done = f >> 31;
+        } else {
+            alive = rec[L.w_flags]; arrived = rec[L.w_flags + 1]; slot = rec[L.w_flags + 2];
+            const uint32_t mm = rec[L.w_flags + 3];
+            n_arrived = mm & 0xFFu; n_deads = (mm >> 8) & 0xFFu; done = (mm >> 16) & 1u;
+        }
+    }
+    // writes positions and flags (beam and gem masks are already in place); all lanes must call it
+    __device__ __forceinline__ void pack() {
+        const uint32_t other = __shfl_down_sync(kFull, pos, 1, Wd);
+        if (gl < A && !(gl & 1)) rec[gl >> 1] = pos | ((gl + 1 < A ? other : 0u) << 16);
+        if (gl == 0) {
+            if (!L.wide_flags) {
+                const uint32_t nd = n_deads > 7u ? 7u : n_deads;  // only "> 0" is ever observed (env.py:253-254)
+                rec[L.w_flags] = alive | (arrived << 8) | (slot << 16) | (n_arrived << 24) | (nd << 28) | (done << 31);
+            } else {
+                rec[L.w_flags] = alive; rec[L.w_flags + 1] = arrived; rec[L.w_flags + 2] = slot;
+                rec[L.w_flags + 3] = (n_arrived & 0xFFu) | ((n_deads > 255u ? 255u : n_deads) << 8) | (done << 16);
+            }
+        }
+    }
+
+    // ---- tile protocol, lane-parallel ---------------------------------------------------------------------
+    // Tile::leave for the alive agents (tile.rs:52-61, laser.rs:199-202 + :157-162 + :50-55): every beam through
+    // the agent's cell whose bit there is off is re-armed from that offset on (unless disabled); the slot clears.
+    __device__ __forceinline__ void leave_all(bool on) {
+        const bool active = on && gl < A && ((alive >> gl) & 1u);
+        if (active) {
+            const LleCellBeams cb = m.cellbeams[cell(pos)];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const uint32_t e = cb.e[n];
+                if (e != LLE_NO_BEAM && be_enabled(e) && !on_bit(be_b(e), be_k(e))) {
+                    const uint64_t msk = (~0ull << be_k(e)) & len_mask(be_len(e));
+                    uint32_t* w = on_words(be_b(e));
+                    if ((uint32_t)msk) atomicOr(w, (uint32_t)msk);
+                    if (L.on_words == 2 && (uint32_t)(msk >> 32)) atomicOr(w + 1, (uint32_t)(msk >> 32));
+                }
+            }
+        }
+        slot &= ~gballot(active);
+        __syncwarp();
+    }
+    // Tile::pre_enter at `target` (tile.rs:21-27, laser.rs:173-182): an alive agent cuts the enabled beams of its
+    // own colour from its offset on.  `alive_flags` are the flags the reference sees at that point.
+    __device__ __forceinline__ void pre_enter_all(bool on, uint32_t target, uint32_t alive_flags) {
+        if (on && gl < A && ((alive_flags >> gl) & 1u)) {
+            const LleCellBeams cb = m.cellbeams[cell(target)];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const uint32_t e = cb.e[n];
+                if (e != LLE_NO_BEAM && be_enabled(e) && be_colour(e) == gl) {
+                    const uint64_t msk = (1ull << be_k(e)) - 1ull;
+                    uint32_t* w = on_words(be_b(e));
+                    atomicAnd(w, (uint32_t)msk);
+                    if (L.on_words == 2) atomicAnd(w + 1, (uint32_t)(msk >> 32));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // Tile::enter at `target` (tile.rs:29-50, laser.rs:184-197, gem.rs:26-35, void.rs:13-22).  An on beam of
+    // another colour stops the agent before the wrapped tile (alive -> dies, dead -> nothing; the base tile is
+    // NOT entered).  Otherwise the base tile takes the agent.  Returns this lane's event code.
+    __device__ __forceinline__ uint32_t enter_all(bool on, uint32_t target) {
+        uint32_t code = EV_NONE;
+        bool die = false, arrive = false, take_slot = false;
+        if (on && gl < A) {
+            const uint32_t c = cell(target);
+            const LleCellBeams cb = m.cellbeams[c];
+            bool lethal = false;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const uint32_t e = cb.e[n];
+                if (e != LLE_NO_BEAM && be_colour(e) != gl && on_bit(be_b(e), be_k(e))) lethal = true;
+            }
+            const bool is_alive = (alive >> gl) & 1u;
+            if (lethal) {
+                if (is_alive) { die = true; code = EV_DIED; }
+            } else {
+                take_slot = true;
+                const uint32_t info = m.cellinfo[c];
+                const uint32_t kind = info & 7u;
+                if (kind == LLE_T_EXIT) {
+                    if (!((arrived >> gl) & 1u)) { arrive = true; code = EV_EXIT; }
+                } else if (kind == LLE_T_GEM) {
+                    const uint32_t g = (info >> 8) & 63u;
+                    uint32_t* gw = rec + L.w_gems + (g >> 5);
+                    if (!((*gw >> (g & 31u)) & 1u)) {  // no two agents share a cell: no race on this bit
+                        atomicOr(gw, 1u << (g & 31u));
+                        code = EV_GEM;
+                    }
+                } else if (kind == LLE_T_VOID) {
+                    if (is_alive) { die = true; code = EV_DIED; }
+                }
+            }
+        }
+        alive &= ~gballot(die);
+        arrived |= gballot(arrive);
+        slot |= gballot(take_slot);
+        __syncwarp();
+        return code;
+    }
+    // all tiles reset (tile.rs:75-84; laser.rs:168-171: an enabled beam ends fully on, a disabled one stays off)
+    __device__ __forceinline__ void tiles_reset(bool on) {
+        if (on) {
+            for (int b = gl; b < m.NB; b += Wd) {
+                const LleBeam bm = m.beams[b];
+                const uint64_t v = bm.enabled ? len_mask(bm.len) : 0ull;
+                on_words(b)[0] = (uint32_t)v;
+                if (L.on_words == 2) on_words(b)[1] = (uint32_t)(v >> 32);
+            }
+            if (gl == 0) set_collected(0);
+            slot = 0;
+        }
+        __syncwarp();
+    }
+    // World::reset (world.rs:411-432) with one start per agent (RNG-free, utils/mod.rs:63), then
+    // RewardStrategy.reset / LLE.reset bookkeeping (env.py:191-203).
+    __device__ __forceinline__ void reset(bool on) {
+        tiles_reset(on);
+        if (on) {
+            alive = amask; arrived = 0; n_arrived = 0; n_deads = 0; done = 0;
+            pos = gl < A ? (uint32_t)m.hdr->start[gl] : 0u;
+        }
+        pre_enter_all(on, pos, alive);
+        (void)enter_all(on, pos);  // events are dropped (world.rs:428-430)
+    }
+    // World::compute_available_actions (world.rs:343-363) as a 5-bit mask indexed by Action value.
+    __device__ __forceinline__ uint32_t available() const {
+        const bool active = gl < A && ((alive >> gl) & 1u) && !((arrived >> gl) & 1u);
+        uint32_t nbr = 0;
+        if (active) nbr = (m.cellinfo[cell(pos)] >> 3) & 15u;
+        for (int o = 0; o < A; ++o) {
+            const uint32_t op = gshfl(pos, o);
+            if (((slot >> o) & 1u) && o != gl) {  // Tile::is_occupied (tile.rs:97-99)
+                const int d = (int)op - (int)pos;
+                if (d == -256) nbr &= ~1u;
+                else if (d == 256) nbr &= ~2u;
+                else if (d == 1) nbr &= ~4u;
+                else if (d == -1) nbr &= ~8u;
+            }
+        }
+        return 16u | nbr;  // Stay is always listed
+    }
+    // LLE.available_actions with walkable_lasers == False (env.py:153-163): drop every listed action (STAY
+    // included) whose target holds an on, listed (world.rs:159-172) laser of another colour.
+    __device__ __forceinline__ uint32_t available_no_walk(uint32_t mask) const {
+        uint32_t out = 0;
+        if (gl < A) {
+#pragma unroll
+            for (int act = 0; act < 5; ++act) {
+                if (!((mask >> act) & 1u)) continue;
+                const LleCellBeams cb = m.cellbeams[cell(pos + act_delta(act))];
+                bool blocked = false;
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const uint32_t e = cb.e[n];
+                    if (e != LLE_NO_BEAM && be_listed(e) && be_colour(e) != gl && on_bit(be_b(e), be_k(e))) blocked = true;
+                }
+                if (!blocked) out |= 1u << act;
+            }
+        }
+        return out;
+    }
+    // World::step after validation (world.rs:454-472) for the worlds with `on`.  Returns this lane's event byte;
+    // the counts are group-uniform.
+    __device__ __forceinline__ uint32_t step(bool on, uint32_t act, uint32_t& n_gem, uint32_t& n_exit, uint32_t& n_died) {
+        uint32_t np = (on && gl < A) ? pos + act_delta(act) : 0xFFFF0000u + gl;  // inactive lanes never collide
+        // vertex conflicts (world.rs:365-378 + utils/mod.rs:18-36): every agent whose target is shared goes back
+        for (;;) {
+            bool dup = false;
+            for (int o = 0; o < A; ++o) {
+                const uint32_t other = gshfl(np, o);
+                if (o != gl && other == np) dup = true;
+            }
+            dup = dup && on && gl < A;
+            if (!__any_sync(kFull, dup)) break;
+            if (dup) np = pos;
+        }
+        uint32_t ev = 0;
+        n_gem = n_exit = n_died = 0;
+        bool again = on;  // move_agents (world.rs:477-505), repeated while an agent of this world died (:468-472)
+        for (uint32_t pass = 1;; ++pass) {
+            leave_all(again);
+            pre_enter_all(again, np, alive);
+            const uint32_t code = enter_all(again, np);
+            if (pass == 1) {
+                ev = code;
+                if (on && gl < A) pos = np;
+            } else if (code != EV_NONE) {
+                ev |= (pass > 63u ? 63u : pass) << 2;  // passes >= 2 can only emit deaths
+            }
+            const uint32_t died = gballot(code == EV_DIED);
+            n_died += __popc(died);
+            n_gem += __popc(gballot(code == EV_GEM));
+            n_exit += __popc(gballot(code == EV_EXIT));
+            again = again && died != 0;
+            if (!__any_sync(kFull, again)) break;
+        }
+        return ev;
+    }
+    // SingleObjective / MultiObjective.compute_reward (reward_strategy.py:58-75, :90-109) and LLE.compute_done
+    // (env.py:253-254): updates the counters (if `on`); component r of the reward.
+    __device__ __forceinline__ void account(bool on, uint32_t n_exit, uint32_t n_died) {
+        if (on) {
+            n_arrived += n_exit;
+            n_deads += n_died;
+            done = (n_arrived == (uint32_t)A || n_deads > 0) ? 1u : 0u;
+        }
+    }
+    __device__ __forceinline__ float reward_component(int r, int R, uint32_t n_gem, uint32_t n_exit, uint32_t n_died) const {
+        const bool all_in = n_arrived == (uint32_t)A;
+        if (R == 1) return (float)n_gem + (float)n_exit - (float)n_died + (all_in ? 1.0f : 0.0f);  // death override is dead code (:71-72)
+        switch (r) {
+            case 0: return n_died ? 0.0f : (float)n_gem;
+            case 1: return n_died ? 0.0f : (float)n_exit;
+            case 2: return -(float)n_died;
+            default: return (!n_died && all_in) ? 1.0f : 0.0f;
+        }
+    }
+    // Body of World::set_state after the argument checks (world.rs:541-594) for the worlds with `on`.  `target`
+    // per lane; sg / sa requested gem and alive masks.  Returns ERR_OK, ERR_STATE_NOT_WALKABLE (nothing entered)
+    // or ERR_STATE_MISMATCH per world (group-uniform).
+    __device__ __forceinline__ uint32_t set_state_apply(bool on, uint32_t target, uint64_t sg, uint32_t sa, uint32_t& code,
+                                                        uint32_t& n_gem, uint32_t& n_exit, uint32_t& n_died) {
+        code = EV_NONE;
+        n_gem = n_exit = n_died = 0;
+        tiles_reset(on);
+        if (on && gl == 0) set_collected(sg & m.gem_toplevel);  // only top-level Gem tiles can be force-collected (:550-554)
+        const bool wall = on && gl < A && (m.cellinfo[cell(target)] & 7u) == LLE_T_WALL;
+        const bool blocked = gballot(wall) != 0;  // :556-568
+        const bool go = on && !blocked;
+        __syncwarp();
+        pre_enter_all(go, target, alive);  // with the agents' *current* alive flags (:555)
+        if (go) {
+            if (gl < A) pos = target;  // :571
+            alive = amask;             // agent.reset() (:578)
+            arrived = 0;
+        }
+        code = enter_all(go, pos);
+        if (go) alive &= sa;  // forced death, no event (:583-585)
+        n_died = __popc(gballot(code == EV_DIED));
+        n_gem = __popc(gballot(code == EV_GEM));
+        n_exit = __popc(gballot(code == EV_EXIT));
+        if (!on) return ERR_OK;
+        if (blocked) return ERR_STATE_NOT_WALKABLE;
+        if (collected() != sg || alive != (sa & amask)) return ERR_STATE_MISMATCH;  // :588-594
+        return ERR_OK;
+    }
+};
+
+// ---- observation tile: descriptor bits read straight from a record ------------------------------------------
+__device__ __forceinline__ bool rec_lit(const uint32_t* rec, const LleStateLayout& L, const LlePatch& pe) {
+    if (pe.src == 0xFF)  // gem: lit while NOT collected (observations.py:260-263)
+        return !((rec[L.w_gems + (pe.bit >> 5)] >> (pe.bit & 31)) & 1u);
+    return (rec[L.w_on + pe.src * L.on_words + (pe.bit >> 5)] >> (pe.bit & 31)) & 1u;  // laser: lit while on (:256-259)
+}
+__device__ __forceinline__ uint32_t rec_pos(const uint32_t* rec, int a) {
+    const uint32_t w = rec[a >> 1];
+    return (a & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LleStateLayout L = p.L;
+    const int A = p.A, stride = L.stride;
+    uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
+    float* tiles = reinterpret_cast<float*>(wbase);                                          // [n_buf][tile_floats]
+    uint32_t* recs = reinterpret_cast<uint32_t*>(tiles + (size_t)p.n_buf * p.tile_floats);   // [group][stride]
+    uint32_t* applied = recs + (size_t)p.group * stride;                                     // [n_buf][E][stride]
+    int32_t* tags = reinterpret_cast<int32_t*>(applied + (size_t)p.n_buf * p.E * stride);    // [n_buf][E] map id, [n_buf] chunk
+    int32_t* map_ids = tags + p.n_buf * p.E + p.n_buf;                                       // [group]
+    for (int k = lane; k < p.n_buf * p.E + p.n_buf; k += 32) tags[k] = -1;
+    __syncwarp();
+
+    const int Wd = p.Wd, P = 32 / Wd;
+    World w;
+    w.L = L;
+    w.A = A;
+    w.W = p.W;
+    w.Wd = Wd;
+    w.gl = lane & (Wd - 1);
+    w.gbase = (uint32_t)(lane & ~(Wd - 1));
+    w.wmask = Wd >= 32 ? ~0u : ((1u << Wd) - 1u);
+    w.amask = A >= 32 ? ~0u : ((1u << A) - 1u);
+    const int sub = lane / Wd, gl = w.gl;
+    int bound_map = -1;       // map bound to this lane's World
+    MapDev rm;                // map bound for rendering (warp-uniform)
+    int render_map = -1;
+    int buf = 0;
+
+    for (;;) {
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&p.sched[0], 1u);
+        ticket = __shfl_sync(kFull, ticket, 0);
+        if (ticket >= p.n_tickets) break;
+        const int64_t env0 = (int64_t)ticket * p.group;
+
+        // ================================================================== logic: P worlds at a time
+        for (int g0 = 0; g0 < p.group; g0 += P) {
+            const int g = g0 + sub;
+            const int64_t env = env0 + g;  // N_pad is a multiple of the group size: always a world
+            const int map_id = p.map_of_env ? __ldg(p.map_of_env + env) : 0;
+            if (map_id != bound_map) {
+                w.m.bind(p.blobs[map_id]);
+                bound_map = map_id;
+            }
+            if (gl == 0) map_ids[g] = map_id;
+            uint32_t* rec = recs + (size_t)g * stride;
+            const uint32_t* grec = p.records + env * stride;
+            for (int k = gl; k < stride; k += Wd) rec[k] = grec[k];
+            __syncwarp();
+            w.rec = rec;
+            w.unpack();
+
+            uint32_t ev = 0, act = 4, err = ERR_OK, n_gem = 0, n_exit = 0, n_died = 0;
+            bool touch = true;  // whether reward/done/events/err/actions are (re)written
+            bool paid = false;  // whether a reward is due (a transition happened)
+            const bool real = env < p.N;
+
+            if (p.mode == MODE_STEP) {
+                const uint32_t av = w.available();
+                if (p.actions_in) {
+                    if (real && gl < A) act = (uint32_t)(uint8_t)p.actions_in[env * A + gl];  // padding worlds just STAY
+                } else {
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)p.t, (uint32_t)(gl >> 2), (uint32_t)(p.t >> 32),
+                                  (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+                    const uint32_t word = (gl & 3) == 0 ? r[0] : (gl & 3) == 1 ? r[1] : (gl & 3) == 2 ? r[2] : r[3];
+                    act = pick_action(word, av);
+                }
+                const bool bad = w.gballot(gl < A && (act > 4u || !((av >> act) & 1u))) != 0;
+                if (p.lle_semantics && w.done) err = ERR_DONE;
+                else if (bad) err = ERR_INVALID_ACTION;  // the world is left untouched (world.rs:444-453)
+                paid = err == ERR_OK;
+                ev = w.step(paid, act, n_gem, n_exit, n_died);
+                w.account(paid, n_exit, n_died);
+            } else if (p.mode == MODE_RESET) {
+                const bool on = !p.reset_mask || !real || p.reset_mask[env];
+                w.reset(on);
+                touch = on;
+            } else {  // MODE_SET_STATE: World::set_state (world.rs:515-597) + LLE.set_state (env.py:208-216)
+                touch = real;  // padding worlds: nothing to force
+                int si = 0, sj = 0;
+                bool want_alive = false;
+                if (real && gl < A) {
+                    si = p.ss_pos[(env * A + gl) * 2];
+                    sj = p.ss_pos[(env * A + gl) * 2 + 1];
+                    want_alive = p.ss_alive[env * A + gl] != 0;
+                }
+                const uint32_t sa = w.gballot(want_alive) & w.amask;
+                uint64_t sg = 0;
+                for (int b0 = 0; b0 < p.G; b0 += Wd) {
+                    const bool bit = real && b0 + gl < p.G && p.ss_gems[env * p.G + b0 + gl] != 0;
+                    sg |= (uint64_t)w.gballot(bit) << b0;
+                }
+                if (real && p.lle_semantics) {  // reward_strategy.reset() precedes world.set_state (env.py:213)
+                    w.n_arrived = 0;
+                    w.n_deads = 0;
+                }
+                bool dup = false;
+                for (int o = 0; o < A; ++o) {
+                    const int oi = (int)w.gshfl((uint32_t)si, o), oj = (int)w.gshfl((uint32_t)sj, o);
+                    if (o != gl && oi == si && oj == sj) dup = true;
+                }
+                const bool any_dup = w.gballot(dup && gl < A) != 0;
+                const bool any_oob = w.gballot(gl < A && (si < 0 || sj < 0 || si >= p.H || sj >= p.W)) != 0;
+                if (real) {
+                    if (any_dup) err = ERR_STATE_DUPLICATE;          // :529-534
+                    else if (any_oob) err = ERR_STATE_OUT_OF_WORLD;  // :536-540
+                }
+                const bool go = real && err == ERR_OK;
+                const uint32_t cur_pos = w.pos;  // current_state = self.get_state() (:541)
+                const uint64_t cur_g = w.collected();
+                const uint32_t cur_a = w.alive;
+                const uint32_t target = go ? (((uint32_t)si << 8) | (uint32_t)sj) : w.pos;
+                const uint32_t r1 = w.set_state_apply(go, target, sg, sa, ev, n_gem, n_exit, n_died);
+                if (go) err = r1;
+                // self.set_state(&current_state).unwrap() (:563): the previous state is re-derived, events dropped
+                const bool restore = go && r1 == ERR_STATE_NOT_WALKABLE;
+                if (__any_sync(kFull, restore)) {
+                    uint32_t e2, a2, b2, c2;
+                    (void)w.set_state_apply(restore, cur_pos, cur_g, cur_a, e2, a2, b2, c2);
+                }
+                if (restore) ev = 0;
+                // compute_reward(events); done = compute_done() (env.py:215-216)
+                w.account(go && err == ERR_OK && p.lle_semantics, n_exit, n_died);
+            }
+
+            if (touch) {
+                for (int r = gl; r < p.R; r += Wd)
+                    p.reward[env * p.R + r] = paid ? w.reward_component(r, p.R, n_gem, n_exit, n_died) : 0.0f;
+                if (gl == 0) {
+                    p.done[env] = (uint8_t)w.done;
+                    p.err[env] = (uint8_t)err;
+                }
+                if (gl < A) {
+                    p.events[env * A + gl] = (uint8_t)ev;
+                    p.actions[env * A + gl] = (int8_t)act;
+                }
+            }
+            // auto-reset: the transition above is reported; observation / state / availability below are those
+            // of the freshly reset world (SURVEY §8d "Auto-reset")
+            const bool do_reset = p.mode == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
+            if (__any_sync(kFull, do_reset)) w.reset(do_reset);
+
+            w.pack();
+            __syncwarp();
+            {   // record back to HBM and the small per-step vectors
+                uint32_t* out = p.records + env * stride;
+                for (int k = gl; k < stride; k += Wd) out[k] = rec[k];
+                // PyWorldState::as_array (pyworld_state.rs:79-101): [i0,j0,...,gems...,alive...]
+                const uint64_t coll = w.collected();
+                for (int k = gl; k < p.S; k += Wd) {
+                    float v;
+                    if (k < 2 * A) {
+                        const uint32_t pp = rec_pos(rec, k >> 1);
+                        v = (float)((k & 1) ? (pp & 0xFFu) : (pp >> 8));
+                    } else if (k < 2 * A + p.G) {
+                        v = ((coll >> (k - 2 * A)) & 1ull) ? 1.0f : 0.0f;
+                    } else {
+                        v = ((w.alive >> (k - 2 * A - p.G)) & 1u) ? 1.0f : 0.0f;
+                    }
+                    p.state[env * p.S + k] = v;
+                }
+                uint32_t mask = w.available();
+                if (!p.walkable) mask = w.available_no_walk(mask);
+                for (int k0 = 0; k0 < 5 * A; k0 += Wd) {  // LLE.available_actions (env.py:146-163): u8[A,5]
+                    const int k = k0 + gl;
+                    const uint32_t mk = w.gshfl(mask, (k / 5) & (Wd - 1));
+                    if (k < 5 * A) p.avail[env * 5 * A + k] = (uint8_t)((mk >> (k % 5)) & 1u);
+                }
+            }
+        }
+        __syncwarp();
+        if (!p.write_obs) continue;
+
+        // ================================================================== observations of the group
+        const int tiles_per_group = p.n_chunks > 1 ? p.group : p.group / p.E;
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+            const int lo = chunk * p.chunk_floats;  // float range [lo, hi) of one world's block
+            const int hi = min(lo + p.chunk_floats, (int)p.obs_stride);
+            for (int tix = 0; tix < tiles_per_group; ++tix) {
+                float* tile = tiles + (size_t)buf * p.tile_floats;
+                // the bulk store that last read this buffer must have finished reading it
+                if (lane == 0) {
+                    if (p.n_buf == 2) bulk_wait_read<1>();
+                    else bulk_wait_read<0>();
+                }
+                __syncwarp();
+                const int n_sub = p.n_chunks > 1 ? 1 : p.E;
+                for (int s = 0; s < n_sub; ++s) {
+                    const int g = p.n_chunks > 1 ? tix : tix * p.E + s;
+                    const int mid = map_ids[g];
+                    if (mid != render_map) {
+                        rm.bind(p.blobs[mid]);
+                        render_map = mid;
+                    }
+                    float* sub_tile = tile + (size_t)s * p.obs_stride;
+                    uint32_t* old = applied + ((size_t)buf * p.E + s) * stride;
+                    const uint32_t* cur = recs + (size_t)g * stride;
+                    const bool same = tags[buf * p.E + s] == mid && tags[p.n_buf * p.E + buf] == chunk;
+                    if (!same) {
+                        // (re)build from the map's static plane (observations.py:216-237); pad floats are zero
+                        const int nf = hi - lo;
+                        for (int f = lane * 4; f < nf; f += 128) {
+                            const int gi = lo + f;
+                            float4 v;
+                            if (gi + 3 < rm.obs_floats) {
+                                v = __ldg(reinterpret_cast<const float4*>(rm.stat + gi));
+                            } else {
+                                v.x = gi + 0 < rm.obs_floats ? __ldg(rm.stat + gi + 0) : 0.f;
+                                v.y = gi + 1 < rm.obs_floats ? __ldg(rm.stat + gi + 1) : 0.f;
+                                v.z = gi + 2 < rm.obs_floats ? __ldg(rm.stat + gi + 2) : 0.f;
+                                v.w = gi + 3 < rm.obs_floats ? __ldg(rm.stat + gi + 3) : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(sub_tile + f) = v;
+                        }
+                    } else {
+                        // un-patch what the previous occupant had lit and the new one has not
+                        if (lane < A) {
+                            const uint32_t op = rec_pos(old, lane);
+                            const int idx = lane * p.HW + (int)(op >> 8) * p.W + (int)(op & 0xFFu);
+                            if (idx >= lo && idx < hi) sub_tile[idx - lo] = 0.0f;  // agent planes have no static content
+                        }
+                        for (int k = lane; k < rm.n_patch; k += 32) {
+                            const LlePatch pe = rm.patches[k];
+                            if ((int)pe.idx >= lo && (int)pe.idx < hi && rec_lit(old, L, pe) && !rec_lit(cur, L, pe))
+                                sub_tile[pe.idx - lo] = (float)pe.stat;
+                        }
+                    }
+                    __syncwarp();
+                    // patch: lit laser cells and uncollected gems, then the agents (observations.py:256-265).  Every
+                    // lit entry is rewritten so that entries aliasing one cell (crossing beams of one colour,
+                    // colours >= n_agents) stay correct whatever was un-patched above.
+                    for (int k = lane; k < rm.n_patch; k += 32) {
+                        const LlePatch pe = rm.patches[k];
+                        if ((int)pe.idx >= lo && (int)pe.idx < hi && rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = 1.0f;
+                    }
+                    if (lane < A) {
+                        const uint32_t np = rec_pos(cur, lane);
+                        const int idx = lane * p.HW + (int)(np >> 8) * p.W + (int)(np & 0xFFu);
+                        if (idx >= lo && idx < hi) sub_tile[idx - lo] = 1.0f;
+                    }
+                    for (int k = lane; k < stride; k += 32) old[k] = cur[k];
+                    if (lane == 0) tags[buf * p.E + s] = mid;
+                }
+                if (lane == 0) tags[p.n_buf * p.E + buf] = chunk;
+                fence_proxy_async_smem();  // generic-proxy writes above -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    const int64_t first_env = env0 + (p.n_chunks > 1 ? tix : tix * p.E);
+                    float* dst = p.obs + first_env * p.obs_stride + lo;
+                    const uint32_t bytes = (uint32_t)((p.n_chunks > 1 ? (hi - lo) : p.E * (int)p.obs_stride) * 4);
+                    bulk_store(dst, tile, bytes);
+                    bulk_commit();
+                }
+                buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        bulk_wait_all();
+        __threadfence();
+        const uint32_t finished = atomicAdd(&p.sched[1], 1u);
+        if (finished == p.n_warps_total - 1) {  // last warp out re-arms the ticket counter for the next launch
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// Unpacks the records for white-box comparisons (tests) and `get_state`-style host queries.
+__global__ void lle_export_raw_kernel(const uint32_t* records, LleStateLayout L, int64_t N, int A, int NBmax, int16_t* pos,
+                                      uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on, uint64_t* collected,
+                                      uint8_t* counters) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= N) return;
+    const uint32_t* rec = records + env * L.stride;
+    uint32_t al, ar, sl, na, nd, dn;
+    if (!L.wide_flags) {
+        const uint32_t f = rec[L.w_flags];
+        al = f & 0xFF; ar = (f >> 8) & 0xFF; sl = (f >> 16) & 0xFF; na = (f >> 24) & 0xF; nd = (f >> 28) & 7; dn = f >> 31;
+    } else {
+        al = rec[L.w_flags]; ar = rec[L.w_flags + 1]; sl = rec[L.w_flags + 2];
+        const uint32_t mm = rec[L.w_flags + 3];
+        na = mm & 0xFF; nd = (mm >> 8) & 0xFF; dn = (mm >> 16) & 1;
+    }
+    for (int a = 0; a < A; ++a) {
+        const uint32_t pp = rec_pos(rec, a);
+        if (pos) { pos[(env * A + a) * 2] = (int16_t)(pp >> 8); pos[(env * A + a) * 2 + 1] = (int16_t)(pp & 0xFF); }
+        if (alive) alive[env * A + a] = (al >> a) & 1;
+        if (arrived) arrived[env * A + a] = (ar >> a) & 1;
+        if (slot) slot[env * A + a] = (sl >> a) & 1;
+    }
+    if (collected) {
+        uint64_t c = 0;
+        if (L.gem_words >= 1) c = rec[L.w_gems];
+        if (L.gem_words == 2) c |= (uint64_t)rec[L.w_gems + 1] << 32;
+        collected[env] = c;
+    }
+    if (beam_on) {
+        for (int b = 0; b < NBmax; ++b) {
+            uint64_t v = rec[L.w_on + b * L.on_words];
+            if (L.on_words == 2) v |= (uint64_t)rec[L.w_on + b * 2 + 1] << 32;
+            beam_on[env * NBmax + b] = v;
+        }
+    }
+    if (counters) { counters[env * 3] = (uint8_t)na; counters[env * 3 + 1] = (uint8_t)nd; counters[env * 3 + 2] = (uint8_t)dn; }
+}
+
+}  // namespace lle
