@@ -164,6 +164,12 @@ LLE_API int lle_vec_reset(lle_vec* vec, const uint8_t* mask_dev, void* cuda_stre
  * actions with Philox4x32-10 (key = seed, counter = (env_id_base+env, step, agent/4)). */
 LLE_API int lle_vec_step(lle_vec* vec, const int8_t* actions_dev, void* cuda_stream);
 
+/* `n_steps` consecutive lockstep steps with device-sampled actions in ONE launch.  Bit-identical to calling
+ * lle_vec_step(vec, NULL, stream) n_steps times: every step writes all of its outputs (the buffers end up holding
+ * the last step's), but each warp keeps ownership of its worlds across steps, so there is no launch gap and no
+ * ramp-up / drain between steps. */
+LLE_API int lle_vec_rollout(lle_vec* vec, int32_t n_steps, void* cuda_stream);
+
 /* Same step, host-facing: copies `actions_host` (i8[N,A], pinned for async behaviour; NULL = device sampling)
  * to the device, steps, and copies reward (f32[N,reward_dim]) and done (u8[N]) back, then synchronises the
  * stream.  The observation stays resident in HBM (zero-copy DLPack hand-off to the policy). */
@@ -191,6 +197,10 @@ LLE_API int lle_vec_launch_count(lle_vec* vec, uint64_t* out);
  * lle_vec_timing_begin and lle_vec_timing_end; *launches receives how many were timed. */
 LLE_API int lle_vec_timing_begin(lle_vec* vec, void* cuda_stream);
 LLE_API int lle_vec_timing_end(lle_vec* vec, void* cuda_stream, float* total_ms, uint64_t* launches);
+
+/* Development aid (only when the vec was created with LLE_B200_TIMELINE=1 in the environment): per warp of the last
+ * launch, 4 globaltimer readings in ns: kernel start, first observation store issued, last store issued, warp end. */
+LLE_API int lle_vec_debug_timeline(lle_vec* vec, uint64_t* out_host, int64_t cap_warps, int64_t* n_warps);
 
 #ifdef __cplusplus
 }

@@ -78,11 +78,12 @@ struct LleMapHeader {
 //   [0, w_flags)        packed positions (i<<8 | j), two per word
 //   [w_flags, w_gems)   A <= 8: alive | arrived<<8 | slot<<16 | n_arrived<<24 (4 bits) | n_deads<<28 (3 bits, saturating)
 //                       | done<<31 ; else four words: alive, arrived, slot, n_arrived | n_deads<<8 | done<<16
+//   [w_avail, w_gems)   World::available_actions cache (world.rs:37): one byte per agent, bit = Action value
 //   [w_gems, w_on)      collected mask (0, 1 or 2 words)
 //   [w_on, n_words)     beam on-masks (LaserBeam.beam, laser.rs:16): 1 word per beam when every beam of the
 //                       batch is <= 32 cells, else 2
 struct LleStateLayout {
-    int32_t n_words, w_flags, w_gems, w_on;
+    int32_t n_words, w_flags, w_avail, w_gems, w_on;
     int32_t gem_words, on_words;  // words of the gem mask (0/1/2), words per beam (1/2)
     int32_t wide_flags;           // A > 8
     int32_t stride;               // n_words rounded up to 4 words (16 bytes)
@@ -93,7 +94,8 @@ static inline LleStateLayout lle_state_layout(int A, int G, int NB, int max_beam
     LleStateLayout L;
     L.wide_flags = A > 8;
     L.w_flags = (A + 1) / 2;
-    L.w_gems = L.w_flags + (L.wide_flags ? 4 : 1);
+    L.w_avail = L.w_flags + (L.wide_flags ? 4 : 1);
+    L.w_gems = L.w_avail + (A + 3) / 4;
     L.gem_words = G == 0 ? 0 : (G <= 32 ? 1 : 2);
     L.w_on = L.w_gems + L.gem_words;
     L.on_words = max_beam_len <= 32 ? 1 : 2;

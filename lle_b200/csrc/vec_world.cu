@@ -58,6 +58,7 @@ struct lle_vec {
     uint8_t* d_err = nullptr;
     uint32_t* d_sched = nullptr;
     int8_t* d_actions_stage = nullptr;  // for step_host
+    uint64_t* d_timeline = nullptr;     // development aid (LLE_B200_TIMELINE=1)
     int64_t obs_stride = 0;
     // launch configuration
     int grid = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
@@ -103,6 +104,8 @@ KParams base_params(lle_vec* v) {
     p.sched = v->d_sched;
     p.n_tickets = (uint32_t)(v->N_pad / v->group);
     p.n_warps_total = (uint32_t)(v->grid * kWarps);
+    p.n_steps = 1;
+    p.timeline = v->d_timeline;
     return p;
 }
 
@@ -215,7 +218,7 @@ int lle_vec_destroy(lle_vec* v) {
     for (auto* b : v->d_blobs) cudaFree(b);
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
-    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_actions_stage);
+    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline);
     if (v->ev0) cudaEventDestroy(v->ev0);
     if (v->ev1) cudaEventDestroy(v->ev1);
     delete v;
@@ -282,7 +285,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         size_t bytes = (size_t)v->n_buf * v->tile_floats * 4;             // tiles
         bytes += (size_t)v->group * v->L.stride * 4;                      // records of the group
         bytes += (size_t)v->n_buf * v->E * v->L.stride * 4;               // records applied to the tiles
-        bytes += (size_t)(v->n_buf * v->E + v->n_buf + v->group) * 4;     // tags + map ids
+        bytes += (size_t)(2 * v->n_buf * v->E + v->n_buf + v->group) * 4; // tags + map ids + fresh flags
         v->warp_smem = (int)((bytes + 127) / 128 * 128);
         v->smem = (size_t)v->warp_smem * kWarps;
     }
@@ -328,6 +331,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     LLE_CUDA(dalloc(&v->d_err, Np));
     LLE_CUDA(dalloc(&v->d_sched, 2));
     LLE_CUDA(dalloc(&v->d_actions_stage, (size_t)v->A * Np));
+    if (env_int("LLE_B200_TIMELINE", 0)) LLE_CUDA(dalloc(&v->d_timeline, (size_t)v->grid * kWarps * 4));
     LLE_CUDA(cudaEventCreate(&v->ev0));
     LLE_CUDA(cudaEventCreate(&v->ev1));
 
@@ -374,6 +378,19 @@ int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
     return LLE_OK;
 }
 
+int lle_vec_rollout(lle_vec* v, int32_t n_steps, void* stream) {
+    if (!v || n_steps < 1) return fail(LLE_INVALID_ARGUMENT, "bad argument");
+    LLE_CUDA(cudaSetDevice(v->device));
+    KParams p = base_params(v);
+    p.mode = MODE_STEP;
+    p.actions_in = nullptr;
+    p.n_steps = n_steps;
+    LLE_CUDA(launch(v, p, (cudaStream_t)stream));
+    v->launches++;
+    v->t += (uint64_t)n_steps;
+    return LLE_OK;
+}
+
 int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
     LLE_CUDA(cudaSetDevice(v->device));
@@ -412,6 +429,17 @@ int lle_vec_export_raw(lle_vec* v, int16_t* pos, uint8_t* alive, uint8_t* arrive
                                                                       pos, alive, arrived, slot, v->NBmax ? beam_on : nullptr, collected, counters);
     LLE_CUDA(cudaGetLastError());
     v->launches++;
+    return LLE_OK;
+}
+
+int lle_vec_debug_timeline(lle_vec* v, uint64_t* out_host, int64_t cap_warps, int64_t* n_warps) {
+    if (!v || !n_warps) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    *n_warps = v->d_timeline ? (int64_t)v->grid * kWarps : 0;
+    if (v->d_timeline && out_host) {
+        LLE_CUDA(cudaSetDevice(v->device));
+        LLE_CUDA(cudaDeviceSynchronize());
+        LLE_CUDA(cudaMemcpy(out_host, v->d_timeline, (size_t)std::min<int64_t>(cap_warps, *n_warps) * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
     return LLE_OK;
 }
 

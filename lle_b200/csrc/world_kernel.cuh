@@ -84,6 +84,8 @@ struct KParams {
     int32_t warp_smem_bytes;
     uint32_t* sched;       // [0] next ticket, [1] warps finished
     uint32_t n_tickets, n_warps_total;
+    uint64_t* timeline;    // development aid: per warp {start, first store, last store, end} in ns (globaltimer), or nullptr
+    int32_t n_steps;       // > 1: rollout mode (MODE_STEP, device-sampled actions): each warp owns a fixed set of tickets
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -96,6 +98,16 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Ampere-style asynchronous 16-byte global -> shared copies (SASS: LDGSTS), used to (re)build a tile from the
+// map's static plane without staging through registers
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // ---- map view -------------------------------------------------------------------------------------------
 struct MapDev {
@@ -195,6 +207,14 @@ struct World {
         if (L.gem_words == 2) rec[L.w_gems + 1] = (uint32_t)(c >> 32);
     }
 
+    // World::available_actions cache (world.rs:37, refreshed by compute_available_actions :343-363)
+    __device__ __forceinline__ uint32_t cached_avail() const {
+        return gl < A ? (uint32_t)reinterpret_cast<const uint8_t*>(rec + L.w_avail)[gl] : 16u;
+    }
+    __device__ __forceinline__ void store_avail(uint32_t mask) {
+        if (gl < A) reinterpret_cast<uint8_t*>(rec + L.w_avail)[gl] = (uint8_t)mask;
+    }
+
     // ---- record <-> registers
     __device__ __forceinline__ void unpack() {
         pos = 0;
@@ -237,7 +257,8 @@ struct World {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
                 const uint32_t e = cb.e[n];
-                if (e != LLE_NO_BEAM && be_enabled(e) && !on_bit(be_b(e), be_k(e))) {
+                if (e == LLE_NO_BEAM) break;  // entries are packed from index 0
+                if (be_enabled(e) && !on_bit(be_b(e), be_k(e))) {
                     const uint64_t msk = (~0ull << be_k(e)) & len_mask(be_len(e));
                     uint32_t* w = on_words(be_b(e));
                     if ((uint32_t)msk) atomicOr(w, (uint32_t)msk);
@@ -256,7 +277,8 @@ struct World {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
                 const uint32_t e = cb.e[n];
-                if (e != LLE_NO_BEAM && be_enabled(e) && be_colour(e) == gl) {
+                if (e == LLE_NO_BEAM) break;
+                if (be_enabled(e) && be_colour(e) == gl) {
                     const uint64_t msk = (1ull << be_k(e)) - 1ull;
                     uint32_t* w = on_words(be_b(e));
                     atomicAnd(w, (uint32_t)msk);
@@ -279,7 +301,8 @@ struct World {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
                 const uint32_t e = cb.e[n];
-                if (e != LLE_NO_BEAM && be_colour(e) != gl && on_bit(be_b(e), be_k(e))) lethal = true;
+                if (e == LLE_NO_BEAM) break;
+                if (be_colour(e) != gl && on_bit(be_b(e), be_k(e))) lethal = true;
             }
             const bool is_alive = (alive >> gl) & 1u;
             if (lethal) {
@@ -468,7 +491,63 @@ __device__ __forceinline__ uint32_t rec_pos(const uint32_t* rec, int a) {
     return (a & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-__global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
+// Per-lane register copy of the first 64 patch entries of the map being rendered (entries lane and lane + 32):
+// the float index, the static value to restore, and where in a record the controlling bit lives.
+struct PatchCache {
+    uint32_t idx0, idx1;
+    float stat0, stat1;
+    uint16_t word0, word1;  // record word holding the bit
+    uint8_t bit0, bit1, gem0, gem1;
+    bool valid0, valid1;
+    __device__ __forceinline__ void load(const MapDev& rm, const LleStateLayout& L, int lane) {
+        valid0 = lane < rm.n_patch;
+        valid1 = lane + 32 < rm.n_patch;
+        idx0 = idx1 = 0; stat0 = stat1 = 0.f; word0 = word1 = 0; bit0 = bit1 = gem0 = gem1 = 0;
+        if (valid0) {
+            const LlePatch pe = rm.patches[lane];
+            idx0 = pe.idx; stat0 = (float)pe.stat; gem0 = pe.src == 0xFF; bit0 = pe.bit & 31;
+            word0 = (uint16_t)(gem0 ? L.w_gems + (pe.bit >> 5) : L.w_on + pe.src * L.on_words + (pe.bit >> 5));
+        }
+        if (valid1) {
+            const LlePatch pe = rm.patches[lane + 32];
+            idx1 = pe.idx; stat1 = (float)pe.stat; gem1 = pe.src == 0xFF; bit1 = pe.bit & 31;
+            word1 = (uint16_t)(gem1 ? L.w_gems + (pe.bit >> 5) : L.w_on + pe.src * L.on_words + (pe.bit >> 5));
+        }
+    }
+    // a laser cell is lit while its beam bit is on, a gem while it is NOT collected (observations.py:256-263)
+    __device__ __forceinline__ bool lit0(const uint32_t* rec) const { return (((rec[word0] >> bit0) & 1u) ^ gem0) != 0; }
+    __device__ __forceinline__ bool lit1(const uint32_t* rec) const { return (((rec[word1] >> bit1) & 1u) ^ gem1) != 0; }
+};
+
+// (Re)build floats [lo, hi) of one world's block from the map's static plane (observations.py:216-237) with
+// asynchronous copies; pad floats beyond C*H*W are zero.  Completion: cp_async_wait_all() + __syncwarp().
+__device__ __forceinline__ void tile_rebuild_async(float* sub_tile, const MapDev& rm, int lo, int hi, int lane) {
+    const int nf = hi - lo;
+    for (int f = lane * 4; f < nf; f += 128) {
+        const int gi = lo + f;
+        if (gi + 3 < rm.obs_floats) {
+            cp_async16(sub_tile + f, rm.stat + gi);
+        } else {
+            float4 v;
+            v.x = gi + 0 < rm.obs_floats ? __ldg(rm.stat + gi + 0) : 0.f;
+            v.y = gi + 1 < rm.obs_floats ? __ldg(rm.stat + gi + 1) : 0.f;
+            v.z = gi + 2 < rm.obs_floats ? __ldg(rm.stat + gi + 2) : 0.f;
+            v.w = gi + 3 < rm.obs_floats ? __ldg(rm.stat + gi + 3) : 0.f;
+            *reinterpret_cast<float4*>(sub_tile + f) = v;
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+#ifndef LLE_MIN_CTAS
+#define LLE_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LleStateLayout L = p.L;
@@ -479,7 +558,9 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
     uint32_t* applied = recs + (size_t)p.group * stride;                                     // [n_buf][E][stride]
     int32_t* tags = reinterpret_cast<int32_t*>(applied + (size_t)p.n_buf * p.E * stride);    // [n_buf][E] map id, [n_buf] chunk
     int32_t* map_ids = tags + p.n_buf * p.E + p.n_buf;                                       // [group]
+    int32_t* fresh = map_ids + p.group;  // [n_buf][E]: 1 = just rebuilt from the static plane (copies may be in flight)
     for (int k = lane; k < p.n_buf * p.E + p.n_buf; k += 32) tags[k] = -1;
+    for (int k = lane; k < p.n_buf * p.E; k += 32) fresh[k] = 0;
     __syncwarp();
 
     const int Wd = p.Wd, P = 32 / Wd;
@@ -495,15 +576,53 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
     const int sub = lane / Wd, gl = w.gl;
     int bound_map = -1;       // map bound to this lane's World
     MapDev rm;                // map bound for rendering (warp-uniform)
+    PatchCache pc;
     int render_map = -1;
     int buf = 0;
 
+    const uint32_t warp_global = blockIdx.x * kWarps + warp;
+    const bool rollout = p.n_steps > 1;
+    uint64_t t_first = 0, t_last = 0;
+    if (p.timeline && lane == 0) p.timeline[warp_global * 4] = globaltimer_ns();
+    uint32_t own_ticket = warp_global;  // rollout mode: tickets warp_global, warp_global + n_warps_total, ...
+    int step_index = 0;
+    bool first = true;
     for (;;) {
         uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&p.sched[0], 1u);
-        ticket = __shfl_sync(kFull, ticket, 0);
-        if (ticket >= p.n_tickets) break;
+        if (rollout) {
+            // every warp owns the same worlds at every step, so step t+1 of a world only ever follows its own step t:
+            // no grid-wide synchronisation between steps
+            if (own_ticket >= p.n_tickets) {
+                own_ticket = warp_global;
+                if (++step_index >= p.n_steps) break;
+            }
+            if (own_ticket >= p.n_tickets) break;
+            ticket = own_ticket;
+            own_ticket += p.n_warps_total;
+        } else {
+            if (lane == 0) ticket = atomicAdd(&p.sched[0], 1u);
+            ticket = __shfl_sync(kFull, ticket, 0);
+            if (ticket >= p.n_tickets) break;
+        }
         const int64_t env0 = (int64_t)ticket * p.group;
+        const uint64_t t_now = p.t + (uint64_t)step_index;
+        if (first && p.write_obs && p.n_chunks == 1) {
+            // start filling this warp's tiles from the static plane of the first world's map now: the copies land
+            // while the first logic pass runs
+            first = false;
+            const int mid = p.map_of_env ? __ldg(p.map_of_env + env0) : 0;
+            rm.bind(p.blobs[mid]);
+            render_map = mid;
+            pc.load(rm, L, lane);
+            for (int b = 0; b < p.n_buf; ++b)
+                for (int s = 0; s < p.E; ++s) {
+                    tile_rebuild_async(tiles + (size_t)b * p.tile_floats + (size_t)s * p.obs_stride, rm, 0, (int)p.obs_stride, lane);
+                    if (lane == 0) { tags[b * p.E + s] = mid; fresh[b * p.E + s] = 1; }
+                }
+            if (lane == 0)
+                for (int b = 0; b < p.n_buf; ++b) tags[p.n_buf * p.E + b] = 0;
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 
         // ================================================================== logic: P worlds at a time
         for (int g0 = 0; g0 < p.group; g0 += P) {
@@ -517,7 +636,7 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
             if (gl == 0) map_ids[g] = map_id;
             uint32_t* rec = recs + (size_t)g * stride;
             const uint32_t* grec = p.records + env * stride;
-            for (int k = gl; k < stride; k += Wd) rec[k] = grec[k];
+            for (int k = gl; k < stride; k += Wd) rec[k] = __ldcg(grec + k);  // L2 only: rollout mode re-reads its own writes
             __syncwarp();
             w.rec = rec;
             w.unpack();
@@ -528,12 +647,12 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
             const bool real = env < p.N;
 
             if (p.mode == MODE_STEP) {
-                const uint32_t av = w.available();
+                const uint32_t av = w.cached_avail();
                 if (p.actions_in) {
                     if (real && gl < A) act = (uint32_t)(uint8_t)p.actions_in[env * A + gl];  // padding worlds just STAY
                 } else {
                     uint32_t r[4];
-                    philox4x32_10((uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)p.t, (uint32_t)(gl >> 2), (uint32_t)(p.t >> 32),
+                    philox4x32_10((uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, (uint32_t)(gl >> 2), (uint32_t)(t_now >> 32),
                                   (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
                     const uint32_t word = (gl & 3) == 0 ? r[0] : (gl & 3) == 1 ? r[1] : (gl & 3) == 2 ? r[2] : r[3];
                     act = pick_action(word, av);
@@ -613,31 +732,32 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
             const bool do_reset = p.mode == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
             if (__any_sync(kFull, do_reset)) w.reset(do_reset);
 
+            // compute_available_actions (world.rs:343-363) closes reset (:431), step (:473) and a successful set_state
+            // (:595, also reached by the restore at :563); a set_state that fails with InvalidWorldState returns before it,
+            // leaving the cache stale, and so do we.
+            const bool refresh = p.mode != MODE_SET_STATE || err == ERR_OK || err == ERR_STATE_NOT_WALKABLE;
+            uint32_t mask = w.available();
+            if (refresh) w.store_avail(mask);
+            else mask = w.cached_avail();
+            if (!p.walkable) mask = w.available_no_walk(mask);  // LLE-level mask (env.py:153-163), output only
             w.pack();
             __syncwarp();
             {   // record back to HBM and the small per-step vectors
                 uint32_t* out = p.records + env * stride;
-                for (int k = gl; k < stride; k += Wd) out[k] = rec[k];
+                for (int k = gl; k < stride; k += Wd) __stcg(out + k, rec[k]);
                 // PyWorldState::as_array (pyworld_state.rs:79-101): [i0,j0,...,gems...,alive...]
-                const uint64_t coll = w.collected();
-                for (int k = gl; k < p.S; k += Wd) {
-                    float v;
-                    if (k < 2 * A) {
-                        const uint32_t pp = rec_pos(rec, k >> 1);
-                        v = (float)((k & 1) ? (pp & 0xFFu) : (pp >> 8));
-                    } else if (k < 2 * A + p.G) {
-                        v = ((coll >> (k - 2 * A)) & 1ull) ? 1.0f : 0.0f;
-                    } else {
-                        v = ((w.alive >> (k - 2 * A - p.G)) & 1u) ? 1.0f : 0.0f;
-                    }
-                    p.state[env * p.S + k] = v;
+                float* st = p.state + env * p.S;
+                if (gl < A) {
+                    st[2 * gl] = (float)(w.pos >> 8);
+                    st[2 * gl + 1] = (float)(w.pos & 0xFFu);
+                    st[2 * A + p.G + gl] = ((w.alive >> gl) & 1u) ? 1.0f : 0.0f;
+                    uint8_t* av = p.avail + (env * A + gl) * 5;  // LLE.available_actions (env.py:146-163): u8[A,5]
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) av[k] = (uint8_t)((mask >> k) & 1u);
                 }
-                uint32_t mask = w.available();
-                if (!p.walkable) mask = w.available_no_walk(mask);
-                for (int k0 = 0; k0 < 5 * A; k0 += Wd) {  // LLE.available_actions (env.py:146-163): u8[A,5]
-                    const int k = k0 + gl;
-                    const uint32_t mk = w.gshfl(mask, (k / 5) & (Wd - 1));
-                    if (k < 5 * A) p.avail[env * 5 * A + k] = (uint8_t)((mk >> (k % 5)) & 1u);
+                if (p.G) {
+                    const uint64_t coll = w.collected();
+                    for (int g = gl; g < p.G; g += Wd) st[2 * A + g] = ((coll >> g) & 1ull) ? 1.0f : 0.0f;
                 }
             }
         }
@@ -646,6 +766,7 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
 
         // ================================================================== observations of the group
         const int tiles_per_group = p.n_chunks > 1 ? p.group : p.group / p.E;
+        const bool whole = p.n_chunks == 1;  // a tile holds whole worlds: every patch index is in range
         for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
             const int lo = chunk * p.chunk_floats;  // float range [lo, hi) of one world's block
             const int hi = min(lo + p.chunk_floats, (int)p.obs_stride);
@@ -657,72 +778,74 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
                     else bulk_wait_read<0>();
                 }
                 __syncwarp();
-                const int n_sub = p.n_chunks > 1 ? 1 : p.E;
+                const int n_sub = whole ? p.E : 1;
                 for (int s = 0; s < n_sub; ++s) {
-                    const int g = p.n_chunks > 1 ? tix : tix * p.E + s;
+                    const int g = whole ? tix * p.E + s : tix;
                     const int mid = map_ids[g];
                     if (mid != render_map) {
                         rm.bind(p.blobs[mid]);
                         render_map = mid;
+                        pc.load(rm, L, lane);
                     }
                     float* sub_tile = tile + (size_t)s * p.obs_stride;
                     uint32_t* old = applied + ((size_t)buf * p.E + s) * stride;
                     const uint32_t* cur = recs + (size_t)g * stride;
-                    const bool same = tags[buf * p.E + s] == mid && tags[p.n_buf * p.E + buf] == chunk;
+                    const int slot_id = buf * p.E + s;
+                    const bool same = tags[slot_id] == mid && tags[p.n_buf * p.E + buf] == chunk;
+                    // what this world lights: laser cells whose beam bit is on, uncollected gems (observations.py:256-263)
+                    const bool now0 = pc.valid0 && pc.lit0(cur), now1 = pc.valid1 && pc.lit1(cur);
+                    const bool in0 = whole || ((int)pc.idx0 >= lo && (int)pc.idx0 < hi);
+                    const bool in1 = whole || ((int)pc.idx1 >= lo && (int)pc.idx1 < hi);
                     if (!same) {
-                        // (re)build from the map's static plane (observations.py:216-237); pad floats are zero
-                        const int nf = hi - lo;
-                        for (int f = lane * 4; f < nf; f += 128) {
-                            const int gi = lo + f;
-                            float4 v;
-                            if (gi + 3 < rm.obs_floats) {
-                                v = __ldg(reinterpret_cast<const float4*>(rm.stat + gi));
-                            } else {
-                                v.x = gi + 0 < rm.obs_floats ? __ldg(rm.stat + gi + 0) : 0.f;
-                                v.y = gi + 1 < rm.obs_floats ? __ldg(rm.stat + gi + 1) : 0.f;
-                                v.z = gi + 2 < rm.obs_floats ? __ldg(rm.stat + gi + 2) : 0.f;
-                                v.w = gi + 3 < rm.obs_floats ? __ldg(rm.stat + gi + 3) : 0.f;
-                            }
-                            *reinterpret_cast<float4*>(sub_tile + f) = v;
-                        }
+                        tile_rebuild_async(sub_tile, rm, lo, hi, lane);
+                        cp_async_wait_all();
+                    } else if (fresh[slot_id]) {
+                        cp_async_wait_all();  // the prefetch issued at kernel start
                     } else {
                         // un-patch what the previous occupant had lit and the new one has not
                         if (lane < A) {
                             const uint32_t op = rec_pos(old, lane);
                             const int idx = lane * p.HW + (int)(op >> 8) * p.W + (int)(op & 0xFFu);
-                            if (idx >= lo && idx < hi) sub_tile[idx - lo] = 0.0f;  // agent planes have no static content
+                            if (whole || (idx >= lo && idx < hi)) sub_tile[idx - lo] = 0.0f;  // agent planes have no static content
                         }
-                        for (int k = lane; k < rm.n_patch; k += 32) {
+                        if (pc.valid0 && in0 && pc.lit0(old) && !now0) sub_tile[pc.idx0 - lo] = pc.stat0;
+                        if (pc.valid1 && in1 && pc.lit1(old) && !now1) sub_tile[pc.idx1 - lo] = pc.stat1;
+                        for (int k = 64 + lane; k < rm.n_patch; k += 32) {
                             const LlePatch pe = rm.patches[k];
-                            if ((int)pe.idx >= lo && (int)pe.idx < hi && rec_lit(old, L, pe) && !rec_lit(cur, L, pe))
+                            if ((whole || ((int)pe.idx >= lo && (int)pe.idx < hi)) && rec_lit(old, L, pe) && !rec_lit(cur, L, pe))
                                 sub_tile[pe.idx - lo] = (float)pe.stat;
                         }
                     }
                     __syncwarp();
-                    // patch: lit laser cells and uncollected gems, then the agents (observations.py:256-265).  Every
-                    // lit entry is rewritten so that entries aliasing one cell (crossing beams of one colour,
-                    // colours >= n_agents) stay correct whatever was un-patched above.
-                    for (int k = lane; k < rm.n_patch; k += 32) {
+                    // patch.  Every lit entry is rewritten so that entries aliasing one cell (crossing beams of one colour,
+                    // colours >= n_agents) stay correct whatever was un-patched above; then the agents (observations.py:264-265).
+                    if (now0 && in0) sub_tile[pc.idx0 - lo] = 1.0f;
+                    if (now1 && in1) sub_tile[pc.idx1 - lo] = 1.0f;
+                    for (int k = 64 + lane; k < rm.n_patch; k += 32) {
                         const LlePatch pe = rm.patches[k];
-                        if ((int)pe.idx >= lo && (int)pe.idx < hi && rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = 1.0f;
+                        if ((whole || ((int)pe.idx >= lo && (int)pe.idx < hi)) && rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = 1.0f;
                     }
                     if (lane < A) {
                         const uint32_t np = rec_pos(cur, lane);
                         const int idx = lane * p.HW + (int)(np >> 8) * p.W + (int)(np & 0xFFu);
-                        if (idx >= lo && idx < hi) sub_tile[idx - lo] = 1.0f;
+                        if (whole || (idx >= lo && idx < hi)) sub_tile[idx - lo] = 1.0f;
                     }
                     for (int k = lane; k < stride; k += 32) old[k] = cur[k];
-                    if (lane == 0) tags[buf * p.E + s] = mid;
+                    if (lane == 0) { tags[slot_id] = mid; fresh[slot_id] = 0; }
                 }
                 if (lane == 0) tags[p.n_buf * p.E + buf] = chunk;
                 fence_proxy_async_smem();  // generic-proxy writes above -> visible to the async proxy
                 __syncwarp();
                 if (lane == 0) {
-                    const int64_t first_env = env0 + (p.n_chunks > 1 ? tix : tix * p.E);
+                    const int64_t first_env = env0 + (whole ? tix * p.E : tix);
                     float* dst = p.obs + first_env * p.obs_stride + lo;
-                    const uint32_t bytes = (uint32_t)((p.n_chunks > 1 ? (hi - lo) : p.E * (int)p.obs_stride) * 4);
+                    const uint32_t bytes = (uint32_t)((whole ? p.E * (int)p.obs_stride : (hi - lo)) * 4);
                     bulk_store(dst, tile, bytes);
                     bulk_commit();
+                    if (p.timeline) {
+                        t_last = globaltimer_ns();
+                        if (!t_first) t_first = t_last;
+                    }
                 }
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
             }
@@ -732,11 +855,18 @@ __global__ void __launch_bounds__(kThreads) lle_world_kernel(const KParams p) {
     if (lane == 0) {
         bulk_wait_all();
         __threadfence();
-        const uint32_t finished = atomicAdd(&p.sched[1], 1u);
-        if (finished == p.n_warps_total - 1) {  // last warp out re-arms the ticket counter for the next launch
-            p.sched[0] = 0;
-            p.sched[1] = 0;
-            __threadfence();
+        if (p.timeline) {
+            p.timeline[warp_global * 4 + 1] = t_first;
+            p.timeline[warp_global * 4 + 2] = t_last;
+            p.timeline[warp_global * 4 + 3] = globaltimer_ns();
+        }
+        if (!rollout) {
+            const uint32_t finished = atomicAdd(&p.sched[1], 1u);
+            if (finished == p.n_warps_total - 1) {  // last warp out re-arms the ticket counter for the next launch
+                p.sched[0] = 0;
+                p.sched[1] = 0;
+                __threadfence();
+            }
         }
     }
 }

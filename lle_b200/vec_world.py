@@ -184,6 +184,10 @@ class VecWorld:
             ptr = actions.data_ptr()
         check(lib().lle_vec_step(self._h, ptr, _stream_ptr(self.device)))
 
+    def rollout(self, n_steps: int):
+        """`n_steps` device-sampled lockstep steps in one launch (bit-identical to n_steps calls of step(None))."""
+        check(lib().lle_vec_rollout(self._h, int(n_steps), _stream_ptr(self.device)))
+
     def step_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor):
         """Host-facing step: H2D actions, step, D2H reward/done, stream sync (lle_vec_step_host)."""
         ptr = None

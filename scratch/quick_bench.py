@@ -10,6 +10,7 @@ ap.add_argument("--envs", type=int, default=65536)
 ap.add_argument("--steps", type=int, default=2000)
 ap.add_argument("--no-obs", action="store_true")
 ap.add_argument("--map", type=str, default=None)
+ap.add_argument("--rollout", type=int, default=0)
 args = ap.parse_args()
 maps = lle_b200.Map(level=args.level)
 vec = lle_b200.VecWorld(maps, args.envs, seed=1, write_obs=not args.no_obs)
@@ -17,10 +18,16 @@ for _ in range(50):
     vec.step(None)
 vec.synchronize()
 vec.timing_begin()
-for _ in range(args.steps):
-    vec.step(None)
-ms, n = vec.timing_end()
+if args.rollout:
+    for _ in range(args.steps // args.rollout):
+        vec.rollout(args.rollout)
+    ms, n = vec.timing_end()
+    n = (args.steps // args.rollout) * args.rollout
+else:
+    for _ in range(args.steps):
+        vec.step(None)
+    ms, n = vec.timing_end()
 us = ms * 1e3 / n
 obs_bytes = vec.n_channels * vec.height * vec.width * 4 * args.envs
-print(json.dumps({"level": args.level, "envs": args.envs, "obs": not args.no_obs, "us_per_step": round(us, 2),
+print(json.dumps({"level": args.level, "envs": args.envs, "obs": not args.no_obs, "rollout": args.rollout, "us_per_step": round(us, 2),
                   "env_steps_per_s": round(args.envs / (us * 1e-6)), "obs_GBps": round(obs_bytes / (us * 1e-6) / 1e9, 1)}))
