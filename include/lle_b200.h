@@ -152,6 +152,7 @@ typedef struct {
     uint8_t* events;
     int8_t* actions;
     uint8_t* err;
+    int64_t record_bytes; /* bytes of the per-env engine record kept in HBM (read + written once per step) */
 } lle_vec_buffers;
 LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 

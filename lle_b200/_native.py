@@ -37,7 +37,7 @@ class VecBuffers(C.Structure):
     _fields_ = [("n_envs", C.c_int64)] + [(n, C.c_int32) for n in ("n_agents", "n_gems", "n_channels", "height", "width",
                                                                    "reward_dim", "state_dim", "n_beams_max")] + [
         ("obs_stride", C.c_int64), ("obs", C.c_void_p), ("state", C.c_void_p), ("avail", C.c_void_p), ("reward", C.c_void_p),
-        ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p)]
+        ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p), ("record_bytes", C.c_int64)]
 
 
 _lib = None

@@ -61,6 +61,7 @@ struct lle_vec {
     uint64_t* d_timeline = nullptr;     // development aid (LLE_B200_TIMELINE=1)
     int64_t obs_stride = 0;
     // launch configuration
+    bool fast = false, pdl = true;
     int grid = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
     size_t smem = 0;
     uint64_t t = 0, launches = 0;
@@ -71,9 +72,41 @@ struct lle_vec {
 
 namespace {
 
+template <int MODE>
+cudaError_t launch_mode(lle_vec* v, const KParams& p, cudaStream_t s) {
+    // Programmatic stream serialization: the kernel calls griddepcontrol.wait before it touches anything a
+    // previous launch wrote, so its prologue may overlap the tail of the launch before it.
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)v->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = v->smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = v->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, true>, p);
+    return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, false>, p);
+}
 cudaError_t launch(lle_vec* v, const KParams& p, cudaStream_t s) {
-    lle_world_kernel<<<v->grid, kThreads, v->smem, s>>>(p);
-    return cudaGetLastError();
+    switch (p.mode) {
+        case MODE_STEP: return launch_mode<MODE_STEP>(v, p, s);
+        case MODE_RESET: return launch_mode<MODE_RESET>(v, p, s);
+        default: return launch_mode<MODE_SET_STATE>(v, p, s);
+    }
+}
+
+template <int MODE, bool FAST>
+cudaError_t configure_kernel(size_t smem, int* blocks) {
+    auto kern = lle_world_kernel<MODE, FAST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, smem);
+    if (e == cudaSuccess && (*blocks < 0 || b < *blocks)) *blocks = b;
+    return e;
 }
 
 int env_int(const char* name, int fallback) {
@@ -258,9 +291,11 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     // ticket for `group` consecutive worlds, computes them, then streams their observation tiles.
     v->Wd = 1;
     while (v->Wd < v->A) v->Wd *= 2;
-    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", 1)));
+    // at least 4 lanes per world: with fewer, a pass handles more worlds than a ticket should hold (measured on
+    // level 1: 95 us/step at Wd=1, 75 us at Wd=4)
+    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", 4)));
     const int64_t stride = v->obs_stride;
-    const int64_t kTileTargetFloats = 2048, kTileMaxFloats = 6144;  // 8 KB target, 24 KB cap per tile buffer
+    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", 1024), kTileMaxFloats = 6144;  // >= 4 KB per bulk store, 24 KB cap
     if (stride <= kTileMaxFloats) {
         v->n_chunks = 1;
         v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
@@ -289,9 +324,21 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->warp_smem = (int)((bytes + 127) / 128 * 128);
         v->smem = (size_t)v->warp_smem * kWarps;
     }
-    int blocks_per_sm = 0;
-    LLE_CUDA(cudaFuncSetAttribute(lle_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
-    LLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lle_world_kernel, kThreads, v->smem));
+    v->pdl = env_int("LLE_B200_PDL", 1) != 0;
+    int max_patch = 0;
+    for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)maps[k]->cm.header().n_patch);
+    v->fast = n_maps == 1 && v->n_chunks == 1 && v->E == 1 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 &&
+              opts->write_obs && !env_int("LLE_B200_NO_FAST", 0);
+    int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
+    if (v->fast) {
+        LLE_CUDA((configure_kernel<MODE_STEP, true>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_RESET, true>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_SET_STATE, true>(v->smem, &blocks_per_sm)));
+    } else {
+        LLE_CUDA((configure_kernel<MODE_STEP, false>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_RESET, false>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_SET_STATE, false>(v->smem, &blocks_per_sm)));
+    }
     if (blocks_per_sm < 1) return fail(LLE_CUDA_ERROR, "kernel does not fit on an SM");
     blocks_per_sm = std::min(blocks_per_sm, std::max(1, env_int("LLE_B200_MAX_CTAS_PER_SM", 16)));
     const int64_t n_tickets = v->N_pad / v->group;
@@ -352,6 +399,7 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->obs_stride = v->obs_stride;
     out->obs = v->d_obs; out->state = v->d_state; out->avail = v->d_avail; out->reward = v->d_reward; out->done = v->d_done;
     out->events = v->d_events; out->actions = v->d_actions; out->err = v->d_err;
+    out->record_bytes = (int64_t)v->L.stride * 4;
     return LLE_OK;
 }
 

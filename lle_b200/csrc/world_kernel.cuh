@@ -547,6 +547,11 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #ifndef LLE_MIN_CTAS
 #define LLE_MIN_CTAS 5
 #endif
+// MODE: MODE_STEP / MODE_RESET / MODE_SET_STATE, compiled separately so the step kernel carries no set_state code.
+// FAST: the common shape — one map for the whole batch, one whole world per tile, a single tile buffer, at most 64
+// patch entries and a record of at most 32 words.  The tile then never changes map or chunk, so the tag / freshness
+// bookkeeping of the general path disappears and the per-tile work is a handful of shared-memory accesses.
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -579,6 +584,21 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     PatchCache pc;
     int render_map = -1;
     int buf = 0;
+    bool tile_fresh = true;  // FAST: the tile was just (pre)built from the static plane
+    // Programmatic dependent launch: let the next launch on the stream begin its prologue as soon as SM resources
+    // free up; everything above and the static-plane prefetch below touch nothing the previous launch writes.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if constexpr (FAST) {
+        w.m.bind(p.blobs[0]);
+        bound_map = 0;
+        rm = w.m;
+        render_map = 0;
+        pc.load(rm, L, lane);
+        tile_rebuild_async(tiles, rm, 0, (int)p.obs_stride, lane);  // lands while the first logic pass runs
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ... and wait here until the previous launch (which wrote the records we are about to read) has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t warp_global = blockIdx.x * kWarps + warp;
     const bool rollout = p.n_steps > 1;
@@ -606,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         }
         const int64_t env0 = (int64_t)ticket * p.group;
         const uint64_t t_now = p.t + (uint64_t)step_index;
-        if (first && p.write_obs && p.n_chunks == 1) {
+        if (!FAST && first && p.write_obs && p.n_chunks == 1) {
             // start filling this warp's tiles from the static plane of the first world's map now: the copies land
             // while the first logic pass runs
             first = false;
@@ -617,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             for (int b = 0; b < p.n_buf; ++b)
                 for (int s = 0; s < p.E; ++s) {
                     tile_rebuild_async(tiles + (size_t)b * p.tile_floats + (size_t)s * p.obs_stride, rm, 0, (int)p.obs_stride, lane);
-                    if (lane == 0) { tags[b * p.E + s] = mid; fresh[b * p.E + s] = 1; }
+                    if (!FAST && lane == 0) { tags[b * p.E + s] = mid; fresh[b * p.E + s] = 1; }
                 }
             if (lane == 0)
                 for (int b = 0; b < p.n_buf; ++b) tags[p.n_buf * p.E + b] = 0;
@@ -628,12 +648,14 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         for (int g0 = 0; g0 < p.group; g0 += P) {
             const int g = g0 + sub;
             const int64_t env = env0 + g;  // N_pad is a multiple of the group size: always a world
-            const int map_id = p.map_of_env ? __ldg(p.map_of_env + env) : 0;
-            if (map_id != bound_map) {
-                w.m.bind(p.blobs[map_id]);
-                bound_map = map_id;
+            if constexpr (!FAST) {
+                const int map_id = p.map_of_env ? __ldg(p.map_of_env + env) : 0;
+                if (map_id != bound_map) {
+                    w.m.bind(p.blobs[map_id]);
+                    bound_map = map_id;
+                }
+                if (gl == 0) map_ids[g] = map_id;
             }
-            if (gl == 0) map_ids[g] = map_id;
             uint32_t* rec = recs + (size_t)g * stride;
             const uint32_t* grec = p.records + env * stride;
             for (int k = gl; k < stride; k += Wd) rec[k] = __ldcg(grec + k);  // L2 only: rollout mode re-reads its own writes
@@ -646,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             bool paid = false;  // whether a reward is due (a transition happened)
             const bool real = env < p.N;
 
-            if (p.mode == MODE_STEP) {
+            if constexpr (MODE == MODE_STEP) {
                 const uint32_t av = w.cached_avail();
                 if (p.actions_in) {
                     if (real && gl < A) act = (uint32_t)(uint8_t)p.actions_in[env * A + gl];  // padding worlds just STAY
@@ -663,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 paid = err == ERR_OK;
                 ev = w.step(paid, act, n_gem, n_exit, n_died);
                 w.account(paid, n_exit, n_died);
-            } else if (p.mode == MODE_RESET) {
+            } else if constexpr (MODE == MODE_RESET) {
                 const bool on = !p.reset_mask || !real || p.reset_mask[env];
                 w.reset(on);
                 touch = on;
@@ -729,13 +751,13 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             }
             // auto-reset: the transition above is reported; observation / state / availability below are those
             // of the freshly reset world (SURVEY §8d "Auto-reset")
-            const bool do_reset = p.mode == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
+            const bool do_reset = MODE == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
             if (__any_sync(kFull, do_reset)) w.reset(do_reset);
 
             // compute_available_actions (world.rs:343-363) closes reset (:431), step (:473) and a successful set_state
             // (:595, also reached by the restore at :563); a set_state that fails with InvalidWorldState returns before it,
             // leaving the cache stale, and so do we.
-            const bool refresh = p.mode != MODE_SET_STATE || err == ERR_OK || err == ERR_STATE_NOT_WALKABLE;
+            const bool refresh = MODE != MODE_SET_STATE || err == ERR_OK || err == ERR_STATE_NOT_WALKABLE;
             uint32_t mask = w.available();
             if (refresh) w.store_avail(mask);
             else mask = w.cached_avail();
@@ -765,6 +787,50 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         if (!p.write_obs) continue;
 
         // ================================================================== observations of the group
+        if constexpr (FAST) {
+            const int agent_base = lane * p.HW;
+            for (int g = 0; g < p.group; ++g) {
+                const uint32_t* cur = recs + (size_t)g * stride;
+                // the bulk store that last read the tile must have finished reading it
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                // what this world lights: laser cells whose beam bit is on, uncollected gems (observations.py:256-263)
+                const bool now0 = pc.valid0 && pc.lit0(cur), now1 = pc.valid1 && pc.lit1(cur);
+                if (tile_fresh) {
+                    cp_async_wait_all();  // the static plane prefetched at kernel start
+                    tile_fresh = false;
+                } else {
+                    // un-patch what the previous occupant had lit and this one has not
+                    if (lane < A) {
+                        const uint32_t op = rec_pos(applied, lane);
+                        tiles[agent_base + (int)(op >> 8) * p.W + (int)(op & 0xFFu)] = 0.0f;  // agent planes have no static content
+                    }
+                    if (pc.valid0 && !now0 && pc.lit0(applied)) tiles[pc.idx0] = pc.stat0;
+                    if (pc.valid1 && !now1 && pc.lit1(applied)) tiles[pc.idx1] = pc.stat1;
+                }
+                __syncwarp();
+                // patch.  Every lit entry is rewritten so that entries aliasing one cell (crossing beams of one colour,
+                // colours >= n_agents) stay correct whatever was un-patched above; then the agents (observations.py:264-265).
+                if (now0) tiles[pc.idx0] = 1.0f;
+                if (now1) tiles[pc.idx1] = 1.0f;
+                if (lane < A) {
+                    const uint32_t np = rec_pos(cur, lane);
+                    tiles[agent_base + (int)(np >> 8) * p.W + (int)(np & 0xFFu)] = 1.0f;
+                }
+                if (lane < stride) applied[lane] = cur[lane];
+                fence_proxy_async_smem();  // generic-proxy writes above -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(p.obs + (env0 + g) * p.obs_stride, tiles, (uint32_t)p.obs_stride * 4u);
+                    bulk_commit();
+                    if (p.timeline) {
+                        t_last = globaltimer_ns();
+                        if (!t_first) t_first = t_last;
+                    }
+                }
+            }
+            continue;
+        } else {
         const int tiles_per_group = p.n_chunks > 1 ? p.group : p.group / p.E;
         const bool whole = p.n_chunks == 1;  // a tile holds whole worlds: every patch index is in range
         for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
@@ -850,6 +916,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
             }
         }
+        }  // !FAST
         __syncwarp();
     }
     if (lane == 0) {

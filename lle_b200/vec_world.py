@@ -129,6 +129,7 @@ class VecWorld:
         self.n_envs, self.n_agents, self.n_gems, self.n_channels = int(b.n_envs), b.n_agents, b.n_gems, b.n_channels
         self.height, self.width, self.reward_dim, self.state_dim, self.n_beams_max = b.height, b.width, b.reward_dim, b.state_dim, b.n_beams_max
         self.obs_stride = int(b.obs_stride)
+        self.record_bytes = int(b.record_bytes)
         N, A = self.n_envs, self.n_agents
         dev = self.device
 
