@@ -168,10 +168,15 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world_size > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    n_envs = args.envs
-    vec = lle_b200.VecWorld(lle_b200.Map(level=LEVEL), n_envs, device=dev, seed=SEED, env_id_base=rank * n_envs, auto_reset=True)
+    from lle_b200.sharding import reduce_stats, shard_range
+
+    begin, end = shard_range(args.envs * world_size, rank, world_size)  # weak scaling: args.envs worlds per GPU
+    n_envs = end - begin
+    vec = lle_b200.VecWorld(lle_b200.Map(level=LEVEL), n_envs, device=dev, seed=SEED, env_id_base=begin, auto_reset=True)
     A, G, C, H, W, R = vec.n_agents, vec.n_gems, vec.n_channels, vec.height, vec.width, vec.reward_dim
     K, Wm = args.steps, max(args.warmup, 3)
 
@@ -186,7 +191,6 @@ def run_ours(args) -> None:
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = vec.launch_count
-    episodes = torch.zeros((), dtype=torch.int64, device=dev)
     vec.timing_begin()
     for _ in range(K):
         vec.step(None)
@@ -231,10 +235,9 @@ def run_ours(args) -> None:
     e2e_value = world_size * n_envs * Ke / float(te.item())
     assert int(vec.err.sum()) == 0, "replayed actions must be valid"
 
-    # optional end-of-run stats reduction: the only collective (NCCL all-reduce of a few counters)
-    stats = torch.stack([vec.done.sum().to(torch.int64), episodes])
-    if world_size > 1:
-        dist.all_reduce(stats)
+    # end-of-run stats reduction: the only collective on this path (NCCL all-reduce of a few counters)
+    stats = reduce_stats(torch.stack([vec.done.sum().to(torch.int64), vec.reward.sum().to(torch.int64),
+                                      torch.tensor(n_envs, dtype=torch.int64, device=dev)]))
 
     if rank == 0:
         bytes_env = algorithmic_bytes(A, G, C, H, W, R, record_bytes=vec.record_bytes)
@@ -260,6 +263,7 @@ def run_ours(args) -> None:
                     "steps": Ke, "note": "lle_vec_step_host: pinned host actions -> H2D -> fused step -> D2H reward+done -> stream sync, "
                                          "every step; observations stay in HBM (zero-copy DLPack hand-off)"},
             "gpu_launches": launches,
+            "stats_allreduce": {"done_last_step": int(stats[0]), "reward_last_step": int(stats[1]), "envs_total": int(stats[2])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src, "kernel": "lle_world_kernel<MODE_STEP, FAST>",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": bytes_env,
