@@ -56,7 +56,11 @@ struct lle_vec {
     uint8_t* d_events = nullptr;
     int8_t* d_actions = nullptr;
     uint8_t* d_err = nullptr;
-    uint32_t* d_sched = nullptr;
+    uint32_t* d_sched = nullptr;        // kSchedSlots x {next pair, warps finished}
+    uint32_t* d_flags = nullptr;        // [n_tickets] last completed step sequence number per ticket
+    uint32_t seq = 0;                   // sequence number of the last step launched
+    uint32_t launch_index = 0;          // rotates the scheduler slots
+    bool last_was_step = false;         // the previous launch on this vec was a step (may be overlapped via PDL)
     int8_t* d_actions_stage = nullptr;  // for step_host
     uint64_t* d_timeline = nullptr;     // development aid (LLE_B200_TIMELINE=1)
     int64_t obs_stride = 0;
@@ -72,6 +76,8 @@ struct lle_vec {
 
 namespace {
 
+constexpr int kSchedSlots = 8;  // launches that may be in flight at once through programmatic dependent launch: <= 3
+
 template <int MODE>
 cudaError_t launch_mode(lle_vec* v, const KParams& p, cudaStream_t s) {
     // Programmatic stream serialization: the kernel calls griddepcontrol.wait before it touches anything a
@@ -84,18 +90,29 @@ cudaError_t launch_mode(lle_vec* v, const KParams& p, cudaStream_t s) {
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = v->pdl ? 1 : 0;
+    // only a step that directly follows a step may overlap it: the epoch flags order them ticket by ticket
+    attr[0].val.programmaticStreamSerializationAllowed = (v->pdl && MODE == MODE_STEP && v->last_was_step) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, true>, p);
     return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, false>, p);
 }
-cudaError_t launch(lle_vec* v, const KParams& p, cudaStream_t s) {
+cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
+    p.sched = v->d_sched + 2 * (v->launch_index++ % kSchedSlots);
+    p.flags = v->d_flags;
+    cudaError_t e;
     switch (p.mode) {
-        case MODE_STEP: return launch_mode<MODE_STEP>(v, p, s);
-        case MODE_RESET: return launch_mode<MODE_RESET>(v, p, s);
-        default: return launch_mode<MODE_SET_STATE>(v, p, s);
+        case MODE_STEP:
+            p.seq = v->seq + 1;  // sequence number of the first step of this launch
+            e = launch_mode<MODE_STEP>(v, p, s);
+            v->seq += (uint32_t)p.n_steps;
+            v->last_was_step = true;
+            return e;
+        case MODE_RESET: e = launch_mode<MODE_RESET>(v, p, s); break;
+        default: e = launch_mode<MODE_SET_STATE>(v, p, s); break;
     }
+    v->last_was_step = false;
+    return e;
 }
 
 template <int MODE, bool FAST>
@@ -134,7 +151,6 @@ KParams base_params(lle_vec* v) {
     p.Wd = v->Wd; p.group = v->group; p.E = v->E; p.n_chunks = v->n_chunks; p.chunk_floats = v->chunk_floats; p.tile_floats = v->tile_floats;
     p.n_buf = v->n_buf;
     p.warp_smem_bytes = v->warp_smem;
-    p.sched = v->d_sched;
     p.n_tickets = (uint32_t)(v->N_pad / v->group);
     p.n_warps_total = (uint32_t)(v->grid * kWarps);
     p.n_steps = 1;
@@ -251,7 +267,7 @@ int lle_vec_destroy(lle_vec* v) {
     for (auto* b : v->d_blobs) cudaFree(b);
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
-    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline);
+    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline);
     if (v->ev0) cudaEventDestroy(v->ev0);
     if (v->ev1) cudaEventDestroy(v->ev1);
     delete v;
@@ -376,7 +392,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     LLE_CUDA(dalloc(&v->d_events, (size_t)v->A * Np));
     LLE_CUDA(dalloc(&v->d_actions, (size_t)v->A * Np));
     LLE_CUDA(dalloc(&v->d_err, Np));
-    LLE_CUDA(dalloc(&v->d_sched, 2));
+    LLE_CUDA(dalloc(&v->d_sched, 2 * kSchedSlots));
+    LLE_CUDA(dalloc(&v->d_flags, (size_t)(v->N_pad / v->group)));
     LLE_CUDA(dalloc(&v->d_actions_stage, (size_t)v->A * Np));
     if (env_int("LLE_B200_TIMELINE", 0)) LLE_CUDA(dalloc(&v->d_timeline, (size_t)v->grid * kWarps * 4));
     LLE_CUDA(cudaEventCreate(&v->ev0));

@@ -82,10 +82,12 @@ struct KParams {
     int32_t tile_floats;   // floats per shared-memory tile buffer
     int32_t n_buf;         // tile buffers per warp (1 or 2)
     int32_t warp_smem_bytes;
-    uint32_t* sched;       // [0] next ticket, [1] warps finished
+    uint32_t* sched;       // this launch's scheduler slot: [0] next (step, ticket) pair, [1] warps finished
+    uint32_t* flags;       // [n_tickets] sequence number of the last step completed for the ticket's worlds
+    uint32_t seq;          // sequence number of the (first) step of this launch; step q of a ticket needs flags >= q-1
     uint32_t n_tickets, n_warps_total;
     uint64_t* timeline;    // development aid: per warp {start, first store, last store, end} in ns (globaltimer), or nullptr
-    int32_t n_steps;       // > 1: rollout mode (MODE_STEP, device-sampled actions): each warp owns a fixed set of tickets
+    int32_t n_steps;       // steps in this launch (> 1: rollout with device-sampled actions)
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -538,6 +540,23 @@ __device__ __forceinline__ void tile_rebuild_async(float* sub_tile, const MapDev
     }
 }
 
+// Dataflow ordering between steps.  A ticket's step q may start once the ticket's step q-1 is complete, whichever
+// launch (programmatic dependent launches overlap) or warp ran it.  Completion is published with a gpu-scope release
+// after every write of the ticket (records, outputs, and the observation bulk stores, which must have completed),
+// and consumed with an acquire before the records are read (through L2).
+__device__ __forceinline__ void ticket_release(uint32_t* flag, uint32_t seq) {
+    asm volatile("fence.proxy.async;" ::: "memory");  // completed async-proxy (bulk) writes before the generic-proxy release
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool ticket_ready(const uint32_t* flag, uint32_t need) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return (int32_t)(v - need) >= 0;
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -545,7 +564,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 
 #ifndef LLE_MIN_CTAS
-#define LLE_MIN_CTAS 5
+#define LLE_MIN_CTAS 4
 #endif
 // MODE: MODE_STEP / MODE_RESET / MODE_SET_STATE, compiled separately so the step kernel carries no set_state code.
 // FAST: the common shape — one map for the whole batch, one whole world per tile, a single tile buffer, at most 64
@@ -597,32 +616,38 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         tile_rebuild_async(tiles, rm, 0, (int)p.obs_stride, lane);  // lands while the first logic pass runs
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    // ... and wait here until the previous launch (which wrote the records we are about to read) has completed.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Reset / set_state wait for the whole previous launch.  A step does not: it orders itself ticket by ticket with
+    // the epoch flags, so its first tickets start while the previous step's last ones are still draining.
+    if constexpr (MODE != MODE_STEP) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t warp_global = blockIdx.x * kWarps + warp;
-    const bool rollout = p.n_steps > 1;
+    const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;  // (step, ticket) pairs, handed out in order
     uint64_t t_first = 0, t_last = 0;
     if (p.timeline && lane == 0) p.timeline[warp_global * 4] = globaltimer_ns();
-    uint32_t own_ticket = warp_global;  // rollout mode: tickets warp_global, warp_global + n_warps_total, ...
     int step_index = 0;
     bool first = true;
+    uint32_t owed_ticket = 0, owed_seq = 0;  // the previous ticket, whose completion is published once its stores are done
+    bool owed = false;
     for (;;) {
-        uint32_t ticket = 0;
-        if (rollout) {
-            // every warp owns the same worlds at every step, so step t+1 of a world only ever follows its own step t:
-            // no grid-wide synchronisation between steps
-            if (own_ticket >= p.n_tickets) {
-                own_ticket = warp_global;
-                if (++step_index >= p.n_steps) break;
+        uint32_t pair = 0;
+        if (lane == 0) pair = atomicAdd(&p.sched[0], 1u);
+        pair = __shfl_sync(kFull, pair, 0);
+        if (pair >= n_pairs) break;
+        const uint32_t ticket = pair % p.n_tickets;
+        step_index = (int)(pair / p.n_tickets);
+        const uint32_t my_seq = p.seq + (uint32_t)step_index;
+        if constexpr (MODE == MODE_STEP) {
+            bool flushed = false;
+            if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
+                // Never block while owing a completion: the warp we are about to wait for may be waiting for ours.
+                if (owed) {
+                    bulk_wait_all();
+                    ticket_release(p.flags + owed_ticket, owed_seq);
+                    flushed = true;
+                }
+                while (!ticket_ready(p.flags + ticket, my_seq - 1u)) __nanosleep(64);
             }
-            if (own_ticket >= p.n_tickets) break;
-            ticket = own_ticket;
-            own_ticket += p.n_warps_total;
-        } else {
-            if (lane == 0) ticket = atomicAdd(&p.sched[0], 1u);
-            ticket = __shfl_sync(kFull, ticket, 0);
-            if (ticket >= p.n_tickets) break;
+            if (__shfl_sync(kFull, (int)flushed, 0)) owed = false;
         }
         const int64_t env0 = (int64_t)ticket * p.group;
         const uint64_t t_now = p.t + (uint64_t)step_index;
@@ -784,7 +809,10 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             }
         }
         __syncwarp();
-        if (!p.write_obs) continue;
+        if (!p.write_obs) {
+            if (MODE == MODE_STEP && lane == 0) ticket_release(p.flags + ticket, my_seq);
+            continue;
+        }
 
         // ================================================================== observations of the group
         if constexpr (FAST) {
@@ -827,8 +855,13 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         t_last = globaltimer_ns();
                         if (!t_first) t_first = t_last;
                     }
+                    if (MODE == MODE_STEP && owed && g == 0) {
+                        bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
+                        ticket_release(p.flags + owed_ticket, owed_seq);
+                    }
                 }
             }
+            owed = true; owed_ticket = ticket; owed_seq = my_seq;
             continue;
         } else {
         const int tiles_per_group = p.n_chunks > 1 ? p.group : p.group / p.E;
@@ -912,28 +945,32 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         t_last = globaltimer_ns();
                         if (!t_first) t_first = t_last;
                     }
+                    if (MODE == MODE_STEP && owed && chunk == 0 && tix == 0) {
+                        bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
+                        ticket_release(p.flags + owed_ticket, owed_seq);
+                    }
                 }
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
             }
         }
+        owed = true; owed_ticket = ticket; owed_seq = my_seq;
         }  // !FAST
         __syncwarp();
     }
     if (lane == 0) {
         bulk_wait_all();
+        if (MODE == MODE_STEP && owed) ticket_release(p.flags + owed_ticket, owed_seq);
         __threadfence();
         if (p.timeline) {
             p.timeline[warp_global * 4 + 1] = t_first;
             p.timeline[warp_global * 4 + 2] = t_last;
             p.timeline[warp_global * 4 + 3] = globaltimer_ns();
         }
-        if (!rollout) {
-            const uint32_t finished = atomicAdd(&p.sched[1], 1u);
-            if (finished == p.n_warps_total - 1) {  // last warp out re-arms the ticket counter for the next launch
-                p.sched[0] = 0;
-                p.sched[1] = 0;
-                __threadfence();
-            }
+        const uint32_t finished = atomicAdd(&p.sched[1], 1u);
+        if (finished == p.n_warps_total - 1) {  // last warp out re-arms this scheduler slot for a later launch
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
         }
     }
 }
