@@ -14,9 +14,9 @@ _load_native()  # fail loudly at import time if the extension is not built
 
 from .vec_world import Map, VecWorld  # noqa: E402
 from .world import LLE, Step, World, decode_events  # noqa: E402
-from .env import Builder, VecLLE, from_file, from_str, level  # noqa: E402
+from .env import Builder, VecLLE, VecWorldGroup, from_file, from_str, level  # noqa: E402
 
 __all__ = ["Action", "Agent", "Direction", "EventType", "Gem", "InvalidActionError", "InvalidLevelError",
            "InvalidWorldStateError", "Laser", "LaserSource", "ParsingError", "WorldEvent", "WorldState", "Map", "VecWorld",
-           "World", "LLE", "Step", "VecLLE", "Builder", "level", "from_str", "from_file", "decode_events", "LIB_PATH"]
+           "World", "LLE", "Step", "VecLLE", "VecWorldGroup", "Builder", "level", "from_str", "from_file", "decode_events", "LIB_PATH"]
 __version__ = "0.1.0"

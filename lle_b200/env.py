@@ -58,6 +58,37 @@ class VecLLE:
         return getattr(self, name).__dlpack__()
 
 
+class VecWorldGroup:
+    """Several `VecWorld`s stepped together — for batches whose maps do not share one tensor shape, e.g. the six
+    built-in levels mixed (BASELINE.json configs[3]: channel counts 6/8/8/8/12/12 => one sub-batch per level)."""
+
+    def __init__(self, specs: Sequence[tuple], **kw):
+        """specs: (maps, n_envs) pairs; kw: VecWorld options.  env ids are assigned contiguously across sub-batches."""
+        base = int(kw.pop("env_id_base", 0))
+        self.parts = []
+        for maps, n in specs:
+            self.parts.append(VecWorld(maps, n, env_id_base=base, **kw))
+            base += n
+        self.n_envs = sum(p.n_envs for p in self.parts)
+
+    def reset(self):
+        for p in self.parts:
+            p.reset()
+
+    def step(self):
+        """Device-sampled actions for every sub-batch; the launches are adjacent on the stream and overlap (PDL)."""
+        for p in self.parts:
+            p.step(None)
+
+    def rollout(self, n_steps: int):
+        for p in self.parts:
+            p.rollout(n_steps)
+
+    def synchronize(self):
+        for p in self.parts:
+            p.synchronize()
+
+
 class Builder:
     """Subset of python/lle/env/builder.py that exists on the accelerated path."""
 

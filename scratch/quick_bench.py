@@ -12,8 +12,20 @@ ap.add_argument("--no-obs", action="store_true")
 ap.add_argument("--map", type=str, default=None)
 ap.add_argument("--rollout", type=int, default=0)
 args = ap.parse_args()
-maps = lle_b200.Map(level=args.level)
-vec = lle_b200.VecWorld(maps, args.envs, seed=1, write_obs=not args.no_obs)
+moe = None
+if args.map == "generated":
+    import json
+    import numpy as np
+    texts = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "generated_5x5.json")))["maps"]
+    maps = [lle_b200.Map(t) for t in texts]
+    moe = np.repeat(np.arange(len(maps), dtype=np.int32), args.envs // len(maps))
+elif args.map == "synthetic":
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from _util import synthetic_map
+    maps = lle_b200.Map(synthetic_map(64, 64, 8, 16, seed=5))
+else:
+    maps = lle_b200.Map(level=args.level)
+vec = lle_b200.VecWorld(maps, args.envs, seed=1, write_obs=not args.no_obs, map_of_env=moe)
 for _ in range(50):
     vec.step(None)
 vec.synchronize()
@@ -29,5 +41,5 @@ else:
     ms, n = vec.timing_end()
 us = ms * 1e3 / n
 obs_bytes = vec.n_channels * vec.height * vec.width * 4 * args.envs
-print(json.dumps({"level": args.level, "envs": args.envs, "obs": not args.no_obs, "rollout": args.rollout, "us_per_step": round(us, 2),
+print(json.dumps({"level": args.map or args.level, "envs": args.envs, "obs": not args.no_obs, "rollout": args.rollout, "us_per_step": round(us, 2),
                   "env_steps_per_s": round(args.envs / (us * 1e-6)), "obs_GBps": round(obs_bytes / (us * 1e-6) / 1e9, 1)}))

@@ -118,6 +118,69 @@ def test_large_map_chunked_tiles():
     run_pair([text], None, 64, 40, check_every=3, seed=6)
 
 
+def _generated_maps():
+    import json
+    import os
+
+    from _util import GOLDEN
+
+    with open(os.path.join(GOLDEN, "generated_5x5.json")) as f:
+        return json.load(f)["maps"]
+
+
+def test_config3_generated_maps_heterogeneous_batch():
+    """BASELINE configs[2]: 1,024 distinct generated 5x5 maps (2 agents, 2 lasers) in ONE batch — per-world static
+    planes differ.  8 worlds per map against the oracle, bit-exact."""
+    maps = _generated_maps()
+    assert len(maps) == 1024 and len(set(maps)) == 1024
+    per_map = 8
+    moe = [m for m in range(1024) for _ in range(per_map)]
+    run_pair(maps, moe, 1024 * per_map, 40, check_every=3, seed=21)
+    # maps interleaved world by world (worst case for the tile cache: every sub-tile changes map)
+    moe2 = [(e * 37) % 1024 for e in range(4096)]
+    run_pair(maps, moe2, 4096, 25, check_every=4, seed=22)
+
+
+def test_config3_full_size_properties():
+    """1,024 maps x 1,024 worlds (1,048,576 worlds): size-independent checks."""
+    import lle_b200
+
+    maps = _generated_maps()
+    n = 1024 * 1024
+    moe = np.repeat(np.arange(1024, dtype=np.int32), 1024)
+    vec = lle_b200.VecWorld(maps, n, map_of_env=moe, seed=5)
+    A = vec.n_agents
+    for t in range(30):
+        vec.step(None)
+    vec.synchronize()
+    obs = vec.obs
+    assert torch.all((obs == 0) | (obs == 1) | (obs == -1))
+    assert torch.equal(obs[:, :A].sum(dim=(2, 3)), torch.ones(n, A, device=obs.device))
+    pos = vec.state[:, : 2 * A].reshape(-1, A, 2).long()
+    assert torch.equal(obs[:, :A].flatten(2).argmax(dim=2), pos[..., 0] * vec.width + pos[..., 1])
+    assert torch.all(vec.err == 0)
+    # worlds of one map share their static planes (walls, exits), worlds of different maps do not in general
+    walls = obs[:, 2 * A].reshape(1024, 1024, -1)
+    assert torch.equal(walls, walls[:, :1].expand_as(walls))
+    assert len({tuple(w.tolist()) for w in walls[:, 0].cpu()}) > 500
+
+
+def test_config4_mixed_levels_group():
+    """BASELINE configs[3] at reduced size: the six levels mixed, one sub-batch per level, contiguous global env ids."""
+    import lle_b200
+
+    per_level = 512
+    group = lle_b200.VecWorldGroup([(level_text(l), per_level) for l in range(1, 7)], seed=9)
+    oracles = [lo.OracleVec([level_text(l)], None, per_level, seed=9, env_id_base=(l - 1) * per_level) for l in range(1, 7)]
+    for t in range(60):
+        group.step()
+        for o in oracles:
+            o.step(None)
+    for part, o in zip(group.parts, oracles):
+        d = Dev(part)
+        assert_same(d, o, d.pull(), "mixed levels")
+
+
 def test_set_state_fuzz(layouts):
     import ctypes as C
 
