@@ -309,15 +309,16 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     while (v->Wd < v->A) v->Wd *= 2;
     // at least 4 lanes per world: with fewer, a pass handles more worlds than a ticket should hold (measured on
     // level 1: 95 us/step at Wd=1, 75 us at Wd=4)
-    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", 4)));
+    const bool small_obs = v->obs_stride * 4 < 2048;  // tiny observations: the logic dominates, pack more worlds per pass
+    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", small_obs ? 1 : 4)));
     const int64_t stride = v->obs_stride;
-    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", 1024), kTileMaxFloats = 6144;  // >= 4 KB per bulk store, 24 KB cap
+    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", small_obs ? 2048 : 1024), kTileMaxFloats = 6144;  // 4-8 KB per bulk store
     if (stride <= kTileMaxFloats) {
         v->n_chunks = 1;
         v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
         v->chunk_floats = (int)stride;
         v->tile_floats = (int)(v->E * stride);
-        v->group = std::max(std::max(v->E, 4), 32 / v->Wd);
+        v->group = small_obs ? 32 : std::max(std::max(v->E, 8), 32 / v->Wd);
         v->n_buf = 1;
     } else {
         v->E = 1;
@@ -343,8 +344,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->pdl = env_int("LLE_B200_PDL", 1) != 0;
     int max_patch = 0;
     for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)maps[k]->cm.header().n_patch);
-    v->fast = n_maps == 1 && v->n_chunks == 1 && v->E == 1 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 &&
-              opts->write_obs && !env_int("LLE_B200_NO_FAST", 0);
+    v->fast = v->n_chunks == 1 && v->E <= 32 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 && opts->write_obs &&
+              !env_int("LLE_B200_NO_FAST", 0);
     int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
     if (v->fast) {
         LLE_CUDA((configure_kernel<MODE_STEP, true>(v->smem, &blocks_per_sm)));

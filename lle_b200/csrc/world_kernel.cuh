@@ -607,14 +607,23 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     // Programmatic dependent launch: let the next launch on the stream begin its prologue as soon as SM resources
     // free up; everything above and the static-plane prefetch below touch nothing the previous launch writes.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    uint32_t fresh_bits = 0;  // FAST: sub-tiles that hold a pristine static plane (nothing to un-patch yet)
     if constexpr (FAST) {
-        w.m.bind(p.blobs[0]);
-        bound_map = 0;
-        rm = w.m;
-        render_map = 0;
-        pc.load(rm, L, lane);
-        tile_rebuild_async(tiles, rm, 0, (int)p.obs_stride, lane);  // lands while the first logic pass runs
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (p.map_of_env == nullptr) {  // one map for the whole batch: bind it once and prefetch its static plane
+            w.m.bind(p.blobs[0]);
+            bound_map = 0;
+            rm = w.m;
+            render_map = 0;
+            pc.load(rm, L, lane);
+            for (int s = 0; s < p.E; ++s)  // lands while the first logic pass runs
+                tile_rebuild_async(tiles + (size_t)s * p.obs_stride, rm, 0, (int)p.obs_stride, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            for (int k = lane; k < p.E; k += 32) tags[k] = 0;
+            fresh_bits = ~0u;
+            __syncwarp();
+        } else {
+            tile_fresh = false;
+        }
     }
     // Reset / set_state wait for the whole previous launch.  A step does not: it orders itself ticket by ticket with
     // the epoch flags, so its first tickets start while the previous step's last ones are still draining.
@@ -673,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         for (int g0 = 0; g0 < p.group; g0 += P) {
             const int g = g0 + sub;
             const int64_t env = env0 + g;  // N_pad is a multiple of the group size: always a world
-            if constexpr (!FAST) {
+            if (!FAST || p.map_of_env != nullptr) {
                 const int map_id = p.map_of_env ? __ldg(p.map_of_env + env) : 0;
                 if (map_id != bound_map) {
                     w.m.bind(p.blobs[map_id]);
@@ -817,45 +826,68 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         // ================================================================== observations of the group
         if constexpr (FAST) {
             const int agent_base = lane * p.HW;
-            for (int g = 0; g < p.group; ++g) {
-                const uint32_t* cur = recs + (size_t)g * stride;
+            const bool multi = p.map_of_env != nullptr;
+            const int n_tiles = p.group / p.E;
+            for (int tix = 0; tix < n_tiles; ++tix) {
                 // the bulk store that last read the tile must have finished reading it
                 if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
-                // what this world lights: laser cells whose beam bit is on, uncollected gems (observations.py:256-263)
-                const bool now0 = pc.valid0 && pc.lit0(cur), now1 = pc.valid1 && pc.lit1(cur);
                 if (tile_fresh) {
-                    cp_async_wait_all();  // the static plane prefetched at kernel start
+                    cp_async_wait_all();  // the static planes prefetched at kernel start
                     tile_fresh = false;
-                } else {
-                    // un-patch what the previous occupant had lit and this one has not
-                    if (lane < A) {
-                        const uint32_t op = rec_pos(applied, lane);
-                        tiles[agent_base + (int)(op >> 8) * p.W + (int)(op & 0xFFu)] = 0.0f;  // agent planes have no static content
+                    __syncwarp();
+                }
+                for (int s = 0; s < p.E; ++s) {
+                    const int g = tix * p.E + s;
+                    const uint32_t* cur = recs + (size_t)g * stride;
+                    float* sub = tiles + (size_t)s * p.obs_stride;
+                    uint32_t* old = applied + (size_t)s * stride;
+                    int mid = 0;
+                    if (multi) {
+                        mid = map_ids[g];
+                        if (mid != render_map) {
+                            rm.bind(p.blobs[mid]);
+                            render_map = mid;
+                            pc.load(rm, L, lane);
+                        }
                     }
-                    if (pc.valid0 && !now0 && pc.lit0(applied)) tiles[pc.idx0] = pc.stat0;
-                    if (pc.valid1 && !now1 && pc.lit1(applied)) tiles[pc.idx1] = pc.stat1;
+                    // what this world lights: laser cells whose beam bit is on, uncollected gems (observations.py:256-263)
+                    const bool now0 = pc.valid0 && pc.lit0(cur), now1 = pc.valid1 && pc.lit1(cur);
+                    if (tags[s] != mid) {
+                        tile_rebuild_async(sub, rm, 0, (int)p.obs_stride, lane);  // another map: start from its static plane
+                        cp_async_wait_all();
+                        if (lane == 0) tags[s] = mid;
+                    } else if (!((fresh_bits >> s) & 1u)) {
+                        // un-patch what the previous occupant had lit and this one has not
+                        if (lane < A) {
+                            const uint32_t op = rec_pos(old, lane);
+                            sub[agent_base + (int)(op >> 8) * p.W + (int)(op & 0xFFu)] = 0.0f;  // agent planes have no static content
+                        }
+                        if (pc.valid0 && !now0 && pc.lit0(old)) sub[pc.idx0] = pc.stat0;
+                        if (pc.valid1 && !now1 && pc.lit1(old)) sub[pc.idx1] = pc.stat1;
+                    }
+                    fresh_bits &= ~(1u << s);
+                    __syncwarp();
+                    // patch.  Every lit entry is rewritten so that entries aliasing one cell (crossing beams of one colour,
+                    // colours >= n_agents) stay correct whatever was un-patched above; then the agents (observations.py:264-265).
+                    if (now0) sub[pc.idx0] = 1.0f;
+                    if (now1) sub[pc.idx1] = 1.0f;
+                    if (lane < A) {
+                        const uint32_t np = rec_pos(cur, lane);
+                        sub[agent_base + (int)(np >> 8) * p.W + (int)(np & 0xFFu)] = 1.0f;
+                    }
+                    if (lane < stride) old[lane] = cur[lane];
                 }
-                __syncwarp();
-                // patch.  Every lit entry is rewritten so that entries aliasing one cell (crossing beams of one colour,
-                // colours >= n_agents) stay correct whatever was un-patched above; then the agents (observations.py:264-265).
-                if (now0) tiles[pc.idx0] = 1.0f;
-                if (now1) tiles[pc.idx1] = 1.0f;
-                if (lane < A) {
-                    const uint32_t np = rec_pos(cur, lane);
-                    tiles[agent_base + (int)(np >> 8) * p.W + (int)(np & 0xFFu)] = 1.0f;
-                }
-                if (lane < stride) applied[lane] = cur[lane];
                 fence_proxy_async_smem();  // generic-proxy writes above -> visible to the async proxy
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_store(p.obs + (env0 + g) * p.obs_stride, tiles, (uint32_t)p.obs_stride * 4u);
+                    bulk_store(p.obs + (env0 + (int64_t)tix * p.E) * p.obs_stride, tiles, (uint32_t)(p.E * p.obs_stride) * 4u);
                     bulk_commit();
                     if (p.timeline) {
                         t_last = globaltimer_ns();
                         if (!t_first) t_first = t_last;
                     }
-                    if (MODE == MODE_STEP && owed && g == 0) {
+                    if (MODE == MODE_STEP && owed && tix == 0) {
                         bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
                         ticket_release(p.flags + owed_ticket, owed_seq);
                     }
