@@ -119,6 +119,16 @@ typedef struct {
     int32_t write_obs;       /* 0 skips the layered observation (state/avail/reward still written)     */
     uint64_t seed;           /* Philox key for device-sampled actions                                  */
     uint64_t env_id_base;    /* global id of env 0 (sharding over GPUs keeps streams independent of the GPU count) */
+    /* LaserSubgoal extras (python/lle/env/extras_generators.py:75-101, Builder.add_extras("laser_subgoal")):
+     * n_extras = 0 off, -1 all sources, else the first n_extras entries of extras_src (indices in World::sources() order) */
+    int32_t n_extras;
+    int32_t extras_src[64];
+    /* PotentialShapedLLE (python/lle/env/reward_strategy.py:113-181, Builder.pbrs): pbrs = 1 enables it; n_pbrs / pbrs_src
+     * select the rewarded sources like above (-1 = all).  With reward_dim 4 the shaped term is a fifth reward component. */
+    int32_t pbrs;
+    int32_t n_pbrs;
+    int32_t pbrs_src[64];
+    double pbrs_gamma, pbrs_reward_value;
 } lle_vec_options;
 LLE_API void lle_vec_default_options(lle_vec_options* opts);
 
@@ -139,7 +149,8 @@ LLE_API int lle_vec_destroy(lle_vec* vec);
  *                                  2 GemCollected, 3 AgentDied); bits 2-7: pass >= 2 in which the agent died
  *                                  (world.rs:468-472).  Ordered list = sort by (pass, agent).
  *   actions  i8  [N, A]            the joint action applied (sampled or supplied)
- *   err      u8  [N]               LLE_ENV_* */
+ *   err      u8  [N]               LLE_ENV_*
+ *   extras   f32 [N, A, extras_dim] LaserSubgoal.compute (extras_generators.py:93-98); NULL when extras are off */
 typedef struct {
     int64_t n_envs;
     int32_t n_agents, n_gems, n_channels, height, width, reward_dim, state_dim, n_beams_max;
@@ -153,6 +164,9 @@ typedef struct {
     int8_t* actions;
     uint8_t* err;
     int64_t record_bytes; /* bytes of the per-env engine record kept in HBM (read + written once per step) */
+    float* extras;
+    int32_t extras_dim;
+    int32_t pad;
 } lle_vec_buffers;
 LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 

@@ -80,17 +80,21 @@ struct LleMapHeader {
 //                       | done<<31 ; else four words: alive, arrived, slot, n_arrived | n_deads<<8 | done<<16
 //   [w_avail, w_gems)   World::available_actions cache (world.rs:37): one byte per agent, bit = Action value
 //   [w_gems, w_on)      collected mask (0, 1 or 2 words)
-//   [w_on, n_words)     beam on-masks (LaserBeam.beam, laser.rs:16): 1 word per beam when every beam of the
+//   [w_on, w_sube)      beam on-masks (LaserBeam.beam, laser.rs:16): 1 word per beam when every beam of the
 //                       batch is <= 32 cells, else 2
+//   [w_sube, w_subp)    LaserSubgoal flags (extras_generators.py:91): per agent, one bit per source (sub_words words)
+//   [w_subp, n_words)   PotentialShapedLLE._agents_pos_reached (reward_strategy.py:140), same shape
 struct LleStateLayout {
     int32_t n_words, w_flags, w_avail, w_gems, w_on;
     int32_t gem_words, on_words;  // words of the gem mask (0/1/2), words per beam (1/2)
     int32_t wide_flags;           // A > 8
     int32_t stride;               // n_words rounded up to 4 words (16 bytes)
+    int32_t w_sube, w_subp, sub_words;  // sub_words: words per agent of a subgoal mask (0 when the feature is off)
+    int32_t pad;
 };
 
 #ifdef __cplusplus
-static inline LleStateLayout lle_state_layout(int A, int G, int NB, int max_beam_len) {
+static inline LleStateLayout lle_state_layout(int A, int G, int NB, int max_beam_len, int extras = 0, int pbrs = 0) {
     LleStateLayout L;
     L.wide_flags = A > 8;
     L.w_flags = (A + 1) / 2;
@@ -99,8 +103,12 @@ static inline LleStateLayout lle_state_layout(int A, int G, int NB, int max_beam
     L.gem_words = G == 0 ? 0 : (G <= 32 ? 1 : 2);
     L.w_on = L.w_gems + L.gem_words;
     L.on_words = max_beam_len <= 32 ? 1 : 2;
-    L.n_words = L.w_on + NB * L.on_words;
+    L.sub_words = (extras || pbrs) ? (NB <= 32 ? 1 : 2) : 0;
+    L.w_sube = L.w_on + NB * L.on_words;
+    L.w_subp = L.w_sube + (extras ? A * L.sub_words : 0);
+    L.n_words = L.w_subp + (pbrs ? A * L.sub_words : 0);
     L.stride = (L.n_words + 3) / 4 * 4;
+    L.pad = 0;
     return L;
 }
 #endif

@@ -63,6 +63,10 @@ struct lle_vec {
     bool last_was_step = false;         // the previous launch on this vec was a step (may be overlapped via PDL)
     int8_t* d_actions_stage = nullptr;  // for step_host
     uint64_t* d_timeline = nullptr;     // development aid (LLE_B200_TIMELINE=1)
+    float* d_extras = nullptr;          // [N_pad][A][JE]
+    int JE = 0;
+    uint64_t extras_set = 0, pbrs_set = 0;
+    int8_t extras_beam[64] = {0};
     int64_t obs_stride = 0;
     // launch configuration
     bool fast = false, pdl = true;
@@ -154,6 +158,10 @@ KParams base_params(lle_vec* v) {
     p.n_tickets = (uint32_t)(v->N_pad / v->group);
     p.n_warps_total = (uint32_t)(v->grid * kWarps);
     p.n_steps = 1;
+    p.extras = v->d_extras; p.JE = v->JE; p.pbrs_on = v->opts.pbrs ? 1 : 0;
+    p.extras_set = v->extras_set; p.pbrs_set = v->pbrs_set;
+    p.pbrs_gamma = v->opts.pbrs_gamma; p.pbrs_value = v->opts.pbrs_reward_value;
+    std::memcpy(p.extras_beam, v->extras_beam, sizeof p.extras_beam);
     p.timeline = v->d_timeline;
     return p;
 }
@@ -259,6 +267,7 @@ void lle_vec_default_options(lle_vec_options* o) {
     std::memset(o, 0, sizeof *o);
     o->device = 0; o->reward_dim = 1; o->walkable_lasers = 1; o->auto_reset = 1; o->lle_semantics = 1; o->write_obs = 1;
     o->seed = 0; o->env_id_base = 0;
+    o->n_extras = 0; o->pbrs = 0; o->n_pbrs = -1; o->pbrs_gamma = 0.99; o->pbrs_reward_value = 0.5;  // Builder.pbrs defaults (builder.py:79-80)
 }
 
 int lle_vec_destroy(lle_vec* v) {
@@ -267,7 +276,7 @@ int lle_vec_destroy(lle_vec* v) {
     for (auto* b : v->d_blobs) cudaFree(b);
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
-    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline);
+    cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline); cudaFree(v->d_extras);
     if (v->ev0) cudaEventDestroy(v->ev0);
     if (v->ev1) cudaEventDestroy(v->ev1);
     delete v;
@@ -296,7 +305,28 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
             if (map_of_env[e] < 0 || map_of_env[e] >= n_maps) return fail(LLE_INVALID_ARGUMENT, "map_of_env out of range");
     v->N = n_envs;
     v->N_pad = (n_envs + 31) / 32 * 32;
-    v->L = lle_state_layout(v->A, v->G, v->NBmax, v->max_beam_len);
+    // LaserSubgoal extras / PotentialShapedLLE source selections
+    {
+        auto select = [&](int n, const int32_t* src, uint64_t& set, int8_t* cols, int& count) -> int {
+            set = 0; count = 0;
+            if (n < 0) {
+                for (int b = 0; b < v->NBmax; ++b) { set |= 1ull << b; if (cols) cols[count] = (int8_t)b; ++count; }
+            } else {
+                for (int k = 0; k < n && k < 64; ++k) {
+                    if (src[k] < 0 || src[k] >= v->NBmax) return fail(LLE_INVALID_ARGUMENT, "laser source index out of range");
+                    set |= 1ull << src[k];
+                    if (cols) cols[count] = (int8_t)src[k];
+                    ++count;
+                }
+            }
+            return LLE_OK;
+        };
+        int dummy = 0;
+        if (opts->n_extras != 0) { int rc = select(opts->n_extras, opts->extras_src, v->extras_set, v->extras_beam, v->JE); if (rc) return rc; }
+        if (opts->pbrs) { int rc = select(opts->n_pbrs, opts->pbrs_src, v->pbrs_set, nullptr, dummy); if (rc) return rc; }
+        if (opts->pbrs && opts->reward_dim == 4) v->R = 5;  // np.concat((reward, [potential_reward])) (reward_strategy.py:153)
+    }
+    v->L = lle_state_layout(v->A, v->G, v->NBmax, v->max_beam_len, v->JE > 0, opts->pbrs != 0);
     v->obs_stride = ((int64_t)v->C * v->H * v->W + 3) / 4 * 4;
 
     LLE_CUDA(cudaSetDevice(v->device));
@@ -393,6 +423,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     LLE_CUDA(dalloc(&v->d_events, (size_t)v->A * Np));
     LLE_CUDA(dalloc(&v->d_actions, (size_t)v->A * Np));
     LLE_CUDA(dalloc(&v->d_err, Np));
+    if (v->JE) LLE_CUDA(dalloc(&v->d_extras, (size_t)v->A * v->JE * Np));
     LLE_CUDA(dalloc(&v->d_sched, 2 * kSchedSlots));
     LLE_CUDA(dalloc(&v->d_flags, (size_t)(v->N_pad / v->group)));
     LLE_CUDA(dalloc(&v->d_actions_stage, (size_t)v->A * Np));
@@ -418,6 +449,8 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->obs = v->d_obs; out->state = v->d_state; out->avail = v->d_avail; out->reward = v->d_reward; out->done = v->d_done;
     out->events = v->d_events; out->actions = v->d_actions; out->err = v->d_err;
     out->record_bytes = (int64_t)v->L.stride * 4;
+    out->extras = v->d_extras;
+    out->extras_dim = v->JE;
     return LLE_OK;
 }
 

@@ -88,6 +88,12 @@ struct KParams {
     uint32_t n_tickets, n_warps_total;
     uint64_t* timeline;    // development aid: per warp {start, first store, last store, end} in ns (globaltimer), or nullptr
     int32_t n_steps;       // steps in this launch (> 1: rollout with device-sampled actions)
+    // LaserSubgoal extras / PotentialShapedLLE
+    float* extras;         // [N_pad][A][JE] or nullptr
+    int32_t JE, pbrs_on;
+    uint64_t extras_set, pbrs_set;  // bit b: source b is tracked
+    double pbrs_gamma, pbrs_value;
+    int8_t extras_beam[64];         // source index of extras column j
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -189,6 +195,7 @@ struct World {
     uint32_t gbase, wmask, amask;
     // per lane
     uint32_t pos;
+    uint64_t sub_e, sub_p;  // this agent's LaserSubgoal / PBRS "has stood on a laser of source b" flags
     // group-uniform
     uint32_t alive, arrived, slot, n_arrived, n_deads, done;
 
@@ -217,9 +224,41 @@ struct World {
         if (gl < A) reinterpret_cast<uint8_t*>(rec + L.w_avail)[gl] = (uint8_t)mask;
     }
 
+    // sources (restricted to `set`) one of whose *listed* laser tiles (env/utils.py:6-11 via World::lasers) covers this
+    // agent's cell: `agent_pos in pos_to_reward` of extras_generators.py:95 / reward_strategy.py:171
+    __device__ __forceinline__ uint64_t subgoals_here(uint64_t set) const {
+        uint64_t mm = 0;
+        if (gl < A && set) {
+            const LleCellBeams cb = m.cellbeams[cell(pos)];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const uint32_t e = cb.e[n];
+                if (e == LLE_NO_BEAM) break;
+                if (be_listed(e)) mm |= 1ull << be_b(e);
+            }
+        }
+        return mm & set;
+    }
+    // sum over the lanes of this world's group
+    __device__ __forceinline__ uint32_t gsum(uint32_t v) const {
+        for (int off = Wd >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off, Wd);
+        return v;
+    }
+
     // ---- record <-> registers
     __device__ __forceinline__ void unpack() {
         pos = 0;
+        sub_e = sub_p = 0;
+        if (L.sub_words && gl < A) {
+            if (L.w_subp > L.w_sube) {
+                sub_e = rec[L.w_sube + gl * L.sub_words];
+                if (L.sub_words == 2) sub_e |= (uint64_t)rec[L.w_sube + gl * 2 + 1] << 32;
+            }
+            if (L.n_words > L.w_subp) {
+                sub_p = rec[L.w_subp + gl * L.sub_words];
+                if (L.sub_words == 2) sub_p |= (uint64_t)rec[L.w_subp + gl * 2 + 1] << 32;
+            }
+        }
         if (gl < A) {
             const uint32_t w = rec[gl >> 1];
             pos = (gl & 1) ? (w >> 16) : (w & 0xFFFFu);
@@ -238,6 +277,16 @@ struct World {
     __device__ __forceinline__ void pack() {
         const uint32_t other = __shfl_down_sync(kFull, pos, 1, Wd);
         if (gl < A && !(gl & 1)) rec[gl >> 1] = pos | ((gl + 1 < A ? other : 0u) << 16);
+        if (L.sub_words && gl < A) {
+            if (L.w_subp > L.w_sube) {
+                rec[L.w_sube + gl * L.sub_words] = (uint32_t)sub_e;
+                if (L.sub_words == 2) rec[L.w_sube + gl * 2 + 1] = (uint32_t)(sub_e >> 32);
+            }
+            if (L.n_words > L.w_subp) {
+                rec[L.w_subp + gl * L.sub_words] = (uint32_t)sub_p;
+                if (L.sub_words == 2) rec[L.w_subp + gl * 2 + 1] = (uint32_t)(sub_p >> 32);
+            }
+        }
         if (gl == 0) {
             if (!L.wide_flags) {
                 const uint32_t nd = n_deads > 7u ? 7u : n_deads;  // only "> 0" is ever observed (env.py:253-254)
@@ -349,7 +398,7 @@ struct World {
     }
     // World::reset (world.rs:411-432) with one start per agent (RNG-free, utils/mod.rs:63), then
     // RewardStrategy.reset / LLE.reset bookkeeping (env.py:191-203).
-    __device__ __forceinline__ void reset(bool on) {
+    __device__ __forceinline__ void reset(bool on, uint64_t pbrs_set) {
         tiles_reset(on);
         if (on) {
             alive = amask; arrived = 0; n_arrived = 0; n_deads = 0; done = 0;
@@ -357,6 +406,10 @@ struct World {
         }
         pre_enter_all(on, pos, alive);
         (void)enter_all(on, pos);  // events are dropped (world.rs:428-430)
+        if (on) {
+            sub_e = 0;                        // extras_generator.reset() (env.py:196); marked again when observed
+            sub_p = subgoals_here(pbrs_set);  // PotentialShapedLLE.reset (reward_strategy.py:176-180): clear, then compute_potential()
+        }
     }
     // World::compute_available_actions (world.rs:343-363) as a 5-bit mask indexed by Action value.
     __device__ __forceinline__ uint32_t available() const {
@@ -698,6 +751,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             w.unpack();
 
             uint32_t ev = 0, act = 4, err = ERR_OK, n_gem = 0, n_exit = 0, n_died = 0;
+            double shaped = 0.0;
             bool touch = true;  // whether reward/done/events/err/actions are (re)written
             bool paid = false;  // whether a reward is due (a transition happened)
             const bool real = env < p.N;
@@ -719,9 +773,18 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 paid = err == ERR_OK;
                 ev = w.step(paid, act, n_gem, n_exit, n_died);
                 w.account(paid, n_exit, n_died);
+                if (p.pbrs_on) {  // PotentialShapedLLE.compute_reward (reward_strategy.py:145-158), python-float arithmetic
+                    const uint32_t before = w.gsum((uint32_t)__popcll(w.sub_p));
+                    if (paid) w.sub_p |= w.subgoals_here(p.pbrs_set);
+                    const uint32_t after = w.gsum((uint32_t)__popcll(w.sub_p));
+                    const uint32_t size = (uint32_t)A * (uint32_t)__popcll(p.pbrs_set & len_mask(w.m.NB));
+                    const double prev = __dmul_rn((double)(size - before), p.pbrs_value);
+                    const double curr = __dmul_rn((double)(size - after), p.pbrs_value);
+                    shaped = __dsub_rn(__dmul_rn(p.pbrs_gamma, prev), curr);  // no fused multiply-add, like CPython
+                }
             } else if constexpr (MODE == MODE_RESET) {
                 const bool on = !p.reset_mask || !real || p.reset_mask[env];
-                w.reset(on);
+                w.reset(on, p.pbrs_set);
                 touch = on;
             } else {  // MODE_SET_STATE: World::set_state (world.rs:515-597) + LLE.set_state (env.py:208-216)
                 touch = real;  // padding worlds: nothing to force
@@ -741,6 +804,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 if (real && p.lle_semantics) {  // reward_strategy.reset() precedes world.set_state (env.py:213)
                     w.n_arrived = 0;
                     w.n_deads = 0;
+                    if (p.pbrs_on) w.sub_p = w.subgoals_here(p.pbrs_set);  // ... with the positions the world still has
                 }
                 bool dup = false;
                 for (int o = 0; o < A; ++o) {
@@ -769,11 +833,19 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 if (restore) ev = 0;
                 // compute_reward(events); done = compute_done() (env.py:215-216)
                 w.account(go && err == ERR_OK && p.lle_semantics, n_exit, n_died);
+                if (p.pbrs_on && go && err == ERR_OK && p.lle_semantics) w.sub_p |= w.subgoals_here(p.pbrs_set);  // compute_potential()
             }
 
             if (touch) {
-                for (int r = gl; r < p.R; r += Wd)
-                    p.reward[env * p.R + r] = paid ? w.reward_component(r, p.R, n_gem, n_exit, n_died) : 0.0f;
+                for (int r = gl; r < p.R; r += Wd) {
+                    float v = 0.0f;
+                    if (paid) {
+                        if (p.R == 1) v = __fadd_rn(w.reward_component(0, 1, n_gem, n_exit, n_died), (float)shaped);  // np.float32 += python float
+                        else if (r < 4) v = w.reward_component(r, 4, n_gem, n_exit, n_died);
+                        else v = (float)shaped;  // fifth component of MultiObjective + PBRS (np.concat, :153)
+                    }
+                    p.reward[env * p.R + r] = v;
+                }
                 if (gl == 0) {
                     p.done[env] = (uint8_t)w.done;
                     p.err[env] = (uint8_t)err;
@@ -786,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             // auto-reset: the transition above is reported; observation / state / availability below are those
             // of the freshly reset world (SURVEY §8d "Auto-reset")
             const bool do_reset = MODE == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
-            if (__any_sync(kFull, do_reset)) w.reset(do_reset);
+            if (__any_sync(kFull, do_reset)) w.reset(do_reset, p.pbrs_set);
 
             // compute_available_actions (world.rs:343-363) closes reset (:431), step (:473) and a successful set_state
             // (:595, also reached by the restore at :563); a set_state that fails with InvalidWorldState returns before it,
@@ -796,6 +868,9 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             if (refresh) w.store_avail(mask);
             else mask = w.cached_avail();
             if (!p.walkable) mask = w.available_no_walk(mask);  // LLE-level mask (env.py:153-163), output only
+            // LaserSubgoal.compute runs when the observation is built (env.py:218-223): after a step or a reset, not
+            // after set_state
+            if (p.JE && MODE != MODE_SET_STATE) w.sub_e |= w.subgoals_here(p.extras_set);
             w.pack();
             __syncwarp();
             {   // record back to HBM and the small per-step vectors
@@ -810,6 +885,10 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     uint8_t* av = p.avail + (env * A + gl) * 5;  // LLE.available_actions (env.py:146-163): u8[A,5]
 #pragma unroll
                     for (int k = 0; k < 5; ++k) av[k] = (uint8_t)((mask >> k) & 1u);
+                }
+                if (p.JE && gl < A) {
+                    float* ex = p.extras + (env * A + gl) * p.JE;
+                    for (int j = 0; j < p.JE; ++j) ex[j] = ((w.sub_e >> p.extras_beam[j]) & 1ull) ? 1.0f : 0.0f;
                 }
                 if (p.G) {
                     const uint64_t coll = w.collected();

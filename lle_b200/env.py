@@ -21,10 +21,11 @@ class VecLLE:
     """
 
     def __init__(self, maps, n_envs: int, *, map_of_env: Sequence[int] | None = None, device=0, multi_objective: bool = False,
-                 walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True):
+                 walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True,
+                 extras=None, pbrs: dict | None = None):
         self.world = VecWorld(maps, n_envs, map_of_env=map_of_env, device=device, reward_dim=4 if multi_objective else 1,
                               walkable_lasers=walkable_lasers, auto_reset=auto_reset, lle_semantics=True, write_obs=write_obs,
-                              seed=seed, env_id_base=env_id_base)
+                              seed=seed, env_id_base=env_id_base, extras=extras, pbrs=pbrs)
         for m in self.world.maps:
             if m.obs_invalid and write_obs:
                 raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
@@ -44,6 +45,7 @@ class VecLLE:
     events = property(lambda self: self.world.events)                # (N, A) u8
     actions = property(lambda self: self.world.actions)              # (N, A) i8
     err = property(lambda self: self.world.err)                      # (N,) u8
+    extras = property(lambda self: self.world.extras)                # (N, A, n_sources) f32 or None
 
     def reset(self, mask: torch.Tensor | None = None):
         self.world.reset(mask)
@@ -110,7 +112,34 @@ class Builder:
         return self
 
     def multi_objective(self, enabled: bool = True):
+        if enabled and "pbrs" in self._kw:  # builder.py:66-73
+            raise ValueError("Cannot set multi-objective after setting a reward shaping strategy. Call `multi_objective()` first.")
         self._kw["multi_objective"] = enabled
+        return self
+
+    def pbrs(self, gamma: float = 0.99, reward_value: float = 0.5, lasers_to_reward=None, with_extras: bool = True):
+        """Potential-based reward shaping on laser crossings (builder.py:77-110).  `lasers_to_reward`: source positions
+        (i, j) or source indices; None = all sources."""
+        rewarded = None
+        if lasers_to_reward is not None:
+            src_pos = [s.pos for s in self._maps.sources()] if isinstance(self._maps, Map) else None
+            rewarded = []
+            for item in lasers_to_reward:
+                if isinstance(item, tuple):
+                    if src_pos is None or item not in src_pos:
+                        raise ValueError(f"Invalid laser source: {item}")
+                    rewarded.append(src_pos.index(item))
+                else:
+                    rewarded.append(int(item))
+        self._kw["pbrs"] = dict(gamma=gamma, reward_value=reward_value, lasers_to_reward=rewarded, with_extras=with_extras)
+        return self
+
+    def add_extras(self, *extras):
+        """Only "laser_subgoal" exists on the accelerated path (builder.py:124-150)."""
+        for e in extras:
+            if e != "laser_subgoal":
+                raise ValueError(f"Invalid extra type: {e}")
+            self._kw["extras"] = "laser_subgoal"
         return self
 
     def walkable_lasers(self, walkable: bool = True):

@@ -98,7 +98,11 @@ class VecWorld:
 
     def __init__(self, maps: Sequence[Map | str | int] | Map | str | int, n_envs: int, *, map_of_env: Sequence[int] | None = None,
                  device: int | str | torch.device = 0, reward_dim: int = 1, walkable_lasers: bool = True, auto_reset: bool = True,
-                 lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0):
+                 lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0,
+                 extras: str | Sequence[int] | None = None, pbrs: dict | None = None):
+        """extras: None | "laser_subgoal" (all sources) | source indices (World::sources() order) — Builder.add_extras.
+        pbrs: None | dict(gamma=0.99, reward_value=0.5, lasers_to_reward=None | indices, with_extras=True) — Builder.pbrs
+        (python/lle/env/builder.py:77-150)."""
         if not torch.cuda.is_available():
             raise RuntimeError("lle_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if isinstance(maps, (Map, str, int)):
@@ -111,6 +115,22 @@ class VecWorld:
         opts.reward_dim, opts.walkable_lasers, opts.auto_reset = int(reward_dim), int(walkable_lasers), int(auto_reset)
         opts.lle_semantics, opts.write_obs = int(lle_semantics), int(write_obs)
         opts.seed, opts.env_id_base = int(seed), int(env_id_base)
+        extras_src = None if extras in (None, "laser_subgoal") else [int(x) for x in extras]
+        want_extras = extras is not None
+        if pbrs is not None:
+            opts.pbrs = 1
+            opts.pbrs_gamma = float(pbrs.get("gamma", 0.99))
+            opts.pbrs_reward_value = float(pbrs.get("reward_value", 0.5))
+            rewarded = pbrs.get("lasers_to_reward")
+            opts.n_pbrs = -1 if rewarded is None else len(rewarded)
+            for k, b in enumerate(rewarded or []):
+                opts.pbrs_src[k] = int(b)
+            if pbrs.get("with_extras", True) and not want_extras:
+                want_extras, extras_src = True, (None if rewarded is None else [int(x) for x in rewarded])
+        if want_extras:
+            opts.n_extras = -1 if extras_src is None else len(extras_src)
+            for k, b in enumerate(extras_src or []):
+                opts.extras_src[k] = int(b)
         handles = (C.c_void_p * len(self.maps))(*[m._h for m in self.maps])
         moe = None
         if map_of_env is not None:
@@ -149,6 +169,9 @@ class VecWorld:
         self.events = wrap(b.events, (N, A), "|u1")
         self.actions = wrap(b.actions, (N, A), "|i1")
         self.err = wrap(b.err, (N,), "|u1")
+        #: LaserSubgoal flags (N, A, n_sources); None when extras are off
+        self.extras_dim = int(b.extras_dim)
+        self.extras = wrap(b.extras, (N, A, self.extras_dim), "<f4") if self.extras_dim else None
 
     def __del__(self):
         h = getattr(self, "_h", None)

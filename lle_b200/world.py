@@ -225,15 +225,16 @@ class Step:
     reward: np.ndarray
     done: bool
     events: list
+    extras: np.ndarray | None = None
 
 
 class LLE(_Single):
     """`lle.LLE` (python/lle/env/env.py) for one environment, served by the device path."""
 
     def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
-                 walkable_lasers: bool = True, device=0):
+                 walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, device=0):
         self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
-                          reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers)
+                          reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs)
         if self._map.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         self.reward_dim = self._vec.reward_dim
@@ -260,8 +261,16 @@ class LLE(_Single):
     def available_actions(self) -> np.ndarray:
         return self._available()
 
+    def extras(self) -> np.ndarray:
+        """LaserSubgoal.compute (extras_generators.py:93-98): float32 (A, n_sources)."""
+        self._vec.synchronize()
+        if self._vec.extras is None:
+            return np.zeros((self.n_agents, 0), dtype=np.float32)
+        return self._vec.extras[0].cpu().numpy()
+
     def reset(self):
         self._vec.reset()
+        self.last_extras = self.extras()
         return self.observe(), self.get_state()
 
     def step(self, actions: Sequence[int]) -> Step:
@@ -275,8 +284,9 @@ class LLE(_Single):
             raise ValueError("Cannot step in a done environment")
         if err == 1:
             raise InvalidActionError("InvalidAction")
+        self.last_extras = self.extras()
         return Step(self.observe(), self.available_actions(), self.get_state(), self._vec.reward[0].cpu().numpy(),
-                    bool(self._vec.done[0]), decode_events(self._vec.events[0].cpu().tolist()))
+                    bool(self._vec.done[0]), decode_events(self._vec.events[0].cpu().tolist()), self.last_extras)
 
     def set_state(self, state: WorldState):
         self._force_state(state)

@@ -886,7 +886,44 @@ inline void state_as_array(const WorldState& s, float* out) {
 
 constexpr float REWARD_GEM = 1.0f, REWARD_EXIT = 1.0f, REWARD_DONE = 1.0f, REWARD_DEATH = -1.0f;
 
-// python/lle/env/env.py (LLE) + env/reward_strategy.py (SingleObjective / MultiObjective)
+// python/lle/env/extras_generators.py:75-101 (LaserSubgoal) and the position sets of
+// reward_strategy.py:161-167 (PotentialShapedLLE._compute_positions_to_reward): for each chosen source, the
+// positions of its laser tiles *as listed by World::lasers()* (env/utils.py:6-11), and an (agent, source) matrix of
+// sticky "has stood there" flags.
+struct SubgoalTracker {
+    std::vector<std::vector<Position>> pos_to_reward;  // per chosen source
+    std::vector<std::vector<bool>> reached;            // [agent][source]
+    void init(const World& w, const std::vector<size_t>& sources) {
+        pos_to_reward.clear();
+        auto lasers = w.lasers();
+        for (size_t src : sources) {
+            std::vector<Position> cells;
+            const size_t laser_id = w.source_beam(src)->laser_id;
+            for (const auto& l : lasers)
+                if (l.laser_id == laser_id) cells.push_back(l.pos);
+            pos_to_reward.push_back(cells);
+        }
+        reached.assign(w.n_agents(), std::vector<bool>(sources.size(), false));
+    }
+    void clear() {
+        for (auto& row : reached) std::fill(row.begin(), row.end(), false);
+    }
+    void mark(const World& w) {  // extras_generators.py:93-97 / reward_strategy.py:169-173
+        for (size_t a = 0; a < w.agents_positions.size(); ++a)
+            for (size_t j = 0; j < pos_to_reward.size(); ++j)
+                if (std::find(pos_to_reward[j].begin(), pos_to_reward[j].end(), w.agents_positions[a]) != pos_to_reward[j].end())
+                    reached[a][j] = true;
+    }
+    size_t size() const { return reached.size() * pos_to_reward.size(); }
+    size_t count() const {
+        size_t n = 0;
+        for (const auto& row : reached)
+            for (bool b : row) n += b;
+        return n;
+    }
+};
+
+// python/lle/env/env.py (LLE) + env/reward_strategy.py (SingleObjective / MultiObjective / PotentialShapedLLE)
 struct Env {
     World world;
     Layered layered;
@@ -894,11 +931,43 @@ struct Env {
     bool walkable_lasers;
     size_t n_arrived = 0, n_deads = 0;
     bool done = false;
+    // extras: LaserSubgoal (Builder.add_extras("laser_subgoal"), builder.py:124-150)
+    bool has_extras = false;
+    SubgoalTracker extras;
+    // reward shaping: PotentialShapedLLE (Builder.pbrs, builder.py:77-110)
+    bool has_pbrs = false;
+    SubgoalTracker pbrs;
+    double gamma = 0.99, reward_value = 0.5, previous_potential = 0.0;
 
     Env(World&& w, bool multi_obj = false, bool walkable = true)
         : world(std::move(w)), layered(world), multi_objective(multi_obj), walkable_lasers(walkable) {}
 
-    size_t reward_dim() const { return multi_objective ? 4 : 1; }
+    size_t reward_dim() const { return (multi_objective ? 4 : 1) + (multi_objective && has_pbrs ? 1 : 0); }
+
+    void enable_extras(const std::vector<size_t>& sources) {  // LaserSubgoal.__init__ (extras_generators.py:80-91)
+        has_extras = true;
+        extras.init(world, sources);
+    }
+    void enable_pbrs(double g, double value, const std::vector<size_t>& sources) {  // reward_strategy.py:128-153
+        has_pbrs = true;
+        gamma = g;
+        reward_value = value;
+        pbrs.init(world, sources);
+        previous_potential = compute_potential();
+    }
+    // reward_strategy.py:169-174
+    double compute_potential() {
+        pbrs.mark(world);
+        return (double)(pbrs.size() - pbrs.count()) * reward_value;
+    }
+    // LaserSubgoal.compute (extras_generators.py:93-98) -> float32 [A, J]
+    void compute_extras(float* out) {
+        if (!has_extras) return;
+        extras.mark(world);
+        size_t k = 0;
+        for (const auto& row : extras.reached)
+            for (bool b : row) out[k++] = b ? 1.0f : 0.0f;
+    }
 
     // reward_strategy.py:58-75 (SingleObjective) and :90-109 (MultiObjective)
     void compute_reward(const std::vector<WorldEvent>& events, float* reward) {
@@ -932,16 +1001,32 @@ struct Env {
             }
             std::memcpy(reward, r, sizeof(r));
         }
+        if (has_pbrs) {  // PotentialShapedLLE.compute_reward (reward_strategy.py:145-158)
+            const double current = compute_potential();
+            const double shaped = gamma * previous_potential - current;  // python floats: no fused multiply-add
+            if (!multi_objective) reward[0] = reward[0] + (float)shaped;  // np.float32 += python float (NEP 50: float32 arithmetic)
+            else reward[4] = (float)shaped;  // np.concat gives float64 there; the oracle's buffer is float32 (value rounded once)
+            previous_potential = current;
+        }
     }
     bool compute_done() const { return n_arrived == world.n_agents() || n_deads > 0; }  // env.py:253-254
 
     // env.py:191-203 (randomize_lasers is out of scope)
     void reset() {
         world.reset();
-        n_arrived = 0;
-        n_deads = 0;
+        reset_strategy();
+        if (has_extras) extras.clear();  // extras_generator.reset() (env.py:196)
         done = false;
         layered.setup(world);
+    }
+    // RewardStrategy.reset (:40-42) / PotentialShapedLLE.reset (:176-180)
+    void reset_strategy() {
+        n_arrived = 0;
+        n_deads = 0;
+        if (has_pbrs) {
+            pbrs.clear();
+            previous_potential = compute_potential();
+        }
     }
     // env.py:165-189 ; raises ValueError on a done env (:166-167)
     std::vector<WorldEvent> step(const std::vector<Action>& actions, float* reward) {
@@ -953,10 +1038,9 @@ struct Env {
     }
     // env.py:208-216
     void set_state(const WorldState& s) {
-        n_arrived = 0;
-        n_deads = 0;
+        reset_strategy();  // with the positions the world has *before* the new state is forced (env.py:213)
         auto events = world.set_state(s);
-        float scratch[4];
+        float scratch[5];
         compute_reward(events, scratch);
         done = compute_done();
     }

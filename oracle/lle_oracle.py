@@ -42,7 +42,7 @@ def lib():
         build()
         L = C.CDLL(_LIB_PATH)
         L.lleo_last_error.restype = C.c_char_p
-        for name in ("lleo_world_new", "lleo_env_new", "lleo_vec_new"):
+        for name in ("lleo_world_new", "lleo_env_new", "lleo_vec_new", "lleo_vec_extras", "lleo_vec_reward"):
             getattr(L, name).restype = C.c_void_p
         L.lleo_vec_rollout.restype = C.c_double
         L.lleo_vec_step_count.restype = C.c_uint64
@@ -425,14 +425,36 @@ class Step:
     events: list
 
 
+def _src_list(sources):
+    """None -> all sources (n = -1); otherwise a list of indices into World::sources() order."""
+    if sources is None:
+        return -1, None
+    arr = (C.c_int * max(1, len(sources)))(*[int(x) for x in sources])
+    return len(sources), arr
+
+
 class LLE:
-    def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True):
+    def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True, extras=None, pbrs=None):
+        """extras: None | "laser_subgoal" | list of source indices.  pbrs: None | dict(gamma=0.99, reward_value=0.5,
+        lasers_to_reward=None (all) | list of source indices, with_extras=True) — Builder.pbrs (builder.py:77-110)."""
         st = C.c_int(0)
         self._h = C.c_void_p(lib().lleo_env_new(map_str.encode(), int(multi_objective), int(walkable_lasers), C.byref(st)))
         _check(st.value)
+        extras_src = None if extras in (None, "laser_subgoal") else list(extras)
+        want_extras = extras is not None
+        if pbrs is not None:
+            n, arr = _src_list(pbrs.get("lasers_to_reward"))
+            if pbrs.get("with_extras", True) and not want_extras:
+                want_extras, extras_src = True, pbrs.get("lasers_to_reward")
+            _check(lib().lleo_env_enable_pbrs(self._h, C.c_double(pbrs.get("gamma", 0.99)), C.c_double(pbrs.get("reward_value", 0.5)), n, arr))
+        if want_extras:
+            n, arr = _src_list(extras_src)
+            _check(lib().lleo_env_enable_extras(self._h, n, arr))
         d = (C.c_int * 6)()
         lib().lleo_env_dims(self._h, d)
         self.height, self.width, self.n_agents, self.n_gems, self.n_channels, self.reward_dim = list(d)
+        self.reward_dim = lib().lleo_env_reward_dim(self._h)
+        self.extras_dim = lib().lleo_env_extras_dim(self._h)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -467,9 +489,17 @@ class LLE:
         lib().lleo_env_available(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)))
         return out.astype(bool)
 
+    def extras(self) -> np.ndarray:
+        """LaserSubgoal.compute (extras_generators.py:93-98): float32 (A, n_sources)."""
+        out = np.zeros((self.n_agents, max(self.extras_dim, 1)), dtype=np.float32)
+        lib().lleo_env_extras(self._h, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out[:, : self.extras_dim]
+
     def reset(self):
         _check(lib().lleo_env_reset(self._h))
-        return self.observe(), self.get_state()
+        obs, state = self.observe(), self.get_state()
+        self.last_extras = self.extras()
+        return obs, state
 
     def step(self, actions: Sequence[int]) -> Step:
         acts = (C.c_uint8 * len(actions))(*[int(a) for a in actions])
@@ -480,7 +510,9 @@ class LLE:
         _check(lib().lleo_env_step(self._h, acts, len(actions), reward.ctypes.data_as(C.POINTER(C.c_float)),
                                    C.byref(done), ev, C.byref(n)))
         events = [WorldEvent(EventType(ev[2 * k]), ev[2 * k + 1]) for k in range(n.value)]
-        return Step(self.observe(), self.available_actions(), self.get_state(), reward, bool(done.value), events)
+        step = Step(self.observe(), self.available_actions(), self.get_state(), reward, bool(done.value), events)
+        step.extras = self.last_extras = self.extras()
+        return step
 
     def set_state(self, state: WorldState):
         na, ng = len(state.agents_positions), len(state.gems_collected)
@@ -495,13 +527,26 @@ class OracleVec:
     """N oracle environments stepped in lockstep; arrays are views on the C++ buffers."""
 
     def __init__(self, maps: Sequence[str], map_of_env: Sequence[int] | None, n_envs: int, *, multi_objective=False,
-                 walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0):
+                 walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0, extras=None, pbrs=None):
         texts = (C.c_char_p * len(maps))(*[m.encode() for m in maps])
         moe = None if map_of_env is None else (C.c_int * n_envs)(*[int(m) for m in map_of_env])
         st = C.c_int(0)
         self._h = C.c_void_p(lib().lleo_vec_new(texts, len(maps), moe, n_envs, int(multi_objective), int(walkable_lasers),
                                                 int(auto_reset), C.c_uint64(seed), C.c_uint64(env_id_base), C.byref(st)))
         _check(st.value)
+        self.JE = 0
+        if extras is not None or pbrs is not None:
+            extras_src = None if extras in (None, "laser_subgoal") else list(extras)
+            want_extras = extras is not None
+            pb = pbrs or {}
+            if pbrs is not None and pb.get("with_extras", True) and not want_extras:
+                want_extras, extras_src = True, pb.get("lasers_to_reward")
+            ne, ea = _src_list(extras_src) if want_extras else (0, None)
+            np_, pa = _src_list(pb.get("lasers_to_reward"))
+            _check(lib().lleo_vec_configure(self._h, ne, ea, int(pbrs is not None), C.c_double(pb.get("gamma", 0.99)),
+                                            C.c_double(pb.get("reward_value", 0.5)), np_, pa))
+            lib().lleo_vec_extras_dim.restype = C.c_long
+            self.JE = lib().lleo_vec_extras_dim(self._h)
         d = (C.c_long * 9)()
         lib().lleo_vec_dims(self._h, d)
         self.N, self.A, self.G, self.C, self.H, self.W, self.R, self.S, self.NB = list(d)
@@ -530,6 +575,12 @@ class OracleVec:
         self.slot = view(11, C.c_uint8, np.uint8, (N, A))
         self.beam_on = view(12, C.c_uint64, np.uint64, (N, max(self.NB, 1)))
         self.collected = view(13, C.c_uint64, np.uint64, (N,))
+        if self.JE:
+            lib().lleo_vec_extras.restype = C.c_void_p
+            ptr = lib().lleo_vec_extras(self._h)
+            self.extras = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(N * A * self.JE,)).reshape(N, A, self.JE)
+        else:
+            self.extras = np.zeros((N, A, 0), dtype=np.float32)
 
     def __del__(self):
         h = getattr(self, "_h", None)

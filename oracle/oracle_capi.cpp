@@ -118,7 +118,8 @@ struct Vec {
     size_t N = 0, A = 0, G = 0, C = 0, H = 0, W = 0, R = 1, S = 0, NB = 0;
     bool auto_reset = false;
     uint64_t seed = 0, env_id_base = 0, t = 0;
-    std::vector<float> obs, state, reward;
+    std::vector<float> obs, state, reward, extras;  // extras: LaserSubgoal flags [N, A, JE]
+    size_t JE = 0;
     std::vector<uint8_t> avail, done, events, err;
     std::vector<int8_t> actions;
     // raw engine state for white-box parity checks
@@ -132,6 +133,7 @@ struct Vec {
         env.observe(&obs[e * C * H * W]);
         env.state(&state[e * S]);
         env.available_actions(&avail[e * A * 5]);
+        if (JE) env.compute_extras(&extras[e * A * JE]);
         const World& w = env.world;
         for (size_t a = 0; a < A; ++a) {
             pos[(e * A + a) * 2] = (int16_t)w.agents_positions[a].i;
@@ -408,6 +410,27 @@ int lleo_env_set_state(void* p, const long* pos, int n_agents, const uint8_t* ge
         e.set_state(s);
     });
 }
+int lleo_env_enable_extras(void* p, int n, const int* src) {
+    Env& e = *(Env*)p;
+    return guarded([&] {
+        std::vector<size_t> s;
+        if (n < 0) for (size_t k = 0; k < e.world.laser_source_positions.size(); ++k) s.push_back(k);
+        else for (int k = 0; k < n; ++k) s.push_back((size_t)src[k]);
+        e.enable_extras(s);
+    });
+}
+int lleo_env_enable_pbrs(void* p, double gamma, double value, int n, const int* src) {
+    Env& e = *(Env*)p;
+    return guarded([&] {
+        std::vector<size_t> s;
+        if (n < 0) for (size_t k = 0; k < e.world.laser_source_positions.size(); ++k) s.push_back(k);
+        else for (int k = 0; k < n; ++k) s.push_back((size_t)src[k]);
+        e.enable_pbrs(gamma, value, s);
+    });
+}
+int lleo_env_extras_dim(void* p) { return ((Env*)p)->has_extras ? (int)((Env*)p)->extras.pos_to_reward.size() : 0; }
+void lleo_env_extras(void* p, float* out) { ((Env*)p)->compute_extras(out); }
+int lleo_env_reward_dim(void* p) { return (int)((Env*)p)->reward_dim(); }
 int lleo_env_done(void* p) { return ((Env*)p)->done; }
 int lleo_env_n_arrived(void* p) { return (int)((Env*)p)->n_arrived; }
 void lleo_env_available(void* p, uint8_t* out) { ((Env*)p)->available_actions(out); }
@@ -464,6 +487,41 @@ void* lleo_vec_new(const char** texts, int n_maps, const int* map_of_env, int n_
     });
     return v;
 }
+// Builder.add_extras("laser_subgoal") / Builder.pbrs(...) for every env of the vec (python/lle/env/builder.py:77-150).
+// Source lists are indices into World::sources() order; n < 0 means "all sources".  Resets every env afterwards.
+int lleo_vec_configure(void* p, int n_extras, const int* extras_src, int pbrs, double gamma, double value, int n_pbrs,
+                       const int* pbrs_src) {
+    Vec& v = *(Vec*)p;
+    return guarded([&] {
+        auto pick = [](const World& w, int n, const int* src) {
+            std::vector<size_t> out;
+            if (n < 0) for (size_t k = 0; k < w.laser_source_positions.size(); ++k) out.push_back(k);
+            else for (int k = 0; k < n; ++k) out.push_back((size_t)src[k]);
+            return out;
+        };
+        size_t je = 0;
+        for (auto& e : v.envs) {
+            if (n_extras != 0) {
+                auto src = pick(e->world, n_extras, extras_src);
+                e->enable_extras(src);
+                je = std::max(je, src.size());
+            }
+            if (pbrs) e->enable_pbrs(gamma, value, pick(e->world, n_pbrs, pbrs_src));
+        }
+        v.JE = je;
+        v.extras.assign(v.N * v.A * std::max<size_t>(je, 1), 0.f);
+        v.R = v.envs[0]->reward_dim();
+        v.reward.assign(v.N * v.R, 0.f);
+        for (size_t e = 0; e < v.N; ++e) {
+            v.envs[e]->reset();
+            v.export_env(e);
+        }
+    });
+}
+void* lleo_vec_extras(void* p) { return ((Vec*)p)->extras.data(); }
+long lleo_vec_extras_dim(void* p) { return (long)((Vec*)p)->JE; }
+long lleo_vec_reward_dim(void* p) { return (long)((Vec*)p)->R; }
+void* lleo_vec_reward(void* p) { return ((Vec*)p)->reward.data(); }
 void lleo_vec_free(void* p) { delete (Vec*)p; }
 // out: N, A, G, C, H, W, R, S, NB
 void lleo_vec_dims(void* p, long* out) {
@@ -571,6 +629,7 @@ double lleo_vec_rollout(void* p, int steps, int n_threads, int* threads_used) {
                 env.observe(&v.obs[e * v.C * v.H * v.W]);
                 env.state(&v.state[e * v.S]);
                 env.available_actions(&v.avail[e * v.A * 5]);
+                if (v.JE) env.compute_extras(&v.extras[e * v.A * v.JE]);
             }
         }
     };

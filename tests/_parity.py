@@ -19,6 +19,8 @@ def assert_same(impl, ora, raw=None, ctx=""):
         for name in ("pos", "alive", "arrived", "slot", "collected"):
             a, b = raw[name], np.asarray(getattr(ora, name))
             assert np.array_equal(a, b), f"{ctx}: raw '{name}' differs at {np.argwhere(a != b)[:3]}"
+        if "extras" in raw:
+            assert np.array_equal(raw["extras"], np.asarray(ora.extras)), f"{ctx}: LaserSubgoal extras differ at {np.argwhere(raw['extras'] != np.asarray(ora.extras))[:3]}"
         nb = ora.NB
         if nb:
             assert np.array_equal(raw["beam_on"][:, :nb], np.asarray(ora.beam_on)[:, :nb]), f"{ctx}: raw beam masks differ"

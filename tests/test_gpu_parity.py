@@ -26,6 +26,8 @@ class Dev:
         raw = {k: t.cpu().numpy() for k, t in v.export_raw().items()}
         raw["beam_on"] = raw["beam_on"].view(np.uint64)
         raw["collected"] = raw["collected"].view(np.uint64)
+        if getattr(self, "with_extras", False):
+            raw["extras"] = v.extras.cpu().numpy()
         return raw
 
 
@@ -33,10 +35,13 @@ def make_pair(maps, map_of_env, n_envs, **kw):
     import lle_b200
 
     okw = dict(multi_objective=kw.get("reward_dim", 1) == 4, walkable_lasers=kw.get("walkable_lasers", True),
-               auto_reset=kw.get("auto_reset", True), seed=kw.get("seed", 0), env_id_base=kw.get("env_id_base", 0))
+               auto_reset=kw.get("auto_reset", True), seed=kw.get("seed", 0), env_id_base=kw.get("env_id_base", 0),
+               extras=kw.get("extras"), pbrs=kw.get("pbrs"))
     ora = lo.OracleVec(maps, map_of_env, n_envs, **okw)
     vec = lle_b200.VecWorld(maps, n_envs, map_of_env=map_of_env, **kw)
-    return ora, Dev(vec)
+    dev = Dev(vec)
+    dev.with_extras = ora.JE > 0
+    return ora, dev
 
 
 def run_pair(maps, map_of_env, n_envs, steps, check_every=1, **kw):
@@ -86,6 +91,21 @@ def test_options():
     run_pair([level_text(5)], None, 256, 150, walkable_lasers=False, seed=8)
     ora, dev = run_pair([level_text(6)], None, 256, 250, auto_reset=False, seed=5)
     assert (ora.err == 2).any()
+
+
+def test_laser_subgoal_extras_and_pbrs():
+    """LaserSubgoal flags (extras_generators.py:75-101) and PotentialShapedLLE (reward_strategy.py:113-181)
+    fused into the step, single- and multi-objective, all / selected sources, with and without auto-reset."""
+    run_pair([level_text(6)], None, 300, 200, extras="laser_subgoal", seed=31)
+    run_pair([level_text(5)], None, 300, 200, pbrs=dict(gamma=0.99, reward_value=0.5), seed=32)
+    run_pair([level_text(6)], None, 300, 200, reward_dim=4, pbrs=dict(gamma=0.9, reward_value=0.3, lasers_to_reward=[2, 0]), seed=33)
+    run_pair([level_text(4)], None, 300, 200, pbrs=dict(with_extras=False, lasers_to_reward=[1]), extras=[0], seed=34)
+    run_pair([level_text(6)], None, 200, 200, auto_reset=False, pbrs=dict(gamma=1.0, reward_value=1.0), seed=35)
+    rows = [" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)]
+    run_pair(["\n".join(rows)], None, 64, 80, pbrs=dict(), seed=36)  # 14 sources: extras_dim 14
+    from _util import synthetic_map
+
+    run_pair([synthetic_map(64, 64, 8, 16, seed=5)], None, 64, 30, check_every=3, pbrs=dict(), seed=37)
 
 
 def test_supplied_actions_with_invalid_ones():

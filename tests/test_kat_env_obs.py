@@ -373,3 +373,104 @@ def test_move_end_game(api):  # [C] test_move_end_game
     assert not env.done
     step = env.step([A.NORTH])
     assert step.done and env.done
+
+
+# ----------------------------------------------------------------------------- LaserSubgoal extras / PBRS
+PBRS_MAP = "S0 .  .\n.  . L0W\nX  .  ."
+TWO_LASERS = "S0  S1 X  X\n.   .  . L0W\n.   .  . L1W"
+
+
+def test_pbrs_reset_between_two_episodes(api):  # [E]
+    A = api.Action
+    actions = [[A.SOUTH], [A.EAST], [A.SOUTH], [A.WEST]]
+    expected = [1.0, 0.0, 0.0, 2.0]  # SHAPED_REWARD, 0, 0, REWARD_EXIT + REWARD_DONE
+    env = api.LLE(PBRS_MAP, pbrs=dict(reward_value=1.0, gamma=1.0))
+    for _ in range(5):
+        env.reset()
+        for action, reward in zip(actions, expected):
+            assert env.step(action).reward.tolist() == [reward]
+
+
+def test_pbrs_not_all_lasers(api):  # [E] .pbrs(lasers_to_reward=[(1, 2)])
+    text = "S0 .  .\n.  . L0W\n.  . L0W\nX  .  ."
+    world = api.World(text)
+    idx = [tuple(s.pos) for s in world.laser_sources].index((1, 2))
+    env = api.LLE(text, pbrs=dict(lasers_to_reward=[idx]))
+    env.reset()
+    assert env.extras().shape == (1, 1)
+
+
+def _extras_one_agent(env):
+    env.reset()
+    extras = env.extras()
+    assert extras.shape == (1, 1) and extras.dtype == np.float32
+    assert extras[0][0] == 0.0
+
+
+@pytest.mark.parametrize("kw", [dict(extras="laser_subgoal"), dict(pbrs=dict(with_extras=True))], ids=["extras", "pbrs"])
+def test_subgoal_extras_one_laser(api, kw):  # [O] test_subgoal_extras_one_laser / test_pbrs_subgoals_extras_one_laser
+    env = api.LLE("S0  X\n.  L0W", **kw)
+    _extras_one_agent(env)
+    env.reset()
+    _extras_one_agent(env)
+
+
+def _extras_two_agents(env, A):  # [O] _perform_tests_two_agents
+    env.reset()
+    extras = env.extras()
+    assert extras.shape == (2, 2) and np.all(extras == 0.0)
+    step = env.step([A.SOUTH, A.STAY])
+    assert step.extras.shape == (2, 2)
+    assert step.extras[0].sum() == 1.0 and step.extras[1].sum() == 0.0
+    step = env.step([A.NORTH, A.STAY])
+    assert step.extras[0].sum() == 1.0 and step.extras[1].sum() == 0.0
+    # even when an agent dies, the subgoal is reached
+    step = env.step([A.STAY, A.SOUTH])
+    assert step.done
+    assert step.extras[0].sum() == 1.0 and step.extras[1].sum() == 1.0
+
+
+@pytest.mark.parametrize("kw", [dict(extras="laser_subgoal"), dict(pbrs=dict(with_extras=True))], ids=["extras", "pbrs"])
+def test_subgoal_extras_two_lasers_two_agents(api, kw):  # [O]
+    env = api.LLE(TWO_LASERS, **kw)
+    _extras_two_agents(env, api.Action)
+    env.reset()
+    _extras_two_agents(env, api.Action)
+
+
+def test_pbrs_single_objective(api):  # [S] test_pbrs_single_objective / test_pbrs_with_lle
+    A = api.Action
+    env = api.LLE(PBRS_MAP, pbrs=dict(gamma=0.99, reward_value=0.5))
+    env.reset()
+    step = env.step([A.EAST])  # no base reward; the potential is unchanged
+    assert step.reward.dtype == np.float32 and step.reward.shape == (1,)
+    assert step.reward[0] == np.float32(0.5 * 0.99 - 0.5)
+    step = env.step([A.SOUTH])  # into the laser: the potential drops to 0
+    assert step.reward[0] == np.float32(0.5 * 0.99 - 0)
+    step = env.step([A.SOUTH])
+    assert step.reward[0] == 0.0
+
+
+def test_pbrs_multi_objective(api):  # [S]
+    A = api.Action
+    env = api.LLE(PBRS_MAP, multi_objective=True, pbrs=dict(gamma=0.99, reward_value=0.5))
+    env.reset()
+    step = env.step([A.EAST])
+    assert step.reward.shape == (5,)
+    assert np.allclose(step.reward, np.array([0.0] * 4 + [0.99 * 0.5 - 0.5], dtype=np.float32))
+    step = env.step([A.SOUTH])
+    assert np.allclose(step.reward, np.array([0.0] * 4 + [0.5 * 0.99], dtype=np.float32))
+    step = env.step([A.SOUTH])
+    assert step.reward[-1] == 0.0
+
+
+def test_pbrs_builder_order():  # [S] test_pbrs_raises_value_error (host-side builder logic, no device needed)
+    import lle_b200
+
+    lle_b200.from_str(PBRS_MAP).multi_objective().pbrs()
+    with pytest.raises(ValueError):
+        lle_b200.from_str(PBRS_MAP).pbrs().multi_objective()
+    with pytest.raises(ValueError):
+        lle_b200.from_str(PBRS_MAP).pbrs(lasers_to_reward=[(0, 0)])
+    with pytest.raises(ValueError):
+        lle_b200.from_str(PBRS_MAP).add_extras("nope")
