@@ -215,24 +215,53 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     vec.reset()
     vec.step_count = 10_000_000
-    reward_h = torch.empty((n_envs, R), dtype=torch.float32).pin_memory()
-    done_h = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+    D = max(1, min(4, args.e2e_depth))
+    reward_h = [torch.empty((n_envs, R), dtype=torch.float32).pin_memory() for _ in range(D)]
+    done_h = [torch.empty((n_envs,), dtype=torch.uint8).pin_memory() for _ in range(D)]
+
+    def e2e_sync() -> float:
+        """lle_vec_step_host: H2D, step, D2H, stream sync — one call per step, nothing overlapped."""
+        vec.reset()
+        vec.step_count = 10_000_000
+        barrier()
+        t0 = time.perf_counter()
+        n_done = 0
+        for s in range(Ke):
+            vec.step_host(rec[s], reward_h[0], done_h[0])
+            n_done += int(done_h[0][0])  # the host consumes the result
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    def e2e_pipelined() -> float:
+        """lle_vec_pipeline_submit / _wait with D steps in flight: every step still takes its actions from pinned host
+        memory and lands its reward + done in pinned host memory; the copies overlap the neighbouring steps' kernels."""
+        vec.reset()
+        vec.step_count = 10_000_000
+        barrier()
+        t0 = time.perf_counter()
+        n_done = 0
+        for s in range(Ke):
+            if s >= D:
+                vec.wait_host()
+                n_done += int(done_h[(s - D) % D][0])  # the host consumes the result of step s - D
+            vec.submit_host(rec[s], reward_h[s % D], done_h[s % D])
+        for s in range(max(Ke - D, 0), Ke):
+            vec.wait_host()
+            n_done += int(done_h[s % D][0])
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    def reduce_max(x: float) -> float:
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     for s in range(min(3, Ke)):
-        vec.step_host(rec[s], reward_h, done_h)
-    vec.reset()
-    vec.step_count = 10_000_000
-    barrier()
-    t0 = time.perf_counter()
-    n_done = 0
-    for s in range(Ke):
-        vec.step_host(rec[s], reward_h, done_h)
-        n_done += int(done_h[0])  # the host consumes the result
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world_size * n_envs * Ke / float(te.item())
+        vec.step_host(rec[s], reward_h[0], done_h[0])
+    e2e_pipelined()  # warm-up (creates the pipeline's streams and ring)
+    e2e_sync_value = world_size * n_envs * Ke / reduce_max(e2e_sync())
+    e2e_value = world_size * n_envs * Ke / reduce_max(e2e_pipelined())
     assert int(vec.err.sum()) == 0, "replayed actions must be valid"
 
     # end-of-run stats reduction: the only collective on this path (NCCL all-reduce of a few counters)
@@ -260,8 +289,11 @@ def run_ours(args) -> None:
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A, "d2h_bytes_per_step": n_envs * (4 * R + 1),
-                    "steps": Ke, "note": "lle_vec_step_host: pinned host actions -> H2D -> fused step -> D2H reward+done -> stream sync, "
-                                         "every step; observations stay in HBM (zero-copy DLPack hand-off)"},
+                    "steps": Ke, "pipeline_depth": D, "sync_value": e2e_sync_value,
+                    "note": f"lle_vec_pipeline_submit/_wait, {D} steps in flight: every step copies its actions from pinned host memory "
+                            "(H2D), runs the fused step and copies reward+done to pinned host memory (D2H), all inside the timed "
+                            "region; the host reads each step's result. sync_value = lle_vec_step_host (same copies, stream sync "
+                            "after every step, nothing overlapped). Observations stay in HBM (zero-copy DLPack hand-off)"},
             "gpu_launches": launches,
             "stats_allreduce": {"done_last_step": int(stats[0]), "reward_last_step": int(stats[1]), "envs_total": int(stats[2])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -285,7 +317,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=128)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=512)
+    ap.add_argument("--e2e-steps", type=int, default=2048)
+    ap.add_argument("--e2e-depth", type=int, default=2, help="steps in flight in the pipelined end-to-end arm (1..4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -190,6 +190,18 @@ LLE_API int lle_vec_rollout(lle_vec* vec, int32_t n_steps, void* cuda_stream);
  * stream.  The observation stays resident in HBM (zero-copy DLPack hand-off to the policy). */
 LLE_API int lle_vec_step_host(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* cuda_stream);
 
+/* Pipelined host stepping: the same step as lle_vec_step_host without the per-step stream synchronisation.
+ * lle_vec_pipeline_submit enqueues (1) the copy of `actions_host` (pinned i8[N,A]; NULL = device sampling) on a copy
+ * stream, (2) the fused step on the vec's own compute stream, which waits for the actions inside the kernel, and (3) the
+ * copy of reward / done (pinned f32[N,reward_dim] / u8[N]) to the host on a third stream, and returns at once.
+ * lle_vec_pipeline_wait blocks until the OLDEST submitted step's results are in its host buffers.  Up to 4 steps may be
+ * outstanding; with two or more, the copies of one step overlap the kernels of its neighbours and consecutive step
+ * kernels stay back to back (programmatic dependent launch), so a host-driven loop runs at the device rate.
+ * The first submit after the pipeline was empty is ordered after the work already in `after_stream`; no other call
+ * on the vec is allowed until the pipeline has been drained.  Device buffers (lle_vec_get_buffers) are updated as usual. */
+LLE_API int lle_vec_pipeline_submit(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream);
+LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
+
 /* World::set_state / LLE.set_state (world.rs:515-597, env.py:208-216) for every env.
  *   pos_dev i32[N,A,2], gems_dev u8[N,G], alive_dev u8[N,A] (device).  Per-env failures are reported in err. */
 LLE_API int lle_vec_set_state(lle_vec* vec, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* cuda_stream);

@@ -1,5 +1,6 @@
 // lle_b200 — host side of the C ABI (include/lle_b200.h): map handles, device buffers, launch
 // configuration and the kernel launches.  The kernel itself lives in vec_kernels.cuh.
+#include <cuda.h>  // types of the stream memory operations only; the entry points are resolved at run time
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -76,6 +77,16 @@ struct lle_vec {
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t timing_launches0 = 0;
+    // pipelined host stepping (lle_vec_pipeline_submit / _wait): three streams, a ring of staging slots
+    static constexpr int kPipeSlots = 4;
+    bool pipe_ready = false;
+    cudaStream_t s_in = nullptr, s_main = nullptr, s_out = nullptr, last_stream = nullptr;
+    cudaEvent_t ev_user = nullptr, ev_out[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
+    int8_t* d_stage[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
+    float* d_reward_ring[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t* d_done_ring[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* d_pipe_flags = nullptr;  // [0] actions of submit n have landed, [1] submit n has retired
+    uint64_t pipe_submitted = 0, pipe_completed = 0;
 };
 
 namespace {
@@ -95,7 +106,7 @@ cudaError_t launch_mode(lle_vec* v, const KParams& p, cudaStream_t s) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     // only a step that directly follows a step may overlap it: the epoch flags order them ticket by ticket
-    attr[0].val.programmaticStreamSerializationAllowed = (v->pdl && MODE == MODE_STEP && v->last_was_step) ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (v->pdl && MODE == MODE_STEP && v->last_was_step && v->last_stream == s) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, true>, p);
@@ -111,12 +122,33 @@ cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
             e = launch_mode<MODE_STEP>(v, p, s);
             v->seq += (uint32_t)p.n_steps;
             v->last_was_step = true;
+            v->last_stream = s;
             return e;
         case MODE_RESET: e = launch_mode<MODE_RESET>(v, p, s); break;
         default: e = launch_mode<MODE_SET_STATE>(v, p, s); break;
     }
     v->last_was_step = false;
+    v->last_stream = s;
     return e;
+}
+
+// Stream memory operations of the driver API, resolved through the runtime so that the library carries no link-time
+// dependency on libcuda (it must load on a machine without a driver for the build / ABI checks).
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValue32Fn g_write_value32 = nullptr, g_wait_value32 = nullptr;
+cudaError_t resolve_memops() {
+    if (g_write_value32 && g_wait_value32) return cudaSuccess;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    g_write_value32 = (StreamValue32Fn)fn;
+    e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    g_wait_value32 = (StreamValue32Fn)fn;
+    return cudaSuccess;
 }
 
 template <int MODE, bool FAST>
@@ -277,6 +309,15 @@ int lle_vec_destroy(lle_vec* v) {
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
     cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline); cudaFree(v->d_extras);
+    for (int k = 0; k < lle_vec::kPipeSlots; ++k) {
+        cudaFree(v->d_stage[k]); cudaFree(v->d_reward_ring[k]); cudaFree(v->d_done_ring[k]);
+        if (v->ev_out[k]) cudaEventDestroy(v->ev_out[k]);
+    }
+    cudaFree(v->d_pipe_flags);
+    if (v->ev_user) cudaEventDestroy(v->ev_user);
+    if (v->s_in) cudaStreamDestroy(v->s_in);
+    if (v->s_main) cudaStreamDestroy(v->s_main);
+    if (v->s_out) cudaStreamDestroy(v->s_out);
     if (v->ev0) cudaEventDestroy(v->ev0);
     if (v->ev1) cudaEventDestroy(v->ev1);
     delete v;
@@ -456,6 +497,7 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
 
 int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_RESET;
@@ -467,6 +509,7 @@ int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
 
 int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_STEP;
@@ -479,6 +522,7 @@ int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
 
 int lle_vec_rollout(lle_vec* v, int32_t n_steps, void* stream) {
     if (!v || n_steps < 1) return fail(LLE_INVALID_ARGUMENT, "bad argument");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_STEP;
@@ -507,8 +551,75 @@ int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host
     return LLE_OK;
 }
 
+int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (v->pipe_submitted - v->pipe_completed >= (uint64_t)lle_vec::kPipeSlots)
+        return fail(LLE_INVALID_ARGUMENT, "pipeline full: call lle_vec_pipeline_wait before submitting another step");
+    LLE_CUDA(cudaSetDevice(v->device));
+    if (!v->pipe_ready) {
+        LLE_CUDA(resolve_memops());
+        LLE_CUDA(cudaStreamCreateWithFlags(&v->s_in, cudaStreamNonBlocking));
+        LLE_CUDA(cudaStreamCreateWithFlags(&v->s_main, cudaStreamNonBlocking));
+        LLE_CUDA(cudaStreamCreateWithFlags(&v->s_out, cudaStreamNonBlocking));
+        LLE_CUDA(cudaEventCreateWithFlags(&v->ev_user, cudaEventDisableTiming));
+        for (int k = 0; k < lle_vec::kPipeSlots; ++k) {
+            LLE_CUDA(cudaEventCreateWithFlags(&v->ev_out[k], cudaEventDisableTiming));
+            LLE_CUDA(dalloc(&v->d_stage[k], (size_t)v->A * v->N_pad));
+            LLE_CUDA(dalloc(&v->d_reward_ring[k], (size_t)v->R * v->N_pad));
+            LLE_CUDA(dalloc(&v->d_done_ring[k], (size_t)v->N_pad));
+        }
+        LLE_CUDA(dalloc(&v->d_pipe_flags, 2));
+        LLE_CUDA(cudaDeviceSynchronize());
+        v->pipe_ready = true;
+    }
+    if (v->pipe_submitted == v->pipe_completed) {  // pipeline empty: order it after the caller's stream
+        LLE_CUDA(cudaEventRecord(v->ev_user, (cudaStream_t)after_stream));
+        LLE_CUDA(cudaStreamWaitEvent(v->s_main, v->ev_user, 0));
+    }
+    const uint32_t n = (uint32_t)(++v->pipe_submitted);
+    const int slot = (int)((v->pipe_submitted - 1) % lle_vec::kPipeSlots);
+    KParams p = base_params(v);
+    p.mode = MODE_STEP;
+    if (actions_host) {
+        LLE_CUDA(cudaMemcpyAsync(v->d_stage[slot], actions_host, (size_t)v->N * v->A, cudaMemcpyHostToDevice, v->s_in));
+        if (g_write_value32((CUstream)v->s_in, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 0), n, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+            return fail(LLE_CUDA_ERROR, "cuStreamWriteValue32 failed");
+        p.actions_in = v->d_stage[slot];
+        p.in_flag = v->d_pipe_flags + 0;
+        p.in_need = n;
+    }
+    p.out_flag = v->d_pipe_flags + 1;
+    p.out_value = n;
+    p.reward2 = v->d_reward_ring[slot];
+    p.done2 = v->d_done_ring[slot];
+    LLE_CUDA(launch(v, p, v->s_main));
+    v->launches++;
+    v->t++;
+    if (g_wait_value32((CUstream)v->s_out, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 1), n, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return fail(LLE_CUDA_ERROR, "cuStreamWaitValue32 failed");
+    if (reward_host) LLE_CUDA(cudaMemcpyAsync(reward_host, v->d_reward_ring[slot], (size_t)v->N * v->R * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
+    if (done_host) LLE_CUDA(cudaMemcpyAsync(done_host, v->d_done_ring[slot], (size_t)v->N, cudaMemcpyDeviceToHost, v->s_out));
+    LLE_CUDA(cudaEventRecord(v->ev_out[slot], v->s_out));
+    return LLE_OK;
+}
+
+int lle_vec_pipeline_wait(lle_vec* v, int32_t* outstanding) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (v->pipe_submitted == v->pipe_completed) {
+        if (outstanding) *outstanding = 0;
+        return fail(LLE_INVALID_ARGUMENT, "pipeline empty: nothing to wait for");
+    }
+    LLE_CUDA(cudaSetDevice(v->device));
+    const int slot = (int)(v->pipe_completed % lle_vec::kPipeSlots);
+    LLE_CUDA(cudaEventSynchronize(v->ev_out[slot]));
+    v->pipe_completed++;
+    if (outstanding) *outstanding = (int32_t)(v->pipe_submitted - v->pipe_completed);
+    return LLE_OK;
+}
+
 int lle_vec_set_state(lle_vec* v, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* stream) {
     if (!v || !pos_dev || !alive_dev || (v->G > 0 && !gems_dev)) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_SET_STATE;

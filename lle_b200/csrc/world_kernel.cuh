@@ -94,6 +94,14 @@ struct KParams {
     uint64_t extras_set, pbrs_set;  // bit b: source b is tracked
     double pbrs_gamma, pbrs_value;
     int8_t extras_beam[64];         // source index of extras column j
+    // Pipelined host stepping (lle_vec_pipeline_submit): the actions of this step arrive through a copy engine on
+    // another stream, which then publishes `in_need` to *in_flag (stream memory op); the reward / done of this step are
+    // duplicated into a ring slot that a third stream copies to the host once *out_flag >= out_value.
+    const uint32_t* in_flag;
+    uint32_t in_need, out_value;
+    uint32_t* out_flag;
+    float* reward2;
+    uint8_t* done2;
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -602,6 +610,11 @@ __device__ __forceinline__ void ticket_release(uint32_t* flag, uint32_t seq) {
     __threadfence();
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
 }
+__device__ __forceinline__ bool sys_flag_ready(const uint32_t* flag, uint32_t need) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return (int32_t)(v - need) >= 0;
+}
 __device__ __forceinline__ bool ticket_ready(const uint32_t* flag, uint32_t need) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
@@ -682,6 +695,13 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     // the epoch flags, so its first tickets start while the previous step's last ones are still draining.
     if constexpr (MODE != MODE_STEP) asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    if constexpr (MODE == MODE_STEP) {
+        if (p.in_flag) {  // host-supplied actions still in flight on the copy stream (independent of this stream: no cycle)
+            if (lane == 0)
+                while (!sys_flag_ready(p.in_flag, p.in_need)) __nanosleep(100);
+            __syncwarp();
+        }
+    }
     const uint32_t warp_global = blockIdx.x * kWarps + warp;
     const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;  // (step, ticket) pairs, handed out in order
     uint64_t t_first = 0, t_last = 0;
@@ -845,9 +865,11 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         else v = (float)shaped;  // fifth component of MultiObjective + PBRS (np.concat, :153)
                     }
                     p.reward[env * p.R + r] = v;
+                    if (p.reward2) p.reward2[env * p.R + r] = v;
                 }
                 if (gl == 0) {
                     p.done[env] = (uint8_t)w.done;
+                    if (p.done2) p.done2[env] = (uint8_t)w.done;
                     p.err[env] = (uint8_t)err;
                 }
                 if (gl < A) {
@@ -1082,6 +1104,12 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             p.sched[0] = 0;
             p.sched[1] = 0;
             __threadfence();
+            if (p.out_flag) {
+                // every warp fenced its writes before its increment above; publish the launch to the copy stream that
+                // waits on the flag (max: an overlapped later launch may retire first, and implies this one's tickets)
+                __threadfence_system();
+                atomicMax_system(p.out_flag, p.out_value);
+            }
         }
     }
 }

@@ -221,6 +221,24 @@ class VecWorld:
             ptr = t.data_ptr()
         check(lib().lle_vec_step_host(self._h, ptr, reward_out.data_ptr(), done_out.data_ptr(), _stream_ptr(self.device)))
 
+    def submit_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor):
+        """Pipelined host-facing step (lle_vec_pipeline_submit): enqueue H2D actions -> step -> D2H reward/done on the vec's
+        own streams and return at once.  Buffers should be pinned and must stay alive until the matching `wait_host()`."""
+        ptr = None
+        if actions is not None:
+            t = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(actions)
+            assert t.dtype == torch.int8 and t.is_contiguous() and not t.is_cuda
+            ptr = t.data_ptr()
+        check(lib().lle_vec_pipeline_submit(self._h, ptr, reward_out.data_ptr() if reward_out is not None else None,
+                                            done_out.data_ptr() if done_out is not None else None, _stream_ptr(self.device)))
+
+    def wait_host(self) -> int:
+        """Block until the oldest submitted step's reward / done are in their host buffers; returns the number of steps
+        still outstanding (lle_vec_pipeline_wait)."""
+        left = C.c_int32(0)
+        check(lib().lle_vec_pipeline_wait(self._h, C.byref(left)))
+        return left.value
+
     def set_state(self, positions: torch.Tensor, gems_collected: torch.Tensor, agents_alive: torch.Tensor):
         pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
         gems = gems_collected.to(device=self.device, dtype=torch.uint8).contiguous()

@@ -123,6 +123,52 @@ def test_supplied_actions_with_invalid_ones():
     assert n_bad > 100
 
 
+def test_pipelined_host_stepping():
+    """lle_vec_pipeline_submit / _wait: host actions in, reward + done out, up to 4 steps in flight; every step's host
+    results and the final device buffers equal the oracle's."""
+    for depth, n, level in ((1, 100, 5), (2, 1000, 6), (4, 333, 6)):
+        ora, dev = make_pair([level_text(level)], None, n, seed=40 + depth)
+        vec = dev.vec
+        steps = 60
+        slots = [(torch.empty((n, ora.A), dtype=torch.int8).pin_memory(), torch.empty((n, ora.R), dtype=torch.float32).pin_memory(),
+                  torch.empty((n,), dtype=torch.uint8).pin_memory()) for _ in range(depth)]
+        expect = []
+        inflight = []
+
+        def retire():
+            k = inflight.pop(0)
+            vec.wait_host()
+            _, rew, done = slots[k % depth]
+            assert np.array_equal(rew.numpy(), expect[k][0]), f"depth {depth}: reward of step {k}"
+            assert np.array_equal(done.numpy(), expect[k][1]), f"depth {depth}: done of step {k}"
+
+        for t in range(steps):
+            if len(inflight) == depth:
+                retire()
+            ora.step(None)  # the oracle samples; the device replays the recorded actions from the host
+            expect.append((np.array(ora.reward), np.array(ora.done)))
+            act, rew, done = slots[t % depth]
+            act.copy_(torch.from_numpy(np.array(ora.actions)))
+            vec.submit_host(act, rew, done)
+            inflight.append(t)
+        while inflight:
+            retire()
+        vec.step_count = ora.t
+        assert_same(dev, ora, dev.pull(), f"pipelined depth {depth}")
+        # device sampling through the pipeline, and back to plain stepping afterwards
+        ora.step(None)
+        vec.submit_host(None, slots[0][1], slots[0][2])
+        assert vec.wait_host() == 0
+        assert np.array_equal(slots[0][1].numpy(), ora.reward)
+        ora.step(None)
+        vec.step(None)
+        assert_same(dev, ora, dev.pull(), f"after the pipeline, depth {depth}")
+    with pytest.raises(ValueError):
+        vec.submit_host(None, slots[0][1], slots[0][2])
+        vec.step(None)  # not drained
+    vec.wait_host()
+
+
 def test_many_agents_and_small_maps():
     rows = [" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)]
     run_pair(["\n".join(rows)], None, 64, 60, seed=2)
