@@ -11,6 +11,7 @@ ap.add_argument("--steps", type=int, default=2000)
 ap.add_argument("--no-obs", action="store_true")
 ap.add_argument("--map", type=str, default=None)
 ap.add_argument("--rollout", type=int, default=0)
+ap.add_argument("--sync", action="store_true", help="synchronise after every step (isolated launches)")
 args = ap.parse_args()
 moe = None
 if args.map == "generated":
@@ -38,6 +39,8 @@ if args.rollout:
 else:
     for _ in range(args.steps):
         vec.step(None)
+        if args.sync:
+            vec.synchronize()
     ms, n = vec.timing_end()
 us = ms * 1e3 / n
 obs_bytes = vec.n_channels * vec.height * vec.width * 4 * args.envs
