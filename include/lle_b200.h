@@ -129,7 +129,14 @@ typedef struct {
     int32_t n_pbrs;
     int32_t pbrs_src[64];
     double pbrs_gamma, pbrs_reward_value;
+    /* Observation type (ObservationType.get_observation_generator, python/lle/observations.py:66-97):
+     *   LLE_OBS_LAYERED      obs_param = padding_size: "layered", "flattened" (a view), "layered-padded[-1|-2|-3]"  (:196-293)
+     *   LLE_OBS_PARTIAL      obs_param = odd square size: "partial3x3" / "partial5x5" / "partial7x7"               (:296-369)
+     *   LLE_OBS_PERSPECTIVE  "perspective" (AgentZeroPerspective)                                                 (:372-395)
+     *   LLE_OBS_STATE        obs_param 0 "state", 1 "normalized-state"                                            (:141-158) */
+    int32_t obs_type, obs_param;
 } lle_vec_options;
+enum { LLE_OBS_LAYERED = 0, LLE_OBS_PARTIAL = 1, LLE_OBS_PERSPECTIVE = 2, LLE_OBS_STATE = 3 };
 LLE_API void lle_vec_default_options(lle_vec_options* opts);
 
 /* All maps must share (height, width, n_agents, n_gems).  map_of_env may be NULL (every env uses maps[0]). */
@@ -138,9 +145,12 @@ LLE_API int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int
 LLE_API int lle_vec_destroy(lle_vec* vec);
 
 /* Device pointers of the per-step outputs (valid until lle_vec_destroy).  Layouts, C-contiguous:
- *   obs      f32 [N, obs_stride]   first C*H*W floats of a row = LayeredPadded.observe()[0] (observations.py:254-266);
- *                                  obs_stride = C*H*W rounded up to 4 floats; the agent dimension of the
- *                                  reference's (A,C,H,W) result is a stride-0 repeat of this block (np.tile).
+ *   obs      f32 [N, obs_stride]   one block per env (obs_stride = block length rounded up to 4 floats), by obs_type:
+ *                                    layered      (C,H,W) = LayeredPadded.observe()[0] (observations.py:254-266), C = 2(A+padding)+4;
+ *                                                 the reference's (A+padding,C,H,W) np.tile is a stride-0 repeat of it
+ *                                    partial      (A, 2A+3, size, size): every agent's own window (:331-350)
+ *                                    perspective  (A, C, H, W): every agent's own permuted copy (:381-395)
+ *                                    state        (3A+G,), obs_stride = 3A+G; repeated per agent by the reference (:155-158)
  *   state    f32 [N, 3A+G]         PyWorldState::as_array (pyworld_state.rs:79-101)
  *   avail    u8  [N, A, 5]         LLE.available_actions (env.py:146-163), indexed by Action value
  *   reward   f32 [N, reward_dim]   reward_strategy.py:58-75 / :90-109
@@ -167,6 +177,12 @@ typedef struct {
     float* extras;
     int32_t extras_dim;
     int32_t pad;
+    int32_t obs_type, obs_param;
+    int32_t obs_view_agents;        /* > 0: the agent dimension is a stride-0 repeat of the block (np.tile); 0: materialised */
+    int32_t obs_c, obs_h, obs_w;    /* one agent's observation: (obs_c, obs_h, obs_w); state: (obs_c,) */
+    int32_t obs_invalid;            /* some map's laser colour indexes past the last channel of this observation type: the
+                                       reference raises IndexError when it builds / runs the generator */
+    int32_t pad2;
 } lle_vec_buffers;
 LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 

@@ -33,14 +33,15 @@ class VecOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("device", "reward_dim", "walkable_lasers", "auto_reset", "lle_semantics", "write_obs")] + [
         ("seed", C.c_uint64), ("env_id_base", C.c_uint64), ("n_extras", C.c_int32), ("extras_src", C.c_int32 * 64),
         ("pbrs", C.c_int32), ("n_pbrs", C.c_int32), ("pbrs_src", C.c_int32 * 64), ("pbrs_gamma", C.c_double),
-        ("pbrs_reward_value", C.c_double)]
+        ("pbrs_reward_value", C.c_double), ("obs_type", C.c_int32), ("obs_param", C.c_int32)]
 
 
 class VecBuffers(C.Structure):
     _fields_ = [("n_envs", C.c_int64)] + [(n, C.c_int32) for n in ("n_agents", "n_gems", "n_channels", "height", "width",
                                                                    "reward_dim", "state_dim", "n_beams_max")] + [
         ("obs_stride", C.c_int64), ("obs", C.c_void_p), ("state", C.c_void_p), ("avail", C.c_void_p), ("reward", C.c_void_p),
-        ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p), ("record_bytes", C.c_int64), ("extras", C.c_void_p), ("extras_dim", C.c_int32), ("pad", C.c_int32)]
+        ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p), ("record_bytes", C.c_int64), ("extras", C.c_void_p), ("extras_dim", C.c_int32), ("pad", C.c_int32)] + [
+        (n, C.c_int32) for n in ("obs_type", "obs_param", "obs_view_agents", "obs_c", "obs_h", "obs_w", "obs_invalid", "pad2")]
 
 
 _lib = None

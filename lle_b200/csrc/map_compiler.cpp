@@ -35,7 +35,11 @@ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 }  // namespace
 
-CompiledMap compile_map(const std::string& text) {
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
+    if (spec.kind < LLE_OBS_LAYERED || spec.kind > LLE_OBS_STATE) throw MapError(LLE_INVALID_ARGUMENT, "unknown observation kind");
+    if (spec.kind == LLE_OBS_LAYERED && (spec.param < 0 || spec.param > 64)) throw MapError(LLE_INVALID_ARGUMENT, "padding_size out of range");
+    if (spec.kind == LLE_OBS_PARTIAL && (spec.param < 1 || spec.param % 2 != 1 || spec.param > 31))
+        throw MapError(LLE_INVALID_ARGUMENT, "Can only use odd numbers for the square size");  // observations.py:299
     CompiledMap cm;
     cm.text = text;
 
@@ -177,9 +181,11 @@ CompiledMap compile_map(const std::string& text) {
         cm.max_beam_len = std::max(cm.max_beam_len, s.len);
     }
     cm.H = H; cm.W = W; cm.A = A; cm.G = G; cm.NB = NB;
-    const int C = 2 * A + 4;  // observations.py:205-211
+    // channel layout (observations.py:199-211): the agent count of the layout includes the padding budget
+    const int Ap = A + (spec.kind == LLE_OBS_LAYERED ? spec.param : 0);
+    const int C = 2 * Ap + 4;
     cm.C = C;
-    const int LASER_0 = A, WALL = 2 * A, VOID = WALL + 1, GEM = WALL + 2, EXIT = WALL + 3, HW = H * W;
+    const int LASER_0 = Ap, WALL = 2 * Ap, VOID = WALL + 1, GEM = WALL + 2, EXIT = WALL + 3, HW = H * W;
 
     // ---- lasers listing: the outermost laser of a cell and the one directly under it (world.rs:159-172)
     std::vector<uint64_t> vis(NB, 0);
@@ -217,6 +223,57 @@ CompiledMap compile_map(const std::string& text) {
         uint32_t idx = (uint32_t)(GEM * HW + cm.gems[g].i * W + cm.gems[g].j);
         patch.push_back(LlePatch{idx, 0xFF, (uint8_t)g, (int8_t)stat[idx], 0});
     }
+    std::vector<LleAgentPlane> planes;
+    for (int a = 0; a < A; ++a) planes.push_back(LleAgentPlane{(uint32_t)(a * HW), (uint32_t)a});
+    int obs_floats = C * HW, view_agents = Ap, obs_c = C, obs_h = H, obs_w = W;
+    if (spec.kind == LLE_OBS_PERSPECTIVE) {
+        // AgentZeroPerspective (observations.py:381-395): copy n of the layered block with the agent planes 0 <-> n and
+        // the laser planes 0 <-> n exchanged.  The block of one env is the A copies back to back, so the static plane,
+        // the patch table and the agent-plane table are replicated per copy with the permuted channel.
+        auto perm = [&](int n, int ch) {  // destination channel of source channel `ch` in copy n
+            if (ch == 0) return n;
+            if (ch == n) return 0;
+            if (ch == LASER_0) return LASER_0 + n;
+            if (ch == LASER_0 + n) return LASER_0;
+            return ch;
+        };
+        std::vector<float> all((size_t)A * C * HW, 0.0f);
+        std::vector<LlePatch> all_patch;
+        planes.clear();
+        for (int n = 0; n < A; ++n) {
+            for (int ch = 0; ch < C; ++ch)
+                std::memcpy(&all[((size_t)n * C + perm(n, ch)) * HW], &stat[(size_t)ch * HW], (size_t)HW * sizeof(float));
+            for (const auto& pe : patch) {
+                LlePatch q = pe;
+                q.idx = (uint32_t)(((size_t)n * C + perm(n, (int)(pe.idx / HW))) * HW + pe.idx % HW);
+                all_patch.push_back(q);
+            }
+            for (int a = 0; a < A; ++a) planes.push_back(LleAgentPlane{(uint32_t)(((size_t)n * C + perm(n, a)) * HW), (uint32_t)a});
+        }
+        stat.swap(all);
+        patch.swap(all_patch);
+        obs_floats = A * C * HW;
+        view_agents = 0;
+    } else if (spec.kind == LLE_OBS_PARTIAL) {
+        // PartialGenerator (observations.py:296-369): rendered cell by cell on the device; nothing static
+        const int Cp = 2 * A + 3;
+        for (auto& s : cm.sources)
+            if (A + 1 + s.colour >= Cp) obs_invalid = true;  // obs[a, LASER_0 + agent_id]: numpy IndexError
+        stat.assign(4, 0.0f);
+        patch.clear();
+        planes.clear();
+        obs_floats = A * Cp * spec.param * spec.param;
+        view_agents = 0;
+        obs_c = Cp; obs_h = obs_w = spec.param;
+    } else if (spec.kind == LLE_OBS_STATE) {
+        stat.assign(4, 0.0f);
+        patch.clear();
+        planes.clear();
+        obs_invalid = false;
+        obs_floats = 3 * A + G;
+        view_agents = A;
+        obs_c = obs_floats; obs_h = obs_w = 0;
+    }
     std::stable_sort(patch.begin(), patch.end(), [](const LlePatch& x, const LlePatch& y) { return x.idx < y.idx; });
 
     // ---- blob
@@ -224,8 +281,11 @@ CompiledMap compile_map(const std::string& text) {
     std::memset(&h, 0, sizeof h);
     h.H = H; h.W = W; h.A = A; h.G = G; h.NB = NB; h.C = C;
     h.n_patch = (int)patch.size();
-    h.obs_floats = C * HW;
+    h.obs_floats = obs_floats;
     h.obs_invalid = obs_invalid;
+    h.obs_kind = spec.kind; h.obs_param = spec.param; h.view_agents = view_agents;
+    h.obs_c = obs_c; h.obs_h = obs_h; h.obs_w = obs_w;
+    h.n_ap = (int)planes.size();
     size_t off = align16(sizeof(LleMapHeader));
     h.tiles_off = (uint32_t)off;   off = align16(off + tiles.size() * sizeof(uint16_t));
     h.cellinfo_off = (uint32_t)off;  off = align16(off + (size_t)HW * sizeof(uint32_t));
@@ -233,6 +293,7 @@ CompiledMap compile_map(const std::string& text) {
     h.beams_off = (uint32_t)off;   off = align16(off + (size_t)std::max(NB, 1) * sizeof(LleBeam));
     h.patch_off = (uint32_t)off;   off = align16(off + std::max<size_t>(patch.size(), 1) * sizeof(LlePatch));
     h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
+    h.ap_off = (uint32_t)off;      off = align16(off + std::max<size_t>(planes.size(), 1) * sizeof(LleAgentPlane));
     h.blob_bytes = (uint32_t)off;
     h.gem_toplevel = 0;
     for (int g = 0; g < G; ++g) {
@@ -274,6 +335,8 @@ CompiledMap compile_map(const std::string& text) {
                     if (ti >= 0 && tj >= 0 && ti < H && tj < W && (tiles[ti * W + tj] & 7u) != LLE_T_WALL) nbr |= 1u << act;
                 }
                 info[c] = (tiles[c] & 7u) | (nbr << 3) | ((uint32_t)(tiles[c] >> 8) << 8);
+                for (const auto& src : cm.sources)
+                    if (src.pos.i == i && src.pos.j == j) info[c] |= (1u << 7) | ((uint32_t)src.colour << 16);
                 for (int n = 0; n < 4; ++n) cb[c].e[n] = LLE_NO_BEAM;
                 const auto& lst = cell_beams[c];
                 if (lst.size() > 4) throw MapError(LLE_LIMIT_EXCEEDED, "more than four beams cross one cell");
@@ -291,6 +354,7 @@ CompiledMap compile_map(const std::string& text) {
     }
     if (!patch.empty()) std::memcpy(cm.blob.data() + h.patch_off, patch.data(), patch.size() * sizeof(LlePatch));
     std::memcpy(cm.blob.data() + h.static_off, stat.data(), stat.size() * sizeof(float));
+    if (!planes.empty()) std::memcpy(cm.blob.data() + h.ap_off, planes.data(), planes.size() * sizeof(LleAgentPlane));
     return cm;
 }
 

@@ -54,6 +54,13 @@ struct CompiledMap {
     const LleMapHeader& header() const { return *reinterpret_cast<const LleMapHeader*>(blob.data()); }
 };
 
-CompiledMap compile_map(const std::string& text);
+// Which observation the device tables are laid out for (static_map.h: LLE_OBS_*)
+struct ObsSpec {
+    int kind = LLE_OBS_LAYERED;
+    int param = 0;
+    bool operator==(const ObsSpec& o) const { return kind == o.kind && param == o.param; }
+};
+
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec = ObsSpec());
 
 }  // namespace lle

@@ -9,6 +9,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/lle_b200.h"
+
 #define LLE_MAX_AGENTS 32  // alive/arrived/slot are u32 masks
 #define LLE_MAX_BEAMS 64   // per map
 #define LLE_MAX_GEMS 64    // one u64 collected mask
@@ -43,9 +45,19 @@ struct LlePatch {
 };
 static_assert(sizeof(LlePatch) == 8, "LlePatch layout");
 
+// Observation kinds: LLE_OBS_* of include/lle_b200.h (ObservationType.get_observation_generator, observations.py:66-97)
+
+// Where agent `agent`'s one-hot cell goes in an env's observation block: float index base + i*W + j.
+// Layered: A entries (agent a -> plane a).  Perspective: A*A entries (copy n draws agent a in plane perm_n(a)).
+struct LleAgentPlane {
+    uint32_t base;
+    uint32_t agent;
+};
+
 // Per-cell lookup tables used by the step kernel (one load each instead of a scan over all beams):
 //   cellinfo[cell]  : bits 0-2 base tile kind | bits 3-6 walkable-neighbour mask indexed by Action value
-//                     (N, S, E, W: in bounds and neither Wall nor LaserSource, tile.rs:63-73) | bits 8-15 gem index
+//                     (N, S, E, W: in bounds and neither Wall nor LaserSource, tile.rs:63-73) | bit 7: the cell is a
+//                     laser source | bits 8-15 gem index | bits 16-23 colour of the source (bit 7 set)
 //   cellbeams[cell] : the (at most four: one per direction of travel) beams crossing the cell, inner first.
 //                     entry = b (0-5) | k<<6 (6-11) | colour<<12 (12-19) | len<<20 (20-26) | enabled<<27 | listed<<28
 //                     (listed: the laser tile is one of the two reported by World::lasers(), world.rs:159-172);
@@ -69,6 +81,11 @@ struct LleMapHeader {
     uint32_t blob_bytes;
     uint32_t obs_invalid;     // some LASER_0+colour >= C: the reference raises IndexError (observations.py:235)
     uint64_t gem_toplevel;    // bit g set <=> gem g is NOT wrapped by a laser (world.rs:265-275, :550-554)
+    int32_t obs_kind, obs_param;   // LLE_OBS_* and its parameter
+    int32_t view_agents;           // layered / state: agent copies of the stride-0 view (A + padding); else 0 (materialised)
+    int32_t obs_c, obs_h, obs_w;   // shape of ONE agent's observation (state: obs_c = length, obs_h = obs_w = 0)
+    int32_t n_ap;                  // entries of the agent-plane table
+    uint32_t ap_off;               // LleAgentPlane[n_ap]
     uint16_t start[LLE_MAX_AGENTS];   // packed position (i<<8 | j)
     uint16_t gem_pos[LLE_MAX_GEMS];   // packed position, gems_positions order (parser_v1.rs:149)
 };

@@ -45,6 +45,10 @@ struct lle_vec {
     int A = 0, G = 0, NBmax = 0, C = 0, H = 0, W = 0, S = 0, R = 1, max_beam_len = 0;
     LleStateLayout L;
     // device memory
+    std::vector<CompiledMap> own_maps;  // maps recompiled for a non-default observation type
+    bool render = true;
+    LleMapHeader hdr0;  // header of the first map (observation shape)
+    int obs_invalid = 0;
     std::vector<uint8_t*> d_blobs;
     const uint8_t** d_blob_table = nullptr;
     int32_t* d_map_of_env = nullptr;
@@ -192,7 +196,9 @@ KParams base_params(lle_vec* v) {
     p.events = v->d_events; p.actions = v->d_actions; p.err = v->d_err;
     p.seed = v->opts.seed; p.env_id_base = v->opts.env_id_base; p.t = v->t;
     p.auto_reset = v->opts.auto_reset; p.lle_semantics = v->opts.lle_semantics;
-    p.walkable = v->opts.walkable_lasers; p.write_obs = v->opts.write_obs;
+    p.walkable = v->opts.walkable_lasers; p.write_obs = v->render ? 1 : 0;
+    p.obs_kind = v->opts.obs_type; p.obs_param = v->opts.obs_param;
+    p.state_obs = (v->opts.write_obs && v->opts.obs_type == LLE_OBS_STATE) ? (v->opts.obs_param ? 2 : 1) : 0;
     p.Wd = v->Wd; p.group = v->group; p.E = v->E; p.n_chunks = v->n_chunks; p.chunk_floats = v->chunk_floats; p.tile_floats = v->tile_floats;
     p.n_buf = v->n_buf;
     p.warp_smem_bytes = v->warp_smem;
@@ -340,14 +346,29 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     auto v = std::unique_ptr<lle_vec, int (*)(lle_vec*)>(new lle_vec(), lle_vec_destroy);
     v->opts = *opts;
     v->device = opts->device;
-    const CompiledMap& m0 = maps[0]->cm;
+    // The caller's maps are compiled for the plain layered observation; other observation types get their own device
+    // tables (channel layout, static planes, patch and agent-plane tables) from the same map text.
+    const ObsSpec spec{opts->obs_type, opts->obs_param};
+    std::vector<const CompiledMap*> cms;
+    if (spec == ObsSpec()) {
+        for (int k = 0; k < n_maps; ++k) cms.push_back(&maps[k]->cm);
+    } else {
+        try {
+            for (int k = 0; k < n_maps; ++k) v->own_maps.push_back(compile_map(maps[k]->cm.text, spec));
+        } catch (const MapError& e) {
+            return fail(e.status, e.what());
+        }
+        for (auto& m : v->own_maps) cms.push_back(&m);
+    }
+    const CompiledMap& m0 = *cms[0];
     v->A = m0.A; v->G = m0.G; v->C = m0.C; v->H = m0.H; v->W = m0.W; v->R = opts->reward_dim;
     v->S = 3 * m0.A + m0.G;
     for (int k = 0; k < n_maps; ++k) {
-        const CompiledMap& m = maps[k]->cm;
+        const CompiledMap& m = *cms[k];
         if (m.A != v->A || m.G != v->G || m.H != v->H || m.W != v->W)
             return fail(LLE_INVALID_ARGUMENT, "all maps of a vec must share (height, width, n_agents, n_gems)");
         v->NBmax = std::max(v->NBmax, m.NB);
+        if (m.header().obs_invalid) v->obs_invalid = 1;
         v->max_beam_len = std::max(v->max_beam_len, m.max_beam_len);
     }
     if (map_of_env)
@@ -377,7 +398,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         if (opts->pbrs && opts->reward_dim == 4) v->R = 5;  // np.concat((reward, [potential_reward])) (reward_strategy.py:153)
     }
     v->L = lle_state_layout(v->A, v->G, v->NBmax, v->max_beam_len, v->JE > 0, opts->pbrs != 0);
-    v->obs_stride = ((int64_t)v->C * v->H * v->W + 3) / 4 * 4;
+    v->obs_stride = spec.kind == LLE_OBS_STATE ? (int64_t)v->S : ((int64_t)m0.header().obs_floats + 3) / 4 * 4;
+    v->render = opts->write_obs && spec.kind != LLE_OBS_STATE;  // whether the tile renderer runs
 
     LLE_CUDA(cudaSetDevice(v->device));
     cudaDeviceProp prop;
@@ -392,7 +414,11 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     const bool small_obs = v->obs_stride * 4 < 2048;  // tiny observations: the logic dominates, pack more worlds per pass
     v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", small_obs ? 1 : 4)));
     const int64_t stride = v->obs_stride;
-    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", small_obs ? 2048 : 1024), kTileMaxFloats = 6144;  // 4-8 KB per bulk store
+    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", small_obs ? 2048 : 1024);  // 4-8 KB per bulk store
+    // the partial renderer builds whole worlds (all agents' windows) in one tile: allow up to 48 KB per warp
+    const int64_t kTileMaxFloats = spec.kind == LLE_OBS_PARTIAL ? 12288 : 6144;
+    if (spec.kind == LLE_OBS_PARTIAL && stride > kTileMaxFloats)
+        return fail(LLE_LIMIT_EXCEEDED, "partial observation of one world exceeds 48 KB (n_agents * (2 n_agents + 3) * size^2 floats)");
     if (stride <= kTileMaxFloats) {
         v->n_chunks = 1;
         v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
@@ -402,12 +428,13 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->n_buf = 1;
     } else {
         v->E = 1;
-        v->chunk_floats = (int)kTileMaxFloats / 2;  // 12 KB chunks
+        v->chunk_floats = 3072;  // 12 KB chunks
         v->n_chunks = (int)((stride + v->chunk_floats - 1) / v->chunk_floats);
         v->tile_floats = v->chunk_floats;
         v->group = std::max(8, 32 / v->Wd);
         v->n_buf = 2;
     }
+    if (spec.kind == LLE_OBS_PARTIAL && v->tile_floats <= 3072) v->n_buf = 2;  // zero-fill one tile while the other drains
     v->n_buf = std::max(1, std::min(2, env_int("LLE_B200_NBUF", v->n_buf)));          // tuning knobs (development)
     {
         int g = env_int("LLE_B200_GROUP", v->group);
@@ -424,9 +451,9 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->pdl = env_int("LLE_B200_PDL", 1) != 0;
     v->force_narrow = env_int("LLE_B200_FORCE_NARROW", 0) != 0;
     int max_patch = 0;
-    for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)maps[k]->cm.header().n_patch);
+    for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)cms[k]->header().n_patch);
     v->fast = v->n_chunks == 1 && v->E <= 32 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 && opts->write_obs &&
-              !env_int("LLE_B200_NO_FAST", 0);
+              spec.kind == LLE_OBS_LAYERED && !env_int("LLE_B200_NO_FAST", 0);
     int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
     if (v->fast) {
         LLE_CUDA((configure_kernel<MODE_STEP, true>(v->smem, &blocks_per_sm)));
@@ -453,7 +480,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     // ---- device memory
     std::vector<const uint8_t*> table;
     for (int k = 0; k < n_maps; ++k) {
-        const auto& blob = maps[k]->cm.blob;
+        const auto& blob = cms[k]->blob;
         uint8_t* d = nullptr;
         LLE_CUDA(cudaMalloc((void**)&d, blob.size()));
         v->d_blobs.push_back(d);
@@ -474,6 +501,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     const size_t Np = (size_t)v->N_pad;
     LLE_CUDA(dalloc(&v->d_records, (size_t)v->L.stride * Np));
     if (opts->write_obs) LLE_CUDA(dalloc(&v->d_obs, (size_t)v->obs_stride * Np));
+    v->hdr0 = m0.header();
     LLE_CUDA(dalloc(&v->d_state, (size_t)v->S * Np));
     LLE_CUDA(dalloc(&v->d_avail, (size_t)v->A * 5 * Np));
     LLE_CUDA(dalloc(&v->d_reward, (size_t)v->R * Np));
@@ -509,6 +537,10 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->record_bytes = (int64_t)v->L.stride * 4;
     out->extras = v->d_extras;
     out->extras_dim = v->JE;
+    out->obs_type = v->opts.obs_type; out->obs_param = v->opts.obs_param;
+    out->obs_view_agents = v->hdr0.view_agents;
+    out->obs_c = v->hdr0.obs_c; out->obs_h = v->hdr0.obs_h; out->obs_w = v->hdr0.obs_w;
+    out->obs_invalid = v->obs_invalid;
     return LLE_OK;
 }
 

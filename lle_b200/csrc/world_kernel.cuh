@@ -94,6 +94,9 @@ struct KParams {
     uint64_t extras_set, pbrs_set;  // bit b: source b is tracked
     double pbrs_gamma, pbrs_value;
     int8_t extras_beam[64];         // source index of extras column j
+    // observation kind (static_map.h LLE_OBS_*): layered / perspective go through the tile renderer (write_obs), partial has
+    // its own cell-by-cell renderer, state is written with the small outputs (state_obs: 1 = state, 2 = normalised)
+    int32_t obs_kind, obs_param, state_obs, pad0;
     // Pipelined host stepping (lle_vec_pipeline_submit): the actions of this step arrive through a copy engine on
     // another stream, which then publishes `in_need` to *in_flag (stream memory op); the reward / done of this step are
     // duplicated into a ring slot that a third stream copies to the host once *out_flag >= out_value.
@@ -134,7 +137,8 @@ struct MapDev {
     const LleBeam* beams;
     const LlePatch* patches;
     const float* stat;
-    int n_patch, NB, obs_floats;
+    const LleAgentPlane* agent_planes;
+    int n_patch, NB, obs_floats, n_ap;
     uint64_t gem_toplevel;
     __device__ __forceinline__ void bind(const uint8_t* b) {
         blob = b;
@@ -144,6 +148,8 @@ struct MapDev {
         beams = reinterpret_cast<const LleBeam*>(b + hdr->beams_off);
         patches = reinterpret_cast<const LlePatch*>(b + hdr->patch_off);
         stat = reinterpret_cast<const float*>(b + hdr->static_off);
+        agent_planes = reinterpret_cast<const LleAgentPlane*>(b + hdr->ap_off);
+        n_ap = hdr->n_ap;
         n_patch = hdr->n_patch;
         NB = hdr->NB;
         obs_floats = hdr->obs_floats;
@@ -733,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         }
         const int64_t env0 = (int64_t)ticket * p.group;
         const uint64_t t_now = p.t + (uint64_t)step_index;
-        if (!FAST && first && p.write_obs && p.n_chunks == 1) {
+        if (!FAST && first && p.write_obs && p.n_chunks == 1 && p.obs_kind != LLE_OBS_PARTIAL) {
             // start filling this warp's tiles from the static plane of the first world's map now: the copies land
             // while the first logic pass runs
             first = false;
@@ -908,6 +914,20 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
 #pragma unroll
                     for (int k = 0; k < 5; ++k) av[k] = (uint8_t)((mask >> k) & 1u);
                 }
+                if (p.state_obs) {  // StateGenerator.observe (observations.py:155-158): the state row, positions / [H, W] if normalised
+                    float* ob = p.obs + env * p.S;
+                    if (gl < A) {
+                        const float fi = (float)(w.pos >> 8), fj = (float)(w.pos & 0xFFu);
+                        // float32 / int64 -> float64 division, stored back into the float32 array
+                        ob[2 * gl] = p.state_obs == 2 ? (float)((double)fi / (double)p.H) : fi;
+                        ob[2 * gl + 1] = p.state_obs == 2 ? (float)((double)fj / (double)p.W) : fj;
+                        ob[2 * A + p.G + gl] = ((w.alive >> gl) & 1u) ? 1.0f : 0.0f;
+                    }
+                    if (p.G) {
+                        const uint64_t coll = w.collected();
+                        for (int g = gl; g < p.G; g += Wd) ob[2 * A + g] = ((coll >> g) & 1ull) ? 1.0f : 0.0f;
+                    }
+                }
                 if (p.JE && gl < A) {
                     float* ex = p.extras + (env * A + gl) * p.JE;
                     for (int j = 0; j < p.JE; ++j) ex[j] = ((w.sub_e >> p.extras_beam[j]) & 1ull) ? 1.0f : 0.0f;
@@ -997,6 +1017,83 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             owed = true; owed_ticket = ticket; owed_seq = my_seq;
             continue;
         } else {
+        if (p.obs_kind == LLE_OBS_PARTIAL) {
+            // PartialGenerator.observe (observations.py:331-350): per agent a (2A+3, size, size) window centred on it; channels
+            // agents, WALL, lasers, GEM, EXIT.  One lane per (agent, window cell): it looks the map cell up once and
+            // writes the few non-zero channels into a zero-filled tile, which leaves with one bulk store per E worlds.
+            const int sz = p.obs_param, s2 = sz * sz, ctr = sz >> 1, Cp = 2 * A + 3;
+            const int n_tiles = p.group / p.E, tile_len = p.E * (int)p.obs_stride;
+            for (int tix = 0; tix < n_tiles; ++tix) {
+                float* tile = tiles + (size_t)buf * p.tile_floats;
+                if (lane == 0) {
+                    if (p.n_buf == 2) bulk_wait_read<1>();
+                    else bulk_wait_read<0>();
+                }
+                __syncwarp();
+                for (int f = lane * 4; f < tile_len; f += 128) *reinterpret_cast<float4*>(tile + f) = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                for (int s = 0; s < p.E; ++s) {
+                    const int g = tix * p.E + s;
+                    const int mid = map_ids[g];
+                    if (mid != render_map) {
+                        rm.bind(p.blobs[mid]);
+                        render_map = mid;
+                    }
+                    const uint32_t* cur = recs + (size_t)g * stride;
+                    float* sub = tile + (size_t)s * p.obs_stride;
+                    for (int q = lane; q < A * s2; q += 32) {
+                        const int a = q / s2, r = q - a * s2, wi = r / sz, wj = r - wi * sz;
+                        const uint32_t pa = rec_pos(cur, a);
+                        const int i = (int)(pa >> 8) + wi - ctr, j = (int)(pa & 0xFFu) + wj - ctr;
+                        if (i < 0 || j < 0 || i >= p.H || j >= p.W) continue;  // outside the map: all layers stay 0 (:325-329)
+                        float* o = sub + a * Cp * s2 + r;
+                        const int c = i * p.W + j;
+                        const uint32_t info = rm.cellinfo[c];
+                        const uint32_t kind = info & 7u;
+                        if (kind == LLE_T_WALL) {
+                            o[A * s2] = 1.0f;  // WALL = n_agents; wall_pos includes the sources (parser_v1.rs:22-25)
+                            if (info & 128u) {
+                                const int ch = A + 1 + (int)((info >> 16) & 255u);  // LASER_0 + source.agent_id, fill -1 (:348-350)
+                                if (ch < Cp) o[ch * s2] = -1.0f;
+                            }
+                        } else if (kind == LLE_T_EXIT) {
+                            o[(2 * A + 2) * s2] = 1.0f;
+                        } else if (kind == LLE_T_GEM) {
+                            const uint32_t gi = (info >> 8) & 63u;
+                            if (!((cur[L.w_gems + (gi >> 5)] >> (gi & 31u)) & 1u)) o[(2 * A + 1) * s2] = 1.0f;
+                        }
+                        const LleCellBeams cb = rm.cellbeams[c];
+#pragma unroll
+                        for (int n = 0; n < 4; ++n) {  // lit lasers listed by World::lasers (:352-360)
+                            const uint32_t e = cb.e[n];
+                            if (e == LLE_NO_BEAM) break;
+                            const int k = be_k(e);
+                            if (be_listed(e) && ((cur[L.w_on + be_b(e) * L.on_words + (k >> 5)] >> (k & 31)) & 1u)) {
+                                const int ch = A + 1 + be_colour(e);
+                                if (ch < Cp) o[ch * s2] = 1.0f;
+                            }
+                        }
+                        const uint32_t here = ((uint32_t)i << 8) | (uint32_t)j;
+                        for (int a2 = 0; a2 < A; ++a2)
+                            if (rec_pos(cur, a2) == here) o[a2 * s2] = 1.0f;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(p.obs + (env0 + (int64_t)tix * p.E) * p.obs_stride, tile, (uint32_t)tile_len * 4u);
+                    bulk_commit();
+                    if (MODE == MODE_STEP && owed && tix == 0) {
+                        bulk_wait<1>();
+                        ticket_release(p.flags + owed_ticket, owed_seq);
+                    }
+                }
+                buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
+            }
+            owed = true; owed_ticket = ticket; owed_seq = my_seq;
+            __syncwarp();
+            continue;
+        }
         const int tiles_per_group = p.n_chunks > 1 ? p.group : p.group / p.E;
         const bool whole = p.n_chunks == 1;  // a tile holds whole worlds: every patch index is in range
         for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
@@ -1035,9 +1132,10 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         cp_async_wait_all();  // the prefetch issued at kernel start
                     } else {
                         // un-patch what the previous occupant had lit and the new one has not
-                        if (lane < A) {
-                            const uint32_t op = rec_pos(old, lane);
-                            const int idx = lane * p.HW + (int)(op >> 8) * p.W + (int)(op & 0xFFu);
+                        for (int k = lane; k < rm.n_ap; k += 32) {
+                            const LleAgentPlane ap = rm.agent_planes[k];
+                            const uint32_t op = rec_pos(old, (int)ap.agent);
+                            const int idx = (int)ap.base + (int)(op >> 8) * p.W + (int)(op & 0xFFu);
                             if (whole || (idx >= lo && idx < hi)) sub_tile[idx - lo] = 0.0f;  // agent planes have no static content
                         }
                         if (pc.valid0 && in0 && pc.lit0(old) && !now0) sub_tile[pc.idx0 - lo] = pc.stat0;
@@ -1057,9 +1155,10 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         const LlePatch pe = rm.patches[k];
                         if ((whole || ((int)pe.idx >= lo && (int)pe.idx < hi)) && rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = 1.0f;
                     }
-                    if (lane < A) {
-                        const uint32_t np = rec_pos(cur, lane);
-                        const int idx = lane * p.HW + (int)(np >> 8) * p.W + (int)(np & 0xFFu);
+                    for (int k = lane; k < rm.n_ap; k += 32) {
+                        const LleAgentPlane ap = rm.agent_planes[k];
+                        const uint32_t np = rec_pos(cur, (int)ap.agent);
+                        const int idx = (int)ap.base + (int)(np >> 8) * p.W + (int)(np & 0xFFu);
                         if (whole || (idx >= lo && idx < hi)) sub_tile[idx - lo] = 1.0f;
                     }
                     for (int k = lane; k < stride; k += 32) old[k] = cur[k];

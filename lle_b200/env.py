@@ -10,6 +10,7 @@ from typing import Sequence
 
 import torch
 
+from .types import obs_spec
 from .vec_world import Map, VecWorld
 
 
@@ -22,18 +23,22 @@ class VecLLE:
 
     def __init__(self, maps, n_envs: int, *, map_of_env: Sequence[int] | None = None, device=0, multi_objective: bool = False,
                  walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True,
-                 extras=None, pbrs: dict | None = None):
+                 extras=None, pbrs: dict | None = None, obs_type: str = "layered", padding_size: int = 0):
         self.world = VecWorld(maps, n_envs, map_of_env=map_of_env, device=device, reward_dim=4 if multi_objective else 1,
                               walkable_lasers=walkable_lasers, auto_reset=auto_reset, lle_semantics=True, write_obs=write_obs,
-                              seed=seed, env_id_base=env_id_base, extras=extras, pbrs=pbrs)
-        for m in self.world.maps:
-            if m.obs_invalid and write_obs:
-                raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
+                              seed=seed, env_id_base=env_id_base, extras=extras, pbrs=pbrs, obs_type=obs_type,
+                              padding_size=padding_size)
+        if self.world.obs_invalid and write_obs:
+            raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         w = self.world
         self.n_envs, self.n_agents, self.n_actions = w.n_envs, w.n_agents, 5
-        self.observation_shape = (w.n_channels, w.height, w.width)
+        self.observation_shape = tuple(w.obs.shape[1:]) if self._flat(w) else w.obs_shape  # one agent's observation
         self.state_shape = (w.state_dim,)
         self.reward_dim = w.reward_dim
+
+    @staticmethod
+    def _flat(w) -> bool:
+        return w.obs is not None and w._flatten
 
     # tensors (views on device buffers)
     obs = property(lambda self: self.world.obs)                      # (N, C, H, W)
@@ -150,9 +155,10 @@ class Builder:
         self._kw["auto_reset"] = enabled
         return self
 
-    def obs_type(self, obs_type: str):
-        if obs_type not in ("layered", "flattened"):
-            raise NotImplementedError(f"observation type {obs_type!r} is not on the accelerated path (layered / flattened are)")
+    def obs_type(self, obs_type: str, padding_size: int = 0):
+        """Builder.obs_type (builder.py:42-49): any ObservationType value but "rgb-image"."""
+        obs_spec(obs_type, padding_size)  # ValueError / NotImplementedError
+        self._kw["obs_type"], self._kw["padding_size"] = obs_type, int(padding_size)
         return self
 
     def state_type(self, state_type: str):

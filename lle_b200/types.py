@@ -157,3 +157,24 @@ class ParsingError(ValueError):
 
 class InvalidLevelError(ValueError):
     pass
+
+
+# ObservationType values (python/lle/observations.py:37-60) served by the device path -> (LLE_OBS_* kind, param, flatten)
+OBS_LAYERED, OBS_PARTIAL, OBS_PERSPECTIVE, OBS_STATE = 0, 1, 2, 3
+_OBS_TYPES = {
+    "layered": (OBS_LAYERED, 0, False), "flattened": (OBS_LAYERED, 0, True), "layered-padded": (OBS_LAYERED, None, False),
+    "layered-padded-1": (OBS_LAYERED, 1, False), "layered-padded-2": (OBS_LAYERED, 2, False), "layered-padded-3": (OBS_LAYERED, 3, False),
+    "partial3x3": (OBS_PARTIAL, 3, False), "partial5x5": (OBS_PARTIAL, 5, False), "partial7x7": (OBS_PARTIAL, 7, False),
+    "perspective": (OBS_PERSPECTIVE, 0, False), "state": (OBS_STATE, 0, False), "normalized-state": (OBS_STATE, 1, False),
+}
+
+
+def obs_spec(obs_type: str, padding_size: int = 0) -> tuple[int, int, bool]:
+    """ObservationType.from_str + get_observation_generator (observations.py:62-97).  "rgb-image" needs the renderer,
+    which is not on the accelerated path."""
+    if obs_type == "rgb-image":
+        raise NotImplementedError("observation type 'rgb-image' is not on the accelerated path")
+    if obs_type not in _OBS_TYPES:
+        raise ValueError(f"'{obs_type}' is not a valid ObservationType")
+    kind, param, flatten = _OBS_TYPES[obs_type]
+    return kind, int(padding_size) if param is None else param, flatten

@@ -14,7 +14,7 @@ import torch
 
 from . import _native
 from ._native import MapInfo, VecBuffers, VecOptions, check, lib
-from .types import Direction, InvalidLevelError, LaserSource
+from .types import OBS_STATE, Direction, InvalidLevelError, LaserSource, obs_spec
 
 
 class Map:
@@ -99,8 +99,10 @@ class VecWorld:
     def __init__(self, maps: Sequence[Map | str | int] | Map | str | int, n_envs: int, *, map_of_env: Sequence[int] | None = None,
                  device: int | str | torch.device = 0, reward_dim: int = 1, walkable_lasers: bool = True, auto_reset: bool = True,
                  lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0,
-                 extras: str | Sequence[int] | None = None, pbrs: dict | None = None):
-        """extras: None | "laser_subgoal" (all sources) | source indices (World::sources() order) — Builder.add_extras.
+                 extras: str | Sequence[int] | None = None, pbrs: dict | None = None, obs_type: str = "layered",
+                 padding_size: int = 0):
+        """obs_type: an ObservationType value (observations.py:37-60) other than "rgb-image"; padding_size for "layered-padded".
+        extras: None | "laser_subgoal" (all sources) | source indices (World::sources() order) — Builder.add_extras.
         pbrs: None | dict(gamma=0.99, reward_value=0.5, lasers_to_reward=None | indices, with_extras=True) — Builder.pbrs
         (python/lle/env/builder.py:77-150)."""
         if not torch.cuda.is_available():
@@ -115,6 +117,8 @@ class VecWorld:
         opts.reward_dim, opts.walkable_lasers, opts.auto_reset = int(reward_dim), int(walkable_lasers), int(auto_reset)
         opts.lle_semantics, opts.write_obs = int(lle_semantics), int(write_obs)
         opts.seed, opts.env_id_base = int(seed), int(env_id_base)
+        self.obs_type = obs_type
+        opts.obs_type, opts.obs_param, self._flatten = obs_spec(obs_type, padding_size)
         extras_src = None if extras in (None, "laser_subgoal") else [int(x) for x in extras]
         want_extras = extras is not None
         if pbrs is not None:
@@ -156,12 +160,20 @@ class VecWorld:
         def wrap(ptr, shape, typestr):
             return torch.as_tensor(_DevArray(ptr, shape, typestr, self), device=dev)
 
-        #: layered observation, one (C,H,W) block per env (observations.py:254-266)
+        #: one block per env, shaped by the observation type (include/lle_b200.h: lle_vec_buffers.obs):
+        #: layered (C,H,W) [flattened: (C*H*W,)] / partial (A,2A+3,s,s) / perspective (A,C,H,W) / state (3A+G,)
         self.obs = None
+        self.obs_kind, self.obs_view_agents = int(b.obs_type), int(b.obs_view_agents)
+        #: a laser colour selects a channel past the last layer of this observation type (the reference raises IndexError)
+        self.obs_invalid = bool(b.obs_invalid)
+        self.obs_shape = (b.obs_c,) if self.obs_kind == OBS_STATE else (b.obs_c, b.obs_h, b.obs_w)  # one agent's observation
         if write_obs:
             rows = wrap(b.obs, (N, self.obs_stride), "<f4")
-            chw = self.n_channels * self.height * self.width
-            self.obs = rows[:, :chw].unflatten(1, (self.n_channels, self.height, self.width))
+            block = self.obs_shape if self.obs_view_agents else (A, *self.obs_shape)
+            n = int(np.prod(block))
+            self.obs = rows[:, :n].unflatten(1, block)
+            if self._flatten:
+                self.obs = self.obs.flatten(1)
         self.state = wrap(b.state, (N, self.state_dim), "<f4")
         self.avail = wrap(b.avail, (N, A, 5), "|u1")
         self.reward = wrap(b.reward, (N, self.reward_dim), "<f4")
@@ -182,8 +194,11 @@ class VecWorld:
     # ---- views
     @property
     def obs_per_agent(self) -> torch.Tensor:
-        """(N, A, C, H, W) view whose agent dimension has stride 0 — the values of the reference's np.tile."""
-        return self.obs.unsqueeze(1).expand(-1, self.n_agents, -1, -1, -1)
+        """(N, n_agents[+padding], *shape): what the reference's generator returns per env.  Where the reference tiles
+        one block over the agents (np.tile: layered, flattened, state) the agent dimension is a stride-0 view."""
+        if not self.obs_view_agents:
+            return self.obs
+        return self.obs.unsqueeze(1).expand(-1, self.obs_view_agents, *([-1] * (self.obs.dim() - 1)))
 
     @property
     def obs_flattened(self) -> torch.Tensor:

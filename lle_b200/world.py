@@ -52,7 +52,7 @@ class _Single:
         self._map = Map(map_str, level=level)
         m = self._map
         self.height, self.width, self.n_agents, self.n_gems = m.height, m.width, m.n_agents, m.n_gems
-        self._vec = VecWorld(m, 1, device=device, write_obs=not m.obs_invalid, **vec_kw)
+        self._vec = VecWorld(m, 1, device=device, **vec_kw)
         self._laser_tiles = m.laser_tiles()
         self._sources = m.sources()
 
@@ -118,7 +118,7 @@ class _Single:
 
     def observe_layered(self) -> np.ndarray:
         """LayeredPadded.observe (observations.py:254-266): (A, C, H, W) float32."""
-        if self._map.obs_invalid:
+        if self._vec.obs_invalid:
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         self._vec.synchronize()
         return self._vec.obs_per_agent[0].cpu().numpy()
@@ -232,10 +232,12 @@ class LLE(_Single):
     """`lle.LLE` (python/lle/env/env.py) for one environment, served by the device path."""
 
     def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
-                 walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, device=0):
+                 walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, obs_type: str = "layered",
+                 padding_size: int = 0, device=0):
         self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
-                          reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs)
-        if self._map.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
+                          reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
+                          obs_type=obs_type, padding_size=padding_size)
+        if self._vec.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         self.reward_dim = self._vec.reward_dim
 

@@ -825,13 +825,13 @@ inline World parse_world(const std::string& text) {
 // Python layer restated: observations.py, env/env.py, env/reward_strategy.py
 // ------------------------------------------------------------------------------------------
 
-// python/lle/observations.py:196-266 (LayeredPadded with padding_size = 0 == Layered)
+// python/lle/observations.py:196-266 (LayeredPadded; padding_size = 0 == Layered)
 struct Layered {
     size_t n_agents, A0, LASER_0, WALL, VOID, GEM, EXIT, C, H, W;
     std::vector<float> static_obs;
 
-    explicit Layered(const World& w) {
-        n_agents = w.n_agents();
+    explicit Layered(const World& w, size_t padding_size = 0) {
+        n_agents = w.n_agents() + padding_size;  // observations.py:203
         A0 = 0;
         LASER_0 = A0 + n_agents;
         WALL = LASER_0 + n_agents;
@@ -873,6 +873,71 @@ struct Layered {
     }
 };
 
+// python/lle/observations.py:296-369 (PartialGenerator): one (2A+3, size, size) window per agent, centred on it.
+// Channel order: agents, WALL, lasers, GEM, EXIT (no VOID layer).  Cells outside the map stay 0.
+struct Partial {
+    size_t A, size, center, WALL, LASER_0, GEM, EXIT, C;
+    Partial(const World& w, size_t square_size) {
+        if (square_size % 2 != 1) throw std::invalid_argument("Can only use odd numbers for the square size");  // :299
+        A = w.n_agents();
+        size = square_size;
+        center = size / 2;
+        WALL = A;
+        LASER_0 = WALL + 1;
+        GEM = LASER_0 + A;
+        EXIT = GEM + 1;
+        C = 2 * A + 3;
+    }
+    size_t floats() const { return A * C * size * size; }
+    // obs[a, layer] with numpy's bounds check on the layer index
+    float* layer(float* obs, size_t a, size_t c) const {
+        if (c >= C) throw std::out_of_range("IndexError: partial channel out of range");
+        return obs + (a * C + c) * size * size;
+    }
+    // :322-329
+    void encode(float* layer_ptr, const Position& origin, const Position& p, float fill = 1.0f) const {
+        const long i = (long)p.i - (long)origin.i + (long)center, j = (long)p.j - (long)origin.j + (long)center;
+        if (0 <= i && i < (long)size && 0 <= j && j < (long)size) layer_ptr[i * (long)size + j] = fill;
+    }
+    // :331-350
+    void observe(const World& w, float* obs) const {
+        std::fill(obs, obs + floats(), 0.0f);
+        const auto lasers = w.lasers();
+        const auto gems = w.gems();
+        for (size_t a = 0; a < A; ++a) {
+            const Position& me = w.agents_positions[a];
+            for (size_t a2 = 0; a2 < A; ++a2) encode(layer(obs, a, a2), me, w.agents_positions[a2]);
+            for (size_t g = 0; g < gems.size(); ++g)
+                if (!gems[g]->collected) encode(layer(obs, a, GEM), me, w.gems_positions[g]);
+            for (const auto& p : w.exits) encode(layer(obs, a, EXIT), me, p);
+            for (const auto& p : w.wall_positions) encode(layer(obs, a, WALL), me, p);
+            for (const auto& l : lasers)  // _get_lasers_positions (:352-360): only colours with a lit laser are touched
+                if (l.is_on) encode(layer(obs, a, LASER_0 + l.agent_id), me, l.pos);
+            for (size_t s = 0; s < w.laser_source_positions.size(); ++s)
+                encode(layer(obs, a, LASER_0 + w.source_beam(s)->agent_id), me, w.laser_source_positions[s], -1.0f);
+        }
+    }
+};
+
+// python/lle/observations.py:372-395 (AgentZeroPerspective): the layered observation, where agent n's copy has the
+// agent layers 0 <-> n and the laser layers 0 <-> n swapped.  Output: (A, C, H, W), one distinct copy per agent.
+struct Perspective {
+    Layered base;
+    explicit Perspective(const World& w) : base(w) {}
+    size_t floats() const { return base.n_agents * base.size(); }
+    void observe(const World& w, float* out) const {
+        const size_t n = base.size(), HW = base.H * base.W;
+        std::vector<float> one(n);
+        base.observe(w, one.data());
+        for (size_t a = 0; a < base.n_agents; ++a) std::memcpy(out + a * n, one.data(), n * sizeof(float));  // np.tile
+        for (size_t a = 1; a < base.n_agents; ++a) {
+            float* obs = out + a * n;
+            std::swap_ranges(obs + base.A0 * HW, obs + (base.A0 + 1) * HW, obs + (base.A0 + a) * HW);
+            std::swap_ranges(obs + base.LASER_0 * HW, obs + (base.LASER_0 + 1) * HW, obs + (base.LASER_0 + a) * HW);
+        }
+    }
+};
+
 // src/bindings/world/pyworld_state.rs:79-101
 inline void state_as_array(const WorldState& s, float* out) {
     size_t k = 0;
@@ -883,6 +948,81 @@ inline void state_as_array(const WorldState& s, float* out) {
     for (bool c : s.gems_collected) out[k++] = c ? 1.0f : 0.0f;
     for (bool a : s.agents_alive) out[k++] = a ? 1.0f : 0.0f;
 }
+
+// python/lle/observations.py:141-158 (StateGenerator.observe, one row; np.tile over agents is a pure repeat):
+// float32 state, positions divided by [height, width] (int64 -> the division happens in float64) and stored back to float32
+inline void state_observation(const World& w, bool normalize, float* out) {
+    const WorldState s = w.get_state();
+    state_as_array(s, out);
+    if (normalize)
+        for (size_t a = 0; a < s.agents_positions.size(); ++a) {
+            out[2 * a] = (float)((double)out[2 * a] / (double)w.height);
+            out[2 * a + 1] = (float)((double)out[2 * a + 1] / (double)w.width);
+        }
+}
+
+enum class ObsKind : int { Layered = 0, Partial = 1, Perspective = 2, State = 3 };
+
+// ObservationType.get_observation_generator (observations.py:66-97) for the kinds on the accelerated path.
+// `floats()` is the size of one env's block in the device layout: layered = ONE (C,H,W) copy (np.tile's repeats are a
+// stride-0 view), state = one row, partial / perspective = all agents' (distinct) copies.
+struct ObsGen {
+    ObsKind kind = ObsKind::Layered;
+    int param = 0;  // layered: padding_size; partial: square size; state: 1 = normalised
+    std::unique_ptr<Layered> layered;
+    std::unique_ptr<Partial> partial;
+    std::unique_ptr<Perspective> perspective;
+    size_t state_len = 0;
+    ObsGen(const World& w, ObsKind k, int prm) : kind(k), param(prm) {
+        switch (k) {
+            case ObsKind::Layered: layered = std::make_unique<Layered>(w, (size_t)prm); break;
+            case ObsKind::Partial: partial = std::make_unique<Partial>(w, (size_t)prm); break;
+            case ObsKind::Perspective: perspective = std::make_unique<Perspective>(w); break;
+            case ObsKind::State: state_len = 3 * w.n_agents() + w.n_gems(); break;
+        }
+    }
+    size_t floats() const {
+        switch (kind) {
+            case ObsKind::Layered: return layered->size();
+            case ObsKind::Partial: return partial->floats();
+            case ObsKind::Perspective: return perspective->floats();
+            default: return state_len;
+        }
+    }
+    // out[0] = number of dims of one env's block, out[1..4] = dims, out[5] = agent copies that np.tile adds in front
+    // (0: the block already carries the agent dimension)
+    void block_shape(long* out) const {
+        for (int k = 0; k < 6; ++k) out[k] = 0;
+        switch (kind) {
+            case ObsKind::Layered:
+                out[0] = 3; out[1] = (long)layered->C; out[2] = (long)layered->H; out[3] = (long)layered->W;
+                out[5] = (long)layered->n_agents;  // np.tile(obs, (self.n_agents, ...)) with the padded agent count (:266)
+                break;
+            case ObsKind::Partial:
+                out[0] = 4; out[1] = (long)partial->A; out[2] = (long)partial->C; out[3] = out[4] = (long)partial->size;
+                break;
+            case ObsKind::Perspective:
+                out[0] = 4; out[1] = (long)perspective->base.n_agents; out[2] = (long)perspective->base.C;
+                out[3] = (long)perspective->base.H; out[4] = (long)perspective->base.W;
+                break;
+            default:
+                out[0] = 1; out[1] = (long)state_len; out[5] = (long)((state_len) ? 0 : 0);
+                break;
+        }
+    }
+    void setup(const World& w) {  // ObservationGenerator.reset (observations.py:239-240; called by LLE.reset, env.py:203)
+        if (layered) layered->setup(w);
+        if (perspective) perspective->base.setup(w);
+    }
+    void observe(const World& w, float* out) const {
+        switch (kind) {
+            case ObsKind::Layered: layered->observe(w, out); break;
+            case ObsKind::Partial: partial->observe(w, out); break;
+            case ObsKind::Perspective: perspective->observe(w, out); break;
+            default: state_observation(w, param != 0, out); break;
+        }
+    }
+};
 
 constexpr float REWARD_GEM = 1.0f, REWARD_EXIT = 1.0f, REWARD_DONE = 1.0f, REWARD_DEATH = -1.0f;
 
@@ -926,7 +1066,7 @@ struct SubgoalTracker {
 // python/lle/env/env.py (LLE) + env/reward_strategy.py (SingleObjective / MultiObjective / PotentialShapedLLE)
 struct Env {
     World world;
-    Layered layered;
+    ObsGen obs;
     bool multi_objective;
     bool walkable_lasers;
     size_t n_arrived = 0, n_deads = 0;
@@ -940,7 +1080,9 @@ struct Env {
     double gamma = 0.99, reward_value = 0.5, previous_potential = 0.0;
 
     Env(World&& w, bool multi_obj = false, bool walkable = true)
-        : world(std::move(w)), layered(world), multi_objective(multi_obj), walkable_lasers(walkable) {}
+        : world(std::move(w)), obs(world, ObsKind::Layered, 0), multi_objective(multi_obj), walkable_lasers(walkable) {}
+
+    void set_obs(ObsKind kind, int param) { obs = ObsGen(world, kind, param); }  // Builder.obs_type (builder.py:42-49)
 
     size_t reward_dim() const { return (multi_objective ? 4 : 1) + (multi_objective && has_pbrs ? 1 : 0); }
 
@@ -1017,7 +1159,7 @@ struct Env {
         reset_strategy();
         if (has_extras) extras.clear();  // extras_generator.reset() (env.py:196)
         done = false;
-        layered.setup(world);
+        obs.setup(world);
     }
     // RewardStrategy.reset (:40-42) / PotentialShapedLLE.reset (:176-180)
     void reset_strategy() {
@@ -1066,7 +1208,7 @@ struct Env {
             }
         }
     }
-    void observe(float* out) const { layered.observe(world, out); }
+    void observe(float* out) const { obs.observe(world, out); }
     void state(float* out) const { state_as_array(world.get_state(), out); }
 };
 

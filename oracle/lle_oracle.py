@@ -408,10 +408,47 @@ class World:
         _check(lib().lleo_world_observe_layered(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return np.tile(out, (self.n_agents, 1, 1, 1))
 
+    def observe(self, obs_type: str = "layered", padding_size: int = 0) -> np.ndarray:
+        """`ObservationType(obs_type).get_observation_generator(world, padding_size).observe()` (observations.py:66-97)
+        with a generator built from the live world: (n_agents[+padding], *shape) float32."""
+        kind, param, flatten = obs_spec(obs_type, padding_size)
+        out, shape6 = _observe_into(lambda buf, cap, s6: lib().lleo_world_observe(self._h, kind, param, buf, cap, s6))
+        return _finish_obs(out, shape6, flatten, self.n_agents)
+
     def state_array(self) -> np.ndarray:
         out = np.zeros(3 * self.n_agents + self.n_gems, dtype=np.float32)
         lib().lleo_world_state_array(self._h, out.ctypes.data_as(C.POINTER(C.c_float)))
         return out
+
+
+def obs_spec(obs_type: str, padding_size: int = 0) -> tuple[int, int, bool]:
+    """ObservationType value (observations.py:37-60) -> (kind, param, flatten) of ObsGen."""
+    table = {"layered": (0, 0, False), "flattened": (0, 0, True), "layered-padded": (0, int(padding_size), False),
+             "layered-padded-1": (0, 1, False), "layered-padded-2": (0, 2, False), "layered-padded-3": (0, 3, False),
+             "partial3x3": (1, 3, False), "partial5x5": (1, 5, False), "partial7x7": (1, 7, False),
+             "perspective": (2, 0, False), "state": (3, 0, False), "normalized-state": (3, 1, False)}
+    if obs_type not in table:
+        raise ValueError(f"'{obs_type}' is not a valid ObservationType")
+    return table[obs_type]
+
+
+def _observe_into(call):
+    s6 = (C.c_long * 6)()
+    _check(call(None, 0, s6))  # shape query
+    n = int(np.prod([s6[k] for k in range(1, 1 + s6[0])]))
+    out = np.zeros(n, dtype=np.float32)
+    _check(call(out.ctypes.data_as(C.POINTER(C.c_float)), n, s6))
+    return out, list(s6)
+
+
+def _finish_obs(flat: np.ndarray, s6, flatten: bool, n_agents: int | None = None) -> np.ndarray:
+    """One env's block -> the array the reference returns: np.tile over agents where the generator tiles."""
+    block = flat.reshape([s6[k] for k in range(1, 1 + s6[0])])
+    if s6[0] == 1:  # state: np.tile(state, (n_agents, 1))
+        return np.tile(block, (n_agents, 1))
+    if s6[5]:
+        block = np.tile(block, (s6[5], 1, 1, 1))
+    return block.reshape(block.shape[0], -1) if flatten else block
 
 
 # ------------------------------------------------------------------ LLE (python/lle/env/env.py)
@@ -434,7 +471,8 @@ def _src_list(sources):
 
 
 class LLE:
-    def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True, extras=None, pbrs=None):
+    def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True, extras=None, pbrs=None,
+                 obs_type: str = "layered", padding_size: int = 0):
         """extras: None | "laser_subgoal" | list of source indices.  pbrs: None | dict(gamma=0.99, reward_value=0.5,
         lasers_to_reward=None (all) | list of source indices, with_extras=True) — Builder.pbrs (builder.py:77-110)."""
         st = C.c_int(0)
@@ -455,6 +493,10 @@ class LLE:
         self.height, self.width, self.n_agents, self.n_gems, self.n_channels, self.reward_dim = list(d)
         self.reward_dim = lib().lleo_env_reward_dim(self._h)
         self.extras_dim = lib().lleo_env_extras_dim(self._h)
+        kind, param, self._flatten = obs_spec(obs_type, padding_size)
+        self._s6 = (C.c_long * 6)()
+        _check(lib().lleo_env_set_obs(self._h, kind, param, self._s6))
+        lib().lleo_env_obs_floats.restype = C.c_long
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -475,9 +517,9 @@ class LLE:
         return lib().lleo_env_n_arrived(self._h)
 
     def observe(self) -> np.ndarray:
-        out = np.zeros((self.n_channels, self.height, self.width), dtype=np.float32)
+        out = np.zeros(lib().lleo_env_obs_floats(self._h), dtype=np.float32)
         _check(lib().lleo_env_observe(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
-        return np.tile(out, (self.n_agents, 1, 1, 1))
+        return _finish_obs(out, list(self._s6), self._flatten, self.n_agents)
 
     def get_state(self) -> np.ndarray:
         out = np.zeros(3 * self.n_agents + self.n_gems, dtype=np.float32)
@@ -527,7 +569,8 @@ class OracleVec:
     """N oracle environments stepped in lockstep; arrays are views on the C++ buffers."""
 
     def __init__(self, maps: Sequence[str], map_of_env: Sequence[int] | None, n_envs: int, *, multi_objective=False,
-                 walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0, extras=None, pbrs=None):
+                 walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0, extras=None, pbrs=None,
+                 obs_type: str = "layered", padding_size: int = 0):
         texts = (C.c_char_p * len(maps))(*[m.encode() for m in maps])
         moe = None if map_of_env is None else (C.c_int * n_envs)(*[int(m) for m in map_of_env])
         st = C.c_int(0)
@@ -547,6 +590,10 @@ class OracleVec:
                                             C.c_double(pb.get("reward_value", 0.5)), np_, pa))
             lib().lleo_vec_extras_dim.restype = C.c_long
             self.JE = lib().lleo_vec_extras_dim(self._h)
+        kind, param, _ = obs_spec(obs_type, padding_size)
+        s6 = (C.c_long * 6)()
+        _check(lib().lleo_vec_set_obs(self._h, kind, param, s6))
+        self.obs_block_shape = tuple(s6[k] for k in range(1, 1 + s6[0]))
         d = (C.c_long * 9)()
         lib().lleo_vec_dims(self._h, d)
         self.N, self.A, self.G, self.C, self.H, self.W, self.R, self.S, self.NB = list(d)
@@ -561,7 +608,7 @@ class OracleVec:
             return arr.view(dtype).reshape(shape)
 
         N, A = self.N, self.A
-        self.obs = view(0, C.c_float, np.float32, (N, self.C, self.H, self.W))
+        self.obs = view(0, C.c_float, np.float32, (N, *self.obs_block_shape))
         self.state = view(1, C.c_float, np.float32, (N, self.S))
         self.avail = view(2, C.c_uint8, np.uint8, (N, A, 5))
         self.reward = view(3, C.c_float, np.float32, (N, self.R))

@@ -116,6 +116,7 @@ struct Vec {
     std::vector<std::unique_ptr<Env>> envs;
     std::vector<int> map_of_env;
     size_t N = 0, A = 0, G = 0, C = 0, H = 0, W = 0, R = 1, S = 0, NB = 0;
+    size_t OF = 0;  // floats of one env's observation block (ObsGen::floats)
     bool auto_reset = false;
     uint64_t seed = 0, env_id_base = 0, t = 0;
     std::vector<float> obs, state, reward, extras;  // extras: LaserSubgoal flags [N, A, JE]
@@ -130,7 +131,7 @@ struct Vec {
 
     void export_env(size_t e) {
         Env& env = *envs[e];
-        env.observe(&obs[e * C * H * W]);
+        env.observe(&obs[e * OF]);
         env.state(&state[e * S]);
         env.available_actions(&avail[e * A * 5]);
         if (JE) env.compute_extras(&extras[e * A * JE]);
@@ -378,7 +379,29 @@ void* lleo_env_world(void* p) { return nullptr; (void)p; }
 void lleo_env_dims(void* p, int* out) {
     const Env& e = *(Env*)p;
     out[0] = (int)e.world.height; out[1] = (int)e.world.width; out[2] = (int)e.world.n_agents();
-    out[3] = (int)e.world.n_gems(); out[4] = (int)e.layered.C; out[5] = (int)e.reward_dim();
+    out[3] = (int)e.world.n_gems(); out[4] = (int)(2 * e.world.n_agents() + 4); out[5] = (int)e.reward_dim();
+}
+// Builder.obs_type (builder.py:42-49): kind 0 layered (param = padding), 1 partial (param = size), 2 perspective,
+// 3 state (param 1 = normalised).  out6: block_shape (see ObsGen::block_shape).
+int lleo_env_set_obs(void* p, int kind, int param, long* out6) {
+    Env& e = *(Env*)p;
+    return guarded([&] {
+        e.set_obs((ObsKind)kind, param);
+        e.obs.block_shape(out6);
+    });
+}
+long lleo_env_obs_floats(void* p) { return (long)((Env*)p)->obs.floats(); }
+// a generator built from the live world, as the reference tests do (`PartialGenerator(world, 3).observe()`)
+int lleo_world_observe(void* p, int kind, int param, float* out, long cap, long* out6) {
+    WorldHandle* h = (WorldHandle*)p;
+    return guarded([&] {
+        ObsGen g(h->w, (ObsKind)kind, param);
+        g.block_shape(out6);
+        if (out) {
+            if ((long)g.floats() > cap) throw std::invalid_argument("observation buffer too small");
+            g.observe(h->w, out);
+        }
+    });
 }
 int lleo_env_reset(void* p) { return guarded([&] { ((Env*)p)->reset(); }); }
 int lleo_env_step(void* p, const uint8_t* actions, int n, float* reward, uint8_t* done, int* events_out,
@@ -455,7 +478,7 @@ void* lleo_vec_new(const char** texts, int n_maps, const int* map_of_env, int n_
                                                       walkable_lasers != 0));
         }
         const Env& e0 = *tmp->envs[0];
-        tmp->A = e0.world.n_agents(); tmp->G = e0.world.n_gems(); tmp->C = e0.layered.C;
+        tmp->A = e0.world.n_agents(); tmp->G = e0.world.n_gems(); tmp->C = 2 * tmp->A + 4;
         tmp->H = e0.world.height; tmp->W = e0.world.width; tmp->R = e0.reward_dim();
         tmp->S = 3 * tmp->A + tmp->G;
         for (const auto& e : tmp->envs) {
@@ -465,7 +488,8 @@ void* lleo_vec_new(const char** texts, int n_maps, const int* map_of_env, int n_
             tmp->NB = std::max(tmp->NB, e->world.laser_source_positions.size());
         }
         size_t N = tmp->N, A = tmp->A;
-        tmp->obs.assign(N * tmp->C * tmp->H * tmp->W, 0.f);
+        tmp->OF = e0.obs.floats();
+        tmp->obs.assign(N * tmp->OF, 0.f);
         tmp->state.assign(N * tmp->S, 0.f);
         tmp->reward.assign(N * tmp->R, 0.f);
         tmp->avail.assign(N * A * 5, 0);
@@ -516,6 +540,18 @@ int lleo_vec_configure(void* p, int n_extras, const int* extras_src, int pbrs, d
             v.envs[e]->reset();
             v.export_env(e);
         }
+    });
+}
+// Observation type of every env of the vec (see lleo_env_set_obs); re-exports all envs.  The obs buffer is reallocated:
+// fetch the pointers again with lleo_vec_buffers.
+int lleo_vec_set_obs(void* p, int kind, int param, long* out6) {
+    Vec& v = *(Vec*)p;
+    return guarded([&] {
+        for (auto& e : v.envs) e->set_obs((ObsKind)kind, param);
+        v.envs[0]->obs.block_shape(out6);
+        v.OF = v.envs[0]->obs.floats();
+        v.obs.assign(v.N * v.OF, 0.f);
+        for (size_t e = 0; e < v.N; ++e) v.export_env(e);
     });
 }
 void* lleo_vec_extras(void* p) { return ((Vec*)p)->extras.data(); }
@@ -626,7 +662,7 @@ double lleo_vec_rollout(void* p, int steps, int n_threads, int* threads_used) {
                 encode_events(ev, env.world.last_event_pass, &v.events[e * v.A], v.A);
                 v.done[e] = env.done;
                 if (env.done) env.reset();
-                env.observe(&v.obs[e * v.C * v.H * v.W]);
+                env.observe(&v.obs[e * v.OF]);
                 env.state(&v.state[e * v.S]);
                 env.available_actions(&v.avail[e * v.A * 5]);
                 if (v.JE) env.compute_extras(&v.extras[e * v.A * v.JE]);

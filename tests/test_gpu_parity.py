@@ -36,7 +36,8 @@ def make_pair(maps, map_of_env, n_envs, **kw):
 
     okw = dict(multi_objective=kw.get("reward_dim", 1) == 4, walkable_lasers=kw.get("walkable_lasers", True),
                auto_reset=kw.get("auto_reset", True), seed=kw.get("seed", 0), env_id_base=kw.get("env_id_base", 0),
-               extras=kw.get("extras"), pbrs=kw.get("pbrs"))
+               extras=kw.get("extras"), pbrs=kw.get("pbrs"), obs_type=kw.get("obs_type", "layered"),
+               padding_size=kw.get("padding_size", 0))
     ora = lo.OracleVec(maps, map_of_env, n_envs, **okw)
     vec = lle_b200.VecWorld(maps, n_envs, map_of_env=map_of_env, **kw)
     dev = Dev(vec)
@@ -106,6 +107,39 @@ def test_laser_subgoal_extras_and_pbrs():
     from _util import synthetic_map
 
     run_pair([synthetic_map(64, 64, 8, 16, seed=5)], None, 64, 30, check_every=3, pbrs=dict(), seed=37)
+
+
+@pytest.mark.parametrize("obs_type", ["partial3x3", "partial5x5", "partial7x7", "perspective", "layered-padded-2", "state",
+                                      "normalized-state"])
+def test_observation_types(obs_type):
+    """the other observation generators (observations.py:141-158, :196-214, :296-395) as store epilogues of
+    the same fused step, bit-exact against the oracle's restatement under Philox rollouts."""
+    for level in (3, 5, 6):
+        run_pair([level_text(level)], None, 200, 120, obs_type=obs_type, seed=50 + level)
+    # heterogeneous maps in one batch, ragged size, no auto-reset (dead agents stay in the observation)
+    maps = [level_text(2), level_text(3), level_text(4)]
+    moe = [(e * 7 + e // 5) % 3 for e in range(333)]
+    run_pair(maps, moe, 333, 100, obs_type=obs_type, auto_reset=False, seed=57)
+    run_pair(["S0 . G\nS1 X X"], None, 70, 40, obs_type=obs_type, seed=58)  # tiny map: windows mostly off the map
+
+
+def test_observation_types_large_and_many_agents():
+    from _util import synthetic_map
+
+    big = synthetic_map(64, 64, 8, 16, seed=5)
+    run_pair([big], None, 64, 30, check_every=3, obs_type="perspective", seed=61)   # 8 x 327,680 B per world, chunked
+    run_pair([big], None, 64, 30, check_every=3, obs_type="partial7x7", seed=62)    # 8 x 19 x 49 floats per world
+    run_pair([big], None, 64, 30, check_every=3, obs_type="layered-padded", padding_size=4, seed=63)
+    rows = [" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)]
+    run_pair(["\n".join(rows)], None, 64, 40, obs_type="partial3x3", seed=64)      # 14 agents
+    run_pair(["\n".join(rows)], None, 64, 40, obs_type="perspective", seed=65)
+    run_pair(["S0 L1E X"], None, 40, 10, obs_type="partial3x3", seed=66)            # colour == n_agents spills into GEM
+    import lle_b200
+
+    with pytest.raises(IndexError):  # colour 3 >= n_agents + 2: numpy IndexError in the reference
+        lle_b200.VecLLE(["S0 L3E X"], 4, obs_type="partial3x3")
+    v = lle_b200.VecWorld(level_text(6), 16, obs_type="flattened")
+    assert tuple(v.obs.shape) == (16, 12 * 12 * 13) and tuple(v.obs_per_agent.shape) == (16, 4, 12 * 12 * 13)
 
 
 def test_supplied_actions_with_invalid_ones():

@@ -474,3 +474,171 @@ def test_pbrs_builder_order():  # [S] test_pbrs_raises_value_error (host-side bu
         lle_b200.from_str(PBRS_MAP).pbrs(lasers_to_reward=[(0, 0)])
     with pytest.raises(ValueError):
         lle_b200.from_str(PBRS_MAP).add_extras("nope")
+
+
+# ----------------------------------------------------------------------------- other observation types
+# The reference builds a generator on a World (`PartialGenerator(world, 3)`); here the same generator is selected with
+# `LLE(map, obs_type=...)` (Builder.obs_type, builder.py:42-49) and `env.reset()` stands for `world.reset()`.
+def test_observe_flattened(api):  # [O]
+    text = "@ @ L0S @  @\n@ .  .  .  @\n@ X  G  S0 @\n@ .  .  .  @\n@ @  @  @  @"
+    env = api.LLE(text, obs_type="flattened")
+    obs, _ = env.reset()
+    assert obs.shape == (1, (1 * 2 + 4) * 5 * 5)
+    layered, _ = api.LLE(text).reset()
+    assert np.array_equal(obs, layered.reshape(1, -1))
+
+
+def test_world_initial_observation_normalized_state(api):  # [O] test_world_initial_observation
+    obs, _ = api.LLE("S0 X .\n.  . .\n.  . .", obs_type="normalized-state").reset()
+    assert np.array_equal(np.array([[0.0, 0.0, 1.0]]), obs)
+    obs, _ = api.LLE("S0 X  .\n.  .  S1\n.  .  X", obs_type="normalized-state").reset()
+    assert obs.dtype == np.float32
+    assert np.allclose(np.tile(np.array([0.0, 0.0, 1 / 3, 2 / 3, 1.0, 1.0]), (2, 1)), obs)
+    # float32 state / int64 dimensions -> float64 quotient stored back into float32 (observations.py:156-157)
+    assert np.array_equal(obs[0], np.array([0.0, 0.0, 1.0 / 3, 2.0 / 3, 1.0, 1.0]).astype(np.float32))
+    obs, _ = api.LLE("S0 X  .  .\n.  .  S1  .\n.  X  .  .", obs_type="normalized-state").reset()
+    assert np.allclose(np.tile(np.array([0.0, 0.0, 1 / 3, 1 / 2, 1.0, 1.0]), (2, 1)), obs)
+    obs, _ = api.LLE("S0 X  .  G\n.  .  S1  .\n.  X  .  .", obs_type="normalized-state").reset()
+    assert np.allclose(np.tile(np.array([0.0, 0.0, 1 / 3, 1 / 2, 0.0, 1.0, 1.0]), (2, 1)), obs)
+
+
+def test_state_observation_type(api):  # [O] test_observation_gem_collected through the env
+    env = api.LLE("S0 X . .\n.  . . .\nG  . . .", obs_type="state")
+    obs, state = env.reset()
+    assert obs.shape == (1, 4) and np.array_equal(obs[0], state)
+    env.step([api.Action.SOUTH])
+    obs = env.step([api.Action.SOUTH]).obs
+    assert np.all(obs[:, 2] == 1.0)
+
+
+def test_partial_3x3(api):  # [O]
+    env = api.LLE("S0 X  @\nG  S1 @\n.  .  X", obs_type="partial3x3")
+    obs, _ = env.reset()
+    WALL, LASER_0 = 2, 3
+    GEM, EXIT = LASER_0 + 2, LASER_0 + 3
+    assert obs.shape == (2, 7, 3, 3) and obs.dtype == np.float32
+    obs0, obs1 = obs
+    assert obs0[0, 1, 1] == 1 and obs0[1, 2, 2] == 1
+    assert obs1[0, 0, 0] == 1 and obs1[1, 1, 1] == 1
+    assert obs0[GEM, 2, 1] == 1 and obs1[GEM, 1, 0] == 1
+    assert obs1[EXIT, 2, 2] == 1
+    assert np.all(obs0[WALL] == 0)
+    assert obs1[WALL, 1, 2] == 1 and obs1[WALL, 0, 2] == 1
+
+
+def test_partial_7x7(api):  # [O]
+    env = api.LLE("S0 S1 S2 S3 X X X X", obs_type="partial7x7")
+    observations, _ = env.reset()
+    n_agents, center = 4, 3
+    WALL, LASER_0 = n_agents, n_agents + 1
+    GEM, EXIT = LASER_0 + n_agents, LASER_0 + n_agents + 1
+    assert observations.shape == (4, 2 * n_agents + 3, 7, 7)
+    observations = observations.copy()
+    for agent_num, obs in enumerate(observations):
+        for other in range(n_agents):
+            i, j = center, center - agent_num + other  # agents are side by side
+            assert obs[other, i, j] == 1
+            obs[other, i, j] = 0
+            assert np.all(obs[0] == 0)
+    assert np.all(observations[0, EXIT] == 0)
+    assert observations[1, EXIT, center, center + 3] == 1
+    assert np.all(observations[2, EXIT, center, center + 2:] == 1)
+    assert np.all(observations[3, EXIT, center, center + 1:] == 1)
+    assert np.all(observations[:, WALL] == 0)
+    assert np.all(observations[:, GEM] == 0)
+    assert np.all(observations[:, LASER_0:LASER_0 + n_agents] == 0)
+
+
+def test_partial_3x3_lasers(api):  # [O]
+    env = api.LLE(".   L0S S1\nS0   .   .\nL1E  X   X", obs_type="partial3x3")
+    obs, _ = env.reset()
+    LASER_0 = 3
+    obs0, obs1 = obs
+    assert obs0[LASER_0, 0, 2] == -1
+    assert obs0[LASER_0, 1, 2] == 1
+    assert obs0[LASER_0, 2, 2] == 1
+    assert obs0[LASER_0 + 1, 2, 1] == -1
+    assert obs0[LASER_0 + 1, 2, 2] == 1
+
+
+def test_partial_5x5_shape_and_off_map_cells(api):  # observations.py:301, :325-329
+    env = api.LLE("S0 X", obs_type="partial5x5")
+    obs, _ = env.reset()
+    assert obs.shape == (1, 5, 5, 5)
+    assert obs[0, 0, 2, 2] == 1 and obs[0, 4, 2, 3] == 1  # the agent in the centre, the exit to its right
+    assert obs.sum() == 2  # everything outside the 1x2 map is 0
+
+
+def test_padded_layered(api):  # [O]
+    base, _ = api.LLE("S0 X").reset()
+    for k in (1, 2, 3):
+        obs, _ = api.LLE("S0 X", obs_type=f"layered-padded-{k}").reset()
+        assert obs.shape[1] == base.shape[1] + 2 * k and obs.shape[2:] == base.shape[2:]
+        assert obs.shape[0] == 1 + k  # np.tile over the padded agent count (observations.py:203, :266)
+        # the padded agent and laser layers are empty; the others keep their order
+        assert np.array_equal(obs[0, 0], base[0, 0]) and np.all(obs[:, 1:1 + k] == 0)
+        assert np.array_equal(obs[0, 1 + k], base[0, 1]) and np.all(obs[:, 2 + k:2 + 2 * k] == 0)
+        assert np.array_equal(obs[0, 2 + 2 * k:], base[0, 2:])
+    obs, _ = api.LLE("S0 X", obs_type="layered-padded", padding_size=5).reset()
+    assert obs.shape == (6, 16, 1, 2)
+
+
+def test_padded_layered_takes_foreign_colours(api):  # colour >= n_agents lands in a padded laser layer instead of WALL
+    obs, _ = api.LLE("S0 L1E X", obs_type="layered-padded-1").reset()
+    LASER_0 = 2
+    assert obs[0, LASER_0 + 1, 0, 1] == -1 and obs[0, LASER_0 + 1, 0, 2] == 1
+
+
+def test_perspective(api):  # [O]
+    env = api.LLE("S0  S1 S2 X\nL0E .  X  .\n .  .  X L1W", obs_type="perspective")
+    obs, _ = env.reset()
+    A0, L0 = 0, 3
+    assert obs.shape == (3, 10, 3, 4)
+    obs0, obs1, obs2 = obs
+    assert obs0[A0, 0, 0] == 1 and obs1[A0, 0, 1] == 1 and obs2[A0, 0, 2] == 1
+    assert obs0[L0, 1, 0] == -1
+    assert np.all(obs0[L0, 1, 1:] == 1)
+    assert obs1[L0, 2, 3] == -1
+    assert np.all(obs1[L0, 2, :3] == 1)
+
+
+def test_perspective2(api):  # [O]
+    text = "S0  S1 S2\n .   .  .\nL0E  X  .\nL1E  X  .\nL2E  X  ."
+    base, persp = api.LLE(text), api.LLE(text, obs_type="perspective")
+    layered_obs, _ = base.reset()
+    perspective_obs, _ = persp.reset()
+    A0, L0 = 0, 3
+    positions = [(0, 0), (0, 1), (0, 2)]
+    for actions in (None, [api.Action.SOUTH] * 3):
+        if actions is not None:
+            layered_obs = base.step(actions).obs
+            perspective_obs = persp.step(actions).obs
+            positions = [(i + 1, j) for i, j in positions]
+        assert perspective_obs.shape == (3, 10, 5, 3)
+        for observer, position in enumerate(positions):
+            expected = np.copy(layered_obs[observer])
+            expected[[A0, A0 + observer]] = expected[[A0 + observer, A0]]
+            expected[[L0, L0 + observer]] = expected[[L0 + observer, L0]]
+            np.testing.assert_array_equal(perspective_obs[observer], expected)
+            assert perspective_obs[observer, A0, position[0], position[1]] == 1.0
+
+
+def test_all_observation_shapes(api):  # [O] test_all_shapes for the generators on the accelerated path
+    expect = {"layered": lambda A, G: (2 * A + 4, 12, 13), "flattened": lambda A, G: ((2 * A + 4) * 12 * 13,),
+              "partial3x3": lambda A, G: (2 * A + 3, 3, 3), "partial5x5": lambda A, G: (2 * A + 3, 5, 5),
+              "partial7x7": lambda A, G: (2 * A + 3, 7, 7), "state": lambda A, G: (3 * A + G,),
+              "normalized-state": lambda A, G: (3 * A + G,), "perspective": lambda A, G: (2 * A + 4, 12, 13),
+              "layered-padded-1": lambda A, G: (2 * A + 6, 12, 13), "layered-padded-2": lambda A, G: (2 * A + 8, 12, 13),
+              "layered-padded-3": lambda A, G: (2 * A + 10, 12, 13)}
+    for level in (1, 3, 6):
+        for name, shape in expect.items():
+            env = api.LLE.level(level, obs_type=name)
+            obs, _ = env.reset()
+            A, G = env.n_agents, env.n_gems
+            pad = int(name[-1]) if name.startswith("layered-padded-") else 0
+            assert obs.shape == (A + pad, *shape(A, G)), (level, name, obs.shape)
+
+
+def test_unknown_observation_type(api):
+    with pytest.raises(ValueError):
+        api.LLE("S0 X", obs_type="nope")
