@@ -294,6 +294,16 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
     h.patch_off = (uint32_t)off;   off = align16(off + std::max<size_t>(patch.size(), 1) * sizeof(LlePatch));
     h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
     h.ap_off = (uint32_t)off;      off = align16(off + std::max<size_t>(planes.size(), 1) * sizeof(LleAgentPlane));
+    std::vector<uint32_t> chunk_tbl;  // patches are sorted by idx: chunk c owns entries [tbl[c], tbl[c+1])
+    {
+        const int n_chunks = (obs_floats + LLE_CHUNK_FLOATS - 1) / LLE_CHUNK_FLOATS;
+        size_t k = 0;
+        for (int c = 0; c <= n_chunks; ++c) {
+            while (k < patch.size() && patch[k].idx < (uint32_t)c * LLE_CHUNK_FLOATS) ++k;
+            chunk_tbl.push_back((uint32_t)k);
+        }
+    }
+    h.chunk_tbl_off = (uint32_t)off; off = align16(off + chunk_tbl.size() * sizeof(uint32_t));
     h.blob_bytes = (uint32_t)off;
     h.gem_toplevel = 0;
     for (int g = 0; g < G; ++g) {
@@ -339,6 +349,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
                     if (src.pos.i == i && src.pos.j == j) info[c] |= (1u << 7) | ((uint32_t)src.colour << 16);
                 for (int n = 0; n < 4; ++n) cb[c].e[n] = LLE_NO_BEAM;
                 const auto& lst = cell_beams[c];
+                if (!lst.empty()) info[c] |= 1u << 24;
                 if (lst.size() > 4) throw MapError(LLE_LIMIT_EXCEEDED, "more than four beams cross one cell");
                 for (size_t n = 0; n < lst.size(); ++n) {
                     const int b = lst[n].first, k = lst[n].second;
@@ -354,6 +365,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
     }
     if (!patch.empty()) std::memcpy(cm.blob.data() + h.patch_off, patch.data(), patch.size() * sizeof(LlePatch));
     std::memcpy(cm.blob.data() + h.static_off, stat.data(), stat.size() * sizeof(float));
+    std::memcpy(cm.blob.data() + h.chunk_tbl_off, chunk_tbl.data(), chunk_tbl.size() * sizeof(uint32_t));
     if (!planes.empty()) std::memcpy(cm.blob.data() + h.ap_off, planes.data(), planes.size() * sizeof(LleAgentPlane));
     return cm;
 }

@@ -57,12 +57,15 @@ struct LleAgentPlane {
 // Per-cell lookup tables used by the step kernel (one load each instead of a scan over all beams):
 //   cellinfo[cell]  : bits 0-2 base tile kind | bits 3-6 walkable-neighbour mask indexed by Action value
 //                     (N, S, E, W: in bounds and neither Wall nor LaserSource, tile.rs:63-73) | bit 7: the cell is a
-//                     laser source | bits 8-15 gem index | bits 16-23 colour of the source (bit 7 set)
+//                     laser source | bits 8-15 gem index | bits 16-23 colour of the source (bit 7 set) | bit 24: a beam crosses the cell
 //   cellbeams[cell] : the (at most four: one per direction of travel) beams crossing the cell, inner first.
 //                     entry = b (0-5) | k<<6 (6-11) | colour<<12 (12-19) | len<<20 (20-26) | enabled<<27 | listed<<28
 //                     (listed: the laser tile is one of the two reported by World::lasers(), world.rs:159-172);
 //                     0xFFFFFFFF = no entry.
 #define LLE_NO_BEAM 0xFFFFFFFFu
+// Observation blocks larger than a shared-memory tile are streamed in chunks of this many floats (12 KB).  The map
+// blob carries, per chunk, the first patch entry (sorted by float index) that falls into it.
+#define LLE_CHUNK_FLOATS 3072
 struct LleCellBeams {
     uint32_t e[4];
 };
@@ -86,6 +89,8 @@ struct LleMapHeader {
     int32_t obs_c, obs_h, obs_w;   // shape of ONE agent's observation (state: obs_c = length, obs_h = obs_w = 0)
     int32_t n_ap;                  // entries of the agent-plane table
     uint32_t ap_off;               // LleAgentPlane[n_ap]
+    uint32_t chunk_tbl_off;        // uint32_t[ceil(obs_floats / LLE_CHUNK_FLOATS) + 1]: patch index range of every chunk
+    uint32_t pad1;
     uint16_t start[LLE_MAX_AGENTS];   // packed position (i<<8 | j)
     uint16_t gem_pos[LLE_MAX_GEMS];   // packed position, gems_positions order (parser_v1.rs:149)
 };

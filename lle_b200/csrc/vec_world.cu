@@ -428,7 +428,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->n_buf = 1;
     } else {
         v->E = 1;
-        v->chunk_floats = 3072;  // 12 KB chunks
+        v->chunk_floats = LLE_CHUNK_FLOATS;  // 12 KB chunks
         v->n_chunks = (int)((stride + v->chunk_floats - 1) / v->chunk_floats);
         v->tile_floats = v->chunk_floats;
         v->group = std::max(8, 32 / v->Wd);

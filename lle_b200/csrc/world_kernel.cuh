@@ -138,6 +138,7 @@ struct MapDev {
     const LlePatch* patches;
     const float* stat;
     const LleAgentPlane* agent_planes;
+    const uint32_t* chunk_tbl;
     int n_patch, NB, obs_floats, n_ap;
     uint64_t gem_toplevel;
     __device__ __forceinline__ void bind(const uint8_t* b) {
@@ -150,6 +151,7 @@ struct MapDev {
         stat = reinterpret_cast<const float*>(b + hdr->static_off);
         agent_planes = reinterpret_cast<const LleAgentPlane*>(b + hdr->ap_off);
         n_ap = hdr->n_ap;
+        chunk_tbl = reinterpret_cast<const uint32_t*>(b + hdr->chunk_tbl_off);
         n_patch = hdr->n_patch;
         NB = hdr->NB;
         obs_floats = hdr->obs_floats;
@@ -1022,6 +1024,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             // agents, WALL, lasers, GEM, EXIT.  One lane per (agent, window cell): it looks the map cell up once and
             // writes the few non-zero channels into a zero-filled tile, which leaves with one bulk store per E worlds.
             const int sz = p.obs_param, s2 = sz * sz, ctr = sz >> 1, Cp = 2 * A + 3;
+            const float inv_s2 = 1.0f / (float)s2, inv_sz = 1.0f / (float)sz;
             const int n_tiles = p.group / p.E, tile_len = p.E * (int)p.obs_stride;
             for (int tix = 0; tix < n_tiles; ++tix) {
                 float* tile = tiles + (size_t)buf * p.tile_floats;
@@ -1042,13 +1045,16 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     const uint32_t* cur = recs + (size_t)g * stride;
                     float* sub = tile + (size_t)s * p.obs_stride;
                     for (int q = lane; q < A * s2; q += 32) {
-                        const int a = q / s2, r = q - a * s2, wi = r / sz, wj = r - wi * sz;
+                        // (agent, row, column) of the window cell; the float products are exact for these small integers
+                        const int a = (int)(((float)q + 0.5f) * inv_s2), r = q - a * s2;
+                        const int wi = (int)(((float)r + 0.5f) * inv_sz), wj = r - wi * sz;
                         const uint32_t pa = rec_pos(cur, a);
                         const int i = (int)(pa >> 8) + wi - ctr, j = (int)(pa & 0xFFu) + wj - ctr;
                         if (i < 0 || j < 0 || i >= p.H || j >= p.W) continue;  // outside the map: all layers stay 0 (:325-329)
-                        float* o = sub + a * Cp * s2 + r;
                         const int c = i * p.W + j;
                         const uint32_t info = rm.cellinfo[c];
+                        if (!(info & (7u | (1u << 24)))) continue;  // plain floor, no beam: nothing but agents (below)
+                        float* o = sub + a * Cp * s2 + r;
                         const uint32_t kind = info & 7u;
                         if (kind == LLE_T_WALL) {
                             o[A * s2] = 1.0f;  // WALL = n_agents; wall_pos includes the sources (parser_v1.rs:22-25)
@@ -1062,20 +1068,26 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                             const uint32_t gi = (info >> 8) & 63u;
                             if (!((cur[L.w_gems + (gi >> 5)] >> (gi & 31u)) & 1u)) o[(2 * A + 1) * s2] = 1.0f;
                         }
-                        const LleCellBeams cb = rm.cellbeams[c];
+                        if (info & (1u << 24)) {
+                            const LleCellBeams cb = rm.cellbeams[c];
 #pragma unroll
-                        for (int n = 0; n < 4; ++n) {  // lit lasers listed by World::lasers (:352-360)
-                            const uint32_t e = cb.e[n];
-                            if (e == LLE_NO_BEAM) break;
-                            const int k = be_k(e);
-                            if (be_listed(e) && ((cur[L.w_on + be_b(e) * L.on_words + (k >> 5)] >> (k & 31)) & 1u)) {
-                                const int ch = A + 1 + be_colour(e);
-                                if (ch < Cp) o[ch * s2] = 1.0f;
+                            for (int n = 0; n < 4; ++n) {  // lit lasers listed by World::lasers (:352-360)
+                                const uint32_t e = cb.e[n];
+                                if (e == LLE_NO_BEAM) break;
+                                const int k = be_k(e);
+                                if (be_listed(e) && ((cur[L.w_on + be_b(e) * L.on_words + (k >> 5)] >> (k & 31)) & 1u)) {
+                                    const int ch = A + 1 + be_colour(e);
+                                    if (ch < Cp) o[ch * s2] = 1.0f;
+                                }
                             }
                         }
-                        const uint32_t here = ((uint32_t)i << 8) | (uint32_t)j;
-                        for (int a2 = 0; a2 < A; ++a2)
-                            if (rec_pos(cur, a2) == here) o[a2 * s2] = 1.0f;
+                    }
+                    // agent layers (:335-336): agent a2 as seen from agent a, for the A*A ordered pairs
+                    for (int t = lane; t < A * A; t += 32) {
+                        const int a = t / A, a2 = t - a * A;
+                        const uint32_t pa = rec_pos(cur, a), pb = rec_pos(cur, a2);
+                        const int di = (int)(pb >> 8) - (int)(pa >> 8) + ctr, dj = (int)(pb & 0xFFu) - (int)(pa & 0xFFu) + ctr;
+                        if (di >= 0 && dj >= 0 && di < sz && dj < sz) sub[(a * Cp + a2) * s2 + di * sz + dj] = 1.0f;
                     }
                 }
                 fence_proxy_async_smem();
@@ -1121,10 +1133,15 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     const uint32_t* cur = recs + (size_t)g * stride;
                     const int slot_id = buf * p.E + s;
                     const bool same = tags[slot_id] == mid && tags[p.n_buf * p.E + buf] == chunk;
+                    // Patch entries of this tile.  Whole worlds: the first 64 live in registers (pc), the rest is scanned.
+                    // Chunks: the entries are sorted by float index and the map gives each chunk's range, so a chunk only
+                    // visits its own (a 64x64 map has hundreds of entries and dozens of chunks).
+                    const int k_begin = whole ? 64 : (int)__ldg(rm.chunk_tbl + chunk);
+                    const int k_end = whole ? rm.n_patch : (int)__ldg(rm.chunk_tbl + chunk + 1);
                     // what this world lights: laser cells whose beam bit is on, uncollected gems (observations.py:256-263)
-                    const bool now0 = pc.valid0 && pc.lit0(cur), now1 = pc.valid1 && pc.lit1(cur);
-                    const bool in0 = whole || ((int)pc.idx0 >= lo && (int)pc.idx0 < hi);
-                    const bool in1 = whole || ((int)pc.idx1 >= lo && (int)pc.idx1 < hi);
+                    const bool v0 = whole && pc.valid0, v1 = whole && pc.valid1;
+                    const bool now0 = v0 && pc.lit0(cur), now1 = v1 && pc.lit1(cur);
+                    const bool in0 = whole, in1 = whole;
                     if (!same) {
                         tile_rebuild_async(sub_tile, rm, lo, hi, lane);
                         cp_async_wait_all();
@@ -1138,12 +1155,11 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                             const int idx = (int)ap.base + (int)(op >> 8) * p.W + (int)(op & 0xFFu);
                             if (whole || (idx >= lo && idx < hi)) sub_tile[idx - lo] = 0.0f;  // agent planes have no static content
                         }
-                        if (pc.valid0 && in0 && pc.lit0(old) && !now0) sub_tile[pc.idx0 - lo] = pc.stat0;
-                        if (pc.valid1 && in1 && pc.lit1(old) && !now1) sub_tile[pc.idx1 - lo] = pc.stat1;
-                        for (int k = 64 + lane; k < rm.n_patch; k += 32) {
+                        if (v0 && in0 && pc.lit0(old) && !now0) sub_tile[pc.idx0 - lo] = pc.stat0;
+                        if (v1 && in1 && pc.lit1(old) && !now1) sub_tile[pc.idx1 - lo] = pc.stat1;
+                        for (int k = k_begin + lane; k < k_end; k += 32) {
                             const LlePatch pe = rm.patches[k];
-                            if ((whole || ((int)pe.idx >= lo && (int)pe.idx < hi)) && rec_lit(old, L, pe) && !rec_lit(cur, L, pe))
-                                sub_tile[pe.idx - lo] = (float)pe.stat;
+                            if (rec_lit(old, L, pe) && !rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = (float)pe.stat;
                         }
                     }
                     __syncwarp();
@@ -1151,9 +1167,9 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     // colours >= n_agents) stay correct whatever was un-patched above; then the agents (observations.py:264-265).
                     if (now0 && in0) sub_tile[pc.idx0 - lo] = 1.0f;
                     if (now1 && in1) sub_tile[pc.idx1 - lo] = 1.0f;
-                    for (int k = 64 + lane; k < rm.n_patch; k += 32) {
+                    for (int k = k_begin + lane; k < k_end; k += 32) {
                         const LlePatch pe = rm.patches[k];
-                        if ((whole || ((int)pe.idx >= lo && (int)pe.idx < hi)) && rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = 1.0f;
+                        if (rec_lit(cur, L, pe)) sub_tile[pe.idx - lo] = 1.0f;
                     }
                     for (int k = lane; k < rm.n_ap; k += 32) {
                         const LleAgentPlane ap = rm.agent_planes[k];

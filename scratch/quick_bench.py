@@ -11,6 +11,7 @@ ap.add_argument("--steps", type=int, default=2000)
 ap.add_argument("--no-obs", action="store_true")
 ap.add_argument("--map", type=str, default=None)
 ap.add_argument("--rollout", type=int, default=0)
+ap.add_argument("--obs-type", type=str, default="layered")
 ap.add_argument("--sync", action="store_true", help="synchronise after every step (isolated launches)")
 args = ap.parse_args()
 moe = None
@@ -26,7 +27,7 @@ elif args.map == "synthetic":
     maps = lle_b200.Map(synthetic_map(64, 64, 8, 16, seed=5))
 else:
     maps = lle_b200.Map(level=args.level)
-vec = lle_b200.VecWorld(maps, args.envs, seed=1, write_obs=not args.no_obs, map_of_env=moe)
+vec = lle_b200.VecWorld(maps, args.envs, seed=1, write_obs=not args.no_obs, map_of_env=moe, obs_type=args.obs_type)
 for _ in range(50):
     vec.step(None)
 vec.synchronize()
@@ -43,6 +44,6 @@ else:
             vec.synchronize()
     ms, n = vec.timing_end()
 us = ms * 1e3 / n
-obs_bytes = vec.n_channels * vec.height * vec.width * 4 * args.envs
-print(json.dumps({"level": args.map or args.level, "envs": args.envs, "obs": not args.no_obs, "rollout": args.rollout, "us_per_step": round(us, 2),
+obs_bytes = (vec.obs[0].numel() if vec.obs is not None else 0) * 4 * args.envs
+print(json.dumps({"level": args.map or args.level, "obs_type": args.obs_type, "envs": args.envs, "obs": not args.no_obs, "rollout": args.rollout, "us_per_step": round(us, 2),
                   "env_steps_per_s": round(args.envs / (us * 1e-6)), "obs_GBps": round(obs_bytes / (us * 1e-6) / 1e9, 1)}))
