@@ -215,7 +215,7 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     vec.reset()
     vec.step_count = 10_000_000
-    D = max(1, min(4, args.e2e_depth))
+    D = max(1, min(8, args.e2e_depth))
     reward_h = [torch.empty((n_envs, R), dtype=torch.float32).pin_memory() for _ in range(D)]
     done_h = [torch.empty((n_envs,), dtype=torch.uint8).pin_memory() for _ in range(D)]
 
@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2048)
-    ap.add_argument("--e2e-depth", type=int, default=2, help="steps in flight in the pipelined end-to-end arm (1..4)")
+    ap.add_argument("--e2e-depth", type=int, default=8, help="steps in flight in the pipelined end-to-end arm (1..8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

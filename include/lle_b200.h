@@ -210,7 +210,7 @@ LLE_API int lle_vec_step_host(lle_vec* vec, const int8_t* actions_host, float* r
  * lle_vec_pipeline_submit enqueues (1) the copy of `actions_host` (pinned i8[N,A]; NULL = device sampling) on a copy
  * stream, (2) the fused step on the vec's own compute stream, which waits for the actions inside the kernel, and (3) the
  * copy of reward / done (pinned f32[N,reward_dim] / u8[N]) to the host on a third stream, and returns at once.
- * lle_vec_pipeline_wait blocks until the OLDEST submitted step's results are in its host buffers.  Up to 4 steps may be
+ * lle_vec_pipeline_wait blocks until the OLDEST submitted step's results are in its host buffers.  Up to 8 steps may be
  * outstanding; with two or more, the copies of one step overlap the kernels of its neighbours and consecutive step
  * kernels stay back to back (programmatic dependent launch), so a host-driven loop runs at the device rate.
  * The first submit after the pipeline was empty is ordered after the work already in `after_stream`; no other call

@@ -76,6 +76,7 @@ struct lle_vec {
     // launch configuration
     bool fast = false, pdl = true;
     bool force_narrow = false;  // LLE_B200_FORCE_NARROW=1 (tests)
+    uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
     int grid = 0, grid_step = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
     size_t smem = 0;
@@ -84,13 +85,13 @@ struct lle_vec {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t timing_launches0 = 0;
     // pipelined host stepping (lle_vec_pipeline_submit / _wait): three streams, a ring of staging slots
-    static constexpr int kPipeSlots = 4;
+    static constexpr int kPipeSlots = 8;
     bool pipe_ready = false;
     cudaStream_t s_in = nullptr, s_main = nullptr, s_out = nullptr, last_stream = nullptr;
-    cudaEvent_t ev_user = nullptr, ev_out[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
-    int8_t* d_stage[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
-    float* d_reward_ring[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
-    uint8_t* d_done_ring[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_user = nullptr, ev_out[kPipeSlots] = {};
+    int8_t* d_stage[kPipeSlots] = {};
+    float* d_reward_ring[kPipeSlots] = {};
+    uint8_t* d_done_ring[kPipeSlots] = {};
     uint32_t* d_pipe_flags = nullptr;  // [0] actions of submit n have landed, [1] submit n has retired
     uint64_t pipe_submitted = 0, pipe_completed = 0;
 };
@@ -132,6 +133,13 @@ cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
     switch (p.mode) {
         case MODE_STEP:
             p.seq = v->seq + 1;  // sequence number of the first step of this launch
+            p.retired_seq = v->h_retired_seq;
+            // Narrow-grid software pipelining pays only when several step launches are queued behind one another (a
+            // free-running device loop, or a host pipeline six or more deep): four consecutive launches are then resident
+            // together and more wait behind them.  With fewer in flight (synchronous stepping, a shallow pipeline) the
+            // device would idle between narrow launches, so the full-width grid is used (measured, e2e env-steps/s at
+            // pipeline depth 2/4/6/8: 7.9e8 / 6.2e8 with narrow grids at depth 4 / 8.4e8 / 8.4e8).
+            v->narrow_next = v->force_narrow || (int32_t)(v->seq - *(volatile uint32_t*)v->h_retired_seq) >= 5;
             e = launch_mode<MODE_STEP>(v, p, s);
             v->seq += (uint32_t)p.n_steps;
             v->last_was_step = true;
@@ -329,6 +337,7 @@ int lle_vec_destroy(lle_vec* v) {
         if (v->ev_out[k]) cudaEventDestroy(v->ev_out[k]);
     }
     cudaFree(v->d_pipe_flags);
+    if (v->h_retired_seq) cudaFreeHost(v->h_retired_seq);
     if (v->ev_user) cudaEventDestroy(v->ev_user);
     if (v->s_in) cudaStreamDestroy(v->s_in);
     if (v->s_main) cudaStreamDestroy(v->s_main);
@@ -512,6 +521,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (v->JE) LLE_CUDA(dalloc(&v->d_extras, (size_t)v->A * v->JE * Np));
     LLE_CUDA(dalloc(&v->d_sched, 2 * kSchedSlots));
     LLE_CUDA(dalloc(&v->d_flags, (size_t)(v->N_pad / v->group)));
+    LLE_CUDA(cudaHostAlloc((void**)&v->h_retired_seq, sizeof(uint32_t), cudaHostAllocMapped));
+    *v->h_retired_seq = 0;
     LLE_CUDA(dalloc(&v->d_actions_stage, (size_t)v->A * Np));
     if (env_int("LLE_B200_TIMELINE", 0)) LLE_CUDA(dalloc(&v->d_timeline, (size_t)v->grid * kWarps * 4));
     LLE_CUDA(cudaEventCreate(&v->ev0));
@@ -563,10 +574,6 @@ int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
     KParams p = base_params(v);
     p.mode = MODE_STEP;
     p.actions_in = actions_dev;
-    // Narrow-grid software pipelining only pays when the previous step is still in flight; an isolated step (the caller
-    // synchronised in between) gets the full-width grid.
-    v->narrow_next = v->last_was_step && v->last_stream == (cudaStream_t)stream &&
-                     (v->force_narrow || cudaStreamQuery((cudaStream_t)stream) == cudaErrorNotReady);
     LLE_CUDA(launch(v, p, (cudaStream_t)stream));
     v->launches++;
     v->t++;
@@ -645,7 +652,6 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
     p.out_value = n;
     p.reward2 = v->d_reward_ring[slot];
     p.done2 = v->d_done_ring[slot];
-    v->narrow_next = v->pipe_submitted - v->pipe_completed > 1;  // an earlier submit is still in flight
     LLE_CUDA(launch(v, p, v->s_main));
     v->launches++;
     v->t++;

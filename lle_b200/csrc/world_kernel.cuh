@@ -105,6 +105,9 @@ struct KParams {
     uint32_t* out_flag;
     float* reward2;
     uint8_t* done2;
+    // host-mapped word that receives the sequence number of the last step of this launch when the launch retires: lets the
+    // host see how many step launches are still in flight (a scheduling hint only, see launch_mode in vec_world.cu)
+    volatile uint32_t* retired_seq;
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -1219,6 +1222,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             p.sched[0] = 0;
             p.sched[1] = 0;
             __threadfence();
+            if (MODE == MODE_STEP && p.retired_seq) *p.retired_seq = p.seq + (uint32_t)p.n_steps - 1u;
             if (p.out_flag) {
                 // every warp fenced its writes before its increment above; publish the launch to the copy stream that
                 // waits on the flag (max: an overlapped later launch may retire first, and implies this one's tickets)

@@ -1,0 +1,43 @@
+"""Joins the per-instruction counters of an ncu report (SASS source page) with nvdisasm's line info of the same kernel,
+and prints the instruction / stall-sample share per source line (development aid).
+Usage: python scratch/ncu_lines.py report.ncu-rep mangled_kernel_substring [top_n]"""
+import collections, csv, os, re, subprocess, sys, tempfile
+
+rep, kern = sys.argv[1], sys.argv[2]
+top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "lle_b200", "_native", "liblle_b200.so")], cwd=tmp, capture_output=True)
+cubin = [f for f in os.listdir(tmp) if f.startswith("vec_world")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+lines_of = []  # program order: (offset, line, text)
+inside, cur = False, None
+for ln in dis:
+    if ln.startswith("\t.section\t.text."):
+        inside = kern in ln
+        continue
+    if not inside:
+        continue
+    m = re.search(r'//## File ".*?", line (\d+)', ln)
+    if m:
+        cur = int(m.group(1))
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+    if m:
+        lines_of.append((int(m.group(1), 16), cur, m.group(2).strip()))
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h = rows[1]
+ie, sm = h.index("Instructions Executed"), h.index("# Samples")
+data = rows[2:]
+assert len(data) == len(lines_of), (len(data), len(lines_of))
+src = open(os.path.join(root, "lle_b200", "csrc", "world_kernel.cuh")).read().splitlines()
+inst, samp = collections.Counter(), collections.Counter()
+for r, (off, line, text) in zip(data, lines_of):
+    inst[line] += float(r[ie] or 0)
+    samp[line] += float(r[sm] or 0)
+ti, ts = sum(inst.values()), sum(samp.values())
+print(f"total warp instructions {ti:.0f}, samples {ts:.0f}")
+print("line   instr%  stall%  source")
+for line, v in sorted(inst.items(), key=lambda x: -(x[1] / ti + samp[x[0]] / ts))[:top_n]:
+    print(f"{line:5d}  {v / ti * 100:5.1f}  {samp[line] / ts * 100:5.1f}   {src[line - 1].strip()[:120] if line else ''}")

@@ -158,9 +158,9 @@ def test_supplied_actions_with_invalid_ones():
 
 
 def test_pipelined_host_stepping():
-    """lle_vec_pipeline_submit / _wait: host actions in, reward + done out, up to 4 steps in flight; every step's host
+    """lle_vec_pipeline_submit / _wait: host actions in, reward + done out, up to 8 steps in flight; every step's host
     results and the final device buffers equal the oracle's."""
-    for depth, n, level in ((1, 100, 5), (2, 1000, 6), (4, 333, 6)):
+    for depth, n, level in ((1, 100, 5), (2, 1000, 6), (4, 333, 6), (8, 4096, 6)):
         ora, dev = make_pair([level_text(level)], None, n, seed=40 + depth)
         vec = dev.vec
         steps = 60
