@@ -641,7 +641,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 
 #ifndef LLE_MIN_CTAS
-#define LLE_MIN_CTAS 4
+#define LLE_MIN_CTAS 5
 #endif
 // MODE: MODE_STEP / MODE_RESET / MODE_SET_STATE, compiled separately so the step kernel carries no set_state code.
 // FAST: the common shape — one map for the whole batch, one whole world per tile, a single tile buffer, at most 64
