@@ -744,6 +744,12 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         }
         const int64_t env0 = (int64_t)ticket * p.group;
         const uint64_t t_now = p.t + (uint64_t)step_index;
+        {   // the ticket's records (contiguous, group x stride words) start moving into shared memory now, through L2 only
+            // (rollout mode re-reads its own writes); the first pass below waits for them, later passes find them there
+            const uint32_t* gsrc = p.records + env0 * stride;
+            for (int k = lane * 4; k < p.group * stride; k += 128) cp_async16(recs + k, gsrc + k);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         if (!FAST && first && p.write_obs && p.n_chunks == 1 && p.obs_kind != LLE_OBS_PARTIAL) {
             // start filling this warp's tiles from the static plane of the first world's map now: the copies land
             // while the first logic pass runs
@@ -775,9 +781,10 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 if (gl == 0) map_ids[g] = map_id;
             }
             uint32_t* rec = recs + (size_t)g * stride;
-            const uint32_t* grec = p.records + env * stride;
-            for (int k = gl; k < stride; k += Wd) rec[k] = __ldcg(grec + k);  // L2 only: rollout mode re-reads its own writes
-            __syncwarp();
+            if (g0 == 0) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
             w.rec = rec;
             w.unpack();
 
@@ -963,7 +970,58 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     tile_fresh = false;
                     __syncwarp();
                 }
-                for (int s = 0; s < p.E; ++s) {
+                // Tiles that hold several (tiny) worlds: patch all sub-tiles at once, 32/E lanes per world, when they share
+                // one map and already hold its static plane (always, after the first tile, for single-map batches and for
+                // batches laid out map by map).  Otherwise fall through to the world-by-world path below.
+                bool parallel = false;
+                if (p.E > 1) {
+                    const int Pr = 32 / p.E, s = lane / Pr, e = lane - s * Pr;
+                    const int g = tix * p.E + s;
+                    const int mid = multi ? map_ids[g] : 0;
+                    const int mid0 = __shfl_sync(kFull, mid, 0);
+                    parallel = __all_sync(kFull, mid == mid0);
+                    if (parallel) {
+                        if (mid0 != render_map) {
+                            rm.bind(p.blobs[mid0]);
+                            render_map = mid0;
+                            pc.load(rm, L, lane);
+                        }
+                        if (__any_sync(kFull, tags[s] != mid0)) {  // another map: every sub-tile starts from its static plane
+                            for (int t = 0; t < p.E; ++t) tile_rebuild_async(tiles + (size_t)t * p.obs_stride, rm, 0, (int)p.obs_stride, lane);
+                            cp_async_wait_all();
+                            __syncwarp();
+                            if (lane < p.E) tags[lane] = mid0;
+                            fresh_bits |= p.E >= 32 ? ~0u : ((1u << p.E) - 1u);
+                            __syncwarp();
+                        }
+                        const uint32_t* cur = recs + (size_t)g * stride;
+                        const uint32_t* old = applied + (size_t)s * stride;
+                        float* sub = tiles + (size_t)s * p.obs_stride;
+                        if (!((fresh_bits >> s) & 1u)) {  // un-patch what the previous occupant had lit and this one has not
+                            for (int k = e; k < rm.n_patch; k += Pr) {
+                                const LlePatch pe = rm.patches[k];
+                                if (rec_lit(old, L, pe) && !rec_lit(cur, L, pe)) sub[pe.idx] = (float)pe.stat;
+                            }
+                            for (int a = e; a < A; a += Pr) {
+                                const uint32_t op = rec_pos(old, a);
+                                sub[a * p.HW + (int)(op >> 8) * p.W + (int)(op & 0xFFu)] = 0.0f;
+                            }
+                        }
+                        fresh_bits &= ~(p.E >= 32 ? ~0u : ((1u << p.E) - 1u));
+                        __syncwarp();
+                        for (int k = e; k < rm.n_patch; k += Pr) {  // every lit entry is rewritten (aliasing entries, see below)
+                            const LlePatch pe = rm.patches[k];
+                            if (rec_lit(cur, L, pe)) sub[pe.idx] = 1.0f;
+                        }
+                        for (int a = e; a < A; a += Pr) {
+                            const uint32_t np = rec_pos(cur, a);
+                            sub[a * p.HW + (int)(np >> 8) * p.W + (int)(np & 0xFFu)] = 1.0f;
+                        }
+                        // the tile now shows worlds [tix*E, tix*E + E) of the group: their records are contiguous
+                        for (int k = lane; k < p.E * stride; k += 32) applied[k] = recs[(size_t)tix * p.E * stride + k];
+                    }
+                }
+                for (int s = 0; s < (parallel ? 0 : p.E); ++s) {
                     const int g = tix * p.E + s;
                     const uint32_t* cur = recs + (size_t)g * stride;
                     float* sub = tiles + (size_t)s * p.obs_stride;
