@@ -218,6 +218,17 @@ LLE_API int lle_vec_step_host(lle_vec* vec, const int8_t* actions_host, float* r
 LLE_API int lle_vec_pipeline_submit(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream);
 LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
 
+/* Laser-source mutators for every env that uses map `map_index` (index into the maps given to lle_vec_create):
+ * LaserBeam::set_agent_id / enable / disable (src/core/tiles/laser.rs:69-84, exposed as PyLaserSource.agent_id / set_colour /
+ * enable / disable, src/bindings/tiles/pylaser_source.rs:55-142).  agent_id < 0 keeps the colour, enabled < 0 keeps the
+ * switch.  Disabling turns the whole beam off, enabling turns the whole beam on (turn_on(0): whoever stands in it), and
+ * both survive World::reset (laser.rs:168-171).  The colour is NOT checked against n_agents here (the engine does not,
+ * world_config.rs:137-145; the Python setter does).  Observation / state / availability buffers keep showing the last
+ * step until the next step or reset (lle_vec_reset with an all-zero mask re-exports every env without resetting any).
+ * Synchronises `cuda_stream`.  lle_vec_get_sources: current (agent_id, enabled) pairs of the map's sources. */
+LLE_API int lle_vec_set_source(lle_vec* vec, int32_t map_index, int32_t source_index, int32_t agent_id, int32_t enabled, void* cuda_stream);
+LLE_API int lle_vec_get_sources(lle_vec* vec, int32_t map_index, int32_t* out_pairs, int32_t cap, int32_t* n);
+
 /* World::set_state / LLE.set_state (world.rs:515-597, env.py:208-216) for every env.
  *   pos_dev i32[N,A,2], gems_dev u8[N,G], alive_dev u8[N,A] (device).  Per-env failures are reported in err. */
 LLE_API int lle_vec_set_state(lle_vec* vec, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* cuda_stream);

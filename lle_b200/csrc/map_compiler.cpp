@@ -35,7 +35,7 @@ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 }  // namespace
 
-CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std::vector<SourceState>* source_state) {
     if (spec.kind < LLE_OBS_LAYERED || spec.kind > LLE_OBS_STATE) throw MapError(LLE_INVALID_ARGUMENT, "unknown observation kind");
     if (spec.kind == LLE_OBS_LAYERED && (spec.param < 0 || spec.param > 64)) throw MapError(LLE_INVALID_ARGUMENT, "padding_size out of range");
     if (spec.kind == LLE_OBS_PARTIAL && (spec.param < 1 || spec.param % 2 != 1 || spec.param > 31))
@@ -181,6 +181,14 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
         cm.max_beam_len = std::max(cm.max_beam_len, s.len);
     }
     cm.H = H; cm.W = W; cm.A = A; cm.G = G; cm.NB = NB;
+    if (source_state) {  // mutated after construction: colours and enabled flags as they are now
+        if ((int)source_state->size() != NB) throw MapError(LLE_INVALID_ARGUMENT, "source state does not match the map");
+        for (int b = 0; b < NB; ++b) {
+            if ((*source_state)[b].colour < 0 || (*source_state)[b].colour > 254) throw MapError(LLE_LIMIT_EXCEEDED, "laser colour out of range");
+            cm.sources[b].colour = (*source_state)[b].colour;
+            cm.sources[b].enabled = (*source_state)[b].enabled;
+        }
+    }
     // channel layout (observations.py:199-211): the agent count of the layout includes the padding budget
     const int Ap = A + (spec.kind == LLE_OBS_LAYERED ? spec.param : 0);
     const int C = 2 * Ap + 4;
@@ -326,7 +334,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
         bm.dj = (int8_t)DJ[s.direction];
         bm.len = (uint8_t)s.len;
         bm.colour = (uint8_t)s.colour;
-        bm.enabled = 1;
+        bm.enabled = s.enabled ? 1 : 0;
         bm.src_i = (uint8_t)s.pos.i;
         bm.src_j = (uint8_t)s.pos.j;
         std::memcpy(cm.blob.data() + h.beams_off + b * sizeof(LleBeam), &bm, sizeof bm);
@@ -356,7 +364,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec) {
                     const auto& src = cm.sources[b];
                     const uint32_t listed = (vis[b] >> k) & 1ull;
                     cb[c].e[n] = (uint32_t)b | ((uint32_t)k << 6) | ((uint32_t)src.colour << 12) | ((uint32_t)src.len << 20) |
-                                 (1u << 27) | (listed << 28);
+                                 ((src.enabled ? 1u : 0u) << 27) | (listed << 28);
                 }
             }
         }

@@ -61,6 +61,13 @@ struct ObsSpec {
     bool operator==(const ObsSpec& o) const { return kind == o.kind && param == o.param; }
 };
 
-CompiledMap compile_map(const std::string& text, const ObsSpec& spec = ObsSpec());
+// State of a laser source after the world was built: LaserBeam::{set_agent_id, enable, disable} (src/core/tiles/laser.rs:69-84).
+// The start pruning of laser_setup (world_config.rs:225-243) is a build-time step and keeps using the colours of the text.
+struct SourceState {
+    int colour;
+    bool enabled;
+};
+
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec = ObsSpec(), const std::vector<SourceState>* sources = nullptr);
 
 }  // namespace lle

@@ -46,6 +46,11 @@ struct lle_vec {
     LleStateLayout L;
     // device memory
     std::vector<CompiledMap> own_maps;  // maps recompiled for a non-default observation type
+    // laser sources can be recoloured / switched after creation (lle_vec_set_source): what is needed to recompile a map
+    std::vector<std::string> map_texts;
+    std::vector<std::vector<SourceState>> src_state;
+    std::vector<int> map_patches, map_obs_invalid;
+    std::vector<uint8_t*> retired_blobs;
     bool render = true;
     LleMapHeader hdr0;  // header of the first map (observation shape)
     int obs_invalid = 0;
@@ -329,6 +334,7 @@ int lle_vec_destroy(lle_vec* v) {
     if (!v) return LLE_OK;
     cudaSetDevice(v->device);
     for (auto* b : v->d_blobs) cudaFree(b);
+    for (auto* b : v->retired_blobs) cudaFree(b);
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
     cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline); cudaFree(v->d_extras);
@@ -378,6 +384,12 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
             return fail(LLE_INVALID_ARGUMENT, "all maps of a vec must share (height, width, n_agents, n_gems)");
         v->NBmax = std::max(v->NBmax, m.NB);
         if (m.header().obs_invalid) v->obs_invalid = 1;
+        v->map_texts.push_back(m.text);
+        std::vector<SourceState> st;
+        for (const auto& src : m.sources) st.push_back(SourceState{src.colour, src.enabled});
+        v->src_state.push_back(st);
+        v->map_patches.push_back((int)m.header().n_patch);
+        v->map_obs_invalid.push_back((int)m.header().obs_invalid);
         v->max_beam_len = std::max(v->max_beam_len, m.max_beam_len);
     }
     if (map_of_env)
@@ -552,6 +564,59 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->obs_view_agents = v->hdr0.view_agents;
     out->obs_c = v->hdr0.obs_c; out->obs_h = v->hdr0.obs_h; out->obs_w = v->hdr0.obs_w;
     out->obs_invalid = v->obs_invalid;
+    return LLE_OK;
+}
+
+int lle_vec_get_sources(lle_vec* v, int32_t map_index, int32_t* out, int32_t cap, int32_t* n) {
+    if (!v || !n || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "bad argument");
+    const auto& st = v->src_state[(size_t)map_index];
+    *n = (int32_t)st.size();
+    for (int k = 0; k < (int)st.size() && k < cap && out; ++k) { out[2 * k] = st[k].colour; out[2 * k + 1] = st[k].enabled; }
+    return LLE_OK;
+}
+
+int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int32_t agent_id, int32_t enabled, void* stream) {
+    if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
+    auto& st = v->src_state[(size_t)map_index];
+    if (source_index < 0 || source_index >= (int)st.size()) return fail(LLE_INVALID_ARGUMENT, "laser source index out of range");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    std::vector<SourceState> next = st;
+    if (agent_id >= 0) next[(size_t)source_index].colour = agent_id;
+    const bool was_enabled = st[(size_t)source_index].enabled;
+    if (enabled >= 0) next[(size_t)source_index].enabled = enabled != 0;
+    CompiledMap cm;
+    try {
+        cm = compile_map(v->map_texts[(size_t)map_index], ObsSpec{v->opts.obs_type, v->opts.obs_param}, &next);
+    } catch (const MapError& e) {
+        return fail(e.status, e.what());
+    }
+    if (v->fast && cm.header().n_patch > 64)
+        return fail(LLE_LIMIT_EXCEEDED, "the recoloured map has more than 64 dynamic observation cells (vec was created for the fast tile path)");
+    LLE_CUDA(cudaSetDevice(v->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    LLE_CUDA(cudaStreamSynchronize(s));  // control-plane operation: nothing of this vec is in flight while its map changes
+    uint8_t* d = nullptr;
+    LLE_CUDA(cudaMalloc((void**)&d, cm.blob.size()));
+    LLE_CUDA(cudaMemcpy(d, cm.blob.data(), cm.blob.size(), cudaMemcpyHostToDevice));
+    LLE_CUDA(cudaMemcpy((void*)(v->d_blob_table + map_index), &d, sizeof d, cudaMemcpyHostToDevice));
+    v->retired_blobs.push_back(v->d_blobs[(size_t)map_index]);
+    v->d_blobs[(size_t)map_index] = d;
+    st = next;
+    v->map_patches[(size_t)map_index] = (int)cm.header().n_patch;
+    v->map_obs_invalid[(size_t)map_index] = (int)cm.header().obs_invalid;
+    v->obs_invalid = 0;
+    for (int f : v->map_obs_invalid) v->obs_invalid |= f;
+    if (map_index == 0) v->hdr0 = cm.header();
+    if (enabled >= 0 && (enabled != 0) != was_enabled) {  // LaserBeam::enable / disable (laser.rs:69-77)
+        const int len = cm.sources[(size_t)source_index].len;
+        const uint64_t mask = enabled ? (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) : 0ull;
+        const int threads = 256;
+        const int blocks = (int)((v->N_pad + threads - 1) / threads);
+        lle_set_beam_kernel<<<blocks, threads, 0, s>>>(v->d_records, v->L, v->N_pad, v->d_map_of_env, map_index, source_index, mask);
+        LLE_CUDA(cudaGetLastError());
+        v->launches++;
+    }
+    v->last_was_step = false;
     return LLE_OK;
 }
 

@@ -1291,6 +1291,18 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     }
 }
 
+// LaserBeam::enable / disable (laser.rs:69-77) for one source of one map, in every world that uses the map: the whole
+// beam turns on (turn_on(0), whoever stands in it) or off.
+__global__ void lle_set_beam_kernel(uint32_t* records, LleStateLayout L, int64_t N_pad, const int32_t* map_of_env, int map_index,
+                                    int beam, uint64_t mask) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= N_pad) return;
+    if (map_of_env && map_of_env[env] != map_index) return;
+    uint32_t* w = records + env * L.stride + L.w_on + beam * L.on_words;
+    w[0] = (uint32_t)mask;
+    if (L.on_words == 2) w[1] = (uint32_t)(mask >> 32);
+}
+
 // Unpacks the records for white-box comparisons (tests) and `get_state`-style host queries.
 __global__ void lle_export_raw_kernel(const uint32_t* records, LleStateLayout L, int64_t N, int A, int NBmax, int16_t* pos,
                                       uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on, uint64_t* collected,

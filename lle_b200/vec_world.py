@@ -236,6 +236,28 @@ class VecWorld:
             ptr = t.data_ptr()
         check(lib().lle_vec_step_host(self._h, ptr, reward_out.data_ptr(), done_out.data_ptr(), _stream_ptr(self.device)))
 
+    def set_source(self, source_index: int, *, agent_id: int | None = None, enabled: bool | None = None, map_index: int = 0):
+        """Recolour / switch one laser source in every env that uses map `map_index` (lle_vec_set_source;
+        LaserBeam::set_agent_id / enable / disable, src/core/tiles/laser.rs:69-84)."""
+        check(lib().lle_vec_set_source(self._h, int(map_index), int(source_index), -1 if agent_id is None else int(agent_id),
+                                       -1 if enabled is None else int(bool(enabled)), _stream_ptr(self.device)))
+        b = VecBuffers()
+        check(lib().lle_vec_get_buffers(self._h, C.byref(b)))
+        self.obs_invalid = bool(b.obs_invalid)
+
+    def source_states(self, map_index: int = 0) -> list[tuple[int, bool]]:
+        """Current (agent_id, is_enabled) of the sources of map `map_index` (lle_vec_get_sources)."""
+        n = C.c_int32(0)
+        check(lib().lle_vec_get_sources(self._h, int(map_index), None, 0, C.byref(n)))
+        buf = (C.c_int32 * max(1, 2 * n.value))()
+        check(lib().lle_vec_get_sources(self._h, int(map_index), buf, n.value, C.byref(n)))
+        return [(int(buf[2 * k]), bool(buf[2 * k + 1])) for k in range(n.value)]
+
+    def refresh(self):
+        """Re-export observation / state / availability of every env from its current engine state, resetting none
+        (lle_vec_reset with an all-zero mask)."""
+        self.reset(torch.zeros((self.n_envs,), dtype=torch.uint8, device=self.device))
+
     def submit_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor):
         """Pipelined host-facing step (lle_vec_pipeline_submit): enqueue H2D actions -> step -> D2H reward/done on the vec's
         own streams and return at once.  Buffers should be pinned and must stay alive until the matching `wait_host()`."""

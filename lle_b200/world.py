@@ -85,15 +85,18 @@ class _Single:
     def lasers(self) -> list[Laser]:
         """World::lasers (world.rs:159-172) with `is_on` read from the device beam masks."""
         on = self._raw()["beam_on"].view(np.uint64)
-        return [Laser(pos, lid, colour, direction, bool((int(on[beam]) >> off) & 1), True)
+        states = self._vec.source_states()  # colours and switches may have changed since the map was parsed
+        return [Laser(pos, lid, states[beam][0], direction, bool((int(on[beam]) >> off) & 1), states[beam][1])
                 for pos, lid, colour, direction, beam, off in self._laser_tiles]
 
     @property
-    def laser_sources(self) -> list[LaserSource]:
-        return list(self._sources)
+    def laser_sources(self) -> list["BoundLaserSource"]:
+        """World::sources (world.rs:141-149) as handles that can recolour / switch the source (PyLaserSource)."""
+        states = self._vec.source_states()
+        return [BoundLaserSource(self, k, s, states[k]) for k, s in enumerate(self._sources)]
 
-    def source_at(self, pos) -> LaserSource:
-        for s in self._sources:
+    def source_at(self, pos) -> "BoundLaserSource":
+        for s in self.laser_sources:
             if s.pos == tuple(pos):
                 return s
         raise ValueError(f"There is no laser source at {tuple(pos)}")
@@ -110,7 +113,7 @@ class _Single:
 
     @property
     def n_laser_colours(self) -> int:
-        return len({s.agent_id for s in self._sources})
+        return len({colour for colour, _ in self._vec.source_states()})
 
     @property
     def world_string(self) -> str:
@@ -213,6 +216,63 @@ class World(_Single):
 
     def set_state(self, state: WorldState) -> list[WorldEvent]:
         return self._force_state(state)
+
+
+class BoundLaserSource:
+    """PyLaserSource (src/bindings/tiles/pylaser_source.rs): a snapshot of one source plus a handle on its world.  The
+    mutators act on the device world (lle_vec_set_source) and refresh its exported observation / state / availability."""
+
+    def __init__(self, world: "_Single", index: int, info: LaserSource, state: tuple[int, bool]):
+        self._world, self._index = world, index
+        self.pos, self.direction, self.laser_id, self.beam_len = info.pos, info.direction, info.laser_id, info.beam_len
+        self._agent_id, self._enabled = state
+
+    def _set_status(self, enabled: bool):  # pylaser_source.rs:55-74
+        if self._enabled == bool(enabled):
+            return
+        self._world._vec.set_source(self._index, enabled=bool(enabled))
+        self._world._vec.refresh()
+        self._enabled = bool(enabled)
+
+    is_enabled = property(lambda self: self._enabled, lambda self, v: self._set_status(bool(v)))
+    is_disabled = property(lambda self: not self._enabled, lambda self, v: self._set_status(not v))
+
+    def disable(self):
+        self._set_status(False)
+
+    def enable(self):
+        self._set_status(True)
+
+    @property
+    def agent_id(self) -> int:
+        return self._agent_id
+
+    @agent_id.setter
+    def agent_id(self, new_agent_id: int):  # pylaser_source.rs:107-142
+        new_agent_id = int(new_agent_id)
+        if new_agent_id < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        w = self._world
+        if new_agent_id >= w.n_agents:
+            raise ValueError("Agent ID is greater than the number of agents")
+        w._vec.set_source(self._index, agent_id=new_agent_id)  # the engine's colour changes before the check below, as there
+        w._vec.refresh()
+        cells = {l.pos for l in w.lasers if l.laser_id == self.laser_id}
+        for start_agent, starts in enumerate(w.random_start_pos):
+            if start_agent != new_agent_id and cells & set(starts):
+                raise ValueError(f"Laser source cannot be changed to agent ID {new_agent_id} since it would cross the start "
+                                 f"position of agent {start_agent}")
+        self._agent_id = new_agent_id
+
+    def set_colour(self, colour: int):
+        self.agent_id = colour
+
+    def __eq__(self, other):  # agent id, direction, laser id and position (pylaser_source.rs:144-152)
+        return (isinstance(other, (BoundLaserSource, LaserSource)) and self.agent_id == other.agent_id and self.direction == other.direction
+                and self.laser_id == other.laser_id and self.pos == other.pos)
+
+    def __repr__(self):
+        return f"LaserSource(pos={self.pos}, agent_id={self.agent_id}, direction={self.direction.name}, laser_id={self.laser_id}, is_enabled={self.is_enabled})"
 
 
 @dataclass

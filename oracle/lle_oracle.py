@@ -218,24 +218,38 @@ class Laser:
 
 
 class LaserSource:
+    """PyLaserSource (src/bindings/tiles/pylaser_source.rs): snapshot + handle on the world."""
+
     def __init__(self, world: "World", idx: int, rec):
         self._world, self._idx = world, idx
         self.pos = (int(rec[0]), int(rec[1]))
-        self.agent_id = int(rec[2])
+        self._agent_id = int(rec[2])
         self.direction = Direction(int(rec[3]))
-        self.is_enabled = bool(rec[4])
+        self._enabled = bool(rec[4])
         self.laser_id = int(rec[5])
         self.beam_len = int(rec[6])
 
+    def _set_status(self, enabled: bool):  # pylaser_source.rs:55-74
+        if self._enabled == bool(enabled):
+            return
+        lib().lleo_world_source_set_enabled(self._world._h, self._idx, int(bool(enabled)))
+        self._enabled = bool(enabled)
+
+    is_enabled = property(lambda self: self._enabled, lambda self, v: self._set_status(bool(v)))
+    is_disabled = property(lambda self: not self._enabled, lambda self, v: self._set_status(not v))
+
     def disable(self):
-        lib().lleo_world_source_set_enabled(self._world._h, self._idx, 0)
-        self.is_enabled = False
+        self._set_status(False)
 
     def enable(self):
-        lib().lleo_world_source_set_enabled(self._world._h, self._idx, 1)
-        self.is_enabled = True
+        self._set_status(True)
 
-    def set_colour(self, colour: int):
+    @property
+    def agent_id(self) -> int:
+        return self._agent_id
+
+    @agent_id.setter
+    def agent_id(self, colour: int):
         # src/bindings/tiles/pylaser_source.rs:107-142 (validation of the python setter)
         if colour < 0:
             raise OverflowError("can't convert negative int to unsigned")
@@ -247,6 +261,9 @@ class LaserSource:
         for start_agent, starts in enumerate(w.random_start_pos):
             if start_agent != colour and cells & set(starts):
                 raise ValueError(f"Laser source cannot be changed to agent ID {colour}")
+        self._agent_id = colour
+
+    def set_colour(self, colour: int):
         self.agent_id = colour
 
 
@@ -628,6 +645,10 @@ class OracleVec:
             self.extras = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(N * A * self.JE,)).reshape(N, A, self.JE)
         else:
             self.extras = np.zeros((N, A, 0), dtype=np.float32)
+
+    def set_source(self, source_index: int, *, agent_id: int | None = None, enabled: bool | None = None, map_index: int = 0):
+        _check(lib().lleo_vec_set_source(self._h, int(map_index), int(source_index), -1 if agent_id is None else int(agent_id),
+                                         -1 if enabled is None else int(bool(enabled))))
 
     def __del__(self):
         h = getattr(self, "_h", None)

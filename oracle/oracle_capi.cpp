@@ -554,6 +554,23 @@ int lleo_vec_set_obs(void* p, int kind, int param, long* out6) {
         for (size_t e = 0; e < v.N; ++e) v.export_env(e);
     });
 }
+// LaserBeam::set_agent_id / enable / disable (laser.rs:69-84) on source `idx` of every env whose map is `map_index`
+// (agent_id < 0 / enabled < 0: keep).  Outputs are re-exported; call lleo_vec_reset to refresh the cached static
+// observation layers the way LLE.reset does (ObservationGenerator.reset, observations.py:128-137).
+int lleo_vec_set_source(void* p, int map_index, int idx, int agent_id, int enabled) {
+    Vec& v = *(Vec*)p;
+    return guarded([&] {
+        for (size_t e = 0; e < v.N; ++e) {
+            if (v.map_of_env[e] != map_index) continue;
+            auto b = v.envs[e]->world.source_beam((size_t)idx);
+            if (agent_id >= 0) b->agent_id = (size_t)agent_id;
+            if (enabled == 0 && b->enabled) b->disable();
+            else if (enabled > 0 && !b->enabled) b->enable();
+            v.envs[e]->obs.setup(v.envs[e]->world);
+            v.export_env(e);
+        }
+    });
+}
 void* lleo_vec_extras(void* p) { return ((Vec*)p)->extras.data(); }
 long lleo_vec_extras_dim(void* p) { return (long)((Vec*)p)->JE; }
 long lleo_vec_reward_dim(void* p) { return (long)((Vec*)p)->R; }
@@ -581,6 +598,7 @@ int lleo_vec_reset(void* p) {
             v.done[e] = 0; v.err[e] = 0;
             std::fill(&v.reward[e * v.R], &v.reward[e * v.R] + v.R, 0.f);
             std::memset(&v.events[e * v.A], 0, v.A);
+            std::memset(&v.actions[e * v.A], 4, v.A);  // no action has been taken in the new episode (device ABI: STAY)
             v.export_env(e);
         }
     });

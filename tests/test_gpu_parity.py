@@ -142,6 +142,37 @@ def test_observation_types_large_and_many_agents():
     assert tuple(v.obs.shape) == (16, 12 * 12 * 13) and tuple(v.obs_per_agent.shape) == (16, 4, 12 * 12 * 13)
 
 
+def test_laser_source_mutators_in_a_batch():
+    """lle_vec_set_source (LaserBeam::set_agent_id / enable / disable, laser.rs:69-84) on one map of a heterogeneous batch,
+    then Philox rollouts: every output and the raw engine state stay bit-exact against the oracle."""
+    maps = [level_text(4), level_text(3), level_text(4)]  # 2 agents, 1 gem; sources (colour): lvl4 (0), (1); lvl3 (0)
+    moe = [e % 3 for e in range(300)]
+    for kw in (dict(), dict(obs_type="partial5x5"), dict(walkable_lasers=False), dict(obs_type="perspective", auto_reset=False)):
+        ora, dev = make_pair(maps, moe, 300, seed=70, **kw)
+        for t in range(30):
+            ora.step(None); dev.vec.step(None)
+        for target in (ora, dev.vec):
+            target.set_source(1, enabled=False, map_index=0)   # level 4, second source, in the envs of map 0 only
+            target.set_source(0, agent_id=1, map_index=1)      # level 3: recoloured
+            target.set_source(0, agent_id=1, map_index=2)      # level 4 (third map): both sources now colour 1
+        assert dev.vec.source_states(0) == [(0, True), (1, False)] and dev.vec.source_states(2) == [(1, True), (1, True)]
+        raw = dev.pull()
+        assert np.array_equal(raw["beam_on"][:, :ora.NB], np.asarray(ora.beam_on)[:, :ora.NB])
+        ora.reset(); dev.vec.reset()  # LLE.reset refreshes the cached static layers (observations.py:128-137)
+        assert_same(dev, ora, dev.pull(), "after the reset that follows the mutation")
+        for t in range(120):
+            ora.step(None); dev.vec.step(None)
+            if t % 4 == 0:
+                assert_same(dev, ora, dev.pull(), f"step {t} after the mutation")
+        for target in (ora, dev.vec):
+            target.set_source(1, enabled=True, map_index=0)    # the whole beam comes back on, whoever stands in it
+        raw = dev.pull()
+        assert np.array_equal(raw["beam_on"][:, :ora.NB], np.asarray(ora.beam_on)[:, :ora.NB])
+        for t in range(60):
+            ora.step(None); dev.vec.step(None)
+            assert_same(dev, ora, dev.pull(), f"step {t} after re-enabling")
+
+
 def test_supplied_actions_with_invalid_ones():
     rng = np.random.default_rng(0)
     ora, dev = make_pair([level_text(5)], None, 512, seed=1)

@@ -853,3 +853,134 @@ def test_world_tiles(api):  # [P]
     assert w.start_pos == [(0, 0)]
     assert w.random_start_pos == [[(0, 0)]]
     assert w.exit_pos == [(0, 2)]
+
+
+# ----------------------------------------------------------------------------- laser-source mutators
+# LaserBeam::{set_agent_id, enable, disable} (src/core/tiles/laser.rs:69-84) through PyLaserSource
+# (src/bindings/tiles/pylaser_source.rs:55-142).  [I] tests/world_integration_tests.rs, [P] python/tests/test_world.py
+SRC_MAP = "S0 .   G  X\n.  .  L0W .\n.  S1  .  X\n.  .   .  ."
+
+
+def test_change_laser_id(api):  # [I] change_laser_id :333
+    w = api.World(SRC_MAP)
+    w.reset()
+    assert all(l.agent_id == 0 for l in w.lasers)
+    source = w.laser_sources[0]
+    source.agent_id = 1
+    assert source.agent_id == 1 and w.laser_sources[0].agent_id == 1
+    assert all(l.agent_id == 1 for l in w.lasers)
+    events = w.step([api.Action.SOUTH, api.Action.STAY])  # agent 0 dies in what is now agent 1's laser
+    assert events == [api.WorldEvent(api.EventType.AGENT_DIED, 0)]
+
+
+def test_disable_laser_source(api):  # [I] disable_laser_source :363
+    w = api.World(SRC_MAP)
+    w.reset()
+    assert all(l.is_on for l in w.lasers)
+    source = w.laser_sources[0]
+    source.disable()
+    assert all(l.is_off for l in w.lasers) and not any(l.is_enabled for l in w.lasers)
+    assert w.laser_sources[0].is_disabled
+    source.enable()
+    assert all(l.is_on for l in w.lasers)
+
+
+def test_disable_laser_source_and_block_with_agent(api):  # [I] :384
+    w = api.World("L0E . S0 X")
+    w.reset()
+    assert laser_at(w, (0, 1)).is_on
+    w.laser_sources[0].disable()
+    assert laser_at(w, (0, 1)).is_off
+    w.step([api.Action.WEST])
+    assert laser_at(w, (0, 2)).is_off
+    w.step([api.Action.EAST])
+    assert laser_at(w, (0, 1)).is_off
+
+
+def test_disable_laser_then_reset_does_not_turn_on(api):  # [I] :447
+    w = api.World("L0E . S0 X")
+    w.reset()
+    w.laser_sources[0].disable()
+    w.reset()
+    laser = laser_at(w, (0, 1))
+    assert not laser.is_enabled and laser.is_off
+
+
+def test_enable_turns_the_whole_beam_on(api):  # laser.rs:69-72: enable() is turn_on(0), whoever stands in the beam
+    w = api.World("L0E . S0 X")
+    w.reset()
+    w.step([api.Action.WEST])  # the owner blocks its beam at offset 0
+    assert laser_at(w, (0, 1)).is_off and laser_at(w, (0, 2)).is_off
+    source = w.laser_sources[0]
+    source.is_enabled = False
+    source.is_disabled = False  # assignment forms of disable() / enable() (pylaser_source.rs:84-92)
+    assert laser_at(w, (0, 1)).is_on and laser_at(w, (0, 2)).is_on
+    w.step([api.Action.STAY])  # leave + pre_enter on the same cell cut it again (laser.rs:173-202)
+    assert laser_at(w, (0, 1)).is_off
+
+
+def test_disable_deadly_laser_source_and_walk_into_it(api):  # [P] :470
+    world = api.World("L0S . L0W X\nS0 S1  .  X")
+    world.reset()
+    world.source_at((0, 2)).disable()
+    events = world.step([api.Action.STAY, api.Action.NORTH])
+    assert len(events) == 0
+    assert all(a.is_alive for a in world.agents)
+
+
+def test_change_laser_colour(api):  # [P] :485
+    world = api.World("L1E . S1 S0 X\nL0E .  .  . X")
+    world.reset()
+    assert len(world.lasers) == 8
+    for laser in world.lasers:
+        assert laser.agent_id == (1 if laser.pos[0] == 0 else 0)
+    bot_source = world.source_at((1, 0))
+    bot_source.set_colour(1)
+    world.reset()
+    for laser in world.lasers:
+        if laser.pos[0] == 1:
+            assert laser.agent_id == 1
+    events = world.step([api.Action.SOUTH, api.Action.SOUTH])
+    assert len(events) == 0
+    assert all(a.is_alive for a in world.agents)
+
+
+def test_change_laser_colour_errors(api):  # [P] :517-575
+    world = api.World("L0E S0 . X")
+    world.reset()
+    source = world.source_at((0, 0))
+    with pytest.raises(OverflowError):
+        source.set_colour(-1)
+    for bad in (2, 1):  # there is only one agent
+        with pytest.raises(ValueError):
+            source.set_colour(bad)
+        with pytest.raises(ValueError):
+            source.agent_id = bad
+    world = api.World("L0E X X S0 S1")  # agent 1 would be killed on reset
+    world.reset()
+    with pytest.raises(ValueError):
+        world.source_at((0, 0)).agent_id = 1
+
+
+def test_laser_colour_change_remains_after_reset(api):  # [P] :527
+    world = api.World("L0E X X @ S0 S1")
+    world.reset()
+    world.source_at((0, 0)).agent_id = 1
+    world.reset()
+    assert world.source_at((0, 0)).agent_id == 1
+
+
+def test_change_laser_colour_back(api):  # [P] :578
+    world = api.World("L1E . S1 S0 X\nL0E .  .  . X")
+    world.reset()
+    bot_source = world.source_at((1, 0))
+    bot_source.set_colour(1)
+    world.reset()
+    assert world.source_at((1, 0)).agent_id == 1
+    assert all(l.agent_id == 1 for l in world.lasers)
+    bot_source.set_colour(0)
+    world.reset()
+    assert world.source_at((1, 0)).agent_id == 0
+    for laser in world.lasers:
+        assert laser.agent_id == (1 if laser.pos[0] == 0 else 0)
+    assert world.n_laser_colours == 2
