@@ -229,6 +229,13 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
 LLE_API int lle_vec_set_source(lle_vec* vec, int32_t map_index, int32_t source_index, int32_t agent_id, int32_t enabled, void* cuda_stream);
 LLE_API int lle_vec_get_sources(lle_vec* vec, int32_t map_index, int32_t* out_pairs, int32_t cap, int32_t* n);
 
+/* World::set_exit_positions (src/core/world.rs:195-234; the `World.exit_pos` setter, pyworld.rs:202-210) for every env that
+ * uses map `map_index`: the current exits become floor tiles and the (i, j) pairs of `exits_ij` become the exits.  Agents keep
+ * their position, alive and arrived flags.  Fewer exits than agents -> LLE_PARSE_NOT_ENOUGH_EXITS.  A new exit must be a
+ * floor, start or former exit cell crossed by at most one beam (the reference panics or corrupts its grid otherwise).
+ * Synchronises `cuda_stream`; buffers show the change from the next step / reset on. */
+LLE_API int lle_vec_set_exits(lle_vec* vec, int32_t map_index, const int32_t* exits_ij, int32_t n_exits, void* cuda_stream);
+
 /* World::set_state / LLE.set_state (world.rs:515-597, env.py:208-216) for every env.
  *   pos_dev i32[N,A,2], gems_dev u8[N,G], alive_dev u8[N,A] (device).  Per-env failures are reported in err. */
 LLE_API int lle_vec_set_state(lle_vec* vec, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* cuda_stream);

@@ -35,7 +35,8 @@ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 }  // namespace
 
-CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std::vector<SourceState>* source_state) {
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std::vector<SourceState>* source_state,
+                        const std::vector<Cell>* new_exits) {
     if (spec.kind < LLE_OBS_LAYERED || spec.kind > LLE_OBS_STATE) throw MapError(LLE_INVALID_ARGUMENT, "unknown observation kind");
     if (spec.kind == LLE_OBS_LAYERED && (spec.param < 0 || spec.param > 64)) throw MapError(LLE_INVALID_ARGUMENT, "padding_size out of range");
     if (spec.kind == LLE_OBS_PARTIAL && (spec.param < 1 || spec.param % 2 != 1 || spec.param > 31))
@@ -134,6 +135,18 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         throw MapError(LLE_PARSE_NOT_ENOUGH_EXITS, "NotEnoughExitTiles { n_starts: " + std::to_string(A) +
                                                        ", n_exits: " + std::to_string(cm.exits.size()) + " }");
 
+    if (new_exits) {  // World::set_exit_positions (world.rs:195-234)
+        if ((int)new_exits->size() < A)
+            throw MapError(LLE_PARSE_NOT_ENOUGH_EXITS, "NotEnoughExitTiles { n_starts: " + std::to_string(A) +
+                                                           ", n_exits: " + std::to_string(new_exits->size()) + " }");
+        for (const auto& c : *new_exits) {
+            if (c.i < 0 || c.j < 0 || c.i >= H || c.j >= W) throw MapError(LLE_INDEX_ERROR, "exit position out of the world");
+            const char kind = rows[c.i][c.j].kind;
+            if (kind != '.' && kind != 'S' && kind != 'X')  // the reference panics: "Tile is not a floor"
+                throw MapError(LLE_INVALID_ARGUMENT, "an exit can only be placed on a floor tile");
+        }
+        cm.exits = *new_exits;
+    }
     // ---- base tile plane (world_config.rs:176-199)
     std::vector<uint16_t> tiles((size_t)H * W, LLE_T_FLOOR);
     for (size_t g = 0; g < cm.gems.size(); ++g) tiles[cm.gems[g].i * W + cm.gems[g].j] = (uint16_t)(LLE_T_GEM | (g << 8));
@@ -162,6 +175,10 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
             cell_beams[c.i * W + c.j].push_back({s.laser_id, k});
         }
     }
+    if (new_exits)
+        for (const auto& c : *new_exits)
+            if (cell_beams[c.i * W + c.j].size() > 1)  // the reference's set_tile would drop the inner beam's tile there
+                throw MapError(LLE_PARSE_UNSUPPORTED, "an exit cannot be placed where two beams cross");
     // ---- post_validate (world_config.rs:150-170)
     for (int a = 0; a < A; ++a)
         if (starts[a].empty())

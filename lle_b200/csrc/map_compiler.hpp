@@ -68,6 +68,9 @@ struct SourceState {
     bool enabled;
 };
 
-CompiledMap compile_map(const std::string& text, const ObsSpec& spec = ObsSpec(), const std::vector<SourceState>* sources = nullptr);
+// `exits`: World::set_exit_positions (src/core/world.rs:195-234) applied after the build — the exits of the text become
+// floor tiles and these cells (plain floor, start or former exit cells crossed by at most one beam) become the exits.
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec = ObsSpec(), const std::vector<SourceState>* sources = nullptr,
+                        const std::vector<Cell>* exits = nullptr);
 
 }  // namespace lle

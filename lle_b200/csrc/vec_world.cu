@@ -50,6 +50,8 @@ struct lle_vec {
     std::vector<std::string> map_texts;
     std::vector<std::vector<SourceState>> src_state;
     std::vector<int> map_patches, map_obs_invalid;
+    std::vector<std::vector<Cell>> map_exits;  // World::set_exit_positions overrides (empty: the exits of the text)
+    std::vector<char> map_exits_set;
     std::vector<uint8_t*> retired_blobs;
     bool render = true;
     LleMapHeader hdr0;  // header of the first map (observation shape)
@@ -390,6 +392,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->src_state.push_back(st);
         v->map_patches.push_back((int)m.header().n_patch);
         v->map_obs_invalid.push_back((int)m.header().obs_invalid);
+        v->map_exits.emplace_back();
+        v->map_exits_set.push_back(0);
         v->max_beam_len = std::max(v->max_beam_len, m.max_beam_len);
     }
     if (map_of_env)
@@ -575,6 +579,37 @@ int lle_vec_get_sources(lle_vec* v, int32_t map_index, int32_t* out, int32_t cap
     return LLE_OK;
 }
 
+namespace {
+// Recompiles map `map_index` of the vec with the given source states / exits and swaps the device tables.
+int swap_map(lle_vec* v, int map_index, const std::vector<SourceState>& sources, const std::vector<Cell>* exits, cudaStream_t s,
+             CompiledMap* out_cm) {
+    CompiledMap cm;
+    try {
+        cm = compile_map(v->map_texts[(size_t)map_index], ObsSpec{v->opts.obs_type, v->opts.obs_param}, &sources, exits);
+    } catch (const MapError& e) {
+        return fail(e.status, e.what());
+    }
+    if (v->fast && cm.header().n_patch > 64)
+        return fail(LLE_LIMIT_EXCEEDED, "the modified map has more than 64 dynamic observation cells (vec was created for the fast tile path)");
+    LLE_CUDA(cudaSetDevice(v->device));
+    LLE_CUDA(cudaStreamSynchronize(s));  // control-plane operation: nothing of this vec is in flight while its map changes
+    uint8_t* d = nullptr;
+    LLE_CUDA(cudaMalloc((void**)&d, cm.blob.size()));
+    LLE_CUDA(cudaMemcpy(d, cm.blob.data(), cm.blob.size(), cudaMemcpyHostToDevice));
+    LLE_CUDA(cudaMemcpy((void*)(v->d_blob_table + map_index), &d, sizeof d, cudaMemcpyHostToDevice));
+    v->retired_blobs.push_back(v->d_blobs[(size_t)map_index]);
+    v->d_blobs[(size_t)map_index] = d;
+    v->map_patches[(size_t)map_index] = (int)cm.header().n_patch;
+    v->map_obs_invalid[(size_t)map_index] = (int)cm.header().obs_invalid;
+    v->obs_invalid = 0;
+    for (int f : v->map_obs_invalid) v->obs_invalid |= f;
+    if (map_index == 0) v->hdr0 = cm.header();
+    v->last_was_step = false;
+    if (out_cm) *out_cm = std::move(cm);
+    return LLE_OK;
+}
+}  // namespace
+
 int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int32_t agent_id, int32_t enabled, void* stream) {
     if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
     auto& st = v->src_state[(size_t)map_index];
@@ -584,29 +619,11 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
     if (agent_id >= 0) next[(size_t)source_index].colour = agent_id;
     const bool was_enabled = st[(size_t)source_index].enabled;
     if (enabled >= 0) next[(size_t)source_index].enabled = enabled != 0;
-    CompiledMap cm;
-    try {
-        cm = compile_map(v->map_texts[(size_t)map_index], ObsSpec{v->opts.obs_type, v->opts.obs_param}, &next);
-    } catch (const MapError& e) {
-        return fail(e.status, e.what());
-    }
-    if (v->fast && cm.header().n_patch > 64)
-        return fail(LLE_LIMIT_EXCEEDED, "the recoloured map has more than 64 dynamic observation cells (vec was created for the fast tile path)");
-    LLE_CUDA(cudaSetDevice(v->device));
     cudaStream_t s = (cudaStream_t)stream;
-    LLE_CUDA(cudaStreamSynchronize(s));  // control-plane operation: nothing of this vec is in flight while its map changes
-    uint8_t* d = nullptr;
-    LLE_CUDA(cudaMalloc((void**)&d, cm.blob.size()));
-    LLE_CUDA(cudaMemcpy(d, cm.blob.data(), cm.blob.size(), cudaMemcpyHostToDevice));
-    LLE_CUDA(cudaMemcpy((void*)(v->d_blob_table + map_index), &d, sizeof d, cudaMemcpyHostToDevice));
-    v->retired_blobs.push_back(v->d_blobs[(size_t)map_index]);
-    v->d_blobs[(size_t)map_index] = d;
+    CompiledMap cm;
+    int rc = swap_map(v, map_index, next, v->map_exits_set[(size_t)map_index] ? &v->map_exits[(size_t)map_index] : nullptr, s, &cm);
+    if (rc != LLE_OK) return rc;
     st = next;
-    v->map_patches[(size_t)map_index] = (int)cm.header().n_patch;
-    v->map_obs_invalid[(size_t)map_index] = (int)cm.header().obs_invalid;
-    v->obs_invalid = 0;
-    for (int f : v->map_obs_invalid) v->obs_invalid |= f;
-    if (map_index == 0) v->hdr0 = cm.header();
     if (enabled >= 0 && (enabled != 0) != was_enabled) {  // LaserBeam::enable / disable (laser.rs:69-77)
         const int len = cm.sources[(size_t)source_index].len;
         const uint64_t mask = enabled ? (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) : 0ull;
@@ -616,7 +633,19 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
         LLE_CUDA(cudaGetLastError());
         v->launches++;
     }
-    v->last_was_step = false;
+    return LLE_OK;
+}
+
+int lle_vec_set_exits(lle_vec* v, int32_t map_index, const int32_t* exits_ij, int32_t n_exits, void* stream) {
+    if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
+    if (n_exits < 0 || (n_exits > 0 && !exits_ij)) return fail(LLE_INVALID_ARGUMENT, "bad exit list");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    std::vector<Cell> exits;
+    for (int k = 0; k < n_exits; ++k) exits.push_back(Cell{exits_ij[2 * k], exits_ij[2 * k + 1]});
+    int rc = swap_map(v, map_index, v->src_state[(size_t)map_index], &exits, (cudaStream_t)stream, nullptr);
+    if (rc != LLE_OK) return rc;
+    v->map_exits[(size_t)map_index] = exits;
+    v->map_exits_set[(size_t)map_index] = 1;
     return LLE_OK;
 }
 

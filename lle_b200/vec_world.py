@@ -245,6 +245,11 @@ class VecWorld:
         check(lib().lle_vec_get_buffers(self._h, C.byref(b)))
         self.obs_invalid = bool(b.obs_invalid)
 
+    def set_exits(self, exits: Sequence[tuple[int, int]], map_index: int = 0):
+        """World::set_exit_positions (world.rs:195-234) in every env that uses map `map_index` (lle_vec_set_exits)."""
+        flat = (C.c_int32 * max(1, 2 * len(exits)))(*[int(x) for p in exits for x in p])
+        check(lib().lle_vec_set_exits(self._h, int(map_index), flat, len(exits), _stream_ptr(self.device)))
+
     def source_states(self, map_index: int = 0) -> list[tuple[int, bool]]:
         """Current (agent_id, is_enabled) of the sources of map `map_index` (lle_vec_get_sources)."""
         n = C.c_int32(0)

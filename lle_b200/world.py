@@ -103,7 +103,13 @@ class _Single:
 
     wall_pos = property(lambda self: self._map.walls)
     void_pos = property(lambda self: self._map.voids)
-    exit_pos = property(lambda self: self._map.exits)
+    def _set_exit_pos(self, exits):  # PyWorld.exit_pos setter (pyworld.rs:202-210)
+        exits = [(int(i), int(j)) for i, j in exits]
+        self._vec.set_exits(exits)
+        self._vec.refresh()
+        self._exits = exits
+
+    exit_pos = property(lambda self: getattr(self, "_exits", None) or self._map.exits, _set_exit_pos)
     start_pos = property(lambda self: self._map.starts)
     laser_pos = property(lambda self: self._map.laser_cells)
 

@@ -363,6 +363,25 @@ class World {
         return res;
     }
 
+    // world.rs:195-234: the current exits become floor tiles, the given positions (which must be floor tiles, possibly
+    // under a laser) become exits; agents standing there stay on the tile.
+    void set_exit_positions(const std::vector<Position>& new_exits) {
+        if (new_exits.size() < n_agents())
+            throw ParseError(ParseErrorKind::NotEnoughExitTiles, "NotEnoughExitTiles", (long)n_agents(), (long)new_exits.size());
+        auto replace = [&](const Position& pos, Tile::Kind from, Tile::Kind to, const char* what) {
+            Tile& tile = grid[pos.i][pos.j];
+            Tile* target = &tile;
+            if (tile.kind == Tile::Laser) target = tile.wrapped.get();  // laser.set_tile(...) replaces the wrapped tile (:208-213)
+            if (target->kind != from) throw RuntimeWorldError(RuntimeErrorKind::Panic, what);
+            Tile repl = Tile::make(to);
+            repl.slot = tile.kind == Tile::Laser ? tile.agent() : target->slot;  // `agent: laser.agent()` / `agent`
+            *target = std::move(repl);
+        };
+        for (const auto& pos : exits) replace(pos, Tile::Exit, Tile::Floor, "Tile is not an exit");
+        exits = new_exits;
+        for (const auto& pos : exits) replace(pos, Tile::Floor, Tile::Exit, "Tile is not a floor");
+    }
+
     // world.rs:159-172 — only the outer laser and the one directly under it are listed
     std::vector<LaserView> lasers() const {
         std::vector<LaserView> res;

@@ -394,7 +394,11 @@ class World:
 
     wall_pos = property(lambda self: self._positions(0))
     void_pos = property(lambda self: self._positions(1))
-    exit_pos = property(lambda self: self._positions(2))
+    def _set_exit_pos(self, exits):  # PyWorld.exit_pos setter (pyworld.rs:202-210) -> World::set_exit_positions (world.rs:195-234)
+        flat = (C.c_long * max(1, 2 * len(exits)))(*[int(x) for p in exits for x in p])
+        _check(lib().lleo_world_set_exits(self._h, flat, len(exits)))
+
+    exit_pos = property(lambda self: self._positions(2), _set_exit_pos)
     start_pos = property(lambda self: self._positions(4))
     laser_pos = property(lambda self: self._positions(5))
 
@@ -645,6 +649,10 @@ class OracleVec:
             self.extras = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(N * A * self.JE,)).reshape(N, A, self.JE)
         else:
             self.extras = np.zeros((N, A, 0), dtype=np.float32)
+
+    def set_exits(self, exits, map_index: int = 0):
+        flat = (C.c_long * max(1, 2 * len(exits)))(*[int(x) for p in exits for x in p])
+        _check(lib().lleo_vec_set_exits(self._h, int(map_index), flat, len(exits)))
 
     def set_source(self, source_index: int, *, agent_id: int | None = None, enabled: bool | None = None, map_index: int = 0):
         _check(lib().lleo_vec_set_source(self._h, int(map_index), int(source_index), -1 if agent_id is None else int(agent_id),

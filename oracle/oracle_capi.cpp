@@ -350,6 +350,14 @@ void lleo_world_source_set_enabled(void* p, int idx, int enabled) {
 void lleo_world_source_set_agent_id(void* p, int idx, int agent_id) {
     ((WorldHandle*)p)->w.source_beam((size_t)idx)->agent_id = (size_t)agent_id;
 }
+int lleo_world_set_exits(void* p, const long* ij, int n) {
+    WorldHandle* h = (WorldHandle*)p;
+    return guarded([&] {
+        std::vector<Position> pos;
+        for (int k = 0; k < n; ++k) pos.push_back(Position{(size_t)ij[2 * k], (size_t)ij[2 * k + 1]});
+        h->w.set_exit_positions(pos);
+    });
+}
 void lleo_world_beam_bits(void* p, int idx, uint8_t* out) {
     auto b = ((WorldHandle*)p)->w.source_beam((size_t)idx);
     for (size_t k = 0; k < b->beam.size(); ++k) out[k] = b->beam[k];
@@ -566,6 +574,20 @@ int lleo_vec_set_source(void* p, int map_index, int idx, int agent_id, int enabl
             if (agent_id >= 0) b->agent_id = (size_t)agent_id;
             if (enabled == 0 && b->enabled) b->disable();
             else if (enabled > 0 && !b->enabled) b->enable();
+            v.envs[e]->obs.setup(v.envs[e]->world);
+            v.export_env(e);
+        }
+    });
+}
+// World::set_exit_positions (world.rs:195-234) on every env whose map is `map_index`; static observation layers refreshed.
+int lleo_vec_set_exits(void* p, int map_index, const long* ij, int n) {
+    Vec& v = *(Vec*)p;
+    return guarded([&] {
+        std::vector<Position> pos;
+        for (int k = 0; k < n; ++k) pos.push_back(Position{(size_t)ij[2 * k], (size_t)ij[2 * k + 1]});
+        for (size_t e = 0; e < v.N; ++e) {
+            if (v.map_of_env[e] != map_index) continue;
+            v.envs[e]->world.set_exit_positions(pos);
             v.envs[e]->obs.setup(v.envs[e]->world);
             v.export_env(e);
         }

@@ -166,11 +166,18 @@ def test_laser_source_mutators_in_a_batch():
                 assert_same(dev, ora, dev.pull(), f"step {t} after the mutation")
         for target in (ora, dev.vec):
             target.set_source(1, enabled=True, map_index=0)    # the whole beam comes back on, whoever stands in it
+            target.set_exits([(11, 0), (10, 3), (5, 5)], map_index=1)  # World::set_exit_positions (world.rs:195-234)
         raw = dev.pull()
         assert np.array_equal(raw["beam_on"][:, :ora.NB], np.asarray(ora.beam_on)[:, :ora.NB])
-        for t in range(60):
+        for t in range(60):  # exits moved mid-episode: the reference's cached EXIT layer only refreshes at each env's next
+            ora.step(None); dev.vec.step(None)  # reset (observations.py:128-137), so observations are not compared here
+        raw = dev.pull()
+        for name in ("pos", "alive", "arrived", "slot", "collected"):
+            assert np.array_equal(raw[name], np.asarray(getattr(ora, name))), name
+        ora.reset(); dev.vec.reset()
+        for t in range(80):
             ora.step(None); dev.vec.step(None)
-            assert_same(dev, ora, dev.pull(), f"step {t} after re-enabling")
+            assert_same(dev, ora, dev.pull(), f"step {t} after re-enabling and moving the exits")
 
 
 def test_supplied_actions_with_invalid_ones():

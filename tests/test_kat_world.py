@@ -7,6 +7,7 @@
 Each test names its source.  They run against the oracle (CPU) and, with ``-m gpu``, against the
 CUDA path through the N=1 ``World`` facade — same assertions, bit-exact expectations.
 """
+import numpy as np
 import pytest
 
 
@@ -984,3 +985,53 @@ def test_change_laser_colour_back(api):  # [P] :578
     for laser in world.lasers:
         assert laser.agent_id == (1 if laser.pos[0] == 0 else 0)
     assert world.n_laser_colours == 2
+
+
+# ----------------------------------------------------------------------------- World.exit_pos setter
+def test_set_exit_positions(api):  # [P] test_set_exit_positions :764 ; world.rs:195-234
+    A, E = api.Action, api.EventType
+    world = api.World("S0 . X")
+    world.reset()
+    assert world.exit_pos[0] == (0, 2)
+    world.exit_pos = [(0, 1)]
+    world.reset()
+    assert world.exit_pos[0] == (0, 1)
+    events = world.step([A.EAST])
+    assert events[0].event_type == E.AGENT_EXIT
+    world.exit_pos = [(0, 2)]
+    world.reset()
+    assert world.exit_pos[0] == (0, 2)
+    assert len(world.step([A.EAST])) == 0
+    events = world.step([A.EAST])
+    assert events[0].event_type == E.AGENT_EXIT
+
+
+def test_observe_layered_change_exits(api):  # [O] python/tests/test_observations.py:76
+    world = api.World("S0 X . .")
+    assert world.exit_pos[0] == (0, 1) and len(world.exit_pos) == 1
+    world.exit_pos = [(0, 2), (0, 3)]
+    world.reset()
+    obs = world.observe_layered()
+    EXIT = 2 * 1 + 3
+    assert np.all(obs[:, EXIT, 0, 2] == 1) and np.all(obs[:, EXIT, 0, 3] == 1)
+    assert obs[:, EXIT].sum() == 2
+
+
+def test_set_exit_positions_errors(api):  # world.rs:196-201 ; the reference panics on non-floor tiles (:216-229)
+    world = api.World("S0 . X\nS1 @ X")
+    with pytest.raises(api.ParsingError, match="NotEnoughExitTiles"):
+        world.exit_pos = [(0, 1)]
+    with pytest.raises(Exception):  # the reference panics half-way (and poisons the world's mutex); here the call is refused
+        world.exit_pos = [(0, 1), (1, 1)]  # a wall
+
+
+def test_exit_under_a_laser_moves(api):  # world.rs:208-213 / :222-227: the tile under the (single) laser is replaced
+    world = api.World("L0E . X\nS0  . .\nS1  . X")
+    world.reset()
+    world.exit_pos = [(0, 1), (2, 2)]
+    world.reset()
+    assert laser_at(world, (0, 1)).is_on and laser_at(world, (0, 2)).is_on
+    world.step([api.Action.EAST, api.Action.STAY])
+    events = world.step([api.Action.NORTH, api.Action.STAY])  # agent 0 enters its own beam on the new exit
+    assert events == [api.WorldEvent(api.EventType.AGENT_EXIT, 0)]
+    assert laser_at(world, (0, 2)).is_off
