@@ -38,6 +38,21 @@ for r, (off, line, text) in zip(data, lines_of):
     samp[line] += float(r[sm] or 0)
 ti, ts = sum(inst.values()), sum(samp.values())
 print(f"total warp instructions {ti:.0f}, samples {ts:.0f}")
+# coarse regions of world_kernel.cuh (by the line a SASS instruction is attributed to; inlined helpers count where they are defined)
+marks = []
+for n, text in enumerate(src, 1):
+    for tag in ("struct World {", "struct PatchCache", "template <int MODE, bool FAST>", "// ================================================================== logic",
+                "// ================================================================== observations of the group", "} else {\n"):
+        if tag in text:
+            marks.append((n, text.strip()[:60]))
+marks.append((len(src) + 1, "end"))
+prev = (1, "helpers / PTX wrappers")
+for m in marks:
+    a, b = prev[0], m[0]
+    vi = sum(v for l, v in inst.items() if l and a <= l < b)
+    vs = sum(v for l, v in samp.items() if l and a <= l < b)
+    print(f"region {a:5d}-{b - 1:5d}  instr {vi / ti * 100:5.1f}%  stall {vs / ts * 100:5.1f}%   {prev[1]}")
+    prev = m
 print("line   instr%  stall%  source")
 for line, v in sorted(inst.items(), key=lambda x: -(x[1] / ti + samp[x[0]] / ts))[:top_n]:
     print(f"{line:5d}  {v / ti * 100:5.1f}  {samp[line] / ts * 100:5.1f}   {src[line - 1].strip()[:120] if line else ''}")

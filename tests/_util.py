@@ -68,3 +68,37 @@ def rollout_digest(x) -> list[int]:
         a = np.ascontiguousarray(np.asarray(getattr(x, name)))
         out.append(zlib.crc32(a.tobytes()) ^ (zlib.adler32(a.tobytes()) << 32))
     return out
+
+
+def random_map(rng, allow_invalid: bool = False) -> str:
+    """A random v1 map for differential fuzzing: random size, agents, exits, walls, gems, voids and laser sources of any
+    colour (including colours >= n_agents) and direction.  With allow_invalid, some maps break a parser rule on purpose
+    (too few exits, a duplicated start, a start lost to a foreign beam ...), so that error paths are compared as well."""
+    h, w = rng.randint(1, 7), rng.randint(2, 8)
+    n_agents = rng.randint(1, min(5, h * w // 2))
+    cells = [(i, j) for i in range(h) for j in range(w)]
+    rng.shuffle(cells)
+    grid = [["." for _ in range(w)] for _ in range(h)]
+    take = iter(cells)
+    try:
+        for a in range(n_agents):
+            i, j = next(take)
+            grid[i][j] = f"S{a}"
+        n_exits = n_agents + rng.randint(0, 2)
+        if allow_invalid and rng.random() < 0.05:
+            n_exits = max(0, n_agents - 1)
+        for _ in range(n_exits):
+            i, j = next(take)
+            grid[i][j] = "X"
+        for _ in range(rng.randint(0, 3)):
+            i, j = next(take)
+            grid[i][j] = f"L{rng.randint(0, n_agents + (1 if rng.random() < 0.2 else -1 if n_agents > 1 else 0))}{rng.choice('NESW')}"
+        for (i, j) in take:
+            r = rng.random()
+            grid[i][j] = "@" if r < 0.12 else "G" if r < 0.22 else "V" if r < 0.26 else "."
+    except StopIteration:
+        pass
+    if allow_invalid and rng.random() < 0.03:
+        i, j = rng.choice(cells)
+        grid[i][j] = "S0"
+    return "\n".join(" ".join(row) for row in grid)

@@ -76,6 +76,30 @@ def test_map_compiler_matches_oracle_on_corpus(layouts):
         assert _map_facts_native(level=n) == _map_facts_oracle(level_text(n))
 
 
+def test_map_compiler_matches_oracle_on_random_maps():
+    """Differential fuzzing of the host map compiler against the oracle's parser: 1,500 random maps (random sizes, agents,
+    crossing beams, colours >= n_agents, starts on beams ...), some of them invalid on purpose — same facts or same error."""
+    import random
+
+    import lle_b200
+    from _util import random_map
+
+    rng = random.Random(20261018)
+    n_ok = n_err = 0
+    for _ in range(1500):
+        text = random_map(rng, allow_invalid=True)
+        try:
+            expect = _map_facts_oracle(text)
+        except lo.ParsingError as e:
+            with pytest.raises(lle_b200.ParsingError, match=str(e).split(" ")[0].split("{")[0]):
+                lle_b200.Map(text)
+            n_err += 1
+            continue
+        assert _map_facts_native(text) == expect, text
+        n_ok += 1
+    assert n_ok > 1000 and n_err > 100
+
+
 def test_map_errors():
     import lle_b200
 

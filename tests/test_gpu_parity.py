@@ -71,6 +71,12 @@ def test_config1_anchor_level1():
     run_pair([level_text(1)], None, 4096, 300, check_every=7, seed=1234)
 
 
+def test_config1_anchor_full_length():
+    """SURVEY 8d config 1 as specified: T = 10,000 steps x N = 4,096 envs of level 1, compared bit-exactly at 100+ points
+    of the rollout (every output and the raw engine state)."""
+    run_pair([level_text(1)], None, 4096, 10000, check_every=89, seed=4321)
+
+
 def test_config2_level6_full_size():
     """BASELINE config 2 at full size: lvl6, 65,536 envs, layered observations."""
     run_pair([level_text(6)], None, 65536, 12, seed=77)
@@ -178,6 +184,41 @@ def test_laser_source_mutators_in_a_batch():
         for t in range(80):
             ora.step(None); dev.vec.step(None)
             assert_same(dev, ora, dev.pull(), f"step {t} after re-enabling and moving the exits")
+
+
+def test_random_maps_fuzz():
+    """Differential fuzzing on the device: 400 random maps (crossing beams, foreign colours, voids, starts next to beams),
+    each stepped under Philox actions with a rotating observation type / reward / auto-reset setting."""
+    import random
+
+    from _util import random_map
+
+    rng = random.Random(777)
+    settings = [dict(), dict(obs_type="partial3x3"), dict(obs_type="perspective"), dict(reward_dim=4), dict(auto_reset=False),
+                dict(walkable_lasers=False), dict(obs_type="partial5x5", auto_reset=False), dict(pbrs=dict()),
+                dict(obs_type="layered-padded-1"), dict(obs_type="normalized-state", extras="laser_subgoal")]
+    n_run = 0
+    while n_run < 400:
+        text = random_map(rng)
+        try:
+            lo.World(text)
+        except lo.ParsingError:
+            continue
+        kw = dict(settings[n_run % len(settings)])
+        try:
+            ora, dev = make_pair([text], None, 48, seed=1000 + n_run, **kw)
+        except IndexError:  # a foreign colour selects a channel past the last layer: both sides must refuse
+            import lle_b200
+            with pytest.raises(IndexError):
+                lle_b200.VecLLE([text], 4, **{k: v for k, v in kw.items() if k in ("obs_type",)})
+            n_run += 1
+            continue
+        for t in range(40):
+            ora.step(None)
+            dev.vec.step(None)
+            if t % 3 == 0 or t == 39:
+                assert_same(dev, ora, dev.pull(), f"map {n_run} ({kw}) step {t}\n{text}")
+        n_run += 1
 
 
 def test_supplied_actions_with_invalid_ones():
