@@ -44,6 +44,11 @@ enum {
     LLE_PARSE_INVALID_AGENT_ID = 11,
     LLE_PARSE_INVALID_DIRECTION = 12,
     LLE_PARSE_AGENT_WITHOUT_START = 13,
+    LLE_PARSE_INCONSISTENT_WORLD_STRING_WIDTH = 14,  /* TOML v2 maps, src/core/parsing/toml/toml_config.rs */
+    LLE_PARSE_INCONSISTENT_WORLD_STRING_HEIGHT = 15,
+    LLE_PARSE_INCONSISTENT_NUMBER_OF_AGENTS = 16,
+    LLE_PARSE_POSITION_OUT_OF_BOUNDS = 17,
+    LLE_PARSE_UNKNOWN_TOML_KEY = 18,
     LLE_PARSE_UNSUPPORTED = 20,
     LLE_LIMIT_EXCEEDED = 21,
     LLE_RT_INVALID_ACTION = 101,
@@ -100,6 +105,10 @@ LLE_API int lle_map_get_info(const lle_map* map, lle_map_info* out);
  * starts} (world.rs:125-127, 236-238, 289-303) and the laser cells. Returns the count via *n. */
 enum { LLE_POS_WALLS = 0, LLE_POS_VOIDS = 1, LLE_POS_EXITS = 2, LLE_POS_GEMS = 3, LLE_POS_STARTS = 4, LLE_POS_LASER_CELLS = 5 };
 LLE_API int lle_map_positions(const lle_map* map, int kind, int32_t* out_ij, int32_t cap, int32_t* n);
+/* World::possible_starts (world.rs:297-303; `World.random_start_pos`): the start candidates of `agent` after the laser
+ * pruning of laser_setup (world_config.rs:225-243), row-major.  One entry for v1 maps; TOML v2 maps may give several, and
+ * World::reset then samples distinct starts (see lle_vec_reset). */
+LLE_API int lle_map_start_candidates(const lle_map* map, int32_t agent, int32_t* out_ij, int32_t cap, int32_t* n);
 /* World::sources() (world.rs:141-149): 7 ints per source: i, j, agent_id, direction(0 N,1 E,2 S,3 W), enabled, laser_id, beam_len */
 LLE_API int lle_map_sources(const lle_map* map, int32_t* out, int32_t cap, int32_t* n);
 /* World::lasers() (world.rs:159-172): 7 ints per laser tile: i, j, laser_id, agent_id, direction, beam index, offset in beam */
@@ -189,6 +198,17 @@ LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 /* World::reset / LLE.reset (world.rs:411-432, env.py:191-203) for every env, or for the envs whose byte in
  * `mask_dev` (device, u8[N]) is non-zero.  Rewrites obs/state/avail; clears reward/done/events/err of those envs. */
 LLE_API int lle_vec_reset(lle_vec* vec, const uint8_t* mask_dev, void* cuda_stream);
+/* Maps with several start candidates per agent (TOML v2): every reset — explicit or automatic — samples distinct start
+ * positions like sample_different (src/utils/mod.rs:39-86).  The reference draws from rand::StdRng, whose stream is not
+ * pinned by any test or lockfile; this library defines its own: for attempt n = 0..15, agent a draws word (a & 3) of
+ * Philox4x32-10(counter = (env_id_base + env, step count, 0x40000000 | n << 8 | a >> 2, number of explicit resets so far),
+ * key = seed) and probes its row-major sorted candidates cyclically from index mulhi(word, count); agents are served by
+ * increasing number of candidates (stable) and take the first candidate no earlier agent took; an agent with no free
+ * candidate fails the attempt; after 16 failed attempts a fixed assignment (bipartite matching) is used. */
+
+/* Re-exports observation / state / availability (and extras) of every env from its current engine state without resetting
+ * any (after lle_vec_set_source / lle_vec_set_exits, when the change should show before the next step). */
+LLE_API int lle_vec_refresh(lle_vec* vec, void* cuda_stream);
 
 /* World::step + LLE.step (world.rs:435-475, env.py:165-189) for every env in one kernel launch.
  * actions_dev: device i8[N, A] of Action values, or NULL to sample uniformly among the available
@@ -224,7 +244,7 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
  * switch.  Disabling turns the whole beam off, enabling turns the whole beam on (turn_on(0): whoever stands in it), and
  * both survive World::reset (laser.rs:168-171).  The colour is NOT checked against n_agents here (the engine does not,
  * world_config.rs:137-145; the Python setter does).  Observation / state / availability buffers keep showing the last
- * step until the next step or reset (lle_vec_reset with an all-zero mask re-exports every env without resetting any).
+ * step until the next step or reset (lle_vec_refresh re-exports every env without resetting any).
  * Synchronises `cuda_stream`.  lle_vec_get_sources: current (agent_id, enabled) pairs of the map's sources. */
 LLE_API int lle_vec_set_source(lle_vec* vec, int32_t map_index, int32_t source_index, int32_t agent_id, int32_t enabled, void* cuda_stream);
 LLE_API int lle_vec_get_sources(lle_vec* vec, int32_t map_index, int32_t* out_pairs, int32_t cap, int32_t* n);
@@ -247,6 +267,8 @@ LLE_API int lle_vec_set_state(lle_vec* vec, const int32_t* pos_dev, const uint8_
 LLE_API int lle_vec_export_raw(lle_vec* vec, int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
                        uint64_t* collected, uint8_t* counters, void* cuda_stream);
 
+/* World::seed (world.rs:92-96): the Philox key of the action sampler and of the start sampler. */
+LLE_API int lle_vec_set_seed(lle_vec* vec, uint64_t seed);
 /* Step counter used as the Philox counter word (incremented by every lle_vec_step). */
 LLE_API int lle_vec_get_step_count(lle_vec* vec, uint64_t* out);
 LLE_API int lle_vec_set_step_count(lle_vec* vec, uint64_t value);

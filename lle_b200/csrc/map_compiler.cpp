@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cstring>
+#include <functional>
 #include <sstream>
 
 namespace lle {
@@ -35,16 +36,9 @@ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 }  // namespace
 
-CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std::vector<SourceState>* source_state,
-                        const std::vector<Cell>* new_exits) {
-    if (spec.kind < LLE_OBS_LAYERED || spec.kind > LLE_OBS_STATE) throw MapError(LLE_INVALID_ARGUMENT, "unknown observation kind");
-    if (spec.kind == LLE_OBS_LAYERED && (spec.param < 0 || spec.param > 64)) throw MapError(LLE_INVALID_ARGUMENT, "padding_size out of range");
-    if (spec.kind == LLE_OBS_PARTIAL && (spec.param < 1 || spec.param % 2 != 1 || spec.param > 31))
-        throw MapError(LLE_INVALID_ARGUMENT, "Can only use odd numbers for the square size");  // observations.py:299
-    CompiledMap cm;
-    cm.text = text;
-
-    // ---- grammar (parser_v1.rs:132-175): lines, trimmed, blank lines skipped, whitespace-separated tokens
+// ---- v1 grammar (parser_v1.rs:132-175): lines, trimmed, blank lines skipped, whitespace-separated tokens
+RawConfig parse_v1_config(const std::string& text) {
+    RawConfig rc;
     std::vector<std::vector<Token>> rows;
     {
         std::istringstream lines(text);
@@ -103,31 +97,58 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         }
     }
     if (rows.empty()) throw MapError(LLE_PARSE_EMPTY_WORLD, "EmptyWorld");
-    const int H = (int)rows.size(), W = (int)rows[0].size();
-
+    rc.H = (int)rows.size();
+    rc.W = (int)rows[0].size();
     // ---- row-major collection (parser_v1.rs:147-161)
-    std::vector<std::vector<Cell>> starts;  // candidate starts per agent (<= 1 in v1)
-    for (int i = 0; i < H; ++i) {
-        for (int j = 0; j < W; ++j) {
+    for (int i = 0; i < rc.H; ++i) {
+        for (int j = 0; j < rc.W; ++j) {
             const Token& t = rows[i][j];
             Cell c{i, j};
             switch (t.kind) {
-                case 'G': cm.gems.push_back(c); break;
-                case '@': cm.walls.push_back(c); break;
-                case 'X': cm.exits.push_back(c); break;
-                case 'V': cm.voids.push_back(c); break;
+                case 'G': rc.gems.push_back(c); break;
+                case '@': rc.walls.push_back(c); break;
+                case 'X': rc.exits.push_back(c); break;
+                case 'V': rc.voids.push_back(c); break;
                 case 'S':
-                    if ((int)starts.size() <= t.id) starts.resize(t.id + 1);
-                    starts[t.id].push_back(c);
+                    if ((int)rc.starts.size() <= t.id) rc.starts.resize(t.id + 1);
+                    rc.starts[t.id].push_back(c);
                     break;
                 case 'L':
-                    cm.sources.push_back(SourceInfo{c, t.id, t.dir, (int)cm.sources.size(), 0, true});
-                    cm.walls.push_back(c);  // a source is also a wall (parser_v1.rs:22-25)
+                    rc.sources.push_back(RawSource{c, t.id, t.dir, (int)rc.sources.size()});
+                    rc.walls.push_back(c);  // a source is also a wall (parser_v1.rs:22-25)
                     break;
                 default: break;
             }
         }
     }
+    return rc;
+}
+
+// parsing::parse (src/core/parsing/mod.rs:14-21): TOML (v2) first, the v1 grammar when the text is not a v2 document
+RawConfig parse_config(const std::string& text) {
+    RawConfig rc;
+    if (parse_toml_config(text, rc)) return rc;
+    return parse_v1_config(text);
+}
+
+CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std::vector<SourceState>* source_state,
+                        const std::vector<Cell>* new_exits) {
+    if (spec.kind < LLE_OBS_LAYERED || spec.kind > LLE_OBS_STATE) throw MapError(LLE_INVALID_ARGUMENT, "unknown observation kind");
+    if (spec.kind == LLE_OBS_LAYERED && (spec.param < 0 || spec.param > 64)) throw MapError(LLE_INVALID_ARGUMENT, "padding_size out of range");
+    if (spec.kind == LLE_OBS_PARTIAL && (spec.param < 1 || spec.param % 2 != 1 || spec.param > 31))
+        throw MapError(LLE_INVALID_ARGUMENT, "Can only use odd numbers for the square size");  // observations.py:299
+    CompiledMap cm;
+    cm.text = text;
+    const RawConfig rc = parse_config(text);
+    const int H = rc.H, W = rc.W;
+    cm.gems = rc.gems; cm.walls = rc.walls; cm.exits = rc.exits; cm.voids = rc.voids;
+    std::vector<std::vector<Cell>> starts = rc.starts;  // candidate starts per agent (exactly one in v1)
+    for (const auto& s : rc.sources) cm.sources.push_back(SourceInfo{s.pos, s.colour, s.direction, s.laser_id, 0, true});
+    for (const auto* lst : {&cm.gems, &cm.walls, &cm.exits, &cm.voids})
+        for (const auto& c : *lst)
+            if (c.i < 0 || c.j < 0 || c.i >= H || c.j >= W) throw MapError(LLE_PARSE_POSITION_OUT_OF_BOUNDS, "PositionOutOfBounds");
+    for (const auto& s : cm.sources)  // the reference indexes its grid with the position and panics
+        if (s.pos.i < 0 || s.pos.j < 0 || s.pos.i >= H || s.pos.j >= W) throw MapError(LLE_PARSE_POSITION_OUT_OF_BOUNDS, "PositionOutOfBounds");
     // ---- pre_validate (world_config.rs:124-148)
     const int A = (int)starts.size();
     if (A == 0) throw MapError(LLE_PARSE_NO_AGENTS, "NoAgents");
@@ -141,8 +162,10 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
                                                            ", n_exits: " + std::to_string(new_exits->size()) + " }");
         for (const auto& c : *new_exits) {
             if (c.i < 0 || c.j < 0 || c.i >= H || c.j >= W) throw MapError(LLE_INDEX_ERROR, "exit position out of the world");
-            const char kind = rows[c.i][c.j].kind;
-            if (kind != '.' && kind != 'S' && kind != 'X')  // the reference panics: "Tile is not a floor"
+            auto in = [&](const std::vector<Cell>& lst) { return std::find(lst.begin(), lst.end(), c) != lst.end(); };
+            bool is_source = false;
+            for (const auto& src : cm.sources) is_source = is_source || src.pos == c;
+            if (in(cm.gems) || in(cm.voids) || in(cm.walls) || is_source)  // the reference panics: "Tile is not a floor"
                 throw MapError(LLE_INVALID_ARGUMENT, "an exit can only be placed on a floor tile");
         }
         cm.exits = *new_exits;
@@ -154,16 +177,24 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     for (auto& c : cm.voids) tiles[c.i * W + c.j] = LLE_T_VOID;
     for (auto& c : cm.walls) tiles[c.i * W + c.j] = LLE_T_WALL;
 
-    // ---- beams and start pruning (world_config.rs:203-250), sources in laser_id order
-    std::vector<std::vector<std::pair<int, int>>> cell_beams((size_t)H * W);  // (beam, offset), inner first
-    for (auto& s : cm.sources) {
+    // ---- beams and start pruning (world_config.rs:203-250), sources in list order.  A beam walks while the tile is
+    // walkable: it stops at walls and at the sources placed before it (the source tile is written after its beam, :247).
+    std::vector<std::vector<std::pair<int, int>>> cell_beams((size_t)H * W);  // (beam index, offset), inner first
+    std::vector<char> placed((size_t)H * W, 0);
+    for (int b = 0; b < (int)cm.sources.size(); ++b) {
+        auto& s = cm.sources[b];
         int i = s.pos.i + DI[s.direction], j = s.pos.j + DJ[s.direction];
         std::vector<Cell> cells;
-        while (i >= 0 && j >= 0 && i < H && j < W && (tiles[i * W + j] & 7u) != LLE_T_WALL) {
+        while (i >= 0 && j >= 0 && i < H && j < W && (tiles[i * W + j] & 7u) != LLE_T_WALL && !placed[i * W + j]) {
             cells.push_back(Cell{i, j});
             i += DI[s.direction];
             j += DJ[s.direction];
         }
+        for (int later = b + 1; later < (int)cm.sources.size(); ++later)
+            if (std::find(cells.begin(), cells.end(), cm.sources[later].pos) != cells.end())
+                // only possible with TOML [[lasers]] outside the wall list: the reference lets the earlier beam run through the
+                // cell and then overwrites its laser tile with the source, leaving `lasers_positions` inconsistent
+                throw MapError(LLE_PARSE_UNSUPPORTED, "a laser source sits on the beam of an earlier source");
         s.len = (int)cells.size();
         bool shielded = false;  // `is_blocked`: from the owner's single start on, the beam is cut at reset
         for (int k = 0; k < s.len; ++k) {
@@ -172,9 +203,11 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
             if (!shielded)
                 for (int a = 0; a < A; ++a)
                     if (a != s.colour) starts[a].erase(std::remove(starts[a].begin(), starts[a].end(), c), starts[a].end());
-            cell_beams[c.i * W + c.j].push_back({s.laser_id, k});
+            cell_beams[c.i * W + c.j].push_back({b, k});
         }
+        placed[s.pos.i * W + s.pos.j] = 1;
     }
+    for (const auto& s : cm.sources) tiles[s.pos.i * W + s.pos.j] = LLE_T_WALL;  // Tile::LaserSource is not walkable (tile.rs:63-73)
     if (new_exits)
         for (const auto& c : *new_exits)
             if (cell_beams[c.i * W + c.j].size() > 1)  // the reference's set_tile would drop the inner beam's tile there
@@ -183,10 +216,39 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     for (int a = 0; a < A; ++a)
         if (starts[a].empty())
             throw MapError(LLE_PARSE_AGENT_WITHOUT_START, "AgentWithoutStart { agent_id: " + std::to_string(a) + " }");
+    bool random_starts = false;
     for (int a = 0; a < A; ++a) {
-        if (starts[a].size() != 1) throw MapError(LLE_PARSE_UNSUPPORTED, "random start positions are not supported");
+        random_starts = random_starts || starts[a].size() != 1;
         cm.starts.push_back(starts[a][0]);
     }
+    cm.start_candidates = starts;
+    // sample_different (src/utils/mod.rs:39-86) visits the agents by increasing number of candidates (stable sort)
+    std::vector<int> order(A);
+    for (int a = 0; a < A; ++a) order[a] = a;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return starts[x].size() < starts[y].size(); });
+    if (random_starts) {
+        // a complete assignment of distinct starts must exist (the reference panics at the first reset otherwise): augmenting paths
+        std::vector<int> owner((size_t)H * W, -1);
+        std::function<bool(int, std::vector<char>&)> place = [&](int a, std::vector<char>& seen) {
+            for (const auto& c : starts[a]) {
+                const int cell = c.i * W + c.j;
+                if (seen[cell]) continue;
+                seen[cell] = 1;
+                if (owner[cell] < 0 || place(owner[cell], seen)) { owner[cell] = a; return true; }
+            }
+            return false;
+        };
+        for (int a = 0; a < A; ++a) {
+            std::vector<char> seen((size_t)H * W, 0);
+            if (!place(a, seen)) throw MapError(LLE_PARSE_NOT_ENOUGH_STARTS, "Could not assign positions to agents");
+        }
+        for (int cell = 0; cell < H * W; ++cell)  // the device's last resort when its sampling attempts all dead-end
+            if (owner[cell] >= 0) cm.starts[owner[cell]] = Cell{cell / W, cell % W};
+    }
+    // duplicated gem positions make World::gems() report one tile twice; the device format indexes gems by cell
+    for (size_t g = 0; g < cm.gems.size(); ++g)
+        for (size_t g2 = g + 1; g2 < cm.gems.size(); ++g2)
+            if (cm.gems[g] == cm.gems[g2]) throw MapError(LLE_PARSE_UNSUPPORTED, "a gem position is listed twice");
 
     // ---- device-format limits
     const int G = (int)cm.gems.size(), NB = (int)cm.sources.size();
@@ -319,6 +381,18 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     h.patch_off = (uint32_t)off;   off = align16(off + std::max<size_t>(patch.size(), 1) * sizeof(LlePatch));
     h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
     h.ap_off = (uint32_t)off;      off = align16(off + std::max<size_t>(planes.size(), 1) * sizeof(LleAgentPlane));
+    // start candidates (World.random_start_positions): per agent (first index, count), then the packed positions
+    std::vector<uint32_t> cand_index;
+    std::vector<uint16_t> cand_pos;
+    for (int a = 0; a < A; ++a) {
+        cand_index.push_back((uint32_t)cand_pos.size());
+        cand_index.push_back((uint32_t)starts[a].size());
+        for (const auto& c : starts[a]) cand_pos.push_back((uint16_t)((c.i << 8) | c.j));
+    }
+    h.random_starts = random_starts ? 1 : 0;
+    h.cand_index_off = (uint32_t)off; off = align16(off + cand_index.size() * sizeof(uint32_t));
+    h.cand_pos_off = (uint32_t)off;   off = align16(off + std::max<size_t>(cand_pos.size(), 1) * sizeof(uint16_t));
+    for (int a = 0; a < A; ++a) h.start_order[a] = (uint8_t)order[a];
     std::vector<uint32_t> chunk_tbl;  // patches are sorted by idx: chunk c owns entries [tbl[c], tbl[c+1])
     {
         const int n_chunks = (obs_floats + LLE_CHUNK_FLOATS - 1) / LLE_CHUNK_FLOATS;
@@ -373,6 +447,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
                 for (const auto& src : cm.sources)
                     if (src.pos.i == i && src.pos.j == j) info[c] |= (1u << 7) | ((uint32_t)src.colour << 16);
                 for (int n = 0; n < 4; ++n) cb[c].e[n] = LLE_NO_BEAM;
+                if (std::find(cm.walls.begin(), cm.walls.end(), Cell{i, j}) != cm.walls.end()) info[c] |= 1u << 25;
                 const auto& lst = cell_beams[c];
                 if (!lst.empty()) info[c] |= 1u << 24;
                 if (lst.size() > 4) throw MapError(LLE_LIMIT_EXCEEDED, "more than four beams cross one cell");
@@ -391,6 +466,8 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     if (!patch.empty()) std::memcpy(cm.blob.data() + h.patch_off, patch.data(), patch.size() * sizeof(LlePatch));
     std::memcpy(cm.blob.data() + h.static_off, stat.data(), stat.size() * sizeof(float));
     std::memcpy(cm.blob.data() + h.chunk_tbl_off, chunk_tbl.data(), chunk_tbl.size() * sizeof(uint32_t));
+    std::memcpy(cm.blob.data() + h.cand_index_off, cand_index.data(), cand_index.size() * sizeof(uint32_t));
+    if (!cand_pos.empty()) std::memcpy(cm.blob.data() + h.cand_pos_off, cand_pos.data(), cand_pos.size() * sizeof(uint16_t));
     if (!planes.empty()) std::memcpy(cm.blob.data() + h.ap_off, planes.data(), planes.size() * sizeof(LleAgentPlane));
     return cm;
 }

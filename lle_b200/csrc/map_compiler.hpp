@@ -43,10 +43,27 @@ struct LaserTileInfo {  // one entry of World::lasers() (outer two per cell), in
     int laser_id, colour, direction, beam, offset;
 };
 
+// What both map grammars produce before the world is built (WorldConfig, src/core/parsing/world_config.rs:12-22)
+struct RawSource {
+    Cell pos;
+    int colour, direction /* 0 N, 1 E, 2 S, 3 W */, laser_id;
+};
+struct RawConfig {
+    int H = 0, W = 0;
+    std::vector<Cell> gems, voids, exits, walls;
+    std::vector<std::vector<Cell>> starts;  // candidate start positions per agent
+    std::vector<RawSource> sources;
+};
+RawConfig parse_v1_config(const std::string& text);
+// TOML v2 (src/core/parsing/toml/*.rs).  Returns false when the text is not a v2 document (ParseError::NotV2: the caller
+// falls back to v1, parsing/mod.rs:14-21); throws MapError for v2 documents that are invalid.
+bool parse_toml_config(const std::string& text, RawConfig& out);
+
 struct CompiledMap {
     std::string text;
     int H = 0, W = 0, A = 0, G = 0, NB = 0, C = 0;
     std::vector<Cell> walls, voids, exits, gems, starts, laser_cells;
+    std::vector<std::vector<Cell>> start_candidates;  // World.random_start_positions (after the laser pruning)
     std::vector<SourceInfo> sources;
     std::vector<LaserTileInfo> lasers;
     int max_beam_len = 0;

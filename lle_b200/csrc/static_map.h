@@ -58,6 +58,7 @@ struct LleAgentPlane {
 //   cellinfo[cell]  : bits 0-2 base tile kind | bits 3-6 walkable-neighbour mask indexed by Action value
 //                     (N, S, E, W: in bounds and neither Wall nor LaserSource, tile.rs:63-73) | bit 7: the cell is a
 //                     laser source | bits 8-15 gem index | bits 16-23 colour of the source (bit 7 set) | bit 24: a beam crosses the cell
+//                     | bit 25: the cell is in World::walls() (every wall; sources too, except TOML [[lasers]] outside `walls`)
 //   cellbeams[cell] : the (at most four: one per direction of travel) beams crossing the cell, inner first.
 //                     entry = b (0-5) | k<<6 (6-11) | colour<<12 (12-19) | len<<20 (20-26) | enabled<<27 | listed<<28
 //                     (listed: the laser tile is one of the two reported by World::lasers(), world.rs:159-172);
@@ -91,7 +92,12 @@ struct LleMapHeader {
     uint32_t ap_off;               // LleAgentPlane[n_ap]
     uint32_t chunk_tbl_off;        // uint32_t[ceil(obs_floats / LLE_CHUNK_FLOATS) + 1]: patch index range of every chunk
     uint32_t pad1;
-    uint16_t start[LLE_MAX_AGENTS];   // packed position (i<<8 | j)
+    int32_t random_starts;         // some agent has several start candidates: World::reset samples (world.rs:421)
+    uint32_t cand_index_off;       // uint32_t[2*A]: first index and count of each agent's candidates in cand_pos
+    uint32_t cand_pos_off;         // uint16_t[]: packed candidate positions, sorted like AgentConfig::compute_start_positions
+    uint32_t pad3;
+    uint8_t start_order[LLE_MAX_AGENTS];  // agents by increasing number of candidates (stable), the order sample_different assigns them
+    uint16_t start[LLE_MAX_AGENTS];   // packed position (i<<8 | j); with random starts: the first candidate
     uint16_t gem_pos[LLE_MAX_GEMS];   // packed position, gems_positions order (parser_v1.rs:149)
 };
 

@@ -70,6 +70,7 @@ struct lle_vec {
     uint8_t* d_err = nullptr;
     uint32_t* d_sched = nullptr;        // kSchedSlots x {next pair, warps finished}
     uint32_t* d_flags = nullptr;        // [n_tickets] last completed step sequence number per ticket
+    uint32_t reset_epoch = 0;           // explicit resets so far (start-sampling counter word, random starts)
     uint32_t seq = 0;                   // sequence number of the last step launched
     uint32_t launch_index = 0;          // rotates the scheduler slots
     bool last_was_step = false;         // the previous launch on this vec was a step (may be overlapped via PDL)
@@ -225,6 +226,7 @@ KParams base_params(lle_vec* v) {
     p.pbrs_gamma = v->opts.pbrs_gamma; p.pbrs_value = v->opts.pbrs_reward_value;
     std::memcpy(p.extras_beam, v->extras_beam, sizeof p.extras_beam);
     p.timeline = v->d_timeline;
+    p.reset_epoch = v->reset_epoch;
     return p;
 }
 
@@ -297,6 +299,17 @@ int lle_map_positions(const lle_map* map, int kind, int32_t* out_ij, int32_t cap
     for (int k = 0; k < (int)v->size() && k < cap && out_ij; ++k) {
         out_ij[2 * k] = (*v)[k].i;
         out_ij[2 * k + 1] = (*v)[k].j;
+    }
+    return LLE_OK;
+}
+
+int lle_map_start_candidates(const lle_map* map, int32_t agent, int32_t* out_ij, int32_t cap, int32_t* n) {
+    if (!map || !n || agent < 0 || agent >= map->cm.A) return fail(LLE_INVALID_ARGUMENT, "bad argument");
+    const auto& v = map->cm.start_candidates[(size_t)agent];
+    *n = (int32_t)v.size();
+    for (int k = 0; k < (int)v.size() && k < cap && out_ij; ++k) {
+        out_ij[2 * k] = v[k].i;
+        out_ij[2 * k + 1] = v[k].j;
     }
     return LLE_OK;
 }
@@ -653,9 +666,22 @@ int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
     if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     LLE_CUDA(cudaSetDevice(v->device));
+    v->reset_epoch++;
     KParams p = base_params(v);
     p.mode = MODE_RESET;
     p.reset_mask = mask_dev;
+    LLE_CUDA(launch(v, p, (cudaStream_t)stream));
+    v->launches++;
+    return LLE_OK;
+}
+
+int lle_vec_refresh(lle_vec* v, void* stream) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    LLE_CUDA(cudaSetDevice(v->device));
+    KParams p = base_params(v);
+    p.mode = MODE_RESET;
+    p.refresh_only = 1;
     LLE_CUDA(launch(v, p, (cudaStream_t)stream));
     v->launches++;
     return LLE_OK;
@@ -807,6 +833,7 @@ int lle_vec_debug_timeline(lle_vec* v, uint64_t* out_host, int64_t cap_warps, in
     return LLE_OK;
 }
 
+int lle_vec_set_seed(lle_vec* v, uint64_t seed) { if (!v) return fail(LLE_INVALID_ARGUMENT, "null"); v->opts.seed = seed; return LLE_OK; }
 int lle_vec_get_step_count(lle_vec* v, uint64_t* out) { if (!v || !out) return fail(LLE_INVALID_ARGUMENT, "null"); *out = v->t; return LLE_OK; }
 int lle_vec_set_step_count(lle_vec* v, uint64_t value) { if (!v) return fail(LLE_INVALID_ARGUMENT, "null"); v->t = value; return LLE_OK; }
 int lle_vec_launch_count(lle_vec* v, uint64_t* out) { if (!v || !out) return fail(LLE_INVALID_ARGUMENT, "null"); *out = v->launches; return LLE_OK; }

@@ -108,6 +108,8 @@ struct KParams {
     // host-mapped word that receives the sequence number of the last step of this launch when the launch retires: lets the
     // host see how many step launches are still in flight (a scheduling hint only, see launch_mode in vec_world.cu)
     volatile uint32_t* retired_seq;
+    uint32_t reset_epoch;  // number of explicit resets of the vec so far: part of the start-sampling counter (random starts)
+    uint32_t refresh_only; // MODE_RESET launch that resets no env: re-exports observation / state / availability only
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -417,12 +419,63 @@ struct World {
     }
     // World::reset (world.rs:411-432) with one start per agent (RNG-free, utils/mod.rs:63), then
     // RewardStrategy.reset / LLE.reset bookkeeping (env.py:191-203).
-    __device__ __forceinline__ void reset(bool on, uint64_t pbrs_set) {
+    // sample_different (src/utils/mod.rs:39-86) for maps whose agents have several start candidates (TOML v2 maps).  The
+    // reference draws from rand::StdRng (unpinned); the stream here is this library's own contract, restated by the oracle:
+    // attempt n = 0..15: agent a draws word (a & 3) of Philox4x32-10(counter = (env id, step, 0x40000000 | n << 8 | a >> 2,
+    // reset epoch), key = seed) and starts probing its (row-major sorted) candidates at k = mulhi(word, count); agents are
+    // served by increasing number of candidates (stable) and take the first candidate, cyclically from k, that no earlier
+    // agent took; an agent without a free candidate fails the attempt.  After 16 failed attempts the assignment computed
+    // by the map compiler (a bipartite matching, hdr->start) is used.
+    __device__ __forceinline__ void sample_starts(bool on, uint32_t env_lo, uint32_t t32, uint32_t epoch, uint64_t seed) {
+        const uint32_t* cidx = reinterpret_cast<const uint32_t*>(m.blob + m.hdr->cand_index_off);
+        const uint16_t* cpos = reinterpret_cast<const uint16_t*>(m.blob + m.hdr->cand_pos_off);
+        const bool mine = on && gl < A;
+        uint32_t first = 0, n = 1;
+        if (mine) { first = cidx[2 * gl]; n = cidx[2 * gl + 1]; }
+        bool need = on;  // group-uniform
+        for (uint32_t attempt = 0; attempt < 16u; ++attempt) {
+            if (!__any_sync(kFull, need)) break;
+            uint32_t r[4];
+            philox4x32_10(env_lo, t32, 0x40000000u | (attempt << 8) | (uint32_t)(gl >> 2), epoch, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            const uint32_t word = (gl & 3) == 0 ? r[0] : (gl & 3) == 1 ? r[1] : (gl & 3) == 2 ? r[2] : r[3];
+            const uint32_t k = __umulhi(word, n);
+            uint32_t my = 0xFFFFFFFFu;  // this agent's pick, once made
+            bool failed = false;         // group-uniform
+            for (int i = 0; i < A; ++i) {
+                const int a = on ? (int)m.hdr->start_order[i] : 0;
+                const uint32_t na = gshfl(n, a);
+                uint32_t probe = 0;
+                bool settled = !need || failed;  // group-uniform
+                while (__any_sync(kFull, !settled)) {
+                    uint32_t c = 0xFFFFFFFEu;
+                    if (mine && gl == a) c = cpos[first + (k + probe) % n];
+                    c = gshfl(c, a);
+                    const bool clash = gballot(my == c) != 0;
+                    if (!settled) {
+                        if (!clash) {
+                            if (gl == a) my = c;
+                            settled = true;
+                        } else if (++probe >= na) {
+                            failed = true;
+                            settled = true;
+                        }
+                    }
+                }
+            }
+            if (need && !failed) {
+                if (mine) pos = my;
+                need = false;
+            }
+        }
+    }
+    __device__ __forceinline__ void reset(bool on, uint64_t pbrs_set, uint32_t env_lo = 0, uint32_t t32 = 0, uint32_t epoch = 0,
+                                          uint64_t seed = 0) {
         tiles_reset(on);
         if (on) {
             alive = amask; arrived = 0; n_arrived = 0; n_deads = 0; done = 0;
             pos = gl < A ? (uint32_t)m.hdr->start[gl] : 0u;
         }
+        if (__any_sync(kFull, on && m.hdr->random_starts)) sample_starts(on && m.hdr->random_starts, env_lo, t32, epoch, seed);
         pre_enter_all(on, pos, alive);
         (void)enter_all(on, pos);  // events are dropped (world.rs:428-430)
         if (on) {
@@ -821,8 +874,8 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     shaped = __dsub_rn(__dmul_rn(p.pbrs_gamma, prev), curr);  // no fused multiply-add, like CPython
                 }
             } else if constexpr (MODE == MODE_RESET) {
-                const bool on = !p.reset_mask || !real || p.reset_mask[env];
-                w.reset(on, p.pbrs_set);
+                const bool on = !p.refresh_only && (!p.reset_mask || !real || p.reset_mask[env]);
+                w.reset(on, p.pbrs_set, (uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, p.reset_epoch, p.seed);
                 touch = on;
             } else {  // MODE_SET_STATE: World::set_state (world.rs:515-597) + LLE.set_state (env.py:208-216)
                 touch = real;  // padding worlds: nothing to force
@@ -898,7 +951,8 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             // auto-reset: the transition above is reported; observation / state / availability below are those
             // of the freshly reset world (SURVEY §8d "Auto-reset")
             const bool do_reset = MODE == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
-            if (__any_sync(kFull, do_reset)) w.reset(do_reset, p.pbrs_set);
+            if (__any_sync(kFull, do_reset))
+                w.reset(do_reset, p.pbrs_set, (uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, p.reset_epoch, p.seed);
 
             // compute_available_actions (world.rs:343-363) closes reset (:431), step (:473) and a successful set_state
             // (:595, also reached by the restore at :563); a set_state that fails with InvalidWorldState returns before it,
@@ -1118,7 +1172,9 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         float* o = sub + a * Cp * s2 + r;
                         const uint32_t kind = info & 7u;
                         if (kind == LLE_T_WALL) {
-                            o[A * s2] = 1.0f;  // WALL = n_agents; wall_pos includes the sources (parser_v1.rs:22-25)
+                            // WALL = n_agents; wall_pos holds the walls and the v1 sources (parser_v1.rs:22-25), but not
+                            // the sources of a TOML [[lasers]] table
+                            if (info & (1u << 25)) o[A * s2] = 1.0f;
                             if (info & 128u) {
                                 const int ch = A + 1 + (int)((info >> 16) & 255u);  // LASER_0 + source.agent_id, fill -1 (:348-350)
                                 if (ch < Cp) o[ch * s2] = -1.0f;

@@ -59,6 +59,18 @@ class Map:
     starts = property(lambda self: self.positions(4))
     laser_cells = property(lambda self: self.positions(5))
 
+    @property
+    def random_starts(self) -> list[list[tuple[int, int]]]:
+        """World.random_start_pos (world.rs:297-303): the start candidates of every agent."""
+        out = []
+        for a in range(self.n_agents):
+            n = C.c_int32(0)
+            check(lib().lle_map_start_candidates(self._h, a, None, 0, C.byref(n)))
+            buf = (C.c_int32 * max(1, 2 * n.value))()
+            check(lib().lle_map_start_candidates(self._h, a, buf, n.value, C.byref(n)))
+            out.append([(buf[2 * k], buf[2 * k + 1]) for k in range(n.value)])
+        return out
+
     def sources(self) -> list[LaserSource]:
         n = C.c_int32(0)
         check(lib().lle_map_sources(self._h, None, 0, C.byref(n)))
@@ -258,10 +270,14 @@ class VecWorld:
         check(lib().lle_vec_get_sources(self._h, int(map_index), buf, n.value, C.byref(n)))
         return [(int(buf[2 * k]), bool(buf[2 * k + 1])) for k in range(n.value)]
 
+    def seed(self, seed: int):
+        """World::seed (world.rs:92-96): Philox key of the action sampler and of the start sampler."""
+        check(lib().lle_vec_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+
     def refresh(self):
         """Re-export observation / state / availability of every env from its current engine state, resetting none
-        (lle_vec_reset with an all-zero mask)."""
-        self.reset(torch.zeros((self.n_envs,), dtype=torch.uint8, device=self.device))
+        (lle_vec_refresh)."""
+        check(lib().lle_vec_refresh(self._h, _stream_ptr(self.device)))
 
     def submit_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor):
         """Pipelined host-facing step (lle_vec_pipeline_submit): enqueue H2D actions -> step -> D2H reward/done on the vec's

@@ -55,6 +55,8 @@ class _Single:
         self._vec = VecWorld(m, 1, device=device, **vec_kw)
         self._laser_tiles = m.laser_tiles()
         self._sources = m.sources()
+        self._random_starts = any(len(c) != 1 for c in m.random_starts)
+        self._after_reset()
 
     # ---- state queries (one small D2H each)
     def _raw(self):
@@ -110,12 +112,25 @@ class _Single:
         self._exits = exits
 
     exit_pos = property(lambda self: getattr(self, "_exits", None) or self._map.exits, _set_exit_pos)
-    start_pos = property(lambda self: self._map.starts)
+    @property
+    def start_pos(self):
+        """World::starts (world.rs:289-291): where the agents were placed by the last reset."""
+        if not self._random_starts:
+            return self._map.starts
+        return list(self._last_starts)
     laser_pos = property(lambda self: self._map.laser_cells)
 
     @property
     def random_start_pos(self):
-        return [[p] for p in self._map.starts]
+        return self._map.random_starts
+
+    def seed(self, seed_value: int):
+        """World::seed (world.rs:92-96).  The start sampler's stream is this library's own (include/lle_b200.h, lle_vec_reset)."""
+        self._vec.seed(seed_value)
+
+    def _after_reset(self):
+        if self._random_starts:
+            self._last_starts = self.agents_positions
 
     @property
     def n_laser_colours(self) -> int:
@@ -196,6 +211,7 @@ class World(_Single):
 
     def reset(self):
         self._vec.reset()
+        self._after_reset()
 
     def step(self, actions) -> list[WorldEvent]:
         acts = _check_actions(actions, self.n_agents)
@@ -338,6 +354,7 @@ class LLE(_Single):
 
     def reset(self):
         self._vec.reset()
+        self._after_reset()
         self.last_extras = self.extras()
         return self.observe(), self.get_state()
 

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <optional>
 #include <sstream>
@@ -127,6 +128,30 @@ struct RuntimeWorldError : std::runtime_error {
     long a = 0, b = 0, c = 0;
     RuntimeWorldError(RuntimeErrorKind k, const std::string& msg, long a_ = 0, long b_ = 0, long c_ = 0)
         : std::runtime_error(msg), kind(k), a(a_), b(b_), c(c_) {}
+};
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), restated from the published algorithm.
+// Pinned by the Random123 known-answer vectors in tests/test_oracle_philox.py.
+struct Philox {
+    static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+        uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32);
+        lo = (uint32_t)p;
+    }
+    static void run(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+        uint32_t k0 = key[0], k1 = key[1];
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, c0, hi0, lo0);
+            mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+            uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
 };
 
 // src/agent.rs:6-49
@@ -344,6 +369,11 @@ class World {
     std::vector<Position> start_positions;
     std::vector<bool> conflict_scratch;
     std::string source_text;  // what the world was parsed from (pickle/clone convenience)
+    // Start sampling (random starts, TOML v2 maps).  The reference owns a rand::StdRng seeded by World::seed (world.rs:80,
+    // :92-96) whose stream is PARITY UNPINNED (no lockfile, no test pins the values).  The device library defines its own
+    // Philox stream (include/lle_b200.h, lle_vec_reset); the harness sets its counter words before every reset.
+    uint64_t rng_seed = 0;
+    uint32_t rng_env = 0, rng_t = 0, rng_epoch = 1;
     // Bookkeeping that is NOT in the reference: the move_agents pass (1, 2, ...) that emitted each
     // event of the last step(), so tests can check the device's (pass, agent) event encoding.
     std::vector<int> last_event_pass;
@@ -598,9 +628,10 @@ class World {
     }
 
   private:
-    // src/utils/mod.rs:39-86, restricted to the RNG-free case (every candidate list has one
-    // entry, :62-65 never shuffles).  The backtracking and the final `result[id]` re-indexing
-    // (:82) are kept as written.
+    // src/utils/mod.rs:39-86.  With one candidate per agent no RNG is consumed (:62-65 never shuffles) and the backtracking
+    // and the final `result[id]` re-indexing (:82) are kept as written.  With several candidates the draw order follows
+    // the device library's documented contract (attempts, Philox words, cyclic probing; after 16 dead-ended attempts the
+    // fixed assignment of a bipartite matching), because rand::StdRng::shuffle cannot be reproduced.
     std::vector<Position> sample_different() const {
         const auto& starts = random_start_positions;
         size_t n = starts.size();
@@ -608,6 +639,9 @@ class World {
         for (size_t i = 0; i < n; ++i) idx[i] = i;
         std::stable_sort(idx.begin(), idx.end(),
                          [&](size_t x, size_t y) { return starts[x].size() < starts[y].size(); });
+        bool random = false;
+        for (const auto& c : starts) random = random || c.size() != 1;
+        if (random) return sample_different_philox(idx);
         std::vector<Position> result;
         assign_positions(0, idx, starts, result);
         if (result.size() != n) throw RuntimeWorldError(RuntimeErrorKind::Panic, "Could not assign positions to agents");
@@ -615,14 +649,57 @@ class World {
         for (size_t id : idx) out.push_back(result[id]);
         return out;
     }
+    std::vector<Position> sample_different_philox(const std::vector<size_t>& order) const {
+        const auto& starts = random_start_positions;
+        const size_t n = starts.size();
+        const uint32_t key[2] = {(uint32_t)rng_seed, (uint32_t)(rng_seed >> 32)};
+        for (uint32_t attempt = 0; attempt < 16; ++attempt) {
+            std::vector<Position> pick(n);
+            std::vector<bool> has(n, false);
+            bool failed = false;
+            for (size_t a : order) {
+                const uint32_t ctr[4] = {rng_env, rng_t, 0x40000000u | (attempt << 8) | (uint32_t)(a >> 2), rng_epoch};
+                uint32_t out[4];
+                Philox::run(ctr, key, out);
+                const uint32_t cnt = (uint32_t)starts[a].size();
+                const uint32_t k = (uint32_t)(((uint64_t)out[a & 3] * cnt) >> 32);
+                bool found = false;
+                for (uint32_t probe = 0; probe < cnt && !found; ++probe) {
+                    const Position& c = starts[a][(k + probe) % cnt];
+                    bool taken = false;
+                    for (size_t b = 0; b < n; ++b) taken = taken || (has[b] && pick[b] == c);
+                    if (!taken) { pick[a] = c; has[a] = true; found = true; }
+                }
+                if (!found) { failed = true; break; }
+            }
+            if (!failed) return pick;
+        }
+        // last resort: a fixed assignment by augmenting paths over the agents in id order, candidates in list order
+        const size_t cells = width * height;
+        std::vector<long> owner(cells, -1);
+        std::function<bool(size_t, std::vector<bool>&)> place = [&](size_t a, std::vector<bool>& seen) {
+            for (const auto& c : starts[a]) {
+                const size_t cell = c.i * width + c.j;
+                if (seen[cell]) continue;
+                seen[cell] = true;
+                if (owner[cell] < 0 || place((size_t)owner[cell], seen)) { owner[cell] = (long)a; return true; }
+            }
+            return false;
+        };
+        for (size_t a = 0; a < n; ++a) {
+            std::vector<bool> seen(cells, false);
+            if (!place(a, seen)) throw RuntimeWorldError(RuntimeErrorKind::Panic, "Could not assign positions to agents");
+        }
+        std::vector<Position> out(n);
+        for (size_t cell = 0; cell < cells; ++cell)
+            if (owner[cell] >= 0) out[(size_t)owner[cell]] = Position{cell / width, cell % width};
+        return out;
+    }
     static bool assign_positions(size_t i, const std::vector<size_t>& idx,
                                  const std::vector<std::vector<Position>>& starts,
                                  std::vector<Position>& result) {
         if (idx.empty()) return true;
         const auto& possible = starts[idx[i]];
-        if (possible.size() > 1)
-            throw RuntimeWorldError(RuntimeErrorKind::Panic,
-                                    "random start positions are outside the oracle's pinned scope");
         for (const auto& pos : possible) {
             if (std::find(result.begin(), result.end(), pos) == result.end()) {
                 result.push_back(pos);
@@ -833,9 +910,58 @@ inline WorldConfig parse_v1(const std::string& world_str) {
     return cfg;
 }
 
+// A WorldConfig written out field by field.  TOML v2 maps are deserialised by oracle/toml_config.py (tomllib + a
+// restatement of src/core/parsing/toml/*.rs) and handed over in this form:
+//   %LLE-CONFIG / size H W / gems n i j ... / voids n ... / exits n ... / walls n ... / agents A / A x "starts n i j ..." /
+//   lasers n / n x "laser i j agent_id direction(0 N,1 E,2 S,3 W) laser_id"
+inline WorldConfig parse_config_text(const std::string& text) {
+    // tokens are read as strings and converted with std::stoul (iostream number parsing depends on the process locale)
+    std::istringstream in(text);
+    std::string word;
+    WorldConfig cfg;
+    auto expect = [&](const char* w) {
+        if (!(in >> word) || word != w) throw std::invalid_argument(std::string("config text: expected ") + w);
+    };
+    auto number = [&]() -> size_t {
+        if (!(in >> word)) throw std::invalid_argument("config text: truncated");
+        return (size_t)std::stoul(word);
+    };
+    auto positions = [&](const char* name) {
+        expect(name);
+        std::vector<Position> out(number());
+        for (auto& p : out) {
+            p.i = number();
+            p.j = number();
+        }
+        return out;
+    };
+    expect("%LLE-CONFIG");
+    expect("size");
+    cfg.height = number();
+    cfg.width = number();
+    cfg.gems = positions("gems");
+    cfg.voids = positions("voids");
+    cfg.exits = positions("exits");
+    cfg.walls = positions("walls");
+    expect("agents");
+    const size_t n_agents = number();
+    for (size_t a = 0; a < n_agents; ++a) cfg.random_starts.push_back(positions("starts"));
+    expect("lasers");
+    const size_t n_lasers = number();
+    for (size_t k = 0; k < n_lasers; ++k) {
+        expect("laser");
+        Position pos;
+        pos.i = number();
+        pos.j = number();
+        const size_t agent = number(), dir = number(), laser_id = number();
+        cfg.lasers.emplace_back(pos, LaserConfig{(Direction)dir, agent, laser_id});
+    }
+    return cfg;
+}
+
 inline World parse_world(const std::string& text) {
-    // parsing/mod.rs:14-21 tries TOML first; TOML (v2) maps are outside the oracle's scope.
-    World w = parse_v1(text).into_world();
+    // parsing/mod.rs:14-21 tries TOML first, then v1.  TOML arrives here already deserialised (see parse_config_text).
+    World w = text.rfind("%LLE-CONFIG", 0) == 0 ? parse_config_text(text).into_world() : parse_v1(text).into_world();
     w.source_text = text;
     return w;
 }

@@ -167,6 +167,50 @@ def _check(status: int):
         _raise(status)
 
 
+# ------------------------------------------------------------------ map text (parsing/mod.rs:14-21: TOML v2 first, then v1)
+def v1_config(world_str: str) -> dict:
+    """parse_v1 (parser_v1.rs:132-175) as a dict of position lists; raises ParsingError like the reference."""
+    buf = C.create_string_buffer(1 << 20)
+    _check(lib().lleo_v1_config_text(world_str.encode(), buf, len(buf)))
+    tok = buf.value.decode().split()
+    k = 0
+
+    def take(name):
+        nonlocal k
+        assert tok[k] == name, (tok[k], name)
+        n = int(tok[k + 1])
+        out = [(int(tok[k + 2 + 2 * q]), int(tok[k + 3 + 2 * q])) for q in range(n)]
+        k += 2 + 2 * n
+        return out
+
+    assert tok[0] == "%LLE-CONFIG" and tok[1] == "size"
+    cfg = dict(height=int(tok[2]), width=int(tok[3]))
+    k = 4
+    for name in ("gems", "voids", "exits", "walls"):
+        cfg[name] = take(name)
+    n_agents = int(tok[k + 1])
+    k += 2
+    cfg["starts"] = [take("starts") for _ in range(n_agents)]
+    n_lasers = int(tok[k + 1])
+    k += 2
+    cfg["lasers"] = []
+    for _ in range(n_lasers):
+        cfg["lasers"].append(tuple(int(x) for x in tok[k + 1:k + 6]))
+        k += 6
+    return cfg
+
+
+def prepare_map_text(text: str) -> bytes:
+    """What the C++ oracle is given for a map: v1 text as is, a TOML v2 document as the config text of its WorldConfig."""
+    from . import toml_config
+
+    try:
+        cfg = toml_config.to_config_text(text)
+    except toml_config.TomlMapError as e:
+        raise ParsingError(str(e)) from None
+    return (cfg if cfg is not None else text).encode()
+
+
 # ------------------------------------------------------------------ levels
 def level_text(n: int) -> str:
     """The six built-in maps, committed as fixtures under tests/golden/levels/ (copied verbatim from
@@ -272,7 +316,7 @@ class World:
 
     def __init__(self, map_str: str):
         st = C.c_int(0)
-        self._h = C.c_void_p(lib().lleo_world_new(map_str.encode(), C.byref(st)))
+        self._h = C.c_void_p(lib().lleo_world_new(prepare_map_text(map_str), C.byref(st)))
         _check(st.value)
         self.map_str = map_str
         d = (C.c_int * 8)()
@@ -404,7 +448,19 @@ class World:
 
     @property
     def random_start_pos(self):
-        return self._random_starts
+        """World::possible_starts (world.rs:297-303)."""
+        buf = (C.c_long * 200000)()
+        n = lib().lleo_world_random_starts(self._h, buf, len(buf))
+        out, k = [], 0
+        while k < n:
+            cnt = buf[k]
+            out.append([(int(buf[k + 1 + 2 * q]), int(buf[k + 2 + 2 * q])) for q in range(cnt)])
+            k += 1 + 2 * cnt
+        return out
+
+    def seed(self, seed_value: int):
+        """World::seed (world.rs:92-96); the start sampler's stream is the device library's contract (lle_oracle.hpp)."""
+        lib().lleo_world_seed(self._h, C.c_uint64(int(seed_value) & 0xFFFFFFFFFFFFFFFF))
 
     @property
     def n_laser_colours(self):
@@ -497,7 +553,7 @@ class LLE:
         """extras: None | "laser_subgoal" | list of source indices.  pbrs: None | dict(gamma=0.99, reward_value=0.5,
         lasers_to_reward=None (all) | list of source indices, with_extras=True) — Builder.pbrs (builder.py:77-110)."""
         st = C.c_int(0)
-        self._h = C.c_void_p(lib().lleo_env_new(map_str.encode(), int(multi_objective), int(walkable_lasers), C.byref(st)))
+        self._h = C.c_void_p(lib().lleo_env_new(prepare_map_text(map_str), int(multi_objective), int(walkable_lasers), C.byref(st)))
         _check(st.value)
         extras_src = None if extras in (None, "laser_subgoal") else list(extras)
         want_extras = extras is not None
@@ -592,7 +648,7 @@ class OracleVec:
     def __init__(self, maps: Sequence[str], map_of_env: Sequence[int] | None, n_envs: int, *, multi_objective=False,
                  walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0, extras=None, pbrs=None,
                  obs_type: str = "layered", padding_size: int = 0):
-        texts = (C.c_char_p * len(maps))(*[m.encode() for m in maps])
+        texts = (C.c_char_p * len(maps))(*[prepare_map_text(m) for m in maps])
         moe = None if map_of_env is None else (C.c_int * n_envs)(*[int(m) for m in map_of_env])
         st = C.c_int(0)
         self._h = C.c_void_p(lib().lleo_vec_new(texts, len(maps), moe, n_envs, int(multi_objective), int(walkable_lasers),

@@ -47,29 +47,7 @@ int guarded(F&& f) {
     }
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11), restated from the published algorithm.
-// Pinned by the Random123 known-answer vectors in tests/test_oracle_philox.py.
-struct Philox {
-    static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-        uint64_t p = (uint64_t)a * b;
-        hi = (uint32_t)(p >> 32);
-        lo = (uint32_t)p;
-    }
-    static void run(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
-        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
-        uint32_t k0 = key[0], k1 = key[1];
-        for (int r = 0; r < 10; ++r) {
-            uint32_t hi0, lo0, hi1, lo1;
-            mulhilo(0xD2511F53u, c0, hi0, lo0);
-            mulhilo(0xCD9E8D57u, c2, hi1, lo1);
-            uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-            k0 += 0x9E3779B9u;
-            k1 += 0xBB67AE85u;
-        }
-        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-    }
-};
+using lle_oracle::Philox;  // restated in lle_oracle.hpp (the start sampler of World::reset needs it too)
 
 // Action rule: counter = (env_id, step_lo, agent/4, step_hi), key = (seed_lo, seed_hi);
 // agent a takes word a%4; action = k-th set bit of the availability mask in Action.value order,
@@ -119,6 +97,11 @@ struct Vec {
     size_t OF = 0;  // floats of one env's observation block (ObsGen::floats)
     bool auto_reset = false;
     uint64_t seed = 0, env_id_base = 0, t = 0;
+    uint32_t reset_epoch = 1;  // explicit resets so far (the construction reset is the first)
+    void arm_rng(size_t e, uint64_t step) {  // counter words of the start sampler for a reset of env e at step `step`
+        World& w = envs[e]->world;
+        w.rng_seed = seed; w.rng_env = (uint32_t)(env_id_base + e); w.rng_t = (uint32_t)step; w.rng_epoch = reset_epoch;
+    }
     std::vector<float> obs, state, reward, extras;  // extras: LaserSubgoal flags [N, A, JE]
     size_t JE = 0;
     std::vector<uint8_t> avail, done, events, err;
@@ -192,7 +175,10 @@ struct Vec {
             }
         }
         done[e] = env.done;
-        if (env.done && auto_reset && err[e] == 0) env.reset();
+        if (env.done && auto_reset && err[e] == 0) {
+            arm_rng(e, t);
+            env.reset();
+        }
         export_env(e);
     }
 };
@@ -206,6 +192,40 @@ const char* lleo_last_error() { return g_last_error.c_str(); }
 void lleo_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { Philox::run(ctr, key, out); }
 int lleo_sample_action(uint64_t seed, uint32_t env_id, uint64_t step, uint32_t agent, uint32_t mask5) {
     return sample_action(seed, env_id, step, agent, mask5);
+}
+
+// parse_v1 (parser_v1.rs:132-175) of a world string, written out in the config-text form (lle_oracle.hpp:
+// parse_config_text) — oracle/toml_config.py completes a v2 document with it (toml_config.rs:36-95).
+int lleo_v1_config_text(const char* text, char* out, long cap) {
+    return guarded([&] {
+        WorldConfig cfg = parse_v1(text);
+        std::string os;  // std::to_string, not iostream formatting (locale-independent)
+        auto num = [&](size_t v) { os += " " + std::to_string(v); };
+        auto positions = [&](const char* name, const std::vector<Position>& v) {
+            os += name;
+            num(v.size());
+            for (const auto& p : v) { num(p.i); num(p.j); }
+            os += "\n";
+        };
+        os += "%LLE-CONFIG\nsize";
+        num(cfg.height); num(cfg.width);
+        os += "\n";
+        positions("gems", cfg.gems);
+        positions("voids", cfg.voids);
+        positions("exits", cfg.exits);
+        positions("walls", cfg.walls);
+        os += "agents"; num(cfg.random_starts.size()); os += "\n";
+        for (const auto& s : cfg.random_starts) positions("starts", s);
+        os += "lasers"; num(cfg.lasers.size()); os += "\n";
+        for (const auto& l : cfg.lasers) {
+            os += "laser";
+            num(l.first.i); num(l.first.j); num(l.second.agent_id); num((size_t)l.second.direction); num(l.second.laser_id);
+            os += "\n";
+        }
+        const std::string& str = os;
+        if ((long)str.size() + 1 > cap) throw std::invalid_argument("config text buffer too small");
+        std::memcpy(out, str.c_str(), str.size() + 1);
+    });
 }
 
 // ---------------------------------------------------------------- World
@@ -227,12 +247,35 @@ void lleo_world_dims(void* p, int* out) {
     out[4] = (int)w.laser_source_positions.size(); out[5] = (int)w.exits.size();
     out[6] = (int)w.wall_positions.size(); out[7] = (int)w.void_positions.size();
 }
-int lleo_world_reset(void* p) { return guarded([&] { ((WorldHandle*)p)->w.reset(); }); }
+// counter words of the start sampler, kept like the device's N = 1 facade keeps them: the construction reset is explicit
+// reset number 1, every later reset() adds one, every step() call (failed ones included) advances the step count
+int lleo_world_reset(void* p) {
+    World& w = ((WorldHandle*)p)->w;
+    w.rng_epoch++;
+    return guarded([&] { w.reset(); });
+}
+void lleo_world_seed(void* p, uint64_t seed) { ((WorldHandle*)p)->w.rng_seed = seed; }
+void lleo_env_seed(void* p, uint64_t seed) { ((Env*)p)->world.rng_seed = seed; }
+// out: per agent the candidate count, then the (i, j) pairs, agent after agent; returns the number of ints written
+int lleo_world_random_starts(void* p, long* out, int cap) {
+    const World& w = ((WorldHandle*)p)->w;
+    int n = 0;
+    for (const auto& c : w.random_start_positions) {
+        if (n < cap) out[n] = (long)c.size();
+        ++n;
+        for (const auto& pos : c) {
+            if (n + 1 < cap) { out[n] = (long)pos.i; out[n + 1] = (long)pos.j; }
+            n += 2;
+        }
+    }
+    return n;
+}
 
 // events_out: pairs (type, agent_id); passes_out (optional): pass index per event
 int lleo_world_step(void* p, const uint8_t* actions, int n, int* events_out, int* passes_out, int* n_events) {
     World& w = ((WorldHandle*)p)->w;
     *n_events = 0;
+    w.rng_t++;  // after the call: the step count the next reset would see
     return guarded([&] {
         std::vector<Action> acts;
         for (int a = 0; a < n; ++a) acts.push_back((Action)actions[a]);
@@ -411,11 +454,16 @@ int lleo_world_observe(void* p, int kind, int param, float* out, long cap, long*
         }
     });
 }
-int lleo_env_reset(void* p) { return guarded([&] { ((Env*)p)->reset(); }); }
+int lleo_env_reset(void* p) {
+    Env& e = *(Env*)p;
+    e.world.rng_epoch++;
+    return guarded([&] { e.reset(); });
+}
 int lleo_env_step(void* p, const uint8_t* actions, int n, float* reward, uint8_t* done, int* events_out,
                   int* n_events) {
     Env& e = *(Env*)p;
     *n_events = 0;
+    e.world.rng_t++;
     return guarded([&] {
         std::vector<Action> acts;
         for (int a = 0; a < n; ++a) acts.push_back((Action)actions[a]);
@@ -512,6 +560,7 @@ void* lleo_vec_new(const char** texts, int n_maps, const int* map_of_env, int n_
         tmp->beam_on.assign(N * std::max<size_t>(tmp->NB, 1), 0);
         tmp->collected.assign(N, 0);
         for (size_t e = 0; e < N; ++e) {
+            tmp->arm_rng(e, 0);
             tmp->envs[e]->reset();
             tmp->export_env(e);
         }
@@ -545,6 +594,7 @@ int lleo_vec_configure(void* p, int n_extras, const int* extras_src, int pbrs, d
         v.R = v.envs[0]->reward_dim();
         v.reward.assign(v.N * v.R, 0.f);
         for (size_t e = 0; e < v.N; ++e) {
+            v.arm_rng(e, v.t);
             v.envs[e]->reset();
             v.export_env(e);
         }
@@ -614,8 +664,10 @@ void lleo_vec_buffers(void* p, void** out) {
 }
 int lleo_vec_reset(void* p) {
     Vec& v = *(Vec*)p;
+    v.reset_epoch++;
     return guarded([&] {
         for (size_t e = 0; e < v.N; ++e) {
+            v.arm_rng(e, v.t);
             v.envs[e]->reset();
             v.done[e] = 0; v.err[e] = 0;
             std::fill(&v.reward[e * v.R], &v.reward[e * v.R] + v.R, 0.f);
@@ -701,7 +753,10 @@ double lleo_vec_rollout(void* p, int steps, int n_threads, int* threads_used) {
                 auto ev = env.step(acts, &v.reward[e * v.R]);
                 encode_events(ev, env.world.last_event_pass, &v.events[e * v.A], v.A);
                 v.done[e] = env.done;
-                if (env.done) env.reset();
+                if (env.done) {
+                    v.arm_rng(e, t);
+                    env.reset();
+                }
                 env.observe(&v.obs[e * v.OF]);
                 env.state(&v.state[e * v.S]);
                 env.available_actions(&v.avail[e * v.A * 5]);
