@@ -447,10 +447,10 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     // ticket for `group` consecutive worlds, computes them, then streams their observation tiles.
     v->Wd = 1;
     while (v->Wd < v->A) v->Wd *= 2;
-    // at least 4 lanes per world: with fewer, a pass handles more worlds than a ticket should hold (measured on
-    // level 1: 95 us/step at Wd=1, 75 us at Wd=4)
+    // at least 2 lanes per world (16 worlds per pass, 16 per ticket).  Measured on B200 with narrow-grid pipelining
+    // (us/step, lanes per world 1 / 2 / 4): level 1: 40.7 / 40.3 / 45.4; level 3: 51.8 / 51.5 / 58.0
     const bool small_obs = v->obs_stride * 4 < 2048;  // tiny observations: the logic dominates, pack more worlds per pass
-    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", small_obs ? 1 : 4)));
+    v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", small_obs ? 1 : 2)));
     const int64_t stride = v->obs_stride;
     const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", small_obs ? 2048 : 1024);  // 4-8 KB per bulk store
     // the partial renderer builds whole worlds (all agents' windows) in one tile: allow up to 48 KB per warp
