@@ -168,8 +168,11 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world_size > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner (and any warning) to stdout unless told otherwise
+        # (NCCL_DEBUG_FILE is honoured only above the VERSION level)
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from lle_b200.sharding import reduce_stats, shard_range
