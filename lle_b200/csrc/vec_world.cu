@@ -1,5 +1,5 @@
 // lle_b200 — host side of the C ABI (include/lle_b200.h): map handles, device buffers, launch
-// configuration and the kernel launches.  The kernel itself lives in vec_kernels.cuh.
+// configuration and the kernel launches.  The kernel itself lives in world_kernel.cuh.
 #include <cuda.h>  // types of the stream memory operations only; the entry points are resolved at run time
 #include <cuda_runtime.h>
 

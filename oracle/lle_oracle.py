@@ -728,8 +728,13 @@ class OracleVec:
     def t(self, value: int):
         lib().lleo_vec_set_step_count(self._h, C.c_uint64(value))
 
-    def reset(self):
-        _check(lib().lleo_vec_reset(self._h))
+    def reset(self, mask: np.ndarray | None = None):
+        if mask is None:
+            _check(lib().lleo_vec_reset(self._h))
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            assert m.shape == (self.N,)
+            _check(lib().lleo_vec_reset_masked(self._h, m.ctypes.data_as(C.POINTER(C.c_uint8))))
 
     def step(self, actions: np.ndarray | None = None, n_threads: int = 0):
         ptr = None

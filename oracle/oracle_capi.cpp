@@ -662,11 +662,15 @@ void lleo_vec_buffers(void* p, void** out) {
     out[8] = v.pos.data(); out[9] = v.alive.data(); out[10] = v.arrived.data(); out[11] = v.slot.data();
     out[12] = v.beam_on.data(); out[13] = v.collected.data();
 }
-int lleo_vec_reset(void* p) {
+int lleo_vec_reset_masked(void* p, const uint8_t* mask);
+int lleo_vec_reset(void* p) { return lleo_vec_reset_masked(p, nullptr); }
+// lle_vec_reset with a mask: only the envs whose byte is non-zero are reset (all when mask is null)
+int lleo_vec_reset_masked(void* p, const uint8_t* mask) {
     Vec& v = *(Vec*)p;
     v.reset_epoch++;
     return guarded([&] {
         for (size_t e = 0; e < v.N; ++e) {
+            if (mask && !mask[e]) continue;
             v.arm_rng(e, v.t);
             v.envs[e]->reset();
             v.done[e] = 0; v.err[e] = 0;

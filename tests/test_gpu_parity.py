@@ -221,6 +221,98 @@ def test_random_maps_fuzz():
         n_run += 1
 
 
+def test_masked_reset():
+    """lle_vec_reset with a per-env mask: only the flagged envs start a new episode (and have their transition outputs
+    cleared); the others keep everything."""
+    rng = np.random.default_rng(5)
+    for kw in (dict(), dict(auto_reset=False, reward_dim=4), dict(obs_type="partial3x3", extras="laser_subgoal", pbrs=dict())):
+        ora, dev = make_pair([level_text(6)], None, 500, seed=90, **kw)
+        for rnd in range(6):
+            for _ in range(15):
+                ora.step(None); dev.vec.step(None)
+            mask = (rng.random(500) < (0.0 if rnd == 3 else 0.4)).astype(np.uint8)
+            ora.reset(mask); dev.vec.reset(torch.from_numpy(mask).cuda())
+            assert_same(dev, ora, dev.pull(), f"masked reset {rnd} ({kw})")
+        ora.step(None); dev.vec.step(None)
+        assert_same(dev, ora, dev.pull(), "step after the masked resets")
+
+
+def test_mixed_operation_sequences():
+    """A random interleaving of every way to drive a vec — single steps (sampled / supplied), rollouts, the host pipeline,
+    full and masked resets, set_state, refresh, source and exit mutators — checked against the oracle after every
+    operation.  Exercises the ordering between launch kinds (programmatic dependent launches, narrow grids, epoch flags)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(2026)
+    L = lo.lib()
+    n = 777
+    ora, dev = make_pair([level_text(6)], None, n, seed=91)
+    vec = dev.vec
+    A, R = ora.A, ora.R
+    pinned = [(torch.empty((n, A), dtype=torch.int8).pin_memory(), torch.empty((n, R), dtype=torch.float32).pin_memory(),
+               torch.empty((n,), dtype=torch.uint8).pin_memory()) for _ in range(4)]
+    for op_index in range(160):
+        op = rng.choice(["steps", "supplied", "rollout", "pipeline", "reset", "masked", "set_state", "refresh", "source", "exits"],
+                        p=[0.25, 0.1, 0.15, 0.15, 0.05, 0.08, 0.07, 0.05, 0.05, 0.05])
+        if op == "steps":
+            for _ in range(int(rng.integers(1, 12))):  # back to back, no synchronisation in between
+                ora.step(None); vec.step(None)
+        elif op == "supplied":
+            ora.step(None)  # the oracle samples a valid joint action; the device replays it (some made invalid)
+            vec.step(torch.from_numpy(np.array(ora.actions)).cuda())
+        elif op == "rollout":
+            k = int(rng.integers(1, 9))
+            vec.rollout(k)
+            for _ in range(k):
+                ora.step(None)
+        elif op == "pipeline":
+            k = int(rng.integers(1, 5))
+            expect = []
+            for q in range(k):
+                ora.step(None)
+                expect.append((np.array(ora.reward), np.array(ora.done)))
+                pinned[q][0].copy_(torch.from_numpy(np.array(ora.actions)))
+                vec.submit_host(pinned[q][0], pinned[q][1], pinned[q][2])
+            for q in range(k):
+                vec.wait_host()
+                assert np.array_equal(pinned[q][1].numpy(), expect[q][0]) and np.array_equal(pinned[q][2].numpy(), expect[q][1])
+        elif op == "reset":
+            ora.reset(); vec.reset()
+        elif op == "masked":
+            mask = (rng.random(n) < 0.3).astype(np.uint8)
+            ora.reset(mask); vec.reset(torch.from_numpy(mask).cuda())
+        elif op == "set_state":
+            pos = np.stack([rng.integers(0, ora.H, size=(n, A)), rng.integers(0, ora.W, size=(n, A))], axis=-1).astype(np.int32)
+            gems = rng.integers(0, 2, size=(n, ora.G)).astype(np.uint8)
+            alive = (rng.random((n, A)) < 0.9).astype(np.uint8)
+            vec.set_state(torch.from_numpy(pos), torch.from_numpy(gems), torch.from_numpy(alive))
+            for e in range(n):
+                p = (C.c_long * (2 * A))(*[int(x) for x in pos[e].reshape(-1)])
+                g = (C.c_uint8 * max(1, ora.G))(*[int(x) for x in gems[e]])
+                a = (C.c_uint8 * A)(*[int(x) for x in alive[e]])
+                L.lleo_vec_set_state_env(ora._h, C.c_long(e), p, A, g, ora.G, a)
+            L.lleo_vec_refresh(ora._h)
+            raw = dev.pull()
+            for name in ("pos", "alive", "arrived", "slot", "collected"):
+                assert np.array_equal(raw[name], np.asarray(getattr(ora, name))), f"op {op_index} set_state raw {name}"
+            assert np.array_equal(raw["beam_on"][:, :ora.NB], np.asarray(ora.beam_on)[:, :ora.NB])
+            ora.reset(); vec.reset()  # err / event bytes of a failed set_state are compared in test_set_state_fuzz
+        elif op == "refresh":
+            vec.refresh()
+        elif op == "source":
+            b, colour, enabled = int(rng.integers(0, 3)), int(rng.integers(0, 4)), bool(rng.integers(0, 2))
+            for target in (ora, vec):
+                target.set_source(b, agent_id=colour, enabled=enabled)
+            ora.reset(); vec.reset()  # the reference's cached static layers follow at the next reset
+        elif op == "exits":
+            exits = [(11, int(j)) for j in rng.choice(12, size=5, replace=False)]  # (11, 12) holds a gem
+            for target in (ora, vec):
+                target.set_exits(exits)
+            ora.reset(); vec.reset()
+        assert vec.step_count == ora.t, (op, vec.step_count, ora.t)
+        assert_same(dev, ora, dev.pull(), f"op {op_index}: {op}")
+
+
 def test_supplied_actions_with_invalid_ones():
     rng = np.random.default_rng(0)
     ora, dev = make_pair([level_text(5)], None, 512, seed=1)
