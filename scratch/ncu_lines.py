@@ -39,6 +39,29 @@ for r, (off, line, text) in zip(data, lines_of):
 ti, ts = sum(inst.values()), sum(samp.values())
 print(f"total warp instructions {ti:.0f}, samples {ts:.0f}")
 # coarse regions of world_kernel.cuh (by the line a SASS instruction is attributed to; inlined helpers count where they are defined)
+# per-function view: every `__device__` helper / method and the kernel's commented sections start a region
+import re as _re
+fmarks = [(1, "file head")]
+for n, text in enumerate(src, 1):
+    m = _re.search(r"__device__ __forceinline__ [\w:<>\*&\s]+?\b(\w+)\(", text)
+    if m:
+        fmarks.append((n, m.group(1)))
+    elif "__global__" in text and "lle_world_kernel" in text:
+        fmarks.append((n, "kernel: prologue"))
+    elif "// ====" in text and "logic" in text:
+        fmarks.append((n, "kernel: logic glue + small outputs"))
+    elif "// ====" in text and "observations of the group" in text:
+        fmarks.append((n, "kernel: render"))
+fmarks.append((len(src) + 1, "end"))
+rows_f = []
+for (a, name), (b, _) in zip(fmarks, fmarks[1:]):
+    vi = sum(v for l, v in inst.items() if l and a <= l < b)
+    vs = sum(v for l, v in samp.items() if l and a <= l < b)
+    if vi or vs:
+        rows_f.append((vi / ti * 100, vs / ts * 100, name, a))
+print("function / section      instr%  stall%")
+for vi, vs, name, a in sorted(rows_f, reverse=True)[:22]:
+    print(f"  {name:34s} {vi:5.1f}  {vs:5.1f}   (line {a})")
 marks = []
 for n, text in enumerate(src, 1):
     for tag in ("struct World {", "struct PatchCache", "template <int MODE, bool FAST>", "// ================================================================== logic",

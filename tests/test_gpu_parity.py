@@ -436,6 +436,35 @@ def test_config3_full_size_properties():
     assert len({tuple(w.tolist()) for w in walls[:, 0].cpu()}) > 500
 
 
+def test_config3_full_size_windows_against_the_oracle():
+    """BASELINE configs[2] at full size (1,024 maps x 1,024 worlds): an env's stream depends only on its global id, so
+    windows of the 1,048,576-world batch are replayed by small oracle batches (env_id_base = window start) and compared
+    bit-exactly, every output, for 40 steps."""
+    import lle_b200
+
+    maps = _generated_maps()
+    n = 1024 * 1024
+    moe = np.repeat(np.arange(1024, dtype=np.int32), 1024)
+    vec = lle_b200.VecWorld(maps, n, map_of_env=moe, seed=6)
+    rng = np.random.default_rng(3)
+    starts = [0, n - 256] + [int(x) for x in rng.integers(0, n - 256, size=6)]  # windows straddle map boundaries too
+    oracles = []
+    for s0 in starts:
+        ids = sorted(set(int(m) for m in moe[s0:s0 + 256]))
+        local = [ids.index(int(m)) for m in moe[s0:s0 + 256]]
+        oracles.append(lo.OracleVec([maps[i] for i in ids], local, 256, seed=6, env_id_base=s0))
+    for t in range(40):
+        vec.step(None)
+        for ora in oracles:
+            ora.step(None)
+        if t % 5 == 4:
+            vec.synchronize()
+            for s0, ora in zip(starts, oracles):
+                for name in ("obs", "state", "avail", "reward", "done", "events", "actions", "err"):
+                    a = getattr(vec, name)[s0:s0 + 256].cpu().numpy()
+                    assert np.array_equal(a, np.asarray(getattr(ora, name))), f"window at {s0}, step {t}: {name}"
+
+
 def test_config4_mixed_levels_group():
     """BASELINE configs[3] at reduced size: the six levels mixed, one sub-batch per level, contiguous global env ids."""
     import lle_b200
