@@ -1,0 +1,29 @@
+"""The C ABI used from a plain-C host program (examples/c_client.c): no Python, torch or CUDA headers on the host side —
+the shape of the reference-side FFI binding."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _exe():
+    import __graft_entry__
+
+    return __graft_entry__.build_c_client()
+
+
+def test_c_client_builds_against_the_public_header_only():
+    exe = _exe()
+    assert os.access(exe, os.X_OK)
+    needed = subprocess.run(["readelf", "-d", exe], capture_output=True, text=True).stdout
+    assert "liblle_b200.so" in needed and "libcudart" not in needed and "libtorch" not in needed
+
+
+@pytest.mark.gpu
+def test_c_client_runs():
+    res = subprocess.run([_exe(), "4096", "150"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    lines = res.stdout.strip().splitlines()
+    assert lines[-1] == "ok" and "episodes finished" in lines[1] and "0 unexpected transitions" in lines[2]
