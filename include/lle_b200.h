@@ -144,6 +144,15 @@ typedef struct {
      *   LLE_OBS_PERSPECTIVE  "perspective" (AgentZeroPerspective)                                                 (:372-395)
      *   LLE_OBS_STATE        obs_param 0 "state", 1 "normalized-state"                                            (:141-158) */
     int32_t obs_type, obs_param;
+    /* LLE(randomize_lasers=True) (python/lle/env/env.py:198-200, Builder.randomize_lasers): after every LLE-level reset
+     * (lle_vec_reset and auto-reset; not the construction reset) each laser source of the env takes a random colour in
+     * [0, n_agents).  The reference draws from Python's global `random` (unpinned); the stream here is this library's own:
+     * source b takes word (b & 3) of Philox4x32-10(counter = (env_id_base + env, step count, 0x20000000 | b >> 2, number of
+     * explicit resets), key = seed), colour = mulhi(word, n_agents).  Needs n_agents ^ n_sources <= 4096 colourings (each is a
+     * precompiled map variant), no laser across a start position and source colours < n_agents; excludes lle_vec_set_source
+     * and lle_vec_set_exits. */
+    int32_t randomize_lasers;
+    int32_t pad_options;
 } lle_vec_options;
 enum { LLE_OBS_LAYERED = 0, LLE_OBS_PARTIAL = 1, LLE_OBS_PERSPECTIVE = 2, LLE_OBS_STATE = 3 };
 LLE_API void lle_vec_default_options(lle_vec_options* opts);
@@ -192,6 +201,10 @@ typedef struct {
     int32_t obs_invalid;            /* some map's laser colour indexes past the last channel of this observation type: the
                                        reference raises IndexError when it builds / runs the generator */
     int32_t pad2;
+    int32_t* map_index;             /* i32[N] or NULL: index of each env's current map; with randomize_lasers:
+                                       map * n_variants + colouring, colouring = sum over sources b of colour_b * n_agents^b */
+    int32_t n_variants;             /* colourings per map (1 without randomize_lasers) */
+    int32_t pad3;
 } lle_vec_buffers;
 LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 

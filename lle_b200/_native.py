@@ -11,7 +11,8 @@ import os
 from .types import InvalidActionError, InvalidLevelError, InvalidWorldStateError, ParsingError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_native", "liblle_b200.so")
+# LLE_B200_LIB: development aid (A/B timing of two builds of this same library on one GPU box)
+LIB_PATH = os.environ.get("LLE_B200_LIB") or os.path.join(_HERE, "_native", "liblle_b200.so")
 
 SYMBOLS = [
     "lle_last_error", "lle_version", "lle_map_parse", "lle_map_level", "lle_map_free", "lle_map_get_info",
@@ -33,7 +34,8 @@ class VecOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("device", "reward_dim", "walkable_lasers", "auto_reset", "lle_semantics", "write_obs")] + [
         ("seed", C.c_uint64), ("env_id_base", C.c_uint64), ("n_extras", C.c_int32), ("extras_src", C.c_int32 * 64),
         ("pbrs", C.c_int32), ("n_pbrs", C.c_int32), ("pbrs_src", C.c_int32 * 64), ("pbrs_gamma", C.c_double),
-        ("pbrs_reward_value", C.c_double), ("obs_type", C.c_int32), ("obs_param", C.c_int32)]
+        ("pbrs_reward_value", C.c_double), ("obs_type", C.c_int32), ("obs_param", C.c_int32), ("randomize_lasers", C.c_int32),
+        ("pad_options", C.c_int32)]
 
 
 class VecBuffers(C.Structure):
@@ -41,7 +43,8 @@ class VecBuffers(C.Structure):
                                                                    "reward_dim", "state_dim", "n_beams_max")] + [
         ("obs_stride", C.c_int64), ("obs", C.c_void_p), ("state", C.c_void_p), ("avail", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p), ("record_bytes", C.c_int64), ("extras", C.c_void_p), ("extras_dim", C.c_int32), ("pad", C.c_int32)] + [
-        (n, C.c_int32) for n in ("obs_type", "obs_param", "obs_view_agents", "obs_c", "obs_h", "obs_w", "obs_invalid", "pad2")]
+        (n, C.c_int32) for n in ("obs_type", "obs_param", "obs_view_agents", "obs_c", "obs_h", "obs_w", "obs_invalid", "pad2")] + [
+        ("map_index", C.c_void_p), ("n_variants", C.c_int32), ("pad3", C.c_int32)]
 
 
 _lib = None

@@ -53,6 +53,10 @@ struct lle_vec {
     std::vector<std::vector<Cell>> map_exits;  // World::set_exit_positions overrides (empty: the exits of the text)
     std::vector<char> map_exits_set;
     std::vector<uint8_t*> retired_blobs;
+    // LLE(randomize_lasers=True): every map is compiled once per colouring (variant index = sum colour_b * A^b)
+    bool randomize = false, creating = false;
+    int n_variants = 1;
+    std::vector<CompiledMap> variant_maps;  // [n_maps * n_variants]
     bool render = true;
     LleMapHeader hdr0;  // header of the first map (observation shape)
     int obs_invalid = 0;
@@ -227,6 +231,8 @@ KParams base_params(lle_vec* v) {
     std::memcpy(p.extras_beam, v->extras_beam, sizeof p.extras_beam);
     p.timeline = v->d_timeline;
     p.reset_epoch = v->reset_epoch;
+    p.randomize = (v->randomize && !v->creating) ? 1 : 0;  // the construction reset is World::new's, not LLE.reset (env.py:191-203)
+    p.n_variants = v->n_variants;
     return p;
 }
 
@@ -412,6 +418,37 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (map_of_env)
         for (int64_t e = 0; e < n_envs; ++e)
             if (map_of_env[e] < 0 || map_of_env[e] >= n_maps) return fail(LLE_INVALID_ARGUMENT, "map_of_env out of range");
+    if (opts->randomize_lasers) {
+        // env.py:198-200 recolours every source at every reset with source.set_colour(random colour), which raises when the
+        // beam crosses a start position of another agent (pylaser_source.rs:121-139): such maps cannot be randomised freely
+        int64_t V = 1;
+        for (int b = 0; b < v->NBmax; ++b) {
+            V *= v->A;
+            if (V > 4096) return fail(LLE_LIMIT_EXCEEDED, "randomize_lasers: more than 4096 colourings (n_agents ^ n_sources)");
+        }
+        v->n_variants = (int)V;
+        v->randomize = true;
+        for (int k = 0; k < n_maps; ++k) {
+            const CompiledMap& m = *cms[k];
+            for (const auto& l : m.lasers)
+                for (int a = 0; a < m.A; ++a)
+                    for (const auto& st : m.start_candidates[(size_t)a])
+                        if (st == l.pos)
+                            return fail(LLE_INVALID_ARGUMENT, "randomize_lasers: a laser crosses a start position (set_colour would raise, pylaser_source.rs:121-139)");
+            for (const auto& src : m.sources)
+                if (src.colour >= m.A) return fail(LLE_INVALID_ARGUMENT, "randomize_lasers: a source colour is >= n_agents");
+            for (int variant = 0; variant < v->n_variants; ++variant) {
+                std::vector<SourceState> st;
+                int rest = variant;
+                for (int b = 0; b < m.NB; ++b) { st.push_back(SourceState{rest % v->A, true}); rest /= v->A; }
+                try {
+                    v->variant_maps.push_back(compile_map(m.text, spec, &st));
+                } catch (const MapError& e) {
+                    return fail(e.status, e.what());
+                }
+            }
+        }
+    }
     v->N = n_envs;
     v->N_pad = (n_envs + 31) / 32 * 32;
     // LaserSubgoal extras / PotentialShapedLLE source selections
@@ -490,8 +527,11 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->force_narrow = env_int("LLE_B200_FORCE_NARROW", 0) != 0;
     int max_patch = 0;
     for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)cms[k]->header().n_patch);
+    for (const auto& m : v->variant_maps) max_patch = std::max(max_patch, (int)m.header().n_patch);
+    bool random_starts = false;  // start sampling lives in the general kernel only
+    for (int k = 0; k < n_maps; ++k) random_starts = random_starts || cms[k]->header().random_starts;
     v->fast = v->n_chunks == 1 && v->E <= 32 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 && opts->write_obs &&
-              spec.kind == LLE_OBS_LAYERED && !env_int("LLE_B200_NO_FAST", 0);
+              spec.kind == LLE_OBS_LAYERED && !v->randomize && !random_starts && !env_int("LLE_B200_NO_FAST", 0);
     int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
     if (v->fast) {
         LLE_CUDA((configure_kernel<MODE_STEP, true>(v->smem, &blocks_per_sm)));
@@ -517,8 +557,11 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
 
     // ---- device memory
     std::vector<const uint8_t*> table;
-    for (int k = 0; k < n_maps; ++k) {
-        const auto& blob = cms[k]->blob;
+    std::vector<const CompiledMap*> upload;  // blob table: one entry per map, or per (map, colouring) with randomize_lasers
+    if (v->randomize) for (const auto& m : v->variant_maps) upload.push_back(&m);
+    else upload = cms;
+    for (size_t k = 0; k < upload.size(); ++k) {
+        const auto& blob = upload[k]->blob;
         uint8_t* d = nullptr;
         LLE_CUDA(cudaMalloc((void**)&d, blob.size()));
         v->d_blobs.push_back(d);
@@ -527,10 +570,17 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     }
     LLE_CUDA(cudaMalloc((void**)&v->d_blob_table, table.size() * sizeof(uint8_t*)));
     LLE_CUDA(cudaMemcpy((void*)v->d_blob_table, table.data(), table.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice));
-    if (map_of_env && n_maps > 1) {
+    if ((map_of_env && n_maps > 1) || v->randomize) {
         std::vector<int32_t> padded((size_t)v->N_pad, 0);
-        std::copy(map_of_env, map_of_env + n_envs, padded.begin());
-        for (int64_t e = n_envs; e < v->N_pad; ++e) padded[(size_t)e] = map_of_env[n_envs - 1];
+        if (map_of_env) std::copy(map_of_env, map_of_env + n_envs, padded.begin());
+        for (int64_t e = n_envs; e < v->N_pad; ++e) padded[(size_t)e] = map_of_env ? map_of_env[n_envs - 1] : 0;
+        if (v->randomize)  // entries become blob indices: map * n_variants + the colouring the text describes
+            for (auto& id : padded) {
+                const CompiledMap& m = *cms[(size_t)id];
+                int variant = 0, scale = 1;
+                for (int b = 0; b < m.NB; ++b) { variant += m.sources[(size_t)b].colour * scale; scale *= v->A; }
+                id = id * v->n_variants + variant;
+            }
         LLE_CUDA(dalloc(&v->d_map_of_env, (size_t)v->N_pad));
         LLE_CUDA(cudaMemcpy(v->d_map_of_env, padded.data(), padded.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     } else if (map_of_env && n_maps == 1) {
@@ -558,7 +608,9 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     LLE_CUDA(cudaEventCreate(&v->ev1));
 
     // World::new resets itself (world.rs:82)
+    v->creating = true;
     int rc = lle_vec_reset(v.get(), nullptr, nullptr);
+    v->creating = false;
     if (rc != LLE_OK) return rc;
     LLE_CUDA(cudaDeviceSynchronize());
     *out = v.release();
@@ -581,6 +633,8 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->obs_view_agents = v->hdr0.view_agents;
     out->obs_c = v->hdr0.obs_c; out->obs_h = v->hdr0.obs_h; out->obs_w = v->hdr0.obs_w;
     out->obs_invalid = v->obs_invalid;
+    out->map_index = v->d_map_of_env;
+    out->n_variants = v->n_variants;
     return LLE_OK;
 }
 
@@ -627,6 +681,7 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
     if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
     auto& st = v->src_state[(size_t)map_index];
     if (source_index < 0 || source_index >= (int)st.size()) return fail(LLE_INVALID_ARGUMENT, "laser source index out of range");
+    if (v->randomize) return fail(LLE_INVALID_ARGUMENT, "source mutators are not available together with randomize_lasers");
     if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     std::vector<SourceState> next = st;
     if (agent_id >= 0) next[(size_t)source_index].colour = agent_id;
@@ -652,6 +707,7 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
 int lle_vec_set_exits(lle_vec* v, int32_t map_index, const int32_t* exits_ij, int32_t n_exits, void* stream) {
     if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
     if (n_exits < 0 || (n_exits > 0 && !exits_ij)) return fail(LLE_INVALID_ARGUMENT, "bad exit list");
+    if (v->randomize) return fail(LLE_INVALID_ARGUMENT, "the exit setter is not available together with randomize_lasers");
     if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     std::vector<Cell> exits;
     for (int k = 0; k < n_exits; ++k) exits.push_back(Cell{exits_ij[2 * k], exits_ij[2 * k + 1]});

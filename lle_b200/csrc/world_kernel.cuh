@@ -52,7 +52,9 @@ enum : uint32_t {
 
 struct KParams {
     const uint8_t* const* blobs;  // device array [n_maps] of map blobs
-    const int32_t* map_of_env;    // device [N_pad] or nullptr
+    int32_t* map_of_env;          // device [N_pad] or nullptr: index of each env's current map blob.  With randomize_lasers the
+                                  // blob table holds `n_variants` colourings per map (index = map * n_variants + variant) and a reset
+                                  // rewrites the env's entry
     uint32_t* records;            // [N_pad][L.stride]
     LleStateLayout L;
     int64_t N, N_pad;
@@ -109,6 +111,8 @@ struct KParams {
     // host see how many step launches are still in flight (a scheduling hint only, see launch_mode in vec_world.cu)
     volatile uint32_t* retired_seq;
     uint32_t reset_epoch;  // number of explicit resets of the vec so far: part of the start-sampling counter (random starts)
+    int32_t randomize;     // LLE(randomize_lasers=True), env.py:198-200: every LLE-level reset recolours the sources at random
+    int32_t n_variants;    // colourings per map: n_agents ^ n_sources (source b's colour = digit b in base n_agents)
     uint32_t refresh_only; // MODE_RESET launch that resets no env: re-exports observation / state / availability only
 };
 
@@ -468,14 +472,16 @@ struct World {
             }
         }
     }
+    // `sample`: compile-time switch of the start sampler — batches with random starts run on the general kernel, so the
+    // fast kernel does not carry the sampler's code
     __device__ __forceinline__ void reset(bool on, uint64_t pbrs_set, uint32_t env_lo = 0, uint32_t t32 = 0, uint32_t epoch = 0,
-                                          uint64_t seed = 0) {
+                                          uint64_t seed = 0, bool sample = false) {
         tiles_reset(on);
         if (on) {
             alive = amask; arrived = 0; n_arrived = 0; n_deads = 0; done = 0;
             pos = gl < A ? (uint32_t)m.hdr->start[gl] : 0u;
         }
-        if (__any_sync(kFull, on && m.hdr->random_starts)) sample_starts(on && m.hdr->random_starts, env_lo, t32, epoch, seed);
+        if (sample && __any_sync(kFull, on && m.hdr->random_starts)) sample_starts(on && m.hdr->random_starts, env_lo, t32, epoch, seed);
         pre_enter_all(on, pos, alive);
         (void)enter_all(on, pos);  // events are dropped (world.rs:428-430)
         if (on) {
@@ -693,6 +699,30 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 
+// LLE.reset with randomize_lasers (env.py:198-200): after world.reset() every source gets a random colour.  The reference
+// draws random.randint(0, n_agents - 1) from Python's global generator (unpinned); the stream here is this library's
+// contract: source b takes word (b & 3) of Philox4x32-10(counter = (env id, step, 0x20000000 | b >> 2, explicit-reset
+// count), key = seed) and colour = mulhi(word, n_agents).  The colouring selects one of the map's precompiled variants
+// (index = map * n_variants + sum colour_b * n_agents^b), recorded in map_of_env.  Out of line: resets are rare and the
+// step kernel should not carry this in its registers.
+__device__ __noinline__ int recolour_variant(int32_t* map_of_env, uint64_t env_id_base, uint64_t seed, uint32_t reset_epoch, int n_agents,
+                                             int n_variants, int64_t env, uint64_t t_now, int n_sources, int map_id) {
+    const int base = map_id / n_variants;
+    int variant = 0, scale = 1;
+    uint32_t r[4] = {0, 0, 0, 0};
+    for (int b = 0; b < n_sources; ++b) {
+        if ((b & 3) == 0)
+            philox4x32_10((uint32_t)(env_id_base + (uint64_t)env), (uint32_t)t_now, 0x20000000u | (uint32_t)(b >> 2), reset_epoch,
+                          (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const uint32_t word = (b & 3) == 0 ? r[0] : (b & 3) == 1 ? r[1] : (b & 3) == 2 ? r[2] : r[3];
+        variant += (int)__umulhi(word, (uint32_t)n_agents) * scale;
+        scale *= n_agents;
+    }
+    const int next = base * n_variants + variant;
+    __stcg(map_of_env + env, next);
+    return next;
+}
+
 #ifndef LLE_MIN_CTAS
 #define LLE_MIN_CTAS 5
 #endif
@@ -807,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             // start filling this warp's tiles from the static plane of the first world's map now: the copies land
             // while the first logic pass runs
             first = false;
-            const int mid = p.map_of_env ? __ldg(p.map_of_env + env0) : 0;
+            const int mid = p.map_of_env ? __ldcg(p.map_of_env + env0) : 0;
             rm.bind(p.blobs[mid]);
             render_map = mid;
             pc.load(rm, L, lane);
@@ -825,14 +855,30 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         for (int g0 = 0; g0 < p.group; g0 += P) {
             const int g = g0 + sub;
             const int64_t env = env0 + g;  // N_pad is a multiple of the group size: always a world
+            int map_id = 0;
             if (!FAST || p.map_of_env != nullptr) {
-                const int map_id = p.map_of_env ? __ldg(p.map_of_env + env) : 0;
+                map_id = p.map_of_env ? __ldcg(p.map_of_env + env) : 0;  // through L2: a reset of the previous (overlapped) step may have rewritten it
                 if (map_id != bound_map) {
                     w.m.bind(p.blobs[map_id]);
                     bound_map = map_id;
                 }
                 if (gl == 0) map_ids[g] = map_id;
             }
+            // LLE.reset with randomize_lasers (env.py:198-200): the worlds with `on` take a new colouring (recolour_variant,
+            // above); the reset that precedes it ran with the previous colours, like the reference
+            auto recolour = [&](bool on) {
+                if constexpr (FAST) return;  // randomize_lasers runs on the general kernel (the host selects it): no cost here
+                int next = map_id;
+                if (on && gl == 0)
+                    next = recolour_variant(p.map_of_env, p.env_id_base, p.seed, p.reset_epoch, A, p.n_variants, env, t_now, w.m.NB, map_id);
+                map_id = __shfl_sync(kFull, next, (int)(lane & ~(Wd - 1)));
+                if (on && map_id != bound_map) {
+                    w.m.bind(p.blobs[map_id]);
+                    bound_map = map_id;
+                }
+                if (on && gl == 0) map_ids[g] = map_id;
+                __syncwarp();
+            };
             uint32_t* rec = recs + (size_t)g * stride;
             if (g0 == 0) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -875,8 +921,10 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                 }
             } else if constexpr (MODE == MODE_RESET) {
                 const bool on = !p.refresh_only && (!p.reset_mask || !real || p.reset_mask[env]);
-                w.reset(on, p.pbrs_set, (uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, p.reset_epoch, p.seed);
+                w.reset(on, p.pbrs_set, (uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, p.reset_epoch, p.seed, !FAST);
                 touch = on;
+                if constexpr (!FAST)
+                    if (p.randomize && __any_sync(kFull, on)) recolour(on);
             } else {  // MODE_SET_STATE: World::set_state (world.rs:515-597) + LLE.set_state (env.py:208-216)
                 touch = real;  // padding worlds: nothing to force
                 int si = 0, sj = 0;
@@ -951,8 +999,11 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             // auto-reset: the transition above is reported; observation / state / availability below are those
             // of the freshly reset world (SURVEY §8d "Auto-reset")
             const bool do_reset = MODE == MODE_STEP && p.auto_reset && w.done && err == ERR_OK;
-            if (__any_sync(kFull, do_reset))
-                w.reset(do_reset, p.pbrs_set, (uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, p.reset_epoch, p.seed);
+            if (__any_sync(kFull, do_reset)) {
+                w.reset(do_reset, p.pbrs_set, (uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, p.reset_epoch, p.seed, !FAST);
+                if constexpr (!FAST)
+                    if (p.randomize) recolour(do_reset);
+            }
 
             // compute_available_actions (world.rs:343-363) closes reset (:431), step (:473) and a successful set_state
             // (:595, also reached by the restore at :563); a set_state that fails with InvalidWorldState returns before it,

@@ -23,11 +23,12 @@ class VecLLE:
 
     def __init__(self, maps, n_envs: int, *, map_of_env: Sequence[int] | None = None, device=0, multi_objective: bool = False,
                  walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True,
-                 extras=None, pbrs: dict | None = None, obs_type: str = "layered", padding_size: int = 0):
+                 extras=None, pbrs: dict | None = None, obs_type: str = "layered", padding_size: int = 0,
+                 randomize_lasers: bool = False):
         self.world = VecWorld(maps, n_envs, map_of_env=map_of_env, device=device, reward_dim=4 if multi_objective else 1,
                               walkable_lasers=walkable_lasers, auto_reset=auto_reset, lle_semantics=True, write_obs=write_obs,
                               seed=seed, env_id_base=env_id_base, extras=extras, pbrs=pbrs, obs_type=obs_type,
-                              padding_size=padding_size)
+                              padding_size=padding_size, randomize_lasers=randomize_lasers)
         if self.world.obs_invalid and write_obs:
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         w = self.world
@@ -145,6 +146,11 @@ class Builder:
             if e != "laser_subgoal":
                 raise ValueError(f"Invalid extra type: {e}")
             self._kw["extras"] = "laser_subgoal"
+        return self
+
+    def randomize_lasers(self, enabled: bool = True):
+        """Randomize the colour of the lasers at each reset (builder.py:112-115, env.py:198-200)."""
+        self._kw["randomize_lasers"] = bool(enabled)
         return self
 
     def walkable_lasers(self, walkable: bool = True):

@@ -112,7 +112,7 @@ class VecWorld:
                  device: int | str | torch.device = 0, reward_dim: int = 1, walkable_lasers: bool = True, auto_reset: bool = True,
                  lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0,
                  extras: str | Sequence[int] | None = None, pbrs: dict | None = None, obs_type: str = "layered",
-                 padding_size: int = 0):
+                 padding_size: int = 0, randomize_lasers: bool = False):
         """obs_type: an ObservationType value (observations.py:37-60) other than "rgb-image"; padding_size for "layered-padded".
         extras: None | "laser_subgoal" (all sources) | source indices (World::sources() order) — Builder.add_extras.
         pbrs: None | dict(gamma=0.99, reward_value=0.5, lasers_to_reward=None | indices, with_extras=True) — Builder.pbrs
@@ -131,6 +131,7 @@ class VecWorld:
         opts.seed, opts.env_id_base = int(seed), int(env_id_base)
         self.obs_type = obs_type
         opts.obs_type, opts.obs_param, self._flatten = obs_spec(obs_type, padding_size)
+        opts.randomize_lasers = int(bool(randomize_lasers))
         extras_src = None if extras in (None, "laser_subgoal") else [int(x) for x in extras]
         want_extras = extras is not None
         if pbrs is not None:
@@ -193,6 +194,9 @@ class VecWorld:
         self.events = wrap(b.events, (N, A), "|u1")
         self.actions = wrap(b.actions, (N, A), "|i1")
         self.err = wrap(b.err, (N,), "|u1")
+        #: with randomize_lasers: (N,) i32, map * n_variants + colouring (colour of source b = digit b in base n_agents)
+        self.n_variants = int(b.n_variants)
+        self.map_index = wrap(b.map_index, (N,), "<i4") if b.map_index else None
         #: LaserSubgoal flags (N, A, n_sources); None when extras are off
         self.extras_dim = int(b.extras_dim)
         self.extras = wrap(b.extras, (N, A, self.extras_dim), "<f4") if self.extras_dim else None
@@ -261,6 +265,18 @@ class VecWorld:
         """World::set_exit_positions (world.rs:195-234) in every env that uses map `map_index` (lle_vec_set_exits)."""
         flat = (C.c_int32 * max(1, 2 * len(exits)))(*[int(x) for p in exits for x in p])
         check(lib().lle_vec_set_exits(self._h, int(map_index), flat, len(exits), _stream_ptr(self.device)))
+
+    def source_colours(self) -> torch.Tensor:
+        """(N, n_sources) current colour of every source of every env (they differ per env with randomize_lasers)."""
+        nb = self.n_beams_max
+        if self.n_variants == 1:
+            per_map = torch.tensor([[c for c, _ in self.source_states(k)] + [0] * (nb - len(self.source_states(k)))
+                                    for k in range(len(self.maps))], dtype=torch.int32, device=self.device).reshape(len(self.maps), nb)
+            idx = self.map_index.long() if self.map_index is not None else torch.zeros(self.n_envs, dtype=torch.long, device=self.device)
+            return per_map[idx]
+        variant = self.map_index.long() % self.n_variants
+        digits = [(variant // (self.n_agents ** k)) % self.n_agents for k in range(nb)]
+        return torch.stack(digits, dim=1).to(torch.int32) if nb else torch.zeros((self.n_envs, 0), dtype=torch.int32, device=self.device)
 
     def source_states(self, map_index: int = 0) -> list[tuple[int, bool]]:
         """Current (agent_id, is_enabled) of the sources of map `map_index` (lle_vec_get_sources)."""

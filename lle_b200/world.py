@@ -87,15 +87,23 @@ class _Single:
     def lasers(self) -> list[Laser]:
         """World::lasers (world.rs:159-172) with `is_on` read from the device beam masks."""
         on = self._raw()["beam_on"].view(np.uint64)
-        states = self._vec.source_states()  # colours and switches may have changed since the map was parsed
+        states = self._source_states()  # colours and switches may have changed since the map was parsed
         return [Laser(pos, lid, states[beam][0], direction, bool((int(on[beam]) >> off) & 1), states[beam][1])
                 for pos, lid, colour, direction, beam, off in self._laser_tiles]
 
     @property
     def laser_sources(self) -> list["BoundLaserSource"]:
         """World::sources (world.rs:141-149) as handles that can recolour / switch the source (PyLaserSource)."""
-        states = self._vec.source_states()
+        states = self._source_states()
         return [BoundLaserSource(self, k, s, states[k]) for k, s in enumerate(self._sources)]
+
+    def _source_states(self) -> list[tuple[int, bool]]:
+        states = self._vec.source_states()
+        if self._vec.n_variants > 1:  # randomize_lasers: this world's own colours
+            self._vec.synchronize()
+            colours = self._vec.source_colours()[0].cpu().tolist()
+            states = [(int(colours[k]), en) for k, (_, en) in enumerate(states)]
+        return states
 
     def source_at(self, pos) -> "BoundLaserSource":
         for s in self.laser_sources:
@@ -134,7 +142,7 @@ class _Single:
 
     @property
     def n_laser_colours(self) -> int:
-        return len({colour for colour, _ in self._vec.source_states()})
+        return len({colour for colour, _ in self._source_states()})
 
     @property
     def world_string(self) -> str:
@@ -315,10 +323,10 @@ class LLE(_Single):
 
     def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
                  walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, obs_type: str = "layered",
-                 padding_size: int = 0, device=0):
+                 padding_size: int = 0, randomize_lasers: bool = False, device=0):
         self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
                           reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
-                          obs_type=obs_type, padding_size=padding_size)
+                          obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers)
         if self._vec.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         self.reward_dim = self._vec.reward_dim

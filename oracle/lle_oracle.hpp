@@ -1223,6 +1223,10 @@ struct Env {
     bool has_pbrs = false;
     SubgoalTracker pbrs;
     double gamma = 0.99, reward_value = 0.5, previous_potential = 0.0;
+    // LLE(randomize_lasers=True) (env.py:83, :198-200).  Python's global `random` cannot be reproduced; the colours follow
+    // the device library's documented Philox contract (include/lle_b200.h, lle_vec_options.randomize_lasers), with the
+    // counter words the harness keeps in world.rng_*.
+    bool randomize_lasers = false;
 
     Env(World&& w, bool multi_obj = false, bool walkable = true)
         : world(std::move(w)), obs(world, ObsKind::Layered, 0), multi_objective(multi_obj), walkable_lasers(walkable) {}
@@ -1299,11 +1303,21 @@ struct Env {
     bool compute_done() const { return n_arrived == world.n_agents() || n_deads > 0; }  // env.py:253-254
 
     // env.py:191-203 (randomize_lasers is out of scope)
-    void reset() {
+    void reset(bool lle_level = true) {
         world.reset();
         reset_strategy();
         if (has_extras) extras.clear();  // extras_generator.reset() (env.py:196)
         done = false;
+        if (randomize_lasers && lle_level) {  // env.py:198-200, after world.reset(): source.set_colour(random colour)
+            const uint32_t key[2] = {(uint32_t)world.rng_seed, (uint32_t)(world.rng_seed >> 32)};
+            const uint32_t n_agents = (uint32_t)world.n_agents();
+            for (size_t b = 0; b < world.laser_source_positions.size(); ++b) {
+                const uint32_t ctr[4] = {world.rng_env, world.rng_t, 0x20000000u | (uint32_t)(b >> 2), world.rng_epoch};
+                uint32_t out[4];
+                Philox::run(ctr, key, out);
+                world.source_beam(b)->agent_id = (size_t)(((uint64_t)out[b & 3] * n_agents) >> 32);
+            }
+        }
         obs.setup(world);
     }
     // RewardStrategy.reset (:40-42) / PotentialShapedLLE.reset (:176-180)

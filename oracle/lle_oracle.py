@@ -549,7 +549,7 @@ def _src_list(sources):
 
 class LLE:
     def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True, extras=None, pbrs=None,
-                 obs_type: str = "layered", padding_size: int = 0):
+                 obs_type: str = "layered", padding_size: int = 0, randomize_lasers: bool = False):
         """extras: None | "laser_subgoal" | list of source indices.  pbrs: None | dict(gamma=0.99, reward_value=0.5,
         lasers_to_reward=None (all) | list of source indices, with_extras=True) — Builder.pbrs (builder.py:77-110)."""
         st = C.c_int(0)
@@ -570,6 +570,7 @@ class LLE:
         self.height, self.width, self.n_agents, self.n_gems, self.n_channels, self.reward_dim = list(d)
         self.reward_dim = lib().lleo_env_reward_dim(self._h)
         self.extras_dim = lib().lleo_env_extras_dim(self._h)
+        lib().lleo_env_set_randomize_lasers(self._h, int(bool(randomize_lasers)))
         kind, param, self._flatten = obs_spec(obs_type, padding_size)
         self._s6 = (C.c_long * 6)()
         _check(lib().lleo_env_set_obs(self._h, kind, param, self._s6))
@@ -607,6 +608,20 @@ class LLE:
         out = np.zeros((self.n_agents, 5), dtype=np.uint8)
         lib().lleo_env_available(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)))
         return out.astype(bool)
+
+    @property
+    def laser_sources(self):
+        """env.world.laser_sources: read-only snapshots (pos, agent_id, direction, is_enabled, laser_id, beam_len)."""
+        buf = (C.c_int * (7 * 64))()
+        n = lib().lleo_env_sources(self._h, buf, 64)
+        return [LaserSource(None, k, buf[7 * k:7 * k + 7]) for k in range(n)]
+
+    @property
+    def lasers(self):
+        buf = (C.c_int * (7 * 4096))()
+        n = lib().lleo_env_lasers(self._h, buf, 4096)
+        return [Laser((buf[7 * k], buf[7 * k + 1]), buf[7 * k + 2], buf[7 * k + 3], Direction(buf[7 * k + 4]), bool(buf[7 * k + 5]),
+                      bool(buf[7 * k + 6])) for k in range(n)]
 
     def extras(self) -> np.ndarray:
         """LaserSubgoal.compute (extras_generators.py:93-98): float32 (A, n_sources)."""
@@ -647,7 +662,7 @@ class OracleVec:
 
     def __init__(self, maps: Sequence[str], map_of_env: Sequence[int] | None, n_envs: int, *, multi_objective=False,
                  walkable_lasers=True, auto_reset=True, seed=0, env_id_base=0, extras=None, pbrs=None,
-                 obs_type: str = "layered", padding_size: int = 0):
+                 obs_type: str = "layered", padding_size: int = 0, randomize_lasers: bool = False):
         texts = (C.c_char_p * len(maps))(*[prepare_map_text(m) for m in maps])
         moe = None if map_of_env is None else (C.c_int * n_envs)(*[int(m) for m in map_of_env])
         st = C.c_int(0)
@@ -667,6 +682,7 @@ class OracleVec:
                                             C.c_double(pb.get("reward_value", 0.5)), np_, pa))
             lib().lleo_vec_extras_dim.restype = C.c_long
             self.JE = lib().lleo_vec_extras_dim(self._h)
+        lib().lleo_vec_set_randomize_lasers(self._h, int(bool(randomize_lasers)))
         kind, param, _ = obs_spec(obs_type, padding_size)
         s6 = (C.c_long * 6)()
         _check(lib().lleo_vec_set_obs(self._h, kind, param, s6))

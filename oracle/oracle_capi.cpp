@@ -561,7 +561,7 @@ void* lleo_vec_new(const char** texts, int n_maps, const int* map_of_env, int n_
         tmp->collected.assign(N, 0);
         for (size_t e = 0; e < N; ++e) {
             tmp->arm_rng(e, 0);
-            tmp->envs[e]->reset();
+            tmp->envs[e]->reset(false);  // the construction reset is World::new's, not LLE.reset
             tmp->export_env(e);
         }
         v = tmp.release();
@@ -595,11 +595,40 @@ int lleo_vec_configure(void* p, int n_extras, const int* extras_src, int pbrs, d
         v.reward.assign(v.N * v.R, 0.f);
         for (size_t e = 0; e < v.N; ++e) {
             v.arm_rng(e, v.t);
-            v.envs[e]->reset();
+            v.envs[e]->reset(false);
             v.export_env(e);
         }
     });
 }
+// LLE(randomize_lasers=True) for every env of the vec (takes effect from the next LLE-level reset on)
+void lleo_vec_set_randomize_lasers(void* p, int enabled) {
+    for (auto& e : ((Vec*)p)->envs) e->randomize_lasers = enabled != 0;
+}
+// the env's world through the World getters above: a WorldHandle view is not needed, only the two listings
+int lleo_env_sources(void* p, int* out, int max) {
+    const World& w = ((Env*)p)->world;
+    int n = 0;
+    for (size_t s = 0; s < w.laser_source_positions.size() && n < max; ++s, ++n) {
+        auto b = w.source_beam(s);
+        int* o = out + 7 * n;
+        o[0] = (int)w.laser_source_positions[s].i; o[1] = (int)w.laser_source_positions[s].j;
+        o[2] = (int)b->agent_id; o[3] = dir_code(b->direction); o[4] = b->enabled; o[5] = (int)b->laser_id;
+        o[6] = (int)b->beam.size();
+    }
+    return (int)w.laser_source_positions.size();
+}
+int lleo_env_lasers(void* p, int* out, int max) {
+    auto ls = ((Env*)p)->world.lasers();
+    int n = 0;
+    for (const auto& l : ls) {
+        if (n >= max) break;
+        int* o = out + 7 * n++;
+        o[0] = (int)l.pos.i; o[1] = (int)l.pos.j; o[2] = (int)l.laser_id; o[3] = (int)l.agent_id;
+        o[4] = dir_code(l.direction); o[5] = l.is_on; o[6] = l.is_enabled;
+    }
+    return (int)ls.size();
+}
+void lleo_env_set_randomize_lasers(void* p, int enabled) { ((Env*)p)->randomize_lasers = enabled != 0; }
 // Observation type of every env of the vec (see lleo_env_set_obs); re-exports all envs.  The obs buffer is reallocated:
 // fetch the pointers again with lleo_vec_buffers.
 int lleo_vec_set_obs(void* p, int kind, int param, long* out6) {

@@ -37,7 +37,7 @@ def make_pair(maps, map_of_env, n_envs, **kw):
     okw = dict(multi_objective=kw.get("reward_dim", 1) == 4, walkable_lasers=kw.get("walkable_lasers", True),
                auto_reset=kw.get("auto_reset", True), seed=kw.get("seed", 0), env_id_base=kw.get("env_id_base", 0),
                extras=kw.get("extras"), pbrs=kw.get("pbrs"), obs_type=kw.get("obs_type", "layered"),
-               padding_size=kw.get("padding_size", 0))
+               padding_size=kw.get("padding_size", 0), randomize_lasers=kw.get("randomize_lasers", False))
     ora = lo.OracleVec(maps, map_of_env, n_envs, **okw)
     vec = lle_b200.VecWorld(maps, n_envs, map_of_env=map_of_env, **kw)
     dev = Dev(vec)
@@ -219,6 +219,38 @@ def test_random_maps_fuzz():
             if t % 3 == 0 or t == 39:
                 assert_same(dev, ora, dev.pull(), f"map {n_run} ({kw}) step {t}\n{text}")
         n_run += 1
+
+
+def test_randomize_lasers():
+    """LLE(randomize_lasers=True) (env.py:198-200): every LLE-level reset (explicit, masked, automatic) recolours the env's
+    sources; the colours come from the library's own Philox stream, restated by the oracle (Python's `random` is unpinned)."""
+    for maps, moe, n, kw in (([level_text(6)], None, 400, dict()), ([level_text(4)], None, 300, dict(obs_type="partial5x5", walkable_lasers=False)),
+                             ([level_text(3), level_text(4)], [e % 2 for e in range(256)], 256, dict(reward_dim=4, obs_type="perspective")),
+                             ([level_text(5)], None, 200, dict(auto_reset=False, extras="laser_subgoal"))):
+        ora, dev = make_pair(maps, moe, n, seed=95, randomize_lasers=True, **kw)
+        assert_same(dev, ora, dev.pull(), "construction: the colours of the text")
+        colours0 = dev.vec.source_colours().cpu().numpy()
+        for t in range(150):
+            ora.step(None); dev.vec.step(None)
+            if t % 5 == 0:
+                assert_same(dev, ora, dev.pull(), f"step {t} ({kw})")
+        ora.reset(); dev.vec.reset()
+        assert_same(dev, ora, dev.pull(), "explicit reset")
+        colours1 = dev.vec.source_colours().cpu().numpy()
+        assert (colours1 != colours0).any() and colours1.min() >= 0 and colours1.max() < ora.A
+        if ora.NB >= 2 and n >= 256:
+            assert len({tuple(c) for c in colours1}) > 2  # envs draw independently
+        mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+        ora.reset(mask); dev.vec.reset(torch.from_numpy(mask).cuda())
+        assert_same(dev, ora, dev.pull(), "masked reset")
+        colours2 = dev.vec.source_colours().cpu().numpy()
+        assert np.array_equal(colours2[mask == 0], colours1[mask == 0])
+        for t in range(60):
+            ora.step(None); dev.vec.step(None)
+        assert_same(dev, ora, dev.pull(), "after more steps")
+    import lle_b200
+    with pytest.raises(ValueError):  # a laser across a start position: set_colour would raise in the reference
+        lle_b200.VecWorld("S0 . X\nL0E S1 X", 4, randomize_lasers=True)
 
 
 def test_masked_reset():

@@ -642,3 +642,19 @@ def test_all_observation_shapes(api):  # [O] test_all_shapes for the generators 
 def test_unknown_observation_type(api):
     with pytest.raises(ValueError):
         api.LLE("S0 X", obs_type="nope")
+
+
+def test_randomized_lasers(api):  # [E] python/tests/test_env.py:381 test_randomized_lasers
+    env = api.LLE("S0 S1 L0S\n.   . L1W\n.   . L0W\nX   X  .", randomize_lasers=True)
+    n_sources = len(env.laser_sources)
+    encountered = [[False] * env.n_agents for _ in range(n_sources)]
+    for _ in range(200):  # the reference allows 1,000 tries; 2^-200 is already impossible enough
+        env.reset()
+        for k, source in enumerate(env.laser_sources):
+            encountered[k][source.agent_id] = True
+        if all(all(e) for e in encountered):
+            break
+    assert all(all(e) for e in encountered), "the two colours were never encountered for some lasers"
+    # the laser tiles follow their source (world.lasers reads the live colour)
+    by_id = {s.laser_id: s.agent_id for s in env.laser_sources}
+    assert all(l.agent_id == by_id[l.laser_id] for l in env.lasers)
