@@ -126,7 +126,7 @@ typedef struct {
     int32_t auto_reset;      /* reset a done env inside the step that finished it (not in the reference) */
     int32_t lle_semantics;   /* 1: LLE.step rules (done envs refuse to step, env.py:166-167); 0: raw World */
     int32_t write_obs;       /* 0 skips the layered observation (state/avail/reward still written)     */
-    uint64_t seed;           /* Philox key for device-sampled actions                                  */
+    uint64_t seed;           /* Philox key: sampled actions, start sampling, laser colours (World::seed) */
     uint64_t env_id_base;    /* global id of env 0 (sharding over GPUs keeps streams independent of the GPU count) */
     /* LaserSubgoal extras (python/lle/env/extras_generators.py:75-101, Builder.add_extras("laser_subgoal")):
      * n_extras = 0 off, -1 all sources, else the first n_extras entries of extras_src (indices in World::sources() order) */
