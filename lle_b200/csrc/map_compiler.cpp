@@ -395,10 +395,12 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     for (int a = 0; a < A; ++a) h.start_order[a] = (uint8_t)order[a];
     std::vector<uint32_t> chunk_tbl;  // patches are sorted by idx: chunk c owns entries [tbl[c], tbl[c+1])
     {
-        const int n_chunks = (obs_floats + LLE_CHUNK_FLOATS - 1) / LLE_CHUNK_FLOATS;
+        const int64_t block = ((int64_t)obs_floats + 3) / 4 * 4;  // the vec pads a block to 4 floats (obs_stride)
+        const int chunk = lle_chunk_floats(block);
+        const int n_chunks = (int)((block + chunk - 1) / chunk);
         size_t k = 0;
         for (int c = 0; c <= n_chunks; ++c) {
-            while (k < patch.size() && patch[k].idx < (uint32_t)c * LLE_CHUNK_FLOATS) ++k;
+            while (k < patch.size() && patch[k].idx < (uint32_t)c * (uint32_t)chunk) ++k;
             chunk_tbl.push_back((uint32_t)k);
         }
     }

@@ -503,10 +503,17 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->n_buf = 1;
     } else {
         v->E = 1;
-        v->chunk_floats = LLE_CHUNK_FLOATS;  // 12 KB chunks
+        v->chunk_floats = lle_chunk_floats(stride);  // <= 12 KB, balanced (static_map.h)
         v->n_chunks = (int)((stride + v->chunk_floats - 1) / v->chunk_floats);
         v->tile_floats = v->chunk_floats;
-        v->group = std::max(8, 32 / v->Wd);
+        // A ticket walks its worlds chunk by chunk, so the two tile buffers are rebuilt from the static plane twice per
+        // chunk index and ticket: the more worlds per ticket, the fewer rebuilds per world (perspective level 6 x 65,536:
+        // 350 / 317 / 299 us/step with 8 / 16 / 32) — as long as there are enough tickets to balance the warps (64x64 x 16,384:
+        // 809 / 825 / 1,084 us/step): at least 2,048 tickets.
+        // Tickets are also the grain of the dataflow ordering between overlapped steps, so very large ones stall the
+        // pipeline (64x64 x 131,072: 2.02e7 / 2.07e7 / 1.72e7 env-steps/s with 8 / 16 / 32): at most 6 MB per ticket.
+        v->group = 32;
+        while (v->group > std::max(8, 32 / v->Wd) && (v->N_pad / v->group < 2048 || (int64_t)v->group * stride * 4 > (6 << 20))) v->group >>= 1;
         v->n_buf = 2;
     }
     if (spec.kind == LLE_OBS_PARTIAL && v->tile_floats <= 3072) v->n_buf = 2;  // zero-fill one tile while the other drains
