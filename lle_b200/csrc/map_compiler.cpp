@@ -347,7 +347,19 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         for (auto& s : cm.sources)
             if (A + 1 + s.colour >= Cp) obs_invalid = true;  // obs[a, LASER_0 + agent_id]: numpy IndexError
         stat.assign(4, 0.0f);
+        // For the feature-driven renderer (sparse maps): every cell content the generator encodes, as a patch entry with
+        // idx = packed position | channel << 16, stat = the value, src = LLE_FEATURE_STATIC / 0xFF (gem) / beam index.
+        // All writes commute: equal values or distinct (channel, cell) targets.
         patch.clear();
+        auto feature = [&](const Cell& c, int channel, int value, int src, int bit) {
+            if (channel < Cp)
+                patch.push_back(LlePatch{(uint32_t)((c.i << 8) | c.j) | ((uint32_t)channel << 16), (uint8_t)src, (uint8_t)bit, (int8_t)value, 0});
+        };
+        for (const auto& c : cm.walls) feature(c, A, 1, LLE_FEATURE_STATIC, 0);                       // WALL = n_agents
+        for (const auto& c : cm.exits) feature(c, 2 * A + 2, 1, LLE_FEATURE_STATIC, 0);               // EXIT
+        for (const auto& sinfo : cm.sources) feature(sinfo.pos, A + 1 + sinfo.colour, -1, LLE_FEATURE_STATIC, 0);
+        for (int g = 0; g < G; ++g) feature(cm.gems[g], 2 * A + 1, 1, 0xFF, g);                        // GEM, while not collected
+        for (const auto& l : cm.lasers) feature(l.pos, A + 1 + l.colour, 1, l.beam, l.offset);       // listed laser tiles, while on
         planes.clear();
         obs_floats = A * Cp * spec.param * spec.param;
         view_agents = 0;

@@ -36,6 +36,7 @@ static_assert(sizeof(LleBeam) == 24, "LleBeam layout");
 // One dynamic cell of the layered observation other than the agents' own cells: a laser tile
 // (1.0 while its beam bit is on) or a gem (1.0 until collected).  `idx` is the float index inside
 // one env's (C,H,W) block; `stat` is what the static plane holds there (restored when the bit is off).
+#define LLE_FEATURE_STATIC 0xFD  // LlePatch.src of a partial-observation feature that does not depend on state
 struct LlePatch {
     uint32_t idx;
     uint8_t src;   // beam index, or 0xFF for a gem

@@ -87,6 +87,7 @@ struct lle_vec {
     int64_t obs_stride = 0;
     // launch configuration
     bool fast = false, pdl = true;
+    bool by_feature = false;  // partial observations rendered feature by feature (kernel KIND 2): every map has <= 2 s^2 features
     bool force_narrow = false;  // LLE_B200_FORCE_NARROW=1 (tests)
     uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
@@ -135,8 +136,9 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = overlaps ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, true>, p);
-    return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, false>, p);
+    if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 1>, p);
+    if (v->by_feature) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 2>, p);
+    return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 0>, p);
 }
 cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
     p.sched = v->d_sched + 2 * (v->launch_index++ % kSchedSlots);
@@ -184,9 +186,9 @@ cudaError_t resolve_memops() {
     return cudaSuccess;
 }
 
-template <int MODE, bool FAST>
+template <int MODE, int KIND>
 cudaError_t configure_kernel(size_t smem, int* blocks) {
-    auto kern = lle_world_kernel<MODE, FAST>;
+    auto kern = lle_world_kernel<MODE, KIND>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int b = 0;
@@ -539,15 +541,24 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     for (int k = 0; k < n_maps; ++k) random_starts = random_starts || cms[k]->header().random_starts;
     v->fast = v->n_chunks == 1 && v->E <= 32 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 && opts->write_obs &&
               spec.kind == LLE_OBS_LAYERED && !v->randomize && !random_starts && !env_int("LLE_B200_NO_FAST", 0);
+    if (spec.kind == LLE_OBS_PARTIAL && !env_int("LLE_B200_NO_FEATURES", 0)) {
+        v->by_feature = true;  // a window task costs about three feature tasks (measured on level 6)
+        for (int k = 0; k < n_maps; ++k) v->by_feature = v->by_feature && (int)cms[k]->header().n_patch <= 2 * spec.param * spec.param;
+        for (const auto& m : v->variant_maps) v->by_feature = v->by_feature && (int)m.header().n_patch <= 2 * spec.param * spec.param;
+    }
     int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
     if (v->fast) {
-        LLE_CUDA((configure_kernel<MODE_STEP, true>(v->smem, &blocks_per_sm)));
-        LLE_CUDA((configure_kernel<MODE_RESET, true>(v->smem, &blocks_per_sm)));
-        LLE_CUDA((configure_kernel<MODE_SET_STATE, true>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_STEP, 1>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_RESET, 1>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_SET_STATE, 1>(v->smem, &blocks_per_sm)));
+    } else if (v->by_feature) {
+        LLE_CUDA((configure_kernel<MODE_STEP, 2>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_RESET, 2>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_SET_STATE, 2>(v->smem, &blocks_per_sm)));
     } else {
-        LLE_CUDA((configure_kernel<MODE_STEP, false>(v->smem, &blocks_per_sm)));
-        LLE_CUDA((configure_kernel<MODE_RESET, false>(v->smem, &blocks_per_sm)));
-        LLE_CUDA((configure_kernel<MODE_SET_STATE, false>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_STEP, 0>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_RESET, 0>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_SET_STATE, 0>(v->smem, &blocks_per_sm)));
     }
     if (blocks_per_sm < 1) return fail(LLE_CUDA_ERROR, "kernel does not fit on an SM");
     blocks_per_sm = std::min(blocks_per_sm, std::max(1, env_int("LLE_B200_MAX_CTAS_PER_SM", 16)));
@@ -665,6 +676,8 @@ int swap_map(lle_vec* v, int map_index, const std::vector<SourceState>& sources,
     }
     if (v->fast && cm.header().n_patch > 64)
         return fail(LLE_LIMIT_EXCEEDED, "the modified map has more than 64 dynamic observation cells (vec was created for the fast tile path)");
+    if (v->by_feature && (int)cm.header().n_patch > 2 * v->opts.obs_param * v->opts.obs_param)
+        return fail(LLE_LIMIT_EXCEEDED, "the modified map has too many features for the feature-driven partial renderer the vec was created with");
     LLE_CUDA(cudaSetDevice(v->device));
     LLE_CUDA(cudaStreamSynchronize(s));  // control-plane operation: nothing of this vec is in flight while its map changes
     uint8_t* d = nullptr;

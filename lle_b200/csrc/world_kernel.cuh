@@ -730,8 +730,11 @@ __device__ __noinline__ int recolour_variant(int32_t* map_of_env, uint64_t env_i
 // FAST: the common shape — one map for the whole batch, one whole world per tile, a single tile buffer, at most 64
 // patch entries and a record of at most 32 words.  The tile then never changes map or chunk, so the tag / freshness
 // bookkeeping of the general path disappears and the per-tile work is a handful of shared-memory accesses.
-template <int MODE, bool FAST>
+// KIND: 0 general, 1 FAST (above), 2 general with the feature-driven renderer of partial observations (sparse maps).
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const KParams p) {
+    constexpr bool FAST = KIND == 1;
+    constexpr bool BY_FEATURE = KIND == 2;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LleStateLayout L = p.L;
@@ -1210,7 +1213,25 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     }
                     const uint32_t* cur = recs + (size_t)g * stride;
                     float* sub = tile + (size_t)s * p.obs_stride;
-                    for (int q = lane; q < A * s2; q += 32) {
+                    if constexpr (BY_FEATURE) {
+                        // Sparse maps (the host selects this kernel when every map has at most 2 s^2 features): one lane per
+                        // (agent, feature) — the map's walls, exits, sources, gems and laser tiles — instead of one per
+                        // (agent, window cell): uniform, branch-light tasks.  A 7x7 window of level 6 has 196 cell tasks of
+                        // ~100 instructions each; its 300 feature tasks take ~20 each (173 -> 142 us/step).
+                        const int F = rm.n_patch;
+                        const float inv_f = 1.0f / (float)max(F, 1);
+                        for (int t = lane; t < A * F; t += 32) {
+                            const int a = (int)(((float)t + 0.5f) * inv_f), f = t - a * F;
+                            const LlePatch pe = rm.patches[f];
+                            const uint32_t pa = rec_pos(cur, a);
+                            const int di = (int)((pe.idx >> 8) & 255u) - (int)(pa >> 8) + ctr;
+                            const int dj = (int)(pe.idx & 255u) - (int)(pa & 0xFFu) + ctr;
+                            if (di < 0 || dj < 0 || di >= sz || dj >= sz) continue;
+                            if (pe.src != LLE_FEATURE_STATIC && !rec_lit(cur, L, pe)) continue;
+                            sub[(a * Cp + (int)(pe.idx >> 16)) * s2 + di * sz + dj] = (float)pe.stat;
+                        }
+                    }
+                    for (int q = lane; q < (BY_FEATURE ? 0 : A * s2); q += 32) {
                         // (agent, row, column) of the window cell; the float products are exact for these small integers
                         const int a = (int)(((float)q + 0.5f) * inv_s2), r = q - a * s2;
                         const int wi = (int)(((float)r + 0.5f) * inv_sz), wj = r - wi * sz;
