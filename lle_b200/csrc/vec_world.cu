@@ -87,6 +87,7 @@ struct lle_vec {
     int64_t obs_stride = 0;
     // launch configuration
     bool fast = false, pdl = true;
+    int feature_limit = 0;
     bool by_feature = false;  // partial observations rendered feature by feature (kernel KIND 2): every map has <= 2 s^2 features
     bool force_narrow = false;  // LLE_B200_FORCE_NARROW=1 (tests)
     uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
@@ -543,8 +544,9 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
               spec.kind == LLE_OBS_LAYERED && !v->randomize && !random_starts && !env_int("LLE_B200_NO_FAST", 0);
     if (spec.kind == LLE_OBS_PARTIAL && !env_int("LLE_B200_NO_FEATURES", 0)) {
         v->by_feature = true;  // a window task costs about three feature tasks (measured on level 6)
-        for (int k = 0; k < n_maps; ++k) v->by_feature = v->by_feature && (int)cms[k]->header().n_patch <= 2 * spec.param * spec.param;
-        for (const auto& m : v->variant_maps) v->by_feature = v->by_feature && (int)m.header().n_patch <= 2 * spec.param * spec.param;
+        v->feature_limit = env_int("LLE_B200_FEATURE_FACTOR", 2) * spec.param * spec.param;
+        for (int k = 0; k < n_maps; ++k) v->by_feature = v->by_feature && (int)cms[k]->header().n_patch <= v->feature_limit;
+        for (const auto& m : v->variant_maps) v->by_feature = v->by_feature && (int)m.header().n_patch <= v->feature_limit;
     }
     int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
     if (v->fast) {
@@ -676,7 +678,7 @@ int swap_map(lle_vec* v, int map_index, const std::vector<SourceState>& sources,
     }
     if (v->fast && cm.header().n_patch > 64)
         return fail(LLE_LIMIT_EXCEEDED, "the modified map has more than 64 dynamic observation cells (vec was created for the fast tile path)");
-    if (v->by_feature && (int)cm.header().n_patch > 2 * v->opts.obs_param * v->opts.obs_param)
+    if (v->by_feature && (int)cm.header().n_patch > v->feature_limit)
         return fail(LLE_LIMIT_EXCEEDED, "the modified map has too many features for the feature-driven partial renderer the vec was created with");
     LLE_CUDA(cudaSetDevice(v->device));
     LLE_CUDA(cudaStreamSynchronize(s));  // control-plane operation: nothing of this vec is in flight while its map changes
