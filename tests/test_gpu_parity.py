@@ -497,6 +497,31 @@ def test_config3_full_size_windows_against_the_oracle():
                     assert np.array_equal(a, np.asarray(getattr(ora, name))), f"window at {s0}, step {t}: {name}"
 
 
+def test_config5_large_batch_windows_against_the_oracle():
+    """BASELINE configs[4] shape (64x64, 8 agents, 16 sources) at 16,384 worlds (5.4 GB of observations, 32 worlds per
+    ticket): windows of the batch replayed by oracle batches with the same global env ids, bit-exact."""
+    import lle_b200
+    from _util import synthetic_map
+
+    text = synthetic_map(64, 64, 8, 16, seed=5)
+    n = 16384
+    vec = lle_b200.VecWorld(text, n, seed=8)
+    starts = [0, 5000, n - 24]
+    oracles = [lo.OracleVec([text], None, 24, seed=8, env_id_base=s0) for s0 in starts]
+    for t in range(24):
+        vec.step(None)
+        for ora in oracles:
+            ora.step(None)
+        if t % 6 == 5:
+            vec.synchronize()
+            for s0, ora in zip(starts, oracles):
+                for name in ("obs", "state", "avail", "reward", "done", "events", "actions", "err"):
+                    a = getattr(vec, name)[s0:s0 + 24].cpu().numpy()
+                    assert np.array_equal(a, np.asarray(getattr(ora, name))), f"window at {s0}, step {t}: {name}"
+    obs = vec.obs
+    assert torch.equal(obs[:, :8].sum(dim=(2, 3)), torch.ones(n, 8, device=obs.device))  # one cell per agent plane, every world
+
+
 def test_config4_mixed_levels_group():
     """BASELINE configs[3] at reduced size: the six levels mixed, one sub-batch per level, contiguous global env ids."""
     import lle_b200
