@@ -298,6 +298,80 @@ LLE_API int lle_vec_timing_end(lle_vec* vec, void* cuda_stream, float* total_ms,
  * launch, 4 globaltimer readings in ns: kernel start, first observation store issued, last store issued, warp end. */
 LLE_API int lle_vec_debug_timeline(lle_vec* vec, uint64_t* out_host, int64_t cap_warps, int64_t* n_warps);
 
+/* =====================================================================================================================
+ * Layout generator: `lle.generate(...)` / `WorldGenerator` of python/lle/generator/generator.py, one
+ * *attempt* per device thread.
+ *
+ * An attempt is `WorldGenerator._try_generate(seed)` with constraint=None (generator.py:243-254): seed a
+ * `random.Random`, place agents -> exits -> lasers -> walls -> gems (generator.py:188-228, placements.py, geometry.py),
+ * check the beam geometry (candidates.py:27-41).  The device code re-implements CPython's `random.Random` (MT19937 seeded
+ * with an int, `_randbelow_with_getrandbits`, `sample`, `shuffle`, `choice`, `randint`, `choices`; CPython 3.12), so the
+ * layout of seed s is the reference's layout for that seed, bit for bit (tests/golden/generator_vectors.json).
+ * Batches correspond to the reference's parallel path `_generate_n_multi` (generator.py:296-314), whose attempts are
+ * seeded one by one with `rng.randrange(sys.maxsize)`: lle_gen_attempt_seeds reproduces that seed list.
+ *
+ * Not the reference's: (1) `cluster_shape` is an option (placements.py:44-60 draws it from Python's global, unseeded
+ * generator in each of its three callers; here one shape serves all three); (2) the `labels` byte is a breadth-first
+ * reachability heuristic of this library - LLE_GEN_WALKABLE: the agents can be matched to distinct exits they reach
+ * through non-wall, non-source cells; LLE_GEN_INDEPENDENT: the same when agent a also avoids every cell lit (at reset,
+ * nobody blocking) by a beam of another colour; LLE_GEN_NEEDS_BLOCKER: walkable but not independent.  It is NOT the
+ * SAT-based `Cooperative()` / `Independent()` predicates of world_filter.py (out of scope).
+ * Limits: height, width <= 32; n_agents <= 32.
+ * ===================================================================================================================== */
+typedef struct lle_gen lle_gen;
+
+enum { LLE_GEN_STARTS_RANDOM = 0, LLE_GEN_STARTS_EDGE = 1, LLE_GEN_STARTS_CLUSTERED = 2 };
+enum { LLE_GEN_EXITS_RANDOM = 0, LLE_GEN_EXITS_EDGE = 1, LLE_GEN_EXITS_CLUSTER = 2, LLE_GEN_EXITS_OPPOSITE = 3 };
+enum { LLE_GEN_LASERS_FREE = 0, LLE_GEN_LASERS_CROSS_AGENT = 1, LLE_GEN_LASERS_CROSS_CLUSTER = 2 };
+enum { LLE_GEN_SPAN_ANY = 0, LLE_GEN_SPAN_ACROSS = -1 };           /* or an explicit minimum length >= 2 */
+enum { LLE_GEN_WALLS_AUTO = -1 };                                   /* (width * height) / 10, generator.py:165 */
+enum { LLE_GEN_WALKABLE = 1, LLE_GEN_INDEPENDENT = 2, LLE_GEN_NEEDS_BLOCKER = 4 };
+/* cell codes of the generated grids */
+enum { LLE_CELL_FLOOR = 0, LLE_CELL_WALL = 1, LLE_CELL_EXIT = 2, LLE_CELL_GEM = 3, LLE_CELL_START = 16 /* + agent */,
+       LLE_CELL_SOURCE = 64 /* + 4 * colour + direction (0 N, 1 S, 2 E, 3 W) */ };
+
+/* The keyword arguments of WorldGenerator.__init__ (generator.py:97-114). */
+typedef struct {
+    int32_t width, height, n_agents;
+    int32_t starts, exits;
+    int32_t n_lasers, n_gems;
+    int32_t laser_placement, laser_span;
+    int32_t n_walls, walls_shapes;                   /* walls_style: 0 "individual", 1 "shapes" */
+    int32_t n_rooms_rows, n_rooms_cols, door_size;   /* rooms mode when n_rooms_rows > 0 (generator.py:156-161) */
+    int32_t cluster_h, cluster_w;                    /* clustered starts / exits only */
+} lle_gen_options;
+LLE_API void lle_gen_default_options(lle_gen_options* opts);
+
+/* Validates like WorldGenerator.__init__ (generator.py:116-181; LLE_INVALID_ARGUMENT carries its message) and allocates
+ * device buffers for `capacity` attempts per run. */
+LLE_API int lle_gen_create(const lle_gen_options* opts, int32_t device, int64_t capacity, lle_gen** out);
+LLE_API int lle_gen_destroy(lle_gen* gen);
+
+/* generator.py:296-301: out[i] = the i-th `rng.randrange(sys.maxsize)` after `rng.seed(seed)` (host, MT19937). */
+LLE_API int lle_gen_attempt_seeds(uint64_t seed, int64_t n, uint64_t* out);
+
+/* Runs n <= capacity independent chains on the device, one per thread.  Chain i seeds its generator with seeds_dev[i] (or
+ * first_seed + i when seeds_dev is NULL) and makes up to max_attempts attempts from that one stream, stopping at the first
+ * layout whose label byte contains every bit of `require` (0: any layout): max_attempts = 1 is
+ * `WorldGenerator._try_generate(seed)`, max_attempts = m is `WorldGenerator.generate(m, seed)` (generator.py:268-284), both
+ * with the label test in the place of the reference's constraint (`_accept_world` draws no random number). */
+LLE_API int lle_gen_run(lle_gen* gen, const uint64_t* seeds_dev, uint64_t first_seed, int64_t n, int32_t max_attempts, uint32_t require,
+                        void* cuda_stream);
+
+typedef struct {
+    int64_t capacity, n;       /* n: chains of the last run */
+    int32_t height, width;
+    uint8_t* cells;            /* u8[capacity, height*width] cell codes (all floor when the chain found nothing) */
+    uint8_t* status;           /* u8[capacity] 1 = layout, 0 = none (LayoutRetry / rejected in every attempt) */
+    uint8_t* labels;           /* u8[capacity] LLE_GEN_* bits (0 when status is 0) */
+    int32_t* tries;            /* i32[capacity] attempts the chain used */
+} lle_gen_buffers;
+LLE_API int lle_gen_get_buffers(lle_gen* gen, lle_gen_buffers* out);
+
+/* The v1 map text of a cell grid (host; world_builder.py:83-88: tokens joined by ' ', rows by '\n'). Returns the length
+ * needed (without the terminator) in *len; writes at most cap bytes including the terminator. */
+LLE_API int lle_gen_cells_to_text(const uint8_t* cells_host, int32_t height, int32_t width, char* out, size_t cap, size_t* len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@ SYMBOLS = [
     "lle_vec_pipeline_wait", "lle_vec_set_source", "lle_vec_get_sources", "lle_vec_set_exits", "lle_vec_set_state",
     "lle_vec_export_raw", "lle_vec_set_seed", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
     "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline",
+    "lle_gen_default_options", "lle_gen_create", "lle_gen_destroy", "lle_gen_attempt_seeds", "lle_gen_run", "lle_gen_get_buffers",
+    "lle_gen_cells_to_text",
 ]
 
 
@@ -45,6 +47,17 @@ class VecBuffers(C.Structure):
         ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p), ("record_bytes", C.c_int64), ("extras", C.c_void_p), ("extras_dim", C.c_int32), ("pad", C.c_int32)] + [
         (n, C.c_int32) for n in ("obs_type", "obs_param", "obs_view_agents", "obs_c", "obs_h", "obs_w", "obs_invalid", "pad2")] + [
         ("map_index", C.c_void_p), ("n_variants", C.c_int32), ("pad3", C.c_int32)]
+
+
+class GenOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "n_agents", "starts", "exits", "n_lasers", "n_gems", "laser_placement",
+                                          "laser_span", "n_walls", "walls_shapes", "n_rooms_rows", "n_rooms_cols", "door_size",
+                                          "cluster_h", "cluster_w")]
+
+
+class GenBuffers(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("n", C.c_int64), ("height", C.c_int32), ("width", C.c_int32), ("cells", C.c_void_p),
+                ("status", C.c_void_p), ("labels", C.c_void_p), ("tries", C.c_void_p)]
 
 
 _lib = None
@@ -99,6 +112,14 @@ def lib():
     L.lle_vec_timing_begin.argtypes = [C.c_void_p, C.c_void_p]
     L.lle_vec_timing_end.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     L.lle_vec_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.lle_gen_default_options.argtypes = [C.POINTER(GenOptions)]
+    L.lle_gen_default_options.restype = None
+    L.lle_gen_create.argtypes = [C.POINTER(GenOptions), C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]
+    L.lle_gen_destroy.argtypes = [C.c_void_p]
+    L.lle_gen_attempt_seeds.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
+    L.lle_gen_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p]
+    L.lle_gen_get_buffers.argtypes = [C.c_void_p, C.POINTER(GenBuffers)]
+    L.lle_gen_cells_to_text.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L
 

@@ -102,3 +102,20 @@ def random_map(rng, allow_invalid: bool = False) -> str:
         i, j = rng.choice(cells)
         grid[i][j] = "S0"
     return "\n".join(" ".join(row) for row in grid)
+
+
+def build_gen_host_shim() -> str:
+    """g++ build of tests/host_shim/gen_host.cpp: the generator core of the CUDA kernel (lle_b200/csrc/gen_core.cuh,
+    __host__ __device__) instantiated on the host for the CPU test-suite.  Test infrastructure only."""
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "host_shim", "gen_host.cpp")
+    out_dir = os.path.join(here, "host_shim", "_build")
+    out = os.path.join(out_dir, "libgen_host.so")
+    csrc = os.path.join(os.path.dirname(here), "lle_b200", "csrc")
+    deps = [src, os.path.join(csrc, "gen_core.cuh"), os.path.join(csrc, "gen_config.hpp"), os.path.join(os.path.dirname(here), "include", "lle_b200.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", out], check=True)
+    return out
