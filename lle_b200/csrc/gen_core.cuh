@@ -56,44 +56,60 @@ struct Config {  // == lle_gen_options after validation (n_walls resolved, room 
 // --------------------------------------------------------------------------------------------------------------------
 // CPython's random.Random
 // --------------------------------------------------------------------------------------------------------------------
-struct PyRandom {
-    uint32_t mt[624];
-    int idx;
+// `Store` holds the 624 state words (a plain array: host stack, or local memory on the device).
+struct ArrayStore {
+    uint32_t w[624];
+    LLE_HD uint32_t& operator[](int i) { return w[i]; }
+};
 
-    // `base` = the state after init_genrand(19650218), a constant table (624 words) computed once by the host.
-    LLE_HD void seed(uint64_t s, const uint32_t* __restrict__ base) {
-        uint32_t key[2] = {(uint32_t)s, (uint32_t)(s >> 32)};
-        const int keylen = key[1] ? 2 : 1;  // random_seed: abs(seed) as little-endian 32-bit digits, at least one
-        for (int t = 0; t < 624; ++t) mt[t] = base[t];
-        int i = 1, j = 0;
-        uint32_t prev = mt[0];
-        for (int k = 624; k; --k) {
-            prev = (mt[i] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+template <class Store>
+struct PyRandomT {
+    Store mt;
+    int idx;  // next state word to regenerate and hand out
+
+    // random_seed(int) -> init_by_array(key) (Modules/_randommodule.c).  `base(i)` = word i of the state after
+    // init_genrand(19650218), a constant table.  The two passes of init_by_array are written without their wrap-around
+    // tests: pass 1 walks i = 1..623 and then i = 1 once more, pass 2 walks i = 2..623 and then i = 1; with a key of one or
+    // two 32-bit digits, `key[j] + j` alternates between k_odd (odd i) and k_even (even i).  Pass 1 reads the table
+    // directly, so the state is written once before pass 2 instead of being initialised first.
+    template <class Base>
+    LLE_HD void seed(uint64_t s, Base base) {
+        const uint32_t hi = (uint32_t)(s >> 32);
+        const uint32_t k_odd = (uint32_t)s;             // key[0] + 0
+        const uint32_t k_even = hi ? hi + 1u : k_odd;    // key[1] + 1 when abs(seed) has two digits, else key[0] + 0 again
+        uint32_t prev = base(0);
+        for (int i = 1; i < 623; i += 2) {
+            prev = (base(i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_odd;
             mt[i] = prev;
-            if (++i >= 624) { mt[0] = prev; i = 1; }
-            if (++j >= keylen) j = 0;
+            prev = (base(i + 1) ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_even;
+            mt[i + 1] = prev;
         }
-        for (int k = 623; k; --k) {
+        prev = (base(623) ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_odd;
+        mt[623] = prev;
+        prev = (mt[1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_even;  // wrapped: mt[0] = mt[623], i = 1, step 623
+        mt[1] = prev;
+        for (int i = 2; i < 624; ++i) {
             prev = (mt[i] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
             mt[i] = prev;
-            if (++i >= 624) { mt[0] = prev; i = 1; }
         }
+        prev = (mt[1] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - 1u;    // wrapped again
+        mt[1] = prev;
         mt[0] = 0x80000000u;
-        idx = 624;
+        idx = 0;
     }
     LLE_HD static uint32_t mix(uint32_t u, uint32_t v, uint32_t far) {
         const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
-        return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        return far ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
     }
-    LLE_HD_NOINLINE void twist() {
-        for (int k = 0; k < 227; ++k) mt[k] = mix(mt[k], mt[k + 1], mt[k + 397]);
-        for (int k = 227; k < 623; ++k) mt[k] = mix(mt[k], mt[k + 1], mt[k - 227]);
-        mt[623] = mix(mt[623], mt[0], mt[396]);
-        idx = 0;
-    }
+    // genrand_uint32 with the regeneration done one word at a time: the block update of the reference implementation
+    // rewrites mt[0..623] in increasing order and in place, so producing word k right before it is handed out reads
+    // exactly the same old / new neighbours.  An attempt that draws 80 numbers regenerates 80 words, not 624.
     LLE_HD uint32_t next() {
-        if (idx >= 624) twist();
-        uint32_t y = mt[idx++];
+        const int k = idx;
+        const int k1 = k == 623 ? 0 : k + 1;
+        uint32_t y = mix(mt[k], mt[k1], mt[k < 227 ? k + 397 : k - 227]);
+        mt[k] = y;
+        idx = k1;
         y ^= y >> 11;
         y ^= (y << 7) & 0x9d2c5680u;
         y ^= (y << 15) & 0xefc60000u;
@@ -160,9 +176,12 @@ LLE_HD int nth_set_bit(uint32_t x, int n) {
     return ctz32(x);
 }
 
+using PyRandom = PyRandomT<ArrayStore>;
+
+template <class Rng>
 struct Attempt {
     const Config& c;
-    PyRandom& rng;
+    Rng& rng;
     uint16_t* work;  // kWork entries
     int H, W;
     Grid reserved;
@@ -175,7 +194,7 @@ struct Attempt {
     int edge, agent_r, agent_c, exit_r, exit_c;
     int16_t lanes[kMaxAgents];
 
-    LLE_HD Attempt(const Config& cfg, PyRandom& r, uint16_t* w) : c(cfg), rng(r), work(w), H(cfg.height), W(cfg.width) {}
+    LLE_HD Attempt(const Config& cfg, Rng& r, uint16_t* w) : c(cfg), rng(r), work(w), H(cfg.height), W(cfg.width) {}
 
     // ---- populations ------------------------------------------------------------------------------------------------
     // number of cells whose bit is clear in `blocked` (row masks)
@@ -731,10 +750,16 @@ struct Attempt {
 // attempts drawing from the same stream; max_attempts = 1 is `_try_generate(seed)`.  A layout is accepted when its label
 // byte contains every bit of `require` (the place of `_accept_world`, generator.py:256-266, which draws no random number).
 // Outputs: cells[H*W], *status (1 = layout, 0 = none), *label, *tries (attempts used).
-LLE_HD void chain(const Config& cfg, const uint32_t* __restrict__ mt_base, uint64_t seed, int max_attempts, uint8_t require, PyRandom& rng,
+struct TablePtr {  // the init_genrand table through a pointer (host); the kernel reads it from constant memory
+    const uint32_t* p;
+    LLE_HD uint32_t operator()(int i) const { return p[i]; }
+};
+
+template <class Rng, class Base>
+LLE_HD void chain(const Config& cfg, Base mt_base, uint64_t seed, int max_attempts, uint8_t require, Rng& rng,
                   uint16_t* work, uint8_t* cells, uint8_t* status, uint8_t* label, int32_t* tries) {
     rng.seed(seed, mt_base);
-    Attempt at(cfg, rng, work);
+    Attempt<Rng> at(cfg, rng, work);
     bool ok = false;
     uint8_t lab = 0;
     int t = 0;

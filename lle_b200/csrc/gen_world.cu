@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,20 +27,32 @@ using lle::fail;
 
 namespace {
 
-// Thread per attempt, grid-stride.  Everything an attempt touches besides its output row lives in local memory
-// (MT19937 state 2.5 KB, candidate list 8 KB, masks), which the hardware interleaves across the lanes of a warp; the
-// attempts of a warp diverge freely (rejection sampling, retries), so the kernel is latency- and issue-bound, not
-// bandwidth-bound: see DESIGN.md 4b.
-__global__ void __launch_bounds__(128) lle_gen_kernel(const __grid_constant__ llegen::Config cfg, const uint32_t* __restrict__ mt_base,
-                                                      const uint64_t* __restrict__ seeds, uint64_t first_seed, int64_t n, int max_attempts,
-                                                      uint8_t require, uint8_t* __restrict__ cells, uint8_t* __restrict__ status,
-                                                      uint8_t* __restrict__ labels, int32_t* __restrict__ tries) {
+// init_genrand(19650218): 624 words, read with a warp-uniform index by the first seeding pass
+__constant__ uint32_t c_mt_base[624];
+struct ConstTable {
+    __device__ __forceinline__ uint32_t operator()(int i) const { return c_mt_base[i]; }
+};
+
+// Thread per chain, grid-stride.  What an attempt costs is mostly CPython's seeding: init_by_array is 1,247 dependent steps
+// over the 624-word MT19937 state (gen_core.cuh), so the kernel is latency- and issue-bound and wants many warps per SM to
+// overlap those chains.  The state (2.5 KB) and the placement scratch (candidate list, masks) live in local memory, which
+// the hardware interleaves across the lanes of a warp; 128-thread CTAs at <= 64 registers, `ctas_per_sm` of them resident
+// (8 for small grids = 1,024 threads per SM; fewer for large grids, whose candidate lists would otherwise push the
+// states out of L1/L2).  Measured alternatives: the states in lane-interleaved shared memory (92 threads per
+// SM fill the 227 KB) are 3x slower - three warps cannot hide the chain.  Attempts of a warp diverge freely (rejection
+// sampling, retries).
+constexpr int kGenThreads = 128;
+
+__global__ void __launch_bounds__(kGenThreads, 8) lle_gen_kernel(const __grid_constant__ llegen::Config cfg, const uint64_t* __restrict__ seeds,
+                                                                 uint64_t first_seed, int64_t n, int max_attempts, uint8_t require,
+                                                                 uint8_t* __restrict__ cells, uint8_t* __restrict__ status,
+                                                                 uint8_t* __restrict__ labels, int32_t* __restrict__ tries) {
     llegen::PyRandom rng;
     alignas(8) uint16_t work[llegen::kWork];
     const int hw = cfg.height * cfg.width;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.x * kGenThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kGenThreads) {
         const uint64_t seed = seeds ? seeds[i] : first_seed + (uint64_t)i;
-        llegen::chain(cfg, mt_base, seed, max_attempts, require, rng, work, cells + i * hw, status + i, labels + i, tries + i);
+        llegen::chain(cfg, ConstTable{}, seed, max_attempts, require, rng, work, cells + i * hw, status + i, labels + i, tries + i);
     }
 }
 
@@ -48,7 +61,7 @@ struct HostMT {  // CPython's generator on the host, for lle_gen_attempt_seeds o
     explicit HostMT(uint64_t seed) {
         uint32_t base[624];
         llegen::mt_base_table(base);
-        r.seed(seed, base);
+        r.seed(seed, llegen::TablePtr{base});
     }
     // getrandbits(63): two 32-bit words, low word first, the last one shifted down (Modules/_randommodule.c)
     uint64_t bits63() {
@@ -65,7 +78,6 @@ struct lle_gen {
     llegen::Config cfg;
     int device = 0;
     int64_t capacity = 0, n = 0;
-    uint32_t* d_mt_base = nullptr;
     uint8_t* d_cells = nullptr;
     uint8_t* d_status = nullptr;
     uint8_t* d_labels = nullptr;
@@ -96,8 +108,7 @@ LLE_API int lle_gen_create(const lle_gen_options* opts, int32_t device, int64_t 
     g->opts = o, g->cfg = c, g->device = device, g->capacity = capacity;
     uint32_t base[624];
     llegen::mt_base_table(base);
-    cudaError_t e = cudaMalloc(&g->d_mt_base, sizeof(base));
-    if (e == cudaSuccess) e = cudaMemcpy(g->d_mt_base, base, sizeof(base), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpyToSymbol(c_mt_base, base, sizeof(base));
     if (e == cudaSuccess) e = cudaMalloc(&g->d_cells, (size_t)capacity * area);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_status, (size_t)capacity);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_labels, (size_t)capacity);
@@ -108,7 +119,12 @@ LLE_API int lle_gen_create(const lle_gen_options* opts, int32_t device, int64_t 
         lle_gen_destroy(g);
         return fail(LLE_CUDA_ERROR, std::string("lle_gen_create: ") + cudaGetErrorString(e));
     }
-    g->grid = sms * 4;  // 4 CTAs x 128 threads per SM: 16 warps hide the local-memory latency of the seeding loop
+    // resident CTAs per SM by grid size (measured on B200: 5x5 290 M attempts/s at 8, 10x10 61 M at 6, 32x32 3.1 M at 4);
+    // LLE_GEN_CTAS overrides it (development knob for A/B timing)
+    int ctas = area <= 36 ? 8 : area <= 144 ? 6 : 4;
+    if (const char* knob = std::getenv("LLE_GEN_CTAS"))
+        if (std::atoi(knob) > 0) ctas = std::atoi(knob);
+    g->grid = sms * ctas;
     *out = g;
     return LLE_OK;
 }
@@ -116,7 +132,6 @@ LLE_API int lle_gen_create(const lle_gen_options* opts, int32_t device, int64_t 
 LLE_API int lle_gen_destroy(lle_gen* g) {
     if (!g) return LLE_OK;
     cudaSetDevice(g->device);
-    cudaFree(g->d_mt_base);
     cudaFree(g->d_cells);
     cudaFree(g->d_status);
     cudaFree(g->d_labels);
@@ -145,10 +160,10 @@ LLE_API int lle_gen_run(lle_gen* g, const uint64_t* seeds_dev, uint64_t first_se
     GEN_CUDA(cudaSetDevice(g->device));
     g->n = n;
     if (n == 0) return LLE_OK;
-    const int64_t blocks_needed = (n + 127) / 128;
+    const int64_t blocks_needed = (n + kGenThreads - 1) / kGenThreads;
     const int grid = (int)(blocks_needed < g->grid ? blocks_needed : g->grid);
-    lle_gen_kernel<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(g->cfg, g->d_mt_base, seeds_dev, first_seed, n, max_attempts, (uint8_t)require,
-                                                                       g->d_cells, g->d_status, g->d_labels, g->d_tries);
+    lle_gen_kernel<<<grid, kGenThreads, 0, (cudaStream_t)cuda_stream>>>(g->cfg, seeds_dev, first_seed, n, max_attempts, (uint8_t)require, g->d_cells,
+                                                                        g->d_status, g->d_labels, g->d_tries);
     GEN_CUDA(cudaGetLastError());
     return LLE_OK;
 }

@@ -1,6 +1,6 @@
 """Joins the per-instruction counters of an ncu report (SASS source page) with nvdisasm's line info of the same kernel,
 and prints the instruction / stall-sample share per source line (development aid).
-Usage: python scratch/ncu_lines.py report.ncu-rep mangled_kernel_substring [top_n]"""
+Usage: python scratch/ncu_lines.py report.ncu-rep mangled_kernel_substring [top_n [cubin_prefix source_file]]"""
 import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, kern = sys.argv[1], sys.argv[2]
@@ -8,7 +8,9 @@ top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "lle_b200", "_native", "liblle_b200.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.startswith("vec_world")][0]
+cubin_prefix = sys.argv[4] if len(sys.argv) > 4 else "vec_world"
+source_file = sys.argv[5] if len(sys.argv) > 5 else "world_kernel.cuh"
+cubin = [f for f in os.listdir(tmp) if f.startswith(cubin_prefix)][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 lines_of = []  # program order: (offset, line, text)
 inside, cur = False, None
@@ -31,7 +33,7 @@ h = rows[1]
 ie, sm = h.index("Instructions Executed"), h.index("# Samples")
 data = rows[2:]
 assert len(data) == len(lines_of), (len(data), len(lines_of))
-src = open(os.path.join(root, "lle_b200", "csrc", "world_kernel.cuh")).read().splitlines()
+src = open(os.path.join(root, "lle_b200", "csrc", source_file)).read().splitlines()
 inst, samp = collections.Counter(), collections.Counter()
 for r, (off, line, text) in zip(data, lines_of):
     inst[line] += float(r[ie] or 0)
@@ -43,7 +45,7 @@ print(f"total warp instructions {ti:.0f}, samples {ts:.0f}")
 import re as _re
 fmarks = [(1, "file head")]
 for n, text in enumerate(src, 1):
-    m = _re.search(r"__device__ __forceinline__ [\w:<>\*&\s]+?\b(\w+)\(", text)
+    m = _re.search(r"(?:__device__ __forceinline__|LLE_HD(?:_NOINLINE)?) [\w:<>\*&\s]+?\b(\w+)\(", text)
     if m:
         fmarks.append((n, m.group(1)))
     elif "__global__" in text and "lle_world_kernel" in text:

@@ -25,6 +25,6 @@ extern "C" int gen_host_run(const lle_gen_options* opts, const uint64_t* seeds, 
     alignas(8) static thread_local uint16_t work[llegen::kWork];
     const int hw = cfg.height * cfg.width;
     for (int64_t i = 0; i < n; ++i) 
-        llegen::chain(cfg, base, seeds[i], max_attempts, (uint8_t)require, rng, work, cells + i * hw, status + i, labels + i, tries + i);
+        llegen::chain(cfg, llegen::TablePtr{base}, seeds[i], max_attempts, (uint8_t)require, rng, work, cells + i * hw, status + i, labels + i, tries + i);
     return 0;
 }
