@@ -32,6 +32,15 @@ class Action(enum.IntEnum):
     def cardinality() -> int:
         return 5
 
+    @staticmethod
+    def from_delta(di: int, dj: int) -> "Action":
+        """PyAction::from_delta (src/bindings/world/pyaction.rs:68-87).  As in the reference, the pair is read as (x, y):
+        (0, -1) is NORTH and (-1, 0) is WEST, unlike `.delta`, which is (row, column)."""
+        table = {(0, 0): Action.STAY, (-1, 0): Action.WEST, (1, 0): Action.EAST, (0, -1): Action.NORTH, (0, 1): Action.SOUTH}
+        if (di, dj) not in table:
+            raise ValueError(f"Invalid delta: ({di}, {dj}). Valid deltas for actions are (-1, 0), (1, 0), (0, -1), or (0, 1).")
+        return table[(di, dj)]
+
 
 _DELTAS = {0: (-1, 0), 1: (1, 0), 2: (0, 1), 3: (0, -1), 4: (0, 0)}
 _OPPOSITE = {Action.NORTH: Action.SOUTH, Action.SOUTH: Action.NORTH, Action.EAST: Action.WEST, Action.WEST: Action.EAST,

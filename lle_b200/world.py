@@ -241,11 +241,75 @@ class World(_Single):
         order = (Action.STAY, Action.NORTH, Action.EAST, Action.SOUTH, Action.WEST)
         return [[a for a in order if avail[agent, int(a)]] for agent in range(self.n_agents)]
 
+    def set_agents_positions(self, agents_positions) -> list[WorldEvent]:
+        """PyWorld::set_agents_positions (pyworld.rs:252-263): the current state with new positions, through set_state."""
+        state = self.get_state()
+        state.agents_positions = [tuple(int(x) for x in p) for p in agents_positions]
+        return self.set_state(state)
+
+    def set_agent_position(self, agent_id: int, position) -> list[WorldEvent]:
+        """PyWorld::set_agent_position (pyworld.rs:282-299)."""
+        if agent_id < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        if agent_id >= self.n_agents:
+            raise ValueError(f"Agent id {agent_id} is out of bounds")
+        state = self.get_state()
+        state.agents_positions[agent_id] = tuple(int(x) for x in position)
+        return self.set_state(state)
+
+    def gem_at(self, position) -> Gem:
+        """PyWorld::gem_at (pyworld.rs:315-327): only a top-level Gem tile qualifies; a gem wrapped by a laser tile is a
+        `Tile::Laser` there and raises like any other tile."""
+        i, j = (int(x) for x in position)
+        if not (0 <= i < self.height and 0 <= j < self.width):
+            raise IndexError("Position out of bounds")
+        on_beam = {l.pos for l in self.lasers}
+        for gem in self.gems:
+            if gem.pos == (i, j) and (i, j) not in on_beam:
+                return gem
+        raise ValueError(f"Tile at position {(i, j)} is not a gem")
+
+    def save(self, filename: str) -> None:
+        """PyWorld::save (pyworld.rs:183-189)."""
+        try:
+            with open(filename, "w") as f:
+                f.write(self.world_string)
+        except OSError as e:
+            raise ValueError(f"Could not write to file: {filename}: {e}") from e
+
+    def available_joint_actions(self) -> list[list[Action]]:
+        """World::available_joint_actions (world.rs:257-263): the cartesian product of the agents' available actions."""
+        import itertools
+
+        return [list(joint) for joint in itertools.product(*self.available_actions())]
+
     def get_state(self) -> WorldState:
         return self._world_state()
 
     def set_state(self, state: WorldState) -> list[WorldEvent]:
         return self._force_state(state)
+
+    # `impl Clone for World` (world.rs:645-652): a world re-built from the configuration (sources as they are now), then
+    # set_state(get_state()); PyWorld.__deepcopy__ / __getstate__ / __setstate__ (pyworld.rs:557-626) build on it.
+    def _config(self):
+        return (self._map.text, [(s.agent_id, s.is_enabled) for s in self.laser_sources], self.get_state(), self._vec.device.index or 0)
+
+    @staticmethod
+    def _from_config(text, sources, state, device):
+        w = World(text, device)
+        for src, (agent_id, enabled) in zip(w.laser_sources, sources):
+            if src.agent_id != agent_id:
+                src.agent_id = agent_id
+            if src.is_enabled != enabled:
+                src.is_enabled = enabled
+        w.set_state(state)
+        return w
+
+    def __deepcopy__(self, _memo) -> "World":
+        return World._from_config(*self._config())
+
+    def __reduce__(self):
+        return (World._from_config, self._config())
 
 
 class BoundLaserSource:

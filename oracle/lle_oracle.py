@@ -64,6 +64,18 @@ class Action(enum.IntEnum):
     def delta(self):
         return {0: (-1, 0), 1: (1, 0), 2: (0, 1), 3: (0, -1), 4: (0, 0)}[int(self)]
 
+    @staticmethod
+    def variants():
+        return list(Action)
+
+    @staticmethod
+    def from_delta(di: int, dj: int) -> "Action":
+        """src/bindings/world/pyaction.rs:68-87 (the pair is (x, y) there: (0, -1) is NORTH, (-1, 0) is WEST)."""
+        table = {(0, 0): Action.STAY, (-1, 0): Action.WEST, (1, 0): Action.EAST, (0, -1): Action.NORTH, (0, 1): Action.SOUTH}
+        if (di, dj) not in table:
+            raise ValueError(f"Invalid delta: ({di}, {dj}). Valid deltas for actions are (-1, 0), (1, 0), (0, -1), or (0, 1).")
+        return table[(di, dj)]
+
 
 class EventType(enum.IntEnum):
     """src/bindings/world/pyevent.rs:9-17."""
@@ -288,6 +300,12 @@ class LaserSource:
     def enable(self):
         self._set_status(True)
 
+    def __eq__(self, other):  # agent id, direction, laser id and position (pylaser_source.rs:144-152)
+        return (isinstance(other, LaserSource) and self.agent_id == other.agent_id and self.direction == other.direction
+                and self.laser_id == other.laser_id and self.pos == other.pos)
+
+    __hash__ = None
+
     @property
     def agent_id(self) -> int:
         return self._agent_id
@@ -371,6 +389,69 @@ class World:
         lib().lleo_world_available(self._h, mask, order)
         return [[Action(order[a * 5 + k]) for k in range(5) if order[a * 5 + k] >= 0] for a in range(self.n_agents)]
 
+    def set_agents_positions(self, agents_positions) -> list[WorldEvent]:
+        """PyWorld::set_agents_positions (pyworld.rs:252-263): the current state with new positions, through set_state."""
+        state = self.get_state()
+        state.agents_positions = [tuple(int(x) for x in p) for p in agents_positions]
+        return self.set_state(state)
+
+    def set_agent_position(self, agent_id: int, position) -> list[WorldEvent]:
+        """PyWorld::set_agent_position (pyworld.rs:282-299)."""
+        if agent_id < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        if agent_id >= self.n_agents:
+            raise ValueError(f"Agent id {agent_id} is out of bounds")
+        state = self.get_state()
+        state.agents_positions[agent_id] = tuple(int(x) for x in position)
+        return self.set_state(state)
+
+    def gem_at(self, position) -> Gem:
+        """PyWorld::gem_at (pyworld.rs:315-327): only a top-level Gem tile qualifies; a gem wrapped by a laser tile is a
+        `Tile::Laser` there and raises like any other tile."""
+        i, j = (int(x) for x in position)
+        if not (0 <= i < self.height and 0 <= j < self.width):
+            raise IndexError("Position out of bounds")
+        on_beam = {l.pos for l in self.lasers}
+        for gem in self.gems:
+            if gem.pos == (i, j) and (i, j) not in on_beam:
+                return gem
+        raise ValueError(f"Tile at position {(i, j)} is not a gem")
+
+    def save(self, filename: str) -> None:
+        """PyWorld::save (pyworld.rs:183-189)."""
+        try:
+            with open(filename, "w") as f:
+                f.write(self.world_string)
+        except OSError as e:
+            raise ValueError(f"Could not write to file: {filename}: {e}") from e
+
+    def available_joint_actions(self) -> list[list[Action]]:
+        """world.rs:257-263"""
+        import itertools
+
+        return [list(joint) for joint in itertools.product(*self.available_actions())]
+
+    # world.rs:645-652 `impl Clone for World`; pyworld.rs:557-626 __deepcopy__ / __getstate__ / __setstate__
+    def _config(self):
+        return (self.map_str, [(s.agent_id, s.is_enabled) for s in self.laser_sources], self.get_state())
+
+    @staticmethod
+    def _from_config(text, sources, state):
+        w = World(text)
+        for src, (agent_id, enabled) in zip(w.laser_sources, sources):
+            if src.agent_id != agent_id:
+                src.agent_id = agent_id
+            if src.is_enabled != enabled:
+                src.is_enabled = enabled
+        w.set_state(state)
+        return w
+
+    def __deepcopy__(self, _memo) -> "World":
+        return World._from_config(*self._config())
+
+    def __reduce__(self):
+        return (World._from_config, self._config())
+
     def available_mask(self) -> np.ndarray:
         mask = (C.c_uint8 * (5 * self.n_agents))()
         lib().lleo_world_available(self._h, mask, None)
@@ -388,7 +469,7 @@ class World:
         na, ng = len(state.agents_positions), len(state.gems_collected)
         pos = (C.c_long * max(1, 2 * na))(*[int(x) for p in state.agents_positions for x in p])
         gems = (C.c_uint8 * max(1, ng))(*[int(g) for g in state.gems_collected])
-        alive = (C.c_uint8 * max(1, na))(*[int(a) for a in state.agents_alive])
+        alive = (C.c_uint8 * max(1, na, len(state.agents_alive)))(*[int(a) for a in state.agents_alive])
         ev = (C.c_int * (4 * max(1, self.n_agents)))()
         n = C.c_int(0)
         _check(lib().lleo_world_set_state(self._h, pos, na, gems, ng, alive, ev, C.byref(n)))
@@ -436,6 +517,7 @@ class World:
                 return s
         raise ValueError(f"No laser source at {pos}")
 
+    world_string = property(lambda self: self.map_str)
     wall_pos = property(lambda self: self._positions(0))
     void_pos = property(lambda self: self._positions(1))
     def _set_exit_pos(self, exits):  # PyWorld.exit_pos setter (pyworld.rs:202-210) -> World::set_exit_positions (world.rs:195-234)
@@ -652,7 +734,7 @@ class LLE:
         na, ng = len(state.agents_positions), len(state.gems_collected)
         pos = (C.c_long * max(1, 2 * na))(*[int(x) for p in state.agents_positions for x in p])
         gems = (C.c_uint8 * max(1, ng))(*[int(g) for g in state.gems_collected])
-        alive = (C.c_uint8 * max(1, na))(*[int(a) for a in state.agents_alive])
+        alive = (C.c_uint8 * max(1, na, len(state.agents_alive)))(*[int(a) for a in state.agents_alive])
         _check(lib().lleo_env_set_state(self._h, pos, na, gems, ng, alive))
 
 

@@ -1035,3 +1035,157 @@ def test_exit_under_a_laser_moves(api):  # world.rs:208-213 / :222-227: the tile
     events = world.step([api.Action.NORTH, api.Action.STAY])  # agent 0 enters its own beam on the new exit
     assert events == [api.WorldEvent(api.EventType.AGENT_EXIT, 0)]
     assert laser_at(world, (0, 2)).is_off
+
+
+# ---- copies, pickling, joint actions (the rest of the PyWorld surface)
+def test_deepcopy(api):  # [P] python/tests/test_world.py:300
+    from copy import deepcopy
+
+    world = api.World("S0 . X")
+    world2 = deepcopy(world)
+    assert world.agents_positions == world2.agents_positions
+    assert world.agents_positions is not world2.agents_positions
+    assert world.width == world2.width
+
+
+def test_deepcopy_not_initial_state(api):  # [P] python/tests/test_world.py:308
+    from copy import deepcopy
+
+    world = api.World("S0 . X")
+    world.reset()
+    world.step([api.Action.EAST])
+    world2 = deepcopy(world)
+    assert world.agents_positions == world2.agents_positions == [(0, 1)]
+    assert world.width == world2.width
+    world2.step([api.Action.EAST])  # world.rs:645-652: the clone is a world of its own
+    assert world.agents_positions == [(0, 1)] and world2.agents_positions == [(0, 2)]
+    assert world.get_state() != world2.get_state()
+
+
+def test_pickle_world_state(api):  # [P] python/tests/test_serialization.py:8
+    import pickle
+    import random
+
+    rng = random.Random(0)
+    for _ in range(50):
+        s = api.WorldState(gems_collected=[rng.choice([True, False]) for _ in range(rng.randint(0, 10))],
+                           agents_positions=[(rng.randint(0, 50), rng.randint(0, 90)) for _ in range(rng.randint(0, 10))])
+        assert pickle.loads(pickle.dumps(s)) == s
+
+
+def test_pickle_world(api):  # [P] python/tests/test_serialization.py:19 (5 steps per level instead of 20)
+    import pickle
+    import random
+
+    rng = random.Random(1)
+    for lvl in range(1, 7):
+        world = api.World.level(lvl)
+        world.reset()
+        for _ in range(5):
+            world.step([rng.choice(a) for a in world.available_actions()])
+            other = pickle.loads(pickle.dumps(world))
+            assert (other.n_agents, other.n_gems, other.height, other.width) == (world.n_agents, world.n_gems, world.height, world.width)
+            assert other.exit_pos == world.exit_pos and other.start_pos == world.start_pos
+            assert other.wall_pos == world.wall_pos and other.void_pos == world.void_pos
+            assert world.get_state() == other.get_state()
+            assert world.available_actions() == other.available_actions()
+
+
+def test_pickled_world_keeps_same_laser_ids(api):  # [P] python/tests/test_serialization.py:41
+    import pickle
+
+    world = api.World("L0E L1S S0 S1 X X")
+    other = pickle.loads(pickle.dumps(world))
+    for source in world.laser_sources:
+        assert source in other.laser_sources
+        mine, theirs = world.source_at(source.pos), other.source_at(source.pos)
+        assert (mine.laser_id, mine.agent_id, mine.direction) == (theirs.laser_id, theirs.agent_id, theirs.direction)
+
+
+def test_copy_keeps_mutated_sources(api):  # world.rs:98-110: get_config() reads the sources as they are now
+    from copy import deepcopy
+
+    world = api.World("L0E . .\nS0 . X\nS1 . X")
+    world.reset()
+    world.source_at((0, 0)).agent_id = 1
+    world.source_at((0, 0)).disable()
+    other = deepcopy(world)
+    src = other.source_at((0, 0))
+    assert src.agent_id == 1 and not src.is_enabled
+
+
+def test_available_joint_actions(api):  # [D] src/bindings/world/pyworld.rs:483-485 (doc example) ; world.rs:257-263
+    world = api.World(". .  .  . .\n. S0 . S1 .\n. X  .  X .\n")
+    world.reset()
+    joint = world.available_joint_actions()
+    assert len(joint) == len(api.Action.variants()) ** 2
+    assert joint[0] == [a[0] for a in world.available_actions()] and all(len(j) == 2 for j in joint)
+    walled = api.World("@ @ @\n@ S0 X")
+    walled.reset()
+    assert walled.available_joint_actions() == [[api.Action.STAY], [api.Action.EAST]]
+
+
+def test_action_from_delta_pickle_deepcopy(api):  # [P] python/tests/test_actions.py:40-90
+    import copy
+    import pickle
+
+    A = api.Action
+    for a in A.variants():
+        assert copy.deepcopy(a) == a and pickle.loads(pickle.dumps(a)) == a
+    assert A.from_delta(0, 0) == A.STAY and A.from_delta(0, -1) == A.NORTH and A.from_delta(0, 1) == A.SOUTH
+    assert A.from_delta(1, 0) == A.EAST and A.from_delta(-1, 0) == A.WEST
+    with pytest.raises(ValueError):
+        A.from_delta(1, 1)
+
+
+def test_set_agent_position_doc_example(api):  # [D] src/bindings/world/pyworld.rs:274-281
+    world = api.World("S0 . . X")
+    world.reset()
+    assert world.set_agent_position(0, (0, 2)) == []
+    events = world.step([api.Action.EAST])
+    assert events[0].event_type == api.EventType.AGENT_EXIT
+    with pytest.raises(ValueError):
+        world.set_agent_position(1, (0, 0))
+    with pytest.raises(IndexError):
+        world.set_agent_position(0, (0, 9))
+
+
+def test_set_agents_positions(api):  # pyworld.rs:252-263: the current state with new positions, through set_state
+    world = api.World("S0 G . X\nS1 . . X")
+    world.reset()
+    events = world.set_agents_positions([(0, 2), (1, 3)])
+    assert events == [api.WorldEvent(api.EventType.AGENT_EXIT, 1)]
+    assert world.agents_positions == [(0, 2), (1, 3)] and world.get_state().gems_collected == [False]
+    # onto the gem: the state handed to set_state still says "not collected", so its final comparison fails (world.rs:588-594)
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_agents_positions([(0, 1), (1, 3)])
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_agents_positions([(0, 0)])
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_agents_positions([(0, 2), (0, 2)])
+
+
+def test_gem_at_doc_example(api):  # [D] src/bindings/world/pyworld.rs:306-314
+    world = api.World("S0 G X")
+    world.reset()
+    assert not world.gem_at((0, 1)).is_collected
+    world.step([api.Action.EAST])
+    assert world.gem_at((0, 1)).is_collected
+    with pytest.raises(ValueError):
+        world.gem_at((0, 0))
+    with pytest.raises(IndexError):
+        world.gem_at((3, 0))
+    wrapped = api.World("L0E G X\nS0 . .")  # the gem sits under a laser tile: Tile::Laser, not Tile::Gem (pyworld.rs:321-326)
+    wrapped.reset()
+    with pytest.raises(ValueError):
+        wrapped.gem_at((0, 1))
+
+
+def test_save_writes_the_world_string(api, tmp_path):  # pyworld.rs:183-189
+    world = api.World("S0 G X")
+    path = tmp_path / "map.txt"
+    world.save(str(path))
+    again = api.World(path.read_text())
+    assert (again.width, again.height, again.n_gems) == (3, 1, 1)
+    with pytest.raises(ValueError):
+        world.save(str(tmp_path / "missing_dir" / "map.txt"))
