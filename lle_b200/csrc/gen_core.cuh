@@ -68,32 +68,36 @@ struct PyRandomT {
     int idx;  // next state word to regenerate and hand out
 
     // random_seed(int) -> init_by_array(key) (Modules/_randommodule.c).  `base(i)` = word i of the state after
-    // init_genrand(19650218), a constant table.  The two passes of init_by_array are written without their wrap-around
-    // tests: pass 1 walks i = 1..623 and then i = 1 once more, pass 2 walks i = 2..623 and then i = 1; with a key of one or
-    // two 32-bit digits, `key[j] + j` alternates between k_odd (odd i) and k_even (even i).  Pass 1 reads the table
-    // directly, so the state is written once before pass 2 instead of being initialised first.
+    // init_genrand(19650218), a constant table.  init_by_array makes two passes over the state, each a dependent chain:
+    // pass 1 walks i = 1..623 and then i = 1 once more, pass 2 walks i = 2..623 and then i = 1; with a key of one or two
+    // 32-bit digits, `key[j] + j` alternates between k_odd (odd i) and k_even (even i).  Pass 2 cannot start before pass 1
+    // has ended (it continues from pass 1's last value), and it reads every word pass 1 wrote - 2.5 KB per thread that the
+    // resident threads cannot keep in cache.  So pass 1 runs twice instead: once in registers only, to reach its last
+    // value, and once more in lock-step with pass 2, which then takes each pass-1 word from a register.  The state is
+    // written exactly once and never read while seeding; the two chains of the second walk overlap.
     template <class Base>
     LLE_HD void seed(uint64_t s, Base base) {
         const uint32_t hi = (uint32_t)(s >> 32);
         const uint32_t k_odd = (uint32_t)s;             // key[0] + 0
         const uint32_t k_even = hi ? hi + 1u : k_odd;    // key[1] + 1 when abs(seed) has two digits, else key[0] + 0 again
-        uint32_t prev = base(0);
-        for (int i = 1; i < 623; i += 2) {
-            prev = (base(i) ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_odd;
-            mt[i] = prev;
-            prev = (base(i + 1) ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_even;
-            mt[i + 1] = prev;
+        const uint32_t first = (base(1) ^ ((base(0) ^ (base(0) >> 30)) * 1664525u)) + k_odd;  // pass 1 at i = 1
+        uint32_t p1 = first;
+        for (int i = 2; i < 624; i += 2) {
+            p1 = (base(i) ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + k_even;
+            p1 = (base(i + 1) ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + k_odd;
         }
-        prev = (base(623) ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_odd;
-        mt[623] = prev;
-        prev = (mt[1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + k_even;  // wrapped: mt[0] = mt[623], i = 1, step 623
-        mt[1] = prev;
-        for (int i = 2; i < 624; ++i) {
-            prev = (mt[i] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
-            mt[i] = prev;
+        const uint32_t wrapped = (first ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + k_even;  // mt[0] = mt[623], then i = 1 again
+        p1 = first;
+        uint32_t p2 = wrapped;
+        for (int i = 2; i < 624; i += 2) {
+            p1 = (base(i) ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + k_even;
+            p2 = (p1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
+            mt[i] = p2;
+            p1 = (base(i + 1) ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + k_odd;
+            p2 = (p1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)(i + 1);
+            mt[i + 1] = p2;
         }
-        prev = (mt[1] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - 1u;    // wrapped again
-        mt[1] = prev;
+        mt[1] = (wrapped ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - 1u;  // pass 2 wrapped: mt[0] = mt[623], i = 1
         mt[0] = 0x80000000u;
         idx = 0;
     }

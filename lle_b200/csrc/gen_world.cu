@@ -119,7 +119,7 @@ LLE_API int lle_gen_create(const lle_gen_options* opts, int32_t device, int64_t 
         lle_gen_destroy(g);
         return fail(LLE_CUDA_ERROR, std::string("lle_gen_create: ") + cudaGetErrorString(e));
     }
-    // resident CTAs per SM by grid size (measured on B200: 5x5 290 M attempts/s at 8, 10x10 61 M at 6, 32x32 3.1 M at 4);
+    // resident CTAs per SM by grid size (measured on B200: 5x5 405 M attempts/s at 8, 10x10 65 M at 6, 32x32 3.1 M at 4);
     // LLE_GEN_CTAS overrides it (development knob for A/B timing)
     int ctas = area <= 36 ? 8 : area <= 144 ? 6 : 4;
     if (const char* knob = std::getenv("LLE_GEN_CTAS"))
