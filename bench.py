@@ -207,6 +207,22 @@ def run_ours(args) -> None:
     ms_max = float(t.item())
     value = world_size * n_envs * K / (ms_max / 1e3)
 
+    # ---------------- the same K steps as lle_vec_rollout launches (128 steps per launch, bit-identical results): reported
+    # beside the headline as "rollout", not as the headline (the contract's step = one launch)
+    RL = 128
+    n_roll = max(1, K // RL)
+    vec.rollout(RL)
+    barrier()
+    vec.timing_begin()
+    for _ in range(n_roll):
+        vec.rollout(RL)
+    ms_roll, roll_launches = vec.timing_end()
+    barrier()
+    tr = torch.tensor([ms_roll], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+    rollout_value = world_size * n_envs * n_roll * RL / (float(tr.item()) / 1e3)
+
     # ---------------- end-to-end arm: host actions in (pinned, H2D), reward + done out (D2H), sync every step
     Ke = min(K, args.e2e_steps)
     vec.reset()
@@ -298,6 +314,9 @@ def run_ours(args) -> None:
                             "region; the host reads each step's result. sync_value = lle_vec_step_host (same copies, stream sync "
                             "after every step, nothing overlapped). Observations stay in HBM (zero-copy DLPack hand-off)"},
             "gpu_launches": launches,
+            "rollout": {"value": rollout_value, "unit": UNIT, "steps_per_launch": RL, "launches": int(roll_launches),
+                        "ms_per_step": float(tr.item()) / (n_roll * RL),
+                        "note": "lle_vec_rollout(128): the same steps, 128 per launch, ordered by the per-ticket epoch flags; device-timed"},
             "stats_allreduce": {"done_last_step": int(stats[0]), "reward_last_step": int(stats[1]), "envs_total": int(stats[2])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src, "kernel": "lle_world_kernel<MODE_STEP, FAST>",

@@ -217,6 +217,27 @@ def test_core_matches_the_oracle_on_random_configurations(core):
     assert n_layouts > 600
 
 
+def test_core_matches_the_oracle_at_the_limits(core):
+    """Largest grids, most agents / gems / walls, degenerate 1 x N grids, rooms: chains of 3 attempts against the oracle.
+    (The host instantiation of this core also runs these and 400 random configurations under ASan / UBSan cleanly.)"""
+    cases = [dict(width=32, height=32, n_agents=32, n_lasers=32, n_gems=100, n_walls=400, walls_style="shapes"),
+             dict(width=32, height=32, n_agents=8, n_lasers=8, n_gems=900, n_walls=0),
+             dict(width=32, height=1, n_agents=3, n_lasers=2, n_walls=2), dict(width=1, height=32, n_agents=2, n_lasers=1, n_walls=3),
+             dict(width=32, height=32, n_agents=4, starts="edge", exits="opposite", n_lasers=4, laser_placement="cross-agent", n_walls=300),
+             dict(width=32, height=32, n_agents=4, starts="clustered", exits="opposite", n_lasers=4, laser_placement="cross-cluster",
+                  cluster_shape=(2, 2), n_walls=100, n_gems=50),
+             dict(width=31, height=29, n_agents=5, n_lasers=3, n_rooms_rows=3, n_rooms_cols=4, door_size=2, n_gems=10)]
+    for kw in cases:
+        cfg = og.GenConfig(**kw)
+        seeds = list(range(10))
+        cells, status, labels, tries = core.run(cfg, seeds, max_attempts=3)
+        for i, s in enumerate(seeds):
+            lay, t = og.generate(cfg, 3, s)
+            assert bool(status[i]) == (lay is not None) and tries[i] == t, (kw, s)
+            if lay:
+                assert cells[i].tobytes() == lay.cell_codes() and labels[i] == og.analyse(lay), (kw, s)
+
+
 def test_label_heuristic_known_cases():
     """Hand-made layouts: an open room is independent; a foreign beam across the only corridor needs a blocker; a walled-in
     agent is not walkable."""
