@@ -110,3 +110,54 @@ def test_map_errors():
             lle_b200.Map(text)
     with pytest.raises(lle_b200.InvalidLevelError):
         lle_b200.Map(level=7)
+
+
+def test_argument_validation_precedes_any_device_call():
+    """Empty, oversized and inconsistent inputs are refused with LLE_INVALID_ARGUMENT (202) before a device is touched, so this
+    runs without a GPU: zero worlds, zero maps, null pointers, a map index out of range, maps of different shapes, a reward
+    dimension the reference does not have; generator batches beyond capacity, zero attempts, unknown label bits."""
+    N = _native()
+    L = N.lib()
+    m1, m6, small = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert L.lle_map_level(1, C.byref(m1)) == 0 and L.lle_map_level(6, C.byref(m6)) == 0
+    text = b"S0 . X"
+    assert L.lle_map_parse(text, len(text), C.byref(small)) == 0
+    opts = N.VecOptions()
+    L.lle_vec_default_options(C.byref(opts))
+    out = C.c_void_p()
+    one = (C.c_void_p * 1)(m6)
+
+    def create(maps, n_maps, map_of_env, n_envs, o=opts):
+        return L.lle_vec_create(maps, n_maps, map_of_env, n_envs, C.byref(o) if o is not None else None, C.byref(out))
+
+    assert create(one, 1, None, 0) == 202          # empty batch
+    assert create(one, 1, None, -5) == 202
+    assert create(one, 0, None, 16) == 202         # no maps
+    assert create(None, 1, None, 16) == 202
+    assert create(one, 1, None, 16, None) == 202   # no options
+    bad = (C.c_int32 * 4)(0, 0, 1, 0)
+    assert create(one, 1, bad, 4) == 202 and b"map_of_env" in L.lle_last_error()
+    two = (C.c_void_p * 2)(m6, m1)
+    assert create(two, 2, (C.c_int32 * 2)(0, 1), 2) == 202 and b"share" in L.lle_last_error()
+    o2 = N.VecOptions()
+    L.lle_vec_default_options(C.byref(o2))
+    o2.reward_dim = 3
+    assert create(one, 1, None, 16, o2) == 202
+    assert not out.value
+    for m in (m1, m6, small):
+        L.lle_map_free(m)
+    # generator
+    g = N.GenOptions()
+    L.lle_gen_default_options(C.byref(g))
+    h = C.c_void_p()
+    assert L.lle_gen_create(C.byref(g), 0, 0, C.byref(h)) == 202      # capacity < 1
+    assert L.lle_gen_create(None, 0, 16, C.byref(h)) == 202
+    g.width = 33
+    assert L.lle_gen_create(C.byref(g), 0, 16, C.byref(h)) == 21      # LLE_LIMIT_EXCEEDED
+    g.width, g.n_agents = 5, 33
+    assert L.lle_gen_create(C.byref(g), 0, 16, C.byref(h)) == 21
+    assert L.lle_gen_run(None, None, 0, 1, 1, 0, None) == 202
+    assert L.lle_gen_attempt_seeds(1, -1, None) == 202 and L.lle_gen_attempt_seeds(1, 0, None) == 0
+    assert L.lle_gen_cells_to_text(None, 1, 1, None, 0, None) == 202
+    cells = (C.c_uint8 * 2)(0, 9)
+    assert L.lle_gen_cells_to_text(cells, 1, 2, None, 0, None) == 202 and b"unknown cell code" in L.lle_last_error()

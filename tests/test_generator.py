@@ -401,3 +401,20 @@ def test_builder_chain():
     assert world is not None and (world.height, world.width, world.n_agents) == (5, 5, 2)
     with pytest.raises(NotImplementedError):
         generate(5, 5, 2).cooperative()
+
+
+@pytest.mark.gpu
+def test_run_argument_checks_and_empty_batch():
+    from lle_b200 import _native
+    from lle_b200.generator import WorldGenerator
+
+    g = WorldGenerator(width=5, height=5, n_agents=2, batch=8)
+    with pytest.raises(ValueError, match="max_attempts must be >= 1"):  # generator.py:279-280
+        g.run(first_seed=0, n=8, max_attempts=0)
+    with pytest.raises(ValueError):
+        g.run(first_seed=0, n=8, require=8)
+    assert _native.lib().lle_gen_run(g._h, None, 0, 9, 1, 0, None) == 202  # beyond the capacity
+    cells, status, labels, tries = g.run(first_seed=0, n=0)
+    assert status.numel() == 0 and cells.shape == (0, 5, 5)
+    cells, status, labels, tries = g.run(first_seed=0, n=8)
+    assert int(status.sum()) > 0
