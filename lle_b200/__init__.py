@@ -3,6 +3,7 @@
 Public surface (mirrors the reference's `lle` package for the accelerated path):
     World, WorldState, Action, EventType, WorldEvent, LLE        single-world API (N = 1 on the device)
     VecWorld, VecLLE, Map, level, from_str, from_file            batched API
+    generate, WorldGenerator, GeneratorBuilder                   lle.generate(...): layouts generated on the device
 The package needs its CUDA extension (lle_b200/_native/liblle_b200.so, sm_100a) and a CUDA device;
 there is no CPU fallback.
 """
@@ -15,8 +16,10 @@ _load_native()  # fail loudly at import time if the extension is not built
 from .vec_world import Map, VecWorld  # noqa: E402
 from .world import LLE, Step, World, decode_events  # noqa: E402
 from .env import Builder, VecLLE, VecWorldGroup, from_file, from_str, level  # noqa: E402
+from .generator import GeneratorBuilder, WorldGenerator, generate  # noqa: E402
 
 __all__ = ["Action", "Agent", "Direction", "EventType", "Gem", "InvalidActionError", "InvalidLevelError",
            "InvalidWorldStateError", "Laser", "LaserSource", "ParsingError", "WorldEvent", "WorldState", "Map", "VecWorld",
-           "World", "LLE", "Step", "VecLLE", "VecWorldGroup", "Builder", "level", "from_str", "from_file", "decode_events", "LIB_PATH"]
+           "World", "LLE", "Step", "VecLLE", "VecWorldGroup", "Builder", "level", "from_str", "from_file", "decode_events", "LIB_PATH",
+           "generate", "WorldGenerator", "GeneratorBuilder"]
 __version__ = "0.1.0"

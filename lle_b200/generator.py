@@ -248,9 +248,14 @@ class GeneratorBuilder:
         text = self._make_generator(device, batch=1).generate(max_attempts, seed)
         return None if text is None else World(text)
 
-    def take(self, n: int, *, seed: int | None = None, max_attempts: int | None = None, device: int = 0, distinct: bool = False) -> Iterator[str]:
-        """Up to n map texts (builder.py:346-371 with parallel workers); hand them to `VecWorld` / `World`."""
-        return self._make_generator(device).generate_n(n, seed=seed, max_attempts=max_attempts, distinct=distinct)
+    def take(self, n: int, *, seed: int | None = None, max_attempts: int | None = None, device: int = 0, distinct: bool = False,
+             texts: bool = False) -> Iterator:
+        """Up to n worlds (builder.py:346-371 with parallel workers).  Yields `World` objects like the reference; with
+        `texts=True` the v1 map texts instead, which is what a batch wants (`VecWorld(list_of_texts, ...)`)."""
+        from .world import World
+
+        for text in self._make_generator(device).generate_n(n, seed=seed, max_attempts=max_attempts, distinct=distinct):
+            yield text if texts else World(text, device)
 
 
 def generate(width: int = 10, height: int = 10, n_agents: int = 3) -> GeneratorBuilder:

@@ -392,11 +392,13 @@ def test_builder_chain():
     """lle.generate(...).lasers(...).walls(...).take(n) (builder.py) on the device, and its World terminal."""
     from lle_b200.generator import generate
 
-    texts = list(generate(6, 6, 3).lanes().lasers(2, placement="cross-agent").walls(3, style="shapes").gems(2).take(5, seed=8))
+    texts = list(generate(6, 6, 3).lanes().lasers(2, placement="cross-agent").walls(3, style="shapes").gems(2).take(5, seed=8, texts=True))
     cfg = og.GenConfig(width=6, height=6, n_agents=3, starts="edge", exits="opposite", n_lasers=2, laser_placement="cross-agent", n_walls=3,
                        walls_style="shapes", n_gems=2)
     want = [lay.to_v1() for lay in (og.try_generate(cfg, s) for s in og.attempt_seeds(8, 500)) if lay][:5]
     assert texts == want
+    worlds = list(generate(6, 6, 3).lanes().lasers(2, placement="cross-agent").walls(3, style="shapes").gems(2).take(2, seed=8))
+    assert [w.world_string for w in worlds] == want[:2] and worlds[0].n_agents == 3 and worlds[0].n_gems == 2
     world = generate(5, 5, 2).lasers(1).rooms(2).build(seed=4, max_attempts=50)
     assert world is not None and (world.height, world.width, world.n_agents) == (5, 5, 2)
     with pytest.raises(NotImplementedError):
