@@ -109,6 +109,11 @@ class Builder:
         self._n = int(n)
         return self
 
+    def name(self, name: str):
+        """builder.py:117-119"""
+        self._name = name
+        return self
+
     def device(self, device):
         self._kw["device"] = device
         return self
@@ -180,7 +185,9 @@ class Builder:
         return self
 
     def build(self) -> VecLLE:
-        return VecLLE(self._maps, self._n, **self._kw)
+        env = VecLLE(self._maps, self._n, **self._kw)
+        env.name = getattr(self, "_name", "LLE")
+        return env
 
 
 def level(n: int) -> Builder:

@@ -387,17 +387,48 @@ class LLE(_Single):
 
     def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
                  walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, obs_type: str = "layered",
-                 padding_size: int = 0, randomize_lasers: bool = False, device=0):
+                 padding_size: int = 0, randomize_lasers: bool = False, device=0, name: str | None = None):
         self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
                           reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
                           obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers)
         if self._vec.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         self.reward_dim = self._vec.reward_dim
+        # the attributes the reference serialises (env.py:60-66, python/tests/test_serialization.py:49-58)
+        self.obs_type, self.state_type = obs_type, "state"
+        self.walkable_lasers, self.randomize_lasers = bool(walkable_lasers), bool(randomize_lasers)
+        self._name = name if name is not None else (f"LLE-lvl{level}" if level is not None else "LLE")  # env.py:238-242
 
     @staticmethod
     def level(level: int, **kw) -> "LLE":
         return LLE(level=level, **kw)
+
+    @staticmethod
+    def from_str(world_string: str, **kw) -> "LLE":
+        """env.py:220-224 (the reference returns its Builder; the options are keyword arguments here)."""
+        return LLE(world_string, **kw)
+
+    @staticmethod
+    def from_file(path: str, **kw) -> "LLE":
+        """env.py:226-232"""
+        with open(path) as f:
+            return LLE(f.read(), name=f"LLE-{os.path.basename(path)}", **kw)
+
+    name = property(lambda self: self._name)     # env.py:114-118
+    world = property(lambda self: self)          # env.py:128-130: the world getters live on this object
+
+    @property
+    def agent_state_size(self) -> int:
+        """StateGenerator.unit_size (env.py:132-138, observations.py:150-153): i, j and the alive flag."""
+        return 3
+
+    def compute_done(self) -> bool:
+        """env.py:253-254"""
+        return self.done
+
+    def get_observation(self):
+        """env.py:218 (marlenv's Observation): (data, available_actions, extras)."""
+        return self.observe(), self.available_actions(), self.extras()
 
     @property
     def done(self) -> bool:

@@ -670,3 +670,26 @@ def test_full_size_properties():
             assert torch.all(vec.avail[:, :, 4] == 1)                                                 # STAY always available
             n_done += int(vec.done.sum())
     assert n_done > 0
+
+
+@pytest.mark.gpu
+def test_lle_facade_accessors(tmp_path):
+    """The remaining members of `LLE` (python/lle/env/env.py:114-138, :218-254) on the N = 1 facade."""
+    import lle_b200
+
+    env = lle_b200.LLE.level(6)
+    assert env.name == "LLE-lvl6" and (env.width, env.height) == (13, 12) and env.agent_state_size == 3
+    assert env.world.n_agents == 4 and env.world.exit_pos == lle_b200.World.level(6).exit_pos
+    assert (env.obs_type, env.state_type, env.walkable_lasers, env.randomize_lasers) == ("layered", "state", True, False)
+    env.reset()
+    obs, avail, extras = env.get_observation()
+    assert obs.shape == (4, 12, 12, 13) and avail.shape == (4, 5) and extras.shape == (4, 0)
+    assert env.compute_done() is False
+    path = tmp_path / "tiny"
+    path.write_text("S0 X")
+    env = lle_b200.LLE.from_file(str(path), multi_objective=True)
+    assert env.name == "LLE-tiny" and env.reward_dim == 4
+    env.reset()
+    step = env.step([lle_b200.Action.EAST])
+    assert step.done and env.compute_done() and lle_b200.LLE.from_str("S0 X").name == "LLE"
+    assert lle_b200.level(1).name("mine").n_envs(4).build().name == "mine"
