@@ -129,8 +129,9 @@ class WorldGenerator:
         """generator.py:268-284: attempts drawn from one stream until a layout is accepted."""
         if seed is None:
             seed = self._rng.randrange(sys.maxsize)
-        # the reference searches without bound when max_attempts is None; one device thread stops after a million attempts
-        cells, status, _, _ = self.run([seed], max_attempts=1_000_000 if max_attempts is None else max_attempts)
+        # the reference searches without bound when max_attempts is None; a chain is one device thread (about 0.4 ms per
+        # attempt at full occupancy, less alone), so an unbounded search stops after 20,000 attempts and returns None
+        cells, status, _, _ = self.run([seed], max_attempts=20_000 if max_attempts is None else max_attempts)
         return cells_to_text(cells[0], self.height, self.width) if int(status[0]) else None
 
     def generate_n(self, n: int, seed: int | None = None, max_attempts: int | None = None, distinct: bool = False) -> Iterator[str]:
