@@ -100,6 +100,48 @@ int main(int argc, char** argv) {
     free(actions); free(reward); free(done); free(ring_reward); free(ring_done);
     CHECK(lle_vec_destroy(vec));
     lle_map_free(map);
+
+    /* phase 5: layouts generated on the device (lle.generate(5, 5, 2).lasers(2)), read back, compiled and stepped */
+    lle_gen_options gopts;
+    lle_gen_default_options(&gopts);
+    gopts.n_lasers = 2;
+    lle_gen* gen = NULL;
+    enum { ATTEMPTS = 4096, KEEP = 64 };
+    CHECK(lle_gen_create(&gopts, 0, ATTEMPTS, &gen));
+    CHECK(lle_gen_run(gen, NULL, 0, ATTEMPTS, 1, LLE_GEN_WALKABLE, NULL)); /* attempt i = _try_generate(seed = i) */
+    static uint8_t cells[ATTEMPTS * 25], status[ATTEMPTS];
+    CHECK(lle_gen_fetch(gen, 0, ATTEMPTS, cells, status, NULL, NULL, NULL));
+    lle_map* gmaps[KEEP];
+    int kept = 0, accepted = 0;
+    for (int i = 0; i < ATTEMPTS; ++i) {
+        accepted += status[i];
+        if (status[i] && kept < KEEP) {
+            char text[256];
+            size_t len = 0;
+            CHECK(lle_gen_cells_to_text(cells + i * 25, 5, 5, text, sizeof(text), &len));
+            CHECK(lle_map_parse(text, len, &gmaps[kept]));
+            ++kept;
+        }
+    }
+    if (kept < KEEP) return 5;
+    int32_t* map_of_env = (int32_t*)malloc(sizeof(int32_t) * KEEP * 16);
+    for (int e = 0; e < KEEP * 16; ++e) map_of_env[e] = e / 16;
+    lle_vec* gvec = NULL;
+    CHECK(lle_vec_create((const lle_map* const*)gmaps, KEEP, map_of_env, KEEP * 16, &opts, &gvec));
+    float* greward = (float*)malloc(sizeof(float) * KEEP * 16);
+    uint8_t* gdone = (uint8_t*)malloc(KEEP * 16);
+    long gepisodes = 0;
+    CHECK(lle_vec_reset(gvec, NULL, NULL));
+    for (int t = 0; t < 50; ++t) {
+        CHECK(lle_vec_step_host(gvec, NULL, greward, gdone, NULL));
+        for (int e = 0; e < KEEP * 16; ++e) gepisodes += gdone[e];
+    }
+    printf("generated maps  : %d of %d attempts accepted, %d maps x 16 envs stepped 50 times, %ld episodes finished\n", accepted, ATTEMPTS, kept,
+           gepisodes);
+    free(map_of_env); free(greward); free(gdone);
+    CHECK(lle_vec_destroy(gvec));
+    for (int k = 0; k < kept; ++k) lle_map_free(gmaps[k]);
+    CHECK(lle_gen_destroy(gen));
     printf("ok\n");
     return 0;
 }

@@ -368,6 +368,12 @@ typedef struct {
 } lle_gen_buffers;
 LLE_API int lle_gen_get_buffers(lle_gen* gen, lle_gen_buffers* out);
 
+/* Copies chains [first, first + n) of the last run into host buffers (any of them may be NULL) after waiting for the work
+ * queued on cuda_stream: cells u8[n, height*width], status u8[n], labels u8[n], tries i32[n].  For hosts without a CUDA
+ * runtime of their own (the same role as lle_vec_step_host). */
+LLE_API int lle_gen_fetch(lle_gen* gen, int64_t first, int64_t n, uint8_t* cells_host, uint8_t* status_host, uint8_t* labels_host,
+                          int32_t* tries_host, void* cuda_stream);
+
 /* The v1 map text of a cell grid (host; world_builder.py:83-88: tokens joined by ' ', rows by '\n'). Returns the length
  * needed (without the terminator) in *len; writes at most cap bytes including the terminator. */
 LLE_API int lle_gen_cells_to_text(const uint8_t* cells_host, int32_t height, int32_t width, char* out, size_t cap, size_t* len);

@@ -176,6 +176,21 @@ LLE_API int lle_gen_get_buffers(lle_gen* g, lle_gen_buffers* out) {
     return LLE_OK;
 }
 
+LLE_API int lle_gen_fetch(lle_gen* g, int64_t first, int64_t n, uint8_t* cells, uint8_t* status, uint8_t* labels, int32_t* tries, void* cuda_stream) {
+    if (!g || first < 0 || n < 0 || first + n > g->n) return fail(LLE_INVALID_ARGUMENT, "lle_gen_fetch: the range must lie within the last run");
+    GEN_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t hw = (size_t)g->cfg.height * g->cfg.width;
+    if (n > 0) {
+        if (cells) GEN_CUDA(cudaMemcpyAsync(cells, g->d_cells + (size_t)first * hw, (size_t)n * hw, cudaMemcpyDeviceToHost, st));
+        if (status) GEN_CUDA(cudaMemcpyAsync(status, g->d_status + first, (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (labels) GEN_CUDA(cudaMemcpyAsync(labels, g->d_labels + first, (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (tries) GEN_CUDA(cudaMemcpyAsync(tries, g->d_tries + first, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    GEN_CUDA(cudaStreamSynchronize(st));
+    return LLE_OK;
+}
+
 LLE_API int lle_gen_cells_to_text(const uint8_t* cells, int32_t height, int32_t width, char* out, size_t cap, size_t* len) {
     if (!cells || height < 1 || width < 1) return fail(LLE_INVALID_ARGUMENT, "lle_gen_cells_to_text: bad arguments");
     std::string s;

@@ -27,3 +27,4 @@ def test_c_client_runs():
     assert res.returncode == 0, res.stdout + res.stderr
     lines = res.stdout.strip().splitlines()
     assert lines[-1] == "ok" and "episodes finished" in lines[1] and "0 unexpected transitions" in lines[2]
+    assert lines[-2].startswith("generated maps") and "64 maps x 16 envs" in lines[-2]

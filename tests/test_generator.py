@@ -451,3 +451,10 @@ def test_run_argument_checks_and_empty_batch():
     assert status.numel() == 0 and cells.shape == (0, 5, 5)
     cells, status, labels, tries = g.run(first_seed=0, n=8)
     assert int(status.sum()) > 0
+    # lle_gen_fetch: the host-buffer read-back for hosts without a CUDA runtime returns what the device views show
+    hc, hs, hl, ht = np.zeros((3, 25), np.uint8), np.zeros(3, np.uint8), np.zeros(3, np.uint8), np.zeros(3, np.int32)
+    rc = _native.lib().lle_gen_fetch(g._h, 2, 3, hc.ctypes.data, hs.ctypes.data, hl.ctypes.data, ht.ctypes.data, None)
+    assert rc == 0
+    assert np.array_equal(hc, cells[2:5].reshape(3, 25).cpu().numpy()) and np.array_equal(hs, status[2:5].cpu().numpy())
+    assert np.array_equal(hl, labels[2:5].cpu().numpy()) and np.array_equal(ht, tries[2:5].cpu().numpy())
+    assert _native.lib().lle_gen_fetch(g._h, 6, 3, None, None, None, None, None) == 202  # beyond the last run
