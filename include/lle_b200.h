@@ -374,6 +374,10 @@ LLE_API int lle_gen_get_buffers(lle_gen* gen, lle_gen_buffers* out);
 LLE_API int lle_gen_fetch(lle_gen* gen, int64_t first, int64_t n, uint8_t* cells_host, uint8_t* status_host, uint8_t* labels_host,
                           int32_t* tries_host, void* cuda_stream);
 
+/* `CandidateLayout.is_geometry_valid` (python/lle/generator/candidates.py:27-41) of a cell grid (host): every source has an
+ * in-bounds first beam cell and a beam of >= 2 cells before a wall or another source, and no exit lies on a beam. */
+LLE_API int lle_gen_geometry_valid(const uint8_t* cells_host, int32_t height, int32_t width, int32_t* valid);
+
 /* The v1 map text of a cell grid (host; world_builder.py:83-88: tokens joined by ' ', rows by '\n'). Returns the length
  * needed (without the terminator) in *len; writes at most cap bytes including the terminator. */
 LLE_API int lle_gen_cells_to_text(const uint8_t* cells_host, int32_t height, int32_t width, char* out, size_t cap, size_t* len);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "lle_vec_export_raw", "lle_vec_set_seed", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
     "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline",
     "lle_gen_default_options", "lle_gen_create", "lle_gen_destroy", "lle_gen_attempt_seeds", "lle_gen_run", "lle_gen_get_buffers",
-    "lle_gen_fetch", "lle_gen_cells_to_text",
+    "lle_gen_fetch", "lle_gen_geometry_valid", "lle_gen_cells_to_text",
 ]
 
 
@@ -120,6 +120,7 @@ def lib():
     L.lle_gen_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p]
     L.lle_gen_get_buffers.argtypes = [C.c_void_p, C.POINTER(GenBuffers)]
     L.lle_gen_fetch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lle_gen_geometry_valid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     L.lle_gen_cells_to_text.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L

@@ -191,6 +191,30 @@ LLE_API int lle_gen_fetch(lle_gen* g, int64_t first, int64_t n, uint8_t* cells, 
     return LLE_OK;
 }
 
+LLE_API int lle_gen_geometry_valid(const uint8_t* cells, int32_t H, int32_t W, int32_t* valid) {
+    if (!cells || !valid || H < 1 || W < 1) return fail(LLE_INVALID_ARGUMENT, "lle_gen_geometry_valid: bad arguments");
+    std::vector<char> lit((size_t)H * W, 0);
+    *valid = 1;
+    for (int r = 0; r < H && *valid; ++r)
+        for (int c = 0; c < W && *valid; ++c) {
+            const uint8_t v = cells[r * W + c];
+            if (v < LLE_CELL_SOURCE) continue;
+            const int d = (v - LLE_CELL_SOURCE) & 3;  // 0 N, 1 S, 2 E, 3 W
+            const int dr = d == 0 ? -1 : d == 1 ? 1 : 0, dc = d == 2 ? 1 : d == 3 ? -1 : 0;
+            int len = 0;
+            for (int i = r + dr, j = c + dc; i >= 0 && i < H && j >= 0 && j < W; i += dr, j += dc) {
+                const uint8_t t = cells[i * W + j];
+                if (t == LLE_CELL_WALL || t >= LLE_CELL_SOURCE) break;
+                lit[(size_t)i * W + j] = 1;
+                ++len;
+            }
+            if (len < 2) *valid = 0;
+        }
+    for (int k = 0; k < H * W && *valid; ++k)
+        if (cells[k] == LLE_CELL_EXIT && lit[k]) *valid = 0;
+    return LLE_OK;
+}
+
 LLE_API int lle_gen_cells_to_text(const uint8_t* cells, int32_t height, int32_t width, char* out, size_t cap, size_t* len) {
     if (!cells || height < 1 || width < 1) return fail(LLE_INVALID_ARGUMENT, "lle_gen_cells_to_text: bad arguments");
     std::string s;

@@ -49,6 +49,14 @@ def cells_to_text(cells: np.ndarray | torch.Tensor, height: int, width: int) -> 
     return buf.value.decode()
 
 
+def is_geometry_valid(cells: np.ndarray | torch.Tensor, height: int, width: int) -> bool:
+    """CandidateLayout.is_geometry_valid (candidates.py:27-41) of a cell grid, via lle_gen_geometry_valid."""
+    arr = np.ascontiguousarray(cells.cpu().numpy() if isinstance(cells, torch.Tensor) else cells, dtype=np.uint8).reshape(-1)
+    ok = C.c_int32(0)
+    check(lib().lle_gen_geometry_valid(arr.ctypes.data_as(C.c_void_p), height, width, C.byref(ok)))
+    return bool(ok.value)
+
+
 def attempt_seeds(seed: int, n: int) -> np.ndarray:
     """generator.py:296-301: the seeds `_generate_n_multi` hands to its workers."""
     out = np.empty(n, dtype=np.uint64)
