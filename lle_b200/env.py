@@ -33,6 +33,7 @@ class VecLLE:
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         w = self.world
         self.n_envs, self.n_agents, self.n_actions = w.n_envs, w.n_agents, 5
+        self.width, self.height = w.width, w.height  # env.py:120-126
         self.observation_shape = tuple(w.obs.shape[1:]) if self._flat(w) else w.obs_shape  # one agent's observation
         self.state_shape = (w.state_dim,)
         self.reward_dim = w.reward_dim

@@ -258,6 +258,21 @@ class Direction(enum.IntEnum):
     SOUTH = 2
     WEST = 3
 
+    @classmethod
+    def _missing_(cls, value):
+        """Direction("N") / ("E") / ("S") / ("W") (src/bindings/tiles/pydirection.rs; python/tests/test_direction.py:12-23)."""
+        if isinstance(value, str) and value in ("N", "E", "S", "W"):
+            return (cls.NORTH, cls.EAST, cls.SOUTH, cls.WEST)["NESW".index(value)]
+        raise ValueError(f"Invalid direction: {value!r}")
+
+    @property
+    def delta(self):
+        """(di, dj) of one step (src/core/tiles/direction.rs:20-27)."""
+        return ((-1, 0), (0, 1), (1, 0), (0, -1))[int(self)]
+
+    def opposite(self) -> "Direction":
+        return Direction((int(self) + 2) % 4)
+
 
 @dataclass(frozen=True)
 class Laser:

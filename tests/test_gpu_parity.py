@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the oracle
 on the same seeded inputs, bit for bit — outputs (obs, state, avail, reward, done, events, actions, err) and
 the raw engine state (positions, alive/arrived, tile slots, beam masks, gems)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -693,3 +695,9 @@ def test_lle_facade_accessors(tmp_path):
     step = env.step([lle_b200.Action.EAST])
     assert step.done and env.compute_done() and lle_b200.LLE.from_str("S0 X").name == "LLE"
     assert lle_b200.level(1).name("mine").n_envs(4).build().name == "mine"
+    # python/tests/test_other.py:4-16
+    env = lle_b200.from_str("X S0 G .").build()
+    assert (env.width, env.height) == (4, 1)
+    for lvl in range(1, 7):
+        lle_b200.level(lvl).build()
+    lle_b200.from_file(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels", "lvl1")).build()

@@ -1189,3 +1189,32 @@ def test_save_writes_the_world_string(api, tmp_path):  # pyworld.rs:183-189
     assert (again.width, again.height, again.n_gems) == (3, 1, 1)
     with pytest.raises(ValueError):
         world.save(str(tmp_path / "missing_dir" / "map.txt"))
+
+
+# ---- small value types (python/tests/test_direction.py, test_actions.py, test_death_strategy.py, test_other.py)
+def test_direction(api):  # [P] python/tests/test_direction.py:4-36
+    D = api.Direction
+    dirs = [D.NORTH, D.SOUTH, D.EAST, D.WEST]
+    for d in dirs:
+        assert d == d and all(d != d2 for d2 in dirs if d is not d2)
+    assert D("N") == D.NORTH and D("W") == D.WEST
+    with pytest.raises(ValueError):
+        D("z")
+    assert (D.NORTH.delta, D.SOUTH.delta, D.EAST.delta, D.WEST.delta) == ((-1, 0), (1, 0), (0, 1), (0, -1))
+    assert D.NORTH.opposite() == D.SOUTH and D.SOUTH.opposite() == D.NORTH
+    assert D.EAST.opposite() == D.WEST and D.WEST.opposite() == D.EAST
+
+
+def test_action_value_type(api):  # [P] python/tests/test_actions.py:4-38
+    A = api.Action
+    assert A.NORTH == A.NORTH and A(0) == A(0)
+    values = [A.NORTH, A.SOUTH, A.EAST, A.WEST, A.WEST]
+    assert [values.count(a) for a in (A.NORTH, A.SOUTH, A.EAST, A.WEST)] == [1, 1, 1, 2]
+    assert {a.name for a in A.variants()} == {"NORTH", "SOUTH", "EAST", "WEST", "STAY"}
+    assert len({hash(a) for a in A.variants()}) == 5 and len(set(A.variants())) == 5
+
+
+def test_end_strategy(api):  # [P] python/tests/test_death_strategy.py:4-18
+    env = api.LLE("S0  G  X\nS1 L1N X")
+    env.reset()
+    assert env.step([api.Action.EAST.value, api.Action.STAY.value]).done
