@@ -262,6 +262,12 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
 LLE_API int lle_vec_set_source(lle_vec* vec, int32_t map_index, int32_t source_index, int32_t agent_id, int32_t enabled, void* cuda_stream);
 LLE_API int lle_vec_get_sources(lle_vec* vec, int32_t map_index, int32_t* out_pairs, int32_t cap, int32_t* n);
 
+/* Gem::collect (src/core/tiles/gem.rs:17-19) as reached through PyGem.collect (src/bindings/tiles/pygem.rs:51-65): gem
+ * `gem_index` (World::gems order) of map `map_index` becomes collected in every env of that map; nothing else changes (no
+ * event, no reward).  LLE_INVALID_ARGUMENT when the gem sits under a laser tile (a Tile::Laser there, "not a gem").  Call
+ * lle_vec_refresh to re-export observation / state. */
+LLE_API int lle_vec_collect_gem(lle_vec* vec, int32_t map_index, int32_t gem_index, void* cuda_stream);
+
 /* World::set_exit_positions (src/core/world.rs:195-234; the `World.exit_pos` setter, pyworld.rs:202-210) for every env that
  * uses map `map_index`: the current exits become floor tiles and the (i, j) pairs of `exits_ij` become the exits.  Agents keep
  * their position, alive and arrived flags.  Fewer exits than agents -> LLE_PARSE_NOT_ENOUGH_EXITS.  A new exit must be a

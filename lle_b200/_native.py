@@ -18,7 +18,7 @@ SYMBOLS = [
     "lle_last_error", "lle_version", "lle_map_parse", "lle_map_level", "lle_map_free", "lle_map_get_info",
     "lle_map_positions", "lle_map_start_candidates", "lle_map_sources", "lle_map_lasers", "lle_map_text", "lle_vec_default_options", "lle_vec_create",
     "lle_vec_destroy", "lle_vec_get_buffers", "lle_vec_reset", "lle_vec_refresh", "lle_vec_step", "lle_vec_rollout", "lle_vec_step_host", "lle_vec_pipeline_submit",
-    "lle_vec_pipeline_wait", "lle_vec_set_source", "lle_vec_get_sources", "lle_vec_set_exits", "lle_vec_set_state",
+    "lle_vec_pipeline_wait", "lle_vec_set_source", "lle_vec_get_sources", "lle_vec_set_exits", "lle_vec_collect_gem", "lle_vec_set_state",
     "lle_vec_export_raw", "lle_vec_set_seed", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
     "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline",
     "lle_gen_default_options", "lle_gen_create", "lle_gen_destroy", "lle_gen_attempt_seeds", "lle_gen_run", "lle_gen_get_buffers",
@@ -103,6 +103,7 @@ def lib():
     L.lle_vec_set_source.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.lle_vec_get_sources.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
     L.lle_vec_set_exits.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p]
+    L.lle_vec_collect_gem.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.lle_vec_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lle_vec_export_raw.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     L.lle_vec_set_seed.argtypes = [C.c_void_p, C.c_uint64]

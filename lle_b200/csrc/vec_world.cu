@@ -50,6 +50,7 @@ struct lle_vec {
     std::vector<std::string> map_texts;
     std::vector<std::vector<SourceState>> src_state;
     std::vector<int> map_patches, map_obs_invalid;
+    std::vector<uint64_t> map_gem_toplevel;  // per map: gems that are top-level Gem tiles (not wrapped by a laser tile)
     std::vector<std::vector<Cell>> map_exits;  // World::set_exit_positions overrides (empty: the exits of the text)
     std::vector<char> map_exits_set;
     std::vector<uint8_t*> retired_blobs;
@@ -409,6 +410,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->NBmax = std::max(v->NBmax, m.NB);
         if (m.header().obs_invalid) v->obs_invalid = 1;
         v->map_texts.push_back(m.text);
+        v->map_gem_toplevel.push_back(m.header().gem_toplevel);
         std::vector<SourceState> st;
         for (const auto& src : m.sources) st.push_back(SourceState{src.colour, src.enabled});
         v->src_state.push_back(st);
@@ -723,6 +725,21 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
         LLE_CUDA(cudaGetLastError());
         v->launches++;
     }
+    return LLE_OK;
+}
+
+int lle_vec_collect_gem(lle_vec* v, int32_t map_index, int32_t gem_index, void* stream) {
+    if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
+    if (gem_index < 0 || gem_index >= v->G) return fail(LLE_INDEX_ERROR, "gem index out of range");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (!((v->map_gem_toplevel[(size_t)map_index] >> gem_index) & 1ull))  // pygem.rs:54-62: a gem under a laser tile is a Tile::Laser
+        return fail(LLE_INVALID_ARGUMENT, "the tile is not a gem (the gem is wrapped by a laser tile)");
+    LLE_CUDA(cudaSetDevice(v->device));
+    const int threads = 256;
+    const int blocks = (int)((v->N_pad + threads - 1) / threads);
+    lle_collect_gem_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(v->d_records, v->L, v->N_pad, v->d_map_of_env, map_index, gem_index);
+    LLE_CUDA(cudaGetLastError());
+    v->launches++;
     return LLE_OK;
 }
 

@@ -1431,6 +1431,15 @@ __global__ void lle_set_beam_kernel(uint32_t* records, LleStateLayout L, int64_t
     if (L.on_words == 2) w[1] = (uint32_t)(mask >> 32);
 }
 
+// Gem::collect (gem.rs:17-19) through PyGem.collect (pygem.rs:51-65): gem `gem` of one map becomes collected in every world
+// that uses the map; nothing else changes (no event, no reward, slots untouched).
+__global__ void lle_collect_gem_kernel(uint32_t* records, LleStateLayout L, int64_t N_pad, const int32_t* map_of_env, int map_index, int gem) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= N_pad) return;
+    if (map_of_env && map_of_env[env] != map_index) return;
+    records[env * L.stride + L.w_gems + (gem >> 5)] |= 1u << (gem & 31);
+}
+
 // Unpacks the records for white-box comparisons (tests) and `get_state`-style host queries.
 __global__ void lle_export_raw_kernel(const uint32_t* records, LleStateLayout L, int64_t N, int A, int NBmax, int16_t* pos,
                                       uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on, uint64_t* collected,

@@ -3,7 +3,7 @@ src/bindings/world/{pyaction,pyevent,pyworld_state}.rs, src/bindings/pyexception
 from __future__ import annotations
 
 import enum
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -134,10 +134,26 @@ class Agent:
         return not self.is_dead
 
 
-@dataclass(frozen=True)
+@dataclass
 class Gem:
+    """PyGem (src/bindings/tiles/pygem.rs): a snapshot (`pos`, `is_collected`) plus, when it comes from a world, a handle on it."""
+
     pos: tuple
     is_collected: bool
+    _world: object = field(default=None, repr=False, compare=False)
+    _index: int = field(default=-1, repr=False, compare=False)
+
+    def collect(self):
+        """PyGem.collect (pygem.rs:51-65): marks the gem collected in the world; ValueError when the tile is not a top-level gem."""
+        if self._world is None:
+            raise ValueError("this Gem is not bound to a world")
+        self._world._collect_gem(self._index, self.pos)
+        self.is_collected = True
+
+    @property
+    def agent(self):
+        """PyGem.agent (pygem.rs:67-76): the agent standing on the tile, if any (None under a laser tile)."""
+        return None if self._world is None else self._world._tile_agent(self.pos, gem=True)
 
 
 @dataclass(frozen=True)
@@ -150,10 +166,20 @@ class Laser:
     direction: Direction
     is_on: bool
     is_enabled: bool
+    _world: object = field(default=None, repr=False, compare=False)
 
     @property
     def is_off(self) -> bool:
         return not self.is_on
+
+    @property
+    def is_disabled(self) -> bool:  # pylaser.rs:67-70
+        return not self.is_enabled
+
+    @property
+    def agent(self):
+        """PyLaser.agent (pylaser.rs:73-81): the agent standing on the tile, if any."""
+        return None if self._world is None else self._world._tile_agent(self.pos)
 
 
 @dataclass(frozen=True)

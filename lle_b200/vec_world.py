@@ -261,6 +261,10 @@ class VecWorld:
         check(lib().lle_vec_get_buffers(self._h, C.byref(b)))
         self.obs_invalid = bool(b.obs_invalid)
 
+    def collect_gem(self, gem_index: int, map_index: int = 0):
+        """PyGem.collect for gem `gem_index` in every env of a map (lle_vec_collect_gem); call refresh() afterwards."""
+        check(lib().lle_vec_collect_gem(self._h, map_index, gem_index, _stream_ptr(self.device)))
+
     def set_exits(self, exits: Sequence[tuple[int, int]], map_index: int = 0):
         """World::set_exit_positions (world.rs:195-234) in every env that uses map `map_index` (lle_vec_set_exits)."""
         flat = (C.c_int32 * max(1, 2 * len(exits)))(*[int(x) for p in exits for x in p])

@@ -76,7 +76,25 @@ class _Single:
     @property
     def gems(self) -> list[Gem]:
         coll = int(self._raw()["collected"])
-        return [Gem(p, bool((coll >> g) & 1)) for g, p in enumerate(self._map.gems)]
+        return [Gem(p, bool((coll >> g) & 1), self, g) for g, p in enumerate(self._map.gems)]
+
+    def _collect_gem(self, index: int, pos):
+        try:
+            self._vec.collect_gem(index)
+        except ValueError as e:  # pygem.rs:57-61
+            raise ValueError(f"Tile at {tuple(pos)} is not a gem") from e
+        self._vec.refresh()
+
+    def _tile_agent(self, pos, gem: bool = False):
+        """`Tile::agent()` (tile.rs) of the tile at `pos`: the agent whose slot is set there.  PyGem.agent answers None for a gem
+        under a laser tile (pygem.rs:71-75: the tile is a Tile::Laser)."""
+        raw = self._raw()
+        if gem and tuple(pos) in {l[0] for l in self._laser_tiles}:
+            return None
+        for a in range(self.n_agents):
+            if bool(raw["slot"][a]) and (int(raw["pos"][a][0]), int(raw["pos"][a][1])) == tuple(pos):
+                return a
+        return None
 
     @property
     def gems_collected(self) -> int:
@@ -88,7 +106,7 @@ class _Single:
         """World::lasers (world.rs:159-172) with `is_on` read from the device beam masks."""
         on = self._raw()["beam_on"].view(np.uint64)
         states = self._source_states()  # colours and switches may have changed since the map was parsed
-        return [Laser(pos, lid, states[beam][0], direction, bool((int(on[beam]) >> off) & 1), states[beam][1])
+        return [Laser(pos, lid, states[beam][0], direction, bool((int(on[beam]) >> off) & 1), states[beam][1], self)
                 for pos, lid, colour, direction, beam, off in self._laser_tiles]
 
     @property

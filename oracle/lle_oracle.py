@@ -15,7 +15,7 @@ import ctypes as C
 import enum
 import os
 import subprocess
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Sequence
 
 import numpy as np
@@ -246,10 +246,25 @@ class Agent:
         return not self.is_dead
 
 
-@dataclass(frozen=True)
+@dataclass
 class Gem:
+    """PyGem (src/bindings/tiles/pygem.rs)."""
     pos: tuple
     is_collected: bool
+    _world: object = field(default=None, repr=False, compare=False)
+
+    def collect(self):  # pygem.rs:51-65
+        rc = lib().lleo_world_gem_collect(self._world._h, C.c_long(self.pos[0]), C.c_long(self.pos[1]))
+        if rc:
+            raise ValueError(f"Tile at {self.pos} is not a gem")
+        self.is_collected = True
+
+    @property
+    def agent(self):  # pygem.rs:67-76
+        if self.pos in {l.pos for l in self._world.lasers}:
+            return None
+        a = lib().lleo_world_tile_agent(self._world._h, C.c_long(self.pos[0]), C.c_long(self.pos[1]))
+        return None if a < 0 else a
 
 
 class Direction(enum.IntEnum):
@@ -282,10 +297,20 @@ class Laser:
     direction: Direction
     is_on: bool
     is_enabled: bool
+    _world: object = field(default=None, repr=False, compare=False)
 
     @property
     def is_off(self):
         return not self.is_on
+
+    @property
+    def is_disabled(self):
+        return not self.is_enabled
+
+    @property
+    def agent(self):  # pylaser.rs:73-81
+        a = lib().lleo_world_tile_agent(self._world._h, C.c_long(self.pos[0]), C.c_long(self.pos[1]))
+        return None if a < 0 else a
 
 
 class LaserSource:
@@ -506,7 +531,7 @@ class World:
     def gems(self):
         flags = (C.c_uint8 * max(1, self.n_gems))()
         lib().lleo_world_gem_flags(self._h, flags)
-        return [Gem(p, bool(flags[g])) for g, p in enumerate(self._positions(3))]
+        return [Gem(p, bool(flags[g]), self) for g, p in enumerate(self._positions(3))]
 
     @property
     def gems_collected(self) -> int:
@@ -518,7 +543,7 @@ class World:
         buf = (C.c_int * (7 * cap))()
         n = lib().lleo_world_lasers(self._h, buf, cap)
         return [Laser((buf[7 * k], buf[7 * k + 1]), buf[7 * k + 2], buf[7 * k + 3], Direction(buf[7 * k + 4]),
-                      bool(buf[7 * k + 5]), bool(buf[7 * k + 6])) for k in range(n)]
+                      bool(buf[7 * k + 5]), bool(buf[7 * k + 6]), self) for k in range(n)]
 
     @property
     def laser_sources(self):

@@ -385,6 +385,22 @@ void lleo_world_gem_flags(void* p, uint8_t* out) {
     auto gems = ((WorldHandle*)p)->w.gems();
     for (size_t g = 0; g < gems.size(); ++g) out[g] = gems[g]->collected;
 }
+// PyGem::collect (src/bindings/tiles/pygem.rs:51-65): only a top-level Gem tile; returns 0, or 1 when the tile is not a gem
+int lleo_world_gem_collect(void* p, long i, long j) {
+    World& w = ((WorldHandle*)p)->w;
+    if (i < 0 || j < 0 || (size_t)i >= w.height || (size_t)j >= w.width) return 2;
+    Tile& t = w.grid[(size_t)i][(size_t)j];
+    if (t.kind != Tile::Gem) return 1;
+    t.collected = true;  // Gem::collect (gem.rs:17-19)
+    return 0;
+}
+// PyGem::agent / PyLaser::agent (pygem.rs:67-76, pylaser.rs:73-81): the agent standing on the tile, -1 if none
+int lleo_world_tile_agent(void* p, long i, long j) {
+    World& w = ((WorldHandle*)p)->w;
+    if (i < 0 || j < 0 || (size_t)i >= w.height || (size_t)j >= w.width) return -1;
+    auto a = w.grid[(size_t)i][(size_t)j].agent();
+    return a.has_value() ? (int)*a : -1;
+}
 int lleo_world_n_gems_collected(void* p) { return (int)((WorldHandle*)p)->w.n_gems_collected(); }
 void lleo_world_source_set_enabled(void* p, int idx, int enabled) {
     auto b = ((WorldHandle*)p)->w.source_beam((size_t)idx);

@@ -1218,3 +1218,31 @@ def test_end_strategy(api):  # [P] python/tests/test_death_strategy.py:4-18
     env = api.LLE("S0  G  X\nS1 L1N X")
     env.reset()
     assert env.step([api.Action.EAST.value, api.Action.STAY.value]).done
+
+
+# ---- tile handles: PyGem.collect / .agent, PyLaser.agent (src/bindings/tiles/pygem.rs:51-76, pylaser.rs:61-81)
+def test_gem_collect_and_tile_agents(api):
+    world = api.World("S0 G . X\nS1 . . X")
+    world.reset()
+    gem = world.gems[0]
+    assert not gem.is_collected and gem.agent is None
+    gem.collect()                                     # no event, no step: the flag alone changes (gem.rs:17-19)
+    assert gem.is_collected and world.gems[0].is_collected and world.gems_collected == 1
+    assert world.get_state().gems_collected == [True]
+    assert world.step([api.Action.EAST, api.Action.STAY]) == []   # entering a collected gem collects nothing
+    assert world.gems[0].agent == 0
+    world.reset()
+    assert not world.gems[0].is_collected
+
+
+def test_laser_tile_agent_and_wrapped_gem(api):
+    world = api.World("L1E G . X\nS0 S1 . X")   # the gem sits under agent 1's beam: a Tile::Laser wraps it
+    world.reset()
+    lasers = {l.pos: l for l in world.lasers}
+    assert lasers[(0, 1)].agent is None and not lasers[(0, 1)].is_disabled
+    with pytest.raises(ValueError, match="is not a gem"):
+        world.gems[0].collect()                       # pygem.rs:54-62
+    world.step([api.Action.STAY, api.Action.NORTH])   # agent 1 walks into its own beam, onto the gem
+    lasers = {l.pos: l for l in world.lasers}
+    assert lasers[(0, 1)].agent == 1 and lasers[(0, 2)].agent is None and lasers[(0, 2)].is_off
+    assert world.gems[0].is_collected and world.gems[0].agent is None   # PyGem.agent answers for top-level gems only
