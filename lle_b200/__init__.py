@@ -17,9 +17,11 @@ from .vec_world import Map, VecWorld  # noqa: E402
 from .world import LLE, Step, World, decode_events  # noqa: E402
 from .env import Builder, VecLLE, VecWorldGroup, from_file, from_str, level  # noqa: E402
 from .generator import GeneratorBuilder, WorldGenerator, generate  # noqa: E402
+from .observations import ObservationType  # noqa: E402
+from . import exceptions, generator, observations, tiles, world  # noqa: E402,F401  (the reference's submodule paths)
 
 __all__ = ["Action", "Agent", "Direction", "EventType", "Gem", "InvalidActionError", "InvalidLevelError",
            "InvalidWorldStateError", "Laser", "LaserSource", "ParsingError", "WorldEvent", "WorldState", "Map", "VecWorld",
            "World", "LLE", "Step", "VecLLE", "VecWorldGroup", "Builder", "level", "from_str", "from_file", "decode_events", "LIB_PATH",
-           "generate", "WorldGenerator", "GeneratorBuilder"]
+           "generate", "WorldGenerator", "GeneratorBuilder", "ObservationType", "exceptions", "tiles", "observations", "generator", "world"]
 __version__ = "0.1.0"

@@ -222,6 +222,7 @@ _OBS_TYPES = {
 def obs_spec(obs_type: str, padding_size: int = 0) -> tuple[int, int, bool]:
     """ObservationType.from_str + get_observation_generator (observations.py:62-97).  "rgb-image" needs the renderer,
     which is not on the accelerated path."""
+    obs_type = getattr(obs_type, "value", obs_type)  # an ObservationType member or its string
     if obs_type == "rgb-image":
         raise NotImplementedError("observation type 'rgb-image' is not on the accelerated path")
     if obs_type not in _OBS_TYPES:

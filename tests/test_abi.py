@@ -161,3 +161,22 @@ def test_argument_validation_precedes_any_device_call():
     assert L.lle_gen_cells_to_text(None, 1, 1, None, 0, None) == 202
     cells = (C.c_uint8 * 2)(0, 9)
     assert L.lle_gen_cells_to_text(cells, 1, 2, None, 0, None) == 202 and b"unknown cell code" in L.lle_last_error()
+
+
+def test_reference_import_paths():
+    """`import lle_b200 as lle` keeps the reference's submodule paths (python/lle/__init__.py:211-245) for what is on the path."""
+    import lle_b200 as lle
+    from lle_b200.exceptions import InvalidActionError, InvalidWorldStateError, ParsingError  # noqa: F401
+    from lle_b200.generator import GeneratorBuilder, WorldGenerator, generate  # noqa: F401
+    from lle_b200.observations import ObservationType
+    from lle_b200.tiles import Direction, Gem, Laser, LaserSource  # noqa: F401
+    from lle_b200.types import obs_spec
+    from lle_b200.world import World  # noqa: F401
+
+    assert issubclass(InvalidActionError, ValueError)  # pyexceptions.rs
+    assert ObservationType.from_str("partial7x7") is ObservationType.PARTIAL_7x7
+    assert obs_spec(ObservationType.AGENT0_PERSPECTIVE_LAYERED) == obs_spec("perspective")
+    assert {t.value for t in ObservationType} >= {"layered", "flattened", "state", "normalized-state", "layered-padded"}
+    for name in ("World", "WorldState", "Action", "EventType", "WorldEvent", "LLE", "ObservationType", "from_file", "from_str", "level",
+                 "generate", "GeneratorBuilder", "Agent", "exceptions", "tiles", "observations", "generator", "world"):
+        assert hasattr(lle, name), name
