@@ -9,8 +9,15 @@ there is no CPU fallback.
 """
 from .types import (Action, Agent, Direction, EventType, Gem, InvalidActionError, InvalidLevelError, InvalidWorldStateError,
                     Laser, LaserSource, ParsingError, WorldEvent, WorldState)
+import sys as _sys
+
 from ._native import LIB_PATH, lib as _load_native
 
+if "lle_b200.build" in getattr(_sys, "orig_argv", []) and "-m" in getattr(_sys, "orig_argv", []):
+    # `python -m lle_b200.build` imports this package before it runs the builder: build first, then load
+    from . import build as _build
+
+    _build.build(force="--force" in _sys.argv, verbose=True)
 _load_native()  # fail loudly at import time if the extension is not built
 
 from .vec_world import Map, VecWorld  # noqa: E402

@@ -23,6 +23,17 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built library (it is git-ignored): build it in-tree before anything imports the package.
+    # nvcc cross-compiles without a GPU; where there is no nvcc either, the imports below fail loudly, as they should.
+    import importlib.util
+    import shutil
+
+    lib = os.path.join(ROOT, "lle_b200", "_native", "liblle_b200.so")
+    if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        spec = importlib.util.spec_from_file_location("_lle_b200_build", os.path.join(ROOT, "lle_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
 
 
 def _oracle_api():
