@@ -148,10 +148,13 @@ class WorldGenerator:
             seed = self._rng.randrange(sys.maxsize)
         budget = sys.maxsize if max_attempts is None else max_attempts
         found, done, seen = 0, 0, set()
-        # the attempt seeds form one MT19937 stream: draw them in growing prefixes
+        # generator.py:296-301: the host draws one seed per attempt from its own generator, exactly as the reference does
+        # (`self._rng.seed(seed)`, then `randrange(sys.maxsize)` per attempt); lle_gen_attempt_seeds is the same list for
+        # hosts without a CPython
+        self._rng.seed(seed)
         while found < n and done < budget:
             take = int(min(self.batch, budget - done))
-            seeds = attempt_seeds(seed, done + take)[done:]
+            seeds = np.fromiter((self._rng.randrange(sys.maxsize) for _ in range(take)), dtype=np.uint64, count=take)
             cells, status, labels, _ = self.run(seeds)
             ok = torch.nonzero(status).flatten().cpu().numpy()
             grids = cells.cpu().numpy()
