@@ -1,0 +1,49 @@
+"""Soak of the dataflow-ordered stepping: the same batch advanced by (a) single-step launches overlapped with programmatic
+dependent launch, (b) rollout launches of 128 steps, (c) rollout launches of 7 steps interleaved with single steps, for many
+steps; the three must end in bit-identical engine state and outputs.  python scratch/soak.py [steps] [envs]"""
+import os, sys, time, zlib
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lle_b200
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
+envs = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+
+
+def digest(v):
+    v.synchronize()
+    out = []
+    raw = v.export_raw()
+    for name in ("obs", "state", "avail", "reward", "done", "events", "actions"):
+        out.append(zlib.crc32(getattr(v, name).cpu().numpy().tobytes()))
+    for k in sorted(raw):
+        out.append(zlib.crc32(raw[k].cpu().numpy().tobytes()))
+    return out
+
+
+def run(mode):
+    v = lle_b200.VecWorld(lle_b200.Map(level=6), envs, seed=11)
+    t0 = time.time()
+    done = 0
+    while done < steps:
+        if mode == "single":
+            v.step(None); done += 1
+        elif mode == "rollout128":
+            k = min(128, steps - done); v.rollout(k); done += k
+        else:
+            k = min(7, steps - done); v.rollout(k); done += k
+            if done < steps:
+                v.step(None); done += 1
+    d = digest(v)
+    return d, time.time() - t0
+
+
+ref = None
+for mode in ("single", "rollout128", "mixed"):
+    d, secs = run(mode)
+    print(mode, f"{steps} steps x {envs} envs in {secs:.1f} s", d[:4])
+    if ref is None:
+        ref = d
+    assert d == ref, f"{mode} differs from single-step execution"
+print("soak ok: identical state and outputs in all three modes")
