@@ -521,20 +521,24 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         while (v->group > std::max(8, 32 / v->Wd) && (v->N_pad / v->group < 2048 || (int64_t)v->group * stride * 4 > (6 << 20))) v->group >>= 1;
         v->n_buf = 2;
     }
-    if (spec.kind == LLE_OBS_PARTIAL && v->tile_floats <= 3072) v->n_buf = 2;  // zero-fill one tile while the other drains
-    v->n_buf = std::max(1, std::min(2, env_int("LLE_B200_NBUF", v->n_buf)));          // tuning knobs (development)
     {
         int g = env_int("LLE_B200_GROUP", v->group);
         if (g >= v->E && g >= 32 / v->Wd && g <= 32 && (g & (g - 1)) == 0) v->group = g;
     }
-    {
-        size_t bytes = (size_t)v->n_buf * v->tile_floats * 4;             // tiles
-        bytes += (size_t)v->group * v->L.stride * 4;                      // records of the group
-        bytes += (size_t)v->n_buf * v->E * v->L.stride * 4;               // records applied to the tiles
-        bytes += (size_t)(2 * v->n_buf * v->E + v->n_buf + v->group) * 4; // tags + map ids + fresh flags
-        v->warp_smem = (int)((bytes + 127) / 128 * 128);
-        v->smem = (size_t)v->warp_smem * kWarps;
-    }
+    auto warp_smem_for = [&](int n_buf) {
+        size_t bytes = (size_t)n_buf * v->tile_floats * 4;             // tiles
+        bytes += (size_t)v->group * v->L.stride * 4;                   // records of the group
+        bytes += (size_t)n_buf * v->E * v->L.stride * 4;               // records applied to the tiles
+        bytes += (size_t)(2 * n_buf * v->E + n_buf + v->group) * 4;    // tags + map ids + fresh flags
+        return (int)((bytes + 127) / 128 * 128);
+    };
+    // Partial observations: a second tile lets a warp zero-fill and draw one tile while the other drains, but only pays
+    // while four CTAs still fit an SM (228 KB, 1 KB reserved per CTA).  Measured on level 6 x 65,536, two buffers / one:
+    // partial3x3 72 / 79 us per step (4 / 5 CTAs per SM), partial5x5 84 / 85, partial7x7 135 / 100 (3 / 5 CTAs).
+    if (spec.kind == LLE_OBS_PARTIAL && 4 * ((size_t)warp_smem_for(2) * kWarps + 1024) <= 233472) v->n_buf = 2;
+    v->n_buf = std::max(1, std::min(2, env_int("LLE_B200_NBUF", v->n_buf)));          // tuning knobs (development)
+    v->warp_smem = warp_smem_for(v->n_buf);
+    v->smem = (size_t)v->warp_smem * kWarps;
     v->pdl = env_int("LLE_B200_PDL", 1) != 0;
     v->force_narrow = env_int("LLE_B200_FORCE_NARROW", 0) != 0;
     int max_patch = 0;
