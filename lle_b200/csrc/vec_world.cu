@@ -494,7 +494,11 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     const bool small_obs = v->obs_stride * 4 < 2048;  // tiny observations: the logic dominates, pack more worlds per pass
     v->Wd = std::max(v->Wd, std::min(32, env_int("LLE_B200_MIN_WD", small_obs ? 1 : 2)));
     const int64_t stride = v->obs_stride;
-    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", small_obs ? 2048 : 1024);  // 4-8 KB per bulk store
+    // 4-8 KB per bulk store; partial observations: up to 9.6 KB, one tile buffer and 16 worlds per ticket, which keeps five
+    // CTAs per SM (sweep of buffers x tile size x ticket size on level 6 x 65,536, us per step before -> after:
+    // partial3x3 72.5 -> 57.9, partial5x5 84.4 -> 79.2, partial7x7 134.7 -> 94.5)
+    const bool partial_obs = spec.kind == LLE_OBS_PARTIAL;
+    const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", partial_obs ? 2400 : small_obs ? 2048 : 1024);
     // the partial renderer builds whole worlds (all agents' windows) in one tile: allow up to 48 KB per warp
     const int64_t kTileMaxFloats = spec.kind == LLE_OBS_PARTIAL ? 12288 : 6144;
     if (spec.kind == LLE_OBS_PARTIAL && stride > kTileMaxFloats)
@@ -504,7 +508,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
         v->chunk_floats = (int)stride;
         v->tile_floats = (int)(v->E * stride);
-        v->group = small_obs ? 32 : std::max(std::max(v->E, 8), 32 / v->Wd);
+        v->group = partial_obs ? std::max(std::max(v->E, 16), 32 / v->Wd) : small_obs ? 32 : std::max(std::max(v->E, 8), 32 / v->Wd);
         v->n_buf = 1;
     } else {
         v->E = 1;
@@ -532,10 +536,6 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         bytes += (size_t)(2 * n_buf * v->E + n_buf + v->group) * 4;    // tags + map ids + fresh flags
         return (int)((bytes + 127) / 128 * 128);
     };
-    // Partial observations: a second tile lets a warp zero-fill and draw one tile while the other drains, but only pays
-    // while four CTAs still fit an SM (228 KB, 1 KB reserved per CTA).  Measured on level 6 x 65,536, two buffers / one:
-    // partial3x3 72 / 79 us per step (4 / 5 CTAs per SM), partial5x5 84 / 85, partial7x7 135 / 100 (3 / 5 CTAs).
-    if (spec.kind == LLE_OBS_PARTIAL && 4 * ((size_t)warp_smem_for(2) * kWarps + 1024) <= 233472) v->n_buf = 2;
     v->n_buf = std::max(1, std::min(2, env_int("LLE_B200_NBUF", v->n_buf)));          // tuning knobs (development)
     v->warp_smem = warp_smem_for(v->n_buf);
     v->smem = (size_t)v->warp_smem * kWarps;
