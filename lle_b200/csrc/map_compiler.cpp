@@ -147,14 +147,17 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     for (const auto* lst : {&cm.gems, &cm.walls, &cm.exits, &cm.voids})
         for (const auto& c : *lst)
             if (c.i < 0 || c.j < 0 || c.i >= H || c.j >= W) throw MapError(LLE_PARSE_POSITION_OUT_OF_BOUNDS, "PositionOutOfBounds");
-    for (const auto& s : cm.sources)  // the reference indexes its grid with the position and panics
-        if (s.pos.i < 0 || s.pos.j < 0 || s.pos.i >= H || s.pos.j >= W) throw MapError(LLE_PARSE_POSITION_OUT_OF_BOUNDS, "PositionOutOfBounds");
     // ---- pre_validate (world_config.rs:124-148)
     const int A = (int)starts.size();
     if (A == 0) throw MapError(LLE_PARSE_NO_AGENTS, "NoAgents");
     if ((int)cm.exits.size() < A)
         throw MapError(LLE_PARSE_NOT_ENOUGH_EXITS, "NotEnoughExitTiles { n_starts: " + std::to_string(A) +
                                                        ", n_exits: " + std::to_string(cm.exits.size()) + " }");
+
+    // a [[lasers]] position is not bounds-checked by the reference's parser: it indexes its grid with it after pre_validate and
+    // panics (world_config.rs:247); here the document is refused at the same point
+    for (const auto& s : cm.sources)
+        if (s.pos.i < 0 || s.pos.j < 0 || s.pos.i >= H || s.pos.j >= W) throw MapError(LLE_PARSE_POSITION_OUT_OF_BOUNDS, "PositionOutOfBounds");
 
     if (new_exits) {  // World::set_exit_positions (world.rs:195-234)
         if ((int)new_exits->size() < A)
@@ -176,7 +179,11 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     for (auto& c : cm.exits) tiles[c.i * W + c.j] = LLE_T_EXIT;
     for (auto& c : cm.voids) tiles[c.i * W + c.j] = LLE_T_VOID;
     for (auto& c : cm.walls) tiles[c.i * W + c.j] = LLE_T_WALL;
-
+    // two [[lasers]] entries on one cell: the reference writes the second source tile over the first (world_config.rs:247) and
+    // lists the surviving source twice, with the first beam's laser tiles orphaned
+    for (size_t a = 0; a < cm.sources.size(); ++a)
+        for (size_t b = a + 1; b < cm.sources.size(); ++b)
+            if (cm.sources[a].pos == cm.sources[b].pos) throw MapError(LLE_PARSE_UNSUPPORTED, "Unsupported: two laser sources on one cell");
     // ---- beams and start pruning (world_config.rs:203-250), sources in list order.  A beam walks while the tile is
     // walkable: it stops at walls and at the sources placed before it (the source tile is written after its beam, :247).
     std::vector<std::vector<std::pair<int, int>>> cell_beams((size_t)H * W);  // (beam index, offset), inner first
@@ -194,7 +201,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
             if (std::find(cells.begin(), cells.end(), cm.sources[later].pos) != cells.end())
                 // only possible with TOML [[lasers]] outside the wall list: the reference lets the earlier beam run through the
                 // cell and then overwrites its laser tile with the source, leaving `lasers_positions` inconsistent
-                throw MapError(LLE_PARSE_UNSUPPORTED, "a laser source sits on the beam of an earlier source");
+                throw MapError(LLE_PARSE_UNSUPPORTED, "Unsupported: a laser source sits on the beam of an earlier source");
         s.len = (int)cells.size();
         bool shielded = false;  // `is_blocked`: from the owner's single start on, the beam is cut at reset
         for (int k = 0; k < s.len; ++k) {
@@ -208,10 +215,21 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         placed[s.pos.i * W + s.pos.j] = 1;
     }
     for (const auto& s : cm.sources) tiles[s.pos.i * W + s.pos.j] = LLE_T_WALL;  // Tile::LaserSource is not walkable (tile.rs:63-73)
+    // A gem position overwritten by an exit, a void, a wall or a laser source (only possible in TOML documents): the reference keeps the
+    // position in `gems_positions`, so World::gems / get_state reach `unreachable!()` (world.rs:129-139) - the world is unusable
+    for (auto& c : cm.gems)
+        if ((tiles[c.i * W + c.j] & 7u) != LLE_T_GEM)
+            throw MapError(LLE_PARSE_UNSUPPORTED, "Unsupported: a gem position is also an exit, void, wall or laser source cell (World::gems panics there in the reference)");
     if (new_exits)
         for (const auto& c : *new_exits)
             if (cell_beams[c.i * W + c.j].size() > 1)  // the reference's set_tile would drop the inner beam's tile there
-                throw MapError(LLE_PARSE_UNSUPPORTED, "an exit cannot be placed where two beams cross");
+                throw MapError(LLE_PARSE_UNSUPPORTED, "Unsupported: an exit cannot be placed where two beams cross");
+    // A start candidate on a laser source (only possible with TOML [[lasers]]): World::reset panics in the reference as soon as
+    // that candidate is drawn ("The agent should be able to pre-enter", world.rs:424-427) - refused here
+    for (int a = 0; a < A; ++a)
+        for (const auto& c : starts[a])
+            for (const auto& src : cm.sources)
+                if (c == src.pos) throw MapError(LLE_PARSE_UNSUPPORTED, "Unsupported: a start position coincides with a laser source");
     // ---- post_validate (world_config.rs:150-170)
     for (int a = 0; a < A; ++a)
         if (starts[a].empty())
@@ -222,6 +240,10 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         cm.starts.push_back(starts[a][0]);
     }
     cm.start_candidates = starts;
+    if (!random_starts)  // every agent has one start: two agents sharing it make sample_different panic (utils/mod.rs:80-84)
+        for (int a = 0; a < A; ++a)
+            for (int b = a + 1; b < A; ++b)
+                if (starts[a][0] == starts[b][0]) throw MapError(LLE_PARSE_NOT_ENOUGH_STARTS, "Could not assign positions to agents");
     // sample_different (src/utils/mod.rs:39-86) visits the agents by increasing number of candidates (stable sort)
     std::vector<int> order(A);
     for (int a = 0; a < A; ++a) order[a] = a;
@@ -248,7 +270,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     // duplicated gem positions make World::gems() report one tile twice; the device format indexes gems by cell
     for (size_t g = 0; g < cm.gems.size(); ++g)
         for (size_t g2 = g + 1; g2 < cm.gems.size(); ++g2)
-            if (cm.gems[g] == cm.gems[g2]) throw MapError(LLE_PARSE_UNSUPPORTED, "a gem position is listed twice");
+            if (cm.gems[g] == cm.gems[g2]) throw MapError(LLE_PARSE_UNSUPPORTED, "Unsupported: a gem position is listed twice");
 
     // ---- device-format limits
     const int G = (int)cm.gems.size(), NB = (int)cm.sources.size();

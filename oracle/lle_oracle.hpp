@@ -757,6 +757,10 @@ struct WorldConfig {
         std::vector<std::vector<bool>> is_laser(height, std::vector<bool>(width, false));
         long w = (long)width, h = (long)height;
         for (const auto& [src_pos, cfg] : lasers) {
+            // a [[lasers]] position is a plain Position in the reference (toml_laser_config.rs:9-15), not bounds-checked:
+            // `grid[pos.i][pos.j] = ...` (world_config.rs:247) panics with an index error
+            if (src_pos.i >= height || src_pos.j >= width)
+                throw RuntimeWorldError(RuntimeErrorKind::Panic, "index out of bounds: a laser source outside the grid");
             std::vector<Position> beam_positions;
             auto delta = direction_delta(cfg.direction);
             long i = (long)src_pos.i + delta.first, j = (long)src_pos.j + delta.second;

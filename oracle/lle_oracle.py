@@ -530,7 +530,8 @@ class World:
     @property
     def gems(self):
         flags = (C.c_uint8 * max(1, self.n_gems))()
-        lib().lleo_world_gem_flags(self._h, flags)
+        if lib().lleo_world_gem_flags(self._h, flags):
+            raise RuntimeError("unreachable: a gem position holds no gem tile (World::gems panics there, world.rs:129-139)")
         return [Gem(p, bool(flags[g]), self) for g, p in enumerate(self._positions(3))]
 
     @property

@@ -381,9 +381,15 @@ int lleo_world_positions(void* p, int kind, int* out, int max) {
     }
     return (int)v->size();
 }
-void lleo_world_gem_flags(void* p, uint8_t* out) {
+// World::gems (world.rs:129-139) reaches `unreachable!()` when a gem position holds no gem tile (a TOML document that lists a
+// gem on a wall / exit / void cell): returns 1 there instead of the flags, and the Python side raises
+int lleo_world_gem_flags(void* p, uint8_t* out) {
     auto gems = ((WorldHandle*)p)->w.gems();
-    for (size_t g = 0; g < gems.size(); ++g) out[g] = gems[g]->collected;
+    for (size_t g = 0; g < gems.size(); ++g) {
+        if (!gems[g]) return 1;
+        out[g] = gems[g]->collected;
+    }
+    return 0;
 }
 // PyGem::collect (src/bindings/tiles/pygem.rs:51-65): only a top-level Gem tile; returns 0, or 1 when the tile is not a gem
 int lleo_world_gem_collect(void* p, long i, long j) {
