@@ -458,3 +458,22 @@ def test_run_argument_checks_and_empty_batch():
     assert np.array_equal(hc, cells[2:5].reshape(3, 25).cpu().numpy()) and np.array_equal(hs, status[2:5].cpu().numpy())
     assert np.array_equal(hl, labels[2:5].cpu().numpy()) and np.array_equal(ht, tries[2:5].cpu().numpy())
     assert _native.lib().lle_gen_fetch(g._h, 6, 3, None, None, None, None, None) == 202  # beyond the last run
+
+
+def test_generated_layouts_compile_identically_in_product_and_oracle():
+    """CPU: the v1 text of generated layouts goes through the product's host map compiler and through the oracle parser with the
+    same result (cells, sources, beams, starts) - the hand-over from the generator to `lle_vec_create`."""
+    from test_toml_maps import _facts_native, _facts_oracle
+
+    rng = random.Random(99)
+    n = 0
+    for _ in range(40):
+        cfg = random_config(rng)
+        for seed in range(12):
+            lay = og.try_generate(cfg, seed)
+            if lay is None:
+                continue
+            text = lay.to_v1()
+            assert _facts_native(text) == _facts_oracle(text), (cfg, seed)
+            n += 1
+    assert n > 150
