@@ -543,6 +543,8 @@ class World:
         cap = 2 * self.height * self.width + 8
         buf = (C.c_int * (7 * cap))()
         n = lib().lleo_world_lasers(self._h, buf, cap)
+        if n < 0:
+            raise RuntimeError("unreachable: a laser position holds no laser tile (World::lasers panics there, world.rs:159-172)")
         return [Laser((buf[7 * k], buf[7 * k + 1]), buf[7 * k + 2], buf[7 * k + 3], Direction(buf[7 * k + 4]),
                       bool(buf[7 * k + 5]), bool(buf[7 * k + 6]), self) for k in range(n)]
 

@@ -339,7 +339,12 @@ void lleo_world_agents(void* p, uint8_t* dead, uint8_t* arrived) {
 }
 // per laser: i, j, laser_id, agent_id, direction, is_on, is_enabled  -> returns count (<= max)
 int lleo_world_lasers(void* p, int* out, int max) {
-    auto ls = ((WorldHandle*)p)->w.lasers();
+    std::vector<LaserView> ls;
+    try {
+        ls = ((WorldHandle*)p)->w.lasers();
+    } catch (const RuntimeWorldError&) {
+        return -1;  // `unreachable!()` in World::lasers (world.rs:159-172): an inconsistent world; the Python side raises
+    }
     int n = 0;
     for (const auto& l : ls) {
         if (n >= max) break;
