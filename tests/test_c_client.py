@@ -28,3 +28,12 @@ def test_c_client_runs():
     lines = res.stdout.strip().splitlines()
     assert lines[-1] == "ok" and "episodes finished" in lines[1] and "0 unexpected transitions" in lines[2]
     assert lines[-2].startswith("generated maps") and "64 maps x 16 envs" in lines[-2]
+
+
+@pytest.mark.gpu
+def test_quickstart_example_runs():
+    import sys
+
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "quickstart.py"), "1024"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.strip().splitlines()[-1] == "ok" and "generated maps: 64 distinct" in res.stdout
