@@ -101,10 +101,11 @@ class VecWorldGroup:
 class Builder:
     """Subset of python/lle/env/builder.py that exists on the accelerated path."""
 
-    def __init__(self, maps):
+    def __init__(self, maps, name: str = "LLE"):
         self._maps = maps
         self._kw = {}
         self._n = 1
+        self._name = name  # builder.py:25
 
     def n_envs(self, n: int):
         self._n = int(n)
@@ -126,6 +127,8 @@ class Builder:
     def multi_objective(self, enabled: bool = True):
         if enabled and "pbrs" in self._kw:  # builder.py:66-73
             raise ValueError("Cannot set multi-objective after setting a reward shaping strategy. Call `multi_objective()` first.")
+        if enabled and not self._kw.get("multi_objective"):
+            self._name = f"{self._name}-MO"  # builder.py:75
         self._kw["multi_objective"] = enabled
         return self
 
@@ -144,6 +147,7 @@ class Builder:
                 else:
                     rewarded.append(int(item))
         self._kw["pbrs"] = dict(gamma=gamma, reward_value=reward_value, lasers_to_reward=rewarded, with_extras=with_extras)
+        self._name = f"{self._name}-PBRS"  # builder.py:102
         return self
 
     def add_extras(self, *extras):
@@ -187,12 +191,12 @@ class Builder:
 
     def build(self) -> VecLLE:
         env = VecLLE(self._maps, self._n, **self._kw)
-        env.name = getattr(self, "_name", "LLE")
+        env.name = self._name
         return env
 
 
 def level(n: int) -> Builder:
-    return Builder(Map(level=n))
+    return Builder(Map(level=n), f"LLE-lvl{n}")  # env.py:238-242
 
 
 def from_str(world_string: str) -> Builder:
@@ -200,5 +204,7 @@ def from_str(world_string: str) -> Builder:
 
 
 def from_file(path: str) -> Builder:
+    import os
+
     with open(path) as f:
-        return Builder(Map(f.read()))
+        return Builder(Map(f.read()), f"LLE-{os.path.basename(path)}")  # env.py:226-232

@@ -415,7 +415,10 @@ class LLE(_Single):
         # the attributes the reference serialises (env.py:60-66, python/tests/test_serialization.py:49-58)
         self.obs_type, self.state_type = obs_type, "state"
         self.walkable_lasers, self.randomize_lasers = bool(walkable_lasers), bool(randomize_lasers)
-        self._name = name if name is not None else (f"LLE-lvl{level}" if level is not None else "LLE")  # env.py:238-242
+        # env.py:220-242 + builder.py:61-102: "LLE-lvl<n>" / "LLE-<file>" / "LLE", then "-MO" and "-PBRS" in the order they were set
+        self._name = name if name is not None else (f"LLE-lvl{level}" if level is not None else "LLE")
+        if name is None or name.startswith("LLE-"):
+            self._name += ("-MO" if multi_objective else "") + ("-PBRS" if pbrs is not None else "")
 
     @staticmethod
     def level(level: int, **kw) -> "LLE":

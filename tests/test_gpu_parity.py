@@ -690,11 +690,22 @@ def test_lle_facade_accessors(tmp_path):
     path = tmp_path / "tiny"
     path.write_text("S0 X")
     env = lle_b200.LLE.from_file(str(path), multi_objective=True)
-    assert env.name == "LLE-tiny" and env.reward_dim == 4
+    assert env.name == "LLE-tiny-MO" and env.reward_dim == 4  # builder.py:75
     env.reset()
     step = env.step([lle_b200.Action.EAST])
     assert step.done and env.compute_done() and lle_b200.LLE.from_str("S0 X").name == "LLE"
     assert lle_b200.level(1).name("mine").n_envs(4).build().name == "mine"
+    # [P] python/tests/test_env.py test_env_name
+    for lvl in (1, 6):
+        assert lle_b200.level(lvl).build().name == f"LLE-lvl{lvl}" and lle_b200.level(lvl).multi_objective().build().name == f"LLE-lvl{lvl}-MO"
+        assert lle_b200.LLE.level(lvl, multi_objective=True).name == f"LLE-lvl{lvl}-MO"
+    assert lle_b200.from_str("S0 X").build().name == "LLE" and lle_b200.from_str("S0 X").multi_objective().build().name == "LLE-MO"
+    assert lle_b200.from_file(str(path)).build().name == "LLE-tiny" and lle_b200.from_str("S0 L0E X").pbrs().build().name == "LLE-PBRS"
+    # [P] python/tests/test_core.py test_width_height, test_state_default
+    env = lle_b200.from_str("S0 X . .\n.  . . .\nG  . . .").build()
+    assert (env.width, env.height) == (4, 3) and env.state_shape == (env.n_agents * 3 + 1,)
+    env.reset()
+    assert tuple(env.state.shape[1:]) == env.state_shape
     # python/tests/test_other.py:4-16
     env = lle_b200.from_str("X S0 G .").build()
     assert (env.width, env.height) == (4, 1)

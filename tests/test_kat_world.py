@@ -1246,3 +1246,82 @@ def test_laser_tile_agent_and_wrapped_gem(api):
     lasers = {l.pos: l for l in world.lasers}
     assert lasers[(0, 1)].agent == 1 and lasers[(0, 2)].agent is None and lasers[(0, 2)].is_off
     assert world.gems[0].is_collected and world.gems[0].agent is None   # PyGem.agent answers for top-level gems only
+
+
+# ---- remaining cases of python/tests/test_world.py
+def test_world_move_and_tuple_actions(api):  # [P] test_world_move, test_world_step_tuple_and_invalid_sequence_action
+    world = api.World("S0 X . .\n.  . . .\n.  . . .")
+    world.reset()
+    world.step([api.Action.SOUTH])
+    world.step([api.Action.EAST])
+    world.step([api.Action.NORTH])
+    assert world.agents_positions == [(0, 1)]
+    world.reset()
+    world.step((api.Action.SOUTH,))
+    assert world.agents_positions == [(1, 0)]
+    with pytest.raises(TypeError, match="Action must be of type Action or list\\[Action\\]"):
+        world.step((23,))
+
+
+def test_world_agents_alive(api):  # [P] test_world_agents
+    world = api.World("S0 S1 S2\nX  X  X")
+    world.reset()
+    assert not any(a.is_dead for a in world.agents) and all(a.is_alive for a in world.agents)
+
+
+def test_world_state_hash(api):  # [P] test_world_state_hash_eq_dead, test_world_state_hash_neq
+    WS = api.WorldState
+    s1, s2 = WS([(0, 0)], [False], [True]), WS([(0, 0)], [False], [False])
+    assert hash(s1) != hash(s2) and s1 != s2
+    s1, s2 = WS([(0, 0)], [False]), WS([(0, 1)], [False])
+    assert hash(s1) != hash(s2) and s1 != s2
+
+
+def test_set_wrong_agent_position(api):  # [P]
+    world = api.World("S0 . . X")
+    with pytest.raises(ValueError):
+        world.set_agent_position(25, (0, 0))
+    with pytest.raises(IndexError):
+        world.set_agent_position(0, (0, 25))
+
+
+def test_set_agents_positions_two_agents(api):  # [P]
+    world = api.World("S0 . . X\nS1 . . X")
+    for j in range(world.width):
+        world.set_agents_positions([(0, j), (1, j)])
+        assert world.agents_positions == [(0, j), (1, j)]
+        world.set_agents_positions([(1, j), (0, j)])
+        assert world.agents_positions == [(1, j), (0, j)]
+
+
+def test_set_conflicting_agents_positions(api):  # [P]
+    world = api.World("S0 . . X\nS1 . . X")
+    with pytest.raises(api.InvalidWorldStateError):
+        world.set_agents_positions([(0, 0), (0, 0)])
+
+
+def test_change_laser_colour_errors(api):  # [P] test_change_laser_colour_to_negative_colour / _to_invalid_colour / _kills_agent_on_start
+    world = api.World("L0E S0 . X")
+    world.reset()
+    source = world.source_at((0, 0))
+    with pytest.raises(OverflowError):
+        source.set_colour(-1)
+    for colour in (2, 1):
+        with pytest.raises(ValueError):
+            source.set_colour(colour)
+        with pytest.raises(ValueError):
+            source.agent_id = colour
+    world = api.World("L0E X X S0 S1")
+    world.reset()
+    with pytest.raises(ValueError):
+        world.source_at((0, 0)).agent_id = 1  # agent 0 would be killed on reset
+
+
+def test_laser_on_start_pos_removed(api):  # [P]
+    world = api.World('world_string = """\n .  S1 X . X\nL1N .  . . ."""\n\n[[agents]]\nstart_positions = [{ i = 0, j = 0 }, { i = 1, j = 1 }]\n')
+    assert world.random_start_pos[0] == [(1, 1)]  # (0, 0) would kill agent 0 in agent 1's beam on start
+
+
+def test_n_laser_colours(api):  # [P] test_n_laser_colours_1agent, test_n_laser_colours_same_colours
+    assert api.World("S0 L0E X\n . L2E X").n_laser_colours == 2
+    assert api.World("S0 L0E X\n . L0E X").n_laser_colours == 1
