@@ -406,6 +406,8 @@ class LLE(_Single):
     def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
                  walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, obs_type: str = "layered",
                  padding_size: int = 0, randomize_lasers: bool = False, device=0, name: str | None = None):
+        self._ctor = dict(map_str=map_str, level=level, multi_objective=multi_objective, walkable_lasers=walkable_lasers, extras=extras,
+                          pbrs=pbrs, obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers, device=device, name=name)
         self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
                           reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
                           obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers)
@@ -446,6 +448,13 @@ class LLE(_Single):
     def compute_done(self) -> bool:
         """env.py:253-254"""
         return self.done
+
+    def __deepcopy__(self, _memo) -> "LLE":
+        """copy.deepcopy(env) (python/tests/test_core.py:test_deep_copy): an environment of its own in the same state - built
+        from the same options, then `set_state`, which also recomputes the reward strategy's counters (env.py:208-216)."""
+        clone = LLE(**self._ctor)
+        clone.set_state(self._world_state())
+        return clone
 
     def get_observation(self):
         """env.py:218 (marlenv's Observation): (data, available_actions, extras)."""

@@ -677,6 +677,8 @@ class LLE:
                  obs_type: str = "layered", padding_size: int = 0, randomize_lasers: bool = False):
         """extras: None | "laser_subgoal" | list of source indices.  pbrs: None | dict(gamma=0.99, reward_value=0.5,
         lasers_to_reward=None (all) | list of source indices, with_extras=True) — Builder.pbrs (builder.py:77-110)."""
+        self._ctor = dict(map_str=map_str, multi_objective=multi_objective, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
+                          obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers)
         st = C.c_int(0)
         self._h = C.c_void_p(lib().lleo_env_new(prepare_map_text(map_str), int(multi_objective), int(walkable_lasers), C.byref(st)))
         _check(st.value)
@@ -710,6 +712,11 @@ class LLE:
     @staticmethod
     def level(n: int, **kw) -> "LLE":
         return LLE(level_text(n), **kw)
+
+    def __deepcopy__(self, _memo) -> "LLE":
+        clone = LLE(**self._ctor)
+        clone.set_state(WorldState.from_array(self.get_state(), self.n_agents, self.n_gems))
+        return clone
 
     @property
     def done(self) -> bool:

@@ -658,3 +658,22 @@ def test_randomized_lasers(api):  # [E] python/tests/test_env.py:381 test_random
     # the laser tiles follow their source (world.lasers reads the live colour)
     by_id = {s.laser_id: s.agent_id for s in env.laser_sources}
     assert all(l.agent_id == by_id[l.laser_id] for l in env.lasers)
+
+
+def test_deep_copy_env(api):  # [P] python/tests/test_core.py test_deep_copy
+    from copy import deepcopy
+
+    env = api.LLE("S0 X")
+    other = deepcopy(env)
+    assert env is not other
+    env.reset()
+    other.reset()
+    assert env.step([api.Action.EAST.value]).done
+    assert not other.step([api.Action.STAY.value]).done   # the copy is an environment of its own
+    # a copy taken in the middle of an episode continues from there
+    env = api.LLE("S0 G . X")
+    env.reset()
+    env.step([api.Action.EAST.value])
+    other = deepcopy(env)
+    assert np.array_equal(other.get_state(), env.get_state())
+    assert other.step([api.Action.EAST.value]).reward == env.step([api.Action.EAST.value]).reward
