@@ -109,11 +109,17 @@ struct lle_vec {
     uint8_t* d_done_ring[kPipeSlots] = {};
     uint32_t* d_pipe_flags = nullptr;  // [0] actions of submit n have landed, [1] submit n has retired
     uint64_t pipe_submitted = 0, pipe_completed = 0;
+    const void* pinned_seen[32] = {};  // host pointers already checked to be page-locked
+    unsigned pinned_next = 0;
 };
 
 namespace {
 
-constexpr int kSchedSlots = 8;  // launches that may be in flight at once through programmatic dependent launch: <= 3
+// Scheduler slots rotate over the launches of a vec.  Any number of (small) launches can be resident at once through
+// programmatic dependent launch, so a slot carries a generation word and a launch waits on the device until the launch that
+// used its slot before has re-armed it (world_kernel.cuh: sched_slot_armed).  One 128-byte line per slot.
+constexpr int kSchedSlots = 8;
+constexpr int kSchedSlotWords = 32;
 
 template <int MODE>
 cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
@@ -142,8 +148,10 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
     if (v->by_feature) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 2>, p);
     return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 0>, p);
 }
+// Host bookkeeping (launch index, sequence number, "the last launch was a step") advances only when the launch was accepted.
 cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
-    p.sched = v->d_sched + 2 * (v->launch_index++ % kSchedSlots);
+    p.sched = v->d_sched + kSchedSlotWords * (v->launch_index % kSchedSlots);
+    p.sched_gen = v->launch_index / kSchedSlots;
     p.flags = v->d_flags;
     cudaError_t e;
     switch (p.mode) {
@@ -157,6 +165,8 @@ cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
             // pipeline depth 2/4/6/8: 7.9e8 / 6.2e8 with narrow grids at depth 4 / 8.4e8 / 8.4e8).
             v->narrow_next = v->force_narrow || (int32_t)(v->seq - *(volatile uint32_t*)v->h_retired_seq) >= 5;
             e = launch_mode<MODE_STEP>(v, p, s);
+            if (e != cudaSuccess) return e;
+            v->launch_index++;
             v->seq += (uint32_t)p.n_steps;
             v->last_was_step = true;
             v->last_stream = s;
@@ -164,6 +174,8 @@ cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
         case MODE_RESET: e = launch_mode<MODE_RESET>(v, p, s); break;
         default: e = launch_mode<MODE_SET_STATE>(v, p, s); break;
     }
+    if (e != cudaSuccess) return e;
+    v->launch_index++;
     v->last_was_step = false;
     v->last_stream = s;
     return e;
@@ -238,6 +250,21 @@ KParams base_params(lle_vec* v) {
     p.randomize = (v->randomize && !v->creating) ? 1 : 0;  // the construction reset is World::new's, not LLE.reset (env.py:191-203)
     p.n_variants = v->n_variants;
     return p;
+}
+
+// Whether `ptr` is page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory).  The answers for the
+// last few pointers are remembered: a host loop passes the same ring of buffers over and over.
+bool is_pinned_host(lle_vec* v, const void* ptr) {
+    for (const void* known : v->pinned_seen)
+        if (known == ptr) return true;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (attr.type != cudaMemoryTypeHost) return false;
+    v->pinned_seen[v->pinned_next++ % 32] = ptr;
+    return true;
 }
 
 template <class T>
@@ -624,7 +651,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     LLE_CUDA(dalloc(&v->d_actions, (size_t)v->A * Np));
     LLE_CUDA(dalloc(&v->d_err, Np));
     if (v->JE) LLE_CUDA(dalloc(&v->d_extras, (size_t)v->A * v->JE * Np));
-    LLE_CUDA(dalloc(&v->d_sched, 2 * kSchedSlots));
+    LLE_CUDA(dalloc(&v->d_sched, (size_t)kSchedSlotWords * kSchedSlots));
     LLE_CUDA(dalloc(&v->d_flags, (size_t)(v->N_pad / v->group)));
     LLE_CUDA(cudaHostAlloc((void**)&v->h_retired_seq, sizeof(uint32_t), cudaHostAllocMapped));
     *v->h_retired_seq = 0;
@@ -803,13 +830,21 @@ int lle_vec_rollout(lle_vec* v, int32_t n_steps, void* stream) {
     if (!v || n_steps < 1) return fail(LLE_INVALID_ARGUMENT, "bad argument");
     if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
     LLE_CUDA(cudaSetDevice(v->device));
-    KParams p = base_params(v);
-    p.mode = MODE_STEP;
-    p.actions_in = nullptr;
-    p.n_steps = n_steps;
-    LLE_CUDA(launch(v, p, (cudaStream_t)stream));
-    v->launches++;
-    v->t += (uint64_t)n_steps;
+    // (step, ticket) pairs are counted in 32 bits on the device: long rollouts over many tickets go out as several launches
+    // (bit-identical: the epoch flags order them exactly like the steps of one launch)
+    const int64_t n_tickets = v->N_pad / v->group;
+    const int32_t max_steps = (int32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)1 << 20, ((int64_t)1 << 30) / n_tickets));
+    for (int32_t left = n_steps; left > 0;) {
+        const int32_t k = std::min(left, max_steps);
+        KParams p = base_params(v);
+        p.mode = MODE_STEP;
+        p.actions_in = nullptr;
+        p.n_steps = k;
+        LLE_CUDA(launch(v, p, (cudaStream_t)stream));
+        v->launches++;
+        v->t += (uint64_t)k;
+        left -= k;
+    }
     return LLE_OK;
 }
 
@@ -855,8 +890,15 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
         LLE_CUDA(cudaEventRecord(v->ev_user, (cudaStream_t)after_stream));
         LLE_CUDA(cudaStreamWaitEvent(v->s_main, v->ev_user, 0));
     }
-    const uint32_t n = (uint32_t)(++v->pipe_submitted);
-    const int slot = (int)((v->pipe_submitted - 1) % lle_vec::kPipeSlots);
+    // Pinned (page-locked) host buffers are REQUIRED: the step kernel spins on a flag that the copy stream publishes behind the
+    // H2D copy, and only a truly asynchronous copy keeps the two streams independent of the calling thread.
+    if ((actions_host && !is_pinned_host(v, actions_host)) || (reward_host && !is_pinned_host(v, reward_host)) ||
+        (done_host && !is_pinned_host(v, done_host)))
+        return fail(LLE_INVALID_ARGUMENT, "lle_vec_pipeline_submit needs pinned (page-locked) host buffers (cudaHostAlloc / cudaHostRegister)");
+    // Nothing is committed to the host bookkeeping until the step kernel has been accepted by the stream.
+    const uint64_t next = v->pipe_submitted + 1;
+    const uint32_t n = (uint32_t)next;
+    const int slot = (int)(v->pipe_submitted % lle_vec::kPipeSlots);
     KParams p = base_params(v);
     p.mode = MODE_STEP;
     if (actions_host) {
@@ -874,12 +916,19 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
     LLE_CUDA(launch(v, p, v->s_main));
     v->launches++;
     v->t++;
-    if (g_wait_value32((CUstream)v->s_out, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 1), n, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-        return fail(LLE_CUDA_ERROR, "cuStreamWaitValue32 failed");
-    if (reward_host) LLE_CUDA(cudaMemcpyAsync(reward_host, v->d_reward_ring[slot], (size_t)v->N * v->R * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
-    if (done_host) LLE_CUDA(cudaMemcpyAsync(done_host, v->d_done_ring[slot], (size_t)v->N, cudaMemcpyDeviceToHost, v->s_out));
-    LLE_CUDA(cudaEventRecord(v->ev_out[slot], v->s_out));
-    return LLE_OK;
+    v->pipe_submitted = next;  // the step is in flight from here on; its completion event is recorded whatever follows
+    int rc = LLE_OK;
+    if (g_wait_value32((CUstream)v->s_out, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 1), n, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+        rc = fail(LLE_CUDA_ERROR, "cuStreamWaitValue32 failed");
+    } else {
+        cudaError_t e = cudaSuccess;
+        if (reward_host) e = cudaMemcpyAsync(reward_host, v->d_reward_ring[slot], (size_t)v->N * v->R * sizeof(float), cudaMemcpyDeviceToHost, v->s_out);
+        if (e == cudaSuccess && done_host) e = cudaMemcpyAsync(done_host, v->d_done_ring[slot], (size_t)v->N, cudaMemcpyDeviceToHost, v->s_out);
+        if (e != cudaSuccess) rc = fail(LLE_CUDA_ERROR, std::string("copy of reward / done to the host: ") + cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaEventRecord(v->ev_out[slot], v->s_out);
+    if (e != cudaSuccess && rc == LLE_OK) rc = fail(LLE_CUDA_ERROR, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
+    return rc;
 }
 
 int lle_vec_pipeline_wait(lle_vec* v, int32_t* outstanding) {

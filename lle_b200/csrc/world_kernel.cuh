@@ -84,7 +84,10 @@ struct KParams {
     int32_t tile_floats;   // floats per shared-memory tile buffer
     int32_t n_buf;         // tile buffers per warp (1 or 2)
     int32_t warp_smem_bytes;
-    uint32_t* sched;       // this launch's scheduler slot: [0] next (step, ticket) pair, [1] warps finished
+    uint32_t* sched;       // this launch's scheduler slot: [0] next (step, ticket) pair, [1] warps finished, [2] generation =
+                           // completed uses of the slot (slots rotate; a launch may only touch its slot once the launch that
+                           // used it before has re-armed it, see sched_gen)
+    uint32_t sched_gen;    // generation this launch expects in sched[2]
     uint32_t* flags;       // [n_tickets] sequence number of the last step completed for the ticket's worlds
     uint32_t seq;          // sequence number of the (first) step of this launch; step q of a ticket needs flags >= q-1
     uint32_t n_tickets, n_warps_total;
@@ -690,6 +693,11 @@ __device__ __forceinline__ bool ticket_ready(const uint32_t* flag, uint32_t need
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     return (int32_t)(v - need) >= 0;
 }
+__device__ __forceinline__ bool sched_slot_armed(const uint32_t* gen, uint32_t want) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gen) : "memory");
+    return v == want;
+}
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -800,7 +808,13 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         }
     }
     const uint32_t warp_global = blockIdx.x * kWarps + warp;
-    const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;  // (step, ticket) pairs, handed out in order
+    const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;  // (step, ticket) pairs, handed out in order (the host keeps it < 2^31)
+    // Scheduler slots rotate over the launches.  Programmatic dependent launch lets many small launches be resident at once,
+    // so the launch that used this slot kSchedSlots launches ago may still be running: wait until its last warp has re-armed
+    // the slot (it never waits for us, and all of its CTAs are resident by the time this launch may start: no cycle).
+    if (lane == 0)
+        while (!sched_slot_armed(p.sched + 2, p.sched_gen)) __nanosleep(32);
+    __syncwarp();
     uint64_t t_first = 0, t_last = 0;
     if (p.timeline && lane == 0) p.timeline[warp_global * 4] = globaltimer_ns();
     int step_index = 0;
@@ -1408,6 +1422,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             p.sched[0] = 0;
             p.sched[1] = 0;
             __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sched + 2), "r"(p.sched_gen + 1u) : "memory");
             if (MODE == MODE_STEP && p.retired_seq) *p.retired_seq = p.seq + (uint32_t)p.n_steps - 1u;
             if (p.out_flag) {
                 // every warp fenced its writes before its increment above; publish the launch to the copy stream that

@@ -398,6 +398,7 @@ class Step:
     done: bool
     events: list
     extras: np.ndarray | None = None
+    info: dict | None = None
 
 
 class LLE(_Single):
@@ -504,7 +505,17 @@ class LLE(_Single):
             raise InvalidActionError("InvalidAction")
         self.last_extras = self.extras()
         return Step(self.observe(), self.available_actions(), self.get_state(), self._vec.reward[0].cpu().numpy(),
-                    bool(self._vec.done[0]), decode_events(self._vec.events[0].cpu().tolist()), self.last_extras)
+                    bool(self._vec.done[0]), decode_events(self._vec.events[0].cpu().tolist()), self.last_extras, self.info())
+
+    def info(self) -> dict:
+        """Step.info (env.py:174-188): gems_collected, exit_rate, has-arrived-i, is-alive-i."""
+        raw = self._raw()
+        out = {"gems_collected": bin(int(raw["collected"]) & self._map.gem_toplevel).count("1"),
+               "exit_rate": int(raw["counters"][0]) / self.n_agents}
+        for i in range(self.n_agents):
+            out[f"has-arrived-{i}"] = bool(raw["arrived"][i])
+            out[f"is-alive-{i}"] = bool(raw["alive"][i])
+        return out
 
     def set_state(self, state: WorldState):
         self._force_state(state)

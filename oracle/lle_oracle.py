@@ -662,6 +662,7 @@ class Step:
     reward: np.ndarray
     done: bool
     events: list
+    info: dict = field(default_factory=dict)
 
 
 def _src_list(sources):
@@ -776,9 +777,19 @@ class LLE:
         _check(lib().lleo_env_step(self._h, acts, len(actions), reward.ctypes.data_as(C.POINTER(C.c_float)),
                                    C.byref(done), ev, C.byref(n)))
         events = [WorldEvent(EventType(ev[2 * k]), ev[2 * k + 1]) for k in range(n.value)]
-        step = Step(self.observe(), self.available_actions(), self.get_state(), reward, bool(done.value), events)
+        step = Step(self.observe(), self.available_actions(), self.get_state(), reward, bool(done.value), events, self.info())
         step.extras = self.last_extras = self.extras()
         return step
+
+    def info(self) -> dict:
+        """Step.info (env.py:174-188): gems_collected, exit_rate, has-arrived-i, is-alive-i."""
+        dead, arrived = (C.c_uint8 * self.n_agents)(), (C.c_uint8 * self.n_agents)()
+        gems = lib().lleo_env_info(self._h, dead, arrived)
+        out = {"gems_collected": int(gems), "exit_rate": self.n_arrived / self.n_agents}
+        for i in range(self.n_agents):
+            out[f"has-arrived-{i}"] = bool(arrived[i])
+            out[f"is-alive-{i}"] = not bool(dead[i])
+        return out
 
     def set_state(self, state: WorldState):
         na, ng = len(state.agents_positions), len(state.gems_collected)

@@ -542,6 +542,15 @@ int lleo_env_n_arrived(void* p) { return (int)((Env*)p)->n_arrived; }
 void lleo_env_available(void* p, uint8_t* out) { ((Env*)p)->available_actions(out); }
 int lleo_env_observe(void* p, float* out) { return guarded([&] { ((Env*)p)->observe(out); }); }
 void lleo_env_state(void* p, float* out) { ((Env*)p)->state(out); }
+// Step.info of LLE.step (env.py:174-188): World::n_gems_collected and, per agent, Agent.is_dead / has_arrived
+int lleo_env_info(void* p, uint8_t* dead, uint8_t* arrived) {
+    const World& w = ((Env*)p)->world;
+    for (size_t a = 0; a < w.n_agents(); ++a) {
+        dead[a] = w.agents[a].is_dead();
+        arrived[a] = w.agents[a].has_arrived();
+    }
+    return (int)w.n_gems_collected();
+}
 
 // ---------------------------------------------------------------- Vec (N envs, device-layout outputs)
 void* lleo_vec_new(const char** texts, int n_maps, const int* map_of_env, int n_envs, int multi_objective,
