@@ -10,8 +10,12 @@ of `LLE.step` written: layered observation, state vector, availability mask, rew
         reference engine on all host cores (the Rust crate cannot be built in this image: no cargo/rustc)
 
 For N > 1 launch with torchrun (one rank per GPU); envs are range-sharded over ranks (weak scaling, no
-collective on the step path; one NCCL all-reduce(MAX) of the elapsed time and one of the episode counter).
-Prints ONE JSON line on rank 0.
+collective on the step path; NCCL carries only the reductions of the timings and of three counters).
+Prints ONE JSON line on rank 0.  Keys beyond the contract:
+  configs    the other BASELINE.json workloads (1, 3, 4, 5 of SURVEY §8d) at their stated per-GPU sizes, bounded steps
+  e2e        value = closed loop (the host reads step t's results before it chooses step t+1's actions), two half-batches
+             in flight; pipelined_value = open loop, 8 recorded steps in flight; sync_value = one blocking call per step
+  ranks      per-rank ms per step of the headline window (min / max / all)
 """
 from __future__ import annotations
 
@@ -31,22 +35,13 @@ ENVS_PER_GPU = 65536
 SEED = 2026
 METRIC = "env-steps/s (layered obs, device-timed)"
 UNIT = "env-steps/s"
+# bounded timed steps of the other configs: (steps, warm-up) — about 0.1-0.2 s of device time each
+CONFIG_STEPS = {1: (512, 16), 3: (96, 8), 4: (32, 4), 5: (8, 3)}
 
 
 def level_text(n: int) -> str:
     with open(os.path.join(ROOT, "lle_b200", "resources", "levels", f"lvl{n}")) as f:
         return f.read()
-
-
-def algorithmic_bytes(A: int, G: int, C: int, H: int, W: int, R: int, record_bytes: int) -> dict:
-    """B = OBS + ST + AV + AC + RDE + 2*S (bytes that must cross HBM per env-step)."""
-    obs = 4 * C * H * W
-    st = 4 * (3 * A + G)
-    av = 5 * A
-    ac = A
-    rde = 4 * R + 1 + A + 1  # reward, done, events, err
-    return dict(obs=obs, state=st, avail=av, actions=ac, reward_done_events=rde, record_rw=2 * record_bytes,
-                total=obs + st + av + ac + rde + 2 * record_bytes)
 
 
 def measured_peak() -> tuple[float, str]:
@@ -59,15 +54,14 @@ def measured_peak() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per launch of the step kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic() -> dict:
+    """dram bytes per launch of the step kernel from the committed `ncu --set full` capture (profiles/traffic.json names the
+    capture and the commit it was taken at; it is a profile reading, not something this run measures)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -77,7 +71,7 @@ class ClockSampler:
     def __init__(self, device_index: int):
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -124,7 +118,9 @@ def cpu_baseline(sample_seconds: float = 12.0, n_envs: int = 4096, threads: int 
     value = n_envs * steps / secs
     return {"value": value, "unit": UNIT, "cores": used, "kind": "port",
             "sample": f"{n_envs} envs x {steps} steps of level {LEVEL} in {secs:.2f} s, C++ restatement of the reference engine "
-                      f"(Rust toolchain unavailable), one World per thread, {used} threads, layered obs + state + avail written each step",
+                      f"(Rust toolchain unavailable) with the reference's own allocation pattern (a fresh observation array and "
+                      f"laser / gem lists per step, as python/lle/observations.py:254-266 does), one World per thread, {used} threads, "
+                      f"layered obs + state + avail written each step",
             "seconds": secs}
 
 
@@ -154,15 +150,33 @@ def run_reference(args) -> None:
     print(json.dumps(line))
 
 
+def pin_rank_to_cores(local_rank: int, local_world: int) -> list[int] | None:
+    """One disjoint slice of the host cores per rank: the step loop of a rank is host-driven (one launch per step), and
+    eight Python processes migrating over the same cores show up as per-rank jitter in the MAX-over-ranks timing."""
+    if local_world <= 1:
+        return None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // local_world)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 def run_ours(args) -> None:
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = pin_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world_size))))
+
     import torch
     import torch.distributed as dist
 
     import lle_b200
+    from lle_b200 import workloads
 
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -180,7 +194,7 @@ def run_ours(args) -> None:
     begin, end = shard_range(args.envs * world_size, rank, world_size)  # weak scaling: args.envs worlds per GPU
     n_envs = end - begin
     vec = lle_b200.VecWorld(lle_b200.Map(level=LEVEL), n_envs, device=dev, seed=SEED, env_id_base=begin, auto_reset=True)
-    A, G, C, H, W, R = vec.n_agents, vec.n_gems, vec.n_channels, vec.height, vec.width, vec.reward_dim
+    A, R = vec.n_agents, vec.reward_dim
     K, Wm = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -188,7 +202,30 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm: K fused steps back to back, no host sync inside
+    def reduce_max(x: float) -> float:
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def gather(x: float) -> list[float]:
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world_size == 1:
+            return [float(tt.item())]
+        out = [torch.zeros_like(tt) for _ in range(world_size)]
+        dist.all_gather(out, tt)
+        return [float(o.item()) for o in out]
+
+    # ---------------- device-resident arm: K fused steps back to back, no host sync inside.
+    # Untimed preheat first (not counted as warm-up steps): a fresh process finds the GPU at idle clocks, and W = 5 steps are
+    # 0.4 ms of work; the timed window should see the clocks a running job sees.
+    t0 = time.perf_counter()
+    preheat = 0
+    while time.perf_counter() - t0 < args.preheat_ms / 1e3:
+        for _ in range(64):
+            vec.step(None)
+        preheat += 64
+        torch.cuda.synchronize()
     for _ in range(Wm):
         vec.step(None)
     barrier()
@@ -199,17 +236,14 @@ def run_ours(args) -> None:
         vec.step(None)
     ms_total, timed_launches = vec.timing_end()
     barrier()
-    clocks = sampler.stop() if sampler else None
     launches = vec.launch_count - launches0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    per_rank = gather(ms_total / K)
+    ms_max = max(per_rank) * K
     value = world_size * n_envs * K / (ms_max / 1e3)
 
-    # ---------------- the same K steps as lle_vec_rollout launches (128 steps per launch, bit-identical results): reported
-    # beside the headline as "rollout", not as the headline (the contract's step = one launch)
-    RL = 128
+    # ---------------- the same K steps as lle_vec_rollout launches (up to 128 steps per launch, bit-identical results):
+    # reported beside the headline as "rollout", not as the headline (the contract's step = one launch)
+    RL = min(128, max(K, 1))
     n_roll = max(1, K // RL)
     vec.rollout(RL)
     barrier()
@@ -218,44 +252,51 @@ def run_ours(args) -> None:
         vec.rollout(RL)
     ms_roll, roll_launches = vec.timing_end()
     barrier()
-    tr = torch.tensor([ms_roll], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-    rollout_value = world_size * n_envs * n_roll * RL / (float(tr.item()) / 1e3)
+    clocks = sampler.stop() if sampler else None
+    ms_roll_max = reduce_max(ms_roll)
+    rollout_value = world_size * n_envs * n_roll * RL / (ms_roll_max / 1e3)
 
-    # ---------------- end-to-end arm: host actions in (pinned, H2D), reward + done out (D2H), sync every step
-    Ke = min(K, args.e2e_steps)
+    # ---------------- end-to-end arms: host actions in (pinned, H2D), reward + done out (D2H) every step
+    Ke = max(1, min(K, args.e2e_steps))
+    T0 = 10_000_000
+    half = n_envs // 2
     vec.reset()
-    vec.step_count = 10_000_000
-    rec = torch.empty((Ke, n_envs, A), dtype=torch.int8).pin_memory()
-    for s in range(Ke):  # record a valid action stream on the device, then replay it from the host
+    vec.step_count = T0
+    rec_act = torch.empty((Ke, n_envs, A), dtype=torch.int8).pin_memory()
+    rec_done = torch.empty((Ke, n_envs), dtype=torch.uint8).pin_memory()
+    for s in range(Ke):  # record a valid action stream (and the done flags it leads to) on the device, then drive from the host
         vec.step(None)
-        rec[s].copy_(vec.actions, non_blocking=True)
+        rec_act[s].copy_(vec.actions, non_blocking=True)
+        rec_done[s].copy_(vec.done, non_blocking=True)
     torch.cuda.synchronize()
-    vec.reset()
-    vec.step_count = 10_000_000
+    stay = torch.full((n_envs, A), 4, dtype=torch.int8).pin_memory()
     D = max(1, min(8, args.e2e_depth))
     reward_h = [torch.empty((n_envs, R), dtype=torch.float32).pin_memory() for _ in range(D)]
     done_h = [torch.empty((n_envs,), dtype=torch.uint8).pin_memory() for _ in range(D)]
 
+    def restart(v, t=T0):
+        v.reset()
+        v.step_count = t
+
     def e2e_sync() -> float:
-        """lle_vec_step_host: H2D, step, D2H, stream sync — one call per step, nothing overlapped."""
-        vec.reset()
-        vec.step_count = 10_000_000
+        """lle_vec_step_host, closed loop: H2D, step, D2H, stream sync — one blocking call per step; the actions of step s are
+        chosen only after every done flag of step s-1 has been read (they match the recording, so the recorded actions stay
+        valid; otherwise everyone would STAY)."""
+        restart(vec)
         barrier()
         t0 = time.perf_counter()
-        n_done = 0
+        acts = rec_act[0]
         for s in range(Ke):
-            vec.step_host(rec[s], reward_h[0], done_h[0])
-            n_done += int(done_h[0][0])  # the host consumes the result
+            vec.step_host(acts, reward_h[0], done_h[0])
+            if s + 1 < Ke:
+                acts = rec_act[s + 1] if torch.equal(done_h[0], rec_done[s]) else stay
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
     def e2e_pipelined() -> float:
-        """lle_vec_pipeline_submit / _wait with D steps in flight: every step still takes its actions from pinned host
-        memory and lands its reward + done in pinned host memory; the copies overlap the neighbouring steps' kernels."""
-        vec.reset()
-        vec.step_count = 10_000_000
+        """lle_vec_pipeline_submit / _wait with D steps in flight (OPEN loop: step s+D is submitted before step s is read —
+        what a replay buffer or a scripted evaluation can do, not an acting agent)."""
+        restart(vec)
         barrier()
         t0 = time.perf_counter()
         n_done = 0
@@ -263,35 +304,94 @@ def run_ours(args) -> None:
             if s >= D:
                 vec.wait_host()
                 n_done += int(done_h[(s - D) % D][0])  # the host consumes the result of step s - D
-            vec.submit_host(rec[s], reward_h[s % D], done_h[s % D])
+            vec.submit_host(rec_act[s], reward_h[s % D], done_h[s % D])
         for s in range(max(Ke - D, 0), Ke):
             vec.wait_host()
             n_done += int(done_h[s % D][0])
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    def reduce_max(x: float) -> float:
-        tt = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+    # closed loop with two half-batches in flight (the EnvPool pattern): while the host reads half A's results and chooses its
+    # next actions, half B steps.  Two vecs over the same global env ids as the two halves of the batch.
+    halves = [lle_b200.VecWorld(lle_b200.Map(level=LEVEL), half, device=dev, seed=SEED, env_id_base=begin + h * half, auto_reset=True)
+              for h in range(2)]
+    rec_act_h = [rec_act[:, h * half:(h + 1) * half].contiguous().pin_memory() for h in range(2)]
+    rec_done_h = [rec_done[:, h * half:(h + 1) * half].contiguous().pin_memory() for h in range(2)]
+    stay_h = stay[:half].contiguous().pin_memory()
+    rw_h = [torch.empty((half, R), dtype=torch.float32).pin_memory() for _ in range(2)]
+    dn_h = [torch.empty((half,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    mismatches = [0]
+
+    def e2e_closed_loop() -> float:
+        for v in halves:
+            restart(v)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(Ke):
+            for h in range(2):
+                acts = rec_act_h[h][s]
+                if s > 0:
+                    halves[h].wait_host()  # results of step s-1 of this half are in host memory
+                    if not torch.equal(dn_h[h], rec_done_h[h][s - 1]):  # the policy reads every result byte
+                        acts = stay_h
+                        mismatches[0] += 1
+                halves[h].submit_host(acts, rw_h[h], dn_h[h])
+        for h in range(2):
+            halves[h].wait_host()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
 
     for s in range(min(3, Ke)):
-        vec.step_host(rec[s], reward_h[0], done_h[0])
+        vec.step_host(rec_act[s], reward_h[0], done_h[0])
     e2e_pipelined()  # warm-up (creates the pipeline's streams and ring)
+    e2e_closed_loop()
     e2e_sync_value = world_size * n_envs * Ke / reduce_max(e2e_sync())
-    e2e_value = world_size * n_envs * Ke / reduce_max(e2e_pipelined())
+    e2e_pipe_value = world_size * n_envs * Ke / reduce_max(e2e_pipelined())
     assert int(vec.err.sum()) == 0, "replayed actions must be valid"
+    mismatches[0] = 0
+    e2e_closed_value = world_size * 2 * half * Ke / reduce_max(e2e_closed_loop())
+    assert mismatches[0] == 0 and all(int(v.err.sum()) == 0 for v in halves), "the closed loop left the recorded trajectory"
+    del halves
 
     # end-of-run stats reduction: the only collective on this path (NCCL all-reduce of a few counters)
     stats = reduce_stats(torch.stack([vec.done.sum().to(torch.int64), vec.reward.sum().to(torch.int64),
                                       torch.tensor(n_envs, dtype=torch.int64, device=dev)]))
+    bytes_env = workloads.algorithmic_bytes(vec)
+    obs_shape = [vec.n_channels, vec.height, vec.width]
+    del vec
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE.json workloads at their stated per-GPU sizes (bounded steps)
+    peak, peak_src = measured_peak()
+    configs = {}
+    for cfg in ([] if args.no_configs else [1, 3, 4, 5]):
+        n_cfg = workloads.DEFAULT_ENVS[cfg]
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        if cfg == 5:
+            per_env = 4 * 20 * 64 * 64 + 4096
+            while n_cfg * per_env > 0.92 * free_b and n_cfg > 1024:
+                n_cfg //= 2  # a GPU with less memory than a B200: say so in the line
+        b0, _ = shard_range(n_cfg * world_size, rank, world_size)
+        wl = workloads.build(cfg, n_cfg, device=dev, seed=SEED, env_id_base=b0)
+        steps_c, warm_c = CONFIG_STEPS[cfg]
+        barrier()
+        ms_c = reduce_max(wl.measure(steps_c, warm_c))
+        ach = wl.algorithmic_bytes() / (ms_c / 1e3) / 1e9
+        errs = sum(int(p.err.sum()) for p in wl.parts)
+        configs[str(cfg)] = {
+            "workload": wl.description, "envs_per_gpu": wl.n_envs, "envs": wl.n_envs * world_size, "steps": steps_c, "warmup": warm_c,
+            "ms_per_step": ms_c, "env_steps_per_s": world_size * wl.n_envs / (ms_c / 1e3),
+            "agent_env_steps_per_s": world_size * wl.agent_envs / (ms_c / 1e3), "launches_per_step": len(wl.parts),
+            "algorithmic_bytes_per_step_per_gpu": wl.algorithmic_bytes(), "env_errors": errs,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+        }
+        del wl
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        bytes_env = algorithmic_bytes(A, G, C, H, W, R, record_bytes=vec.record_bytes)
-        peak, peak_src = measured_peak()
         kernel_ms = ms_total / max(timed_launches, 1)
         achieved = bytes_env["total"] * n_envs / (kernel_ms / 1e3) / 1e9
+        traffic = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": Wm,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -299,29 +399,39 @@ def run_ours(args) -> None:
             "config": {
                 "workload": f"World.level({LEVEL}) 4 agents, 3 laser sources (BASELINE.json says 4; the level file has 3), "
                             f"{n_envs} batched envs per GPU with layered observations (BASELINE.json configs[1])",
-                "envs_per_gpu": n_envs, "agents": A, "obs_shape": [C, H, W], "actions": "device Philox4x32-10, uniform over available",
+                "envs_per_gpu": n_envs, "agents": A, "obs_shape": obs_shape,
+                "actions": "device Philox4x32-10, uniform over available",
                 "auto_reset": True, "agent_env_steps_per_s": value * A,
-                "l2": f"each step rewrites {n_envs * C * H * W * 4 / 1e6:.0f} MB of observations per GPU (> 126 MB L2); no flush needed",
+                "l2": f"each step rewrites {n_envs * bytes_env['obs'] / 1e6:.0f} MB of observations per GPU (> 126 MB L2); no flush needed",
                 "sharding": "contiguous env ranges per rank, no collective on the step path",
                 "launch": "one fused kernel launch per step (programmatic dependent launch between steps); "
                           "lle_vec_rollout(K) runs K steps in one launch with identical results",
+                "preheat": f"{preheat} untimed steps (~{args.preheat_ms:.0f} ms) before the {Wm} warm-up steps, so that the timed window "
+                           f"runs at the clocks of a running job",
+                "host_cores_of_rank0": cores,
             },
+            "ranks": {"ms_per_step_min": min(per_rank), "ms_per_step_max": max(per_rank), "ms_per_step": per_rank},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A, "d2h_bytes_per_step": n_envs * (4 * R + 1),
-                    "steps": Ke, "pipeline_depth": D, "sync_value": e2e_sync_value,
-                    "note": f"lle_vec_pipeline_submit/_wait, {D} steps in flight: every step copies its actions from pinned host memory "
-                            "(H2D), runs the fused step and copies reward+done to pinned host memory (D2H), all inside the timed "
-                            "region; the host reads each step's result. sync_value = lle_vec_step_host (same copies, stream sync "
-                            "after every step, nothing overlapped). Observations stay in HBM (zero-copy DLPack hand-off)"},
+            "e2e": {"value": e2e_closed_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A, "d2h_bytes_per_step": n_envs * (4 * R + 1),
+                    "steps": Ke, "closed_loop": True, "sub_batches_in_flight": 2,
+                    "pipelined_value": e2e_pipe_value, "pipeline_depth": D, "sync_value": e2e_sync_value,
+                    "note": "value: CLOSED loop through lle_vec_pipeline_submit/_wait on two half-batches (two vecs over the same global "
+                            "env ids): the host reads every done flag of a half's step t from pinned memory before it submits that half's "
+                            "step t+1, while the other half steps; every step copies its actions H2D and reward+done D2H inside the timed "
+                            "region. sync_value: the same dependency with one blocking lle_vec_step_host call per step on the whole batch. "
+                            f"pipelined_value: OPEN loop, {D} recorded steps in flight (not what an acting agent can do). "
+                            "Observations stay in HBM (zero-copy DLPack hand-off to a device policy)"},
             "gpu_launches": launches,
             "rollout": {"value": rollout_value, "unit": UNIT, "steps_per_launch": RL, "launches": int(roll_launches),
-                        "ms_per_step": float(tr.item()) / (n_roll * RL),
-                        "note": "lle_vec_rollout(128): the same steps, 128 per launch, ordered by the per-ticket epoch flags; device-timed"},
+                        "ms_per_step": ms_roll_max / (n_roll * RL),
+                        "note": "lle_vec_rollout: the same steps, many per launch, ordered by the per-ticket epoch flags; device-timed"},
+            "configs": configs,
             "stats_allreduce": {"done_last_step": int(stats[0]), "reward_last_step": int(stats[1]), "envs_total": int(stats[2])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(), "peak_source": peak_src, "kernel": "lle_world_kernel<MODE_STEP, FAST>",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": bytes_env,
-                         "algorithmic_bytes_per_launch": bytes_env["total"] * n_envs},
+                         "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                         "traffic_commit": traffic.get("commit"), "peak_source": peak_src,
+                         "kernel": "lle_world_kernel<MODE_STEP, FAST>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_env_step": bytes_env, "algorithmic_bytes_per_launch": bytes_env["total"] * n_envs},
         }
         if world_size == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline()
@@ -340,8 +450,10 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2048)
-    ap.add_argument("--e2e-depth", type=int, default=8, help="steps in flight in the pipelined end-to-end arm (1..8)")
+    ap.add_argument("--e2e-depth", type=int, default=8, help="steps in flight in the open-loop pipelined arm (1..8)")
+    ap.add_argument("--preheat-ms", type=float, default=250.0, help="untimed device work before the warm-up steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -70,8 +70,11 @@ int main(int argc, char** argv) {
 
     /* phase 3: pipelined host stepping, four steps in flight (device-sampled actions) */
     CHECK(lle_vec_reset(vec, NULL, NULL));
-    float* ring_reward = (float*)malloc(4 * (size_t)n_envs * buf.reward_dim * sizeof(float));
-    uint8_t* ring_done = (uint8_t*)malloc(4 * (size_t)n_envs);
+    /* the pipelined calls need pinned host buffers: the library hands them out (no CUDA runtime in this program) */
+    float* ring_reward = NULL;
+    uint8_t* ring_done = NULL;
+    CHECK(lle_host_alloc(4 * (size_t)n_envs * buf.reward_dim * sizeof(float), (void**)&ring_reward));
+    CHECK(lle_host_alloc(4 * (size_t)n_envs, (void**)&ring_done));
     long pipelined_episodes = 0;
     for (int t = 0; t < steps + 4; ++t) {
         if (t >= 4) {
@@ -97,7 +100,9 @@ int main(int argc, char** argv) {
     CHECK(lle_vec_launch_count(vec, &launches));
     printf("mutators        : source 1 disabled, exits moved; %llu kernel launches in total\n", (unsigned long long)launches);
 
-    free(actions); free(reward); free(done); free(ring_reward); free(ring_done);
+    free(actions); free(reward); free(done);
+    CHECK(lle_host_free(ring_reward));
+    CHECK(lle_host_free(ring_done));
     CHECK(lle_vec_destroy(vec));
     lle_map_free(map);
 

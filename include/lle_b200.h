@@ -239,6 +239,13 @@ LLE_API int lle_vec_rollout(lle_vec* vec, int32_t n_steps, void* cuda_stream);
  * stream.  The observation stays resident in HBM (zero-copy DLPack hand-off to the policy). */
 LLE_API int lle_vec_step_host(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* cuda_stream);
 
+/* Page-locked (pinned) host memory for the host-facing calls below.  lle_vec_pipeline_submit REQUIRES its action / reward / done
+ * buffers to be pinned (memory from here, cudaHostAlloc, cudaHostRegister or torch's pin_memory): the step kernel waits on the
+ * device for the action copy and writes reward / done straight into the host buffers.  A host without a CUDA runtime of its own
+ * (the reference's Rust crate) allocates them here. */
+LLE_API int lle_host_alloc(size_t bytes, void** out);
+LLE_API int lle_host_free(void* ptr);
+
 /* Pipelined host stepping: the same step as lle_vec_step_host without the per-step stream synchronisation.
  * lle_vec_pipeline_submit enqueues (1) the copy of `actions_host` (pinned i8[N,A]; NULL = device sampling) on a copy
  * stream, (2) the fused step on the vec's own compute stream, which waits for the actions inside the kernel, and (3) the

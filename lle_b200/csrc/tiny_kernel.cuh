@@ -1,0 +1,249 @@
+// lle_b200 — the step kernel for TINY maps (sm_100a): one THREAD per world.
+//
+// The general kernel (world_kernel.cuh) gives a world to a group of lanes, one lane per agent, and talks between the
+// agents of a world with group ballots and shuffles.  That is the right shape when the observation dominates (level 6:
+// 7.5 KB per world), but on a 5x5 map (BASELINE configs[2]: 800 B per world, 2 agents) the step is bound by instruction
+// issue: 136 warp-instructions per world, of which the group machinery, the per-lane predicates and the 32/E-lanes-per-world
+// tile patching are most (profiles/ncu_cfg3_r01_summary.csv).  Here a lane owns a whole world:
+//   * the agents of a world are walked by a compile-time loop (A_ <= 4) in the reference's own order — leave, pre_enter,
+//     enter, repeated while somebody died (world.rs:454-505) — with positions, flags and events in registers and the beam /
+//     gem masks in a lane-private column of shared memory (dynamic index by beam): no ballots, no shuffles, no predicated
+//     phases, and 32 worlds advance per warp pass instead of 32 / Wd;
+//   * a lane patches ITS world's sub-tile of the warp's observation tile (un-patch what the previous occupant had lit, patch
+//     what this one lights, move the agents' one-hots), E lanes at a time, and the tile leaves with one TMA bulk store;
+//   * every lane follows its own map (blob pointer per lane), so heterogeneous batches need no uniformity checks.
+// Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
+// per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
+// (static_map.h), Philox action sampling, auto-reset, the host-pipeline flags.  Reset / set_state / refresh launches of the
+// same vec run on the general kernel.  Results are bit-identical by construction of the tests (tests/test_gpu_parity.py,
+// tests/test_gpu_fullsize.py run both).
+#pragma once
+#include "tiny_core.cuh"
+#include "world_kernel.cuh"
+
+namespace lle {
+
+#ifndef LLE_TINY_MIN_CTAS
+#define LLE_TINY_MIN_CTAS 6
+#endif
+
+// word k of the record of lane `lane` in the warp's [stride][32] column block; `applied` columns are [stride][E]
+struct SmemColumn {
+    uint32_t* base;
+    int pitch;
+    __device__ __forceinline__ uint32_t& operator()(int word) const { return base[word * pitch]; }
+};
+
+// `n` bytes (compile-time) from registers to global memory with the widest stores the alignment of `n` allows
+template <int N>
+__device__ __forceinline__ void store_bytes(uint8_t* dst, const uint32_t (&b)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k += 4)
+            *reinterpret_cast<uint32_t*>(dst + k) = b[k] | (b[k + 1] << 8) | (b[k + 2] << 16) | (b[k + 3] << 24);
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) *reinterpret_cast<uint16_t*>(dst + k) = (uint16_t)(b[k] | (b[k + 1] << 8));
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) dst[k] = (uint8_t)b[k];
+    }
+}
+
+template <int A_>
+__global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_kernel(const KParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = p.L.stride, w_flags = p.L.w_flags, w_avail = p.L.w_avail, w_gems = p.L.w_gems, w_on = p.L.w_on;
+    const bool has_gems = p.L.gem_words != 0;
+    const int W = p.W, E = p.E, ostr = (int)p.obs_stride;
+    uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
+    float* tiles = reinterpret_cast<float*>(wbase);                                  // [E][ostr]: E worlds per bulk store
+    uint32_t* srec = reinterpret_cast<uint32_t*>(tiles + p.tile_floats);             // [stride][32]: word k of lane l at k*32+l
+    uint32_t* applied = srec + stride * 32;                                          // [stride][E]: the record each sub-tile shows
+    int32_t* tags = reinterpret_cast<int32_t*>(applied + stride * E);                // [E]: the map each sub-tile was built from
+    for (int k = lane; k < E; k += 32) tags[k] = -1;
+    __syncwarp();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
+        if (lane == 0)
+            while (!sys_flag_ready(p.in_flag, p.in_need)) __nanosleep(100);
+        __syncwarp();
+    }
+    if (lane == 0)
+        while (!sched_slot_armed(p.sched + 2, p.sched_gen)) __nanosleep(32);
+    __syncwarp();
+
+    const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;
+    uint32_t owed_ticket = 0, owed_seq = 0;
+    bool owed = false;
+    TinyWorld<A_, SmemColumn> w;
+    w.rec = SmemColumn{srec + lane, 32};
+    w.L = TinyLayout{w_flags, w_avail, w_gems, w_on, stride, has_gems};
+    w.W = W;
+    int bound_map = -1;
+
+    for (;;) {
+        uint32_t pair = 0;
+        if (lane == 0) pair = atomicAdd(&p.sched[0], 1u);
+        pair = __shfl_sync(kFull, pair, 0);
+        if (pair >= n_pairs) break;
+        const uint32_t ticket = pair % p.n_tickets;
+        const int step_index = (int)(pair / p.n_tickets);
+        const uint32_t my_seq = p.seq + (uint32_t)step_index;
+        {
+            bool flushed = false;
+            if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
+                if (owed) {  // never block while owing a completion
+                    bulk_wait_all();
+                    ticket_release(p.flags + owed_ticket, owed_seq);
+                    flushed = true;
+                }
+                while (!ticket_ready(p.flags + ticket, my_seq - 1u)) __nanosleep(64);
+            }
+            if (__shfl_sync(kFull, (int)flushed, 0)) owed = false;
+        }
+        const int64_t env = (int64_t)ticket * 32 + lane;  // the ticket is 32 consecutive worlds, one per lane
+        const uint64_t t_now = p.t + (uint64_t)step_index;
+        const bool real = env < p.N;
+
+        // ---- record -> lane-private column of shared memory (through L2: an overlapped launch may just have written it)
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(p.records + env * stride);
+            for (int q = 0; q < stride / 4; ++q) {
+                const uint4 v = __ldcg(src + q);
+                w.rec(4 * q + 0) = v.x; w.rec(4 * q + 1) = v.y; w.rec(4 * q + 2) = v.z; w.rec(4 * q + 3) = v.w;
+            }
+        }
+        const int map_id = p.map_of_env ? __ldcg(p.map_of_env + env) : 0;
+        if (map_id != bound_map) {
+            w.bind(p.blobs[map_id]);
+            bound_map = map_id;
+        }
+        w.unpack();
+        const uint32_t av_cache = w.rec(w_avail);  // World::available_actions cache: one byte per agent (A_ <= 4)
+
+        // ---- actions (world.rs:444-453): supplied, or sampled uniformly among the available ones
+        uint32_t act[A_], ev[A_];
+        bool bad = false;
+        {
+            uint32_t r[4] = {0, 0, 0, 0};
+            if (!p.actions_in)
+                philox4x32_10((uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, 0u, (uint32_t)(t_now >> 32), (uint32_t)p.seed,
+                              (uint32_t)(p.seed >> 32), r);
+#pragma unroll
+            for (int a = 0; a < A_; ++a) {
+                const uint32_t av = (av_cache >> (8 * a)) & 0xFFu;
+                act[a] = 4u;
+                if (p.actions_in) {
+                    if (real) act[a] = (uint32_t)(uint8_t)p.actions_in[env * A_ + a];  // padding worlds just STAY
+                } else {
+                    act[a] = pick_action(r[a], av);
+                }
+                if (act[a] > 4u || !((av >> act[a]) & 1u)) bad = true;
+                ev[a] = 0;
+            }
+        }
+        uint32_t err = ERR_OK;
+        if (p.lle_semantics && w.done) err = ERR_DONE;  // env.py:166-167
+        else if (bad) err = ERR_INVALID_ACTION;          // the world is left untouched
+        const bool paid = err == ERR_OK;
+        uint32_t n_gem = 0, n_exit = 0, n_died = 0;
+        if (paid) w.step(act, ev, n_gem, n_exit, n_died);
+        {   // reward / done / err / events / actions of the transition just taken
+            float rw[4];
+            w.reward(paid, p.R, n_gem, n_exit, n_died, rw);
+            if (p.R == 1) {
+                p.reward[env] = rw[0];
+                if (p.reward2 && real) p.reward2[env] = rw[0];  // the host's own buffer: N worlds, no padding
+            } else {
+                *reinterpret_cast<float4*>(p.reward + env * 4) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+                if (p.reward2 && real) *reinterpret_cast<float4*>(p.reward2 + env * 4) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+            }
+            p.done[env] = (uint8_t)w.done;
+            if (p.done2 && real) p.done2[env] = (uint8_t)w.done;
+            p.err[env] = (uint8_t)err;
+            store_bytes<A_>(p.events + env * A_, ev);
+            store_bytes<A_>(reinterpret_cast<uint8_t*>(p.actions) + env * A_, act);
+        }
+        // auto-reset: the transition above is reported; observation / state / availability are the fresh world's
+        if (p.auto_reset && w.done && err == ERR_OK) w.reset();
+
+        // ---- World::compute_available_actions (world.rs:343-363) + LLE.available_actions (env.py:146-163)
+        uint32_t cache = 0, avb[5 * A_];
+#pragma unroll
+        for (int a = 0; a < A_; ++a) {
+            uint32_t mask = w.available(a);
+            cache |= mask << (8 * a);
+            if (!p.walkable) mask = w.available_no_walk(a, mask);  // LLE-level mask, output only
+#pragma unroll
+            for (int k = 0; k < 5; ++k) avb[5 * a + k] = (mask >> k) & 1u;
+        }
+        store_bytes<5 * A_>(p.avail + env * (5 * A_), avb);
+
+        // ---- record back (registers -> column -> HBM) and the state vector (pyworld_state.rs:79-101)
+        w.pack(cache);
+        {
+            uint4* dst = reinterpret_cast<uint4*>(p.records + env * stride);
+            for (int q = 0; q < stride / 4; ++q) __stcg(dst + q, make_uint4(w.rec(4 * q + 0), w.rec(4 * q + 1), w.rec(4 * q + 2), w.rec(4 * q + 3)));
+            float* st = p.state + env * p.S;
+#pragma unroll
+            for (int a = 0; a < A_; ++a) {
+                st[2 * a] = (float)(w.pos[a] >> 8);
+                st[2 * a + 1] = (float)(w.pos[a] & 0xFFu);
+                st[2 * A_ + p.G + a] = ((w.alive >> a) & 1u) ? 1.0f : 0.0f;
+            }
+            if (has_gems) {
+                const uint32_t coll = w.rec(w_gems);
+                for (int g = 0; g < p.G; ++g) st[2 * A_ + g] = ((coll >> g) & 1u) ? 1.0f : 0.0f;
+            }
+        }
+        __syncwarp();
+
+        // ---- layered observation (observations.py:254-266): E lanes at a time patch their world's sub-tile, one bulk store each
+        for (int r = 0; r < 32 / E; ++r) {
+            if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
+            __syncwarp();
+            if (lane / E == r) {
+                const int s = lane - r * E;
+                float* sub = tiles + (size_t)s * ostr;
+                const bool fresh = tags[s] != map_id;
+                if (fresh) {  // another map (or the first use): start from its static plane (observations.py:216-237)
+                    const float* stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
+                    const int obs_floats = w.hdr->obs_floats;
+                    for (int f = 0; f < ostr; f += 4) {
+                        float4 v;
+                        if (f + 3 < obs_floats) v = __ldg(reinterpret_cast<const float4*>(stat + f));
+                        else {
+                            v.x = f + 0 < obs_floats ? __ldg(stat + f + 0) : 0.f; v.y = f + 1 < obs_floats ? __ldg(stat + f + 1) : 0.f;
+                            v.z = f + 2 < obs_floats ? __ldg(stat + f + 2) : 0.f; v.w = f + 3 < obs_floats ? __ldg(stat + f + 3) : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(sub + f) = v;
+                    }
+                    tags[s] = map_id;
+                }
+                w.render(sub, fresh, SmemColumn{applied + s, E}, p.HW);
+                for (int k = 0; k < stride; ++k) applied[k * E + s] = w.rec(k);  // the sub-tile now shows this world
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(p.obs + ((int64_t)ticket * 32 + (int64_t)r * E) * ostr, tiles, (uint32_t)(E * ostr) * 4u);
+                bulk_commit();
+                if (owed && r == 0) {
+                    bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
+                    ticket_release(p.flags + owed_ticket, owed_seq);
+                }
+            }
+        }
+        owed = true; owed_ticket = ticket; owed_seq = my_seq;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        bulk_wait_all();
+        if (owed) ticket_release(p.flags + owed_ticket, owed_seq);
+        launch_epilogue(p, true);
+    }
+}
+
+}  // namespace lle

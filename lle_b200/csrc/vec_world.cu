@@ -15,6 +15,7 @@
 #include "levels_embedded.inc"
 #include "map_compiler.hpp"
 #include "world_kernel.cuh"
+#include "tiny_kernel.cuh"
 
 namespace lle {
 
@@ -91,6 +92,10 @@ struct lle_vec {
     int feature_limit = 0;
     bool by_feature = false;  // partial observations rendered feature by feature (kernel KIND 2): every map has <= 2 s^2 features
     bool force_narrow = false;  // LLE_B200_FORCE_NARROW=1 (tests)
+    // tiny maps: step launches run the thread-per-world kernel (tiny_kernel.cuh) with its own tiling and grid
+    bool tiny = false;
+    int tiny_E = 8, tiny_warp_smem = 0, tiny_grid = 0;
+    size_t tiny_smem = 0;
     uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
     int grid = 0, grid_step = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
@@ -102,14 +107,15 @@ struct lle_vec {
     // pipelined host stepping (lle_vec_pipeline_submit / _wait): three streams, a ring of staging slots
     static constexpr int kPipeSlots = 8;
     bool pipe_ready = false;
-    cudaStream_t s_in = nullptr, s_main = nullptr, s_out = nullptr, last_stream = nullptr;
-    cudaEvent_t ev_user = nullptr, ev_out[kPipeSlots] = {};
+    cudaStream_t s_in = nullptr, s_main = nullptr, last_stream = nullptr;
+    cudaEvent_t ev_user = nullptr;
     int8_t* d_stage[kPipeSlots] = {};
-    float* d_reward_ring[kPipeSlots] = {};
-    uint8_t* d_done_ring[kPipeSlots] = {};
-    uint32_t* d_pipe_flags = nullptr;  // [0] actions of submit n have landed, [1] submit n has retired
+    uint32_t* d_pipe_flags = nullptr;  // [0] actions of submit n have landed (written by the copy stream)
+    uint32_t* h_out_flags = nullptr;   // pinned + mapped, one word per ring slot: submit n has retired and its results are in host memory
+    uint32_t* d_out_flags = nullptr;   // the same words as the device sees them
     uint64_t pipe_submitted = 0, pipe_completed = 0;
-    const void* pinned_seen[32] = {};  // host pointers already checked to be page-locked
+    const void* pinned_seen[32] = {};  // host pointers already checked to be page-locked ...
+    void* pinned_dev[32] = {};         // ... and the address the device reaches them at
     unsigned pinned_next = 0;
 };
 
@@ -144,6 +150,22 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = overlaps ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if constexpr (MODE == MODE_STEP) {
+        if (v->tiny) {  // thread-per-world kernel: same tickets, flags and records, its own tile layout
+            cfg.gridDim = dim3((unsigned)v->tiny_grid);
+            cfg.dynamicSmemBytes = v->tiny_smem;
+            p.n_warps_total = (uint32_t)(v->tiny_grid * kWarps);
+            p.E = v->tiny_E;
+            p.tile_floats = (int32_t)(v->tiny_E * v->obs_stride);
+            p.warp_smem_bytes = v->tiny_warp_smem;
+            switch (v->A) {
+                case 1: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<1>, p);
+                case 2: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<2>, p);
+                case 3: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<3>, p);
+                default: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<4>, p);
+            }
+        }
+    }
     if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 1>, p);
     if (v->by_feature) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 2>, p);
     return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 0>, p);
@@ -252,19 +274,22 @@ KParams base_params(lle_vec* v) {
     return p;
 }
 
-// Whether `ptr` is page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory).  The answers for the
-// last few pointers are remembered: a host loop passes the same ring of buffers over and over.
-bool is_pinned_host(lle_vec* v, const void* ptr) {
-    for (const void* known : v->pinned_seen)
-        if (known == ptr) return true;
+// The device-side address of page-locked host memory (cudaHostAlloc / cudaHostRegister / lle_host_alloc / torch pin_memory), or
+// nullptr when `ptr` is not page-locked.  The answers for the last few pointers are remembered: a host loop passes the same
+// ring of buffers over and over.
+void* device_view(lle_vec* v, const void* ptr) {
+    for (int k = 0; k < 32; ++k)
+        if (v->pinned_seen[k] == ptr) return v->pinned_dev[k];
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        return nullptr;
     }
-    if (attr.type != cudaMemoryTypeHost) return false;
-    v->pinned_seen[v->pinned_next++ % 32] = ptr;
-    return true;
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+    const unsigned k = v->pinned_next++ % 32;
+    v->pinned_seen[k] = ptr;
+    v->pinned_dev[k] = attr.devicePointer;
+    return attr.devicePointer;
 }
 
 template <class T>
@@ -391,15 +416,14 @@ int lle_vec_destroy(lle_vec* v) {
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
     cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline); cudaFree(v->d_extras);
     for (int k = 0; k < lle_vec::kPipeSlots; ++k) {
-        cudaFree(v->d_stage[k]); cudaFree(v->d_reward_ring[k]); cudaFree(v->d_done_ring[k]);
-        if (v->ev_out[k]) cudaEventDestroy(v->ev_out[k]);
+        cudaFree(v->d_stage[k]);
     }
     cudaFree(v->d_pipe_flags);
+    if (v->h_out_flags) cudaFreeHost(v->h_out_flags);
     if (v->h_retired_seq) cudaFreeHost(v->h_retired_seq);
     if (v->ev_user) cudaEventDestroy(v->ev_user);
     if (v->s_in) cudaStreamDestroy(v->s_in);
     if (v->s_main) cudaStreamDestroy(v->s_main);
-    if (v->s_out) cudaStreamDestroy(v->s_out);
     if (v->ev0) cudaEventDestroy(v->ev0);
     if (v->ev1) cudaEventDestroy(v->ev1);
     delete v;
@@ -596,6 +620,32 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         LLE_CUDA((configure_kernel<MODE_SET_STATE, 0>(v->smem, &blocks_per_sm)));
     }
     if (blocks_per_sm < 1) return fail(LLE_CUDA_ERROR, "kernel does not fit on an SM");
+    // Tiny maps (small observation, few agents, a record of at most 8 words): the step runs one thread per world.
+    v->tiny = v->fast && small_obs && v->A <= 4 && v->L.n_words <= 8 && !v->L.wide_flags && v->L.on_words == 1 && v->L.gem_words <= 1 &&
+              v->L.sub_words == 0 && v->group == 32 && !env_int("LLE_B200_NO_TINY", 0);
+    if (v->tiny) {
+        int e = env_int("LLE_B200_TINY_E", v->E);
+        v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 8;
+        size_t bytes = (size_t)v->tiny_E * stride * 4 + (size_t)v->L.stride * 32 * 4 + (size_t)v->L.stride * v->tiny_E * 4 + (size_t)v->tiny_E * 4;
+        v->tiny_warp_smem = (int)((bytes + 127) / 128 * 128);
+        v->tiny_smem = (size_t)v->tiny_warp_smem * kWarps;
+        int tb = 0;
+        auto configure = [&](auto kern) -> cudaError_t {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->tiny_smem);
+            if (e2 != cudaSuccess) return e2;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb, kern, kThreads, v->tiny_smem);
+        };
+        switch (v->A) {
+            case 1: LLE_CUDA(configure(lle_tiny_step_kernel<1>)); break;
+            case 2: LLE_CUDA(configure(lle_tiny_step_kernel<2>)); break;
+            case 3: LLE_CUDA(configure(lle_tiny_step_kernel<3>)); break;
+            default: LLE_CUDA(configure(lle_tiny_step_kernel<4>)); break;
+        }
+        if (tb < 1) v->tiny = false;
+        tb = std::min(tb, std::max(1, env_int("LLE_B200_TINY_CTAS_PER_SM", 16)));
+        const int64_t tickets = v->N_pad / v->group;
+        v->tiny_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)prop.multiProcessorCount * tb, (tickets + kWarps - 1) / kWarps));
+    }
     blocks_per_sm = std::min(blocks_per_sm, std::max(1, env_int("LLE_B200_MAX_CTAS_PER_SM", 16)));
     const int64_t n_tickets = v->N_pad / v->group;
     v->grid = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * blocks_per_sm, (n_tickets + kWarps - 1) / kWarps);
@@ -848,9 +898,35 @@ int lle_vec_rollout(lle_vec* v, int32_t n_steps, void* stream) {
     return LLE_OK;
 }
 
+namespace {
+int pipeline_setup(lle_vec* v) {
+    if (v->pipe_ready) return LLE_OK;
+    LLE_CUDA(resolve_memops());
+    LLE_CUDA(cudaStreamCreateWithFlags(&v->s_in, cudaStreamNonBlocking));
+    LLE_CUDA(cudaStreamCreateWithFlags(&v->s_main, cudaStreamNonBlocking));
+    LLE_CUDA(cudaEventCreateWithFlags(&v->ev_user, cudaEventDisableTiming));
+    for (int k = 0; k < lle_vec::kPipeSlots; ++k) LLE_CUDA(dalloc(&v->d_stage[k], (size_t)v->A * v->N_pad));
+    LLE_CUDA(dalloc(&v->d_pipe_flags, 2));
+    LLE_CUDA(cudaHostAlloc((void**)&v->h_out_flags, lle_vec::kPipeSlots * 32 * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(v->h_out_flags, 0, lle_vec::kPipeSlots * 32 * sizeof(uint32_t));
+    LLE_CUDA(cudaHostGetDevicePointer((void**)&v->d_out_flags, v->h_out_flags, 0));
+    LLE_CUDA(cudaDeviceSynchronize());
+    v->pipe_ready = true;
+    return LLE_OK;
+}
+}  // namespace
+
 int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
     LLE_CUDA(cudaSetDevice(v->device));
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    // pinned buffers: one submit + wait of the pipeline below (one copy, one launch, results written straight to host memory)
+    if ((!actions_host || device_view(v, actions_host)) && (!reward_host || device_view(v, reward_host)) && (!done_host || device_view(v, done_host))) {
+        int rc = lle_vec_pipeline_submit(v, actions_host, reward_host, done_host, stream);
+        if (rc != LLE_OK) return rc;
+        return lle_vec_pipeline_wait(v, nullptr);
+    }
+    // pageable buffers: staged copies on the caller's stream, then a stream synchronisation
     cudaStream_t s = (cudaStream_t)stream;
     const int8_t* dev_actions = nullptr;
     if (actions_host) {
@@ -865,36 +941,33 @@ int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host
     return LLE_OK;
 }
 
+int lle_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    LLE_CUDA(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable | cudaHostAllocMapped));
+    return LLE_OK;
+}
+int lle_host_free(void* ptr) {
+    if (ptr) LLE_CUDA(cudaFreeHost(ptr));
+    return LLE_OK;
+}
+
 int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
     if (v->pipe_submitted - v->pipe_completed >= (uint64_t)lle_vec::kPipeSlots)
         return fail(LLE_INVALID_ARGUMENT, "pipeline full: call lle_vec_pipeline_wait before submitting another step");
     LLE_CUDA(cudaSetDevice(v->device));
-    if (!v->pipe_ready) {
-        LLE_CUDA(resolve_memops());
-        LLE_CUDA(cudaStreamCreateWithFlags(&v->s_in, cudaStreamNonBlocking));
-        LLE_CUDA(cudaStreamCreateWithFlags(&v->s_main, cudaStreamNonBlocking));
-        LLE_CUDA(cudaStreamCreateWithFlags(&v->s_out, cudaStreamNonBlocking));
-        LLE_CUDA(cudaEventCreateWithFlags(&v->ev_user, cudaEventDisableTiming));
-        for (int k = 0; k < lle_vec::kPipeSlots; ++k) {
-            LLE_CUDA(cudaEventCreateWithFlags(&v->ev_out[k], cudaEventDisableTiming));
-            LLE_CUDA(dalloc(&v->d_stage[k], (size_t)v->A * v->N_pad));
-            LLE_CUDA(dalloc(&v->d_reward_ring[k], (size_t)v->R * v->N_pad));
-            LLE_CUDA(dalloc(&v->d_done_ring[k], (size_t)v->N_pad));
-        }
-        LLE_CUDA(dalloc(&v->d_pipe_flags, 2));
-        LLE_CUDA(cudaDeviceSynchronize());
-        v->pipe_ready = true;
-    }
+    if (int rc = pipeline_setup(v)) return rc;
+    // Pinned (page-locked) host buffers are REQUIRED: the step kernel spins on a flag that the copy stream publishes behind the
+    // H2D copy (only a truly asynchronous copy keeps the two streams independent of the calling thread), and it writes reward
+    // and done straight into the host buffers (zero-copy), followed by a completion word the host polls.
+    void* reward_dev = reward_host ? device_view(v, reward_host) : nullptr;
+    void* done_dev = done_host ? device_view(v, done_host) : nullptr;
+    if ((actions_host && !device_view(v, actions_host)) || (reward_host && !reward_dev) || (done_host && !done_dev))
+        return fail(LLE_INVALID_ARGUMENT, "lle_vec_pipeline_submit needs pinned (page-locked) host buffers (lle_host_alloc / cudaHostAlloc / cudaHostRegister)");
     if (v->pipe_submitted == v->pipe_completed) {  // pipeline empty: order it after the caller's stream
         LLE_CUDA(cudaEventRecord(v->ev_user, (cudaStream_t)after_stream));
         LLE_CUDA(cudaStreamWaitEvent(v->s_main, v->ev_user, 0));
     }
-    // Pinned (page-locked) host buffers are REQUIRED: the step kernel spins on a flag that the copy stream publishes behind the
-    // H2D copy, and only a truly asynchronous copy keeps the two streams independent of the calling thread.
-    if ((actions_host && !is_pinned_host(v, actions_host)) || (reward_host && !is_pinned_host(v, reward_host)) ||
-        (done_host && !is_pinned_host(v, done_host)))
-        return fail(LLE_INVALID_ARGUMENT, "lle_vec_pipeline_submit needs pinned (page-locked) host buffers (cudaHostAlloc / cudaHostRegister)");
     // Nothing is committed to the host bookkeeping until the step kernel has been accepted by the stream.
     const uint64_t next = v->pipe_submitted + 1;
     const uint32_t n = (uint32_t)next;
@@ -909,26 +982,15 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
         p.in_flag = v->d_pipe_flags + 0;
         p.in_need = n;
     }
-    p.out_flag = v->d_pipe_flags + 1;
+    p.out_flag = v->d_out_flags + slot * 32;  // one 128-byte line per slot
     p.out_value = n;
-    p.reward2 = v->d_reward_ring[slot];
-    p.done2 = v->d_done_ring[slot];
+    p.reward2 = (float*)reward_dev;
+    p.done2 = (uint8_t*)done_dev;
     LLE_CUDA(launch(v, p, v->s_main));
     v->launches++;
     v->t++;
-    v->pipe_submitted = next;  // the step is in flight from here on; its completion event is recorded whatever follows
-    int rc = LLE_OK;
-    if (g_wait_value32((CUstream)v->s_out, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 1), n, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
-        rc = fail(LLE_CUDA_ERROR, "cuStreamWaitValue32 failed");
-    } else {
-        cudaError_t e = cudaSuccess;
-        if (reward_host) e = cudaMemcpyAsync(reward_host, v->d_reward_ring[slot], (size_t)v->N * v->R * sizeof(float), cudaMemcpyDeviceToHost, v->s_out);
-        if (e == cudaSuccess && done_host) e = cudaMemcpyAsync(done_host, v->d_done_ring[slot], (size_t)v->N, cudaMemcpyDeviceToHost, v->s_out);
-        if (e != cudaSuccess) rc = fail(LLE_CUDA_ERROR, std::string("copy of reward / done to the host: ") + cudaGetErrorString(e));
-    }
-    cudaError_t e = cudaEventRecord(v->ev_out[slot], v->s_out);
-    if (e != cudaSuccess && rc == LLE_OK) rc = fail(LLE_CUDA_ERROR, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
-    return rc;
+    v->pipe_submitted = next;
+    return LLE_OK;
 }
 
 int lle_vec_pipeline_wait(lle_vec* v, int32_t* outstanding) {
@@ -937,9 +999,25 @@ int lle_vec_pipeline_wait(lle_vec* v, int32_t* outstanding) {
         if (outstanding) *outstanding = 0;
         return fail(LLE_INVALID_ARGUMENT, "pipeline empty: nothing to wait for");
     }
-    LLE_CUDA(cudaSetDevice(v->device));
     const int slot = (int)(v->pipe_completed % lle_vec::kPipeSlots);
-    LLE_CUDA(cudaEventSynchronize(v->ev_out[slot]));
+    const uint32_t n = (uint32_t)(v->pipe_completed + 1);
+    volatile uint32_t* flag = v->h_out_flags + slot * 32;
+    // The last warp of the step writes n here after a system-scope fence behind every result byte.  Poll; look at the stream
+    // now and then so that a failed launch surfaces as an error instead of a hang.
+    for (uint64_t spins = 0; (int32_t)(*flag - n) < 0; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xFFFFF) == 0xFFFFF) {
+            cudaSetDevice(v->device);
+            cudaError_t e = cudaStreamQuery(v->s_main);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(LLE_CUDA_ERROR, std::string("step kernel failed: ") + cudaGetErrorString(e));
+            if (e == cudaSuccess && (int32_t)(*flag - n) < 0)  // the stream drained without publishing: should not happen
+                return fail(LLE_CUDA_ERROR, "the step retired without publishing its completion");
+        }
+    }
+    __sync_synchronize();
     v->pipe_completed++;
     if (outstanding) *outstanding = (int32_t)(v->pipe_submitted - v->pipe_completed);
     return LLE_OK;

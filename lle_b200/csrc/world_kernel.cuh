@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include "static_map.h"
+#include "step_common.cuh"
 
 namespace lle {
 
@@ -35,20 +36,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 enum Mode : int { MODE_STEP = 0, MODE_RESET = 1, MODE_SET_STATE = 2 };
-
-// event codes of one agent in one pass (bits 0-1 of the exported event byte)
-enum : uint32_t { EV_NONE = 0, EV_EXIT = 1, EV_GEM = 2, EV_DIED = 3 };
-
-// per-env error codes (LLE_ENV_* of include/lle_b200.h)
-enum : uint32_t {
-    ERR_OK = 0,
-    ERR_INVALID_ACTION = 1,      // RuntimeWorldError::InvalidAction (world.rs:444-453)
-    ERR_DONE = 2,                // "Cannot step in a done environment" (env.py:166-167)
-    ERR_STATE_DUPLICATE = 3,     // world.rs:529-534
-    ERR_STATE_OUT_OF_WORLD = 4,  // world.rs:536-540
-    ERR_STATE_NOT_WALKABLE = 5,  // world.rs:556-568
-    ERR_STATE_MISMATCH = 6,      // world.rs:588-594
-};
 
 struct KParams {
     const uint8_t* const* blobs;  // device array [n_maps] of map blobs
@@ -170,41 +157,6 @@ struct MapDev {
         gem_toplevel = hdr->gem_toplevel;
     }
 };
-
-// beam-entry fields (static_map.h: LleCellBeams)
-__device__ __forceinline__ int be_b(uint32_t e) { return e & 63u; }
-__device__ __forceinline__ int be_k(uint32_t e) { return (e >> 6) & 63u; }
-__device__ __forceinline__ int be_colour(uint32_t e) { return (e >> 12) & 255u; }
-__device__ __forceinline__ int be_len(uint32_t e) { return (e >> 20) & 127u; }
-__device__ __forceinline__ bool be_enabled(uint32_t e) { return (e >> 27) & 1u; }
-__device__ __forceinline__ bool be_listed(uint32_t e) { return (e >> 28) & 1u; }
-
-__device__ __forceinline__ uint64_t len_mask(int len) { return len >= 64 ? ~0ull : ((1ull << len) - 1ull); }
-
-// Action deltas on a packed position (i<<8 | j), src/action.rs:18-26 (N=0, S=1, E=2, W=3, STAY=4)
-__device__ __forceinline__ int act_delta(int a) { return a == 0 ? -256 : a == 1 ? 256 : a == 2 ? 1 : a == 3 ? -1 : 0; }
-
-// ---- Philox4x32-10 action stream -------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t* out) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-// k-th set bit of a 5-bit availability mask, k = mulhi(word, popcount)
-__device__ __forceinline__ uint32_t pick_action(uint32_t word, uint32_t mask) {
-    uint32_t k = __umulhi(word, (uint32_t)__popc(mask & 31u));
-    uint32_t m = mask & 31u;
-    for (uint32_t n = 0; n < k; ++n) m &= m - 1;  // drop the k lowest set bits
-    return m ? (uint32_t)(__ffs(m) - 1) : 4u;
-}
 
 // =============================================================================================================
 // Sub-warp groups: a warp processes P = 32/Wd worlds at once, Wd = the power of two >= n_agents.  Lane
@@ -731,6 +683,27 @@ __device__ __noinline__ int recolour_variant(int32_t* map_of_env, uint64_t env_i
     return next;
 }
 
+// End of a launch, lane 0 of every warp: count the warp out; the last warp re-arms the launch's scheduler slot for a later
+// launch (generation word, see sched_slot_armed) and publishes the launch to the host.  With host-facing stepping
+// (lle_vec_pipeline_submit) reward / done went straight into pinned host memory: every warp fences them at system scope before
+// it is counted, and the last one writes the step number into the slot's completion word, which the host polls.
+__device__ __forceinline__ void launch_epilogue(const KParams& p, bool is_step) {
+    if (p.out_flag) __threadfence_system();
+    else __threadfence();
+    const uint32_t finished = atomicAdd(&p.sched[1], 1u);
+    if (finished == p.n_warps_total - 1) {
+        p.sched[0] = 0;
+        p.sched[1] = 0;
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sched + 2), "r"(p.sched_gen + 1u) : "memory");
+        if (is_step && p.retired_seq) *p.retired_seq = p.seq + (uint32_t)p.n_steps - 1u;
+        if (p.out_flag) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.out_flag), "r"(p.out_value) : "memory");
+        }
+    }
+}
+
 #ifndef LLE_MIN_CTAS
 #define LLE_MIN_CTAS 5
 #endif
@@ -1001,11 +974,11 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                         else v = (float)shaped;  // fifth component of MultiObjective + PBRS (np.concat, :153)
                     }
                     p.reward[env * p.R + r] = v;
-                    if (p.reward2) p.reward2[env * p.R + r] = v;
+                    if (p.reward2 && real) p.reward2[env * p.R + r] = v;  // the host's own buffer: N worlds, no padding
                 }
                 if (gl == 0) {
                     p.done[env] = (uint8_t)w.done;
-                    if (p.done2) p.done2[env] = (uint8_t)w.done;
+                    if (p.done2 && real) p.done2[env] = (uint8_t)w.done;
                     p.err[env] = (uint8_t)err;
                 }
                 if (gl < A) {
@@ -1411,25 +1384,11 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     if (lane == 0) {
         bulk_wait_all();
         if (MODE == MODE_STEP && owed) ticket_release(p.flags + owed_ticket, owed_seq);
-        __threadfence();
+        launch_epilogue(p, MODE == MODE_STEP);
         if (p.timeline) {
             p.timeline[warp_global * 4 + 1] = t_first;
             p.timeline[warp_global * 4 + 2] = t_last;
             p.timeline[warp_global * 4 + 3] = globaltimer_ns();
-        }
-        const uint32_t finished = atomicAdd(&p.sched[1], 1u);
-        if (finished == p.n_warps_total - 1) {  // last warp out re-arms this scheduler slot for a later launch
-            p.sched[0] = 0;
-            p.sched[1] = 0;
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sched + 2), "r"(p.sched_gen + 1u) : "memory");
-            if (MODE == MODE_STEP && p.retired_seq) *p.retired_seq = p.seq + (uint32_t)p.n_steps - 1u;
-            if (p.out_flag) {
-                // every warp fenced its writes before its increment above; publish the launch to the copy stream that
-                // waits on the flag (max: an overlapped later launch may retire first, and implies this one's tickets)
-                __threadfence_system();
-                atomicMax_system(p.out_flag, p.out_value);
-            }
         }
     }
 }

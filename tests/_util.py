@@ -9,52 +9,10 @@ def level_text(n: int) -> str:
 
 
 def synthetic_map(h: int, w: int, n_agents: int, n_sources: int, seed: int = 0, n_gems: int | None = None) -> str:
-    """Seeded synthetic map in the v1 grammar (BASELINE config 5): border-free grid, starts on the first row,
-    exits on the last row, laser sources of mixed colours and directions placed so that every beam is at most
-    63 cells long and never crosses a start tile, a few walls and gems."""
-    import random
+    """The seeded synthetic map of BASELINE config 5 (lle_b200/workloads.py: a text generator, no device work)."""
+    from lle_b200.workloads import synthetic_map as make
 
-    rng = random.Random(seed)
-    grid = [["." for _ in range(w)] for _ in range(h)]
-    start_cols = rng.sample(range(2, w - 2), n_agents)
-    for a, j in enumerate(start_cols):
-        grid[0][j] = f"S{a}"
-    exit_cols = rng.sample(range(2, w - 2), n_agents)
-    for j in exit_cols:
-        grid[h - 1][j] = "X"
-    used_rows, used_cols = {0, h - 1}, set(start_cols) | set(exit_cols)
-    placed = 0
-    attempts = 0
-    while placed < n_sources and attempts < 10000:
-        attempts += 1
-        colour = placed % n_agents
-        if rng.random() < 0.5:  # horizontal beam on a free row
-            i = rng.randrange(2, h - 2)
-            if i in used_rows:
-                continue
-            used_rows.add(i)
-            if rng.random() < 0.5:
-                grid[i][0] = f"L{colour}E"
-            else:
-                grid[i][w - 1] = f"L{colour}W"
-            # a wall somewhere keeps the beam <= 63 cells on 64-wide maps
-            grid[i][rng.randrange(w // 2, w - 1) if grid[i][0].startswith("L") else rng.randrange(1, w // 2)] = "@"
-        else:  # vertical beam on a free column, starting below the start row
-            j = rng.randrange(1, w - 1)
-            if j in used_cols:
-                continue
-            used_cols.add(j)
-            grid[1][j] = f"L{colour}S"
-            grid[rng.randrange(h // 2, h - 1)][j] = "@"
-        placed += 1
-    free = [(i, j) for i in range(1, h - 1) for j in range(w) if grid[i][j] == "."]
-    rng.shuffle(free)
-    n_gems = n_agents if n_gems is None else n_gems
-    for i, j in free[:n_gems]:
-        grid[i][j] = "G"
-    for i, j in free[n_gems : n_gems + (h * w) // 40]:
-        grid[i][j] = "@"
-    return "\n".join(" ".join(f"{t:>4}" for t in row) for row in grid)
+    return make(h, w, n_agents, n_sources, seed, n_gems)
 
 
 def rollout_digest(x) -> list[int]:
@@ -118,4 +76,21 @@ def build_gen_host_shim() -> str:
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(out_dir, exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", out], check=True)
+    return out
+
+
+def build_tiny_host_shim() -> str:
+    """g++ build of tests/host_shim/tiny_host.cpp: the per-world core of the tiny-map step kernel (lle_b200/csrc/tiny_core.cuh,
+    __host__ __device__) plus the product's host map compiler, for the CPU test-suite.  Test infrastructure only."""
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), "lle_b200", "csrc")
+    srcs = [os.path.join(here, "host_shim", "tiny_host.cpp"), os.path.join(csrc, "map_compiler.cpp"), os.path.join(csrc, "toml_config.cpp")]
+    out_dir = os.path.join(here, "host_shim", "_build")
+    out = os.path.join(out_dir, "libtiny_host.so")
+    deps = srcs + [os.path.join(csrc, f) for f in ("tiny_core.cuh", "step_common.cuh", "static_map.h", "map_compiler.hpp", "toml_lite.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++"] + srcs + ["-o", out], check=True)
     return out

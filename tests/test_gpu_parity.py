@@ -712,3 +712,51 @@ def test_lle_facade_accessors(tmp_path):
     for lvl in range(1, 7):
         lle_b200.level(lvl).build()
     lle_b200.from_file(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "levels", "lvl1")).build()
+
+
+def test_many_small_launches_in_flight():
+    """A batch of one ticket: every step launch is a single CTA, so dozens of programmatically dependent launches are resident
+    at once and the rotating scheduler slots are reused while their previous users still run (the slot generation word orders
+    them).  Free-running for 4,000 steps, then every output against the oracle; and the same through rollout launches."""
+    import lle_b200
+
+    text = level_text(6)
+    for n in (8, 64, 300):
+        vec = lle_b200.VecWorld(text, n, seed=31)
+        roll = lle_b200.VecWorld(text, n, seed=31)
+        ora = lo.OracleVec([text], None, n, seed=31)
+        for _ in range(4000):
+            vec.step(None)
+        for k in (1000, 1000, 2000):
+            roll.rollout(k)
+        for _ in range(4000):
+            ora.step(None)
+        d = Dev(vec)
+        assert_same(d, ora, d.pull(), f"{n} envs, 4000 free-running steps")
+        d = Dev(roll)
+        assert_same(d, ora, d.pull(), f"{n} envs, rollout launches")
+
+
+def test_dlpack_round_trip():
+    """north_star: the batch is exposed as zero-copy DLPack / torch tensors.  torch.from_dlpack on the capsule of every buffer
+    aliases the device buffer the kernel writes (same pointer; a step shows through the imported tensor)."""
+    import lle_b200
+
+    env = lle_b200.level(6).n_envs(256).seed(5).build()
+    env.reset()
+    imported = {name: torch.from_dlpack(env.dlpack(name)) for name in ("obs", "state", "available_actions", "reward", "done", "events", "actions")}
+    for name, t in imported.items():
+        src = getattr(env, name)
+        assert t.data_ptr() == src.data_ptr() and t.shape == src.shape and t.dtype == src.dtype and t.device == src.device, name
+    before = imported["state"].clone()
+    for _ in range(5):
+        env.step(None)
+    torch.cuda.synchronize()
+    assert not torch.equal(before, imported["state"])            # the imported tensor sees the kernel's writes
+    assert torch.equal(imported["obs"], env.obs) and torch.equal(imported["state"], env.state)
+    # numpy-style consumers on the host side of DLPack: a CPU copy round-trips through the protocol too
+    host = torch.from_dlpack(env.state.cpu().__dlpack__())
+    assert torch.equal(host, env.state.cpu())
+    # the per-agent view (np.tile in the reference) is a stride-0 expand of the same memory
+    per_agent = env.obs_per_agent
+    assert per_agent.data_ptr() == env.obs.data_ptr() and per_agent.stride(1) == 0
