@@ -152,6 +152,11 @@ typedef struct {
      * precompiled map variant), no laser across a start position and source colours < n_agents; excludes lle_vec_set_source
      * and lle_vec_set_exits. */
     int32_t randomize_lasers;
+    /* LLE(state_type=...) / Builder.state_type (python/lle/env/builder.py:51-58, env.py:86, :205-206): the observation generator
+     * whose first-agent observation is the environment's *state*.  Default LLE_OBS_STATE / 0 (the state vector, lle_vec_buffers.state).
+     * Any other type adds a second observation buffer (lle_vec_buffers.state_obs), rendered from the same engine records by a
+     * second launch after every step / reset / set_state; step launches then run strictly one after the other. */
+    int32_t state_type, state_param;
     int32_t pad_options;
 } lle_vec_options;
 enum { LLE_OBS_LAYERED = 0, LLE_OBS_PARTIAL = 1, LLE_OBS_PERSPECTIVE = 2, LLE_OBS_STATE = 3 };
@@ -205,6 +210,12 @@ typedef struct {
                                        map * n_variants + colouring, colouring = sum over sources b of colour_b * n_agents^b */
     int32_t n_variants;             /* colourings per map (1 without randomize_lasers) */
     int32_t pad3;
+    /* state_type other than the state vector: one block per env laid out like `obs` for that type (NULL otherwise).  The
+     * reference's state is the FIRST agent's observation (observations.py:118-119): the block itself when state_view_agents > 0,
+     * else its first (state_c, state_h, state_w) part. */
+    float* state_obs;
+    int64_t state_obs_stride;
+    int32_t state_type, state_param, state_view_agents, state_c, state_h, state_w;
 } lle_vec_buffers;
 LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 
@@ -292,6 +303,31 @@ LLE_API int lle_vec_set_state(lle_vec* vec, const int32_t* pos_dev, const uint8_
  *   beam_on u64[N,n_beams_max] (bit k = LaserBeam.beam[k], laser.rs:16); collected u64[N]; counters u8[N,3] = n_arrived, n_deads, done */
 LLE_API int lle_vec_export_raw(lle_vec* vec, int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
                        uint64_t* collected, uint8_t* counters, void* cuda_stream);
+
+/* The whole engine record, for checkpoints: lle_vec_export_raw plus the World::available_actions cache (world.rs:37, one 5-bit
+ * mask per agent, bit = Action value) and the LaserSubgoal / PotentialShapedLLE flags (bit b = source b), and its inverse.
+ * A batch re-created with the same maps and options, given lle_vec_import_raw_state(exported arrays), the step count
+ * (lle_vec_set_step_count), the reset count (lle_vec_set_reset_count) and - with randomize_lasers - the map_index buffer,
+ * continues bit-identically (the reference's WorldState alone cannot: it drops beam bits, slots and arrivals, world.rs:507-513).
+ * Export: any pointer may be NULL.  Import: every array of a feature the vec uses is required; observation / state /
+ * availability buffers are re-exported from the imported records (lle_vec_refresh).  Device pointers. */
+typedef struct {
+    int16_t* pos;              /* i16[N,A,2] */
+    uint8_t* alive;            /* u8[N,A] */
+    uint8_t* arrived;          /* u8[N,A] */
+    uint8_t* slot;             /* u8[N,A] */
+    uint64_t* beam_on;         /* u64[N,n_beams_max] */
+    uint64_t* collected;       /* u64[N] */
+    uint8_t* counters;         /* u8[N,3] n_arrived, n_deads (saturating), done */
+    uint8_t* avail_cache;      /* u8[N,A] */
+    uint64_t* subgoals_extras; /* u64[N,A] */
+    uint64_t* subgoals_pbrs;   /* u64[N,A] */
+} lle_raw_state;
+LLE_API int lle_vec_export_raw_state(lle_vec* vec, const lle_raw_state* dst, void* cuda_stream);
+LLE_API int lle_vec_import_raw_state(lle_vec* vec, const lle_raw_state* src, void* cuda_stream);
+/* Number of explicit resets so far: a word of the start-sampling / laser-recolouring Philox counters (see lle_vec_reset). */
+LLE_API int lle_vec_get_reset_count(lle_vec* vec, uint32_t* out);
+LLE_API int lle_vec_set_reset_count(lle_vec* vec, uint32_t value);
 
 /* World::seed (world.rs:92-96): the Philox key of the action sampler and of the start sampler. */
 LLE_API int lle_vec_set_seed(lle_vec* vec, uint64_t seed);

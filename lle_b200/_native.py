@@ -20,7 +20,8 @@ SYMBOLS = [
     "lle_vec_destroy", "lle_vec_get_buffers", "lle_vec_reset", "lle_vec_refresh", "lle_vec_step", "lle_vec_rollout", "lle_vec_step_host", "lle_vec_pipeline_submit",
     "lle_vec_pipeline_wait", "lle_vec_set_source", "lle_vec_get_sources", "lle_vec_set_exits", "lle_vec_collect_gem", "lle_vec_set_state",
     "lle_vec_export_raw", "lle_vec_set_seed", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
-    "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline", "lle_host_alloc", "lle_host_free",
+    "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline", "lle_host_alloc", "lle_host_free", "lle_vec_export_raw_state", "lle_vec_import_raw_state",
+    "lle_vec_get_reset_count", "lle_vec_set_reset_count",
     "lle_gen_default_options", "lle_gen_create", "lle_gen_destroy", "lle_gen_attempt_seeds", "lle_gen_run", "lle_gen_get_buffers",
     "lle_gen_fetch", "lle_gen_geometry_valid", "lle_gen_cells_to_text",
 ]
@@ -37,7 +38,7 @@ class VecOptions(C.Structure):
         ("seed", C.c_uint64), ("env_id_base", C.c_uint64), ("n_extras", C.c_int32), ("extras_src", C.c_int32 * 64),
         ("pbrs", C.c_int32), ("n_pbrs", C.c_int32), ("pbrs_src", C.c_int32 * 64), ("pbrs_gamma", C.c_double),
         ("pbrs_reward_value", C.c_double), ("obs_type", C.c_int32), ("obs_param", C.c_int32), ("randomize_lasers", C.c_int32),
-        ("pad_options", C.c_int32)]
+        ("state_type", C.c_int32), ("state_param", C.c_int32), ("pad_options", C.c_int32)]
 
 
 class VecBuffers(C.Structure):
@@ -46,7 +47,13 @@ class VecBuffers(C.Structure):
         ("obs_stride", C.c_int64), ("obs", C.c_void_p), ("state", C.c_void_p), ("avail", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("events", C.c_void_p), ("actions", C.c_void_p), ("err", C.c_void_p), ("record_bytes", C.c_int64), ("extras", C.c_void_p), ("extras_dim", C.c_int32), ("pad", C.c_int32)] + [
         (n, C.c_int32) for n in ("obs_type", "obs_param", "obs_view_agents", "obs_c", "obs_h", "obs_w", "obs_invalid", "pad2")] + [
-        ("map_index", C.c_void_p), ("n_variants", C.c_int32), ("pad3", C.c_int32)]
+        ("map_index", C.c_void_p), ("n_variants", C.c_int32), ("pad3", C.c_int32), ("state_obs", C.c_void_p), ("state_obs_stride", C.c_int64)] + [
+        (n, C.c_int32) for n in ("state_type", "state_param", "state_view_agents", "state_c", "state_h", "state_w")]
+
+
+class RawState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pos", "alive", "arrived", "slot", "beam_on", "collected", "counters", "avail_cache",
+                                          "subgoals_extras", "subgoals_pbrs")]
 
 
 class GenOptions(C.Structure):
@@ -113,6 +120,10 @@ def lib():
     L.lle_vec_timing_begin.argtypes = [C.c_void_p, C.c_void_p]
     L.lle_vec_timing_end.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     L.lle_vec_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.lle_vec_export_raw_state.argtypes = [C.c_void_p, C.POINTER(RawState), C.c_void_p]
+    L.lle_vec_import_raw_state.argtypes = [C.c_void_p, C.POINTER(RawState), C.c_void_p]
+    L.lle_vec_get_reset_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.lle_vec_set_reset_count.argtypes = [C.c_void_p, C.c_uint32]
     L.lle_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.lle_host_free.argtypes = [C.c_void_p]
     L.lle_gen_default_options.argtypes = [C.POINTER(GenOptions)]

@@ -238,35 +238,16 @@ struct TinyWorld {
         }
     }
 
-    // ---- layered observation (observations.py:254-266) of this world in `sub`, a block of obs_stride floats that last showed
-    // the record `Old` (an accessor like Rec) of a world of the same map; `fresh`: the block was just copied from the map's
-    // static plane (nothing to un-patch).  HW = H*W.
-    LLE_HD bool lit(const LlePatch& pe) { return lit_word(pe, rec(pe.src == 0xFF ? L.w_gems : L.w_on + pe.src)); }
-    static LLE_HD bool lit_word(const LlePatch& pe, uint32_t w) {
-        // a laser cell is lit while its beam bit is on, a gem while it is NOT collected (observations.py:256-263)
-        return (((w >> pe.bit) & 1u) != 0) != (pe.src == 0xFF);
-    }
-    template <class Old>
-    LLE_HD void render(float* sub, bool fresh, Old old, int HW) {
+    // ---- layered observation (observations.py:254-266) of this world in `sub`, a block of obs_stride floats that holds a
+    // copy of the map's static plane (walls, voids, exits, sources: observations.py:216-237).  HW = H*W.
+    // A laser cell is lit while its beam bit is on, a gem while it is NOT collected (:256-263); then the agents (:264-265).
+    LLE_HD void render(float* sub, int HW) {
         const LlePatch* patches = reinterpret_cast<const LlePatch*>(blob + hdr->patch_off);
         const int n_patch = hdr->n_patch;
-        if (!fresh) {  // un-patch what the previous occupant had lit and this world has not; clear its agents' cells
-            for (int k = 0; k < n_patch; ++k) {
-                const LlePatch pe = patches[k];
-                if (lit_word(pe, old(pe.src == 0xFF ? L.w_gems : L.w_on + pe.src)) && !lit(pe)) sub[pe.idx] = (float)pe.stat;
-            }
-            LLE_UNROLL
-            for (int a = 0; a < A_; ++a) {
-                const uint32_t w = old(a >> 1);
-                const uint32_t op = (a & 1) ? (w >> 16) : (w & 0xFFFFu);
-                sub[a * HW + (int)(op >> 8) * W + (int)(op & 0xFFu)] = 0.0f;  // agent planes have no static content
-            }
-        }
-        // every lit entry is rewritten (entries may alias one cell: crossing beams of one colour, colours >= n_agents), then
-        // the agents (observations.py:264-265)
         for (int k = 0; k < n_patch; ++k) {
             const LlePatch pe = patches[k];
-            if (lit(pe)) sub[pe.idx] = 1.0f;
+            const uint32_t w = rec(pe.src == 0xFF ? L.w_gems : L.w_on + pe.src);
+            if ((((w >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;
         }
         LLE_UNROLL
         for (int a = 0; a < A_; ++a) sub[a * HW + (int)(pos[a] >> 8) * W + (int)(pos[a] & 0xFFu)] = 1.0f;

@@ -9,8 +9,10 @@
 //     enter, repeated while somebody died (world.rs:454-505) — with positions, flags and events in registers and the beam /
 //     gem masks in a lane-private column of shared memory (dynamic index by beam): no ballots, no shuffles, no predicated
 //     phases, and 32 worlds advance per warp pass instead of 32 / Wd;
-//   * a lane patches ITS world's sub-tile of the warp's observation tile (un-patch what the previous occupant had lit, patch
-//     what this one lights, move the agents' one-hots), E lanes at a time, and the tile leaves with one TMA bulk store;
+//   * the observation tile of E worlds is rebuilt from the maps' static planes by the whole warp with asynchronous 16-byte
+//     copies (a warp meets another map with nearly every ticket of a heterogeneous batch, so there is nothing to un-patch),
+//     then E lanes patch their own world's sub-tile (lit laser cells, uncollected gems, the agents' one-hots) and the tile
+//     leaves with one TMA bulk store;
 //   * every lane follows its own map (blob pointer per lane), so heterogeneous batches need no uniformity checks.
 // Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
 // per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
@@ -60,10 +62,6 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
     float* tiles = reinterpret_cast<float*>(wbase);                                  // [E][ostr]: E worlds per bulk store
     uint32_t* srec = reinterpret_cast<uint32_t*>(tiles + p.tile_floats);             // [stride][32]: word k of lane l at k*32+l
-    uint32_t* applied = srec + stride * 32;                                          // [stride][E]: the record each sub-tile shows
-    int32_t* tags = reinterpret_cast<int32_t*>(applied + stride * E);                // [E]: the map each sub-tile was built from
-    for (int k = lane; k < E; k += 32) tags[k] = -1;
-    __syncwarp();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
         if (lane == 0)
@@ -200,31 +198,31 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         __syncwarp();
 
-        // ---- layered observation (observations.py:254-266): E lanes at a time patch their world's sub-tile, one bulk store each
+        // ---- layered observation (observations.py:254-266), E worlds per bulk store
+        const float* my_stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
+        const int obs_floats = w.hdr->obs_floats;  // C*H*W: the same for every map of the batch
         for (int r = 0; r < 32 / E; ++r) {
             if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
             __syncwarp();
-            if (lane / E == r) {
-                const int s = lane - r * E;
-                float* sub = tiles + (size_t)s * ostr;
-                const bool fresh = tags[s] != map_id;
-                if (fresh) {  // another map (or the first use): start from its static plane (observations.py:216-237)
-                    const float* stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
-                    const int obs_floats = w.hdr->obs_floats;
-                    for (int f = 0; f < ostr; f += 4) {
+            // every sub-tile starts from the static plane of its world's map (observations.py:216-237): the warp copies them
+            for (int s2 = 0; s2 < E; ++s2) {
+                const uint64_t sp = __shfl_sync(kFull, (uint64_t)(uintptr_t)my_stat, r * E + s2);
+                const float* stat = reinterpret_cast<const float*>((uintptr_t)sp);
+                float* sub2 = tiles + (size_t)s2 * ostr;
+                for (int f = lane * 4; f < ostr; f += 128) {
+                    if (f + 3 < obs_floats) {
+                        cp_async16(sub2 + f, stat + f);
+                    } else {  // the padding behind C*H*W (a multiple of 4 floats per block)
                         float4 v;
-                        if (f + 3 < obs_floats) v = __ldg(reinterpret_cast<const float4*>(stat + f));
-                        else {
-                            v.x = f + 0 < obs_floats ? __ldg(stat + f + 0) : 0.f; v.y = f + 1 < obs_floats ? __ldg(stat + f + 1) : 0.f;
-                            v.z = f + 2 < obs_floats ? __ldg(stat + f + 2) : 0.f; v.w = f + 3 < obs_floats ? __ldg(stat + f + 3) : 0.f;
-                        }
-                        *reinterpret_cast<float4*>(sub + f) = v;
+                        v.x = f + 0 < obs_floats ? __ldg(stat + f + 0) : 0.f; v.y = f + 1 < obs_floats ? __ldg(stat + f + 1) : 0.f;
+                        v.z = f + 2 < obs_floats ? __ldg(stat + f + 2) : 0.f; v.w = f + 3 < obs_floats ? __ldg(stat + f + 3) : 0.f;
+                        *reinterpret_cast<float4*>(sub2 + f) = v;
                     }
-                    tags[s] = map_id;
                 }
-                w.render(sub, fresh, SmemColumn{applied + s, E}, p.HW);
-                for (int k = 0; k < stride; ++k) applied[k * E + s] = w.rec(k);  // the sub-tile now shows this world
             }
+            cp_async_wait_all();
+            __syncwarp();
+            if (lane / E == r) w.render(tiles + (size_t)(lane - r * E) * ostr, p.HW);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {

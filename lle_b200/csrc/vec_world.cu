@@ -41,6 +41,10 @@ struct lle_map {
 
 struct lle_vec {
     lle_vec_options opts;
+    // LLE(state_type=...): a second vec over the SAME engine records (and map indices), created for the state's observation
+    // type; it never steps, it only re-exports (lle_vec_refresh) after every launch of this one
+    lle_vec* shadow = nullptr;
+    bool borrows_records = false;  // this vec is somebody's shadow: records / map indices belong to the owner
     int device = 0;
     int64_t N = 0, N_pad = 0;
     int A = 0, G = 0, NBmax = 0, C = 0, H = 0, W = 0, S = 0, R = 1, max_beam_len = 0;
@@ -98,6 +102,7 @@ struct lle_vec {
     size_t tiny_smem = 0;
     uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
+    int narrow_depth = 1;      // step launches in flight from which the narrow grid is used (LLE_B200_NARROW_DEPTH)
     int grid = 0, grid_step = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
     size_t smem = 0;
     uint64_t t = 0, launches = 0;
@@ -180,12 +185,13 @@ cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
         case MODE_STEP:
             p.seq = v->seq + 1;  // sequence number of the first step of this launch
             p.retired_seq = v->h_retired_seq;
-            // Narrow-grid software pipelining pays only when several step launches are queued behind one another (a
-            // free-running device loop, or a host pipeline six or more deep): four consecutive launches are then resident
-            // together and more wait behind them.  With fewer in flight (synchronous stepping, a shallow pipeline) the
-            // device would idle between narrow launches, so the full-width grid is used (measured, e2e env-steps/s at
-            // pipeline depth 2/4/6/8: 7.9e8 / 6.2e8 with narrow grids at depth 4 / 8.4e8 / 8.4e8).
-            v->narrow_next = v->force_narrow || (int32_t)(v->seq - *(volatile uint32_t*)v->h_retired_seq) >= 5;
+            // Narrow-grid software pipelining: a step that finds its predecessor still in flight runs on a grid of
+            // `grid_step` CTAs (two per SM for large observations), so that two or three consecutive launches are resident at once
+            // and the next step's prologue and first tickets overlap this step's tail.  A step that finds the device idle
+            // (synchronous stepping, a policy between two steps) takes the full-width grid: alone, a narrow launch cannot
+            // saturate HBM.  Measured on B200, level 6 x 65,536, us/step in windows of 20 / 2,000 launches after a sync, CTAs per
+            // SM 1 / 2 / 3 / 5: 81.6 / 79.4 / 80.6 / 83.6 and 75.6 / 76.3 / 78.6 / 82.3 (profiles/grid_sweep_r02.jsonl).
+            v->narrow_next = v->force_narrow || (int32_t)(v->seq - *(volatile uint32_t*)v->h_retired_seq) >= v->narrow_depth;
             e = launch_mode<MODE_STEP>(v, p, s);
             if (e != cudaSuccess) return e;
             v->launch_index++;
@@ -303,6 +309,26 @@ int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 }  // namespace
 
+namespace {
+template <bool IMPORT>
+int raw_state_launch(lle_vec* v, const RawState& r, void* stream) {
+    LLE_CUDA(cudaSetDevice(v->device));
+    const int threads = 128;
+    const int blocks = (int)((v->N + threads - 1) / threads);
+    lle_raw_state_kernel<IMPORT><<<blocks, threads, 0, (cudaStream_t)stream>>>(v->d_records, v->L, v->N, v->A, v->NBmax, r);
+    LLE_CUDA(cudaGetLastError());
+    v->launches++;
+    return LLE_OK;
+}
+RawState raw_of(const lle_raw_state* s, int n_beams) {
+    RawState r;
+    r.pos = s->pos; r.alive = s->alive; r.arrived = s->arrived; r.slot = s->slot; r.beam_on = n_beams ? s->beam_on : nullptr;
+    r.collected = s->collected; r.counters = s->counters; r.avail_cache = s->avail_cache;
+    r.sub_extras = s->subgoals_extras; r.sub_pbrs = s->subgoals_pbrs;
+    return r;
+}
+}  // namespace
+
 extern "C" {
 
 const char* lle_last_error(void) { return g_error.c_str(); }
@@ -405,11 +431,14 @@ void lle_vec_default_options(lle_vec_options* o) {
     o->device = 0; o->reward_dim = 1; o->walkable_lasers = 1; o->auto_reset = 1; o->lle_semantics = 1; o->write_obs = 1;
     o->seed = 0; o->env_id_base = 0;
     o->n_extras = 0; o->pbrs = 0; o->n_pbrs = -1; o->pbrs_gamma = 0.99; o->pbrs_reward_value = 0.5;  // Builder.pbrs defaults (builder.py:79-80)
+    o->state_type = LLE_OBS_STATE; o->state_param = 0;  // ObservationType.STATE (builder.py:22)
 }
 
 int lle_vec_destroy(lle_vec* v) {
     if (!v) return LLE_OK;
     cudaSetDevice(v->device);
+    if (v->shadow) lle_vec_destroy(v->shadow);
+    if (v->borrows_records) { v->d_records = nullptr; v->d_map_of_env = nullptr; }
     for (auto* b : v->d_blobs) cudaFree(b);
     for (auto* b : v->retired_blobs) cudaFree(b);
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
@@ -592,6 +621,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->smem = (size_t)v->warp_smem * kWarps;
     v->pdl = env_int("LLE_B200_PDL", 1) != 0;
     v->force_narrow = env_int("LLE_B200_FORCE_NARROW", 0) != 0;
+    v->narrow_depth = std::max(1, env_int("LLE_B200_NARROW_DEPTH", 1));
     int max_patch = 0;
     for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)cms[k]->header().n_patch);
     for (const auto& m : v->variant_maps) max_patch = std::max(max_patch, (int)m.header().n_patch);
@@ -626,7 +656,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (v->tiny) {
         int e = env_int("LLE_B200_TINY_E", v->E);
         v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 8;
-        size_t bytes = (size_t)v->tiny_E * stride * 4 + (size_t)v->L.stride * 32 * 4 + (size_t)v->L.stride * v->tiny_E * 4 + (size_t)v->tiny_E * 4;
+        size_t bytes = (size_t)v->tiny_E * stride * 4 + (size_t)v->L.stride * 32 * 4;  // the tile + the records' columns
         v->tiny_warp_smem = (int)((bytes + 127) / 128 * 128);
         v->tiny_smem = (size_t)v->tiny_warp_smem * kWarps;
         int tb = 0;
@@ -653,7 +683,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     {
         // measured on B200 (us/step, 1 CTA per SM vs the full grid): level 6 x 65,536: 76.5 vs 81.4; level 1: 49.7 vs 54.0;
         // 1,024 generated 5x5 maps x 1,024 (instruction-bound, 445 us steps): 467 vs 445 -> tiny observations keep the full grid
-        const int step_ctas = std::max(1, std::min(blocks_per_sm, env_int("LLE_B200_STEP_CTAS_PER_SM", small_obs ? blocks_per_sm : 1)));
+        const int step_ctas = std::max(1, std::min(blocks_per_sm, env_int("LLE_B200_STEP_CTAS_PER_SM", small_obs ? blocks_per_sm : 2)));
         v->grid_step = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * step_ctas, (n_tickets + kWarps - 1) / kWarps);
         v->grid_step = std::max(v->grid_step, 1);
     }
@@ -716,6 +746,27 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->creating = false;
     if (rc != LLE_OK) return rc;
     LLE_CUDA(cudaDeviceSynchronize());
+    if (opts->state_type != LLE_OBS_STATE || opts->state_param != 0) {
+        lle_vec_options so = *opts;
+        so.obs_type = opts->state_type; so.obs_param = opts->state_param;
+        so.state_type = LLE_OBS_STATE; so.state_param = 0;
+        so.write_obs = 1;
+        lle_vec* sh = nullptr;
+        if (int rc2 = lle_vec_create(maps, n_maps, map_of_env, n_envs, &so, &sh)) return rc2;
+        if (sh->L.stride != v->L.stride || sh->N_pad != v->N_pad || (sh->d_map_of_env == nullptr) != (v->d_map_of_env == nullptr)) {
+            lle_vec_destroy(sh);
+            return fail(LLE_INVALID_ARGUMENT, "state_type: record layouts differ");
+        }
+        cudaFree(sh->d_records);
+        cudaFree(sh->d_map_of_env);
+        sh->d_records = v->d_records;
+        sh->d_map_of_env = v->d_map_of_env;
+        sh->borrows_records = true;
+        v->shadow = sh;
+        v->pdl = false;  // the re-export launch sits between two steps: they cannot overlap programmatically
+        if (int rc2 = lle_vec_refresh(sh, nullptr)) return rc2;
+        LLE_CUDA(cudaDeviceSynchronize());
+    }
     *out = v.release();
     return LLE_OK;
 }
@@ -738,6 +789,16 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->obs_invalid = v->obs_invalid;
     out->map_index = v->d_map_of_env;
     out->n_variants = v->n_variants;
+    if (v->shadow) {
+        const lle_vec* sh = v->shadow;
+        out->state_obs = sh->d_obs; out->state_obs_stride = sh->obs_stride;
+        out->state_type = sh->opts.obs_type; out->state_param = sh->opts.obs_param;
+        out->state_view_agents = sh->hdr0.view_agents;
+        out->state_c = sh->hdr0.obs_c; out->state_h = sh->hdr0.obs_h; out->state_w = sh->hdr0.obs_w;
+        if (sh->obs_invalid) out->obs_invalid = 1;
+    } else {
+        out->state_type = LLE_OBS_STATE;
+    }
     return LLE_OK;
 }
 
@@ -792,6 +853,8 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
     if (agent_id >= 0) next[(size_t)source_index].colour = agent_id;
     const bool was_enabled = st[(size_t)source_index].enabled;
     if (enabled >= 0) next[(size_t)source_index].enabled = enabled != 0;
+    if (v->shadow)
+        if (int rc2 = lle_vec_set_source(v->shadow, map_index, source_index, agent_id, enabled, stream)) return rc2;
     cudaStream_t s = (cudaStream_t)stream;
     CompiledMap cm;
     int rc = swap_map(v, map_index, next, v->map_exits_set[(size_t)map_index] ? &v->map_exits[(size_t)map_index] : nullptr, s, &cm);
@@ -829,6 +892,8 @@ int lle_vec_set_exits(lle_vec* v, int32_t map_index, const int32_t* exits_ij, in
     if (n_exits < 0 || (n_exits > 0 && !exits_ij)) return fail(LLE_INVALID_ARGUMENT, "bad exit list");
     if (v->randomize) return fail(LLE_INVALID_ARGUMENT, "the exit setter is not available together with randomize_lasers");
     if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->shadow)
+        if (int rc2 = lle_vec_set_exits(v->shadow, map_index, exits_ij, n_exits, stream)) return rc2;
     std::vector<Cell> exits;
     for (int k = 0; k < n_exits; ++k) exits.push_back(Cell{exits_ij[2 * k], exits_ij[2 * k + 1]});
     int rc = swap_map(v, map_index, v->src_state[(size_t)map_index], &exits, (cudaStream_t)stream, nullptr);
@@ -837,6 +902,13 @@ int lle_vec_set_exits(lle_vec* v, int32_t map_index, const int32_t* exits_ij, in
     v->map_exits_set[(size_t)map_index] = 1;
     return LLE_OK;
 }
+
+// LLE(state_type=...): after every launch that changes the records, the shadow re-exports the state's observation
+#define LLE_SYNC_SHADOW(v, stream)                                          \
+    do {                                                                    \
+        if ((v)->shadow)                                                    \
+            if (int _rc = lle_vec_refresh((v)->shadow, (void*)(stream))) return _rc; \
+    } while (0)
 
 int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
@@ -848,6 +920,7 @@ int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
     p.reset_mask = mask_dev;
     LLE_CUDA(launch(v, p, (cudaStream_t)stream));
     v->launches++;
+    LLE_SYNC_SHADOW(v, stream);
     return LLE_OK;
 }
 
@@ -860,6 +933,7 @@ int lle_vec_refresh(lle_vec* v, void* stream) {
     p.refresh_only = 1;
     LLE_CUDA(launch(v, p, (cudaStream_t)stream));
     v->launches++;
+    LLE_SYNC_SHADOW(v, stream);
     return LLE_OK;
 }
 
@@ -873,6 +947,7 @@ int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
     LLE_CUDA(launch(v, p, (cudaStream_t)stream));
     v->launches++;
     v->t++;
+    LLE_SYNC_SHADOW(v, stream);
     return LLE_OK;
 }
 
@@ -895,6 +970,7 @@ int lle_vec_rollout(lle_vec* v, int32_t n_steps, void* stream) {
         v->t += (uint64_t)k;
         left -= k;
     }
+    LLE_SYNC_SHADOW(v, stream);
     return LLE_OK;
 }
 
@@ -990,6 +1066,7 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
     v->launches++;
     v->t++;
     v->pipe_submitted = next;
+    LLE_SYNC_SHADOW(v, v->s_main);
     return LLE_OK;
 }
 
@@ -1032,21 +1109,38 @@ int lle_vec_set_state(lle_vec* v, const int32_t* pos_dev, const uint8_t* gems_de
     p.ss_pos = pos_dev; p.ss_gems = gems_dev; p.ss_alive = alive_dev;
     LLE_CUDA(launch(v, p, (cudaStream_t)stream));
     v->launches++;
+    LLE_SYNC_SHADOW(v, stream);
     return LLE_OK;
 }
+
 
 int lle_vec_export_raw(lle_vec* v, int16_t* pos, uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on,
                        uint64_t* collected, uint8_t* counters, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
-    LLE_CUDA(cudaSetDevice(v->device));
-    int threads = 128;
-    int blocks = (int)((v->N + threads - 1) / threads);
-    lle_export_raw_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(v->d_records, v->L, v->N, v->A, v->NBmax,
-                                                                      pos, alive, arrived, slot, v->NBmax ? beam_on : nullptr, collected, counters);
-    LLE_CUDA(cudaGetLastError());
-    v->launches++;
-    return LLE_OK;
+    RawState r;
+    std::memset(&r, 0, sizeof r);
+    r.pos = pos; r.alive = alive; r.arrived = arrived; r.slot = slot; r.beam_on = v->NBmax ? beam_on : nullptr; r.collected = collected; r.counters = counters;
+    return raw_state_launch<false>(v, r, stream);
 }
+
+int lle_vec_export_raw_state(lle_vec* v, const lle_raw_state* dst, void* stream) {
+    if (!v || !dst) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    return raw_state_launch<false>(v, raw_of(dst, v->NBmax), stream);
+}
+
+int lle_vec_import_raw_state(lle_vec* v, const lle_raw_state* src, void* stream) {
+    if (!v || !src) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (!src->pos || !src->alive || !src->arrived || !src->slot || !src->counters || !src->avail_cache || (v->G && !src->collected) ||
+        (v->NBmax && !src->beam_on) || (v->JE && !src->subgoals_extras) || (v->opts.pbrs && !src->subgoals_pbrs))
+        return fail(LLE_INVALID_ARGUMENT, "lle_vec_import_raw_state needs every array of the engine record this vec keeps");
+    v->last_was_step = false;  // the import is an ordinary launch: the next step must not overlap it
+    if (int rc = raw_state_launch<true>(v, raw_of(src, v->NBmax), stream)) return rc;
+    return lle_vec_refresh(v, stream);
+}
+
+int lle_vec_get_reset_count(lle_vec* v, uint32_t* out) { if (!v || !out) return fail(LLE_INVALID_ARGUMENT, "null"); *out = v->reset_epoch; return LLE_OK; }
+int lle_vec_set_reset_count(lle_vec* v, uint32_t value) { if (!v) return fail(LLE_INVALID_ARGUMENT, "null"); v->reset_epoch = value; return LLE_OK; }
 
 int lle_vec_debug_timeline(lle_vec* v, uint64_t* out_host, int64_t cap_warps, int64_t* n_warps) {
     if (!v || !n_warps) return fail(LLE_INVALID_ARGUMENT, "null argument");

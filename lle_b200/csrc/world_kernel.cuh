@@ -1414,13 +1414,63 @@ __global__ void lle_collect_gem_kernel(uint32_t* records, LleStateLayout L, int6
     records[env * L.stride + L.w_gems + (gem >> 5)] |= 1u << (gem & 31);
 }
 
-// Unpacks the records for white-box comparisons (tests) and `get_state`-style host queries.
-__global__ void lle_export_raw_kernel(const uint32_t* records, LleStateLayout L, int64_t N, int A, int NBmax, int16_t* pos,
-                                      uint8_t* alive, uint8_t* arrived, uint8_t* slot, uint64_t* beam_on, uint64_t* collected,
-                                      uint8_t* counters) {
+// The engine record of every world unpacked into plain arrays (EXPORT) or rebuilt from them (IMPORT): what the reference's world
+// holds beyond `WorldState` — tile slots, beam bits (world.rs:507-513 drops them), arrival flags, the reward strategy's counters,
+// the availability cache and the LaserSubgoal / PBRS flags — so that a batch can be checkpointed and resumed bit-exactly.
+struct RawState {  // device pointers, any may be null (lle_raw_state of include/lle_b200.h)
+    int16_t* pos;
+    uint8_t *alive, *arrived, *slot;
+    uint64_t* beam_on;
+    uint64_t* collected;
+    uint8_t* counters;
+    uint8_t* avail_cache;
+    uint64_t *sub_extras, *sub_pbrs;
+};
+template <bool IMPORT>
+__global__ void lle_raw_state_kernel(uint32_t* records, LleStateLayout L, int64_t N, int A, int NBmax, RawState r) {
     const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= N) return;
-    const uint32_t* rec = records + env * L.stride;
+    uint32_t* rec = records + env * L.stride;
+    if constexpr (IMPORT) {
+        uint32_t al = 0, ar = 0, sl = 0;
+        for (int a = 0; a < A; ++a) {
+            if (r.pos) {
+                const uint32_t pp = ((uint32_t)(uint16_t)r.pos[(env * A + a) * 2] << 8) | ((uint32_t)(uint16_t)r.pos[(env * A + a) * 2 + 1] & 0xFFu);
+                uint32_t w = rec[a >> 1];
+                w = (a & 1) ? ((w & 0xFFFFu) | (pp << 16)) : ((w & 0xFFFF0000u) | pp);
+                rec[a >> 1] = w;
+            }
+            if (r.alive && r.alive[env * A + a]) al |= 1u << a;
+            if (r.arrived && r.arrived[env * A + a]) ar |= 1u << a;
+            if (r.slot && r.slot[env * A + a]) sl |= 1u << a;
+            if (r.avail_cache) reinterpret_cast<uint8_t*>(rec + L.w_avail)[a] = r.avail_cache[env * A + a];
+            if (L.sub_words && r.sub_extras && L.w_subp > L.w_sube) {
+                rec[L.w_sube + a * L.sub_words] = (uint32_t)r.sub_extras[env * A + a];
+                if (L.sub_words == 2) rec[L.w_sube + a * 2 + 1] = (uint32_t)(r.sub_extras[env * A + a] >> 32);
+            }
+            if (L.sub_words && r.sub_pbrs && L.n_words > L.w_subp) {
+                rec[L.w_subp + a * L.sub_words] = (uint32_t)r.sub_pbrs[env * A + a];
+                if (L.sub_words == 2) rec[L.w_subp + a * 2 + 1] = (uint32_t)(r.sub_pbrs[env * A + a] >> 32);
+            }
+        }
+        const uint32_t na = r.counters ? r.counters[env * 3] : 0u, nd = r.counters ? r.counters[env * 3 + 1] : 0u, dn = r.counters ? (r.counters[env * 3 + 2] & 1u) : 0u;
+        if (!L.wide_flags) {
+            rec[L.w_flags] = (al & 0xFFu) | ((ar & 0xFFu) << 8) | ((sl & 0xFFu) << 16) | ((na & 0xFu) << 24) | ((nd > 7u ? 7u : nd) << 28) | (dn << 31);
+        } else {
+            rec[L.w_flags] = al; rec[L.w_flags + 1] = ar; rec[L.w_flags + 2] = sl;
+            rec[L.w_flags + 3] = (na & 0xFFu) | ((nd > 255u ? 255u : nd) << 8) | (dn << 16);
+        }
+        if (r.collected) {
+            if (L.gem_words >= 1) rec[L.w_gems] = (uint32_t)r.collected[env];
+            if (L.gem_words == 2) rec[L.w_gems + 1] = (uint32_t)(r.collected[env] >> 32);
+        }
+        if (r.beam_on)
+            for (int b = 0; b < NBmax; ++b) {
+                rec[L.w_on + b * L.on_words] = (uint32_t)r.beam_on[env * NBmax + b];
+                if (L.on_words == 2) rec[L.w_on + b * 2 + 1] = (uint32_t)(r.beam_on[env * NBmax + b] >> 32);
+            }
+        return;
+    }
     uint32_t al, ar, sl, na, nd, dn;
     if (!L.wide_flags) {
         const uint32_t f = rec[L.w_flags];
@@ -1432,25 +1482,42 @@ __global__ void lle_export_raw_kernel(const uint32_t* records, LleStateLayout L,
     }
     for (int a = 0; a < A; ++a) {
         const uint32_t pp = rec_pos(rec, a);
-        if (pos) { pos[(env * A + a) * 2] = (int16_t)(pp >> 8); pos[(env * A + a) * 2 + 1] = (int16_t)(pp & 0xFF); }
-        if (alive) alive[env * A + a] = (al >> a) & 1;
-        if (arrived) arrived[env * A + a] = (ar >> a) & 1;
-        if (slot) slot[env * A + a] = (sl >> a) & 1;
+        if (r.pos) { r.pos[(env * A + a) * 2] = (int16_t)(pp >> 8); r.pos[(env * A + a) * 2 + 1] = (int16_t)(pp & 0xFF); }
+        if (r.alive) r.alive[env * A + a] = (al >> a) & 1;
+        if (r.arrived) r.arrived[env * A + a] = (ar >> a) & 1;
+        if (r.slot) r.slot[env * A + a] = (sl >> a) & 1;
+        if (r.avail_cache) r.avail_cache[env * A + a] = reinterpret_cast<const uint8_t*>(rec + L.w_avail)[a];
+        if (r.sub_extras) {
+            uint64_t v = 0;
+            if (L.sub_words && L.w_subp > L.w_sube) {
+                v = rec[L.w_sube + a * L.sub_words];
+                if (L.sub_words == 2) v |= (uint64_t)rec[L.w_sube + a * 2 + 1] << 32;
+            }
+            r.sub_extras[env * A + a] = v;
+        }
+        if (r.sub_pbrs) {
+            uint64_t v = 0;
+            if (L.sub_words && L.n_words > L.w_subp) {
+                v = rec[L.w_subp + a * L.sub_words];
+                if (L.sub_words == 2) v |= (uint64_t)rec[L.w_subp + a * 2 + 1] << 32;
+            }
+            r.sub_pbrs[env * A + a] = v;
+        }
     }
-    if (collected) {
+    if (r.collected) {
         uint64_t c = 0;
         if (L.gem_words >= 1) c = rec[L.w_gems];
         if (L.gem_words == 2) c |= (uint64_t)rec[L.w_gems + 1] << 32;
-        collected[env] = c;
+        r.collected[env] = c;
     }
-    if (beam_on) {
+    if (r.beam_on) {
         for (int b = 0; b < NBmax; ++b) {
             uint64_t v = rec[L.w_on + b * L.on_words];
             if (L.on_words == 2) v |= (uint64_t)rec[L.w_on + b * 2 + 1] << 32;
-            beam_on[env * NBmax + b] = v;
+            r.beam_on[env * NBmax + b] = v;
         }
     }
-    if (counters) { counters[env * 3] = (uint8_t)na; counters[env * 3 + 1] = (uint8_t)nd; counters[env * 3 + 2] = (uint8_t)dn; }
+    if (r.counters) { r.counters[env * 3] = (uint8_t)na; r.counters[env * 3 + 1] = (uint8_t)nd; r.counters[env * 3 + 2] = (uint8_t)dn; }
 }
 
 }  // namespace lle

@@ -24,18 +24,18 @@ class VecLLE:
     def __init__(self, maps, n_envs: int, *, map_of_env: Sequence[int] | None = None, device=0, multi_objective: bool = False,
                  walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True,
                  extras=None, pbrs: dict | None = None, obs_type: str = "layered", padding_size: int = 0,
-                 randomize_lasers: bool = False):
+                 randomize_lasers: bool = False, state_type: str = "state"):
         self.world = VecWorld(maps, n_envs, map_of_env=map_of_env, device=device, reward_dim=4 if multi_objective else 1,
                               walkable_lasers=walkable_lasers, auto_reset=auto_reset, lle_semantics=True, write_obs=write_obs,
                               seed=seed, env_id_base=env_id_base, extras=extras, pbrs=pbrs, obs_type=obs_type,
-                              padding_size=padding_size, randomize_lasers=randomize_lasers)
+                              padding_size=padding_size, randomize_lasers=randomize_lasers, state_type=state_type)
         if self.world.obs_invalid and write_obs:
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         w = self.world
         self.n_envs, self.n_agents, self.n_actions = w.n_envs, w.n_agents, 5
         self.width, self.height = w.width, w.height  # env.py:120-126
         self.observation_shape = tuple(w.obs.shape[1:]) if self._flat(w) else w.obs_shape  # one agent's observation
-        self.state_shape = (w.state_dim,)
+        self.state_shape = tuple(w.state_of_type.shape[1:])  # env.py:100: the shape of get_state()
         self.reward_dim = w.reward_dim
 
     @staticmethod
@@ -45,7 +45,8 @@ class VecLLE:
     # tensors (views on device buffers)
     obs = property(lambda self: self.world.obs)                      # (N, C, H, W)
     obs_per_agent = property(lambda self: self.world.obs_per_agent)  # (N, A, C, H, W), stride-0 agent dim
-    state = property(lambda self: self.world.state)                  # (N, 3A+G)
+    state = property(lambda self: self.world.state_of_type)          # (N, 3A+G), or (N, *shape) of Builder.state_type
+    state_vector = property(lambda self: self.world.state)           # (N, 3A+G) always: PyWorldState::as_array
     available_actions = property(lambda self: self.world.avail)      # (N, A, 5) u8
     reward = property(lambda self: self.world.reward)                # (N, reward_dim)
     done = property(lambda self: self.world.done)                    # (N,) u8
@@ -178,8 +179,9 @@ class Builder:
         return self
 
     def state_type(self, state_type: str):
-        if state_type != "state":
-            raise NotImplementedError(f"state type {state_type!r} is not on the accelerated path")
+        """Builder.state_type (builder.py:51-58): any ObservationType value but "rgb-image"."""
+        obs_spec(state_type)  # ValueError / NotImplementedError
+        self._kw["state_type"] = getattr(state_type, "value", state_type)
         return self
 
     def death_strategy(self, strategy: str):

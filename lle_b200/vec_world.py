@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import MapInfo, VecBuffers, VecOptions, check, lib
+from ._native import MapInfo, RawState, VecBuffers, VecOptions, check, lib
 from .types import OBS_STATE, Direction, InvalidLevelError, LaserSource, obs_spec
 
 
@@ -112,8 +112,9 @@ class VecWorld:
                  device: int | str | torch.device = 0, reward_dim: int = 1, walkable_lasers: bool = True, auto_reset: bool = True,
                  lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0,
                  extras: str | Sequence[int] | None = None, pbrs: dict | None = None, obs_type: str = "layered",
-                 padding_size: int = 0, randomize_lasers: bool = False):
+                 padding_size: int = 0, randomize_lasers: bool = False, state_type: str = "state"):
         """obs_type: an ObservationType value (observations.py:37-60) other than "rgb-image"; padding_size for "layered-padded".
+        state_type: the ObservationType whose first-agent observation is the state (Builder.state_type, builder.py:51-58).
         extras: None | "laser_subgoal" (all sources) | source indices (World::sources() order) — Builder.add_extras.
         pbrs: None | dict(gamma=0.99, reward_value=0.5, lasers_to_reward=None | indices, with_extras=True) — Builder.pbrs
         (python/lle/env/builder.py:77-150)."""
@@ -132,6 +133,8 @@ class VecWorld:
         self.obs_type = obs_type
         opts.obs_type, opts.obs_param, self._flatten = obs_spec(obs_type, padding_size)
         opts.randomize_lasers = int(bool(randomize_lasers))
+        self.state_type = getattr(state_type, "value", state_type)
+        opts.state_type, opts.state_param, self._state_flatten = obs_spec(state_type, 0)  # the reference builds it with padding_size = 0 (env.py:86)
         extras_src = None if extras in (None, "laser_subgoal") else [int(x) for x in extras]
         want_extras = extras is not None
         if pbrs is not None:
@@ -197,6 +200,15 @@ class VecWorld:
         #: with randomize_lasers: (N,) i32, map * n_variants + colouring (colour of source b = digit b in base n_agents)
         self.n_variants = int(b.n_variants)
         self.map_index = wrap(b.map_index, (N,), "<i4") if b.map_index else None
+        #: LLE(state_type=...): the state observation, one block per env shaped like `obs` of that type; `state_of_type` is what
+        #: the reference's get_state() returns per env (the first agent's observation, observations.py:118-119)
+        self.state_obs = None
+        if b.state_obs:
+            shape = (b.state_c,) if int(b.state_type) == OBS_STATE else (b.state_c, b.state_h, b.state_w)
+            rows = wrap(b.state_obs, (N, int(b.state_obs_stride)), "<f4")
+            block = shape if b.state_view_agents or int(b.state_type) == OBS_STATE else (A, *shape)
+            self.state_obs = rows[:, : int(np.prod(block))].unflatten(1, block)
+            self._state_first = bool(not b.state_view_agents and int(b.state_type) != OBS_STATE)
         #: LaserSubgoal flags (N, A, n_sources); None when extras are off
         self.extras_dim = int(b.extras_dim)
         self.extras = wrap(b.extras, (N, A, self.extras_dim), "<f4") if self.extras_dim else None
@@ -215,6 +227,14 @@ class VecWorld:
         if not self.obs_view_agents:
             return self.obs
         return self.obs.unsqueeze(1).expand(-1, self.obs_view_agents, *([-1] * (self.obs.dim() - 1)))
+
+    @property
+    def state_of_type(self) -> torch.Tensor:
+        """(N, *state_shape): LLE.get_state() of every env for the configured state_type (env.py:205-206)."""
+        if self.state_obs is None:
+            return self.state
+        st = self.state_obs[:, 0] if self._state_first else self.state_obs
+        return st.flatten(1) if self._state_flatten else st
 
     @property
     def obs_flattened(self) -> torch.Tensor:
@@ -339,6 +359,38 @@ class VecWorld:
                                        out["slot"].data_ptr(), out["beam_on"].data_ptr() if self.n_beams_max else None,
                                        out["collected"].data_ptr(), out["counters"].data_ptr(), _stream_ptr(self.device)))
         return out
+
+    _RAW_FIELDS = (("pos", torch.int16, 2), ("alive", torch.uint8, 0), ("arrived", torch.uint8, 0), ("slot", torch.uint8, 0),
+                   ("avail_cache", torch.uint8, 0), ("subgoals_extras", torch.int64, 0), ("subgoals_pbrs", torch.int64, 0))
+
+    def checkpoint(self) -> dict:
+        """Everything a bit-exact resume needs (lle_vec_export_raw_state + the counters of the random streams): device tensors."""
+        N, A, NB = self.n_envs, self.n_agents, max(self.n_beams_max, 1)
+        d = self.device
+        t = {name: torch.zeros((N, A, extra) if extra else (N, A), dtype=dt, device=d) for name, dt, extra in self._RAW_FIELDS}
+        t["beam_on"] = torch.zeros((N, NB), dtype=torch.int64, device=d)
+        t["collected"] = torch.zeros((N,), dtype=torch.int64, device=d)
+        t["counters"] = torch.zeros((N, 3), dtype=torch.uint8, device=d)
+        raw = RawState(**{k: v.data_ptr() for k, v in t.items()})
+        check(lib().lle_vec_export_raw_state(self._h, C.byref(raw), _stream_ptr(self.device)))
+        rc = C.c_uint32(0)
+        check(lib().lle_vec_get_reset_count(self._h, C.byref(rc)))
+        t["step_count"], t["reset_count"] = self.step_count, rc.value
+        if self.map_index is not None:
+            t["map_index"] = self.map_index.clone()
+        return t
+
+    def restore(self, ckpt: dict):
+        """Inverse of checkpoint() on a batch built from the same maps and options (lle_vec_import_raw_state)."""
+        keep = {k: ckpt[k].to(self.device).contiguous() for k in ("pos", "alive", "arrived", "slot", "avail_cache", "subgoals_extras",
+                                                                  "subgoals_pbrs", "beam_on", "collected", "counters")}
+        if self.map_index is not None:
+            self.map_index.copy_(ckpt["map_index"])
+        raw = RawState(**{k: v.data_ptr() for k, v in keep.items()})
+        check(lib().lle_vec_import_raw_state(self._h, C.byref(raw), _stream_ptr(self.device)))
+        self.step_count = int(ckpt["step_count"])
+        check(lib().lle_vec_set_reset_count(self._h, int(ckpt["reset_count"])))
+        self.synchronize()  # `keep` may be freed once the import kernel has run
 
     @property
     def step_count(self) -> int:

@@ -406,17 +406,18 @@ class LLE(_Single):
 
     def __init__(self, map_str: str | None = None, *, level: int | None = None, multi_objective: bool = False,
                  walkable_lasers: bool = True, extras=None, pbrs: dict | None = None, obs_type: str = "layered",
-                 padding_size: int = 0, randomize_lasers: bool = False, device=0, name: str | None = None):
+                 padding_size: int = 0, randomize_lasers: bool = False, device=0, name: str | None = None, state_type: str = "state"):
         self._ctor = dict(map_str=map_str, level=level, multi_objective=multi_objective, walkable_lasers=walkable_lasers, extras=extras,
-                          pbrs=pbrs, obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers, device=device, name=name)
+                          pbrs=pbrs, obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers, device=device, name=name,
+                          state_type=state_type)
         self._init_single(map_str, level, device, lle_semantics=True, auto_reset=False,
                           reward_dim=4 if multi_objective else 1, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
-                          obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers)
+                          obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers, state_type=state_type)
         if self._vec.obs_invalid:  # Layered(world) raises in its constructor (observations.py:235)
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         self.reward_dim = self._vec.reward_dim
         # the attributes the reference serialises (env.py:60-66, python/tests/test_serialization.py:49-58)
-        self.obs_type, self.state_type = obs_type, "state"
+        self.obs_type, self.state_type = obs_type, getattr(state_type, "value", state_type)
         self.walkable_lasers, self.randomize_lasers = bool(walkable_lasers), bool(randomize_lasers)
         # env.py:220-242 + builder.py:61-102: "LLE-lvl<n>" / "LLE-<file>" / "LLE", then "-MO" and "-PBRS" in the order they were set
         self._name = name if name is not None else (f"LLE-lvl{level}" if level is not None else "LLE")
@@ -474,7 +475,13 @@ class LLE(_Single):
         return self.observe_layered()
 
     def get_state(self) -> np.ndarray:
-        return self.state_array()
+        """env.py:205-206: `_state_generator.get_state()` — the state vector, or the first agent's observation of `state_type`."""
+        if self._vec.state_obs is None:
+            return self.state_array()
+        if self._vec.obs_invalid:
+            raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
+        self._vec.synchronize()
+        return self._vec.state_of_type[0].cpu().numpy()
 
     def available_actions(self) -> np.ndarray:
         return self._available()

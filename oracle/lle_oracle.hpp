@@ -1216,6 +1216,7 @@ struct SubgoalTracker {
 struct Env {
     World world;
     ObsGen obs;
+    std::unique_ptr<ObsGen> state_gen;  // LLE(state_type=...): `_state_generator` (env.py:86); null = the default StateGenerator
     bool multi_objective;
     bool walkable_lasers;
     size_t n_arrived = 0, n_deads = 0;
@@ -1236,6 +1237,7 @@ struct Env {
         : world(std::move(w)), obs(world, ObsKind::Layered, 0), multi_objective(multi_obj), walkable_lasers(walkable) {}
 
     void set_obs(ObsKind kind, int param) { obs = ObsGen(world, kind, param); }  // Builder.obs_type (builder.py:42-49)
+    void set_state_type(ObsKind kind, int param) { state_gen = std::make_unique<ObsGen>(world, kind, param); }  // Builder.state_type (:51-58)
 
     size_t reward_dim() const { return (multi_objective ? 4 : 1) + (multi_objective && has_pbrs ? 1 : 0); }
 
@@ -1323,6 +1325,7 @@ struct Env {
             }
         }
         obs.setup(world);
+        if (state_gen) state_gen->setup(world);  // self._state_generator.reset() (env.py:202)
     }
     // RewardStrategy.reset (:40-42) / PotentialShapedLLE.reset (:176-180)
     void reset_strategy() {
@@ -1373,6 +1376,9 @@ struct Env {
     }
     void observe(float* out) const { obs.observe(world, out); }
     void state(float* out) const { state_as_array(world.get_state(), out); }
+    // LLE.get_state (env.py:205-206): `_state_generator.get_state()` = observe()[0] (observations.py:118-119); out holds one env's
+    // whole block of that generator (the caller takes the first agent's part)
+    void state_observation(float* out) const { state_gen->observe(world, out); }
 };
 
 }  // namespace lle_oracle

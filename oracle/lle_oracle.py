@@ -675,11 +675,11 @@ def _src_list(sources):
 
 class LLE:
     def __init__(self, map_str: str, multi_objective: bool = False, walkable_lasers: bool = True, extras=None, pbrs=None,
-                 obs_type: str = "layered", padding_size: int = 0, randomize_lasers: bool = False):
+                 obs_type: str = "layered", padding_size: int = 0, randomize_lasers: bool = False, state_type: str = "state"):
         """extras: None | "laser_subgoal" | list of source indices.  pbrs: None | dict(gamma=0.99, reward_value=0.5,
         lasers_to_reward=None (all) | list of source indices, with_extras=True) — Builder.pbrs (builder.py:77-110)."""
         self._ctor = dict(map_str=map_str, multi_objective=multi_objective, walkable_lasers=walkable_lasers, extras=extras, pbrs=pbrs,
-                          obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers)
+                          obs_type=obs_type, padding_size=padding_size, randomize_lasers=randomize_lasers, state_type=state_type)
         st = C.c_int(0)
         self._h = C.c_void_p(lib().lleo_env_new(prepare_map_text(map_str), int(multi_objective), int(walkable_lasers), C.byref(st)))
         _check(st.value)
@@ -703,6 +703,13 @@ class LLE:
         self._s6 = (C.c_long * 6)()
         _check(lib().lleo_env_set_obs(self._h, kind, param, self._s6))
         lib().lleo_env_obs_floats.restype = C.c_long
+        lib().lleo_env_state_obs_floats.restype = C.c_long
+        self.state_type = state_type
+        self._state_s6 = None
+        if state_type != "state":  # Builder.state_type (builder.py:51-58): any ObservationType as the state
+            kind, param, self._state_flatten = obs_spec(state_type, 0)  # built with padding_size = 0 (env.py:86)
+            self._state_s6 = (C.c_long * 6)()
+            _check(lib().lleo_env_set_state_type(self._h, kind, param, self._state_s6))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -716,7 +723,7 @@ class LLE:
 
     def __deepcopy__(self, _memo) -> "LLE":
         clone = LLE(**self._ctor)
-        clone.set_state(WorldState.from_array(self.get_state(), self.n_agents, self.n_gems))
+        clone.set_state(WorldState.from_array(self.state_array(), self.n_agents, self.n_gems))
         return clone
 
     @property
@@ -733,6 +740,14 @@ class LLE:
         return _finish_obs(out, list(self._s6), self._flatten, self.n_agents)
 
     def get_state(self) -> np.ndarray:
+        """LLE.get_state (env.py:205-206): `_state_generator.get_state()` = the first agent's observation of the state type."""
+        if self._state_s6 is not None:
+            out = np.zeros(lib().lleo_env_state_obs_floats(self._h), dtype=np.float32)
+            _check(lib().lleo_env_state_observation(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+            return _finish_obs(out, list(self._state_s6), self._state_flatten, self.n_agents)[0]
+        return self.state_array()
+
+    def state_array(self) -> np.ndarray:
         out = np.zeros(3 * self.n_agents + self.n_gems, dtype=np.float32)
         lib().lleo_env_state(self._h, out.ctypes.data_as(C.POINTER(C.c_float)))
         return out

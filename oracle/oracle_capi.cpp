@@ -469,6 +469,16 @@ int lleo_env_set_obs(void* p, int kind, int param, long* out6) {
     });
 }
 long lleo_env_obs_floats(void* p) { return (long)((Env*)p)->obs.floats(); }
+// Builder.state_type (builder.py:51-58): any observation generator as the state; out6 like lleo_env_set_obs
+int lleo_env_set_state_type(void* p, int kind, int param, long* out6) {
+    Env& e = *(Env*)p;
+    return guarded([&] {
+        e.set_state_type((ObsKind)kind, param);
+        e.state_gen->block_shape(out6);
+    });
+}
+long lleo_env_state_obs_floats(void* p) { return (long)((Env*)p)->state_gen->floats(); }
+int lleo_env_state_observation(void* p, float* out) { return guarded([&] { ((Env*)p)->state_observation(out); }); }
 // a generator built from the live world, as the reference tests do (`PartialGenerator(world, 3).observe()`)
 int lleo_world_observe(void* p, int kind, int param, float* out, long cap, long* out6) {
     WorldHandle* h = (WorldHandle*)p;

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE: a host (g++) instantiation of the per-world core of the tiny-map step kernel
 // (lle_b200/csrc/tiny_core.cuh is __host__ __device__), driven the way lle_tiny_step_kernel drives it — tickets of 32
-// consecutive worlds, one world per "lane", E sub-tiles per emulated warp whose previous occupants are un-patched — so that
+// consecutive worlds, one world per "lane", E sub-tiles per emulated warp rebuilt from the static planes — so that
 // `-m "not gpu"` tests can compare the very code the kernel runs per thread with the oracle, bit for bit, without a GPU.
 // The maps are compiled by the product's own host map compiler.  The product never loads this file.
 #include <cstdint>
@@ -25,9 +25,7 @@ struct PitchRec {
 };
 
 struct Warp {
-    std::vector<float> tile;        // [E][ostr]
-    std::vector<uint32_t> applied;  // [stride][E]
-    std::vector<int> tags;          // [E]
+    std::vector<float> tile;  // [E][ostr]
 };
 
 struct Shim {
@@ -149,14 +147,9 @@ void step_all(Shim& s, const int8_t* actions_in) {
                 auto& w = lanes[(size_t)lane];
                 const int sidx = lane - r * E;
                 float* sub = wp.tile.data() + (size_t)sidx * s.ostr;
-                const bool fresh = wp.tags[(size_t)sidx] != map_ids[lane];
-                if (fresh) {
-                    const float* stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
-                    for (int64_t f = 0; f < s.ostr; ++f) sub[f] = f < w.hdr->obs_floats ? stat[f] : 0.0f;
-                    wp.tags[(size_t)sidx] = map_ids[lane];
-                }
-                w.render(sub, fresh, PitchRec{wp.applied.data() + sidx, E}, s.H * s.W);
-                for (int k = 0; k < stride; ++k) wp.applied[(size_t)(k * E + sidx)] = w.rec(k);
+                const float* stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
+                for (int64_t f = 0; f < s.ostr; ++f) sub[f] = f < w.hdr->obs_floats ? stat[f] : 0.0f;
+                w.render(sub, s.H * s.W);
             }
             for (int sidx = 0; sidx < E; ++sidx) {
                 const int64_t env = ticket * 32 + (int64_t)r * E + sidx;
@@ -218,8 +211,6 @@ void* tiny_host_create(const char** texts, int n_maps, const int* map_of_env, lo
     s->warps.resize((size_t)std::max(1, n_warps));
     for (auto& w : s->warps) {
         w.tile.assign((size_t)(E * s->ostr), 0.f);
-        w.applied.assign((size_t)(s->L.stride * E), 0);
-        w.tags.assign((size_t)E, -1);
     }
     switch (s->A) {
         case 1: reset_all<1>(*s); break;

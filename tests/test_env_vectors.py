@@ -118,6 +118,34 @@ def test_observation_types_match_reference_python(api, obs_type):
     assert n >= 60
 
 
+@pytest.mark.parametrize("state_type", ["layered", "flattened", "partial3x3", "partial7x7", "normalized-state", "perspective", "layered-padded-2"])
+def test_state_types_match_reference_python(api, state_type):
+    """Builder.state_type (builder.py:51-58): LLE.get_state() is the FIRST agent's observation of that generator
+    (`_state_generator.get_state()`, observations.py:118-119, env.py:205-206) after every step / reset / set_state."""
+    z, _ = data()
+    n = 0
+    for entry in cases():
+        if entry["config"] != "single" or entry["policy"] != "careful" or state_type not in entry["obs_types"]:
+            continue
+        key = entry["key"]
+        want = z[f"{key}|obs|{state_type}"]
+        tiled = entry["obs_tiled"][state_type]
+        env = api.LLE(entry["text"], state_type=state_type)
+        for row, op in enumerate(entry["script"]):
+            if op["op"] == "reset":
+                env.reset()
+            elif op["op"] == "set_state":
+                pos, gems, alive = op["set_state"]
+                env.set_state(api.WorldState([tuple(p) for p in pos], gems, alive))
+            else:
+                env.step(op["actions"])
+            expect = (want[row] if tiled else want[row][0]).astype(np.float32)
+            got = np.asarray(env.get_state())
+            assert got.shape == expect.shape and np.array_equal(got, expect), f"{key} [state_type {state_type}] op {row}"
+        n += 1
+    assert n >= 30
+
+
 def test_colour_past_the_last_channel_raises_like_the_reference(api):
     """Layered(world) raises IndexError in its constructor (observations.py:235) for every option set of that map."""
     raising = [e for e in data()[1] if "raises" in e]

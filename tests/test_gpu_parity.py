@@ -760,3 +760,41 @@ def test_dlpack_round_trip():
     # the per-agent view (np.tile in the reference) is a stride-0 expand of the same memory
     per_agent = env.obs_per_agent
     assert per_agent.data_ptr() == env.obs.data_ptr() and per_agent.stride(1) == 0
+
+
+def test_checkpoint_resume_is_bit_identical(layouts):
+    """lle_vec_export_raw_state / lle_vec_import_raw_state: a fresh batch restored from a mid-rollout checkpoint continues exactly
+    like the original — every output and the raw engine state, incl. stale beam bits after deaths (no auto-reset: the reference's
+    WorldState could not carry them, world.rs:507-513), LaserSubgoal / PBRS flags, the reward counters, randomised laser colours."""
+    import lle_b200
+
+    cases = [
+        dict(maps=[level_text(6)], n=300, kw=dict(seed=41)),
+        dict(maps=[level_text(5)], n=200, kw=dict(seed=42, auto_reset=False, lle_semantics=False)),  # raw World: dead agents, stale bits
+        dict(maps=[level_text(6)], n=200, kw=dict(seed=43, reward_dim=4, extras="laser_subgoal", pbrs=dict(gamma=0.9, reward_value=0.5))),
+        dict(maps=[level_text(4)], n=150, kw=dict(seed=44, randomize_lasers=True)),
+        dict(maps=[layouts["eight-agent-interdependent-8"]], n=100, kw=dict(seed=45, walkable_lasers=False)),
+    ]
+    for c in cases:
+        a = lle_b200.VecWorld(c["maps"], c["n"], **c["kw"])
+        for _ in range(37):
+            a.step(None)
+        ckpt = a.checkpoint()
+        b = lle_b200.VecWorld(c["maps"], c["n"], **c["kw"])
+        b.restore(ckpt)
+        a.synchronize()
+        for name in ("obs", "state", "avail"):  # re-exported from the imported records
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"{name} right after restore"
+        for t in range(60):
+            a.step(None)
+            b.step(None)
+            if t % 10 == 9:
+                a.synchronize()
+                for name in ("obs", "state", "avail", "reward", "done", "events", "actions", "err"):
+                    assert torch.equal(getattr(a, name), getattr(b, name)), f"{name} differs {t + 1} steps after the restore"
+                if a.extras is not None:
+                    assert torch.equal(a.extras, b.extras)
+                ra, rb = a.checkpoint(), b.checkpoint()
+                for k in ra:
+                    same = torch.equal(ra[k], rb[k]) if isinstance(ra[k], torch.Tensor) else ra[k] == rb[k]
+                    assert same, f"raw '{k}' differs {t + 1} steps after the restore"
