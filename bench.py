@@ -13,7 +13,7 @@ For N > 1 launch with torchrun (one rank per GPU); envs are range-sharded over r
 collective on the step path; NCCL carries only the reductions of the timings and of three counters).
 Prints ONE JSON line on rank 0.  Keys beyond the contract:
   configs    the other BASELINE.json workloads (1, 3, 4, 5 of SURVEY §8d) at their stated per-GPU sizes, bounded steps
-  e2e        value = closed loop (the host reads step t's results before it chooses step t+1's actions), two half-batches
+  e2e        value = closed loop (the host reads step t's results before it chooses step t+1's actions), four sub-batches
              in flight; pipelined_value = open loop, 8 recorded steps in flight; sync_value = one blocking call per step
   ranks      per-rank ms per step of the headline window (min / max / all)
 """
@@ -171,6 +171,7 @@ def run_ours(args) -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = pin_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world_size))))
 
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -259,7 +260,6 @@ def run_ours(args) -> None:
     # ---------------- end-to-end arms: host actions in (pinned, H2D), reward + done out (D2H) every step
     Ke = max(1, min(K, args.e2e_steps))
     T0 = 10_000_000
-    half = n_envs // 2
     vec.reset()
     vec.step_count = T0
     rec_act = torch.empty((Ke, n_envs, A), dtype=torch.int8).pin_memory()
@@ -273,6 +273,8 @@ def run_ours(args) -> None:
     D = max(1, min(8, args.e2e_depth))
     reward_h = [torch.empty((n_envs, R), dtype=torch.float32).pin_memory() for _ in range(D)]
     done_h = [torch.empty((n_envs,), dtype=torch.uint8).pin_memory() for _ in range(D)]
+
+    done_np0, rec_done_np0 = done_h[0].numpy(), rec_done.numpy()
 
     def restart(v, t=T0):
         v.reset()
@@ -289,7 +291,7 @@ def run_ours(args) -> None:
         for s in range(Ke):
             vec.step_host(acts, reward_h[0], done_h[0])
             if s + 1 < Ke:
-                acts = rec_act[s + 1] if torch.equal(done_h[0], rec_done[s]) else stay
+                acts = rec_act[s + 1] if np.array_equal(done_np0, rec_done_np0[s]) else stay
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
@@ -311,33 +313,36 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    # closed loop with two half-batches in flight (the EnvPool pattern): while the host reads half A's results and chooses its
-    # next actions, half B steps.  Two vecs over the same global env ids as the two halves of the batch.
-    halves = [lle_b200.VecWorld(lle_b200.Map(level=LEVEL), half, device=dev, seed=SEED, env_id_base=begin + h * half, auto_reset=True)
-              for h in range(2)]
-    rec_act_h = [rec_act[:, h * half:(h + 1) * half].contiguous().pin_memory() for h in range(2)]
-    rec_done_h = [rec_done[:, h * half:(h + 1) * half].contiguous().pin_memory() for h in range(2)]
-    stay_h = stay[:half].contiguous().pin_memory()
-    rw_h = [torch.empty((half, R), dtype=torch.float32).pin_memory() for _ in range(2)]
-    dn_h = [torch.empty((half,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    # closed loop with several sub-batches in flight (the EnvPool pattern): while the host reads one sub-batch's results and chooses
+    # its next actions, the others step.  P vecs over the same global env ids as the P slices of the batch.
+    P = max(1, args.e2e_parts)
+    part = n_envs // P
+    parts = [lle_b200.VecWorld(lle_b200.Map(level=LEVEL), part, device=dev, seed=SEED, env_id_base=begin + h * part, auto_reset=True)
+             for h in range(P)]
+    rec_act_h = [rec_act[:, h * part:(h + 1) * part].contiguous().pin_memory() for h in range(P)]
+    rec_done_np = [rec_done[:, h * part:(h + 1) * part].contiguous().numpy() for h in range(P)]
+    stay_h = stay[:part].contiguous().pin_memory()
+    rw_h = [torch.empty((part, R), dtype=torch.float32).pin_memory() for _ in range(P)]
+    dn_h = [torch.empty((part,), dtype=torch.uint8).pin_memory() for _ in range(P)]
+    dn_np = [t.numpy() for t in dn_h]  # the policy reads the results through numpy (a memcmp; torch.equal costs 25 us per call)
     mismatches = [0]
 
     def e2e_closed_loop() -> float:
-        for v in halves:
+        for v in parts:
             restart(v)
         barrier()
         t0 = time.perf_counter()
         for s in range(Ke):
-            for h in range(2):
+            for h in range(P):
                 acts = rec_act_h[h][s]
                 if s > 0:
-                    halves[h].wait_host()  # results of step s-1 of this half are in host memory
-                    if not torch.equal(dn_h[h], rec_done_h[h][s - 1]):  # the policy reads every result byte
+                    parts[h].wait_host()  # results of step s-1 of this sub-batch are in host memory
+                    if not np.array_equal(dn_np[h], rec_done_np[h][s - 1]):  # the policy reads every result byte
                         acts = stay_h
                         mismatches[0] += 1
-                halves[h].submit_host(acts, rw_h[h], dn_h[h])
-        for h in range(2):
-            halves[h].wait_host()
+                parts[h].submit_host(acts, rw_h[h], dn_h[h], after_current_stream=False)
+        for h in range(P):
+            parts[h].wait_host()
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
@@ -349,9 +354,9 @@ def run_ours(args) -> None:
     e2e_pipe_value = world_size * n_envs * Ke / reduce_max(e2e_pipelined())
     assert int(vec.err.sum()) == 0, "replayed actions must be valid"
     mismatches[0] = 0
-    e2e_closed_value = world_size * 2 * half * Ke / reduce_max(e2e_closed_loop())
-    assert mismatches[0] == 0 and all(int(v.err.sum()) == 0 for v in halves), "the closed loop left the recorded trajectory"
-    del halves
+    e2e_closed_value = world_size * P * part * Ke / reduce_max(e2e_closed_loop())
+    assert mismatches[0] == 0 and all(int(v.err.sum()) == 0 for v in parts), "the closed loop left the recorded trajectory"
+    del parts
 
     # end-of-run stats reduction: the only collective on this path (NCCL all-reduce of a few counters)
     stats = reduce_stats(torch.stack([vec.done.sum().to(torch.int64), vec.reward.sum().to(torch.int64),
@@ -413,12 +418,13 @@ def run_ours(args) -> None:
             "ranks": {"ms_per_step_min": min(per_rank), "ms_per_step_max": max(per_rank), "ms_per_step": per_rank},
             "clocks": clocks,
             "e2e": {"value": e2e_closed_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A, "d2h_bytes_per_step": n_envs * (4 * R + 1),
-                    "steps": Ke, "closed_loop": True, "sub_batches_in_flight": 2,
+                    "steps": Ke, "closed_loop": True, "sub_batches_in_flight": P,
                     "pipelined_value": e2e_pipe_value, "pipeline_depth": D, "sync_value": e2e_sync_value,
-                    "note": "value: CLOSED loop through lle_vec_pipeline_submit/_wait on two half-batches (two vecs over the same global "
-                            "env ids): the host reads every done flag of a half's step t from pinned memory before it submits that half's "
-                            "step t+1, while the other half steps; every step copies its actions H2D and reward+done D2H inside the timed "
-                            "region. sync_value: the same dependency with one blocking lle_vec_step_host call per step on the whole batch. "
+                    "note": f"value: CLOSED loop through lle_vec_pipeline_submit/_wait on {P} sub-batches (vecs over the same global "
+                            "env ids): the host reads every done flag of a sub-batch's step t from pinned memory before it submits that "
+                            "sub-batch's step t+1, while the others step; every step copies its actions H2D (copy engine) and writes reward+done "
+                            "D2H (zero-copy stores of the step kernel) inside the timed region. sync_value: the same dependency with one "
+                            "blocking lle_vec_step_host call per step on the whole batch. "
                             f"pipelined_value: OPEN loop, {D} recorded steps in flight (not what an acting agent can do). "
                             "Observations stay in HBM (zero-copy DLPack hand-off to a device policy)"},
             "gpu_launches": launches,
@@ -451,6 +457,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2048)
     ap.add_argument("--e2e-depth", type=int, default=8, help="steps in flight in the open-loop pipelined arm (1..8)")
+    ap.add_argument("--e2e-parts", type=int, default=4, help="sub-batches in flight in the closed-loop arm")
     ap.add_argument("--preheat-ms", type=float, default=250.0, help="untimed device work before the warm-up steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE workloads")

@@ -157,7 +157,9 @@ typedef struct {
      * Any other type adds a second observation buffer (lle_vec_buffers.state_obs), rendered from the same engine records by a
      * second launch after every step / reset / set_state; step launches then run strictly one after the other. */
     int32_t state_type, state_param;
-    int32_t pad_options;
+    /* 1: also keep, per env, Step.info of LLE.step (python/lle/env/env.py:174-188) and episode statistics, written by the step kernel
+     * (lle_vec_buffers.info / ep_return / ep_length / last_return / last_length): about 20 more bytes per env-step. */
+    int32_t episode_stats;
 } lle_vec_options;
 enum { LLE_OBS_LAYERED = 0, LLE_OBS_PARTIAL = 1, LLE_OBS_PERSPECTIVE = 2, LLE_OBS_STATE = 3 };
 LLE_API void lle_vec_default_options(lle_vec_options* opts);
@@ -216,6 +218,15 @@ typedef struct {
     float* state_obs;
     int64_t state_obs_stride;
     int32_t state_type, state_param, state_view_agents, state_c, state_h, state_w;
+    /* episode_stats (NULL otherwise).  info u8[N, 2 + A] of the transition just taken, before an auto-reset: gems_collected
+     * (World::n_gems_collected, world.rs:265-275), n_arrived (exit_rate = n_arrived / A), has-arrived-i; is-alive-i is the tail of
+     * `state`.  ep_return f32[N, reward_dim] / ep_length i32[N]: reward summed over, and steps of, the running episode;
+     * last_return / last_length: the same of the env's last finished episode (latched by the step that sets done). */
+    uint8_t* info;
+    float* ep_return;
+    int32_t* ep_length;
+    float* last_return;
+    int32_t* last_length;
 } lle_vec_buffers;
 LLE_API int lle_vec_get_buffers(lle_vec* vec, lle_vec_buffers* out);
 
@@ -264,8 +275,10 @@ LLE_API int lle_host_free(void* ptr);
  * lle_vec_pipeline_wait blocks until the OLDEST submitted step's results are in its host buffers.  Up to 8 steps may be
  * outstanding; with two or more, the copies of one step overlap the kernels of its neighbours and consecutive step
  * kernels stay back to back (programmatic dependent launch), so a host-driven loop runs at the device rate.
- * The first submit after the pipeline was empty is ordered after the work already in `after_stream`; no other call
+ * The first submit after the pipeline was empty is ordered after the work already in `after_stream` (pass LLE_STREAM_NONE when
+ * nothing the step depends on is pending on any stream: saves two driver calls per step of a closed loop); no other call
  * on the vec is allowed until the pipeline has been drained.  Device buffers (lle_vec_get_buffers) are updated as usual. */
+#define LLE_STREAM_NONE ((void*)(intptr_t)-1)
 LLE_API int lle_vec_pipeline_submit(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream);
 LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
 

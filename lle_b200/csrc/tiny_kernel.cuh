@@ -9,10 +9,12 @@
 //     enter, repeated while somebody died (world.rs:454-505) — with positions, flags and events in registers and the beam /
 //     gem masks in a lane-private column of shared memory (dynamic index by beam): no ballots, no shuffles, no predicated
 //     phases, and 32 worlds advance per warp pass instead of 32 / Wd;
-//   * the observation tile of E worlds is rebuilt from the maps' static planes by the whole warp with asynchronous 16-byte
-//     copies (a warp meets another map with nearly every ticket of a heterogeneous batch, so there is nothing to un-patch),
-//     then E lanes patch their own world's sub-tile (lit laser cells, uncollected gems, the agents' one-hots) and the tile
-//     leaves with one TMA bulk store;
+//   * an observation tile holds E worlds.  Each of its sub-tiles is first filled with the static plane of its world's map by ONE
+//     TMA bulk load (issued by the lane that owns the world, completing on an mbarrier) — a warp meets another map with nearly
+//     every ticket of a heterogeneous batch, so there is nothing to un-patch, and 16-byte copies cost 40 % of the kernel's
+//     instructions (profiles/ncu_cfg3_tiny_r02_summary.csv) — into one of two tile buffers, a round ahead of its use; then E
+//     lanes patch their own sub-tile (lit laser cells, uncollected gems, the agents' one-hots) and the tile leaves with one
+//     TMA bulk store;
 //   * every lane follows its own map (blob pointer per lane), so heterogeneous batches need no uniformity checks.
 // Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
 // per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
@@ -35,6 +37,30 @@ struct SmemColumn {
     int pitch;
     __device__ __forceinline__ uint32_t& operator()(int word) const { return base[word * pitch]; }
 };
+
+// ---- TMA 1-D bulk LOAD (global -> shared) completing on an mbarrier: one instruction moves a world's whole static plane
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void bulk_load_arrive(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}" ::"r"(b), "r"(parity)
+        : "memory");
+}
 
 // `n` bytes (compile-time) from registers to global memory with the widest stores the alignment of `n` allows
 template <int N>
@@ -60,8 +86,17 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     const bool has_gems = p.L.gem_words != 0;
     const int W = p.W, E = p.E, ostr = (int)p.obs_stride;
     uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
-    float* tiles = reinterpret_cast<float*>(wbase);                                  // [E][ostr]: E worlds per bulk store
-    uint32_t* srec = reinterpret_cast<uint32_t*>(tiles + p.tile_floats);             // [stride][32]: word k of lane l at k*32+l
+    float* tiles = reinterpret_cast<float*>(wbase);                                  // [2][E][ostr]: E worlds per bulk store, two buffers
+    uint32_t* srec = reinterpret_cast<uint32_t*>(tiles + 2 * p.tile_floats);         // [stride][32]: word k of lane l at k*32+l
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(srec + stride * 32);                // [2]: "the static planes of buffer b have landed"
+    if (lane == 0) {
+        mbar_init(mbar + 0, (uint32_t)E);  // one arrival (with its byte count) per sub-tile
+        mbar_init(mbar + 1, (uint32_t)E);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    uint32_t use = 0;  // tile buffer uses so far: buffer = use & 1, mbarrier phase parity = (use >> 1) & 1
+    const uint32_t tile_bytes = (uint32_t)ostr * 4u;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
         if (lane == 0)
@@ -120,6 +155,12 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         w.unpack();
         const uint32_t av_cache = w.rec(w_avail);  // World::available_actions cache: one byte per agent (A_ <= 4)
+        // the static planes (observations.py:216-237) of the first E worlds start moving into the next tile buffer now; the buffer's
+        // last store (two stores ago) must have finished reading it
+        const float* my_stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        if (lane < E) bulk_load_arrive(tiles + (size_t)(use & 1u) * p.tile_floats + (size_t)lane * ostr, my_stat, tile_bytes, mbar + (use & 1u));
 
         // ---- actions (world.rs:444-453): supplied, or sampled uniformly among the available ones
         uint32_t act[A_], ev[A_];
@@ -161,6 +202,17 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             p.done[env] = (uint8_t)w.done;
             if (p.done2 && real) p.done2[env] = (uint8_t)w.done;
             p.err[env] = (uint8_t)err;
+            if (p.ep_return) {  // lle_vec_options.episode_stats
+                for (int k = 0; k < p.R; ++k) episode_stat_reward(p.ep_return + env * p.R + k, p.last_return + env * p.R + k, rw[k], paid, w.done != 0, false);
+                episode_stat_length(p.ep_length + env, p.last_length + env, paid, w.done != 0, false);
+            }
+            if (p.info) {  // Step.info (env.py:174-188)
+                uint8_t* io = p.info + env * (2 + A_);
+                io[0] = (uint8_t)__popc(has_gems ? (w.rec(w_gems) & (uint32_t)w.hdr->gem_toplevel) : 0u);
+                io[1] = (uint8_t)w.n_arrived;
+#pragma unroll
+                for (int a = 0; a < A_; ++a) io[2 + a] = (uint8_t)((w.arrived >> a) & 1u);
+            }
             store_bytes<A_>(p.events + env * A_, ev);
             store_bytes<A_>(reinterpret_cast<uint8_t*>(p.actions) + env * A_, act);
         }
@@ -198,41 +250,28 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         __syncwarp();
 
-        // ---- layered observation (observations.py:254-266), E worlds per bulk store
-        const float* my_stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
-        const int obs_floats = w.hdr->obs_floats;  // C*H*W: the same for every map of the batch
+        // ---- layered observation (observations.py:254-266), E worlds per bulk store.  The static planes of round r + 1 travel
+        // while round r is patched and stored; those of round 0 were requested before the logic above.
         for (int r = 0; r < 32 / E; ++r) {
-            if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
-            __syncwarp();
-            // every sub-tile starts from the static plane of its world's map (observations.py:216-237): the warp copies them
-            for (int s2 = 0; s2 < E; ++s2) {
-                const uint64_t sp = __shfl_sync(kFull, (uint64_t)(uintptr_t)my_stat, r * E + s2);
-                const float* stat = reinterpret_cast<const float*>((uintptr_t)sp);
-                float* sub2 = tiles + (size_t)s2 * ostr;
-                for (int f = lane * 4; f < ostr; f += 128) {
-                    if (f + 3 < obs_floats) {
-                        cp_async16(sub2 + f, stat + f);
-                    } else {  // the padding behind C*H*W (a multiple of 4 floats per block)
-                        float4 v;
-                        v.x = f + 0 < obs_floats ? __ldg(stat + f + 0) : 0.f; v.y = f + 1 < obs_floats ? __ldg(stat + f + 1) : 0.f;
-                        v.z = f + 2 < obs_floats ? __ldg(stat + f + 2) : 0.f; v.w = f + 3 < obs_floats ? __ldg(stat + f + 3) : 0.f;
-                        *reinterpret_cast<float4*>(sub2 + f) = v;
-                    }
-                }
+            if (r + 1 < 32 / E) {
+                if (lane == 0) bulk_wait_read<0>();  // the other buffer's last store (round r - 1) has finished reading it
+                __syncwarp();
+                if (lane / E == r + 1) bulk_load_arrive(tiles + (size_t)((use + 1) & 1u) * p.tile_floats + (size_t)(lane - (r + 1) * E) * ostr, my_stat, tile_bytes, mbar + ((use + 1) & 1u));
             }
-            cp_async_wait_all();
-            __syncwarp();
-            if (lane / E == r) w.render(tiles + (size_t)(lane - r * E) * ostr, p.HW);
+            float* tile = tiles + (size_t)(use & 1u) * p.tile_floats;
+            mbar_wait(mbar + (use & 1u), (use >> 1) & 1u);
+            if (lane / E == r) w.render(tile + (size_t)(lane - r * E) * ostr, p.HW);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                bulk_store(p.obs + ((int64_t)ticket * 32 + (int64_t)r * E) * ostr, tiles, (uint32_t)(E * ostr) * 4u);
+                bulk_store(p.obs + ((int64_t)ticket * 32 + (int64_t)r * E) * ostr, tile, (uint32_t)(E * ostr) * 4u);
                 bulk_commit();
                 if (owed && r == 0) {
                     bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
                     ticket_release(p.flags + owed_ticket, owed_seq);
                 }
             }
+            ++use;
         }
         owed = true; owed_ticket = ticket; owed_seq = my_seq;
         __syncwarp();

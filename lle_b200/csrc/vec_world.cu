@@ -87,6 +87,9 @@ struct lle_vec {
     int8_t* d_actions_stage = nullptr;  // for step_host
     uint64_t* d_timeline = nullptr;     // development aid (LLE_B200_TIMELINE=1)
     float* d_extras = nullptr;          // [N_pad][A][JE]
+    uint8_t* d_info = nullptr;          // episode_stats: Step.info bytes and the episode accumulators
+    float *d_ep_return = nullptr, *d_last_return = nullptr;
+    int32_t *d_ep_length = nullptr, *d_last_length = nullptr;
     int JE = 0;
     uint64_t extras_set = 0, pbrs_set = 0;
     int8_t extras_beam[64] = {0};
@@ -228,10 +231,27 @@ cudaError_t resolve_memops() {
     return cudaSuccess;
 }
 
+// The dynamic shared-memory limit is an attribute of the FUNCTION, shared by every vec of the process: it is raised to the
+// device's opt-in maximum (227 KB on B200) once, never to one vec's own size — a second vec with a smaller tile would otherwise
+// lower it under the first one's launches.
+int g_smem_optin = 0;
+cudaError_t smem_optin(int device, int* out) {
+    if (!g_smem_optin) {
+        cudaError_t e = cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (e != cudaSuccess) return e;
+    }
+    *out = g_smem_optin;
+    return cudaSuccess;
+}
+
 template <int MODE, int KIND>
 cudaError_t configure_kernel(size_t smem, int* blocks) {
     auto kern = lle_world_kernel<MODE, KIND>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = smem_optin(dev, &optin);
+    if (e == cudaSuccess && smem > (size_t)optin) return cudaErrorInvalidValue;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) return e;
     int b = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, smem);
@@ -274,6 +294,7 @@ KParams base_params(lle_vec* v) {
     p.pbrs_gamma = v->opts.pbrs_gamma; p.pbrs_value = v->opts.pbrs_reward_value;
     std::memcpy(p.extras_beam, v->extras_beam, sizeof p.extras_beam);
     p.timeline = v->d_timeline;
+    p.info = v->d_info; p.ep_return = v->d_ep_return; p.ep_length = v->d_ep_length; p.last_return = v->d_last_return; p.last_length = v->d_last_length;
     p.reset_epoch = v->reset_epoch;
     p.randomize = (v->randomize && !v->creating) ? 1 : 0;  // the construction reset is World::new's, not LLE.reset (env.py:191-203)
     p.n_variants = v->n_variants;
@@ -444,6 +465,7 @@ int lle_vec_destroy(lle_vec* v) {
     cudaFree((void*)v->d_blob_table); cudaFree(v->d_map_of_env); cudaFree(v->d_records); cudaFree(v->d_obs); cudaFree(v->d_state);
     cudaFree(v->d_avail); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_events); cudaFree(v->d_actions);
     cudaFree(v->d_err); cudaFree(v->d_sched); cudaFree(v->d_flags); cudaFree(v->d_actions_stage); cudaFree(v->d_timeline); cudaFree(v->d_extras);
+    cudaFree(v->d_info); cudaFree(v->d_ep_return); cudaFree(v->d_last_return); cudaFree(v->d_ep_length); cudaFree(v->d_last_length);
     for (int k = 0; k < lle_vec::kPipeSlots; ++k) {
         cudaFree(v->d_stage[k]);
     }
@@ -656,12 +678,19 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (v->tiny) {
         int e = env_int("LLE_B200_TINY_E", v->E);
         v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 8;
-        size_t bytes = (size_t)v->tiny_E * stride * 4 + (size_t)v->L.stride * 32 * 4;  // the tile + the records' columns
-        v->tiny_warp_smem = (int)((bytes + 127) / 128 * 128);
+        auto tiny_bytes = [&](int E) {  // two tile buffers, the records' columns, two mbarriers
+            const size_t bytes = 2 * (size_t)E * stride * 4 + (size_t)v->L.stride * 32 * 4 + 16;
+            return (bytes + 127) / 128 * 128;
+        };
+        while (v->tiny_E > 4 && tiny_bytes(v->tiny_E) * kWarps > (size_t)(96 << 10)) v->tiny_E /= 2;  // at least two CTAs per SM
+        v->tiny_warp_smem = (int)tiny_bytes(v->tiny_E);
         v->tiny_smem = (size_t)v->tiny_warp_smem * kWarps;
         int tb = 0;
         auto configure = [&](auto kern) -> cudaError_t {
-            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->tiny_smem);
+            int optin = 0;
+            cudaError_t e2 = smem_optin(v->device, &optin);
+            if (e2 == cudaSuccess && v->tiny_smem > (size_t)optin) return cudaErrorInvalidValue;
+            if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (e2 != cudaSuccess) return e2;
             return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb, kern, kThreads, v->tiny_smem);
         };
@@ -731,6 +760,13 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     LLE_CUDA(dalloc(&v->d_actions, (size_t)v->A * Np));
     LLE_CUDA(dalloc(&v->d_err, Np));
     if (v->JE) LLE_CUDA(dalloc(&v->d_extras, (size_t)v->A * v->JE * Np));
+    if (opts->episode_stats) {
+        LLE_CUDA(dalloc(&v->d_info, (size_t)(2 + v->A) * Np));
+        LLE_CUDA(dalloc(&v->d_ep_return, (size_t)v->R * Np));
+        LLE_CUDA(dalloc(&v->d_last_return, (size_t)v->R * Np));
+        LLE_CUDA(dalloc(&v->d_ep_length, Np));
+        LLE_CUDA(dalloc(&v->d_last_length, Np));
+    }
     LLE_CUDA(dalloc(&v->d_sched, (size_t)kSchedSlotWords * kSchedSlots));
     LLE_CUDA(dalloc(&v->d_flags, (size_t)(v->N_pad / v->group)));
     LLE_CUDA(cudaHostAlloc((void**)&v->h_retired_seq, sizeof(uint32_t), cudaHostAllocMapped));
@@ -751,6 +787,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         so.obs_type = opts->state_type; so.obs_param = opts->state_param;
         so.state_type = LLE_OBS_STATE; so.state_param = 0;
         so.write_obs = 1;
+        so.episode_stats = 0;
         lle_vec* sh = nullptr;
         if (int rc2 = lle_vec_create(maps, n_maps, map_of_env, n_envs, &so, &sh)) return rc2;
         if (sh->L.stride != v->L.stride || sh->N_pad != v->N_pad || (sh->d_map_of_env == nullptr) != (v->d_map_of_env == nullptr)) {
@@ -789,6 +826,7 @@ int lle_vec_get_buffers(lle_vec* v, lle_vec_buffers* out) {
     out->obs_invalid = v->obs_invalid;
     out->map_index = v->d_map_of_env;
     out->n_variants = v->n_variants;
+    out->info = v->d_info; out->ep_return = v->d_ep_return; out->ep_length = v->d_ep_length; out->last_return = v->d_last_return; out->last_length = v->d_last_length;
     if (v->shadow) {
         const lle_vec* sh = v->shadow;
         out->state_obs = sh->d_obs; out->state_obs_stride = sh->obs_stride;
@@ -1040,7 +1078,7 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
     void* done_dev = done_host ? device_view(v, done_host) : nullptr;
     if ((actions_host && !device_view(v, actions_host)) || (reward_host && !reward_dev) || (done_host && !done_dev))
         return fail(LLE_INVALID_ARGUMENT, "lle_vec_pipeline_submit needs pinned (page-locked) host buffers (lle_host_alloc / cudaHostAlloc / cudaHostRegister)");
-    if (v->pipe_submitted == v->pipe_completed) {  // pipeline empty: order it after the caller's stream
+    if (v->pipe_submitted == v->pipe_completed && after_stream != LLE_STREAM_NONE) {  // pipeline empty: order it after the caller's stream
         LLE_CUDA(cudaEventRecord(v->ev_user, (cudaStream_t)after_stream));
         LLE_CUDA(cudaStreamWaitEvent(v->s_main, v->ev_user, 0));
     }

@@ -104,6 +104,12 @@ struct KParams {
     int32_t randomize;     // LLE(randomize_lasers=True), env.py:198-200: every LLE-level reset recolours the sources at random
     int32_t n_variants;    // colourings per map: n_agents ^ n_sources (source b's colour = digit b in base n_agents)
     uint32_t refresh_only; // MODE_RESET launch that resets no env: re-exports observation / state / availability only
+    // Step.info of LLE.step (env.py:174-188) and per-env episode statistics (lle_vec_options.episode_stats), or nullptr
+    uint8_t* info;         // [N_pad][2 + A]: gems_collected, n_arrived, has-arrived flags of the transition just taken
+    float* ep_return;      // [N_pad][R]  reward summed over the running episode
+    int32_t* ep_length;    // [N_pad]     its steps so far
+    float* last_return;    // [N_pad][R]  the same two of the last finished episode
+    int32_t* last_length;  // [N_pad]
 };
 
 // ---- PTX wrappers (TMA 1-D bulk store through the async proxy) ----------------------------------------
@@ -683,6 +689,25 @@ __device__ __noinline__ int recolour_variant(int32_t* map_of_env, uint64_t env_i
     return next;
 }
 
+// Episode statistics of one reward component / of the episode length (lle_vec_options.episode_stats).  Out of line: the step
+// kernel should not carry this in its registers when the option is off.
+__device__ __noinline__ void episode_stat_reward(float* running, float* last, float v, bool paid, bool done, bool cleared) {
+    float acc = cleared ? 0.0f : *running;
+    if (paid) {
+        acc = __fadd_rn(acc, v);
+        if (done) { *last = acc; acc = 0.0f; }
+    }
+    *running = acc;
+}
+__device__ __noinline__ void episode_stat_length(int32_t* running, int32_t* last, bool paid, bool done, bool cleared) {
+    int32_t len = cleared ? 0 : *running;
+    if (paid) {
+        ++len;
+        if (done) { *last = len; len = 0; }
+    }
+    *running = len;
+}
+
 // End of a launch, lane 0 of every warp: count the warp out; the last warp re-arms the launch's scheduler slot for a later
 // launch (generation word, see sched_slot_armed) and publishes the launch to the host.  With host-facing stepping
 // (lle_vec_pipeline_submit) reward / done went straight into pinned host memory: every warp fences them at system scope before
@@ -975,11 +1000,21 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     }
                     p.reward[env * p.R + r] = v;
                     if (p.reward2 && real) p.reward2[env * p.R + r] = v;  // the host's own buffer: N worlds, no padding
+                    if (p.ep_return) episode_stat_reward(p.ep_return + env * p.R + r, p.last_return + env * p.R + r, v, paid, w.done != 0, MODE == MODE_RESET);
                 }
                 if (gl == 0) {
                     p.done[env] = (uint8_t)w.done;
                     if (p.done2 && real) p.done2[env] = (uint8_t)w.done;
                     p.err[env] = (uint8_t)err;
+                    if (p.ep_length) episode_stat_length(p.ep_length + env, p.last_length + env, paid, w.done != 0, MODE == MODE_RESET);
+                }
+                if (p.info) {  // Step.info (env.py:174-188): World::n_gems_collected (top-level gems only, world.rs:265-275), n_arrived, Agent.has_arrived
+                    uint8_t* io = p.info + env * (2 + A);
+                    if (gl == 0) {
+                        io[0] = (uint8_t)__popcll(w.collected() & w.m.gem_toplevel);
+                        io[1] = (uint8_t)w.n_arrived;
+                    }
+                    if (gl < A) io[2 + gl] = (uint8_t)((w.arrived >> gl) & 1u);
                 }
                 if (gl < A) {
                     p.events[env * A + gl] = (uint8_t)ev;

@@ -24,11 +24,12 @@ class VecLLE:
     def __init__(self, maps, n_envs: int, *, map_of_env: Sequence[int] | None = None, device=0, multi_objective: bool = False,
                  walkable_lasers: bool = True, auto_reset: bool = True, seed: int = 0, env_id_base: int = 0, write_obs: bool = True,
                  extras=None, pbrs: dict | None = None, obs_type: str = "layered", padding_size: int = 0,
-                 randomize_lasers: bool = False, state_type: str = "state"):
+                 randomize_lasers: bool = False, state_type: str = "state", episode_stats: bool = False):
         self.world = VecWorld(maps, n_envs, map_of_env=map_of_env, device=device, reward_dim=4 if multi_objective else 1,
                               walkable_lasers=walkable_lasers, auto_reset=auto_reset, lle_semantics=True, write_obs=write_obs,
                               seed=seed, env_id_base=env_id_base, extras=extras, pbrs=pbrs, obs_type=obs_type,
-                              padding_size=padding_size, randomize_lasers=randomize_lasers, state_type=state_type)
+                              padding_size=padding_size, randomize_lasers=randomize_lasers, state_type=state_type,
+                              episode_stats=episode_stats)
         if self.world.obs_invalid and write_obs:
             raise IndexError("index out of bounds: a laser colour selects a channel past the last layer")
         w = self.world
@@ -54,6 +55,11 @@ class VecLLE:
     actions = property(lambda self: self.world.actions)              # (N, A) i8
     err = property(lambda self: self.world.err)                      # (N,) u8
     extras = property(lambda self: self.world.extras)                # (N, A, n_sources) f32 or None
+    info = property(lambda self: self.world.info)                    # Step.info per env (episode_stats=True)
+    ep_return = property(lambda self: self.world.ep_return)          # (N, reward_dim) running episode return
+    ep_length = property(lambda self: self.world.ep_length)          # (N,) running episode length
+    last_return = property(lambda self: self.world.last_return)      # (N, reward_dim) return of the last finished episode
+    last_length = property(lambda self: self.world.last_length)      # (N,)
 
     def reset(self, mask: torch.Tensor | None = None):
         self.world.reset(mask)
@@ -176,6 +182,11 @@ class Builder:
         """Builder.obs_type (builder.py:42-49): any ObservationType value but "rgb-image"."""
         obs_spec(obs_type, padding_size)  # ValueError / NotImplementedError
         self._kw["obs_type"], self._kw["padding_size"] = obs_type, int(padding_size)
+        return self
+
+    def episode_stats(self, enabled: bool = True):
+        """Step.info (env.py:174-188) and episode return / length per env, kept by the step kernel."""
+        self._kw["episode_stats"] = bool(enabled)
         return self
 
     def state_type(self, state_type: str):

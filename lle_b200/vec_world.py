@@ -112,7 +112,7 @@ class VecWorld:
                  device: int | str | torch.device = 0, reward_dim: int = 1, walkable_lasers: bool = True, auto_reset: bool = True,
                  lle_semantics: bool = True, write_obs: bool = True, seed: int = 0, env_id_base: int = 0,
                  extras: str | Sequence[int] | None = None, pbrs: dict | None = None, obs_type: str = "layered",
-                 padding_size: int = 0, randomize_lasers: bool = False, state_type: str = "state"):
+                 padding_size: int = 0, randomize_lasers: bool = False, state_type: str = "state", episode_stats: bool = False):
         """obs_type: an ObservationType value (observations.py:37-60) other than "rgb-image"; padding_size for "layered-padded".
         state_type: the ObservationType whose first-agent observation is the state (Builder.state_type, builder.py:51-58).
         extras: None | "laser_subgoal" (all sources) | source indices (World::sources() order) — Builder.add_extras.
@@ -133,6 +133,7 @@ class VecWorld:
         self.obs_type = obs_type
         opts.obs_type, opts.obs_param, self._flatten = obs_spec(obs_type, padding_size)
         opts.randomize_lasers = int(bool(randomize_lasers))
+        opts.episode_stats = int(bool(episode_stats))
         self.state_type = getattr(state_type, "value", state_type)
         opts.state_type, opts.state_param, self._state_flatten = obs_spec(state_type, 0)  # the reference builds it with padding_size = 0 (env.py:86)
         extras_src = None if extras in (None, "laser_subgoal") else [int(x) for x in extras]
@@ -209,6 +210,12 @@ class VecWorld:
             block = shape if b.state_view_agents or int(b.state_type) == OBS_STATE else (A, *shape)
             self.state_obs = rows[:, : int(np.prod(block))].unflatten(1, block)
             self._state_first = bool(not b.state_view_agents and int(b.state_type) != OBS_STATE)
+        #: episode_stats: Step.info of every env (env.py:174-188) and episode return / length accumulators kept by the step kernel
+        self.info_bytes = wrap(b.info, (N, 2 + A), "|u1") if b.info else None
+        self.ep_return = wrap(b.ep_return, (N, self.reward_dim), "<f4") if b.ep_return else None
+        self.ep_length = wrap(b.ep_length, (N,), "<i4") if b.ep_length else None
+        self.last_return = wrap(b.last_return, (N, self.reward_dim), "<f4") if b.last_return else None
+        self.last_length = wrap(b.last_length, (N,), "<i4") if b.last_length else None
         #: LaserSubgoal flags (N, A, n_sources); None when extras are off
         self.extras_dim = int(b.extras_dim)
         self.extras = wrap(b.extras, (N, A, self.extras_dim), "<f4") if self.extras_dim else None
@@ -227,6 +234,18 @@ class VecWorld:
         if not self.obs_view_agents:
             return self.obs
         return self.obs.unsqueeze(1).expand(-1, self.obs_view_agents, *([-1] * (self.obs.dim() - 1)))
+
+    @property
+    def info(self) -> dict:
+        """Step.info of LLE.step (env.py:174-188) for every env, as device tensors (needs episode_stats=True)."""
+        if self.info_bytes is None:
+            raise ValueError("create the batch with episode_stats=True")
+        A, G = self.n_agents, self.n_gems
+        out = {"gems_collected": self.info_bytes[:, 0], "exit_rate": self.info_bytes[:, 1].float() / A}
+        for i in range(A):
+            out[f"has-arrived-{i}"] = self.info_bytes[:, 2 + i].bool()
+            out[f"is-alive-{i}"] = self.state[:, 2 * A + G + i] != 0
+        return out
 
     @property
     def state_of_type(self) -> torch.Tensor:
@@ -319,16 +338,20 @@ class VecWorld:
         (lle_vec_refresh)."""
         check(lib().lle_vec_refresh(self._h, _stream_ptr(self.device)))
 
-    def submit_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor):
-        """Pipelined host-facing step (lle_vec_pipeline_submit): enqueue H2D actions -> step -> D2H reward/done on the vec's
-        own streams and return at once.  Buffers should be pinned and must stay alive until the matching `wait_host()`."""
+    def submit_host(self, actions: np.ndarray | torch.Tensor | None, reward_out: torch.Tensor, done_out: torch.Tensor,
+                    after_current_stream: bool = True):
+        """Pipelined host-facing step (lle_vec_pipeline_submit): H2D copy of the actions, the step (which writes reward / done
+        straight into the pinned host buffers) on the vec's own streams; returns at once.  Buffers must be pinned and stay alive
+        until the matching `wait_host()`.  after_current_stream=False: nothing the step depends on is pending on torch's stream
+        (LLE_STREAM_NONE: a closed host loop that only talks to the env through these two calls)."""
         ptr = None
         if actions is not None:
             t = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(actions)
             assert t.dtype == torch.int8 and t.is_contiguous() and not t.is_cuda
             ptr = t.data_ptr()
         check(lib().lle_vec_pipeline_submit(self._h, ptr, reward_out.data_ptr() if reward_out is not None else None,
-                                            done_out.data_ptr() if done_out is not None else None, _stream_ptr(self.device)))
+                                            done_out.data_ptr() if done_out is not None else None,
+                                            _stream_ptr(self.device) if after_current_stream else C.c_void_p(-1)))
 
     def wait_host(self) -> int:
         """Block until the oldest submitted step's reward / done are in their host buffers; returns the number of steps

@@ -798,3 +798,44 @@ def test_checkpoint_resume_is_bit_identical(layouts):
                 for k in ra:
                     same = torch.equal(ra[k], rb[k]) if isinstance(ra[k], torch.Tensor) else ra[k] == rb[k]
                     assert same, f"raw '{k}' differs {t + 1} steps after the restore"
+
+
+def test_episode_stats_and_info_against_the_oracle():
+    """lle_vec_options.episode_stats: Step.info (env.py:174-188) and the episode return / length kept by the step kernel, against
+    the same quantities accumulated on the host from the oracle's per-step outputs; general kernel and the tiny-map kernel."""
+    import lle_b200
+
+    for text, kw in ((level_text(6), dict(reward_dim=4)), (level_text(3), {}), ("S0 . G\nS1 X X", {}), ("S0 G . V S1\n.  . G . .\nX  . . G X", {})):
+        n = 160
+        vec = lle_b200.VecWorld(text, n, seed=51, episode_stats=True, **kw)
+        ora = lo.OracleVec([text], None, n, seed=51, multi_objective=kw.get("reward_dim", 1) == 4)
+        R, A = vec.reward_dim, vec.n_agents
+        run_ret, run_len = np.zeros((n, R), np.float32), np.zeros(n, np.int32)
+        last_ret, last_len = np.zeros((n, R), np.float32), np.zeros(n, np.int32)
+        arrived = np.zeros((n, A), bool)
+        for t in range(150):
+            vec.step(None)
+            ora.step(None)
+            rew, done, ev = np.asarray(ora.reward), np.asarray(ora.done).astype(bool), np.asarray(ora.events)
+            run_ret += rew
+            run_len += 1
+            arrived |= (ev & 3) == 1  # AgentExit in the first pass (later passes only emit deaths)
+            vec.synchronize()
+            info = vec.info
+            assert np.array_equal(info["exit_rate"].cpu().numpy(), arrived.sum(1).astype(np.float32) / A), f"exit_rate, step {t}"
+            for i in range(A):
+                assert np.array_equal(info[f"has-arrived-{i}"].cpu().numpy(), arrived[:, i]), f"has-arrived-{i}, step {t}"
+            last_ret[done], last_len[done] = run_ret[done], run_len[done]
+            run_ret[done], run_len[done], arrived[done] = 0, 0, False
+            assert np.array_equal(vec.ep_return.cpu().numpy(), run_ret) and np.array_equal(vec.ep_length.cpu().numpy(), run_len), f"running, step {t}"
+            assert np.array_equal(vec.last_return.cpu().numpy(), last_ret) and np.array_equal(vec.last_length.cpu().numpy(), last_len), f"last, step {t}"
+        assert last_len.max() > 0
+        # gems_collected: the N = 1 facade's info (raw engine state) is the reference for the batch
+    env = lle_b200.LLE("S0 G . V S1\n.  . G . .\nX  . . G X")
+    vec = lle_b200.VecWorld("S0 G . V S1\n.  . G . .\nX  . . G X", 1, episode_stats=True, auto_reset=False)
+    env.reset()
+    for acts in ([2, 4], [2, 3], [1, 1], [3, 4]):
+        step = env.step(acts)
+        vec.step(torch.tensor([acts], dtype=torch.int8))
+        vec.synchronize()
+        assert int(vec.info["gems_collected"][0]) == step.info["gems_collected"]

@@ -11,6 +11,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 import torch
 
 import lle_b200
@@ -41,6 +42,7 @@ for parts in args.parts:
     dones = [rec_done[:, h * n:(h + 1) * n].contiguous().pin_memory() for h in range(parts)]
     rw = [torch.empty((n, R), dtype=torch.float32).pin_memory() for _ in range(parts)]
     dn = [torch.empty((n,), dtype=torch.uint8).pin_memory() for _ in range(parts)]
+    dn_np, dones_np = [t.numpy() for t in dn], [t.numpy() for t in dones]
     for rep in range(2):
         for v in vecs:
             v.reset()
@@ -56,13 +58,13 @@ for parts in args.parts:
                     c0 = time.perf_counter_ns()
                     vecs[h].wait_host()
                     c1 = time.perf_counter_ns()
-                    if not torch.equal(dn[h], dones[h][s - 1]):
+                    if not np.array_equal(dn_np[h], dones_np[h][s - 1]):
                         bad += 1
                     c2 = time.perf_counter_ns()
                     t_wait += c1 - c0
                     t_policy += c2 - c1
                 c0 = time.perf_counter_ns()
-                vecs[h].submit_host(a, rw[h], dn[h])
+                vecs[h].submit_host(a, rw[h], dn[h], after_current_stream=False)
                 t_submit += time.perf_counter_ns() - c0
         for h in range(parts):
             vecs[h].wait_host()
