@@ -27,6 +27,8 @@ struct TinyWorld {
     const LleMapHeader* hdr;
     const uint32_t* cellinfo;
     const LleCellBeams* cellbeams;
+    const LlePatch* patches;  // the map's dynamic observation cells (static_map.h)
+    int n_patch;
     uint32_t pos[A_];
     uint32_t alive, arrived, slot, n_arrived, n_deads, done;
 
@@ -35,6 +37,8 @@ struct TinyWorld {
         hdr = reinterpret_cast<const LleMapHeader*>(b);
         cellinfo = reinterpret_cast<const uint32_t*>(b + hdr->cellinfo_off);
         cellbeams = reinterpret_cast<const LleCellBeams*>(b + hdr->cellbeams_off);
+        patches = reinterpret_cast<const LlePatch*>(b + hdr->patch_off);
+        n_patch = hdr->n_patch;
     }
     LLE_HD uint32_t cellof(uint32_t q) const { return (q >> 8) * (uint32_t)W + (q & 0xFFu); }
     LLE_HD uint32_t& on_word(int b) { return rec(L.w_on + b); }
@@ -241,11 +245,14 @@ struct TinyWorld {
     // ---- layered observation (observations.py:254-266) of this world in `sub`, a block of obs_stride floats that holds a
     // copy of the map's static plane (walls, voids, exits, sources: observations.py:216-237).  HW = H*W.
     // A laser cell is lit while its beam bit is on, a gem while it is NOT collected (:256-263); then the agents (:264-265).
-    LLE_HD void render(float* sub, int HW) {
-        const LlePatch* patches = reinterpret_cast<const LlePatch*>(blob + hdr->patch_off);
-        const int n_patch = hdr->n_patch;
+    // `staged(k)`: entry k < kStagedPatches of the map's patch table, copied next to the tile ahead of time (the kernel keeps
+    // them in shared memory: a fresh map with nearly every ticket means a table walk at L2 latency otherwise); the rest is read
+    // from the table itself.
+    static constexpr int kStagedPatches = 8;
+    template <class Staged>
+    LLE_HD void render(float* sub, int HW, Staged staged) {
         for (int k = 0; k < n_patch; ++k) {
-            const LlePatch pe = patches[k];
+            const LlePatch pe = k < kStagedPatches ? staged(k) : patches[k];
             const uint32_t w = rec(pe.src == 0xFF ? L.w_gems : L.w_on + pe.src);
             if ((((w >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;
         }

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     float* tiles = reinterpret_cast<float*>(wbase);                                  // [2][E][ostr]: E worlds per bulk store, two buffers
     uint32_t* srec = reinterpret_cast<uint32_t*>(tiles + 2 * p.tile_floats);         // [stride][32]: word k of lane l at k*32+l
     uint64_t* mbar = reinterpret_cast<uint64_t*>(srec + stride * 32);                // [2]: "the static planes of buffer b have landed"
+    LlePatch* spatch = reinterpret_cast<LlePatch*>(mbar + 2);                        // [8][32]: entry k of lane l's map at k*32+l
+    uint32_t* snext = reinterpret_cast<uint32_t*>(spatch + 8 * 32);                  // [32][stride]: the NEXT ticket's records, prefetched
     if (lane == 0) {
         mbar_init(mbar + 0, (uint32_t)E);  // one arrival (with its byte count) per sub-tile
         mbar_init(mbar + 1, (uint32_t)E);
@@ -116,15 +118,24 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     w.W = W;
     int bound_map = -1;
 
+    // The next (step, ticket) pair is taken, its flag looked at and its records and map index requested while this ticket's
+    // observation is rendered: the latencies of a ticket's first loads hide behind the previous ticket's stores.
+    bool have_next = false, next_ready = false;
+    uint32_t next_pair = 0;
+    int next_map = 0;
     for (;;) {
-        uint32_t pair = 0;
-        if (lane == 0) pair = atomicAdd(&p.sched[0], 1u);
-        pair = __shfl_sync(kFull, pair, 0);
+        uint32_t pair = next_pair;
+        if (!have_next) {
+            if (lane == 0) pair = atomicAdd(&p.sched[0], 1u);
+            pair = __shfl_sync(kFull, pair, 0);
+        }
         if (pair >= n_pairs) break;
+        const bool prefetched = have_next && next_ready;
+        have_next = false;
         const uint32_t ticket = pair % p.n_tickets;
         const int step_index = (int)(pair / p.n_tickets);
         const uint32_t my_seq = p.seq + (uint32_t)step_index;
-        {
+        if (!prefetched) {
             bool flushed = false;
             if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
                 if (owed) {  // never block while owing a completion
@@ -141,14 +152,21 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         const bool real = env < p.N;
 
         // ---- record -> lane-private column of shared memory (through L2: an overlapped launch may just have written it)
-        {
+        int map_id = next_map;
+        if (prefetched) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            for (int q = 0; q < stride / 4; ++q) {
+                const uint4 v = *reinterpret_cast<const uint4*>(snext + lane * stride + 4 * q);
+                w.rec(4 * q + 0) = v.x; w.rec(4 * q + 1) = v.y; w.rec(4 * q + 2) = v.z; w.rec(4 * q + 3) = v.w;
+            }
+        } else {
             const uint4* src = reinterpret_cast<const uint4*>(p.records + env * stride);
             for (int q = 0; q < stride / 4; ++q) {
                 const uint4 v = __ldcg(src + q);
                 w.rec(4 * q + 0) = v.x; w.rec(4 * q + 1) = v.y; w.rec(4 * q + 2) = v.z; w.rec(4 * q + 3) = v.w;
             }
+            map_id = p.map_of_env ? __ldcg(p.map_of_env + env) : 0;
         }
-        const int map_id = p.map_of_env ? __ldcg(p.map_of_env + env) : 0;
         if (map_id != bound_map) {
             w.bind(p.blobs[map_id]);
             bound_map = map_id;
@@ -158,6 +176,13 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         // the static planes (observations.py:216-237) of the first E worlds start moving into the next tile buffer now; the buffer's
         // last store (two stores ago) must have finished reading it
         const float* my_stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
+        {   // ... and the head of the map's patch table moves next to the tile (8 bytes per entry, asynchronous copies)
+            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(spatch + lane);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (uint32_t)k * 256u), "l"(w.patches + k) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
         if (lane < E) bulk_load_arrive(tiles + (size_t)(use & 1u) * p.tile_floats + (size_t)lane * ostr, my_stat, tile_bytes, mbar + (use & 1u));
@@ -250,6 +275,24 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         __syncwarp();
 
+        {   // take the next pair now; if its previous step is already complete, start moving its records and map index
+            uint32_t np2 = 0;
+            int rdy = 0;
+            if (lane == 0) {
+                np2 = atomicAdd(&p.sched[0], 1u);
+                if (np2 < n_pairs) rdy = ticket_ready(p.flags + np2 % p.n_tickets, p.seq + np2 / p.n_tickets - 1u) ? 1 : 0;
+            }
+            next_pair = __shfl_sync(kFull, np2, 0);
+            next_ready = __shfl_sync(kFull, rdy, 0) != 0;
+            have_next = true;
+            if (next_ready) {
+                const int64_t env2 = (int64_t)(next_pair % p.n_tickets) * 32 + lane;
+                const uint32_t* src = p.records + env2 * stride;
+                for (int q = 0; q < stride / 4; ++q) cp_async16(snext + lane * stride + 4 * q, src + 4 * q);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                next_map = p.map_of_env ? __ldcg(p.map_of_env + env2) : 0;
+            }
+        }
         // ---- layered observation (observations.py:254-266), E worlds per bulk store.  The static planes of round r + 1 travel
         // while round r is patched and stored; those of round 0 were requested before the logic above.
         for (int r = 0; r < 32 / E; ++r) {
@@ -260,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             }
             float* tile = tiles + (size_t)(use & 1u) * p.tile_floats;
             mbar_wait(mbar + (use & 1u), (use >> 1) & 1u);
-            if (lane / E == r) w.render(tile + (size_t)(lane - r * E) * ostr, p.HW);
+            if (r == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");  // this lane's patch entries have landed
+            if (lane / E == r) w.render(tile + (size_t)(lane - r * E) * ostr, p.HW, [&](int k) { return spatch[k * 32 + lane]; });
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {

@@ -678,8 +678,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (v->tiny) {
         int e = env_int("LLE_B200_TINY_E", v->E);
         v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 8;
-        auto tiny_bytes = [&](int E) {  // two tile buffers, the records' columns, two mbarriers
-            const size_t bytes = 2 * (size_t)E * stride * 4 + (size_t)v->L.stride * 32 * 4 + 16;
+        auto tiny_bytes = [&](int E) {  // two tile buffers, the records' columns + the prefetched next records, two mbarriers, 8 staged patch entries per lane
+            const size_t bytes = 2 * (size_t)E * stride * 4 + 2 * (size_t)v->L.stride * 32 * 4 + 16 + 8 * 32 * sizeof(LlePatch);
             return (bytes + 127) / 128 * 128;
         };
         while (v->tiny_E > 4 && tiny_bytes(v->tiny_E) * kWarps > (size_t)(96 << 10)) v->tiny_E /= 2;  // at least two CTAs per SM

@@ -638,7 +638,7 @@ __device__ __forceinline__ void tile_rebuild_async(float* sub_tile, const MapDev
 // and consumed with an acquire before the records are read (through L2).
 __device__ __forceinline__ void ticket_release(uint32_t* flag, uint32_t seq) {
     asm volatile("fence.proxy.async;" ::: "memory");  // completed async-proxy (bulk) writes before the generic-proxy release
-    __threadfence();
+    // st.release orders every earlier write of this thread, and (cumulatively) of the lanes it synchronised with, before the flag
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
 }
 __device__ __forceinline__ bool sys_flag_ready(const uint32_t* flag, uint32_t need) {

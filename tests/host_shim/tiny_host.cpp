@@ -149,7 +149,7 @@ void step_all(Shim& s, const int8_t* actions_in) {
                 float* sub = wp.tile.data() + (size_t)sidx * s.ostr;
                 const float* stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
                 for (int64_t f = 0; f < s.ostr; ++f) sub[f] = f < w.hdr->obs_floats ? stat[f] : 0.0f;
-                w.render(sub, s.H * s.W);
+                w.render(sub, s.H * s.W, [&](int k) { return w.patches[k]; });
             }
             for (int sidx = 0; sidx < E; ++sidx) {
                 const int64_t env = ticket * 32 + (int64_t)r * E + sidx;

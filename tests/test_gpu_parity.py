@@ -831,11 +831,22 @@ def test_episode_stats_and_info_against_the_oracle():
             assert np.array_equal(vec.last_return.cpu().numpy(), last_ret) and np.array_equal(vec.last_length.cpu().numpy(), last_len), f"last, step {t}"
         assert last_len.max() > 0
         # gems_collected: the N = 1 facade's info (raw engine state) is the reference for the batch
-    env = lle_b200.LLE("S0 G . V S1\n.  . G . .\nX  . . G X")
-    vec = lle_b200.VecWorld("S0 G . V S1\n.  . G . .\nX  . . G X", 1, episode_stats=True, auto_reset=False)
+    text = "S0 G . V S1\n.  . G . .\nX  . . G X"
+    env = lle_b200.LLE(text)
+    vec = lle_b200.VecWorld(text, 1, episode_stats=True, auto_reset=False)
     env.reset()
-    for acts in ([2, 4], [2, 3], [1, 1], [3, 4]):
+    rng = np.random.default_rng(3)
+    seen = set()
+    for _ in range(120):
+        mask = env.available_actions()
+        acts = [int(rng.choice(np.flatnonzero(mask[a]))) for a in range(2)]
         step = env.step(acts)
         vec.step(torch.tensor([acts], dtype=torch.int8))
         vec.synchronize()
         assert int(vec.info["gems_collected"][0]) == step.info["gems_collected"]
+        assert float(vec.info["exit_rate"][0]) == step.info["exit_rate"]
+        seen.add(step.info["gems_collected"])
+        if step.done:
+            env.reset()
+            vec.reset()
+    assert len(seen) >= 2
