@@ -358,6 +358,22 @@ def run_ours(args) -> None:
     assert mismatches[0] == 0 and all(int(v.err.sum()) == 0 for v in parts), "the closed loop left the recorded trajectory"
     del parts
 
+    # the same closed loop driven by a COMPILED host on the C ABI alone (examples/c_closed_loop.c): what the reference's Rust side
+    # would see through FFI.  One process per rank on the rank's own device, all ranks at once.
+    compiled = None
+    exe = os.path.join(ROOT, "examples", "_build", "c_closed_loop")
+    if os.path.exists(exe) and not args.no_compiled_host:
+        barrier()
+        try:
+            res = subprocess.run([exe, str(local_rank), str(n_envs), str(Ke), str(P)], capture_output=True, text=True, timeout=300)
+            got = json.loads(res.stdout.strip().splitlines()[-1]) if res.returncode == 0 else None
+        except Exception:
+            got = None
+        us = reduce_max(got["parts"][str(P)]["us_per_step"] if got else float("inf"))
+        if us != float("inf"):
+            compiled = {"value": world_size * n_envs / (us / 1e6), "us_per_step": us, "sub_batches_in_flight": P, "steps": Ke,
+                        "host": "compiled C program on the C ABI alone (examples/c_closed_loop.c), one per rank"}
+
     # end-of-run stats reduction: the only collective on this path (NCCL all-reduce of a few counters)
     stats = reduce_stats(torch.stack([vec.done.sum().to(torch.int64), vec.reward.sum().to(torch.int64),
                                       torch.tensor(n_envs, dtype=torch.int64, device=dev)]))
@@ -417,10 +433,12 @@ def run_ours(args) -> None:
             },
             "ranks": {"ms_per_step_min": min(per_rank), "ms_per_step_max": max(per_rank), "ms_per_step": per_rank},
             "clocks": clocks,
-            "e2e": {"value": e2e_closed_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A, "d2h_bytes_per_step": n_envs * (4 * R + 1),
-                    "steps": Ke, "closed_loop": True, "sub_batches_in_flight": P,
+            "e2e": {"value": compiled["value"] if compiled else e2e_closed_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A,
+                    "d2h_bytes_per_step": n_envs * (4 * R + 1), "steps": Ke, "closed_loop": True, "sub_batches_in_flight": P,
+                    "host": compiled["host"] if compiled else "python", "python_host_value": e2e_closed_value,
                     "pipelined_value": e2e_pipe_value, "pipeline_depth": D, "sync_value": e2e_sync_value,
-                    "note": f"value: CLOSED loop through lle_vec_pipeline_submit/_wait on {P} sub-batches (vecs over the same global "
+                    "note": f"value: CLOSED loop through lle_vec_pipeline_submit/_wait from a compiled host (the reference's host side is "
+                            f"Rust; python_host_value is the same loop driven from Python) on {P} sub-batches (vecs over the same global "
                             "env ids): the host reads every done flag of a sub-batch's step t from pinned memory before it submits that "
                             "sub-batch's step t+1, while the others step; every step copies its actions H2D (copy engine) and writes reward+done "
                             "D2H (zero-copy stores of the step kernel) inside the timed region. sync_value: the same dependency with one "
@@ -460,6 +478,7 @@ def main():
     ap.add_argument("--e2e-parts", type=int, default=4, help="sub-batches in flight in the closed-loop arm")
     ap.add_argument("--preheat-ms", type=float, default=250.0, help="untimed device work before the warm-up steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-compiled-host", action="store_true", help="skip the compiled-host closed loop of the e2e arm")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE workloads")
     args = ap.parse_args()
     if args.impl == "reference":

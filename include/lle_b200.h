@@ -261,6 +261,13 @@ LLE_API int lle_vec_rollout(lle_vec* vec, int32_t n_steps, void* cuda_stream);
  * stream.  The observation stays resident in HBM (zero-copy DLPack hand-off to the policy). */
 LLE_API int lle_vec_step_host(lle_vec* vec, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* cuda_stream);
 
+/* Copies `bytes` bytes, starting at byte `offset`, of one of the per-step buffers of lle_vec_get_buffers to host memory after
+ * waiting for the work queued on cuda_stream - for hosts without a CUDA runtime of their own (the reference's Rust crate), e.g.
+ * to look at an observation or to record the actions the device sampled.  The same role as lle_gen_fetch. */
+enum { LLE_BUF_OBS = 0, LLE_BUF_STATE = 1, LLE_BUF_AVAIL = 2, LLE_BUF_REWARD = 3, LLE_BUF_DONE = 4, LLE_BUF_EVENTS = 5, LLE_BUF_ACTIONS = 6,
+       LLE_BUF_ERR = 7, LLE_BUF_EXTRAS = 8, LLE_BUF_STATE_OBS = 9, LLE_BUF_INFO = 10 };
+LLE_API int lle_vec_fetch(lle_vec* vec, int which, size_t offset, size_t bytes, void* host_dst, void* cuda_stream);
+
 /* Page-locked (pinned) host memory for the host-facing calls below.  lle_vec_pipeline_submit REQUIRES its action / reward / done
  * buffers to be pinned (memory from here, cudaHostAlloc, cudaHostRegister or torch's pin_memory): the step kernel waits on the
  * device for the action copy and writes reward / done straight into the host buffers.  A host without a CUDA runtime of its own

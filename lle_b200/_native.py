@@ -20,7 +20,7 @@ SYMBOLS = [
     "lle_vec_destroy", "lle_vec_get_buffers", "lle_vec_reset", "lle_vec_refresh", "lle_vec_step", "lle_vec_rollout", "lle_vec_step_host", "lle_vec_pipeline_submit",
     "lle_vec_pipeline_wait", "lle_vec_set_source", "lle_vec_get_sources", "lle_vec_set_exits", "lle_vec_collect_gem", "lle_vec_set_state",
     "lle_vec_export_raw", "lle_vec_set_seed", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
-    "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline", "lle_host_alloc", "lle_host_free", "lle_vec_export_raw_state", "lle_vec_import_raw_state",
+    "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline", "lle_host_alloc", "lle_host_free", "lle_vec_fetch", "lle_vec_export_raw_state", "lle_vec_import_raw_state",
     "lle_vec_get_reset_count", "lle_vec_set_reset_count",
     "lle_gen_default_options", "lle_gen_create", "lle_gen_destroy", "lle_gen_attempt_seeds", "lle_gen_run", "lle_gen_get_buffers",
     "lle_gen_fetch", "lle_gen_geometry_valid", "lle_gen_cells_to_text",
@@ -125,6 +125,7 @@ def lib():
     L.lle_vec_import_raw_state.argtypes = [C.c_void_p, C.POINTER(RawState), C.c_void_p]
     L.lle_vec_get_reset_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.lle_vec_set_reset_count.argtypes = [C.c_void_p, C.c_uint32]
+    L.lle_vec_fetch.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
     L.lle_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.lle_host_free.argtypes = [C.c_void_p]
     L.lle_gen_default_options.argtypes = [C.POINTER(GenOptions)]

@@ -396,6 +396,16 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         obs_c = obs_floats; obs_h = obs_w = 0;
     }
     std::stable_sort(patch.begin(), patch.end(), [](const LlePatch& x, const LlePatch& y) { return x.idx < y.idx; });
+    // The render list of the tiny-map kernel: the non-zero floats of the static plane (src = LLE_FEATURE_STATIC, stat = the
+    // value), then a copy of the dynamic entries above.  A tiny tile is zero-filled and this list is applied to it.
+    std::vector<LlePatch> static_list;
+    int n_static = 0;
+    if (spec.kind == LLE_OBS_LAYERED) {
+        for (size_t k = 0; k < stat.size(); ++k)
+            if (stat[k] != 0.0f) static_list.push_back(LlePatch{(uint32_t)k, LLE_FEATURE_STATIC, 0, (int8_t)stat[k], 0});
+        n_static = (int)static_list.size();
+        static_list.insert(static_list.end(), patch.begin(), patch.end());
+    }
 
     // ---- blob
     LleMapHeader h;
@@ -415,6 +425,8 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     h.patch_off = (uint32_t)off;   off = align16(off + std::max<size_t>(patch.size(), 1) * sizeof(LlePatch));
     h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
     h.ap_off = (uint32_t)off;      off = align16(off + std::max<size_t>(planes.size(), 1) * sizeof(LleAgentPlane));
+    h.n_static = n_static;
+    h.static_list_off = (uint32_t)off; off = align16(off + std::max<size_t>(static_list.size(), 16) * sizeof(LlePatch));  // the kernel stages 16 entries blindly
     // start candidates (World.random_start_positions): per agent (first index, count), then the packed positions
     std::vector<uint32_t> cand_index;
     std::vector<uint16_t> cand_pos;
@@ -500,6 +512,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
         std::memcpy(cm.blob.data() + h.cellbeams_off, cb.data(), cb.size() * sizeof(LleCellBeams));
     }
     if (!patch.empty()) std::memcpy(cm.blob.data() + h.patch_off, patch.data(), patch.size() * sizeof(LlePatch));
+    if (!static_list.empty()) std::memcpy(cm.blob.data() + h.static_list_off, static_list.data(), static_list.size() * sizeof(LlePatch));
     std::memcpy(cm.blob.data() + h.static_off, stat.data(), stat.size() * sizeof(float));
     std::memcpy(cm.blob.data() + h.chunk_tbl_off, chunk_tbl.data(), chunk_tbl.size() * sizeof(uint32_t));
     std::memcpy(cm.blob.data() + h.cand_index_off, cand_index.data(), cand_index.size() * sizeof(uint32_t));

@@ -107,11 +107,11 @@ struct LleMapHeader {
     int32_t n_ap;                  // entries of the agent-plane table
     uint32_t ap_off;               // LleAgentPlane[n_ap]
     uint32_t chunk_tbl_off;        // uint32_t[n_chunks + 1]: patch index range of every chunk of lle_chunk_floats(padded block) floats
-    uint32_t pad1;
+    int32_t n_static;              // layered observations: non-zero floats of the static plane, listed at static_list_off
     int32_t random_starts;         // some agent has several start candidates: World::reset samples (world.rs:421)
     uint32_t cand_index_off;       // uint32_t[2*A]: first index and count of each agent's candidates in cand_pos
     uint32_t cand_pos_off;         // uint16_t[]: packed candidate positions, sorted like AgentConfig::compute_start_positions
-    uint32_t pad3;
+    uint32_t static_list_off;      // LlePatch[n_static + n_patch]: the static floats (idx, stat = value), then a copy of the patch table
     uint8_t start_order[LLE_MAX_AGENTS];  // agents by increasing number of candidates (stable), the order sample_different assigns them
     uint16_t start[LLE_MAX_AGENTS];   // packed position (i<<8 | j); with random starts: the first candidate
     uint16_t gem_pos[LLE_MAX_GEMS];   // packed position, gems_positions order (parser_v1.rs:149)

@@ -27,8 +27,8 @@ struct TinyWorld {
     const LleMapHeader* hdr;
     const uint32_t* cellinfo;
     const LleCellBeams* cellbeams;
-    const LlePatch* patches;  // the map's dynamic observation cells (static_map.h)
-    int n_patch;
+    const LlePatch* list;  // the map's render list (static_map.h: static_list_off): n_static static floats, then n_patch dynamic cells
+    int n_static, n_patch;
     uint32_t pos[A_];
     uint32_t alive, arrived, slot, n_arrived, n_deads, done;
 
@@ -37,7 +37,8 @@ struct TinyWorld {
         hdr = reinterpret_cast<const LleMapHeader*>(b);
         cellinfo = reinterpret_cast<const uint32_t*>(b + hdr->cellinfo_off);
         cellbeams = reinterpret_cast<const LleCellBeams*>(b + hdr->cellbeams_off);
-        patches = reinterpret_cast<const LlePatch*>(b + hdr->patch_off);
+        list = reinterpret_cast<const LlePatch*>(b + hdr->static_list_off);
+        n_static = hdr->n_static;
         n_patch = hdr->n_patch;
     }
     LLE_HD uint32_t cellof(uint32_t q) const { return (q >> 8) * (uint32_t)W + (q & 0xFFu); }
@@ -242,17 +243,21 @@ struct TinyWorld {
         }
     }
 
-    // ---- layered observation (observations.py:254-266) of this world in `sub`, a block of obs_stride floats that holds a
-    // copy of the map's static plane (walls, voids, exits, sources: observations.py:216-237).  HW = H*W.
-    // A laser cell is lit while its beam bit is on, a gem while it is NOT collected (:256-263); then the agents (:264-265).
-    // `staged(k)`: entry k < kStagedPatches of the map's patch table, copied next to the tile ahead of time (the kernel keeps
-    // them in shared memory: a fresh map with nearly every ticket means a table walk at L2 latency otherwise); the rest is read
-    // from the table itself.
-    static constexpr int kStagedPatches = 8;
+    // ---- layered observation (observations.py:254-266) of this world in `sub`, a ZERO-FILLED block of obs_stride floats.
+    // Write order of the reference: the static layers (walls, voids, exits = 1, sources = -1; :216-237), the laser cells whose
+    // beam bit is on and the gems that are NOT collected (= 1; :256-263), then the agents (:264-265).  HW = H*W.
+    // `staged(k)`: entry k < kStaged of the map's render list, copied next to the tile ahead of time (the kernel keeps them in
+    // shared memory: a warp meets another map with nearly every ticket of a heterogeneous batch, and a table walk at L2 latency
+    // per ticket is what bounds it otherwise); entries beyond are read from the list itself.
+    static constexpr int kStaged = 16;
     template <class Staged>
     LLE_HD void render(float* sub, int HW, Staged staged) {
-        for (int k = 0; k < n_patch; ++k) {
-            const LlePatch pe = k < kStagedPatches ? staged(k) : patches[k];
+        for (int k = 0; k < n_static; ++k) {
+            const LlePatch pe = k < kStaged ? staged(k) : list[k];
+            sub[pe.idx] = (float)pe.stat;
+        }
+        for (int k = n_static; k < n_static + n_patch; ++k) {
+            const LlePatch pe = k < kStaged ? staged(k) : list[k];
             const uint32_t w = rec(pe.src == 0xFF ? L.w_gems : L.w_on + pe.src);
             if ((((w >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;
         }

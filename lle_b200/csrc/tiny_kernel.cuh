@@ -9,12 +9,12 @@
 //     enter, repeated while somebody died (world.rs:454-505) — with positions, flags and events in registers and the beam /
 //     gem masks in a lane-private column of shared memory (dynamic index by beam): no ballots, no shuffles, no predicated
 //     phases, and 32 worlds advance per warp pass instead of 32 / Wd;
-//   * an observation tile holds E worlds.  Each of its sub-tiles is first filled with the static plane of its world's map by ONE
-//     TMA bulk load (issued by the lane that owns the world, completing on an mbarrier) — a warp meets another map with nearly
-//     every ticket of a heterogeneous batch, so there is nothing to un-patch, and 16-byte copies cost 40 % of the kernel's
-//     instructions (profiles/ncu_cfg3_tiny_r02_summary.csv) — into one of two tile buffers, a round ahead of its use; then E
-//     lanes patch their own sub-tile (lit laser cells, uncollected gems, the agents' one-hots) and the tile leaves with one
-//     TMA bulk store;
+//   * an observation tile holds E worlds.  A warp meets another map with nearly every ticket of a heterogeneous batch, so there is
+//     nothing to un-patch, and copying 800-byte static planes around costs more instructions than they are worth (16-byte
+//     copies: 40 % of the kernel; one TMA bulk load per world: 12 %, plus a second tile buffer — profiles/ncu_cfg3_tiny_r02*):
+//     the warp zero-fills the tile, then E lanes apply their map's render list (the dozen non-zero static floats, the lit laser
+//     cells, the uncollected gems, staged in shared memory ahead of time) and their agents' one-hots to their own sub-tile, and
+//     the tile leaves with one TMA bulk store;
 //   * every lane follows its own map (blob pointer per lane), so heterogeneous batches need no uniformity checks.
 // Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
 // per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
@@ -37,30 +37,6 @@ struct SmemColumn {
     int pitch;
     __device__ __forceinline__ uint32_t& operator()(int word) const { return base[word * pitch]; }
 };
-
-// ---- TMA 1-D bulk LOAD (global -> shared) completing on an mbarrier: one instruction moves a world's whole static plane
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
-}
-__device__ __forceinline__ void bulk_load_arrive(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(sdst);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}" ::"r"(b), "r"(parity)
-        : "memory");
-}
 
 // `n` bytes (compile-time) from registers to global memory with the widest stores the alignment of `n` allows
 template <int N>
@@ -85,20 +61,13 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     const int stride = p.L.stride, w_flags = p.L.w_flags, w_avail = p.L.w_avail, w_gems = p.L.w_gems, w_on = p.L.w_on;
     const bool has_gems = p.L.gem_words != 0;
     const int W = p.W, E = p.E, ostr = (int)p.obs_stride;
+    constexpr int kStaged = TinyWorld<A_, SmemColumn>::kStaged;
     uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
-    float* tiles = reinterpret_cast<float*>(wbase);                                  // [2][E][ostr]: E worlds per bulk store, two buffers
-    uint32_t* srec = reinterpret_cast<uint32_t*>(tiles + 2 * p.tile_floats);         // [stride][32]: word k of lane l at k*32+l
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(srec + stride * 32);                // [2]: "the static planes of buffer b have landed"
-    LlePatch* spatch = reinterpret_cast<LlePatch*>(mbar + 2);                        // [8][32]: entry k of lane l's map at k*32+l
-    uint32_t* snext = reinterpret_cast<uint32_t*>(spatch + 8 * 32);                  // [32][stride]: the NEXT ticket's records, prefetched
-    if (lane == 0) {
-        mbar_init(mbar + 0, (uint32_t)E);  // one arrival (with its byte count) per sub-tile
-        mbar_init(mbar + 1, (uint32_t)E);
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    uint32_t use = 0;  // tile buffer uses so far: buffer = use & 1, mbarrier phase parity = (use >> 1) & 1
-    const uint32_t tile_bytes = (uint32_t)ostr * 4u;
+    float* tile = reinterpret_cast<float*>(wbase);                                   // [E][ostr]: E worlds per bulk store
+    uint32_t* srec = reinterpret_cast<uint32_t*>(tile + p.tile_floats);              // [stride][32]: word k of lane l at k*32+l
+    uint32_t* snext = srec + stride * 32;                                            // [32][stride]: the NEXT ticket's records, prefetched
+    LlePatch* slist = reinterpret_cast<LlePatch*>(snext + stride * 32);              // [kStaged][32]: entry k of lane l's render list at k*32+l
+    const int lgE = 31 - __clz(E), rounds = 32 >> lgE;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
         if (lane == 0)
@@ -110,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     __syncwarp();
 
     const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;
+    const bool single_step = p.n_steps == 1;
     uint32_t owed_ticket = 0, owed_seq = 0;
     bool owed = false;
     TinyWorld<A_, SmemColumn> w;
@@ -132,8 +102,9 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         if (pair >= n_pairs) break;
         const bool prefetched = have_next && next_ready;
         have_next = false;
-        const uint32_t ticket = pair % p.n_tickets;
-        const int step_index = (int)(pair / p.n_tickets);
+        // (step, ticket) of a pair; one step per launch is the common case and needs no division
+        const uint32_t ticket = single_step ? pair : pair % p.n_tickets;
+        const int step_index = single_step ? 0 : (int)(pair / p.n_tickets);
         const uint32_t my_seq = p.seq + (uint32_t)step_index;
         if (!prefetched) {
             bool flushed = false;
@@ -173,19 +144,13 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         w.unpack();
         const uint32_t av_cache = w.rec(w_avail);  // World::available_actions cache: one byte per agent (A_ <= 4)
-        // the static planes (observations.py:216-237) of the first E worlds start moving into the next tile buffer now; the buffer's
-        // last store (two stores ago) must have finished reading it
-        const float* my_stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
-        {   // ... and the head of the map's patch table moves next to the tile (8 bytes per entry, asynchronous copies)
-            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(spatch + lane);
+        {   // the head of the map's render list moves next to the tile (8 bytes per entry, asynchronous copies): ready by render time
+            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(slist + lane);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (uint32_t)k * 256u), "l"(w.patches + k) : "memory");
+            for (int k = 0; k < kStaged; ++k)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (uint32_t)k * 256u), "l"(w.list + k) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-        if (lane < E) bulk_load_arrive(tiles + (size_t)(use & 1u) * p.tile_floats + (size_t)lane * ostr, my_stat, tile_bytes, mbar + (use & 1u));
 
         // ---- actions (world.rs:444-453): supplied, or sampled uniformly among the available ones
         uint32_t act[A_], ev[A_];
@@ -275,36 +240,32 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         __syncwarp();
 
+        // ---- layered observation (observations.py:254-266), E worlds per bulk store
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this lane's render-list entries have landed
         {   // take the next pair now; if its previous step is already complete, start moving its records and map index
             uint32_t np2 = 0;
             int rdy = 0;
             if (lane == 0) {
                 np2 = atomicAdd(&p.sched[0], 1u);
-                if (np2 < n_pairs) rdy = ticket_ready(p.flags + np2 % p.n_tickets, p.seq + np2 / p.n_tickets - 1u) ? 1 : 0;
+                if (np2 < n_pairs) rdy = ticket_ready(p.flags + (single_step ? np2 : np2 % p.n_tickets), p.seq + (single_step ? 0u : np2 / p.n_tickets) - 1u) ? 1 : 0;
             }
             next_pair = __shfl_sync(kFull, np2, 0);
             next_ready = __shfl_sync(kFull, rdy, 0) != 0;
             have_next = true;
             if (next_ready) {
-                const int64_t env2 = (int64_t)(next_pair % p.n_tickets) * 32 + lane;
+                const int64_t env2 = (int64_t)(single_step ? next_pair : next_pair % p.n_tickets) * 32 + lane;
                 const uint32_t* src = p.records + env2 * stride;
                 for (int q = 0; q < stride / 4; ++q) cp_async16(snext + lane * stride + 4 * q, src + 4 * q);
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 next_map = p.map_of_env ? __ldcg(p.map_of_env + env2) : 0;
             }
         }
-        // ---- layered observation (observations.py:254-266), E worlds per bulk store.  The static planes of round r + 1 travel
-        // while round r is patched and stored; those of round 0 were requested before the logic above.
-        for (int r = 0; r < 32 / E; ++r) {
-            if (r + 1 < 32 / E) {
-                if (lane == 0) bulk_wait_read<0>();  // the other buffer's last store (round r - 1) has finished reading it
-                __syncwarp();
-                if (lane / E == r + 1) bulk_load_arrive(tiles + (size_t)((use + 1) & 1u) * p.tile_floats + (size_t)(lane - (r + 1) * E) * ostr, my_stat, tile_bytes, mbar + ((use + 1) & 1u));
-            }
-            float* tile = tiles + (size_t)(use & 1u) * p.tile_floats;
-            mbar_wait(mbar + (use & 1u), (use >> 1) & 1u);
-            if (r == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");  // this lane's patch entries have landed
-            if (lane / E == r) w.render(tile + (size_t)(lane - r * E) * ostr, p.HW, [&](int k) { return spatch[k * 32 + lane]; });
+        for (int r = 0; r < rounds; ++r) {
+            if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
+            __syncwarp();
+            for (int f = lane * 4; f < E * ostr; f += 128) *reinterpret_cast<float4*>(tile + f) = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if ((lane >> lgE) == r) w.render(tile + (size_t)(lane & (E - 1)) * ostr, p.HW, [&](int k) { return slist[k * 32 + lane]; });
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -315,7 +276,6 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                     ticket_release(p.flags + owed_ticket, owed_seq);
                 }
             }
-            ++use;
         }
         owed = true; owed_ticket = ticket; owed_seq = my_seq;
         __syncwarp();

@@ -678,8 +678,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     if (v->tiny) {
         int e = env_int("LLE_B200_TINY_E", v->E);
         v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 8;
-        auto tiny_bytes = [&](int E) {  // two tile buffers, the records' columns + the prefetched next records, two mbarriers, 8 staged patch entries per lane
-            const size_t bytes = 2 * (size_t)E * stride * 4 + 2 * (size_t)v->L.stride * 32 * 4 + 16 + 8 * 32 * sizeof(LlePatch);
+        auto tiny_bytes = [&](int E) {  // one tile, the records' columns + the prefetched next records, 16 staged render-list entries per lane
+            const size_t bytes = (size_t)E * stride * 4 + 2 * (size_t)v->L.stride * 32 * 4 + 16 * 32 * sizeof(LlePatch);
             return (bytes + 127) / 128 * 128;
         };
         while (v->tiny_E > 4 && tiny_bytes(v->tiny_E) * kWarps > (size_t)(96 << 10)) v->tiny_E /= 2;  // at least two CTAs per SM
@@ -1052,6 +1052,33 @@ int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host
     if (reward_host) LLE_CUDA(cudaMemcpyAsync(reward_host, v->d_reward, (size_t)v->N * v->R * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (done_host) LLE_CUDA(cudaMemcpyAsync(done_host, v->d_done, (size_t)v->N, cudaMemcpyDeviceToHost, s));
     LLE_CUDA(cudaStreamSynchronize(s));
+    return LLE_OK;
+}
+
+int lle_vec_fetch(lle_vec* v, int which, size_t offset, size_t bytes, void* host_dst, void* stream) {
+    if (!v || !host_dst) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    const size_t N = (size_t)v->N, A = (size_t)v->A;
+    const void* src = nullptr;
+    size_t size = 0;
+    switch (which) {
+        case LLE_BUF_OBS: src = v->d_obs; size = N * (size_t)v->obs_stride * 4; break;
+        case LLE_BUF_STATE: src = v->d_state; size = N * (size_t)v->S * 4; break;
+        case LLE_BUF_AVAIL: src = v->d_avail; size = N * A * 5; break;
+        case LLE_BUF_REWARD: src = v->d_reward; size = N * (size_t)v->R * 4; break;
+        case LLE_BUF_DONE: src = v->d_done; size = N; break;
+        case LLE_BUF_EVENTS: src = v->d_events; size = N * A; break;
+        case LLE_BUF_ACTIONS: src = v->d_actions; size = N * A; break;
+        case LLE_BUF_ERR: src = v->d_err; size = N; break;
+        case LLE_BUF_EXTRAS: src = v->d_extras; size = N * A * (size_t)v->JE * 4; break;
+        case LLE_BUF_STATE_OBS: src = v->shadow ? v->shadow->d_obs : nullptr; size = v->shadow ? N * (size_t)v->shadow->obs_stride * 4 : 0; break;
+        case LLE_BUF_INFO: src = v->d_info; size = N * (2 + A); break;
+        default: return fail(LLE_INVALID_ARGUMENT, "unknown buffer");
+    }
+    if (!src) return fail(LLE_INVALID_ARGUMENT, "the vec does not keep that buffer");
+    if (offset > size || bytes > size - offset) return fail(LLE_INDEX_ERROR, "range outside the buffer");
+    LLE_CUDA(cudaSetDevice(v->device));
+    LLE_CUDA(cudaMemcpyAsync(host_dst, (const uint8_t*)src + offset, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LLE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return LLE_OK;
 }
 

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE: a host (g++) instantiation of the per-world core of the tiny-map step kernel
 // (lle_b200/csrc/tiny_core.cuh is __host__ __device__), driven the way lle_tiny_step_kernel drives it — tickets of 32
-// consecutive worlds, one world per "lane", E sub-tiles per emulated warp rebuilt from the static planes — so that
+// consecutive worlds, one world per "lane", E zero-filled sub-tiles per emulated warp — so that
 // `-m "not gpu"` tests can compare the very code the kernel runs per thread with the oracle, bit for bit, without a GPU.
 // The maps are compiled by the product's own host map compiler.  The product never loads this file.
 #include <cstdint>
@@ -147,9 +147,8 @@ void step_all(Shim& s, const int8_t* actions_in) {
                 auto& w = lanes[(size_t)lane];
                 const int sidx = lane - r * E;
                 float* sub = wp.tile.data() + (size_t)sidx * s.ostr;
-                const float* stat = reinterpret_cast<const float*>(w.blob + w.hdr->static_off);
-                for (int64_t f = 0; f < s.ostr; ++f) sub[f] = f < w.hdr->obs_floats ? stat[f] : 0.0f;
-                w.render(sub, s.H * s.W, [&](int k) { return w.patches[k]; });
+                for (int64_t f = 0; f < s.ostr; ++f) sub[f] = 0.0f;
+                w.render(sub, s.H * s.W, [&](int k) { return w.list[k]; });
             }
             for (int sidx = 0; sidx < E; ++sidx) {
                 const int64_t env = ticket * 32 + (int64_t)r * E + sidx;
