@@ -9,12 +9,15 @@
 //     enter, repeated while somebody died (world.rs:454-505) — with positions, flags and events in registers and the beam /
 //     gem masks in a lane-private column of shared memory (dynamic index by beam): no ballots, no shuffles, no predicated
 //     phases, and 32 worlds advance per warp pass instead of 32 / Wd;
-//   * an observation tile holds E worlds.  A warp meets another map with nearly every ticket of a heterogeneous batch, so there is
-//     nothing to un-patch, and copying 800-byte static planes around costs more instructions than they are worth (16-byte
-//     copies: 40 % of the kernel; one TMA bulk load per world: 12 %, plus a second tile buffer — profiles/ncu_cfg3_tiny_r02*):
-//     the warp zero-fills the tile, then E lanes apply their map's render list (the dozen non-zero static floats, the lit laser
-//     cells, the uncollected gems, staged in shared memory ahead of time) and their agents' one-hots to their own sub-tile, and
-//     the tile leaves with one TMA bulk store;
+//   * the observation is written WITHOUT a shared-memory tile.  A 5x5 layered block is 200 floats of which about 16 are not
+//     zero (a dozen static cells, the lit laser cells, the uncollected gems, the agents), and a warp meets another map with
+//     nearly every ticket of a heterogeneous batch, so there is nothing to keep between tickets.  The warp zero-fills the
+//     ticket's 32 blocks in HBM with fully coalesced 16-byte stores (the write stream the roofline counts), then every lane
+//     applies its map's render list and its agents' one-hots to its own world's block with 4-byte stores, which merge in L2
+//     with the lines written a moment before.  Versions that built the blocks in shared-memory tiles and sent them with TMA
+//     bulk stores (un-patching, 16-byte copies of the static planes, TMA bulk loads on mbarriers, zero-fill + lists in the
+//     tile) all ran at 275-310 us per step of 2^20 worlds: 2,900-3,800 warp-instructions per ticket with a quarter of the lanes
+//     active in the render rounds (profiles/ncu_cfg3_tiny_r02_summary.csv);
 //   * every lane follows its own map (blob pointer per lane), so heterogeneous batches need no uniformity checks.
 // Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
 // per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
@@ -31,7 +34,12 @@ namespace lle {
 #define LLE_TINY_MIN_CTAS 6
 #endif
 
-// word k of the record of lane `lane` in the warp's [stride][32] column block; `applied` columns are [stride][E]
+// word k of the record of lane `lane` in the warp's [stride][32] column block
+// completion of a ticket whose results were written with ordinary stores only (no async-proxy writes to fence)
+__device__ __forceinline__ void ticket_release_plain(uint32_t* flag, uint32_t seq) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+}
+
 struct SmemColumn {
     uint32_t* base;
     int pitch;
@@ -60,14 +68,12 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = p.L.stride, w_flags = p.L.w_flags, w_avail = p.L.w_avail, w_gems = p.L.w_gems, w_on = p.L.w_on;
     const bool has_gems = p.L.gem_words != 0;
-    const int W = p.W, E = p.E, ostr = (int)p.obs_stride;
+    const int W = p.W, ostr = (int)p.obs_stride;
     constexpr int kStaged = TinyWorld<A_, SmemColumn>::kStaged;
     uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
-    float* tile = reinterpret_cast<float*>(wbase);                                   // [E][ostr]: E worlds per bulk store
-    uint32_t* srec = reinterpret_cast<uint32_t*>(tile + p.tile_floats);              // [stride][32]: word k of lane l at k*32+l
+    uint32_t* srec = reinterpret_cast<uint32_t*>(wbase);                             // [stride][32]: word k of lane l at k*32+l
     uint32_t* snext = srec + stride * 32;                                            // [32][stride]: the NEXT ticket's records, prefetched
     LlePatch* slist = reinterpret_cast<LlePatch*>(snext + stride * 32);              // [kStaged][32]: entry k of lane l's render list at k*32+l
-    const int lgE = 31 - __clz(E), rounds = 32 >> lgE;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
         if (lane == 0)
@@ -90,13 +96,25 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
 
     // The next (step, ticket) pair is taken, its flag looked at and its records and map index requested while this ticket's
     // observation is rendered: the latencies of a ticket's first loads hide behind the previous ticket's stores.
+    uint32_t next_in_chunk = 0;
     bool have_next = false, next_ready = false;
     uint32_t next_pair = 0;
     int next_map = 0;
+    // pairs are taken `chunk` at a time: one atomic on the launch's counter per chunk (same-address atomics are serialised by
+    // the L2: one per ticket of 32 tiny worlds is what bounded this kernel at 8.4 ns per ticket, whatever the SM side did)
+    const uint32_t chunk = (uint32_t)max(p.ticket_chunk, 1);
+    uint32_t chunk_end = 0;  // one past the last pair of the chunk this warp holds
+    auto take_pair = [&]() -> uint32_t {  // lane 0 only
+        if (chunk_end == 0 || next_in_chunk >= chunk_end) {
+            next_in_chunk = atomicAdd(&p.sched[0], chunk);
+            chunk_end = next_in_chunk + chunk;
+        }
+        return next_in_chunk++;
+    };
     for (;;) {
         uint32_t pair = next_pair;
         if (!have_next) {
-            if (lane == 0) pair = atomicAdd(&p.sched[0], 1u);
+            if (lane == 0) pair = take_pair();
             pair = __shfl_sync(kFull, pair, 0);
         }
         if (pair >= n_pairs) break;
@@ -110,8 +128,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             bool flushed = false;
             if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
                 if (owed) {  // never block while owing a completion
-                    bulk_wait_all();
-                    ticket_release(p.flags + owed_ticket, owed_seq);
+                    ticket_release_plain(p.flags + owed_ticket, owed_seq);
                     flushed = true;
                 }
                 while (!ticket_ready(p.flags + ticket, my_seq - 1u)) __nanosleep(64);
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             uint32_t np2 = 0;
             int rdy = 0;
             if (lane == 0) {
-                np2 = atomicAdd(&p.sched[0], 1u);
+                np2 = take_pair();
                 if (np2 < n_pairs) rdy = ticket_ready(p.flags + (single_step ? np2 : np2 % p.n_tickets), p.seq + (single_step ? 0u : np2 / p.n_tickets) - 1u) ? 1 : 0;
             }
             next_pair = __shfl_sync(kFull, np2, 0);
@@ -260,29 +277,21 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                 next_map = p.map_of_env ? __ldcg(p.map_of_env + env2) : 0;
             }
         }
-        for (int r = 0; r < rounds; ++r) {
-            if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
-            __syncwarp();
-            for (int f = lane * 4; f < E * ostr; f += 128) *reinterpret_cast<float4*>(tile + f) = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-            if ((lane >> lgE) == r) w.render(tile + (size_t)(lane & (E - 1)) * ostr, p.HW, [&](int k) { return slist[k * 32 + lane]; });
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_store(p.obs + ((int64_t)ticket * 32 + (int64_t)r * E) * ostr, tile, (uint32_t)(E * ostr) * 4u);
-                bulk_commit();
-                if (owed && r == 0) {
-                    bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
-                    ticket_release(p.flags + owed_ticket, owed_seq);
-                }
-            }
+        // the previous ticket's completion is published now: its stores were issued a whole ticket ago, so the release fence
+        // behind them returns at once (a step of the same ticket in a later launch, or in this rollout, may start from here)
+        if (owed && lane == 0) ticket_release_plain(p.flags + owed_ticket, owed_seq);
+        {
+            float4* blocks = reinterpret_cast<float4*>(p.obs + (int64_t)ticket * 32 * ostr);  // the ticket's 32 blocks are contiguous
+            const int n16 = 8 * ostr;                                                         // 32 * ostr / 4 (ostr is a multiple of 4 floats)
+            for (int i = lane; i < n16; i += 32) blocks[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();  // orders the zero-fill (any lane) before the owner lane's 4-byte stores into the same lines
+            w.render(p.obs + env * ostr, p.HW, [&](int k) { return slist[k * 32 + lane]; });
         }
         owed = true; owed_ticket = ticket; owed_seq = my_seq;
         __syncwarp();
     }
     if (lane == 0) {
-        bulk_wait_all();
-        if (owed) ticket_release(p.flags + owed_ticket, owed_seq);
+        if (owed) ticket_release_plain(p.flags + owed_ticket, owed_seq);
         launch_epilogue(p, true);
     }
 }

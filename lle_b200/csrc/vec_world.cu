@@ -101,7 +101,8 @@ struct lle_vec {
     bool force_narrow = false;  // LLE_B200_FORCE_NARROW=1 (tests)
     // tiny maps: step launches run the thread-per-world kernel (tiny_kernel.cuh) with its own tiling and grid
     bool tiny = false;
-    int tiny_E = 8, tiny_warp_smem = 0, tiny_grid = 0;
+    int tiny_E = 8, tiny_warp_smem = 0, tiny_grid = 0, tiny_chunk = 1;
+    int chunk = 1;  // general kernel: pairs per scheduler atomic (LLE_B200_CHUNK)
     size_t tiny_smem = 0;
     uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
@@ -166,6 +167,7 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
             p.E = v->tiny_E;
             p.tile_floats = (int32_t)(v->tiny_E * v->obs_stride);
             p.warp_smem_bytes = v->tiny_warp_smem;
+            p.ticket_chunk = v->tiny_chunk;
             switch (v->A) {
                 case 1: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<1>, p);
                 case 2: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<2>, p);
@@ -289,6 +291,7 @@ KParams base_params(lle_vec* v) {
     p.n_tickets = (uint32_t)(v->N_pad / v->group);
     p.n_warps_total = (uint32_t)(v->grid * kWarps);
     p.n_steps = 1;
+    p.ticket_chunk = v->chunk;
     p.extras = v->d_extras; p.JE = v->JE; p.pbrs_on = v->opts.pbrs ? 1 : 0;
     p.extras_set = v->extras_set; p.pbrs_set = v->pbrs_set;
     p.pbrs_gamma = v->opts.pbrs_gamma; p.pbrs_value = v->opts.pbrs_reward_value;
@@ -644,6 +647,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->pdl = env_int("LLE_B200_PDL", 1) != 0;
     v->force_narrow = env_int("LLE_B200_FORCE_NARROW", 0) != 0;
     v->narrow_depth = std::max(1, env_int("LLE_B200_NARROW_DEPTH", 1));
+    v->chunk = std::max(1, std::min(64, env_int("LLE_B200_CHUNK", 1)));
     int max_patch = 0;
     for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)cms[k]->header().n_patch);
     for (const auto& m : v->variant_maps) max_patch = std::max(max_patch, (int)m.header().n_patch);
@@ -676,14 +680,12 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->tiny = v->fast && small_obs && v->A <= 4 && v->L.n_words <= 8 && !v->L.wide_flags && v->L.on_words == 1 && v->L.gem_words <= 1 &&
               v->L.sub_words == 0 && v->group == 32 && !env_int("LLE_B200_NO_TINY", 0);
     if (v->tiny) {
-        int e = env_int("LLE_B200_TINY_E", v->E);
-        v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 8;
-        auto tiny_bytes = [&](int E) {  // one tile, the records' columns + the prefetched next records, 16 staged render-list entries per lane
-            const size_t bytes = (size_t)E * stride * 4 + 2 * (size_t)v->L.stride * 32 * 4 + 16 * 32 * sizeof(LlePatch);
+        auto tiny_bytes = [&]() {  // the records' columns + the prefetched next records, 16 staged render-list entries per lane
+            const size_t bytes = 2 * (size_t)v->L.stride * 32 * 4 + 16 * 32 * sizeof(LlePatch);
             return (bytes + 127) / 128 * 128;
         };
-        while (v->tiny_E > 4 && tiny_bytes(v->tiny_E) * kWarps > (size_t)(96 << 10)) v->tiny_E /= 2;  // at least two CTAs per SM
-        v->tiny_warp_smem = (int)tiny_bytes(v->tiny_E);
+        v->tiny_chunk = std::max(1, std::min(64, env_int("LLE_B200_TINY_CHUNK", 1)));
+        v->tiny_warp_smem = (int)tiny_bytes();
         v->tiny_smem = (size_t)v->tiny_warp_smem * kWarps;
         int tb = 0;
         auto configure = [&](auto kern) -> cudaError_t {
@@ -1116,12 +1118,24 @@ int lle_vec_pipeline_submit(lle_vec* v, const int8_t* actions_host, float* rewar
     KParams p = base_params(v);
     p.mode = MODE_STEP;
     if (actions_host) {
-        LLE_CUDA(cudaMemcpyAsync(v->d_stage[slot], actions_host, (size_t)v->N * v->A, cudaMemcpyHostToDevice, v->s_in));
-        if (g_write_value32((CUstream)v->s_in, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 0), n, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
-            return fail(LLE_CUDA_ERROR, "cuStreamWriteValue32 failed");
-        p.actions_in = v->d_stage[slot];
-        p.in_flag = v->d_pipe_flags + 0;
-        p.in_need = n;
+        if (v->pipe_submitted == v->pipe_completed) {
+            // Nothing of this vec is in flight (a closed loop: the caller waited for the previous step before choosing these
+            // actions): the copy simply precedes the kernel on the compute stream.  A kernel that waited for its actions on the
+            // device would hold SM slots idle for the ~10 us the copy takes - slots that the other sub-batches of an
+            // EnvPool-style loop could use.
+            LLE_CUDA(cudaMemcpyAsync(v->d_stage[slot], actions_host, (size_t)v->N * v->A, cudaMemcpyHostToDevice, v->s_main));
+            p.actions_in = v->d_stage[slot];
+        } else {
+            // Steps already in flight: the copy travels on its own stream, overlapping the kernels ahead, and the kernel waits
+            // for it on the device (no stream-level dependency between consecutive step kernels: they stay programmatically
+            // dependent launches).
+            LLE_CUDA(cudaMemcpyAsync(v->d_stage[slot], actions_host, (size_t)v->N * v->A, cudaMemcpyHostToDevice, v->s_in));
+            if (g_write_value32((CUstream)v->s_in, (CUdeviceptr)(uintptr_t)(v->d_pipe_flags + 0), n, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                return fail(LLE_CUDA_ERROR, "cuStreamWriteValue32 failed");
+            p.actions_in = v->d_stage[slot];
+            p.in_flag = v->d_pipe_flags + 0;
+            p.in_need = n;
+        }
     }
     p.out_flag = v->d_out_flags + slot * 32;  // one 128-byte line per slot
     p.out_value = n;

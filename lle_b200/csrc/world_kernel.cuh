@@ -80,6 +80,7 @@ struct KParams {
     uint32_t n_tickets, n_warps_total;
     uint64_t* timeline;    // development aid: per warp {start, first store, last store, end} in ns (globaltimer), or nullptr
     int32_t n_steps;       // steps in this launch (> 1: rollout with device-sampled actions)
+    int32_t ticket_chunk;  // tiny-map kernel: consecutive (step, ticket) pairs a warp takes with one atomic (the L2 serialises same-address atomics)
     // LaserSubgoal extras / PotentialShapedLLE
     float* extras;         // [N_pad][A][JE] or nullptr
     int32_t JE, pbrs_on;
@@ -819,13 +820,23 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     bool first = true;
     uint32_t owed_ticket = 0, owed_seq = 0;  // the previous ticket, whose completion is published once its stores are done
     bool owed = false;
+    // pairs are taken `ticket_chunk` at a time with one atomic on the launch's counter (the L2 serialises same-address atomics)
+    const uint32_t chunk = (uint32_t)max(p.ticket_chunk, 1);
+    uint32_t chunk_next = 0, chunk_end = 0;  // lane 0: the pairs of the chunk this warp holds
+    const bool single_step = p.n_steps == 1;
     for (;;) {
         uint32_t pair = 0;
-        if (lane == 0) pair = atomicAdd(&p.sched[0], 1u);
+        if (lane == 0) {
+            if (chunk_next >= chunk_end) {
+                chunk_next = atomicAdd(&p.sched[0], chunk);
+                chunk_end = chunk_next + chunk;
+            }
+            pair = chunk_next++;
+        }
         pair = __shfl_sync(kFull, pair, 0);
         if (pair >= n_pairs) break;
-        const uint32_t ticket = pair % p.n_tickets;
-        step_index = (int)(pair / p.n_tickets);
+        const uint32_t ticket = single_step ? pair : pair % p.n_tickets;
+        step_index = single_step ? 0 : (int)(pair / p.n_tickets);
         const uint32_t my_seq = p.seq + (uint32_t)step_index;
         if constexpr (MODE == MODE_STEP) {
             bool flushed = false;
