@@ -74,6 +74,10 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     uint32_t* srec = reinterpret_cast<uint32_t*>(wbase);                             // [stride][32]: word k of lane l at k*32+l
     uint32_t* snext = srec + stride * 32;                                            // [32][stride]: the NEXT ticket's records, prefetched
     LlePatch* slist = reinterpret_cast<LlePatch*>(snext + stride * 32);              // [kStaged][32]: entry k of lane l's render list at k*32+l
+    const LlePatch** slptr = reinterpret_cast<const LlePatch**>(slist + kStaged * 32); // [32]: lane l's whole render list (entries >= kStaged)
+    uint32_t* smeta = reinterpret_cast<uint32_t*>(slptr + 32);                       // [32]: n_static | n_patch << 16 of lane l's map
+    float* tile = reinterpret_cast<float*>(smeta + 32);                              // [E][ostr]: tile mode (p.E > 0), E worlds per bulk store
+    const int E = p.E;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
         if (lane == 0)
@@ -128,7 +132,8 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             bool flushed = false;
             if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
                 if (owed) {  // never block while owing a completion
-                    ticket_release_plain(p.flags + owed_ticket, owed_seq);
+                    if (E) bulk_wait_all();
+                    ticket_release(p.flags + owed_ticket, owed_seq);
                     flushed = true;
                 }
                 while (!ticket_ready(p.flags + ticket, my_seq - 1u)) __nanosleep(64);
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
 #pragma unroll
             for (int k = 0; k < 5; ++k) avb[5 * a + k] = (mask >> k) & 1u;
         }
-        store_bytes<5 * A_>(p.avail + env * (5 * A_), avb);
+        if (!(p.debug_skip & 2)) store_bytes<5 * A_>(p.avail + env * (5 * A_), avb);
 
         // ---- record back (registers -> column -> HBM) and the state vector (pyworld_state.rs:79-101)
         w.pack(cache);
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             uint4* dst = reinterpret_cast<uint4*>(p.records + env * stride);
             for (int q = 0; q < stride / 4; ++q) __stcg(dst + q, make_uint4(w.rec(4 * q + 0), w.rec(4 * q + 1), w.rec(4 * q + 2), w.rec(4 * q + 3)));
             float* st = p.state + env * p.S;
+            if (!(p.debug_skip & 2))
 #pragma unroll
             for (int a = 0; a < A_; ++a) {
                 st[2 * a] = (float)(w.pos[a] >> 8);
@@ -277,21 +283,68 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                 next_map = p.map_of_env ? __ldcg(p.map_of_env + env2) : 0;
             }
         }
-        // the previous ticket's completion is published now: its stores were issued a whole ticket ago, so the release fence
-        // behind them returns at once (a step of the same ticket in a later launch, or in this rollout, may start from here)
-        if (owed && lane == 0) ticket_release_plain(p.flags + owed_ticket, owed_seq);
-        {
+        if (p.debug_skip & 1) {
+            if (owed && lane == 0) ticket_release_plain(p.flags + owed_ticket, owed_seq);
+        } else if (E == 0) {
+            // direct mode: the warp zero-fills the ticket's 32 blocks in HBM with coalesced 16-byte stores, then every lane applies
+            // its render list and its agents to its own world's block with 4-byte stores (they merge in L2 with the lines just
+            // written).  The previous ticket's completion is published first: its stores were issued a whole ticket ago.
+            if (owed && lane == 0) ticket_release_plain(p.flags + owed_ticket, owed_seq);
             float4* blocks = reinterpret_cast<float4*>(p.obs + (int64_t)ticket * 32 * ostr);  // the ticket's 32 blocks are contiguous
             const int n16 = 8 * ostr;                                                         // 32 * ostr / 4 (ostr is a multiple of 4 floats)
             for (int i = lane; i < n16; i += 32) blocks[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();  // orders the zero-fill (any lane) before the owner lane's 4-byte stores into the same lines
             w.render(p.obs + env * ostr, p.HW, [&](int k) { return slist[k * 32 + lane]; });
+        } else {
+            // tile mode: E worlds per round are built in a zero-filled shared-memory tile by ALL lanes - 32 / E lanes share a
+            // world's render list (read from the owner lane's staged copy and record column) - and leave with one TMA bulk store.
+            const int lgE = 31 - __clz(E), lgl = 5 - lgE, lpw = 1 << lgl;  // lanes per world
+            smeta[lane] = (uint32_t)w.n_static | ((uint32_t)w.n_patch << 16);
+            slptr[lane] = w.list;
+            __syncwarp();
+            for (int r = 0; r < (32 >> lgE); ++r) {
+                if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
+                __syncwarp();
+                for (int f = lane * 4; f < E * ostr; f += 128) *reinterpret_cast<float4*>(tile + f) = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                {
+                    const int ws = (r << lgE) + (lane >> lgl), q = lane & (lpw - 1);  // the world this lane helps to draw, and its share
+                    float* sub = tile + (size_t)(lane >> lgl) * ostr;
+                    const uint32_t meta = smeta[ws];
+                    const int ns = (int)(meta & 0xFFFFu), n = ns + (int)(meta >> 16);
+                    for (int k = q; k < n; k += lpw) {
+                        const LlePatch pe = k < kStaged ? slist[k * 32 + ws] : slptr[ws][k];
+                        if (k < ns) {
+                            sub[pe.idx] = (float)pe.stat;  // static layers (observations.py:216-237)
+                        } else {
+                            const uint32_t wd = srec[(pe.src == 0xFF ? w_gems : w_on + pe.src) * 32 + ws];
+                            if ((((wd >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;  // lit laser cell / uncollected gem (:256-263)
+                        }
+                    }
+                    for (int a = q; a < A_; a += lpw) {  // the agents' one-hots (:264-265): their planes hold nothing else
+                        const uint32_t wd = srec[(a >> 1) * 32 + ws];
+                        const uint32_t pp = (a & 1) ? (wd >> 16) : (wd & 0xFFFFu);
+                        sub[a * p.HW + (int)(pp >> 8) * W + (int)(pp & 0xFFu)] = 1.0f;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(p.obs + ((int64_t)ticket * 32 + ((int64_t)r << lgE)) * ostr, tile, (uint32_t)(E * ostr) * 4u);
+                    bulk_commit();
+                    if (owed && r == 0) {
+                        bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
+                        ticket_release(p.flags + owed_ticket, owed_seq);
+                    }
+                }
+            }
         }
         owed = true; owed_ticket = ticket; owed_seq = my_seq;
         __syncwarp();
     }
     if (lane == 0) {
-        if (owed) ticket_release_plain(p.flags + owed_ticket, owed_seq);
+        if (E) bulk_wait_all();
+        if (owed) ticket_release(p.flags + owed_ticket, owed_seq);
         launch_epilogue(p, true);
     }
 }
