@@ -9,15 +9,15 @@
 //     enter, repeated while somebody died (world.rs:454-505) — with positions, flags and events in registers and the beam /
 //     gem masks in a lane-private column of shared memory (dynamic index by beam): no ballots, no shuffles, no predicated
 //     phases, and 32 worlds advance per warp pass instead of 32 / Wd;
-//   * the observation is written WITHOUT a shared-memory tile.  A 5x5 layered block is 200 floats of which about 16 are not
-//     zero (a dozen static cells, the lit laser cells, the uncollected gems, the agents), and a warp meets another map with
-//     nearly every ticket of a heterogeneous batch, so there is nothing to keep between tickets.  The warp zero-fills the
-//     ticket's 32 blocks in HBM with fully coalesced 16-byte stores (the write stream the roofline counts), then every lane
-//     applies its map's render list and its agents' one-hots to its own world's block with 4-byte stores, which merge in L2
-//     with the lines written a moment before.  Versions that built the blocks in shared-memory tiles and sent them with TMA
-//     bulk stores (un-patching, 16-byte copies of the static planes, TMA bulk loads on mbarriers, zero-fill + lists in the
-//     tile) all ran at 275-310 us per step of 2^20 worlds: 2,900-3,800 warp-instructions per ticket with a quarter of the lanes
-//     active in the render rounds (profiles/ncu_cfg3_tiny_r02_summary.csv);
+//   * a 5x5 layered block is 200 floats of which about 16 are not zero (a dozen static cells, the lit laser cells, the
+//     uncollected gems, the agents), and a warp meets another map with nearly every ticket of a heterogeneous batch, so there
+//     is nothing worth keeping in a tile between tickets.  E worlds at a time, the warp zero-fills a shared-memory tile, ALL
+//     lanes (32 / E per world) apply the worlds' render lists — the non-zero static floats, then the dynamic cells, staged in
+//     shared memory ahead of time — and the agents' one-hots, and the tile leaves with one TMA bulk store.  What was tried on
+//     the way (2^20 worlds, us per step; profiles/cfg3_history_r02.md): un-patching tiles 300, 16-byte copies of the static
+//     planes 275, TMA bulk loads of the static planes on mbarriers 284, one lane per world in the tile 277, no tile at all
+//     (zero-fill and 4-byte list stores straight to HBM: 40 % fewer instructions, but 19 M tiny L2 write requests) 262,
+//     this one 232;
 //   * every lane follows its own map (blob pointer per lane), so heterogeneous batches need no uniformity checks.
 // Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
 // per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
@@ -35,11 +35,6 @@ namespace lle {
 #endif
 
 // word k of the record of lane `lane` in the warp's [stride][32] column block
-// completion of a ticket whose results were written with ordinary stores only (no async-proxy writes to fence)
-__device__ __forceinline__ void ticket_release_plain(uint32_t* flag, uint32_t seq) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
-}
-
 struct SmemColumn {
     uint32_t* base;
     int pitch;
@@ -76,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     LlePatch* slist = reinterpret_cast<LlePatch*>(snext + stride * 32);              // [kStaged][32]: entry k of lane l's render list at k*32+l
     const LlePatch** slptr = reinterpret_cast<const LlePatch**>(slist + kStaged * 32); // [32]: lane l's whole render list (entries >= kStaged)
     uint32_t* smeta = reinterpret_cast<uint32_t*>(slptr + 32);                       // [32]: n_static | n_patch << 16 of lane l's map
-    float* tile = reinterpret_cast<float*>(smeta + 32);                              // [E][ostr]: tile mode (p.E > 0), E worlds per bulk store
+    float* tile = reinterpret_cast<float*>(smeta + 32);                              // [E][ostr]: E worlds per bulk store
     const int E = p.E;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
@@ -132,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             bool flushed = false;
             if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
                 if (owed) {  // never block while owing a completion
-                    if (E) bulk_wait_all();
+                    bulk_wait_all();
                     ticket_release(p.flags + owed_ticket, owed_seq);
                     flushed = true;
                 }
@@ -241,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
 #pragma unroll
             for (int k = 0; k < 5; ++k) avb[5 * a + k] = (mask >> k) & 1u;
         }
-        if (!(p.debug_skip & 2)) store_bytes<5 * A_>(p.avail + env * (5 * A_), avb);
+        store_bytes<5 * A_>(p.avail + env * (5 * A_), avb);
 
         // ---- record back (registers -> column -> HBM) and the state vector (pyworld_state.rs:79-101)
         w.pack(cache);
@@ -249,7 +244,6 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             uint4* dst = reinterpret_cast<uint4*>(p.records + env * stride);
             for (int q = 0; q < stride / 4; ++q) __stcg(dst + q, make_uint4(w.rec(4 * q + 0), w.rec(4 * q + 1), w.rec(4 * q + 2), w.rec(4 * q + 3)));
             float* st = p.state + env * p.S;
-            if (!(p.debug_skip & 2))
 #pragma unroll
             for (int a = 0; a < A_; ++a) {
                 st[2 * a] = (float)(w.pos[a] >> 8);
@@ -283,21 +277,9 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                 next_map = p.map_of_env ? __ldcg(p.map_of_env + env2) : 0;
             }
         }
-        if (p.debug_skip & 1) {
-            if (owed && lane == 0) ticket_release_plain(p.flags + owed_ticket, owed_seq);
-        } else if (E == 0) {
-            // direct mode: the warp zero-fills the ticket's 32 blocks in HBM with coalesced 16-byte stores, then every lane applies
-            // its render list and its agents to its own world's block with 4-byte stores (they merge in L2 with the lines just
-            // written).  The previous ticket's completion is published first: its stores were issued a whole ticket ago.
-            if (owed && lane == 0) ticket_release_plain(p.flags + owed_ticket, owed_seq);
-            float4* blocks = reinterpret_cast<float4*>(p.obs + (int64_t)ticket * 32 * ostr);  // the ticket's 32 blocks are contiguous
-            const int n16 = 8 * ostr;                                                         // 32 * ostr / 4 (ostr is a multiple of 4 floats)
-            for (int i = lane; i < n16; i += 32) blocks[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();  // orders the zero-fill (any lane) before the owner lane's 4-byte stores into the same lines
-            w.render(p.obs + env * ostr, p.HW, [&](int k) { return slist[k * 32 + lane]; });
-        } else {
-            // tile mode: E worlds per round are built in a zero-filled shared-memory tile by ALL lanes - 32 / E lanes share a
-            // world's render list (read from the owner lane's staged copy and record column) - and leave with one TMA bulk store.
+        {
+            // E worlds per round are built in a zero-filled shared-memory tile by ALL lanes - 32 / E lanes share a world's render
+            // list (read from the owner lane's staged copy and record column) - and leave with one TMA bulk store.
             const int lgE = 31 - __clz(E), lgl = 5 - lgE, lpw = 1 << lgl;  // lanes per world
             smeta[lane] = (uint32_t)w.n_static | ((uint32_t)w.n_patch << 16);
             slptr[lane] = w.list;
@@ -312,14 +294,19 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                     float* sub = tile + (size_t)(lane >> lgl) * ostr;
                     const uint32_t meta = smeta[ws];
                     const int ns = (int)(meta & 0xFFFFu), n = ns + (int)(meta >> 16);
-                    for (int k = q; k < n; k += lpw) {
-                        const LlePatch pe = k < kStaged ? slist[k * 32 + ws] : slptr[ws][k];
+                    auto draw = [&](const LlePatch pe, int k) {
                         if (k < ns) {
                             sub[pe.idx] = (float)pe.stat;  // static layers (observations.py:216-237)
                         } else {
                             const uint32_t wd = srec[(pe.src == 0xFF ? w_gems : w_on + pe.src) * 32 + ws];
                             if ((((wd >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;  // lit laser cell / uncollected gem (:256-263)
                         }
+                    };
+                    const int n_staged = min(n, kStaged);
+                    for (int k = q; k < n_staged; k += lpw) draw(slist[k * 32 + ws], k);  // the staged head of the list: shared memory only
+                    if (n > kStaged) {                                                    // long lists: the rest from the map blob
+                        const LlePatch* rest = slptr[ws];
+                        for (int k = kStaged + q; k < n; k += lpw) draw(rest[k], k);
                     }
                     for (int a = q; a < A_; a += lpw) {  // the agents' one-hots (:264-265): their planes hold nothing else
                         const uint32_t wd = srec[(a >> 1) * 32 + ws];
@@ -343,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         __syncwarp();
     }
     if (lane == 0) {
-        if (E) bulk_wait_all();
+        bulk_wait_all();
         if (owed) ticket_release(p.flags + owed_ticket, owed_seq);
         launch_epilogue(p, true);
     }

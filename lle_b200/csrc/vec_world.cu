@@ -102,7 +102,6 @@ struct lle_vec {
     // tiny maps: step launches run the thread-per-world kernel (tiny_kernel.cuh) with its own tiling and grid
     bool tiny = false;
     int tiny_E = 8, tiny_warp_smem = 0, tiny_grid = 0, tiny_chunk = 1;
-    int tiny_debug = 0;
     int chunk = 1;  // general kernel: pairs per scheduler atomic (LLE_B200_CHUNK)
     size_t tiny_smem = 0;
     uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
@@ -169,7 +168,6 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
             p.tile_floats = (int32_t)(v->tiny_E * v->obs_stride);
             p.warp_smem_bytes = v->tiny_warp_smem;
             p.ticket_chunk = v->tiny_chunk;
-            p.debug_skip = v->tiny_debug;
             switch (v->A) {
                 case 1: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<1>, p);
                 case 2: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<2>, p);
@@ -682,16 +680,14 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     v->tiny = v->fast && small_obs && v->A <= 4 && v->L.n_words <= 8 && !v->L.wide_flags && v->L.on_words == 1 && v->L.gem_words <= 1 &&
               v->L.sub_words == 0 && v->group == 32 && !env_int("LLE_B200_NO_TINY", 0);
     if (v->tiny) {
-        // LLE_B200_TINY_E: 0 = observations written straight to HBM (zero-fill + list stores), 8 / 16 = shared-memory tiles of
-        // that many worlds, drawn by all lanes and sent with TMA bulk stores
-        int e = env_int("LLE_B200_TINY_E", 8);
-        v->tiny_E = (e == 0 || e == 8 || e == 16 || e == 32) ? e : 8;
+        // worlds per tile / bulk store (measured on 2^20 5x5 worlds, us per step: 4: 232, 8: 243, 16: 343, 32: 558 - occupancy)
+        int e = env_int("LLE_B200_TINY_E", 4);
+        v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 4;
         auto tiny_bytes = [&]() {  // the records' columns + the prefetched next records, 16 staged list entries per lane, pointers, counts, the tile
             const size_t bytes = 2 * (size_t)v->L.stride * 32 * 4 + 16 * 32 * sizeof(LlePatch) + 32 * 8 + 32 * 4 + (size_t)v->tiny_E * stride * 4;
             return (bytes + 127) / 128 * 128;
         };
         v->tiny_chunk = std::max(1, std::min(64, env_int("LLE_B200_TINY_CHUNK", 1)));
-        v->tiny_debug = env_int("LLE_B200_TINY_SKIP", 0);
         v->tiny_warp_smem = (int)tiny_bytes();
         v->tiny_smem = (size_t)v->tiny_warp_smem * kWarps;
         int tb = 0;

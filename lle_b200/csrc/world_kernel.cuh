@@ -80,7 +80,6 @@ struct KParams {
     uint32_t n_tickets, n_warps_total;
     uint64_t* timeline;    // development aid: per warp {start, first store, last store, end} in ns (globaltimer), or nullptr
     int32_t n_steps;       // steps in this launch (> 1: rollout with device-sampled actions)
-    int32_t debug_skip;    // development aid (LLE_B200_TINY_SKIP): 1 = no observation stores, 2 = also no state / avail stores, 4 = no flags
     int32_t ticket_chunk;  // tiny-map kernel: consecutive (step, ticket) pairs a warp takes with one atomic (the L2 serialises same-address atomics)
     // LaserSubgoal extras / PotentialShapedLLE
     float* extras;         // [N_pad][A][JE] or nullptr
