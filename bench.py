@@ -13,7 +13,7 @@ For N > 1 launch with torchrun (one rank per GPU); envs are range-sharded over r
 collective on the step path; NCCL carries only the reductions of the timings and of three counters).
 Prints ONE JSON line on rank 0.  Keys beyond the contract:
   configs    the other BASELINE.json workloads (1, 3, 4, 5 of SURVEY §8d) at their stated per-GPU sizes, bounded steps
-  e2e        value = closed loop (the host reads step t's results before it chooses step t+1's actions), four sub-batches
+  e2e        value = closed loop (the host reads step t's results before it chooses step t+1's actions), eight sub-batches
              in flight; pipelined_value = open loop, 8 recorded steps in flight; sync_value = one blocking call per step
   ranks      per-rank ms per step of the headline window (min / max / all)
 """
@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2048)
     ap.add_argument("--e2e-depth", type=int, default=8, help="steps in flight in the open-loop pipelined arm (1..8)")
-    ap.add_argument("--e2e-parts", type=int, default=4, help="sub-batches in flight in the closed-loop arm")
+    ap.add_argument("--e2e-parts", type=int, default=8, help="sub-batches in flight in the closed-loop arm")
     ap.add_argument("--preheat-ms", type=float, default=250.0, help="untimed device work before the warm-up steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compiled-host", action="store_true", help="skip the compiled-host closed loop of the e2e arm")
