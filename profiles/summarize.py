@@ -2,10 +2,10 @@
 Usage: python profiles/summarize.py [round_tag]"""
 import collections, csv, json, os, statistics, subprocess, sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
-CMD = "python bench.py --steps 64 --warmup 8 --no-cpu-baseline --e2e-steps 8"
+CMD = "python bench.py --steps 64 --warmup 8 --no-cpu-baseline --e2e-steps 8 --no-configs --no-compiled-host"
 
 rows = list(csv.reader(open(os.path.join(G, f"launches_{tag}.csv"))))
 hdr, data = None, []
@@ -55,7 +55,8 @@ mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
 ur, rd = summary["dram__bytes_read.sum"]
 uw, wr = summary["dram__bytes_write.sum"]
 traffic = statistics.mean(float(r) * mult[ur] + float(w) * mult[uw] for r, w in zip(rd, wr))
-json.dump({"dram_bytes_per_launch": traffic,
+commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+json.dump({"dram_bytes_per_launch": traffic, "commit": commit,
            "source": f"profiles/ncu_full_{tag}_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, mean of 3 launches)",
            "note": "below the 501 MB algorithmic figure because the tail of a launch's writes is still in the 126 MB L2 when the kernel "
                    "ends (written back during the next launch); no re-reads: dram read is 2 MB per launch"},
