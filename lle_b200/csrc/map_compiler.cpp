@@ -426,7 +426,7 @@ CompiledMap compile_map(const std::string& text, const ObsSpec& spec, const std:
     h.static_off = (uint32_t)off;  off = align16(off + stat.size() * sizeof(float));
     h.ap_off = (uint32_t)off;      off = align16(off + std::max<size_t>(planes.size(), 1) * sizeof(LleAgentPlane));
     h.n_static = n_static;
-    h.static_list_off = (uint32_t)off; off = align16(off + std::max<size_t>(static_list.size(), 16) * sizeof(LlePatch));  // the kernel stages 16 entries blindly
+    h.static_list_off = (uint32_t)off; off = align16(off + std::max<size_t>(static_list.size(), 1) * sizeof(LlePatch));
     // start candidates (World.random_start_positions): per agent (first index, count), then the packed positions
     std::vector<uint32_t> cand_index;
     std::vector<uint16_t> cand_pos;

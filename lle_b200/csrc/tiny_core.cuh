@@ -246,18 +246,13 @@ struct TinyWorld {
     // ---- layered observation (observations.py:254-266) of this world in `sub`, a ZERO-FILLED block of obs_stride floats.
     // Write order of the reference: the static layers (walls, voids, exits = 1, sources = -1; :216-237), the laser cells whose
     // beam bit is on and the gems that are NOT collected (= 1; :256-263), then the agents (:264-265).  HW = H*W.
-    // `staged(k)`: entry k < kStaged of the map's render list, copied next to the tile ahead of time (the kernel keeps them in
-    // shared memory: a warp meets another map with nearly every ticket of a heterogeneous batch, and a table walk at L2 latency
-    // per ticket is what bounds it otherwise); entries beyond are read from the list itself.
-    static constexpr int kStaged = 16;
-    template <class Staged>
-    LLE_HD void render(float* sub, int HW, Staged staged) {
+    LLE_HD void render(float* sub, int HW) {
         for (int k = 0; k < n_static; ++k) {
-            const LlePatch pe = k < kStaged ? staged(k) : list[k];
+            const LlePatch pe = list[k];
             sub[pe.idx] = (float)pe.stat;
         }
         for (int k = n_static; k < n_static + n_patch; ++k) {
-            const LlePatch pe = k < kStaged ? staged(k) : list[k];
+            const LlePatch pe = list[k];
             const uint32_t w = rec(pe.src == 0xFF ? L.w_gems : L.w_on + pe.src);
             if ((((w >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;
         }

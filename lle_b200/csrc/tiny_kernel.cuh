@@ -31,7 +31,7 @@
 namespace lle {
 
 #ifndef LLE_TINY_MIN_CTAS
-#define LLE_TINY_MIN_CTAS 6
+#define LLE_TINY_MIN_CTAS 7
 #endif
 
 // word k of the record of lane `lane` in the warp's [stride][32] column block
@@ -64,12 +64,10 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     const int stride = p.L.stride, w_flags = p.L.w_flags, w_avail = p.L.w_avail, w_gems = p.L.w_gems, w_on = p.L.w_on;
     const bool has_gems = p.L.gem_words != 0;
     const int W = p.W, ostr = (int)p.obs_stride;
-    constexpr int kStaged = TinyWorld<A_, SmemColumn>::kStaged;
     uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
     uint32_t* srec = reinterpret_cast<uint32_t*>(wbase);                             // [stride][32]: word k of lane l at k*32+l
     uint32_t* snext = srec + stride * 32;                                            // [32][stride]: the NEXT ticket's records, prefetched
-    LlePatch* slist = reinterpret_cast<LlePatch*>(snext + stride * 32);              // [kStaged][32]: entry k of lane l's render list at k*32+l
-    const LlePatch** slptr = reinterpret_cast<const LlePatch**>(slist + kStaged * 32); // [32]: lane l's whole render list (entries >= kStaged)
+    const LlePatch** slptr = reinterpret_cast<const LlePatch**>(snext + stride * 32); // [32]: the render list of lane l's map
     uint32_t* smeta = reinterpret_cast<uint32_t*>(slptr + 32);                       // [32]: n_static | n_patch << 16 of lane l's map
     float* tile = reinterpret_cast<float*>(smeta + 32);                              // [E][ostr]: E worlds per bulk store
     const int E = p.E;
@@ -79,9 +77,11 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             while (!sys_flag_ready(p.in_flag, p.in_need)) __nanosleep(100);
         __syncwarp();
     }
-    if (lane == 0)
-        while (!sched_slot_armed(p.sched + 2, p.sched_gen)) __nanosleep(32);
-    __syncwarp();
+    if (p.sched_check) {
+        if (lane == 0)
+            while (!sched_slot_armed(p.sched + 2, p.sched_gen)) __nanosleep(32);
+        __syncwarp();
+    }
 
     const uint32_t n_pairs = p.n_tickets * (uint32_t)p.n_steps;
     const bool single_step = p.n_steps == 1;
@@ -103,9 +103,18 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     // the L2: one per ticket of 32 tiny worlds is what bounded this kernel at 8.4 ns per ticket, whatever the SM side did)
     const uint32_t chunk = (uint32_t)max(p.ticket_chunk, 1);
     uint32_t chunk_end = 0;  // one past the last pair of the chunk this warp holds
+    const uint32_t warp_global = blockIdx.x * kWarps + warp;
+    // On an idle device (the host saw every earlier launch retire: a closed loop) all CTAs are resident at once and a warp's first
+    // pair is its own index - no round trip to the launch's counter before it can start.  Not when launches overlap: CTAs then
+    // trickle in as their predecessors' retire, and a pair pinned to a late CTA would hold up everything behind it.
+    bool first_pair = p.sched_check == 0;
     auto take_pair = [&]() -> uint32_t {  // lane 0 only
+        if (first_pair) {
+            first_pair = false;
+            return warp_global;
+        }
         if (chunk_end == 0 || next_in_chunk >= chunk_end) {
-            next_in_chunk = atomicAdd(&p.sched[0], chunk);
+            next_in_chunk = (p.sched_check == 0 ? p.n_warps_total : 0u) + atomicAdd(&p.sched[0], chunk);  // behind the static pairs, if any
             chunk_end = next_in_chunk + chunk;
         }
         return next_in_chunk++;
@@ -161,14 +170,6 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         }
         w.unpack();
         const uint32_t av_cache = w.rec(w_avail);  // World::available_actions cache: one byte per agent (A_ <= 4)
-        {   // the head of the map's render list moves next to the tile (8 bytes per entry, asynchronous copies): ready by render time
-            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(slist + lane);
-#pragma unroll
-            for (int k = 0; k < kStaged; ++k)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (uint32_t)k * 256u), "l"(w.list + k) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-
         // ---- actions (world.rs:444-453): supplied, or sampled uniformly among the available ones
         uint32_t act[A_], ev[A_];
         bool bad = false;
@@ -258,7 +259,6 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
         __syncwarp();
 
         // ---- layered observation (observations.py:254-266), E worlds per bulk store
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this lane's render-list entries have landed
         {   // take the next pair now; if its previous step is already complete, start moving its records and map index
             uint32_t np2 = 0;
             int rdy = 0;
@@ -302,12 +302,8 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                             if ((((wd >> pe.bit) & 1u) != 0) != (pe.src == 0xFF)) sub[pe.idx] = 1.0f;  // lit laser cell / uncollected gem (:256-263)
                         }
                     };
-                    const int n_staged = min(n, kStaged);
-                    for (int k = q; k < n_staged; k += lpw) draw(slist[k * 32 + ws], k);  // the staged head of the list: shared memory only
-                    if (n > kStaged) {                                                    // long lists: the rest from the map blob
-                        const LlePatch* rest = slptr[ws];
-                        for (int k = kStaged + q; k < n; k += lpw) draw(rest[k], k);
-                    }
+                    const LlePatch* list = slptr[ws];
+                    for (int k = q; k < n; k += lpw) draw(list[k], k);
                     for (int a = q; a < A_; a += lpw) {  // the agents' one-hots (:264-265): their planes hold nothing else
                         const uint32_t wd = srec[(a >> 1) * 32 + ws];
                         const uint32_t pp = (a & 1) ? (wd >> 16) : (wd & 0xFFFFu);

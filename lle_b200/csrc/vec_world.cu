@@ -104,7 +104,11 @@ struct lle_vec {
     int tiny_E = 8, tiny_warp_smem = 0, tiny_grid = 0, tiny_chunk = 1;
     int chunk = 1;  // general kernel: pairs per scheduler atomic (LLE_B200_CHUNK)
     size_t tiny_smem = 0;
-    uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: sequence number of the last step launch that retired
+    uint32_t* h_retired_seq = nullptr;  // pinned, device-mapped: [0] sequence number of the last step launch that retired,
+                                        // [32] number of launches of this vec (any mode) whose last warp has left
+    uint32_t* d_retired_count = nullptr;  // device counter behind [32]
+    MapDev map0;                        // the tables of map 0 as device pointers (kernel parameter of single-map batches)
+    bool has_map0 = false;
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
     int narrow_depth = 1;      // step launches in flight from which the narrow grid is used (LLE_B200_NARROW_DEPTH)
     int grid = 0, grid_step = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
@@ -184,6 +188,12 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
 cudaError_t launch(lle_vec* v, KParams& p, cudaStream_t s) {
     p.sched = v->d_sched + kSchedSlotWords * (v->launch_index % kSchedSlots);
     p.sched_gen = v->launch_index / kSchedSlots;
+    // every launch issued so far has retired (a closed loop, synchronous stepping): the slot is certainly re-armed
+    p.sched_check = *(volatile uint32_t*)(v->h_retired_seq + 32) != v->launch_index ? 1u : 0u;
+    p.retired_launch = v->h_retired_seq + 32;
+    p.retired_count = v->d_retired_count;
+    p.map0 = v->map0;
+    p.has_map0 = v->has_map0 ? 1 : 0;
     p.flags = v->d_flags;
     cudaError_t e;
     switch (p.mode) {
@@ -264,6 +274,26 @@ cudaError_t configure_kernel(size_t smem, int* blocks) {
 int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
     return v && *v ? std::atoi(v) : fallback;
+}
+
+// MapDev::bind on the host: the device addresses of a map's tables from the device address of its blob and a host copy of its header
+MapDev host_bind(const uint8_t* dblob, const LleMapHeader& h) {
+    MapDev m;
+    m.blob = dblob;
+    m.hdr = reinterpret_cast<const LleMapHeader*>(dblob);
+    m.cellinfo = reinterpret_cast<const uint32_t*>(dblob + h.cellinfo_off);
+    m.cellbeams = reinterpret_cast<const LleCellBeams*>(dblob + h.cellbeams_off);
+    m.beams = reinterpret_cast<const LleBeam*>(dblob + h.beams_off);
+    m.patches = reinterpret_cast<const LlePatch*>(dblob + h.patch_off);
+    m.stat = reinterpret_cast<const float*>(dblob + h.static_off);
+    m.agent_planes = reinterpret_cast<const LleAgentPlane*>(dblob + h.ap_off);
+    m.n_ap = h.n_ap;
+    m.chunk_tbl = reinterpret_cast<const uint32_t*>(dblob + h.chunk_tbl_off);
+    m.n_patch = h.n_patch;
+    m.NB = h.NB;
+    m.obs_floats = h.obs_floats;
+    m.gem_toplevel = h.gem_toplevel;
+    return m;
 }
 
 KParams base_params(lle_vec* v) {
@@ -473,6 +503,7 @@ int lle_vec_destroy(lle_vec* v) {
         cudaFree(v->d_stage[k]);
     }
     cudaFree(v->d_pipe_flags);
+    cudaFree(v->d_retired_count);
     if (v->h_out_flags) cudaFreeHost(v->h_out_flags);
     if (v->h_retired_seq) cudaFreeHost(v->h_retired_seq);
     if (v->ev_user) cudaEventDestroy(v->ev_user);
@@ -683,8 +714,8 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         // worlds per tile / bulk store (measured on 2^20 5x5 worlds, us per step: 4: 232, 8: 243, 16: 343, 32: 558 - occupancy)
         int e = env_int("LLE_B200_TINY_E", 4);
         v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 4;
-        auto tiny_bytes = [&]() {  // the records' columns + the prefetched next records, 16 staged list entries per lane, pointers, counts, the tile
-            const size_t bytes = 2 * (size_t)v->L.stride * 32 * 4 + 16 * 32 * sizeof(LlePatch) + 32 * 8 + 32 * 4 + (size_t)v->tiny_E * stride * 4;
+        auto tiny_bytes = [&]() {  // the records' columns + the prefetched next records, list pointers, list lengths, the tile
+            const size_t bytes = 2 * (size_t)v->L.stride * 32 * 4 + 32 * 8 + 32 * 4 + (size_t)v->tiny_E * stride * 4;
             return (bytes + 127) / 128 * 128;
         };
         v->tiny_chunk = std::max(1, std::min(64, env_int("LLE_B200_TINY_CHUNK", 1)));
@@ -735,6 +766,10 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         LLE_CUDA(cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice));
         table.push_back(d);
     }
+    if (!v->randomize) {  // blob 0 is map 0 as given
+        v->map0 = host_bind(v->d_blobs[0], upload[0]->header());
+        v->has_map0 = true;
+    }
     LLE_CUDA(cudaMalloc((void**)&v->d_blob_table, table.size() * sizeof(uint8_t*)));
     LLE_CUDA(cudaMemcpy((void*)v->d_blob_table, table.data(), table.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice));
     if ((map_of_env && n_maps > 1) || v->randomize) {
@@ -774,8 +809,9 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     }
     LLE_CUDA(dalloc(&v->d_sched, (size_t)kSchedSlotWords * kSchedSlots));
     LLE_CUDA(dalloc(&v->d_flags, (size_t)(v->N_pad / v->group)));
-    LLE_CUDA(cudaHostAlloc((void**)&v->h_retired_seq, sizeof(uint32_t), cudaHostAllocMapped));
-    *v->h_retired_seq = 0;
+    LLE_CUDA(cudaHostAlloc((void**)&v->h_retired_seq, 64 * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(v->h_retired_seq, 0, 64 * sizeof(uint32_t));
+    LLE_CUDA(dalloc(&v->d_retired_count, 1));
     LLE_CUDA(dalloc(&v->d_actions_stage, (size_t)v->A * Np));
     if (env_int("LLE_B200_TIMELINE", 0)) LLE_CUDA(dalloc(&v->d_timeline, (size_t)v->grid * kWarps * 4));
     LLE_CUDA(cudaEventCreate(&v->ev0));
@@ -879,7 +915,10 @@ int swap_map(lle_vec* v, int map_index, const std::vector<SourceState>& sources,
     v->map_obs_invalid[(size_t)map_index] = (int)cm.header().obs_invalid;
     v->obs_invalid = 0;
     for (int f : v->map_obs_invalid) v->obs_invalid |= f;
-    if (map_index == 0) v->hdr0 = cm.header();
+    if (map_index == 0) {
+        v->hdr0 = cm.header();
+        v->map0 = host_bind(d, cm.header());
+    }
     v->last_was_step = false;
     if (out_cm) *out_cm = std::move(cm);
     return LLE_OK;

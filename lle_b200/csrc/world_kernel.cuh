@@ -37,6 +37,37 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 enum Mode : int { MODE_STEP = 0, MODE_RESET = 1, MODE_SET_STATE = 2 };
 
+// ---- map view -------------------------------------------------------------------------------------------
+struct MapDev {
+    const uint8_t* blob;
+    const LleMapHeader* hdr;
+    const uint32_t* cellinfo;
+    const LleCellBeams* cellbeams;
+    const LleBeam* beams;
+    const LlePatch* patches;
+    const float* stat;
+    const LleAgentPlane* agent_planes;
+    const uint32_t* chunk_tbl;
+    int n_patch, NB, obs_floats, n_ap;
+    uint64_t gem_toplevel;
+    __device__ __forceinline__ void bind(const uint8_t* b) {
+        blob = b;
+        hdr = reinterpret_cast<const LleMapHeader*>(b);
+        cellinfo = reinterpret_cast<const uint32_t*>(b + hdr->cellinfo_off);
+        cellbeams = reinterpret_cast<const LleCellBeams*>(b + hdr->cellbeams_off);
+        beams = reinterpret_cast<const LleBeam*>(b + hdr->beams_off);
+        patches = reinterpret_cast<const LlePatch*>(b + hdr->patch_off);
+        stat = reinterpret_cast<const float*>(b + hdr->static_off);
+        agent_planes = reinterpret_cast<const LleAgentPlane*>(b + hdr->ap_off);
+        n_ap = hdr->n_ap;
+        chunk_tbl = reinterpret_cast<const uint32_t*>(b + hdr->chunk_tbl_off);
+        n_patch = hdr->n_patch;
+        NB = hdr->NB;
+        obs_floats = hdr->obs_floats;
+        gem_toplevel = hdr->gem_toplevel;
+    }
+};
+
 struct KParams {
     const uint8_t* const* blobs;  // device array [n_maps] of map blobs
     int32_t* map_of_env;          // device [N_pad] or nullptr: index of each env's current map blob.  With randomize_lasers the
@@ -75,6 +106,13 @@ struct KParams {
                            // completed uses of the slot (slots rotate; a launch may only touch its slot once the launch that
                            // used it before has re-armed it, see sched_gen)
     uint32_t sched_gen;    // generation this launch expects in sched[2]
+    uint32_t sched_check;  // 0: the host saw the launch that used this slot before retire - no need to look at the generation
+    uint32_t* retired_launch;  // host-mapped: number of launches of the vec (any mode) whose last warp has left
+    uint32_t* retired_count;   // device counter behind it
+    // The tables of map 0 resolved on the host (pointers into its blob): a batch on one map binds them from the parameters instead
+    // of chasing blob table -> header -> tables through three dependent L2 round trips at the start of every warp.
+    MapDev map0;
+    int32_t has_map0, pad_map0;
     uint32_t* flags;       // [n_tickets] sequence number of the last step completed for the ticket's worlds
     uint32_t seq;          // sequence number of the (first) step of this launch; step q of a ticket needs flags >= q-1
     uint32_t n_tickets, n_warps_total;
@@ -134,36 +172,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// ---- map view -------------------------------------------------------------------------------------------
-struct MapDev {
-    const uint8_t* blob;
-    const LleMapHeader* hdr;
-    const uint32_t* cellinfo;
-    const LleCellBeams* cellbeams;
-    const LleBeam* beams;
-    const LlePatch* patches;
-    const float* stat;
-    const LleAgentPlane* agent_planes;
-    const uint32_t* chunk_tbl;
-    int n_patch, NB, obs_floats, n_ap;
-    uint64_t gem_toplevel;
-    __device__ __forceinline__ void bind(const uint8_t* b) {
-        blob = b;
-        hdr = reinterpret_cast<const LleMapHeader*>(b);
-        cellinfo = reinterpret_cast<const uint32_t*>(b + hdr->cellinfo_off);
-        cellbeams = reinterpret_cast<const LleCellBeams*>(b + hdr->cellbeams_off);
-        beams = reinterpret_cast<const LleBeam*>(b + hdr->beams_off);
-        patches = reinterpret_cast<const LlePatch*>(b + hdr->patch_off);
-        stat = reinterpret_cast<const float*>(b + hdr->static_off);
-        agent_planes = reinterpret_cast<const LleAgentPlane*>(b + hdr->ap_off);
-        n_ap = hdr->n_ap;
-        chunk_tbl = reinterpret_cast<const uint32_t*>(b + hdr->chunk_tbl_off);
-        n_patch = hdr->n_patch;
-        NB = hdr->NB;
-        obs_floats = hdr->obs_floats;
-        gem_toplevel = hdr->gem_toplevel;
-    }
-};
 
 // =============================================================================================================
 // Sub-warp groups: a warp processes P = 32/Wd worlds at once, Wd = the power of two >= n_agents.  Lane
@@ -723,6 +731,7 @@ __device__ __forceinline__ void launch_epilogue(const KParams& p, bool is_step) 
         __threadfence();
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sched + 2), "r"(p.sched_gen + 1u) : "memory");
         if (is_step && p.retired_seq) *p.retired_seq = p.seq + (uint32_t)p.n_steps - 1u;
+        if (p.retired_launch) *p.retired_launch = atomicAdd(p.retired_count, 1u) + 1u;  // a lower bound of the launches that have retired
         if (p.out_flag) {
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.out_flag), "r"(p.out_value) : "memory");
@@ -780,7 +789,8 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     uint32_t fresh_bits = 0;  // FAST: sub-tiles that hold a pristine static plane (nothing to un-patch yet)
     if constexpr (FAST) {
         if (p.map_of_env == nullptr) {  // one map for the whole batch: bind it once and prefetch its static plane
-            w.m.bind(p.blobs[0]);
+            if (p.has_map0) w.m = p.map0;
+            else w.m.bind(p.blobs[0]);
             bound_map = 0;
             rm = w.m;
             render_map = 0;
@@ -811,9 +821,11 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     // Scheduler slots rotate over the launches.  Programmatic dependent launch lets many small launches be resident at once,
     // so the launch that used this slot kSchedSlots launches ago may still be running: wait until its last warp has re-armed
     // the slot (it never waits for us, and all of its CTAs are resident by the time this launch may start: no cycle).
-    if (lane == 0)
-        while (!sched_slot_armed(p.sched + 2, p.sched_gen)) __nanosleep(32);
-    __syncwarp();
+    if (p.sched_check) {
+        if (lane == 0)
+            while (!sched_slot_armed(p.sched + 2, p.sched_gen)) __nanosleep(32);
+        __syncwarp();
+    }
     uint64_t t_first = 0, t_last = 0;
     if (p.timeline && lane == 0) p.timeline[warp_global * 4] = globaltimer_ns();
     int step_index = 0;
@@ -824,16 +836,23 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     const uint32_t chunk = (uint32_t)max(p.ticket_chunk, 1);
     uint32_t chunk_next = 0, chunk_end = 0;  // lane 0: the pairs of the chunk this warp holds
     const bool single_step = p.n_steps == 1;
+    // On an idle device (the host saw every earlier launch retire: a closed loop) all CTAs are resident at once and a warp's first
+    // pair is its own index - no round trip to the launch's counter before it can start.  Not when launches overlap: CTAs then
+    // trickle in as their predecessors' retire, and a pair pinned to a late CTA would hold up everything behind it.
+    bool first_pair = p.sched_check == 0;
     for (;;) {
-        uint32_t pair = 0;
-        if (lane == 0) {
-            if (chunk_next >= chunk_end) {
-                chunk_next = atomicAdd(&p.sched[0], chunk);
-                chunk_end = chunk_next + chunk;
+        uint32_t pair = warp_global;
+        if (!first_pair) {
+            if (lane == 0) {
+                if (chunk_next >= chunk_end) {
+                    chunk_next = (p.sched_check == 0 ? p.n_warps_total : 0u) + atomicAdd(&p.sched[0], chunk);  // behind the static pairs, if any
+                    chunk_end = chunk_next + chunk;
+                }
+                pair = chunk_next++;
             }
-            pair = chunk_next++;
+            pair = __shfl_sync(kFull, pair, 0);
         }
-        pair = __shfl_sync(kFull, pair, 0);
+        first_pair = false;
         if (pair >= n_pairs) break;
         const uint32_t ticket = single_step ? pair : pair % p.n_tickets;
         step_index = single_step ? 0 : (int)(pair / p.n_tickets);
@@ -885,7 +904,8 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             if (!FAST || p.map_of_env != nullptr) {
                 map_id = p.map_of_env ? __ldcg(p.map_of_env + env) : 0;  // through L2: a reset of the previous (overlapped) step may have rewritten it
                 if (map_id != bound_map) {
-                    w.m.bind(p.blobs[map_id]);
+                    if (map_id == 0 && p.has_map0) w.m = p.map0;
+                    else w.m.bind(p.blobs[map_id]);
                     bound_map = map_id;
                 }
                 if (gl == 0) map_ids[g] = map_id;

@@ -148,7 +148,7 @@ void step_all(Shim& s, const int8_t* actions_in) {
                 const int sidx = lane - r * E;
                 float* sub = wp.tile.data() + (size_t)sidx * s.ostr;
                 for (int64_t f = 0; f < s.ostr; ++f) sub[f] = 0.0f;
-                w.render(sub, s.H * s.W, [&](int k) { return w.list[k]; });
+                w.render(sub, s.H * s.W);
             }
             for (int sidx = 0; sidx < E; ++sidx) {
                 const int64_t env = ticket * 32 + (int64_t)r * E + sidx;
