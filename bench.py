@@ -25,6 +25,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -65,30 +66,46 @@ def ncu_traffic() -> dict:
 
 
 class ClockSampler:
+    """`nvidia-smi -lms 20` in the background, its lines collected by a reader thread.  nvidia-smi needs 50-150 ms to print its first
+    line and the timed window of the default run is 1.6 ms, so the sampler is started BEFORE the untimed preheat (the same
+    kernel, back to back): the preheat runs until samples arrive, and the samples kept are those taken under that continuous
+    load up to the end of the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
         self.proc = None
+        self.lines: list[str] = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
+
+    def _read(self):
+        try:
+            for line in self.proc.stdout:
+                self.lines.append(line)
+        except Exception:
+            pass
+
+    def n_samples(self) -> int:
+        return len(self.lines)
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        lines = list(self.lines)  # what was sampled up to now: under load
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
         sm, mx, reasons, power = [], [], set(), []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in out.splitlines():
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -102,7 +119,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": "preheat + warm-up + timed steps + rollout: the step kernel back to back", "reasons": sorted(reasons)}
 
 
 def cpu_baseline(sample_seconds: float = 12.0, n_envs: int = 4096, threads: int = 0) -> dict:
@@ -220,9 +237,15 @@ def run_ours(args) -> None:
     # ---------------- device-resident arm: K fused steps back to back, no host sync inside.
     # Untimed preheat first (not counted as warm-up steps): a fresh process finds the GPU at idle clocks, and W = 5 steps are
     # 0.4 ms of work; the timed window should see the clocks a running job sees.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     t0 = time.perf_counter()
     preheat = 0
-    while time.perf_counter() - t0 < args.preheat_ms / 1e3:
+    while True:
+        elapsed = time.perf_counter() - t0
+        # the GPUs stay loaded until rank 0's nvidia-smi has delivered a few samples (bounded: 2 s); every rank stops together
+        more = 1.0 if (elapsed < args.preheat_ms / 1e3 or (sampler is not None and sampler.proc is not None and sampler.n_samples() < 3 and elapsed < 2.0)) else 0.0
+        if reduce_max(more) == 0.0:
+            break
         for _ in range(64):
             vec.step(None)
         preheat += 64
@@ -230,7 +253,6 @@ def run_ours(args) -> None:
     for _ in range(Wm):
         vec.step(None)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = vec.launch_count
     vec.timing_begin()
     for _ in range(K):

@@ -22,6 +22,8 @@ SYMBOLS = [
     "lle_vec_export_raw", "lle_vec_set_seed", "lle_vec_get_step_count", "lle_vec_set_step_count", "lle_vec_launch_count",
     "lle_vec_timing_begin", "lle_vec_timing_end", "lle_vec_debug_timeline", "lle_host_alloc", "lle_host_free", "lle_vec_fetch", "lle_vec_export_raw_state", "lle_vec_import_raw_state",
     "lle_vec_get_reset_count", "lle_vec_set_reset_count",
+    "lle_vec_parts_begin", "lle_vec_parts_count", "lle_vec_parts_range", "lle_vec_parts_launch", "lle_vec_parts_feed", "lle_vec_parts_wait",
+    "lle_vec_parts_end", "lle_vec_parts_abort",
     "lle_gen_default_options", "lle_gen_create", "lle_gen_destroy", "lle_gen_attempt_seeds", "lle_gen_run", "lle_gen_get_buffers",
     "lle_gen_fetch", "lle_gen_geometry_valid", "lle_gen_cells_to_text",
 ]
@@ -108,6 +110,13 @@ def lib():
     L.lle_vec_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lle_vec_pipeline_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lle_vec_pipeline_wait.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.lle_vec_parts_begin.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lle_vec_parts_count.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.lle_vec_parts_range.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    for name in ("lle_vec_parts_launch", "lle_vec_parts_end", "lle_vec_parts_abort"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.lle_vec_parts_feed.argtypes = [C.c_void_p, C.c_int32]
+    L.lle_vec_parts_wait.argtypes = [C.c_void_p, C.c_int32]
     L.lle_vec_set_source.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.lle_vec_get_sources.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
     L.lle_vec_set_exits.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p]

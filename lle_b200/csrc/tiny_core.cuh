@@ -18,6 +18,53 @@ struct TinyLayout {  // the part of LleStateLayout a tiny record uses (n_words <
     bool has_gems;
 };
 
+// ---- PartialGenerator.observe (observations.py:331-350): agent a sees a (2A+3, size, size) window centred on itself; channels:
+// the agents, WALL, one laser channel per agent colour, GEM, EXIT.  `sub` is the world's ZERO-FILLED block of A windows.
+// One task = (agent a, window cell r): look the map cell up once and write its few non-zero channels.  `recw(word)` reads a word of
+// the world's record (static_map.h; tiny records: one word per beam, one gem word); pa = packed position of agent a.
+template <class RecW>
+LLE_HD void partial_cell_task(float* sub, int A, int a, int r, int sz, uint32_t pa, int H, int W, const uint32_t* cellinfo,
+                              const LleCellBeams* cellbeams, int w_gems, int w_on, RecW recw) {
+    const int s2 = sz * sz, ctr = sz >> 1, Cp = 2 * A + 3;
+    const int wi = (int)(((float)r + 0.5f) * (1.0f / (float)sz)), wj = r - wi * sz;  // exact for these small integers
+    const int i = (int)(pa >> 8) + wi - ctr, j = (int)(pa & 0xFFu) + wj - ctr;
+    if (i < 0 || j < 0 || i >= H || j >= W) return;  // outside the map: every layer stays 0 (:325-329)
+    const int c = i * W + j;
+    const uint32_t info = cellinfo[c];
+    if (!(info & (7u | (1u << 24)))) return;  // plain floor without a beam
+    float* o = sub + a * Cp * s2 + r;
+    const uint32_t kind = info & 7u;
+    if (kind == LLE_T_WALL) {
+        if (info & (1u << 25)) o[A * s2] = 1.0f;  // World::walls(): the walls and the v1 sources, not the TOML [[lasers]] sources
+        if (info & 128u) {
+            const int ch = A + 1 + (int)((info >> 16) & 255u);  // LASER_0 + source.agent_id, filled with -1 (:348-350)
+            if (ch < Cp) o[ch * s2] = -1.0f;
+        }
+    } else if (kind == LLE_T_EXIT) {
+        o[(2 * A + 2) * s2] = 1.0f;
+    } else if (kind == LLE_T_GEM) {
+        if (!((recw(w_gems) >> ((info >> 8) & 31u)) & 1u)) o[(2 * A + 1) * s2] = 1.0f;
+    }
+    if (info & (1u << 24)) {
+        const LleCellBeams cb = cellbeams[c];
+        LLE_UNROLL
+        for (int n = 0; n < 4; ++n) {  // lit lasers listed by World::lasers (:352-360)
+            const uint32_t e = cb.e[n];
+            if (e == LLE_NO_BEAM) break;
+            if (be_listed(e) && ((recw(w_on + be_b(e)) >> be_k(e)) & 1u)) {
+                const int ch = A + 1 + be_colour(e);
+                if (ch < Cp) o[ch * s2] = 1.0f;
+            }
+        }
+    }
+}
+// agent layers (:335-336): agent a2 as seen from agent a, one task per ordered pair
+LLE_HD void partial_agent_task(float* sub, int A, int a, int a2, int sz, uint32_t pa, uint32_t pb) {
+    const int ctr = sz >> 1;
+    const int di = (int)(pb >> 8) - (int)(pa >> 8) + ctr, dj = (int)(pb & 0xFFu) - (int)(pa & 0xFFu) + ctr;
+    if (di >= 0 && dj >= 0 && di < sz && dj < sz) sub[(a * (2 * A + 3) + a2) * sz * sz + di * sz + dj] = 1.0f;
+}
+
 template <int A_, class Rec>
 struct TinyWorld {
     Rec rec;
@@ -258,6 +305,14 @@ struct TinyWorld {
         }
         LLE_UNROLL
         for (int a = 0; a < A_; ++a) sub[a * HW + (int)(pos[a] >> 8) * W + (int)(pos[a] & 0xFFu)] = 1.0f;
+    }
+    // ---- partial observation (observations.py:312-369) of this world in `sub`, a ZERO-FILLED block; H = rows of the map
+    LLE_HD void render_partial(float* sub, int sz, int H) {
+        for (int a = 0; a < A_; ++a)
+            for (int r = 0; r < sz * sz; ++r)
+                partial_cell_task(sub, A_, a, r, sz, pos[a], H, W, cellinfo, cellbeams, L.w_gems, L.w_on, [&](int word) { return rec(word); });
+        for (int a = 0; a < A_; ++a)
+            for (int a2 = 0; a2 < A_; ++a2) partial_agent_task(sub, A_, a, a2, sz, pos[a], pos[a2]);
     }
 };
 

@@ -22,7 +22,7 @@
 // Everything around it is the general kernel's protocol, unchanged: tickets of 32 worlds handed out by an atomic counter,
 // per-ticket epoch flags for the dataflow ordering between overlapped launches and rollout steps, the record layout
 // (static_map.h), Philox action sampling, auto-reset, the host-pipeline flags.  Reset / set_state / refresh launches of the
-// same vec run on the general kernel.  Results are bit-identical by construction of the tests (tests/test_gpu_parity.py,
+// same vec run on the general kernel, and so do the steps of a parts loop (lle_vec_parts_*).  Results are bit-identical by construction of the tests (tests/test_gpu_parity.py,
 // tests/test_gpu_fullsize.py run both).
 #pragma once
 #include "tiny_core.cuh"
@@ -57,8 +57,10 @@ __device__ __forceinline__ void store_bytes(uint8_t* dst, const uint32_t (&b)[N]
     }
 }
 
-template <int A_>
-__global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_kernel(const KParams p) {
+// PARTIAL: the observation is PartialGenerator's (A windows of size x size per world, tiny_core.cuh partial_cell_task) instead of
+// the layered block; its own instantiation, so that the layered kernel keeps its 72 registers / 7 CTAs per SM.
+template <int A_, bool PARTIAL = false>
+__global__ void __launch_bounds__(kThreads, PARTIAL ? 4 : LLE_TINY_MIN_CTAS) lle_tiny_step_kernel(const KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = p.L.stride, w_flags = p.L.w_flags, w_avail = p.L.w_avail, w_gems = p.L.w_gems, w_on = p.L.w_on;
@@ -67,9 +69,10 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
     uint8_t* wbase = smem_raw + (size_t)warp * p.warp_smem_bytes;
     uint32_t* srec = reinterpret_cast<uint32_t*>(wbase);                             // [stride][32]: word k of lane l at k*32+l
     uint32_t* snext = srec + stride * 32;                                            // [32][stride]: the NEXT ticket's records, prefetched
-    const LlePatch** slptr = reinterpret_cast<const LlePatch**>(snext + stride * 32); // [32]: the render list of lane l's map
+    const LlePatch** slptr = reinterpret_cast<const LlePatch**>(snext + stride * 32); // [32]: the render list of lane l's map (PARTIAL: its cellinfo)
     uint32_t* smeta = reinterpret_cast<uint32_t*>(slptr + 32);                       // [32]: n_static | n_patch << 16 of lane l's map
-    float* tile = reinterpret_cast<float*>(smeta + 32);                              // [E][ostr]: E worlds per bulk store
+    float* tile = reinterpret_cast<float*>(smeta + 32 + (PARTIAL ? 64 : 0));         // [E][ostr]: E worlds per bulk store
+    const LleCellBeams** sbeams = reinterpret_cast<const LleCellBeams**>(smeta + 32);  // PARTIAL: [32] the beam table of lane l's map
     const int E = p.E;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.in_flag) {  // host-supplied actions still in flight on the copy stream
@@ -281,17 +284,37 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
             // E worlds per round are built in a zero-filled shared-memory tile by ALL lanes - 32 / E lanes share a world's render
             // list (read from the owner lane's staged copy and record column) - and leave with one TMA bulk store.
             const int lgE = 31 - __clz(E), lgl = 5 - lgE, lpw = 1 << lgl;  // lanes per world
-            smeta[lane] = (uint32_t)w.n_static | ((uint32_t)w.n_patch << 16);
-            slptr[lane] = w.list;
+            if constexpr (PARTIAL) {
+                slptr[lane] = reinterpret_cast<const LlePatch*>(w.cellinfo);
+                sbeams[lane] = w.cellbeams;
+            } else {
+                smeta[lane] = (uint32_t)w.n_static | ((uint32_t)w.n_patch << 16);
+                slptr[lane] = w.list;
+            }
             __syncwarp();
             for (int r = 0; r < (32 >> lgE); ++r) {
                 if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
                 __syncwarp();
                 for (int f = lane * 4; f < E * ostr; f += 128) *reinterpret_cast<float4*>(tile + f) = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
-                {
-                    const int ws = (r << lgE) + (lane >> lgl), q = lane & (lpw - 1);  // the world this lane helps to draw, and its share
-                    float* sub = tile + (size_t)(lane >> lgl) * ostr;
+                const int ws = (r << lgE) + (lane >> lgl), q = lane & (lpw - 1);  // the world this lane helps to draw, and its share
+                float* sub = tile + (size_t)(lane >> lgl) * ostr;
+                auto agent_pos = [&](int a) {
+                    const uint32_t wd = srec[(a >> 1) * 32 + ws];
+                    return (a & 1) ? (wd >> 16) : (wd & 0xFFFFu);
+                };
+                if constexpr (PARTIAL) {
+                    // one task per (agent, window cell), then one per ordered pair of agents (observations.py:331-350)
+                    const int sz = p.obs_param, s2 = sz * sz;
+                    const uint32_t* ci = reinterpret_cast<const uint32_t*>(slptr[ws]);
+                    const LleCellBeams* cbm = sbeams[ws];
+                    const float inv_s2 = 1.0f / (float)s2;
+                    for (int t = q; t < A_ * s2; t += lpw) {
+                        const int a = (int)(((float)t + 0.5f) * inv_s2);  // exact for these small integers
+                        partial_cell_task(sub, A_, a, t - a * s2, sz, agent_pos(a), p.H, W, ci, cbm, w_gems, w_on, [&](int word) { return srec[word * 32 + ws]; });
+                    }
+                    for (int t = q; t < A_ * A_; t += lpw) partial_agent_task(sub, A_, t / A_, t % A_, sz, agent_pos(t / A_), agent_pos(t % A_));
+                } else {
                     const uint32_t meta = smeta[ws];
                     const int ns = (int)(meta & 0xFFFFu), n = ns + (int)(meta >> 16);
                     auto draw = [&](const LlePatch pe, int k) {
@@ -305,8 +328,7 @@ __global__ void __launch_bounds__(kThreads, LLE_TINY_MIN_CTAS) lle_tiny_step_ker
                     const LlePatch* list = slptr[ws];
                     for (int k = q; k < n; k += lpw) draw(list[k], k);
                     for (int a = q; a < A_; a += lpw) {  // the agents' one-hots (:264-265): their planes hold nothing else
-                        const uint32_t wd = srec[(a >> 1) * 32 + ws];
-                        const uint32_t pp = (a & 1) ? (wd >> 16) : (wd & 0xFFFFu);
+                        const uint32_t pp = agent_pos(a);
                         sub[a * p.HW + (int)(pp >> 8) * W + (int)(pp & 0xFFu)] = 1.0f;
                     }
                 }

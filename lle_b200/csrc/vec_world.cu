@@ -100,7 +100,7 @@ struct lle_vec {
     bool by_feature = false;  // partial observations rendered feature by feature (kernel KIND 2): every map has <= 2 s^2 features
     bool force_narrow = false;  // LLE_B200_FORCE_NARROW=1 (tests)
     // tiny maps: step launches run the thread-per-world kernel (tiny_kernel.cuh) with its own tiling and grid
-    bool tiny = false;
+    bool tiny = false, tiny_partial = false;
     int tiny_E = 8, tiny_warp_smem = 0, tiny_grid = 0, tiny_chunk = 1;
     int chunk = 1;  // general kernel: pairs per scheduler atomic (LLE_B200_CHUNK)
     size_t tiny_smem = 0;
@@ -127,6 +127,19 @@ struct lle_vec {
     uint32_t* h_out_flags = nullptr;   // pinned + mapped, one word per ring slot: submit n has retired and its results are in host memory
     uint32_t* d_out_flags = nullptr;   // the same words as the device sees them
     uint64_t pipe_submitted = 0, pipe_completed = 0;
+    // closed loop over parts of the batch (lle_vec_parts_*)
+    int parts_n = 0;                    // > 0: a parts loop is open
+    uint32_t parts_tpp = 0;             // tickets per part
+    uint64_t parts_launched = 0;        // whole-batch steps enqueued in this loop
+    std::vector<uint64_t> parts_fed, parts_read;  // per part: steps whose actions were released / whose results were waited for
+    uint32_t* d_part_in = nullptr;      // device: [parts][32] steps fed (written by stream memory ops on s_in)
+    uint32_t* h_part_out = nullptr;     // pinned + mapped: [parts][32] steps whose reward / done are in host memory
+    uint32_t* d_part_out = nullptr;     // the same words as the device sees them
+    uint32_t* d_part_count = nullptr;   // device: [parts] tickets of the part completed in the running step
+    int parts_cap = 0;
+    const int8_t* parts_actions_dev = nullptr;  // device views of the caller's pinned buffers
+    float* parts_reward = nullptr;
+    uint8_t* parts_done = nullptr;
     const void* pinned_seen[32] = {};  // host pointers already checked to be page-locked ...
     void* pinned_dev[32] = {};         // ... and the address the device reaches them at
     unsigned pinned_next = 0;
@@ -150,7 +163,9 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
     // step launches are resident at once and form a software pipeline over the epoch flags: while step t drains, steps
     // t+1.. already stream their first tickets.  Rollouts, resets and set_state use the full-width grid.
     const bool overlaps = v->pdl && MODE == MODE_STEP && v->last_was_step && v->last_stream == s;
-    const int grid = (overlaps && p.n_steps == 1 && v->narrow_next) ? v->grid_step : v->grid;
+    // (A parts loop takes the full grid too: its launches wait for the host part by part, and a wide grid keeps enough unblocked
+    // warps resident.  Level 6 x 65,536, 8 parts, us per step with 2 / 3 / 5 CTAs per SM: 96.9 / 87.8 / 84.5.)
+    const int grid = (overlaps && p.n_steps == 1 && v->narrow_next && !p.part_in) ? v->grid_step : v->grid;
     v->narrow_next = false;
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
@@ -164,7 +179,7 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if constexpr (MODE == MODE_STEP) {
-        if (v->tiny) {  // thread-per-world kernel: same tickets, flags and records, its own tile layout
+        if (v->tiny && !p.part_in) {  // thread-per-world kernel: same tickets, flags and records, its own tile layout (not in a parts loop)
             cfg.gridDim = dim3((unsigned)v->tiny_grid);
             cfg.dynamicSmemBytes = v->tiny_smem;
             p.n_warps_total = (uint32_t)(v->tiny_grid * kWarps);
@@ -172,11 +187,15 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
             p.tile_floats = (int32_t)(v->tiny_E * v->obs_stride);
             p.warp_smem_bytes = v->tiny_warp_smem;
             p.ticket_chunk = v->tiny_chunk;
-            switch (v->A) {
-                case 1: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<1>, p);
-                case 2: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<2>, p);
-                case 3: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<3>, p);
-                default: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<4>, p);
+            switch (v->A * 2 + (v->tiny_partial ? 1 : 0)) {
+                case 2: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<1, false>, p);
+                case 3: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<1, true>, p);
+                case 4: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<2, false>, p);
+                case 5: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<2, true>, p);
+                case 6: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<3, false>, p);
+                case 7: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<3, true>, p);
+                case 8: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<4, false>, p);
+                default: return cudaLaunchKernelEx(&cfg, lle_tiny_step_kernel<4, true>, p);
             }
         }
     }
@@ -491,6 +510,7 @@ void lle_vec_default_options(lle_vec_options* o) {
 int lle_vec_destroy(lle_vec* v) {
     if (!v) return LLE_OK;
     cudaSetDevice(v->device);
+    if (v->parts_n) lle_vec_parts_abort(v);  // no kernel may be left waiting for actions
     if (v->shadow) lle_vec_destroy(v->shadow);
     if (v->borrows_records) { v->d_records = nullptr; v->d_map_of_env = nullptr; }
     for (auto* b : v->d_blobs) cudaFree(b);
@@ -505,6 +525,9 @@ int lle_vec_destroy(lle_vec* v) {
     cudaFree(v->d_pipe_flags);
     cudaFree(v->d_retired_count);
     if (v->h_out_flags) cudaFreeHost(v->h_out_flags);
+    if (v->h_part_out) cudaFreeHost(v->h_part_out);
+    if (v->d_part_in) cudaFree(v->d_part_in);
+    if (v->d_part_count) cudaFree(v->d_part_count);
     if (v->h_retired_seq) cudaFreeHost(v->h_retired_seq);
     if (v->ev_user) cudaEventDestroy(v->ev_user);
     if (v->s_in) cudaStreamDestroy(v->s_in);
@@ -634,6 +657,16 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     // CTAs per SM (sweep of buffers x tile size x ticket size on level 6 x 65,536, us per step before -> after:
     // partial3x3 72.5 -> 57.9, partial5x5 84.4 -> 79.2, partial7x7 134.7 -> 94.5)
     const bool partial_obs = spec.kind == LLE_OBS_PARTIAL;
+    bool random_starts = false;  // start sampling lives in the general kernel only
+    for (int k = 0; k < n_maps; ++k) random_starts = random_starts || cms[k]->header().random_starts;
+    // a record the thread-per-world kernel (tiny_kernel.cuh) can hold: few agents, at most 8 words, one word per beam, one gem word
+    const bool tiny_record = v->A <= 4 && v->L.n_words <= 8 && !v->L.wide_flags && v->L.on_words == 1 && v->L.gem_words <= 1 && v->L.sub_words == 0 &&
+                             !v->randomize && !random_starts && opts->write_obs && !env_int("LLE_B200_NO_TINY", 0);
+    // Partial observations of such worlds, when the windows of one world (A (2A+3) size^2 floats) are under 2 KB (level 6: 3x3):
+    // built by 32 / E lanes in a tile of E worlds; tickets of 32 worlds.  Level 6 x 65,536, us per step, this kernel / the general
+    // one: 3x3 52.5 / 58-67, 5x5 90 / 85, 7x7 166 / 98 - with 2,048 tickets a launch is one wave of warps and the step takes as
+    // long as one ticket, so larger windows (more rounds per ticket) stay on the general kernel, which has four times the warps.
+    const bool tiny_partial = partial_obs && tiny_record && (stride * 4 < 2048 || env_int("LLE_B200_TINY_PARTIAL", 0));
     const int64_t kTileTargetFloats = env_int("LLE_B200_TILE_TARGET", partial_obs ? 2400 : small_obs ? 2048 : 1024);
     // the partial renderer builds whole worlds (all agents' windows) in one tile: allow up to 48 KB per warp
     const int64_t kTileMaxFloats = spec.kind == LLE_OBS_PARTIAL ? 12288 : 6144;
@@ -644,7 +677,7 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->E = std::max(1, std::min(32, pow2_floor((int)std::max<int64_t>(1, kTileTargetFloats / stride))));
         v->chunk_floats = (int)stride;
         v->tile_floats = (int)(v->E * stride);
-        v->group = partial_obs ? std::max(std::max(v->E, 16), 32 / v->Wd) : small_obs ? 32 : std::max(std::max(v->E, 8), 32 / v->Wd);
+        v->group = tiny_partial ? 32 : partial_obs ? std::max(std::max(v->E, 16), 32 / v->Wd) : small_obs ? 32 : std::max(std::max(v->E, 8), 32 / v->Wd);
         v->n_buf = 1;
     } else {
         v->E = 1;
@@ -682,8 +715,6 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     int max_patch = 0;
     for (int k = 0; k < n_maps; ++k) max_patch = std::max(max_patch, (int)cms[k]->header().n_patch);
     for (const auto& m : v->variant_maps) max_patch = std::max(max_patch, (int)m.header().n_patch);
-    bool random_starts = false;  // start sampling lives in the general kernel only
-    for (int k = 0; k < n_maps; ++k) random_starts = random_starts || cms[k]->header().random_starts;
     v->fast = v->n_chunks == 1 && v->E <= 32 && v->n_buf == 1 && max_patch <= 64 && v->L.stride <= 32 && opts->write_obs &&
               spec.kind == LLE_OBS_LAYERED && !v->randomize && !random_starts && !env_int("LLE_B200_NO_FAST", 0);
     if (spec.kind == LLE_OBS_PARTIAL && !env_int("LLE_B200_NO_FEATURES", 0)) {
@@ -708,14 +739,19 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     }
     if (blocks_per_sm < 1) return fail(LLE_CUDA_ERROR, "kernel does not fit on an SM");
     // Tiny maps (small observation, few agents, a record of at most 8 words): the step runs one thread per world.
-    v->tiny = v->fast && small_obs && v->A <= 4 && v->L.n_words <= 8 && !v->L.wide_flags && v->L.on_words == 1 && v->L.gem_words <= 1 &&
-              v->L.sub_words == 0 && v->group == 32 && !env_int("LLE_B200_NO_TINY", 0);
+    v->tiny = ((v->fast && small_obs) || tiny_partial) && tiny_record && v->group == 32;
+    v->tiny_partial = v->tiny && tiny_partial;
     if (v->tiny) {
         // worlds per tile / bulk store (measured on 2^20 5x5 worlds, us per step: 4: 232, 8: 243, 16: 343, 32: 558 - occupancy)
-        int e = env_int("LLE_B200_TINY_E", 4);
-        v->tiny_E = (e == 4 || e == 8 || e == 16 || e == 32) ? e : 4;
+        int e_default = 4;
+        if (tiny_partial) {  // the largest tile of at most 13 KB (level 6 3x3: 8 worlds; measured 2 / 4 / 8: 60.8 / 57.0 / 52.5 us)
+            e_default = 1;
+            while (e_default < 32 && 2 * e_default * stride * 4 <= 13312) e_default *= 2;
+        }
+        int e = env_int("LLE_B200_TINY_E", e_default);
+        v->tiny_E = (e >= (tiny_partial ? 1 : 4) && e <= 32 && (e & (e - 1)) == 0) ? e : e_default;
         auto tiny_bytes = [&]() {  // the records' columns + the prefetched next records, list pointers, list lengths, the tile
-            const size_t bytes = 2 * (size_t)v->L.stride * 32 * 4 + 32 * 8 + 32 * 4 + (size_t)v->tiny_E * stride * 4;
+            const size_t bytes = 2 * (size_t)v->L.stride * 32 * 4 + 32 * 8 + 32 * 4 + (tiny_partial ? 32 * 8 : 0) + (size_t)v->tiny_E * stride * 4;
             return (bytes + 127) / 128 * 128;
         };
         v->tiny_chunk = std::max(1, std::min(64, env_int("LLE_B200_TINY_CHUNK", 1)));
@@ -730,11 +766,15 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
             if (e2 != cudaSuccess) return e2;
             return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb, kern, kThreads, v->tiny_smem);
         };
-        switch (v->A) {
-            case 1: LLE_CUDA(configure(lle_tiny_step_kernel<1>)); break;
-            case 2: LLE_CUDA(configure(lle_tiny_step_kernel<2>)); break;
-            case 3: LLE_CUDA(configure(lle_tiny_step_kernel<3>)); break;
-            default: LLE_CUDA(configure(lle_tiny_step_kernel<4>)); break;
+        switch (v->A * 2 + (tiny_partial ? 1 : 0)) {
+            case 2: LLE_CUDA(configure(lle_tiny_step_kernel<1, false>)); break;
+            case 3: LLE_CUDA(configure(lle_tiny_step_kernel<1, true>)); break;
+            case 4: LLE_CUDA(configure(lle_tiny_step_kernel<2, false>)); break;
+            case 5: LLE_CUDA(configure(lle_tiny_step_kernel<2, true>)); break;
+            case 6: LLE_CUDA(configure(lle_tiny_step_kernel<3, false>)); break;
+            case 7: LLE_CUDA(configure(lle_tiny_step_kernel<3, true>)); break;
+            case 8: LLE_CUDA(configure(lle_tiny_step_kernel<4, false>)); break;
+            default: LLE_CUDA(configure(lle_tiny_step_kernel<4, true>)); break;
         }
         if (tb < 1) v->tiny = false;
         tb = std::min(tb, std::max(1, env_int("LLE_B200_TINY_CTAS_PER_SM", 16)));
@@ -751,6 +791,10 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         const int step_ctas = std::max(1, std::min(blocks_per_sm, env_int("LLE_B200_STEP_CTAS_PER_SM", small_obs ? blocks_per_sm : 2)));
         v->grid_step = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * step_ctas, (n_tickets + kWarps - 1) / kWarps);
         v->grid_step = std::max(v->grid_step, 1);
+    }
+    if (const int cap = env_int("LLE_B200_GRID_CAP", 0); cap > 0) {  // development: CTAs per launch (several vecs sharing one GPU)
+        v->grid = std::min(v->grid, cap);
+        v->grid_step = std::min(v->grid_step, cap);
     }
 
     // ---- device memory
@@ -930,7 +974,7 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
     auto& st = v->src_state[(size_t)map_index];
     if (source_index < 0 || source_index >= (int)st.size()) return fail(LLE_INVALID_ARGUMENT, "laser source index out of range");
     if (v->randomize) return fail(LLE_INVALID_ARGUMENT, "source mutators are not available together with randomize_lasers");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     std::vector<SourceState> next = st;
     if (agent_id >= 0) next[(size_t)source_index].colour = agent_id;
     const bool was_enabled = st[(size_t)source_index].enabled;
@@ -957,7 +1001,7 @@ int lle_vec_set_source(lle_vec* v, int32_t map_index, int32_t source_index, int3
 int lle_vec_collect_gem(lle_vec* v, int32_t map_index, int32_t gem_index, void* stream) {
     if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
     if (gem_index < 0 || gem_index >= v->G) return fail(LLE_INDEX_ERROR, "gem index out of range");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     if (!((v->map_gem_toplevel[(size_t)map_index] >> gem_index) & 1ull))  // pygem.rs:54-62: a gem under a laser tile is a Tile::Laser
         return fail(LLE_INVALID_ARGUMENT, "the tile is not a gem (the gem is wrapped by a laser tile)");
     LLE_CUDA(cudaSetDevice(v->device));
@@ -973,7 +1017,7 @@ int lle_vec_set_exits(lle_vec* v, int32_t map_index, const int32_t* exits_ij, in
     if (!v || map_index < 0 || map_index >= (int)v->src_state.size()) return fail(LLE_INVALID_ARGUMENT, "map index out of range");
     if (n_exits < 0 || (n_exits > 0 && !exits_ij)) return fail(LLE_INVALID_ARGUMENT, "bad exit list");
     if (v->randomize) return fail(LLE_INVALID_ARGUMENT, "the exit setter is not available together with randomize_lasers");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     if (v->shadow)
         if (int rc2 = lle_vec_set_exits(v->shadow, map_index, exits_ij, n_exits, stream)) return rc2;
     std::vector<Cell> exits;
@@ -994,7 +1038,7 @@ int lle_vec_set_exits(lle_vec* v, int32_t map_index, const int32_t* exits_ij, in
 
 int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     LLE_CUDA(cudaSetDevice(v->device));
     v->reset_epoch++;
     KParams p = base_params(v);
@@ -1008,7 +1052,7 @@ int lle_vec_reset(lle_vec* v, const uint8_t* mask_dev, void* stream) {
 
 int lle_vec_refresh(lle_vec* v, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_RESET;
@@ -1021,7 +1065,7 @@ int lle_vec_refresh(lle_vec* v, void* stream) {
 
 int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_STEP;
@@ -1035,7 +1079,7 @@ int lle_vec_step(lle_vec* v, const int8_t* actions_dev, void* stream) {
 
 int lle_vec_rollout(lle_vec* v, int32_t n_steps, void* stream) {
     if (!v || n_steps < 1) return fail(LLE_INVALID_ARGUMENT, "bad argument");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     LLE_CUDA(cudaSetDevice(v->device));
     // (step, ticket) pairs are counted in 32 bits on the device: long rollouts over many tickets go out as several launches
     // (bit-identical: the epoch flags order them exactly like the steps of one launch)
@@ -1077,7 +1121,7 @@ int pipeline_setup(lle_vec* v) {
 int lle_vec_step_host(lle_vec* v, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* stream) {
     if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
     LLE_CUDA(cudaSetDevice(v->device));
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     // pinned buffers: one submit + wait of the pipeline below (one copy, one launch, results written straight to host memory)
     if ((!actions_host || device_view(v, actions_host)) && (!reward_host || device_view(v, reward_host)) && (!done_host || device_view(v, done_host))) {
         int rc = lle_vec_pipeline_submit(v, actions_host, reward_host, done_host, stream);
@@ -1221,9 +1265,164 @@ int lle_vec_pipeline_wait(lle_vec* v, int32_t* outstanding) {
     return LLE_OK;
 }
 
+// ---- closed loop over parts of one batch (include/lle_b200.h)
+int lle_vec_parts_begin(lle_vec* v, int32_t n_parts, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream) {
+    if (!v || !actions_host) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
+    if (v->shadow) return fail(LLE_INVALID_ARGUMENT, "lle_vec_parts_*: not with a state_type observation (its second pass is ordered by whole launches)");
+    const int64_t tickets = v->N_pad / v->group;
+    if (n_parts < 1 || n_parts > 1024 || n_parts > tickets) return fail(LLE_INVALID_ARGUMENT, "n_parts must be in 1..min(1024, tickets of the batch)");
+    LLE_CUDA(cudaSetDevice(v->device));
+    if (int rc = pipeline_setup(v)) return rc;
+    void* a = device_view(v, actions_host);
+    void* r = reward_host ? device_view(v, reward_host) : nullptr;
+    void* d = done_host ? device_view(v, done_host) : nullptr;
+    if (!a || (reward_host && !r) || (done_host && !d))
+        return fail(LLE_INVALID_ARGUMENT, "lle_vec_parts_begin needs pinned (page-locked) host buffers (lle_host_alloc / cudaHostAlloc / cudaHostRegister)");
+    if (n_parts > v->parts_cap) {
+        if (v->h_part_out) cudaFreeHost(v->h_part_out);
+        if (v->d_part_in) cudaFree(v->d_part_in);
+        if (v->d_part_count) cudaFree(v->d_part_count);
+        v->h_part_out = v->d_part_in = v->d_part_count = nullptr;
+        v->parts_cap = 0;
+        LLE_CUDA(cudaMalloc((void**)&v->d_part_in, (size_t)n_parts * 32 * sizeof(uint32_t)));
+        LLE_CUDA(cudaMalloc((void**)&v->d_part_count, (size_t)n_parts * sizeof(uint32_t)));
+        LLE_CUDA(cudaHostAlloc((void**)&v->h_part_out, (size_t)n_parts * 32 * sizeof(uint32_t), cudaHostAllocMapped));
+        LLE_CUDA(cudaHostGetDevicePointer((void**)&v->d_part_out, v->h_part_out, 0));
+        v->parts_cap = n_parts;
+    }
+    if (after_stream != LLE_STREAM_NONE) {  // order the loop after the caller's stream
+        LLE_CUDA(cudaEventRecord(v->ev_user, (cudaStream_t)after_stream));
+        LLE_CUDA(cudaStreamWaitEvent(v->s_main, v->ev_user, 0));
+    }
+    LLE_CUDA(cudaMemsetAsync(v->d_part_in, 0, (size_t)n_parts * 32 * sizeof(uint32_t), v->s_main));
+    LLE_CUDA(cudaMemsetAsync(v->d_part_count, 0, (size_t)n_parts * sizeof(uint32_t), v->s_main));
+    LLE_CUDA(cudaStreamSynchronize(v->s_main));
+    std::memset(v->h_part_out, 0, (size_t)n_parts * 32 * sizeof(uint32_t));
+    __sync_synchronize();
+    v->parts_tpp = (uint32_t)((tickets + n_parts - 1) / n_parts);
+    v->parts_n = (int)((tickets + v->parts_tpp - 1) / v->parts_tpp);  // the last part may be shorter; never an empty one
+    v->parts_launched = 0;
+    v->parts_fed.assign((size_t)v->parts_n, 0);
+    v->parts_read.assign((size_t)v->parts_n, 0);
+    v->parts_actions_dev = (const int8_t*)a;
+    v->parts_reward = (float*)r;
+    v->parts_done = (uint8_t*)d;
+    return LLE_OK;
+}
+
+int lle_vec_parts_count(lle_vec* v, int32_t* n_parts) {
+    if (!v || !n_parts) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    *n_parts = v->parts_n;
+    return LLE_OK;
+}
+
+int lle_vec_parts_range(lle_vec* v, int32_t part, int64_t* first_env, int64_t* n_envs) {
+    if (!v || !first_env || !n_envs) return fail(LLE_INVALID_ARGUMENT, "null argument");
+    if (!v->parts_n || part < 0 || part >= v->parts_n) return fail(LLE_INDEX_ERROR, "no such part (or no parts loop open)");
+    const int64_t lo = (int64_t)part * v->parts_tpp * v->group;
+    const int64_t hi = std::min<int64_t>(v->N, lo + (int64_t)v->parts_tpp * v->group);
+    *first_env = lo;
+    *n_envs = hi - lo;
+    return LLE_OK;
+}
+
+int lle_vec_parts_launch(lle_vec* v) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (!v->parts_n) return fail(LLE_INVALID_ARGUMENT, "no parts loop open: call lle_vec_parts_begin first");
+    uint64_t oldest = v->parts_launched;
+    for (uint64_t r : v->parts_read) oldest = std::min(oldest, r);
+    if (v->parts_launched - oldest >= 4) return fail(LLE_INVALID_ARGUMENT, "four steps in flight: wait for the parts of the oldest one before launching another");
+    LLE_CUDA(cudaSetDevice(v->device));
+    KParams p = base_params(v);
+    p.mode = MODE_STEP;
+    p.actions_in = v->parts_actions_dev;
+    p.reward2 = v->parts_reward;
+    p.done2 = v->parts_done;
+    p.part_in = v->d_part_in;
+    p.part_out = v->d_part_out;
+    p.part_count = v->d_part_count;
+    p.part_tickets = v->parts_tpp;
+    p.in_need = p.out_value = (uint32_t)(v->parts_launched + 1);
+    LLE_CUDA(launch(v, p, v->s_main));
+    v->launches++;
+    v->t++;
+    v->parts_launched++;
+    return LLE_OK;
+}
+
+int lle_vec_parts_feed(lle_vec* v, int32_t part) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (!v->parts_n || part < 0 || part >= v->parts_n) return fail(LLE_INDEX_ERROR, "no such part (or no parts loop open)");
+    if (v->parts_fed[(size_t)part] != v->parts_read[(size_t)part])
+        return fail(LLE_INVALID_ARGUMENT, "the part's previous step has not been waited for: its actions may still be read");
+    // The step kernel reads the part's actions in place (pinned host memory, L1 bypassed): the host's stores are complete before
+    // the stream memory operation that releases them.  (A staging copy per part on the copy stream was measured too: one more
+    // driver call per part and 91-99 us per step instead of 84-88.)
+    __sync_synchronize();
+    const uint32_t n = (uint32_t)(v->parts_fed[(size_t)part] + 1);
+    if (g_write_value32((CUstream)v->s_in, (CUdeviceptr)(uintptr_t)(v->d_part_in + (size_t)part * 32), n, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+        return fail(LLE_CUDA_ERROR, "cuStreamWriteValue32 failed");
+    v->parts_fed[(size_t)part]++;
+    return LLE_OK;
+}
+
+int lle_vec_parts_wait(lle_vec* v, int32_t part) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (!v->parts_n || part < 0 || part >= v->parts_n) return fail(LLE_INDEX_ERROR, "no such part (or no parts loop open)");
+    const uint64_t need = v->parts_read[(size_t)part] + 1;
+    if (v->parts_fed[(size_t)part] < need) return fail(LLE_INVALID_ARGUMENT, "nothing to wait for: feed the part first");
+    if (v->parts_launched < need) return fail(LLE_INVALID_ARGUMENT, "nothing to wait for: the step has not been launched (lle_vec_parts_launch)");
+    volatile uint32_t* flag = v->h_part_out + (size_t)part * 32;
+    const uint32_t n = (uint32_t)need;
+    for (uint64_t spins = 0; (int32_t)(*flag - n) < 0; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xFFFFF) == 0xFFFFF) {
+            cudaSetDevice(v->device);
+            cudaError_t e = cudaStreamQuery(v->s_main);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(LLE_CUDA_ERROR, std::string("step kernel failed: ") + cudaGetErrorString(e));
+            if (e == cudaSuccess && (int32_t)(*flag - n) < 0) return fail(LLE_CUDA_ERROR, "the step retired without publishing the part");
+        }
+    }
+    __sync_synchronize();
+    v->parts_read[(size_t)part]++;
+    return LLE_OK;
+}
+
+// Releases whatever a launched step is still waiting for (the actions it then reads are whatever the buffer holds), drains the
+// streams and closes the loop: for error paths and lle_vec_destroy, so that no kernel is left spinning on the device.
+int lle_vec_parts_abort(lle_vec* v) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (!v->parts_n) return LLE_OK;
+    LLE_CUDA(cudaSetDevice(v->device));
+    for (int k = 0; k < v->parts_n; ++k)
+        if (v->parts_fed[(size_t)k] < v->parts_launched &&
+            g_write_value32((CUstream)v->s_in, (CUdeviceptr)(uintptr_t)(v->d_part_in + (size_t)k * 32), (uint32_t)v->parts_launched, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+            return fail(LLE_CUDA_ERROR, "cuStreamWriteValue32 failed");
+    LLE_CUDA(cudaStreamSynchronize(v->s_in));
+    LLE_CUDA(cudaStreamSynchronize(v->s_main));
+    v->parts_n = 0;
+    return LLE_OK;
+}
+
+int lle_vec_parts_end(lle_vec* v) {
+    if (!v) return fail(LLE_INVALID_ARGUMENT, "null vec");
+    if (!v->parts_n) return LLE_OK;
+    for (int k = 0; k < v->parts_n; ++k)
+        if (v->parts_fed[(size_t)k] != v->parts_launched || v->parts_read[(size_t)k] != v->parts_launched)
+            return fail(LLE_INVALID_ARGUMENT, "every launched step must be fed and waited for on every part before the loop ends (a launched step waits for its actions on the device)");
+    LLE_CUDA(cudaSetDevice(v->device));
+    LLE_CUDA(cudaStreamSynchronize(v->s_in));
+    LLE_CUDA(cudaStreamSynchronize(v->s_main));
+    v->parts_n = 0;
+    return LLE_OK;
+}
+
 int lle_vec_set_state(lle_vec* v, const int32_t* pos_dev, const uint8_t* gems_dev, const uint8_t* alive_dev, void* stream) {
     if (!v || !pos_dev || !alive_dev || (v->G > 0 && !gems_dev)) return fail(LLE_INVALID_ARGUMENT, "null argument");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     LLE_CUDA(cudaSetDevice(v->device));
     KParams p = base_params(v);
     p.mode = MODE_SET_STATE;
@@ -1251,7 +1450,7 @@ int lle_vec_export_raw_state(lle_vec* v, const lle_raw_state* dst, void* stream)
 
 int lle_vec_import_raw_state(lle_vec* v, const lle_raw_state* src, void* stream) {
     if (!v || !src) return fail(LLE_INVALID_ARGUMENT, "null argument");
-    if (v->pipe_submitted != v->pipe_completed) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait first");
+    if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     if (!src->pos || !src->alive || !src->arrived || !src->slot || !src->counters || !src->avail_cache || (v->G && !src->collected) ||
         (v->NBmax && !src->beam_on) || (v->JE && !src->subgoals_extras) || (v->opts.pbrs && !src->subgoals_pbrs))
         return fail(LLE_INVALID_ARGUMENT, "lle_vec_import_raw_state needs every array of the engine record this vec keeps");

@@ -133,6 +133,14 @@ struct KParams {
     // duplicated into a ring slot that a third stream copies to the host once *out_flag >= out_value.
     const uint32_t* in_flag;
     uint32_t in_need, out_value;
+    // Closed loop over parts of the batch (lle_vec_parts_*): the tickets of part k (part_tickets consecutive tickets) start once
+    // part_in[32 k] >= in_need (a stream memory op of the host behind the copy of the part's actions into the staging buffer
+    // actions_in points at), and the warp that completes the part's last ticket writes out_value to part_out[32 k]
+    // (host-mapped) behind a system-scope fence: the reward / done of the part are in host memory (reward2 / done2).
+    const uint32_t* part_in;
+    uint32_t* part_out;
+    uint32_t* part_count;  // device counters: tickets of the part completed in this step
+    uint32_t part_tickets, pad_part;
     uint32_t* out_flag;
     float* reward2;
     uint8_t* done2;
@@ -660,6 +668,42 @@ __device__ __forceinline__ bool ticket_ready(const uint32_t* flag, uint32_t need
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     return (int32_t)(v - need) >= 0;
 }
+// lle_vec_parts_*: count a completed ticket of its part; the last one publishes the part to the host.  A warp's stores to host
+// memory (reward2 / done2) are ordered before its count by a gpu-scope release (they have left the SM; posted PCIe writes keep
+// their order), the last warp acquires the counts, fences at system scope and writes the part's completion word.  The counter
+// is cleared for the next step, whose tickets of this part cannot complete before the host has seen this word and fed the part
+// again.  Out of line: only the parts loop gets here.
+__device__ __noinline__ void part_ticket_done(uint32_t* part_count, uint32_t* part_out, uint32_t part_tickets, uint32_t n_tickets, uint32_t ticket,
+                                              uint32_t value) {
+    const uint32_t part = ticket / part_tickets, first = part * part_tickets;
+    const uint32_t n = min(part_tickets, n_tickets - first);
+    uint32_t before;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(before) : "l"(part_count + part) : "memory");
+    if (before == n - 1u) {
+        part_count[part] = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(part_out + part * 32), "r"(value) : "memory");
+    }
+}
+__device__ __forceinline__ void ticket_done(const KParams& p, uint32_t ticket, uint32_t seq) {
+    ticket_release(p.flags + ticket, seq);
+    if (p.part_out) part_ticket_done(p.part_count, p.part_out, p.part_tickets, p.n_tickets, ticket, p.out_value);
+}
+// The tickets of a part wait for the host's actions (lle_vec_parts_feed).  `fed_upto` (lane 0's register): tickets below it are
+// known to be fed - a warp takes tickets in increasing order, so it looks at a part's word once.  Always true outside that mode.
+__device__ __forceinline__ bool part_fed(const KParams& p, uint32_t ticket, uint32_t& fed_upto) {
+    if (!p.part_in || ticket < fed_upto) return true;
+    const uint32_t part = ticket / p.part_tickets;
+    // gpu scope: the word and the staged actions are written into device memory (L2) by the copy / front-end engines; a
+    // system-scope acquire or fence here costs microseconds per use (measured: 97 -> 127 us per step with one fence.sys per part)
+    if (!ticket_ready(p.part_in + part * 32, p.in_need)) return false;
+    fed_upto = (part + 1u) * p.part_tickets;
+    return true;
+}
+// a host-supplied action; in a parts loop the staging buffer is rewritten by the copy engine while kernels run: through L2 only
+__device__ __forceinline__ uint32_t load_action(const KParams& p, int64_t index) {
+    return (uint32_t)(uint8_t)(p.part_in ? __ldcv(p.actions_in + index) : p.actions_in[index]);
+}
 __device__ __forceinline__ bool sched_slot_armed(const uint32_t* gen, uint32_t want) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gen) : "memory");
@@ -840,6 +884,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     // pair is its own index - no round trip to the launch's counter before it can start.  Not when launches overlap: CTAs then
     // trickle in as their predecessors' retire, and a pair pinned to a late CTA would hold up everything behind it.
     bool first_pair = p.sched_check == 0;
+    uint32_t fed_upto = 0;  // lle_vec_parts_*: tickets below this are known to have their actions
     for (;;) {
         uint32_t pair = warp_global;
         if (!first_pair) {
@@ -859,14 +904,16 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         const uint32_t my_seq = p.seq + (uint32_t)step_index;
         if constexpr (MODE == MODE_STEP) {
             bool flushed = false;
-            if (lane == 0 && !ticket_ready(p.flags + ticket, my_seq - 1u)) {
-                // Never block while owing a completion: the warp we are about to wait for may be waiting for ours.
+            if (lane == 0 && (!ticket_ready(p.flags + ticket, my_seq - 1u) || !part_fed(p, ticket, fed_upto))) {
+                // Never block while owing a completion: the warp we are about to wait for may be waiting for ours (and the host
+                // waits for whole parts before it feeds the next actions).
                 if (owed) {
                     bulk_wait_all();
-                    ticket_release(p.flags + owed_ticket, owed_seq);
+                    ticket_done(p, owed_ticket, owed_seq);
                     flushed = true;
                 }
                 while (!ticket_ready(p.flags + ticket, my_seq - 1u)) __nanosleep(64);
+                while (!part_fed(p, ticket, fed_upto)) __nanosleep(200);
             }
             if (__shfl_sync(kFull, (int)flushed, 0)) owed = false;
         }
@@ -942,7 +989,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             if constexpr (MODE == MODE_STEP) {
                 const uint32_t av = w.cached_avail();
                 if (p.actions_in) {
-                    if (real && gl < A) act = (uint32_t)(uint8_t)p.actions_in[env * A + gl];  // padding worlds just STAY
+                    if (real && gl < A) act = load_action(p, env * A + gl);  // padding worlds just STAY
                 } else {
                     uint32_t r[4];
                     philox4x32_10((uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, (uint32_t)(gl >> 2), (uint32_t)(t_now >> 32),
@@ -1113,7 +1160,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         }
         __syncwarp();
         if (!p.write_obs) {
-            if (MODE == MODE_STEP && lane == 0) ticket_release(p.flags + ticket, my_seq);
+            if (MODE == MODE_STEP && lane == 0) ticket_done(p, ticket, my_seq);
             continue;
         }
 
@@ -1234,7 +1281,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     }
                     if (MODE == MODE_STEP && owed && tix == 0) {
                         bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
-                        ticket_release(p.flags + owed_ticket, owed_seq);
+                        ticket_done(p, owed_ticket, owed_seq);
                     }
                 }
             }
@@ -1339,7 +1386,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     bulk_commit();
                     if (MODE == MODE_STEP && owed && tix == 0) {
                         bulk_wait<1>();
-                        ticket_release(p.flags + owed_ticket, owed_seq);
+                        ticket_done(p, owed_ticket, owed_seq);
                     }
                 }
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
@@ -1437,7 +1484,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     }
                     if (MODE == MODE_STEP && owed && chunk == 0 && tix == 0) {
                         bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
-                        ticket_release(p.flags + owed_ticket, owed_seq);
+                        ticket_done(p, owed_ticket, owed_seq);
                     }
                 }
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
@@ -1449,7 +1496,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     }
     if (lane == 0) {
         bulk_wait_all();
-        if (MODE == MODE_STEP && owed) ticket_release(p.flags + owed_ticket, owed_seq);
+        if (MODE == MODE_STEP && owed) ticket_done(p, owed_ticket, owed_seq);
         launch_epilogue(p, MODE == MODE_STEP);
         if (p.timeline) {
             p.timeline[warp_global * 4 + 1] = t_first;

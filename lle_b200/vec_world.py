@@ -360,6 +360,14 @@ class VecWorld:
         check(lib().lle_vec_pipeline_wait(self._h, C.byref(left)))
         return left.value
 
+    def parts_loop(self, n_parts: int, actions: torch.Tensor, reward_out: torch.Tensor | None, done_out: torch.Tensor | None,
+                   after_current_stream: bool = True) -> "PartsLoop":
+        """Open a closed loop over `n_parts` parts of this batch (lle_vec_parts_*, include/lle_b200.h): every step is one launch
+        over the whole batch, and the step kernel waits part by part for the actions the host releases.  `actions` (int8 [N, A]),
+        `reward_out` (float32 [N, reward_dim]) and `done_out` (uint8 [N]) are pinned host tensors the kernel reads / writes in
+        place.  Use as a context manager."""
+        return PartsLoop(self, n_parts, actions, reward_out, done_out, after_current_stream)
+
     def set_state(self, positions: torch.Tensor, gems_collected: torch.Tensor, agents_alive: torch.Tensor):
         pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
         gems = gems_collected.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -441,3 +449,79 @@ class VecWorld:
 
     def synchronize(self):
         torch.cuda.current_stream(self.device).synchronize()
+
+
+class PartsLoop:
+    """A closed host loop over parts of one VecWorld (lle_vec_parts_begin ... lle_vec_parts_end).
+
+        with vec.parts_loop(8, actions, reward, done) as loop:
+            loop.launch()                         # step 0 (waits on the device for its actions)
+            for k in range(loop.n_parts):
+                actions[loop.slice(k)] = ...      # the first actions
+                loop.feed(k)
+            loop.launch()                         # keep two steps in flight
+            for step in range(steps):
+                for k in range(loop.n_parts):
+                    loop.wait(k)                  # reward / done of part k, step `step`, are in the host tensors
+                    if step + 1 < steps:
+                        actions[loop.slice(k)] = policy(reward[loop.slice(k)], done[loop.slice(k)])
+                        loop.feed(k)
+                if step + 2 < steps:
+                    loop.launch()
+    """
+
+    def __init__(self, vec: VecWorld, n_parts: int, actions: torch.Tensor, reward_out, done_out, after_current_stream: bool = True):
+        for t, dt, shape in ((actions, torch.int8, (vec.n_envs, vec.n_agents)), (reward_out, torch.float32, (vec.n_envs, vec.reward_dim)),
+                             (done_out, torch.uint8, (vec.n_envs,))):
+            if t is None:
+                continue
+            if t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous() or t.is_cuda or not t.is_pinned():
+                raise ValueError(f"parts_loop needs pinned, contiguous host tensors; expected {dt} {shape}")
+        if actions is None:
+            raise ValueError("parts_loop needs an actions tensor")
+        self.vec, self._keep = vec, (actions, reward_out, done_out)
+        check(lib().lle_vec_parts_begin(vec._h, int(n_parts), actions.data_ptr(), reward_out.data_ptr() if reward_out is not None else None,
+                                        done_out.data_ptr() if done_out is not None else None,
+                                        _stream_ptr(vec.device) if after_current_stream else C.c_void_p(-1)))
+        n = C.c_int32(0)
+        check(lib().lle_vec_parts_count(vec._h, C.byref(n)))
+        self.n_parts = n.value
+        self.ranges = []
+        for k in range(self.n_parts):
+            first, count = C.c_int64(0), C.c_int64(0)
+            check(lib().lle_vec_parts_range(vec._h, k, C.byref(first), C.byref(count)))
+            self.ranges.append((first.value, count.value))
+        self._open = True
+
+    def slice(self, part: int) -> slice:
+        first, count = self.ranges[part]
+        return slice(first, first + count)
+
+    def launch(self):
+        check(lib().lle_vec_parts_launch(self.vec._h))
+
+    def feed(self, part: int):
+        check(lib().lle_vec_parts_feed(self.vec._h, int(part)))
+
+    def wait(self, part: int):
+        check(lib().lle_vec_parts_wait(self.vec._h, int(part)))
+
+    def close(self):
+        if self._open:
+            self._open = False
+            check(lib().lle_vec_parts_end(self.vec._h))
+
+    def abort(self):
+        if self._open:
+            self._open = False
+            check(lib().lle_vec_parts_abort(self.vec._h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.close()
+        else:
+            self.abort()  # never leave a kernel waiting for actions
+        return False

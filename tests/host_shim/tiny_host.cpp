@@ -33,6 +33,7 @@ struct Shim {
     std::vector<int> map_of_env;
     int64_t N = 0, N_pad = 0;
     int A = 0, G = 0, H = 0, W = 0, S = 0, R = 1, E = 8;
+    int obs_kind = LLE_OBS_LAYERED, obs_param = 0;
     LleStateLayout L;
     int64_t ostr = 0;
     int walkable = 1, auto_reset = 1, lle_semantics = 1;
@@ -148,7 +149,8 @@ void step_all(Shim& s, const int8_t* actions_in) {
                 const int sidx = lane - r * E;
                 float* sub = wp.tile.data() + (size_t)sidx * s.ostr;
                 for (int64_t f = 0; f < s.ostr; ++f) sub[f] = 0.0f;
-                w.render(sub, s.H * s.W);
+                if (s.obs_kind == LLE_OBS_PARTIAL) w.render_partial(sub, s.obs_param, s.H);
+                else w.render(sub, s.H * s.W);
             }
             for (int sidx = 0; sidx < E; ++sidx) {
                 const int64_t env = ticket * 32 + (int64_t)r * E + sidx;
@@ -164,7 +166,8 @@ void step_all(Shim& s, const int8_t* actions_in) {
 extern "C" {
 
 void* tiny_host_create(const char** texts, int n_maps, const int* map_of_env, long n_envs, int reward_dim, int walkable, int auto_reset,
-                       int lle_semantics, uint64_t seed, uint64_t env_id_base, int E, int n_warps, char* err, int errlen) {
+                       int lle_semantics, uint64_t seed, uint64_t env_id_base, int E, int n_warps, int obs_kind, int obs_param, char* err,
+                       int errlen) {
     auto s = std::make_unique<Shim>();
     auto fail = [&](const std::string& why) -> void* {
         if (err && errlen > 0) {
@@ -174,7 +177,11 @@ void* tiny_host_create(const char** texts, int n_maps, const int* map_of_env, lo
         return nullptr;
     };
     try {
-        for (int k = 0; k < n_maps; ++k) s->maps.push_back(lle::compile_map(texts[k]));
+        lle::ObsSpec spec;
+        spec.kind = obs_kind;
+        spec.param = obs_param;
+        if (obs_kind != LLE_OBS_LAYERED && obs_kind != LLE_OBS_PARTIAL) return fail("the tiny path renders layered and partial observations");
+        for (int k = 0; k < n_maps; ++k) s->maps.push_back(lle::compile_map(texts[k], spec));
     } catch (const std::exception& e) {
         return fail(e.what());
     }
@@ -189,8 +196,10 @@ void* tiny_host_create(const char** texts, int n_maps, const int* map_of_env, lo
     }
     s->L = lle_state_layout(s->A, s->G, nb, max_len);
     if (s->A > 4 || s->L.n_words > 8 || s->L.on_words != 1 || s->L.gem_words > 1) return fail("not a tiny record");
-    if (E != 4 && E != 8 && E != 16 && E != 32) return fail("E must be 4, 8, 16 or 32");
+    if (E < 1 || E > 32 || (E & (E - 1))) return fail("E must be a power of two <= 32");
     s->E = E;
+    s->obs_kind = obs_kind;
+    s->obs_param = obs_param;
     s->N = n_envs;
     s->N_pad = (n_envs + 31) / 32 * 32;
     s->ostr = ((int64_t)m0.header().obs_floats + 3) / 4 * 4;

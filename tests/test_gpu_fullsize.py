@@ -86,6 +86,35 @@ def test_config2_full_size_2000_steps():
     run_windows(wl, windows, 2048, 64)
 
 
+@pytest.mark.parametrize("obs_type", ["partial3x3", "partial5x5"])
+def test_config2_full_size_partial_observations(obs_type):
+    """Level 6 x 65,536 with PartialGenerator observations (thread-per-world kernel): windows replayed by the oracle."""
+    import lle_b200
+    from lle_b200.workloads import level_text
+
+    n = 65536
+    vec = lle_b200.VecWorld(level_text(6), n, seed=SEED, obs_type=obs_type)
+    _BASES[id(vec)] = 0
+    rng = np.random.default_rng(11)
+    windows = []
+    for s0 in spread(n, 48, 6, rng):
+        w = Window.__new__(Window)
+        w.part, w.s0, w.w = vec, s0, 48
+        w.ora = lo.OracleVec([level_text(6)], None, 48, seed=SEED, env_id_base=s0, auto_reset=True, obs_type=obs_type)
+        windows.append(w)
+    for w in windows:
+        w.check("after reset")
+    for t in range(300):
+        vec.step(None)
+        for w in windows:
+            w.step()
+        if t % 60 == 59:
+            vec.synchronize()
+            for w in windows:
+                w.check(f"step {t}")
+    assert int(vec.err.sum()) == 0
+
+
 def test_config1_full_size():
     wl = build(1)
     part = wl.parts[0]

@@ -131,6 +131,28 @@ def test_observation_types(obs_type):
     run_pair(["S0 . G\nS1 X X"], None, 70, 40, obs_type=obs_type, seed=58)  # tiny map: windows mostly off the map
 
 
+@pytest.mark.parametrize("obs_type", ["partial3x3", "partial5x5", "partial7x7"])
+def test_partial_observations_on_the_general_kernel(obs_type, monkeypatch):
+    """Worlds with a small record take the thread-per-world kernel for partial observations too (tiny_kernel.cuh PARTIAL, covered by
+    test_observation_types); the warp-per-group renderer of world_kernel.cuh stays in use for everything else: same cases on it."""
+    monkeypatch.setenv("LLE_B200_NO_TINY", "1")
+    for level in (3, 6):
+        run_pair([level_text(level)], None, 200, 100, obs_type=obs_type, seed=150 + level)
+    maps = [level_text(2), level_text(3), level_text(4)]
+    moe = [(e * 7 + e // 5) % 3 for e in range(333)]
+    run_pair(maps, moe, 333, 80, obs_type=obs_type, auto_reset=False, seed=157)
+
+
+@pytest.mark.parametrize("obs_type", ["partial5x5", "partial7x7"])
+def test_large_windows_forced_onto_the_thread_per_world_kernel(obs_type, monkeypatch):
+    """By default only windows under 2 KB per world (3x3 on level 6) take tiny_kernel.cuh's PARTIAL instantiation; the kernel itself
+    handles any odd size (several rounds per ticket, one world per tile for 7x7)."""
+    monkeypatch.setenv("LLE_B200_TINY_PARTIAL", "1")
+    for level in (3, 6):
+        run_pair([level_text(level)], None, 200, 100, obs_type=obs_type, seed=160 + level)
+    run_pair(["S0 . G\nS1 X X"], None, 70, 40, obs_type=obs_type, seed=168)
+
+
 def test_observation_types_large_and_many_agents():
     from _util import synthetic_map
 
@@ -406,6 +428,121 @@ def test_pipelined_host_stepping():
         vec.submit_host(None, slots[0][1], slots[0][2])
         vec.step(None)  # not drained
     vec.wait_host()
+
+
+def _parts_rollout(ora, dev, n_parts, steps, ahead=2):
+    """Drive `steps` steps through lle_vec_parts_*: the oracle samples, the device replays its actions part by part; the host
+    results of every part and step are compared as they arrive."""
+    vec = dev.vec
+    n = vec.n_envs
+    act = torch.empty((n, ora.A), dtype=torch.int8).pin_memory()
+    rew = torch.empty((n, ora.R), dtype=torch.float32).pin_memory()
+    done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    recorded = []
+    for t in range(steps):
+        ora.step(None)
+        recorded.append((np.array(ora.actions), np.array(ora.reward), np.array(ora.done)))
+    with vec.parts_loop(n_parts, act, rew, done) as loop:
+        assert 1 <= loop.n_parts <= n_parts and sum(c for _, c in loop.ranges) == n and loop.ranges[0][0] == 0
+        for k in range(1, loop.n_parts):
+            assert loop.ranges[k][0] == loop.ranges[k - 1][0] + loop.ranges[k - 1][1]
+        loop.launch()
+        for k in range(loop.n_parts):
+            act[loop.slice(k)] = torch.from_numpy(recorded[0][0][loop.slice(k)])
+            loop.feed(k)
+        for _ in range(1, min(ahead, steps)):
+            loop.launch()
+        for t in range(steps):
+            for k in range(loop.n_parts):
+                sl = loop.slice(k)
+                loop.wait(k)
+                assert np.array_equal(rew.numpy()[sl], recorded[t][1][sl]), f"reward of part {k}, step {t}"
+                assert np.array_equal(done.numpy()[sl], recorded[t][2][sl]), f"done of part {k}, step {t}"
+                if t + 1 < steps:
+                    act[sl] = torch.from_numpy(recorded[t + 1][0][sl])
+                    loop.feed(k)
+            if t + ahead < steps:
+                loop.launch()
+    vec.step_count = ora.t
+    return act, rew, done
+
+
+@pytest.mark.parametrize("n_parts,n,level,ahead", [(1, 100, 5, 1), (3, 1000, 6, 2), (8, 4096, 6, 2), (5, 333, 3, 3), (16, 2100, 6, 4)])
+def test_parts_loop_equals_the_oracle(n_parts, n, level, ahead):
+    """lle_vec_parts_*: one launch per step of the whole batch, the host feeding actions and reading reward / done part by part;
+    every part's host results at every step and the final device buffers equal the oracle's."""
+    ora, dev = make_pair([level_text(level)], None, n, seed=140 + n_parts)
+    _parts_rollout(ora, dev, n_parts, 50, ahead)
+    assert_same(dev, ora, dev.pull(), f"after a parts loop of {n_parts} parts")
+    ora.step(None)
+    dev.vec.step(None)  # plain stepping works again once the loop is closed
+    assert_same(dev, ora, dev.pull(), "after the loop")
+    _parts_rollout(ora, dev, n_parts, 7, ahead)  # and a second loop on the same vec
+    assert_same(dev, ora, dev.pull(), "after a second loop")
+
+
+def test_parts_loop_other_kernels_and_options():
+    """The general kernel (several maps), a vec whose plain steps run on the thread-per-world kernel, multi-objective rewards,
+    partial observations, no auto-reset."""
+    maps = [level_text(2), level_text(3), level_text(4)]
+    moe = [(e * 7 + e // 5) % 3 for e in range(700)]
+    ora, dev = make_pair(maps, moe, 700, seed=151, reward_dim=4)
+    _parts_rollout(ora, dev, 4, 40)
+    assert_same(dev, ora, dev.pull(), "heterogeneous batch")
+    tiny = ["S0 . G . X\n. @ . . .\nL1E . . . .\n. . . @ .\nS1 . . . X", "S0 S1 . . .\n. . L0S . .\n. . . . G\n@ . . . .\nX . . . X"]
+    ora, dev = make_pair(tiny, [e % 2 for e in range(2000)], 2000, seed=152)
+    dev.vec.step(None); ora.step(None)  # a plain step first (thread-per-world kernel), then the loop (general kernel)
+    _parts_rollout(ora, dev, 6, 40)
+    dev.vec.step(None); ora.step(None)
+    assert_same(dev, ora, dev.pull(), "tiny maps")
+    ora, dev = make_pair([level_text(6)], None, 500, seed=153, obs_type="partial3x3", auto_reset=False)
+    _parts_rollout(ora, dev, 4, 40)
+    assert_same(dev, ora, dev.pull(), "partial observations")
+
+
+def test_parts_loop_errors_and_abort():
+    import lle_b200
+
+    vec = lle_b200.VecWorld(level_text(6), 512, seed=1)
+    n, A = 512, vec.n_agents
+    act = torch.full((n, A), 4, dtype=torch.int8).pin_memory()
+    rew = torch.empty((n, 1), dtype=torch.float32).pin_memory()
+    done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    with pytest.raises(ValueError):
+        vec.parts_loop(4, torch.zeros((n, A), dtype=torch.int8), rew, done)  # not pinned
+    with pytest.raises(ValueError):
+        vec.parts_loop(0, act, rew, done)
+    loop = vec.parts_loop(4, act, rew, done)
+    with pytest.raises(ValueError):
+        loop.wait(0)  # nothing fed
+    with pytest.raises(IndexError):
+        loop.feed(99)
+    loop.feed(0)
+    with pytest.raises(ValueError):
+        loop.feed(0)  # the previous step of the part has not been waited for
+    with pytest.raises(ValueError):
+        loop.wait(0)  # fed, but no step launched
+    with pytest.raises(ValueError):
+        vec.step(None)  # the loop is open
+    loop.launch()
+    loop.wait(0)
+    with pytest.raises(ValueError):
+        loop.close()  # parts 1..3 of the launched step were never fed
+    loop._open = True
+    loop.abort()  # releases them (all STAY here), drains, closes
+    vec.step(None)
+    vec.synchronize()
+    assert int(vec.err.sum()) == 0
+    # a loop left open by an exception is aborted by the context manager; destroying a vec with an open loop does not hang
+    with pytest.raises(RuntimeError):
+        with vec.parts_loop(2, act, rew, done) as loop2:
+            loop2.launch()
+            raise RuntimeError("policy failed")
+    vec.step(None)
+    loop3 = vec.parts_loop(2, act, rew, done)
+    loop3.launch()
+    del loop3
+    del vec
 
 
 def test_many_agents_and_small_maps():

@@ -14,9 +14,12 @@ from _util import GOLDEN, build_tiny_host_shim, level_text
 from oracle import lle_oracle as lo
 
 
+_OBS_KINDS = {"layered": (0, 0), "partial3x3": (1, 3), "partial5x5": (1, 5), "partial7x7": (1, 7)}  # LLE_OBS_* of include/lle_b200.h
+
+
 class TinyHost:
     def __init__(self, maps, map_of_env, n_envs, *, multi_objective=False, walkable_lasers=True, auto_reset=True, lle_semantics=True,
-                 seed=0, env_id_base=0, E=8, n_warps=3):
+                 seed=0, env_id_base=0, E=8, n_warps=3, obs_type="layered"):
         self.lib = C.CDLL(build_tiny_host_shim())
         self.lib.tiny_host_create.restype = C.c_void_p
         self.lib.tiny_host_buffer.restype = C.c_void_p
@@ -25,7 +28,7 @@ class TinyHost:
         err = C.create_string_buffer(256)
         self.h = C.c_void_p(self.lib.tiny_host_create(texts, len(maps), moe, C.c_long(n_envs), 4 if multi_objective else 1, int(walkable_lasers),
                                                       int(auto_reset), int(lle_semantics), C.c_uint64(seed), C.c_uint64(env_id_base), E, n_warps,
-                                                      err, 256))
+                                                      *_OBS_KINDS[obs_type], err, 256))
         if not self.h:
             raise ValueError(err.value.decode())
         d = (C.c_long * 8)()
@@ -38,7 +41,7 @@ class TinyHost:
             return np.ctypeslib.as_array(ptr, shape=(int(np.prod(shape)),)).view(dtype).reshape(shape)
 
         self._obs_rows = view(0, C.c_float, np.float32, (n_envs, ostr))
-        self.obs_shape = (Cc, H, W)
+        self.obs_shape = (Cc, H, W) if obs_type == "layered" else (A, 2 * A + 3, int(obs_type[-1]), int(obs_type[-1]))
         self.state = view(1, C.c_float, np.float32, (n_envs, S))
         self.avail = view(2, C.c_uint8, np.uint8, (n_envs, A, 5))
         self.reward = view(3, C.c_float, np.float32, (n_envs, R))
@@ -49,8 +52,7 @@ class TinyHost:
 
     @property
     def obs(self):
-        c, h, w = self.obs_shape
-        return self._obs_rows[:, : c * h * w].reshape(self.n, c, h, w)
+        return self._obs_rows[:, : int(np.prod(self.obs_shape))].reshape((self.n,) + tuple(self.obs_shape))
 
     def step(self, actions=None):
         ptr = None
@@ -77,8 +79,8 @@ def compare(tiny, ora, ctx, fields=FIELDS):
 def run_pair(maps, map_of_env, n, steps, *, E=8, n_warps=3, **kw):
     okw = dict(multi_objective=kw.get("multi_objective", False), walkable_lasers=kw.get("walkable_lasers", True),
                auto_reset=kw.get("auto_reset", True), seed=kw.get("seed", 0), env_id_base=kw.get("env_id_base", 0))
-    ora = lo.OracleVec(maps, map_of_env, n, **okw)
-    tiny = TinyHost(maps, map_of_env, n, E=E, n_warps=n_warps, **okw)
+    ora = lo.OracleVec(maps, map_of_env, n, obs_type=kw.get("obs_type", "layered"), **okw)
+    tiny = TinyHost(maps, map_of_env, n, E=E, n_warps=n_warps, obs_type=kw.get("obs_type", "layered"), **okw)
     # after reset: state / availability come from the core's own reset; observations appear with the first step
     for t in range(steps):
         ora.step(None)
@@ -142,3 +144,18 @@ def test_supplied_actions_with_invalid_ones():
         tiny.step(acts)
         compare(tiny, ora, f"step {t}")
     assert int(np.asarray(ora.err).sum()) > 0
+
+
+@pytest.mark.parametrize("obs_type,E", [("partial3x3", 4), ("partial5x5", 2), ("partial7x7", 1)])
+def test_partial_observations(obs_type, E, layouts):
+    """PartialGenerator (observations.py:312-369) through the per-world core: windows at the border, sources (-1), lit lasers of
+    every colour, gems, exits and the other agents, on the levels and on the layout corpus."""
+    for level in (1, 3, 6):
+        run_pair([level_text(level)], None, 70, 100, seed=30 + level, E=E, obs_type=obs_type)
+    n = 0
+    for k, (name, text) in enumerate(sorted(layouts.items())):
+        if not eligible(text) or k % 3:
+            continue
+        run_pair([text], None, 40, 60, seed=300 + k, E=E, n_warps=2, obs_type=obs_type)
+        n += 1
+    assert n >= 6
