@@ -335,37 +335,41 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    # closed loop with several sub-batches in flight (the EnvPool pattern): while the host reads one sub-batch's results and chooses
-    # its next actions, the others step.  P vecs over the same global env ids as the P slices of the batch.
+    # Closed loop over parts of the batch (lle_vec_parts_*): every step is ONE launch over the whole batch; the step kernel waits
+    # part by part for the actions the host releases, and publishes each part's reward / done to pinned host memory as the part
+    # completes.  The host reads every done flag of a part's step s before it chooses and releases the part's actions of step
+    # s + 1, while the other parts (and the next launch) keep the device busy.
     P = max(1, args.e2e_parts)
-    part = n_envs // P
-    parts = [lle_b200.VecWorld(lle_b200.Map(level=LEVEL), part, device=dev, seed=SEED, env_id_base=begin + h * part, auto_reset=True)
-             for h in range(P)]
-    rec_act_h = [rec_act[:, h * part:(h + 1) * part].contiguous().pin_memory() for h in range(P)]
-    rec_done_np = [rec_done[:, h * part:(h + 1) * part].contiguous().numpy() for h in range(P)]
-    stay_h = stay[:part].contiguous().pin_memory()
-    rw_h = [torch.empty((part, R), dtype=torch.float32).pin_memory() for _ in range(P)]
-    dn_h = [torch.empty((part,), dtype=torch.uint8).pin_memory() for _ in range(P)]
-    dn_np = [t.numpy() for t in dn_h]  # the policy reads the results through numpy (a memcmp; torch.equal costs 25 us per call)
+    act_p = torch.empty((n_envs, A), dtype=torch.int8).pin_memory()
+    rew_p = torch.empty((n_envs, R), dtype=torch.float32).pin_memory()
+    done_p = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+    act_np, done_np, rec_act_np, rec_done_np = act_p.numpy(), done_p.numpy(), rec_act.numpy(), rec_done.numpy()
     mismatches = [0]
 
     def e2e_closed_loop() -> float:
-        for v in parts:
-            restart(v)
+        restart(vec)
+        torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        for s in range(Ke):
-            for h in range(P):
-                acts = rec_act_h[h][s]
-                if s > 0:
-                    parts[h].wait_host()  # results of step s-1 of this sub-batch are in host memory
-                    if not np.array_equal(dn_np[h], rec_done_np[h][s - 1]):  # the policy reads every result byte
-                        acts = stay_h
+        with vec.parts_loop(P, act_p, rew_p, done_p, after_current_stream=False) as loop:
+            slices = [loop.slice(k) for k in range(loop.n_parts)]
+            loop.launch()
+            for k, sl in enumerate(slices):
+                act_np[sl] = rec_act_np[0][sl]
+                loop.feed(k)
+            if Ke > 1:
+                loop.launch()
+            for s in range(Ke):
+                for k, sl in enumerate(slices):
+                    loop.wait(k)  # reward / done of this part's step s are in host memory
+                    ok = np.array_equal(done_np[sl], rec_done_np[s][sl])  # the policy reads every result byte (a memcmp)
+                    if not ok:
                         mismatches[0] += 1
-                parts[h].submit_host(acts, rw_h[h], dn_h[h], after_current_stream=False)
-        for h in range(P):
-            parts[h].wait_host()
-        torch.cuda.synchronize()
+                    if s + 1 < Ke:
+                        act_np[sl] = rec_act_np[s + 1][sl] if ok else 4  # the recorded action stays valid; otherwise everybody STAYs
+                        loop.feed(k)
+                if s + 2 < Ke:
+                    loop.launch()
         return time.perf_counter() - t0
 
     for s in range(min(3, Ke)):
@@ -376,9 +380,8 @@ def run_ours(args) -> None:
     e2e_pipe_value = world_size * n_envs * Ke / reduce_max(e2e_pipelined())
     assert int(vec.err.sum()) == 0, "replayed actions must be valid"
     mismatches[0] = 0
-    e2e_closed_value = world_size * P * part * Ke / reduce_max(e2e_closed_loop())
-    assert mismatches[0] == 0 and all(int(v.err.sum()) == 0 for v in parts), "the closed loop left the recorded trajectory"
-    del parts
+    e2e_closed_value = world_size * n_envs * Ke / reduce_max(e2e_closed_loop())
+    assert mismatches[0] == 0 and int(vec.err.sum()) == 0, "the closed loop left the recorded trajectory"
 
     # the same closed loop driven by a COMPILED host on the C ABI alone (examples/c_closed_loop.c): what the reference's Rust side
     # would see through FFI.  One process per rank on the rank's own device, all ranks at once.
@@ -387,13 +390,15 @@ def run_ours(args) -> None:
     if os.path.exists(exe) and not args.no_compiled_host:
         barrier()
         try:
-            res = subprocess.run([exe, str(local_rank), str(n_envs), str(Ke), str(P)], capture_output=True, text=True, timeout=300)
+            res = subprocess.run([exe, str(local_rank), str(n_envs), str(Ke), f"s{P}", str(P)], capture_output=True, text=True, timeout=300)
             got = json.loads(res.stdout.strip().splitlines()[-1]) if res.returncode == 0 else None
         except Exception:
             got = None
-        us = reduce_max(got["parts"][str(P)]["us_per_step"] if got else float("inf"))
+        us = reduce_max(got["parts"][f"s{P}"]["us_per_step"] if got else float("inf"))
+        us_sub = reduce_max(got["parts"][str(P)]["us_per_step"] if got else float("inf"))
         if us != float("inf"):
-            compiled = {"value": world_size * n_envs / (us / 1e6), "us_per_step": us, "sub_batches_in_flight": P, "steps": Ke,
+            compiled = {"value": world_size * n_envs / (us / 1e6), "us_per_step": us, "parts": P, "steps": Ke,
+                        "sub_batch_vecs_value": world_size * n_envs / (us_sub / 1e6),
                         "host": "compiled C program on the C ABI alone (examples/c_closed_loop.c), one per rank"}
 
     # end-of-run stats reduction: the only collective on this path (NCCL all-reduce of a few counters)
@@ -456,15 +461,18 @@ def run_ours(args) -> None:
             "ranks": {"ms_per_step_min": min(per_rank), "ms_per_step_max": max(per_rank), "ms_per_step": per_rank},
             "clocks": clocks,
             "e2e": {"value": compiled["value"] if compiled else e2e_closed_value, "unit": UNIT, "h2d_bytes_per_step": n_envs * A,
-                    "d2h_bytes_per_step": n_envs * (4 * R + 1), "steps": Ke, "closed_loop": True, "sub_batches_in_flight": P,
+                    "d2h_bytes_per_step": n_envs * (4 * R + 1), "steps": Ke, "closed_loop": True, "parts": P,
                     "host": compiled["host"] if compiled else "python", "python_host_value": e2e_closed_value,
                     "pipelined_value": e2e_pipe_value, "pipeline_depth": D, "sync_value": e2e_sync_value,
-                    "note": f"value: CLOSED loop through lle_vec_pipeline_submit/_wait from a compiled host (the reference's host side is "
-                            f"Rust; python_host_value is the same loop driven from Python) on {P} sub-batches (vecs over the same global "
-                            "env ids): the host reads every done flag of a sub-batch's step t from pinned memory before it submits that "
-                            "sub-batch's step t+1, while the others step; every step copies its actions H2D (copy engine) and writes reward+done "
-                            "D2H (zero-copy stores of the step kernel) inside the timed region. sync_value: the same dependency with one "
-                            "blocking lle_vec_step_host call per step on the whole batch. "
+                    "sub_batch_vecs_value": compiled["sub_batch_vecs_value"] if compiled else None,
+                    "note": f"value: CLOSED loop through lle_vec_parts_* from a compiled host on the C ABI (the reference's host side is Rust; "
+                            f"python_host_value is the same loop driven from Python): ONE launch per step of the whole batch, {P} parts; the host "
+                            "reads every done flag of a part's step t from pinned memory before it writes and releases that part's actions of "
+                            "step t+1 (the step kernel waits for them part by part on the device), while the other parts and the next launch "
+                            "run; the kernel reads the actions from and writes reward+done to pinned host memory inside the timed region "
+                            "(zero-copy, counted as h2d/d2h bytes). sub_batch_vecs_value: the same dependency with the batch cut into "
+                            f"{P} vecs stepped through lle_vec_pipeline_submit/_wait (round 2's first design). sync_value: one blocking "
+                            "lle_vec_step_host call per step on the whole batch. "
                             f"pipelined_value: OPEN loop, {D} recorded steps in flight (not what an acting agent can do). "
                             "Observations stay in HBM (zero-copy DLPack hand-off to a device policy)"},
             "gpu_launches": launches,

@@ -307,6 +307,8 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
  *                         waits for its actions ON THE DEVICE).  lle_vec_parts_abort releases whatever is still waited for
  *                         (those steps then run on whatever the actions buffer holds), drains and closes: for error paths;
  *                         lle_vec_destroy calls it.
+ * A launched step that is never fed keeps spinning on the device and blocks every device-wide synchronisation of the process:
+ * always end or abort the loop (the Python wrapper does so when the loop object is dropped or an exception leaves its block).
  * Per step and part the host pays one poll and one driver call; the device runs full-width step kernels back to back, the parts
  * of consecutive steps overlapping (B200, level 6 x 65,536, 8 parts, compiled host: 84 us per step against 80 us for device-side
  * stepping and 108 us for eight sub-batch vecs).  Results (every buffer of lle_vec_get_buffers) are bit-identical to lle_vec_step

@@ -199,6 +199,13 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
             }
         }
     }
+    if constexpr (MODE == MODE_STEP) {
+        if (p.part_in) {  // a parts loop: its own instantiations
+            if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE_STEP, 1, true>, p);
+            if (v->by_feature) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE_STEP, 2, true>, p);
+            return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE_STEP, 0, true>, p);
+        }
+    }
     if (v->fast) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 1>, p);
     if (v->by_feature) return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 2>, p);
     return cudaLaunchKernelEx(&cfg, lle_world_kernel<MODE, 0>, p);
@@ -275,9 +282,9 @@ cudaError_t smem_optin(int device, int* out) {
     return cudaSuccess;
 }
 
-template <int MODE, int KIND>
+template <int MODE, int KIND, bool PARTS = false>
 cudaError_t configure_kernel(size_t smem, int* blocks) {
-    auto kern = lle_world_kernel<MODE, KIND>;
+    auto kern = lle_world_kernel<MODE, KIND, PARTS>;
     int dev = 0, optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = smem_optin(dev, &optin);
@@ -726,14 +733,17 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
     int blocks_per_sm = -1;  // the grid is shared by the three modes: size it for the most demanding one
     if (v->fast) {
         LLE_CUDA((configure_kernel<MODE_STEP, 1>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_STEP, 1, true>(v->smem, &blocks_per_sm)));
         LLE_CUDA((configure_kernel<MODE_RESET, 1>(v->smem, &blocks_per_sm)));
         LLE_CUDA((configure_kernel<MODE_SET_STATE, 1>(v->smem, &blocks_per_sm)));
     } else if (v->by_feature) {
         LLE_CUDA((configure_kernel<MODE_STEP, 2>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_STEP, 2, true>(v->smem, &blocks_per_sm)));
         LLE_CUDA((configure_kernel<MODE_RESET, 2>(v->smem, &blocks_per_sm)));
         LLE_CUDA((configure_kernel<MODE_SET_STATE, 2>(v->smem, &blocks_per_sm)));
     } else {
         LLE_CUDA((configure_kernel<MODE_STEP, 0>(v->smem, &blocks_per_sm)));
+        LLE_CUDA((configure_kernel<MODE_STEP, 0, true>(v->smem, &blocks_per_sm)));
         LLE_CUDA((configure_kernel<MODE_RESET, 0>(v->smem, &blocks_per_sm)));
         LLE_CUDA((configure_kernel<MODE_SET_STATE, 0>(v->smem, &blocks_per_sm)));
     }

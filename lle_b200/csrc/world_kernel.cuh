@@ -685,14 +685,16 @@ __device__ __noinline__ void part_ticket_done(uint32_t* part_count, uint32_t* pa
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(part_out + part * 32), "r"(value) : "memory");
     }
 }
+template <bool PARTS>
 __device__ __forceinline__ void ticket_done(const KParams& p, uint32_t ticket, uint32_t seq) {
     ticket_release(p.flags + ticket, seq);
-    if (p.part_out) part_ticket_done(p.part_count, p.part_out, p.part_tickets, p.n_tickets, ticket, p.out_value);
+    if constexpr (PARTS) part_ticket_done(p.part_count, p.part_out, p.part_tickets, p.n_tickets, ticket, p.out_value);
 }
 // The tickets of a part wait for the host's actions (lle_vec_parts_feed).  `fed_upto` (lane 0's register): tickets below it are
 // known to be fed - a warp takes tickets in increasing order, so it looks at a part's word once.  Always true outside that mode.
+template <bool PARTS>
 __device__ __forceinline__ bool part_fed(const KParams& p, uint32_t ticket, uint32_t& fed_upto) {
-    if (!p.part_in || ticket < fed_upto) return true;
+    if (!PARTS || ticket < fed_upto) return true;
     const uint32_t part = ticket / p.part_tickets;
     // gpu scope: the word and the staged actions are written into device memory (L2) by the copy / front-end engines; a
     // system-scope acquire or fence here costs microseconds per use (measured: 97 -> 127 us per step with one fence.sys per part)
@@ -701,8 +703,9 @@ __device__ __forceinline__ bool part_fed(const KParams& p, uint32_t ticket, uint
     return true;
 }
 // a host-supplied action; in a parts loop the staging buffer is rewritten by the copy engine while kernels run: through L2 only
+template <bool PARTS>
 __device__ __forceinline__ uint32_t load_action(const KParams& p, int64_t index) {
-    return (uint32_t)(uint8_t)(p.part_in ? __ldcv(p.actions_in + index) : p.actions_in[index]);
+    return (uint32_t)(uint8_t)(PARTS ? __ldcv(p.actions_in + index) : p.actions_in[index]);
 }
 __device__ __forceinline__ bool sched_slot_armed(const uint32_t* gen, uint32_t want) {
     uint32_t v;
@@ -791,7 +794,9 @@ __device__ __forceinline__ void launch_epilogue(const KParams& p, bool is_step) 
 // patch entries and a record of at most 32 words.  The tile then never changes map or chunk, so the tag / freshness
 // bookkeeping of the general path disappears and the per-tile work is a handful of shared-memory accesses.
 // KIND: 0 general, 1 FAST (above), 2 general with the feature-driven renderer of partial observations (sparse maps).
-template <int MODE, int KIND>
+// PARTS: the step kernel of a parts loop (lle_vec_parts_*): tickets wait for their part's actions and completed parts are
+// published to the host.  A separate instantiation: the plain step kernel carries none of it.
+template <int MODE, int KIND, bool PARTS = false>
 __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const KParams p) {
     constexpr bool FAST = KIND == 1;
     constexpr bool BY_FEATURE = KIND == 2;
@@ -904,16 +909,16 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         const uint32_t my_seq = p.seq + (uint32_t)step_index;
         if constexpr (MODE == MODE_STEP) {
             bool flushed = false;
-            if (lane == 0 && (!ticket_ready(p.flags + ticket, my_seq - 1u) || !part_fed(p, ticket, fed_upto))) {
+            if (lane == 0 && (!ticket_ready(p.flags + ticket, my_seq - 1u) || !part_fed<PARTS>(p, ticket, fed_upto))) {
                 // Never block while owing a completion: the warp we are about to wait for may be waiting for ours (and the host
                 // waits for whole parts before it feeds the next actions).
                 if (owed) {
                     bulk_wait_all();
-                    ticket_done(p, owed_ticket, owed_seq);
+                    ticket_done<PARTS>(p, owed_ticket, owed_seq);
                     flushed = true;
                 }
                 while (!ticket_ready(p.flags + ticket, my_seq - 1u)) __nanosleep(64);
-                while (!part_fed(p, ticket, fed_upto)) __nanosleep(200);
+                while (!part_fed<PARTS>(p, ticket, fed_upto)) __nanosleep(200);
             }
             if (__shfl_sync(kFull, (int)flushed, 0)) owed = false;
         }
@@ -989,7 +994,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
             if constexpr (MODE == MODE_STEP) {
                 const uint32_t av = w.cached_avail();
                 if (p.actions_in) {
-                    if (real && gl < A) act = load_action(p, env * A + gl);  // padding worlds just STAY
+                    if (real && gl < A) act = load_action<PARTS>(p, env * A + gl);  // padding worlds just STAY
                 } else {
                     uint32_t r[4];
                     philox4x32_10((uint32_t)(p.env_id_base + (uint64_t)env), (uint32_t)t_now, (uint32_t)(gl >> 2), (uint32_t)(t_now >> 32),
@@ -1160,7 +1165,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
         }
         __syncwarp();
         if (!p.write_obs) {
-            if (MODE == MODE_STEP && lane == 0) ticket_done(p, ticket, my_seq);
+            if (MODE == MODE_STEP && lane == 0) ticket_done<PARTS>(p, ticket, my_seq);
             continue;
         }
 
@@ -1281,7 +1286,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     }
                     if (MODE == MODE_STEP && owed && tix == 0) {
                         bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
-                        ticket_done(p, owed_ticket, owed_seq);
+                        ticket_done<PARTS>(p, owed_ticket, owed_seq);
                     }
                 }
             }
@@ -1386,7 +1391,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     bulk_commit();
                     if (MODE == MODE_STEP && owed && tix == 0) {
                         bulk_wait<1>();
-                        ticket_done(p, owed_ticket, owed_seq);
+                        ticket_done<PARTS>(p, owed_ticket, owed_seq);
                     }
                 }
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
@@ -1484,7 +1489,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
                     }
                     if (MODE == MODE_STEP && owed && chunk == 0 && tix == 0) {
                         bulk_wait<1>();  // every store but the one just issued has completed: the previous ticket is done
-                        ticket_done(p, owed_ticket, owed_seq);
+                        ticket_done<PARTS>(p, owed_ticket, owed_seq);
                     }
                 }
                 buf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
@@ -1496,7 +1501,7 @@ __global__ void __launch_bounds__(kThreads, LLE_MIN_CTAS) lle_world_kernel(const
     }
     if (lane == 0) {
         bulk_wait_all();
-        if (MODE == MODE_STEP && owed) ticket_done(p, owed_ticket, owed_seq);
+        if (MODE == MODE_STEP && owed) ticket_done<PARTS>(p, owed_ticket, owed_seq);
         launch_epilogue(p, MODE == MODE_STEP);
         if (p.timeline) {
             p.timeline[warp_global * 4 + 1] = t_first;

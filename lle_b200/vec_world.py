@@ -220,11 +220,16 @@ class VecWorld:
         self.extras_dim = int(b.extras_dim)
         self.extras = wrap(b.extras, (N, A, self.extras_dim), "<f4") if self.extras_dim else None
 
-    def __del__(self):
+    def destroy(self):
+        """Release the device memory now (lle_vec_destroy; an open parts loop is aborted first).  The tensors handed out become
+        dangling: only for callers that manage lifetimes explicitly — dropping the last reference does the same."""
         h = getattr(self, "_h", None)
         if h:
-            lib().lle_vec_destroy(h)
             self._h = None
+            lib().lle_vec_destroy(h)
+
+    def __del__(self):
+        self.destroy()
 
     # ---- views
     @property
@@ -479,6 +484,7 @@ class PartsLoop:
                 raise ValueError(f"parts_loop needs pinned, contiguous host tensors; expected {dt} {shape}")
         if actions is None:
             raise ValueError("parts_loop needs an actions tensor")
+        self._open = False
         self.vec, self._keep = vec, (actions, reward_out, done_out)
         check(lib().lle_vec_parts_begin(vec._h, int(n_parts), actions.data_ptr(), reward_out.data_ptr() if reward_out is not None else None,
                                         done_out.data_ptr() if done_out is not None else None,
@@ -515,6 +521,13 @@ class PartsLoop:
         if self._open:
             self._open = False
             check(lib().lle_vec_parts_abort(self.vec._h))
+
+    def __del__(self):  # a dropped loop must not leave a launched step waiting for actions on the device
+        try:
+            if self._open and self.vec._h:
+                self.abort()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self

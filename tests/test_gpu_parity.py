@@ -541,8 +541,15 @@ def test_parts_loop_errors_and_abort():
     vec.step(None)
     loop3 = vec.parts_loop(2, act, rew, done)
     loop3.launch()
-    del loop3
-    del vec
+    del loop3  # a dropped loop aborts itself: no launched step is left waiting for actions (it would block the whole device)
+    vec.step(None)
+    loop4 = vec.parts_loop(2, act, rew, done)
+    loop4.launch()
+    vec.destroy()  # lle_vec_destroy aborts an open loop first
+    loop4._open = False
+    other = lle_b200.VecWorld(level_text(3), 64, seed=2)  # the device is free again
+    other.step(None)
+    other.synchronize()
 
 
 def test_many_agents_and_small_maps():
