@@ -28,6 +28,18 @@ for _ in range(200):
 torch.cuda.synchronize()
 print(f"VecLLE: obs {tuple(obs.shape)} {obs.dtype} on {obs.device}; 200 steps x {n_envs} envs, {episodes} episodes, reward sum {total:.0f}")
 
+# 2b. a policy that runs on the HOST between steps (closed loop): one launch per step, the kernel waits part by part for the actions
+rng_state = {"episodes": 0}
+
+
+def host_policy(part, reward, done):                # numpy views of this part's results in pinned host memory
+    rng_state["episodes"] += int(done.sum())
+    return None                                     # None: everybody STAYs; or an int8 array (len(part), n_agents)
+
+
+env.run_host_policy(host_policy, steps=50, n_parts=8)
+print(f"host policy in the loop: 50 steps, {rng_state['episodes']} episodes seen by the policy")
+
 # 3. lle.generate(...): layouts generated on the device (bit-identical per seed to the reference's Python generator), then stepped
 maps = list(generate(5, 5, 2).lasers(2).walls(2).needs_blocker().take(64, seed=0, distinct=True, texts=True))
 batch = lle.VecWorld(maps, 64 * 16, map_of_env=[m for m in range(64) for _ in range(16)], seed=1)

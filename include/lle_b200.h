@@ -309,6 +309,8 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
  *                         lle_vec_destroy calls it.
  * A launched step that is never fed keeps spinning on the device and blocks every device-wide synchronisation of the process:
  * always end or abort the loop (the Python wrapper does so when the loop object is dropped or an exception leaves its block).
+ * (For the same reason a parts loop cannot run under a profiler that serialises kernel launches, e.g. ncu: the launch call would
+ * only return once the step has its actions, which the same thread releases after the call.)
  * Per step and part the host pays one poll and one driver call; the device runs full-width step kernels back to back, the parts
  * of consecutive steps overlapping (B200, level 6 x 65,536, 8 parts, compiled host: 84 us per step against 80 us for device-side
  * stepping and 108 us for eight sub-batch vecs).  Results (every buffer of lle_vec_get_buffers) are bit-identical to lle_vec_step

@@ -73,6 +73,38 @@ class VecLLE:
     def dlpack(self, name: str):
         return getattr(self, name).__dlpack__()
 
+    def run_host_policy(self, policy, steps: int, n_parts: int = 8, first_actions=None):
+        """Closed loop with a policy that runs ON THE HOST between steps (the reference's `while not done: env.step(policy(obs))`,
+        python/lle/env/env.py:165-189, over N envs): `policy(part_slice, reward, done)` gets numpy views of one part's results in
+        pinned host memory and returns that part's next actions (int8 array (n, A), or None to keep everybody on STAY).  Every
+        step is one launch over the whole batch; the step kernel waits part by part for the actions (lle_vec_parts_*), so the
+        device keeps stepping the other parts while the policy thinks.  Returns (reward, done) of the last step (host tensors).
+        Observations stay on the device (`obs`): a host policy that needs them copies the slices it wants."""
+        w = self.world
+        act = torch.full((w.n_envs, w.n_agents), 4, dtype=torch.int8).pin_memory()
+        rew = torch.zeros((w.n_envs, w.reward_dim), dtype=torch.float32).pin_memory()
+        done = torch.zeros((w.n_envs,), dtype=torch.uint8).pin_memory()
+        act_np, rew_np, done_np = act.numpy(), rew.numpy(), done.numpy()
+        if first_actions is not None:
+            act_np[...] = first_actions
+        with w.parts_loop(n_parts, act, rew, done) as loop:
+            slices = [loop.slice(k) for k in range(loop.n_parts)]
+            loop.launch()
+            for k in range(loop.n_parts):
+                loop.feed(k)
+            if steps > 1:
+                loop.launch()
+            for s in range(steps):
+                for k, sl in enumerate(slices):
+                    loop.wait(k)
+                    if s + 1 < steps:
+                        nxt = policy(sl, rew_np[sl], done_np[sl])
+                        act_np[sl] = 4 if nxt is None else nxt
+                        loop.feed(k)
+                if s + 2 < steps:
+                    loop.launch()
+        return rew, done
+
 
 class VecWorldGroup:
     """Several `VecWorld`s stepped together — for batches whose maps do not share one tensor shape, e.g. the six

@@ -6,6 +6,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 CMD = "python bench.py --steps 64 --warmup 8 --no-cpu-baseline --e2e-steps 8 --no-configs --no-compiled-host"
+if tag == "r02f":  # the final capture of round 2 (profiles/capture_final.sh): the closed loop over parts cannot run under ncu
+    CMD += " --no-closed-loop"
 
 rows = list(csv.reader(open(os.path.join(G, f"launches_{tag}.csv"))))
 hdr, data = None, []

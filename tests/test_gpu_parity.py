@@ -552,6 +552,32 @@ def test_parts_loop_errors_and_abort():
     other.synchronize()
 
 
+def test_veclle_run_host_policy():
+    """VecLLE.run_host_policy: a host policy between steps; here it replays the oracle's sampled actions and checks what it is
+    shown, part by part."""
+    import lle_b200
+
+    n, steps = 1500, 30
+    ora = lo.OracleVec([level_text(6)], None, n, seed=77)
+    rec = []
+    for t in range(steps):
+        ora.step(None)
+        rec.append((np.array(ora.actions), np.array(ora.reward), np.array(ora.done)))
+    env = lle_b200.VecLLE(level_text(6), n, seed=77)
+    seen = {}
+
+    def policy(sl, reward, done):
+        t = seen.get(sl.start, 0)
+        assert np.array_equal(reward, rec[t][1][sl]) and np.array_equal(done, rec[t][2][sl]), f"part at {sl.start}, step {t}"
+        seen[sl.start] = t + 1
+        return rec[t + 1][0][sl]
+
+    rew, done = env.run_host_policy(policy, steps, n_parts=5, first_actions=rec[0][0])
+    assert np.array_equal(rew.numpy(), rec[-1][1]) and np.array_equal(done.numpy(), rec[-1][2])
+    env.world.synchronize()
+    assert np.array_equal(env.obs.cpu().numpy(), np.asarray(ora.obs)) and int(env.err.sum()) == 0
+
+
 def test_many_agents_and_small_maps():
     rows = [" .   .   . . . ."] + [f"S{k}  L{k}W  . . . X" for k in range(14)]
     run_pair(["\n".join(rows)], None, 64, 60, seed=2)

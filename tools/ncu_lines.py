@@ -39,7 +39,9 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(out.splitlines()))
 h = rows[1]
 ie, sm = h.index("Instructions Executed"), h.index("# Samples")
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) == len(h) and r[0].strip().startswith("0x")]
+if len(data) > len(where) and len(where):  # several launches in the report (each with its own header rows): keep the first one
+    data = data[:len(where)]
 assert len(data) == len(where), f"the report has {len(data)} instructions, the current build {len(where)}: rebuild the library the report was taken with"
 inst, samp = collections.Counter(), collections.Counter()
 for r, key in zip(data, where):
