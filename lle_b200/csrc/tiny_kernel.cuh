@@ -30,6 +30,9 @@
 
 namespace lle {
 
+#ifndef LLE_TINY_LIST2
+#define LLE_TINY_LIST2 1
+#endif
 #ifndef LLE_TINY_MIN_CTAS
 #define LLE_TINY_MIN_CTAS 7
 #endif
@@ -293,7 +296,10 @@ __global__ void __launch_bounds__(kThreads, PARTIAL ? 4 : LLE_TINY_MIN_CTAS) lle
             }
             __syncwarp();
             for (int r = 0; r < (32 >> lgE); ++r) {
-                if (lane == 0) bulk_wait_read<0>();  // the store that last read the tile has finished reading it
+                // the store that last read the tile has finished reading it.  (A second tile buffer, so that a round is drawn while the
+                // previous one is read, was measured on config 3: E = 2 / 4 with two buffers 238 / 207 us against 190 - it costs
+                // warps per SM, and even the unused run-time branch for it cost 3 %.)
+                if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
                 for (int f = lane * 4; f < E * ostr; f += 128) *reinterpret_cast<float4*>(tile + f) = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
@@ -326,7 +332,18 @@ __global__ void __launch_bounds__(kThreads, PARTIAL ? 4 : LLE_TINY_MIN_CTAS) lle
                         }
                     };
                     const LlePatch* list = slptr[ws];
+#if LLE_TINY_LIST2
+                    // two entries in flight per lane: the dependent load of an entry was 10.7 % of the stall samples (config 3: 192.9 -> 189.6 us; three in flight: 190.1)
+                    for (int k = q; k < n; k += 2 * lpw) {
+                        const int k2 = k + lpw;
+                        const LlePatch e0 = list[k];
+                        const LlePatch e1 = list[k2 < n ? k2 : k];
+                        draw(e0, k);
+                        if (k2 < n) draw(e1, k2);
+                    }
+#else
                     for (int k = q; k < n; k += lpw) draw(list[k], k);
+#endif
                     for (int a = q; a < A_; a += lpw) {  // the agents' one-hots (:264-265): their planes hold nothing else
                         const uint32_t pp = agent_pos(a);
                         sub[a * p.HW + (int)(pp >> 8) * W + (int)(pp & 0xFFu)] = 1.0f;
