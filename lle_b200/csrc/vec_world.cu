@@ -111,7 +111,7 @@ struct lle_vec {
     bool has_map0 = false;
     bool narrow_next = false;  // the next step launch finds its predecessor still running: use the narrow grid
     int narrow_depth = 1;      // step launches in flight from which the narrow grid is used (LLE_B200_NARROW_DEPTH)
-    int grid = 0, grid_step = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
+    int grid = 0, grid_step = 0, grid_idle = 0, Wd = 32, group = 4, E = 1, n_chunks = 1, chunk_floats = 0, tile_floats = 0, n_buf = 1, warp_smem = 0;
     size_t smem = 0;
     uint64_t t = 0, launches = 0;
     // timing
@@ -165,7 +165,10 @@ cudaError_t launch_mode(lle_vec* v, KParams& p, cudaStream_t s) {
     const bool overlaps = v->pdl && MODE == MODE_STEP && v->last_was_step && v->last_stream == s;
     // (A parts loop takes the full grid too: its launches wait for the host part by part, and a wide grid keeps enough unblocked
     // warps resident.  Level 6 x 65,536, 8 parts, us per step with 2 / 3 / 5 CTAs per SM: 96.9 / 87.8 / 84.5.)
-    const int grid = (overlaps && p.n_steps == 1 && v->narrow_next && !p.part_in) ? v->grid_step : v->grid;
+    // A single step that finds the device idle takes four CTAs per SM of the five, which leaves room for the first CTAs of the
+    // launch that follows it (the driver's 20-step window after a sync, idle launch at 5 / 4 / 3 / 2 CTAs per SM: 79.8 / 78.7 /
+    // 78.8 / 78.9 us per step).
+    const int grid = (MODE == MODE_STEP && p.n_steps == 1 && !p.part_in) ? ((overlaps && v->narrow_next) ? v->grid_step : v->grid_idle) : v->grid;
     v->narrow_next = false;
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
@@ -802,9 +805,14 @@ int lle_vec_create(const lle_map* const* maps, int32_t n_maps, const int32_t* ma
         v->grid_step = (int)std::min<int64_t>((int64_t)prop.multiProcessorCount * step_ctas, (n_tickets + kWarps - 1) / kWarps);
         v->grid_step = std::max(v->grid_step, 1);
     }
+    {
+        const int idle_ctas = std::max(1, std::min(blocks_per_sm, env_int("LLE_B200_IDLE_CTAS_PER_SM", small_obs ? blocks_per_sm : 4)));
+        v->grid_idle = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)prop.multiProcessorCount * idle_ctas, (n_tickets + kWarps - 1) / kWarps));
+    }
     if (const int cap = env_int("LLE_B200_GRID_CAP", 0); cap > 0) {  // development: CTAs per launch (several vecs sharing one GPU)
         v->grid = std::min(v->grid, cap);
         v->grid_step = std::min(v->grid_step, cap);
+        v->grid_idle = std::min(v->grid_idle, cap);
     }
 
     // ---- device memory
