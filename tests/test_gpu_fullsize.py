@@ -115,6 +115,62 @@ def test_config2_full_size_partial_observations(obs_type):
     assert int(vec.err.sum()) == 0
 
 
+def test_config2_full_size_closed_loop_over_parts():
+    """Level 6 x 65,536 through lle_vec_parts_* (the loop bench.py times as e2e): the host feeds recorded actions part by part; the
+    reward / done it receives for six windows of envs are compared with the oracle at every step, every output at the end."""
+    import lle_b200
+    from lle_b200.workloads import level_text
+
+    n, steps, P = 65536, 120, 8
+    text = level_text(6)
+    src = lle_b200.VecWorld(text, n, seed=SEED)
+    rec = torch.empty((steps, n, src.n_agents), dtype=torch.int8).pin_memory()
+    for t in range(steps):
+        src.step(None)
+        rec[t].copy_(src.actions, non_blocking=True)
+    src.synchronize()
+    del src
+    rec_np = rec.numpy()
+    vec = lle_b200.VecWorld(text, n, seed=SEED)
+    _BASES[id(vec)] = 0
+    rng = np.random.default_rng(12)
+    windows = []
+    for s0 in spread(n, 40, 4, rng):
+        w = Window.__new__(Window)
+        w.part, w.s0, w.w = vec, s0, 40
+        w.ora = lo.OracleVec([text], None, 40, seed=SEED, env_id_base=s0, auto_reset=True)
+        windows.append(w)
+    act = torch.empty((n, vec.n_agents), dtype=torch.int8).pin_memory()
+    rew = torch.empty((n, vec.reward_dim), dtype=torch.float32).pin_memory()
+    done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    act_np, rew_np, done_np = act.numpy(), rew.numpy(), done.numpy()
+    with vec.parts_loop(P, act, rew, done) as loop:
+        slices = [loop.slice(k) for k in range(loop.n_parts)]
+        loop.launch()
+        for k, sl in enumerate(slices):
+            act_np[sl] = rec_np[0][sl]
+            loop.feed(k)
+        loop.launch()
+        for t in range(steps):
+            for w in windows:
+                w.ora.step(rec_np[t][w.s0:w.s0 + w.w])
+            for k, sl in enumerate(slices):
+                loop.wait(k)
+                for w in windows:
+                    if sl.start <= w.s0 and w.s0 + w.w <= sl.stop:  # the window lies in this part
+                        assert np.array_equal(rew_np[w.s0:w.s0 + w.w], np.asarray(w.ora.reward)), f"reward, window {w.s0}, step {t}"
+                        assert np.array_equal(done_np[w.s0:w.s0 + w.w], np.asarray(w.ora.done)), f"done, window {w.s0}, step {t}"
+                if t + 1 < steps:
+                    act_np[sl] = rec_np[t + 1][sl]
+                    loop.feed(k)
+            if t + 2 < steps:
+                loop.launch()
+    vec.synchronize()
+    for w in windows:
+        w.check("after the loop")
+    assert int(vec.err.sum()) == 0
+
+
 def test_config1_full_size():
     wl = build(1)
     part = wl.parts[0]
