@@ -1,6 +1,6 @@
 """Soak of the dataflow-ordered stepping: the same batch advanced by (a) single-step launches overlapped with programmatic
 dependent launch, (b) rollout launches of 128 steps, (c) rollout launches of 7 steps interleaved with single steps, for many
-steps; the three must end in bit-identical engine state and outputs.  python scratch/soak.py [steps] [envs]"""
+steps; the three must end in bit-identical engine state and outputs.  python tools/soak.py [steps] [envs]"""
 import os, sys, time, zlib
 import numpy as np
 import torch
