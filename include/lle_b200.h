@@ -277,11 +277,12 @@ LLE_API int lle_host_free(void* ptr);
 
 /* Pipelined host stepping: the same step as lle_vec_step_host without the per-step stream synchronisation.
  * lle_vec_pipeline_submit enqueues (1) the copy of `actions_host` (pinned i8[N,A]; NULL = device sampling) on a copy
- * stream, (2) the fused step on the vec's own compute stream, which waits for the actions inside the kernel, and (3) the
- * copy of reward / done (pinned f32[N,reward_dim] / u8[N]) to the host on a third stream, and returns at once.
- * lle_vec_pipeline_wait blocks until the OLDEST submitted step's results are in its host buffers.  Up to 8 steps may be
- * outstanding; with two or more, the copies of one step overlap the kernels of its neighbours and consecutive step
- * kernels stay back to back (programmatic dependent launch), so a host-driven loop runs at the device rate.
+ * stream and (2) the fused step on the vec's own compute stream, which waits for the actions inside the kernel and writes
+ * reward / done (pinned f32[N,reward_dim] / u8[N]) straight into the host buffers, followed by a completion word in pinned
+ * memory; it returns at once.  lle_vec_pipeline_wait polls that word: it blocks until the OLDEST submitted step's results are
+ * in its host buffers.  Up to 8 steps may be outstanding; with two or more, the copies of one step overlap the kernels of its
+ * neighbours and consecutive step kernels stay back to back (programmatic dependent launch), so an OPEN host-driven loop runs
+ * at the device rate.  A CLOSED loop (the actions of step t+1 depend on the results of step t) uses lle_vec_parts_* below.
  * The first submit after the pipeline was empty is ordered after the work already in `after_stream` (pass LLE_STREAM_NONE when
  * nothing the step depends on is pending on any stream: saves two driver calls per step of a closed loop); no other call
  * on the vec is allowed until the pipeline has been drained.  Device buffers (lle_vec_get_buffers) are updated as usual. */
@@ -309,7 +310,9 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
  *                         lle_vec_destroy calls it.
  * A launched step that is never fed keeps spinning on the device and blocks every device-wide synchronisation of the process:
  * always end or abort the loop (the Python wrapper does so when the loop object is dropped or an exception leaves its block).
- * (For the same reason a parts loop cannot run under a profiler that serialises kernel launches, e.g. ncu: the launch call would
+ * For the same reason keep ONE parts loop per device going at a time from a host thread: the waiting CTAs of one loop's launch can
+ * fill the SMs, and if the host then blocks in lle_vec_parts_wait on another vec whose kernel cannot become resident, neither moves.
+ * (And a parts loop cannot run under a profiler that serialises kernel launches, e.g. ncu: the launch call would
  * only return once the step has its actions, which the same thread releases after the call.)
  * Per step and part the host pays one poll and one driver call; the device runs full-width step kernels back to back, the parts
  * of consecutive steps overlapping (B200, level 6 x 65,536, 8 parts, compiled host: 84 us per step against 80 us for device-side
