@@ -41,9 +41,18 @@ struct ConstTable {
 // states out of L1/L2).  Measured alternatives: the states in lane-interleaved shared memory (92 threads per
 // SM fill the 227 KB) are 3x slower - three warps cannot hide the chain.  Attempts of a warp diverge freely (rejection
 // sampling, retries).
-constexpr int kGenThreads = 128;
+// Threads per block / minimum blocks per SM (registers): swept in round 2 on B200, M attempts/s on 5x5 / 10x10 / 8x8 lanes / 32x32:
+// (128, 8) 402 / 65 / 283 / 3.1;  (128, 6) 317 / 65 / 282 / 3.0;  (128, 10) 385 / 64 / 273 / 3.1;  (128, 12) 373 / 64 / 269 / 3.0;
+// (64, 16) 359 / 52 / 215 / 2.7;  (256, 4) 414 / 61 / 290 / 2.1 - occupancy is not the lever.
+#ifndef LLE_GEN_THREADS
+#define LLE_GEN_THREADS 128
+#endif
+#ifndef LLE_GEN_MIN_BLOCKS
+#define LLE_GEN_MIN_BLOCKS 8
+#endif
+constexpr int kGenThreads = LLE_GEN_THREADS;
 
-__global__ void __launch_bounds__(kGenThreads, 8) lle_gen_kernel(const __grid_constant__ llegen::Config cfg, const uint64_t* __restrict__ seeds,
+__global__ void __launch_bounds__(kGenThreads, LLE_GEN_MIN_BLOCKS) lle_gen_kernel(const __grid_constant__ llegen::Config cfg, const uint64_t* __restrict__ seeds,
                                                                  uint64_t first_seed, int64_t n, int max_attempts, uint8_t require,
                                                                  uint8_t* __restrict__ cells, uint8_t* __restrict__ status,
                                                                  uint8_t* __restrict__ labels, int32_t* __restrict__ tries) {

@@ -39,6 +39,10 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         accepted = float(status.float().mean())
+        if os.environ.get("GEN_BENCH_GPU_ONLY"):
+            print(json.dumps({"case": name, "attempts": n, "ms": round(ms, 3), "attempts_per_s": round(n / ms * 1e3), "accepted": round(accepted, 4)}))
+            del g
+            continue
         cfg = og.GenConfig(**kw)
         m = 20000 if kw["width"] <= 10 else 2000
         t = time.perf_counter()
