@@ -1,6 +1,8 @@
 """Soak of the dataflow-ordered stepping: the same batch advanced by (a) single-step launches overlapped with programmatic
 dependent launch, (b) rollout launches of 128 steps, (c) rollout launches of 7 steps interleaved with single steps, for many
-steps; the three must end in bit-identical engine state and outputs.  python tools/soak.py [steps] [envs]"""
+steps; the three must end in bit-identical engine state and outputs.  Then (d) the closed loop over parts (lle_vec_parts_*): a
+recorded action stream of min(steps, 4000) steps fed part by part against the same stream fed to plain steps.
+python tools/soak.py [steps] [envs]"""
 import os, sys, time, zlib
 import numpy as np
 import torch
@@ -47,3 +49,43 @@ for mode in ("single", "rollout128", "mixed"):
         ref = d
     assert d == ref, f"{mode} differs from single-step execution"
 print("soak ok: identical state and outputs in all three modes")
+
+
+# (d) the parts loop against plain stepping on the same supplied actions
+K = min(steps, 4000)
+src = lle_b200.VecWorld(lle_b200.Map(level=6), envs, seed=12)
+A = src.n_agents
+rec = torch.empty((K, envs, A), dtype=torch.int8).pin_memory()
+for t in range(K):
+    src.step(None)
+    rec[t].copy_(src.actions, non_blocking=True)
+d_plain = digest(src)
+del src
+rec_np = rec.numpy()
+v = lle_b200.VecWorld(lle_b200.Map(level=6), envs, seed=12)
+act = torch.empty((envs, A), dtype=torch.int8).pin_memory()
+rew = torch.empty((envs, 1), dtype=torch.float32).pin_memory()
+done = torch.empty((envs,), dtype=torch.uint8).pin_memory()
+act_np = act.numpy()
+t0 = time.time()
+with v.parts_loop(8, act, rew, done) as loop:
+    sl = [loop.slice(k) for k in range(loop.n_parts)]
+    loop.launch()
+    for k in range(loop.n_parts):
+        act_np[sl[k]] = rec_np[0][sl[k]]
+        loop.feed(k)
+    loop.launch()
+    for t in range(K):
+        for k in range(loop.n_parts):
+            loop.wait(k)
+            if t + 1 < K:
+                act_np[sl[k]] = rec_np[t + 1][sl[k]]
+                loop.feed(k)
+        if t + 2 < K:
+            loop.launch()
+secs = time.time() - t0
+v.step_count = K
+d_parts = digest(v)
+print("parts loop", f"{K} steps x {envs} envs in {secs:.2f} s ({envs * K / secs:.3e} env-steps/s from Python)", d_parts[:4])
+assert d_parts == d_plain, "the parts loop differs from plain stepping on the same actions"
+print("soak ok: the parts loop ends in the same state and outputs")
