@@ -41,16 +41,17 @@ def test_quickstart_example_runs():
 
 @pytest.mark.gpu
 def test_c_closed_loop_runs():
-    """examples/c_closed_loop.c: the compiled-host closed loop bench.py reports as e2e (1, 2 and 4 sub-batches in flight); it
-    checks itself that the host saw exactly the recorded done flags and that no env refused an action."""
+    """examples/c_closed_loop.c: the compiled-host closed loop bench.py reports as e2e - over parts of one batch (lle_vec_parts_*,
+    modes s1 / s3 / s8) and over sub-batch vecs (lle_vec_pipeline_submit/_wait, 1 / 2 / 4 in flight); it checks itself that the host
+    saw exactly the recorded done flags, that no env refused an action and that the device's final done flags match."""
     import json
 
     import __graft_entry__
 
     exe = __graft_entry__.build_c_client("c_closed_loop")
-    res = subprocess.run([exe, "0", "8192", "40", "1", "2", "4"], capture_output=True, text=True, timeout=300)
+    res = subprocess.run([exe, "0", "8192", "40", "s1", "s3", "s8", "1", "2", "4"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     out = json.loads(res.stdout.strip().splitlines()[-1])
-    assert set(out["parts"]) == {"1", "2", "4"}
+    assert set(out["parts"]) == {"s1", "s3", "s8", "1", "2", "4"}
     for v in out["parts"].values():
         assert v["mismatches"] == 0 and v["env_errors"] == 0 and v["env_steps_per_s"] > 0
