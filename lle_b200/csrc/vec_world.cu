@@ -1288,7 +1288,8 @@ int lle_vec_parts_begin(lle_vec* v, int32_t n_parts, const int8_t* actions_host,
     if (!v || !actions_host) return fail(LLE_INVALID_ARGUMENT, "null argument");
     if (v->pipe_submitted != v->pipe_completed || v->parts_n) return fail(LLE_INVALID_ARGUMENT, "pipelined steps outstanding: drain with lle_vec_pipeline_wait (or close the parts loop with lle_vec_parts_end) first");
     if (v->shadow) return fail(LLE_INVALID_ARGUMENT, "lle_vec_parts_*: not with a state_type observation (its second pass is ordered by whole launches)");
-    const int64_t tickets = v->N_pad / v->group;
+    // parts are cut over the tickets that hold real envs; the padding tickets behind N (N_pad is a multiple of 32) join the last part
+    const int64_t tickets = (v->N + v->group - 1) / v->group;
     if (n_parts < 1 || n_parts > 1024 || n_parts > tickets) return fail(LLE_INVALID_ARGUMENT, "n_parts must be in 1..min(1024, tickets of the batch)");
     LLE_CUDA(cudaSetDevice(v->device));
     if (int rc = pipeline_setup(v)) return rc;
@@ -1339,7 +1340,7 @@ int lle_vec_parts_range(lle_vec* v, int32_t part, int64_t* first_env, int64_t* n
     if (!v || !first_env || !n_envs) return fail(LLE_INVALID_ARGUMENT, "null argument");
     if (!v->parts_n || part < 0 || part >= v->parts_n) return fail(LLE_INDEX_ERROR, "no such part (or no parts loop open)");
     const int64_t lo = (int64_t)part * v->parts_tpp * v->group;
-    const int64_t hi = std::min<int64_t>(v->N, lo + (int64_t)v->parts_tpp * v->group);
+    const int64_t hi = part == v->parts_n - 1 ? v->N : std::min<int64_t>(v->N, lo + (int64_t)v->parts_tpp * v->group);
     *first_env = lo;
     *n_envs = hi - lo;
     return LLE_OK;
@@ -1361,6 +1362,7 @@ int lle_vec_parts_launch(lle_vec* v) {
     p.part_out = v->d_part_out;
     p.part_count = v->d_part_count;
     p.part_tickets = v->parts_tpp;
+    p.part_last = (uint32_t)(v->parts_n - 1);
     p.in_need = p.out_value = (uint32_t)(v->parts_launched + 1);
     LLE_CUDA(launch(v, p, v->s_main));
     v->launches++;

@@ -140,7 +140,7 @@ struct KParams {
     const uint32_t* part_in;
     uint32_t* part_out;
     uint32_t* part_count;  // device counters: tickets of the part completed in this step
-    uint32_t part_tickets, pad_part;
+    uint32_t part_tickets, part_last;  // tickets per part; index of the last part, which also takes the padding tickets behind N
     uint32_t* out_flag;
     float* reward2;
     uint8_t* done2;
@@ -673,10 +673,10 @@ __device__ __forceinline__ bool ticket_ready(const uint32_t* flag, uint32_t need
 // their order), the last warp acquires the counts, fences at system scope and writes the part's completion word.  The counter
 // is cleared for the next step, whose tickets of this part cannot complete before the host has seen this word and fed the part
 // again.  Out of line: only the parts loop gets here.
-__device__ __noinline__ void part_ticket_done(uint32_t* part_count, uint32_t* part_out, uint32_t part_tickets, uint32_t n_tickets, uint32_t ticket,
-                                              uint32_t value) {
-    const uint32_t part = ticket / part_tickets, first = part * part_tickets;
-    const uint32_t n = min(part_tickets, n_tickets - first);
+__device__ __noinline__ void part_ticket_done(uint32_t* part_count, uint32_t* part_out, uint32_t part_tickets, uint32_t part_last, uint32_t n_tickets,
+                                              uint32_t ticket, uint32_t value) {
+    const uint32_t part = min(ticket / part_tickets, part_last);
+    const uint32_t n = part == part_last ? n_tickets - part_last * part_tickets : part_tickets;
     uint32_t before;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(before) : "l"(part_count + part) : "memory");
     if (before == n - 1u) {
@@ -688,18 +688,18 @@ __device__ __noinline__ void part_ticket_done(uint32_t* part_count, uint32_t* pa
 template <bool PARTS>
 __device__ __forceinline__ void ticket_done(const KParams& p, uint32_t ticket, uint32_t seq) {
     ticket_release(p.flags + ticket, seq);
-    if constexpr (PARTS) part_ticket_done(p.part_count, p.part_out, p.part_tickets, p.n_tickets, ticket, p.out_value);
+    if constexpr (PARTS) part_ticket_done(p.part_count, p.part_out, p.part_tickets, p.part_last, p.n_tickets, ticket, p.out_value);
 }
 // The tickets of a part wait for the host's actions (lle_vec_parts_feed).  `fed_upto` (lane 0's register): tickets below it are
 // known to be fed - a warp takes tickets in increasing order, so it looks at a part's word once.  Always true outside that mode.
 template <bool PARTS>
 __device__ __forceinline__ bool part_fed(const KParams& p, uint32_t ticket, uint32_t& fed_upto) {
     if (!PARTS || ticket < fed_upto) return true;
-    const uint32_t part = ticket / p.part_tickets;
+    const uint32_t part = min(ticket / p.part_tickets, p.part_last);
     // gpu scope: the word and the staged actions are written into device memory (L2) by the copy / front-end engines; a
     // system-scope acquire or fence here costs microseconds per use (measured: 97 -> 127 us per step with one fence.sys per part)
     if (!ticket_ready(p.part_in + part * 32, p.in_need)) return false;
-    fed_upto = (part + 1u) * p.part_tickets;
+    fed_upto = part == p.part_last ? p.n_tickets : (part + 1u) * p.part_tickets;
     return true;
 }
 // a host-supplied action; in a parts loop the staging buffer is rewritten by the copy engine while kernels run: through L2 only

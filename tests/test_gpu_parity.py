@@ -467,7 +467,8 @@ def _parts_rollout(ora, dev, n_parts, steps, ahead=2):
     return act, rew, done
 
 
-@pytest.mark.parametrize("n_parts,n,level,ahead", [(1, 100, 5, 1), (3, 1000, 6, 2), (8, 4096, 6, 2), (5, 333, 3, 3), (16, 2100, 6, 4)])
+@pytest.mark.parametrize("n_parts,n,level,ahead", [(1, 100, 5, 1), (3, 1000, 6, 2), (8, 4096, 6, 2), (5, 333, 3, 3), (16, 2100, 6, 4),
+                                                   (50, 1000, 6, 2), (13, 100, 6, 2), (125, 1000, 6, 3)])  # the last three: padding tickets behind N
 def test_parts_loop_equals_the_oracle(n_parts, n, level, ahead):
     """lle_vec_parts_*: one launch per step of the whole batch, the host feeding actions and reading reward / done part by part;
     every part's host results at every step and the final device buffers equal the oracle's."""
