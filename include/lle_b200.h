@@ -321,7 +321,7 @@ LLE_API int lle_vec_pipeline_wait(lle_vec* vec, int32_t* outstanding);
  * (python/lle/env/env.py:165-189) over a vector of envs whose policy runs on the host between steps.  `after_stream`: as for
  * lle_vec_pipeline_submit. */
 LLE_API int lle_vec_parts_begin(lle_vec* vec, int32_t n_parts, const int8_t* actions_host, float* reward_host, uint8_t* done_host, void* after_stream);
-LLE_API int lle_vec_parts_count(lle_vec* vec, int32_t* n_parts);  /* the number of parts actually formed (<= the number asked for) */
+LLE_API int lle_vec_parts_count(lle_vec* vec, int32_t* n_parts);  /* the number of parts actually formed: <= the number asked for (1..1024), at least one ticket (8-32 envs) each */
 LLE_API int lle_vec_parts_range(lle_vec* vec, int32_t part, int64_t* first_env, int64_t* n_envs);
 LLE_API int lle_vec_parts_launch(lle_vec* vec);
 LLE_API int lle_vec_parts_feed(lle_vec* vec, int32_t part);

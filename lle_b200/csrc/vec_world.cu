@@ -1290,7 +1290,8 @@ int lle_vec_parts_begin(lle_vec* v, int32_t n_parts, const int8_t* actions_host,
     if (v->shadow) return fail(LLE_INVALID_ARGUMENT, "lle_vec_parts_*: not with a state_type observation (its second pass is ordered by whole launches)");
     // parts are cut over the tickets that hold real envs; the padding tickets behind N (N_pad is a multiple of 32) join the last part
     const int64_t tickets = (v->N + v->group - 1) / v->group;
-    if (n_parts < 1 || n_parts > 1024 || n_parts > tickets) return fail(LLE_INVALID_ARGUMENT, "n_parts must be in 1..min(1024, tickets of the batch)");
+    if (n_parts < 1 || n_parts > 1024) return fail(LLE_INVALID_ARGUMENT, "n_parts must be in 1..1024");
+    n_parts = (int32_t)std::min<int64_t>(n_parts, tickets);  // at least one ticket per part: fewer parts than asked for (lle_vec_parts_count)
     LLE_CUDA(cudaSetDevice(v->device));
     if (int rc = pipeline_setup(v)) return rc;
     void* a = device_view(v, actions_host);

@@ -501,6 +501,22 @@ def test_parts_loop_other_kernels_and_options():
     assert_same(dev, ora, dev.pull(), "partial observations")
 
 
+def test_parts_loop_random_configurations():
+    """Seeded sweep over batch sizes (ragged, down to one env), part counts (up to one ticket per part; fewer parts are formed when
+    there are more parts than tickets), launch depths, levels, reward shapes and observation types."""
+    rng = np.random.default_rng(20261019)
+    for case in range(36):
+        level = int(rng.integers(1, 7))
+        n = int(rng.choice([1, 7, 31, 32, 33, 100, 257, 1000, 1999, 3000]))
+        n_parts = int(rng.choice([1, 2, 3, 5, 8, 13, 32, 64, 200]))
+        ahead = int(rng.integers(1, 5))
+        kw = dict(seed=500 + case, reward_dim=int(rng.choice([1, 4])), auto_reset=bool(rng.integers(0, 2)),
+                  obs_type=str(rng.choice(["layered", "layered", "partial3x3", "partial7x7", "perspective", "state"])))
+        ora, dev = make_pair([level_text(level)], None, n, **kw)
+        _parts_rollout(ora, dev, n_parts, 24, ahead)  # more parts than tickets: fewer parts are formed
+        assert_same(dev, ora, dev.pull(), f"case {case}: level {level}, {n} envs, {n_parts} parts, depth {ahead}, {kw}")
+
+
 def test_parts_loop_errors_and_abort():
     import lle_b200
 
@@ -513,6 +529,8 @@ def test_parts_loop_errors_and_abort():
         vec.parts_loop(4, torch.zeros((n, A), dtype=torch.int8), rew, done)  # not pinned
     with pytest.raises(ValueError):
         vec.parts_loop(0, act, rew, done)
+    with pytest.raises(ValueError):
+        vec.parts_loop(5000, act, rew, done)
     loop = vec.parts_loop(4, act, rew, done)
     with pytest.raises(ValueError):
         loop.wait(0)  # nothing fed
